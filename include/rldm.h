@@ -1,0 +1,145 @@
+/* rldm.h -- C ABI of librldm.so, the sm_100a kernel library behind rangeldm_b200.
+ *
+ * Drop-in boundary.  The reference (WoodwindHu/RangeLDM) has no FFI of its own: its hot path is
+ * Python calling third-party `diffusers` modules.  These entry points are what the
+ * replacement classes (`rangeldm_b200.UNet2DModel`, `AutoencoderKL`, the schedulers and the
+ * pipelines) bind through ctypes; each cites the reference arithmetic it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer borrowed from a live torch.Tensor for the duration of the
+ *    call; nothing is allocated, freed or synchronised inside a call;
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all launches are
+ *    stream-ordered and CUDA-graph capturable;
+ *  - return value 0 = success, non-zero = error; `rldm_last_error()` returns a thread-local,
+ *    NUL-terminated description of the last failure;
+ *  - "cl" (channels-last) activations are (B, W, H, C) row-major: C contiguous, then H (beams,
+ *    zero padded), then W (azimuth, CIRCULAR), then B.  The reference layout "ref" is
+ *    (B, C, W, H) (`ldm/dataset.py:230,330`);
+ *  - half = IEEE fp16 (uint16_t storage).  Convolutions multiply fp16 operands on tcgen05 tensor
+ *    cores and accumulate in fp32 (TMEM); everything else is fp32.
+ */
+#ifndef RLDM_H_
+#define RLDM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLDM_VERSION 100
+
+int rldm_version(void);
+const char* rldm_last_error(void);
+
+/* ---- GroupNorm statistics ------------------------------------------------------------------
+ * Replaces the reduction half of F.group_norm in ResnetBlock2D.norm1/norm2, Attention.group_norm,
+ * conv_norm_out (diffusers) == `Normalize` (`vae/sgm/.../model.py:59-62`).
+ * x0:(B,P,C0) [+ x1:(B,P,C1), a virtual channel concat == torch.cat([h, skip], 1)] fp32 cl.
+ * Accumulates (sum, sum of squares) per (b, group) into `sums`[B][G][2] (double), which the caller
+ * must have zeroed.  G groups over C0+C1 channels. */
+int rldm_gn_stats(const float* x0, int c0, const float* x1, int c1, double* sums,
+                  int B, int P, int G, void* stream);
+
+/* ---- prep: (GroupNorm-apply) (+SiLU) (+concat) (+nearest 2x upsample) -> fp16 cl -----------
+ * Replaces F.group_norm's normalise half + F.silu (`model.py:343-345,351-352`), torch.cat of the
+ * skip connection (UpBlock2D) and F.interpolate(scale_factor=2, "nearest") (`model.py:121-122`).
+ * x0:(B,W,H,C0) [+x1:(B,W,H,C1)] fp32 cl.  sums==NULL -> no normalisation (raw cast).
+ * out:(B,W*up,H*up,C0+C1) fp16 cl, up in {1,2}. */
+int rldm_prep(const float* x0, int c0, const float* x1, int c1, const double* sums,
+              const float* gamma, const float* beta, float eps, int G, int silu, int up,
+              uint16_t* out, int B, int W, int H, void* stream);
+
+/* ---- the hot op: circular implicit-GEMM convolution on tcgen05 ------------------------------
+ * Replaces `Conv2d._conv_forward` (`ldm/utils.py:40-58`, twin `vae/sgm/.../model.py:93-108`):
+ * wrap-pad W, zero-pad H, F.conv2d(pad 0); and the nn.Linear projections of Attention (ks=1).
+ *   x   : (B, W, H, Cin) fp16 cl, Cin % 64 == 0
+ *   wgt : [ks*ks][Cout][Cin] fp16, tap = kw_index_along_W * ks + k_index_along_H
+ *         (torch weight (Cout,Cin,kh,kw): kh <-> W, kw <-> H)
+ *   out : (B, Wo, Ho, Cout) fp32 cl;  Wo = W/stride, Ho = H/stride
+ *   pad_lo: taps read input (stride*wo + i - pad_lo) mod W, stride*ho + j - pad_lo (0 outside H).
+ *         ks=3,pad_lo=1: the symmetric circular conv; ks=3,stride=2,pad_lo=0: the VAE-encoder
+ *         Downsample2D(padding=0) asymmetric pad (`ldm/utils.py:109-111`).
+ *   circular: 1 = wrap on W (every shipped config, `all_circonv: True`); 0 = zero pad on W too.
+ *   epilogue: out = acc + bias[c] + temb[b*temb_stride + c] + residual[b,wo,ho,c] (NULL = skip)
+ *   split_k: 0 = choose automatically; > 1: the K loop (taps x channel chunks) is split over
+ *         split_k CTAs per tile which atomically accumulate into `out` (zeroed by this call);
+ *         `residual` must then not alias `out`.
+ * Requires Ho a power of two <= 128 and Cout % 64 == 0. */
+int rldm_conv_tc(const uint16_t* x, const uint16_t* wgt, const float* bias, const float* temb,
+                 int temb_stride, const float* residual, float* out, int B, int W, int H, int Cin,
+                 int Cout, int ks, int stride, int pad_lo, int circular, int split_k, void* stream);
+
+/* CUDA-core restatement of rldm_conv_tc with the identical contract (split_k ignored); used by the
+ * GPU tests to isolate tensor-core descriptor bugs from precision, never by the product path. */
+int rldm_conv_ref(const uint16_t* x, const uint16_t* wgt, const float* bias, const float* temb,
+                  int temb_stride, const float* residual, float* out, int B, int W, int H, int Cin,
+                  int Cout, int ks, int stride, int pad_lo, int circular, void* stream);
+
+/* ---- boundary convolutions with tiny channel counts (CUDA cores, fp32) ----------------------
+ * conv_in: x0 (B,C0,W,H) [+ x1 (B,C1,W,H)] fp32 REF layout, a virtual channel concat that replaces
+ * torch.cat([latents, pos_encoding | condition], 1) (`ldm/pipelines.py:238,358,498`)
+ * -> out (B,W,H,Cout) fp32 cl.  wgt [9][C0+C1][Cout] fp32. */
+int rldm_conv_in(const float* x0, int c0, const float* x1, int c1, const float* wgt,
+                 const float* bias, float* out, int B, int W, int H, int Cout, int circular,
+                 void* stream);
+/* conv_out: x (B,W,H,Cin) fp16 cl (already GN+SiLU'd by rldm_prep) -> out (B,Cout,W,H) fp32 REF
+ * layout, Cout <= 8.  wgt [9][Cout][Cin] fp32. */
+int rldm_conv_out(const uint16_t* x, const float* wgt, const float* bias, float* out, int B, int W,
+                  int H, int Cin, int Cout, int circular, void* stream);
+
+/* ---- attention core ----------------------------------------------------------------------
+ * Replaces F.scaled_dot_product_attention in AttnProcessor2_0: heads of
+ * dim 8, softmax(QK^T/sqrt(8))V, no mask.  qkv:(B,N,3C) fp32 (q|k|v along the last dim, head h at
+ * channels [8h,8h+8)); out:(B,N,C) fp16 (feeds the to_out projection). */
+int rldm_attention(const float* qkv, uint16_t* out, int B, int N, int C, void* stream);
+
+/* ---- time embedding -----------------------------------------------------------------------
+ * Replaces Timesteps + TimestepEmbedding + every ResnetBlock2D.time_emb_proj(silu(emb))
+ * (SURVEY.md App. A.1 steps 1 and ResnetBlock2D).  t:(B) fp32 timesteps.
+ * w1:[D4][D0] b1:[D4] w2:[D4][D4] b2:[D4]; wp:[T][D4] bp:[T] = all projections stacked row-wise.
+ * scratch:(B,D4) fp32; out:(B,T) fp32. */
+int rldm_temb(const float* t, const float* w1, const float* b1, const float* w2, const float* b2,
+              const float* wp, const float* bp, float* scratch, float* out, int B, int D0, int D4,
+              int T, void* stream);
+
+/* ---- fused scheduler step -----------------------------------------------------------------
+ * Replaces DDIMScheduler.step / DDPMScheduler.step / DPMSolverMultistepScheduler.step
+ * (call sites `ldm/pipelines.py:106,244-246,362,502`) with ONE kernel:
+ *    x0   = k[0]*x + k[1]*eps
+ *    xout = k[2]*x + k[3]*x0 + k[4]*x0_prev + k[5]*eps + k[6]*noise
+ * x0_prev / noise / x0_out may be NULL (their coefficient must then be 0).  k: 7 floats on the
+ * DEVICE (a row of the per-step coefficient table), so the step is graph-replayable. */
+int rldm_sched_step(const float* k, const float* x, const float* eps, const float* x0_prev,
+                    const float* noise, float* x_out, float* x0_out, int64_t n, void* stream);
+
+/* ---- layout helpers ----------------------------------------------------------------------- */
+int rldm_ref_to_cl(const float* src, float* dst, int B, int C, int W, int H, void* stream);
+int rldm_cl_to_ref(const float* src, float* dst, int B, int C, int W, int H, void* stream);
+
+/* ---- whole-forward programs ----------------------------------------------------------------
+ * A program is a flat array of rldm_op records built once by the host (all pointers resolved);
+ * rldm_run launches them back to back on `stream` with no host work in between.  This is what
+ * UNet2DModel.forward / AutoencoderKL.decode / the sampling loop execute. */
+enum {
+  RLDM_OP_GN_STATS = 1, RLDM_OP_PREP = 2, RLDM_OP_CONV_TC = 3, RLDM_OP_CONV_IN = 4,
+  RLDM_OP_CONV_OUT = 5, RLDM_OP_ATTENTION = 6, RLDM_OP_TEMB = 7, RLDM_OP_SCHED_STEP = 8,
+  RLDM_OP_MEMSET = 9, RLDM_OP_CONV_REF = 10, RLDM_OP_AXPY = 11
+};
+typedef struct rldm_op {
+  int32_t kind;
+  int32_t i[15];      /* integer arguments in the order of the matching entry point */
+  float f[2];         /* float arguments (eps) */
+  void* p[10];        /* pointer arguments in the order of the matching entry point */
+  int64_t n;          /* element / byte count where the entry point takes one */
+} rldm_op;
+int rldm_run(const rldm_op* ops, int n_ops, void* stream);
+
+/* y = a*x (elementwise, fp32), e.g. latents / scaling_factor (`ldm/pipelines.py:365`). */
+int rldm_scale(const float* x, float a, float* y, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLDM_H_ */

@@ -1,0 +1,192 @@
+"""Generate tests/golden/*.pt (TEST INFRASTRUCTURE ONLY; run in the build container where
+`/root/reference` exists):   python -m oracle.make_golden
+
+Every fixture is produced by the REFERENCE'S OWN CODE (imported read-only, oracle/refshim.py) on
+seeded inputs; weights are the oracle modules' default init under a fixed seed, so tests can
+rebuild them anywhere without the reference tree and without committing megabytes of weights.
+
+  vae_decoder.pt   reference sgm `Decoder.forward` (`vae/sgm/.../model.py:1024-1057`), ch=64, mult (1,2)
+  vae_encoder.pt   reference sgm `Encoder.forward` (`model.py:852-896`)
+  circ_conv.pt     reference circular `Conv2d` (`model.py:93-108`), stride 1 and 2
+  dpmpp2m.pt       reference `DPMPP2MSampler.sampler_step` trajectory (`sampling.py:290-345`) on a toy eps-model
+  ldm_pipeline.pt  reference `LDMPipelineRange.__call__` / `DDIMPipelineRange.__call__`
+                   (`ldm/pipelines.py:282-383,144-258`) driving the oracle nets through the diffusers shim
+  sparse_encoder2.pt reference `SparseRangeImageEncoder2.forward` (`ldm/encoders.py:86-95`)
+"""
+import importlib
+import os
+import sys
+import types
+
+import torch
+
+from . import nets, refshim, schedulers
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+TINY_VAE = dict(block_out_channels=[64, 128], layers_per_block=1)
+TINY_UNET = dict(sample_size=[32, 8], in_channels=5, out_channels=4, layers_per_block=1,
+                 block_out_channels=[64, 128], down_block_types=["DownBlock2D", "AttnDownBlock2D"],
+                 up_block_types=["AttnUpBlock2D", "UpBlock2D"])
+TINY_UNET_PIXEL = dict(TINY_UNET, in_channels=3, out_channels=2)
+
+
+def seeded(ctor, seed, **kw):
+    torch.manual_seed(seed)
+    return ctor(**kw).eval()
+
+
+def toy_eps_matrix():
+    g = torch.Generator().manual_seed(7)
+    return torch.randn(16, 16, generator=g) * 0.3
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    model, sampling, disc = refshim.load()
+    g = torch.Generator().manual_seed(11)
+
+    # ---- VAE decoder / encoder: reference classes with oracle-seeded weights
+    vae = seeded(nets.OracleAutoencoderKL, 1234, **TINY_VAE)
+    rd = refshim.make_decoder(model, ch=64, ch_mult=(1, 2), num_res_blocks=1)
+    rd.load_state_dict(nets.to_sgm_state_dict({k: v for k, v in vae.state_dict().items() if k.startswith("decoder.")},
+                                              nets.sgm_decoder_key_map(2, 1)), strict=True)
+    z = torch.randn(2, 4, 32, 8, generator=g)
+    with torch.no_grad():
+        torch.save({"z": z, "out": rd(z)}, os.path.join(OUT, "vae_decoder.pt"))
+    re_ = refshim.make_encoder(model, ch=64, ch_mult=(1, 2), num_res_blocks=1)
+    re_.load_state_dict(nets.to_sgm_state_dict({k: v for k, v in vae.state_dict().items() if k.startswith("encoder.")},
+                                               nets.sgm_encoder_key_map(2, 1)), strict=True)
+    x = torch.randn(2, 2, 64, 16, generator=g)
+    with torch.no_grad():
+        torch.save({"x": x, "out": re_(x)}, os.path.join(OUT, "vae_encoder.pt"))
+
+    # ---- circular conv
+    torch.manual_seed(5)
+    c1 = model.Conv2d(64, 64, 3, stride=1, padding=1, circular=True)
+    c2 = model.Conv2d(64, 128, 3, stride=2, padding=1, circular=True)
+    xc = torch.randn(1, 64, 16, 8, generator=g)
+    with torch.no_grad():
+        torch.save({"x": xc, "w1": c1.weight, "b1": c1.bias, "y1": c1(xc), "w2": c2.weight, "b2": c2.bias,
+                    "y2": c2(xc)}, os.path.join(OUT, "circ_conv.pt"))
+
+    # ---- DPM-Solver++(2M): the reference's in-tree sampler on a toy eps model
+    guiders = importlib.import_module("sgm.modules.diffusionmodules.guiders")
+    s = schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading")
+    s.set_timesteps(20)
+    Wm = toy_eps_matrix()
+    eps_model = lambda v: torch.tanh(v @ Wm)
+    x0 = torch.randn(4, 16, generator=g)
+    samp = sampling.DPMPP2MSampler.__new__(sampling.DPMPP2MSampler)
+    samp.guider = guiders.IdentityGuider()
+    sig = s.sigmas.double()
+    alpha = 1 / (sig ** 2 + 1).sqrt()
+    xv, old, ones = x0.double() / alpha[0], None, torch.ones(4, dtype=torch.double)
+    traj = []
+    for i in range(20):
+        den = lambda xin, sigma, c, a=alpha[i]: xin - sigma.view(-1, 1) * eps_model((xin * a).float()).double()
+        xv, old = samp.sampler_step(old, None if i == 0 else ones * sig[i - 1], ones * sig[i], ones * sig[i + 1],
+                                    den, xv, {}, None)
+        traj.append((xv * alpha[i + 1]).float())          # back to the VP parameterisation
+    torch.save({"x": x0, "traj": torch.stack(traj), "timesteps": s.timesteps.clone(), "sigmas": s.sigmas.clone()},
+               os.path.join(OUT, "dpmpp2m.pt"))
+
+    # ---- the reference's pipeline loops, driving oracle nets through a names-only diffusers shim
+    class _Out:
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+
+    class _Pipe:
+        def __init__(self):
+            self._mods = {}
+
+        def register_modules(self, **kw):
+            self._mods.update(kw)
+            self.__dict__.update(kw)
+
+        device = torch.device("cpu")
+        _execution_device = torch.device("cpu")
+
+        def progress_bar(self, it):
+            return it
+
+    class _Cfg(dict):
+        __getattr__ = dict.__getitem__
+
+    class UNetAdapter:
+        def __init__(self, net):
+            self.net, self.config, self.dtype, self.device = net, _Cfg(net.cfg), torch.float32, torch.device("cpu")
+
+        def __call__(self, x, t):
+            return _Out(sample=self.net(x, t))
+
+    class VaeAdapter:
+        def __init__(self, vae):
+            self.vae, self.config = vae, _Cfg(scaling_factor=vae.scaling_factor)
+
+        def decode(self, zz):
+            return _Out(sample=self.vae.decode(zz))
+
+    class SchedAdapter:
+        def __init__(self, sch):
+            self.s, self.config = sch, _Cfg()
+            self.init_noise_sigma = sch.init_noise_sigma
+
+        timesteps = property(lambda self: self.s.timesteps)
+
+        def set_timesteps(self, n):
+            self.s.set_timesteps(n)
+
+        def scale_model_input(self, xx, t):
+            return xx
+
+        def step(self, eps, t, xx, eta=0.0, use_clipped_model_output=None, generator=None):
+            if isinstance(self.s, schedulers.OracleDDIMScheduler):
+                return _Out(prev_sample=self.s.step(eps, t, xx, eta=eta))
+            return _Out(prev_sample=self.s.step(eps, t, xx))
+
+    def randn_tensor(shape, generator=None, device=None, dtype=None):
+        return torch.randn(shape, generator=generator, dtype=dtype)
+
+    class _DDIM:  # `DDIMScheduler.from_config(scheduler.config)` (`ldm/pipelines.py:139`) keeps our adapter
+        @staticmethod
+        def from_config(cfg):
+            return SchedAdapter(schedulers.OracleDDIMScheduler())
+
+    for name, attrs in (("diffusers", {}), ("diffusers.utils", {"randn_tensor": randn_tensor}),
+                        ("diffusers.pipelines", {}),
+                        ("diffusers.pipelines.pipeline_utils", {"DiffusionPipeline": _Pipe, "ImagePipelineOutput": _Out}),
+                        ("diffusers.schedulers", {"DDIMScheduler": _DDIM})):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        m.__path__ = []
+        sys.modules[name] = m
+    sys.path.insert(0, os.path.join(refshim.REF_ROOT, "ldm"))
+    refpipes = importlib.import_module("pipelines")          # the reference's ldm/pipelines.py, unchanged
+    enc = importlib.import_module("encoders") if False else None
+
+    unet = seeded(nets.OracleUNet2DModel, 4321, **TINY_UNET)
+    out = {}
+    for sched_name, sch in (("dpm", schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading")),
+                            ("ddim", schedulers.OracleDDIMScheduler())):
+        pipe = refpipes.LDMPipelineRange(VaeAdapter(vae), UNetAdapter(unet), SchedAdapter(sch), pos_encoding=True)
+        gen = torch.Generator().manual_seed(3)
+        out[f"ldm_{sched_name}"] = pipe(batch_size=2, generator=gen, num_inference_steps=5, output_type="torch")
+    upix = seeded(nets.OracleUNet2DModel, 4322, **TINY_UNET_PIXEL)
+    pipe = refpipes.DDIMPipelineRange(UNetAdapter(upix), SchedAdapter(schedulers.OracleDDIMScheduler()),
+                                      pos_encoding=True)
+    gen = torch.Generator().manual_seed(3)
+    out["pixel_ddim"] = pipe(batch_size=2, generator=gen, num_inference_steps=5, output_type="torch")
+    torch.save(out, os.path.join(OUT, "ldm_pipeline.pt"))
+
+    # ---- SparseRangeImageEncoder2: restated from ldm/encoders.py:86-95 (module needs sgm imports; use its body)
+    xs = torch.randn(2, 2, 16, 4, generator=g)
+    B, C, W, H = xs.shape
+    ys = torch.flatten(xs.permute(0, 2, 1, 3), start_dim=1, end_dim=2).reshape(B, W // 4, C * 4, H).permute(0, 2, 1, 3)
+    torch.save({"x": xs, "y": ys.contiguous()}, os.path.join(OUT, "sparse_encoder2.pt"))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

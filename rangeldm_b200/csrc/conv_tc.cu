@@ -1,0 +1,293 @@
+// conv_tc.cu -- horizontally-circular implicit-GEMM convolution on tcgen05 tensor cores.
+//
+// Replaces `Conv2d._conv_forward` (reference `ldm/utils.py:40-58`, twin
+// `vae/sgm/modules/diffusionmodules/model.py:93-108`): F.pad(circular, W) + F.pad(zeros, H) +
+// F.conv2d(pad 0) -- two materialised padded copies and a cuDNN call -- with one kernel:
+//
+//   D[m, n] = sum_{tap, c} A_tap[m, c] * Wt[tap][n][c]      m = output pixel, n = output channel
+//
+// * activations are channels-last fp16 (B, W, H, C); a 128-pixel M tile is 128/Ho whole azimuth
+//   columns.  For each (tap, 64-channel chunk) the producer warp issues one TMA box per column:
+//   the wrap on W is a modular column coordinate, the zero pad on H is TMA out-of-bounds fill, and
+//   stride 2 is the tensor map's element stride -- no padded copy ever exists;
+// * weights [tap][Cout][Cin] fp16 arrive by TMA as the K-major B operand;
+// * both land SWIZZLE_128B in a multi-stage mbarrier ring; one thread issues tcgen05.mma
+//   (M=128, N=BLOCK_N, K=16) accumulating fp32 in TMEM; tcgen05.commit frees the stage;
+// * 4 epilogue warps read TMEM (tcgen05.ld), add bias + time-embedding + residual and store fp32
+//   channels-last (or atomically accumulate when the K loop is split across CTAs).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace rldm {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // fp16 elements = one 128 B swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
+
+struct ConvParams {
+  const float* bias;
+  const float* temb;
+  const float* residual;
+  float* out;
+  int temb_stride;
+  int M_total;      // B*Wo*Ho
+  int Wo, Ho, W_in;
+  int pix_per_img;  // Wo*Ho
+  int Cout;
+  int ks, stride, pad_lo, circular;
+  int total_iters;  // (Cin/64) * ks*ks
+  int iters_per_split;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192, 2)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const ConvParams p) {
+  constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms need 1024 B alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBlockM;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int it0 = blockIdx.z * p.iters_per_split;
+  const int it1 = min(it0 + p.iters_per_split, p.total_iters);
+  const int n_it = it1 - it0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<BLOCK_N>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp: lanes share the column loads) =============
+    const int taps = p.ks * p.ks;
+    const int ncols = kBlockM / p.Ho;
+    const int q0 = m0 / p.Ho;
+    for (int i = 0; i < n_it; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      const int it = it0 + i;
+      const int chunk = it / taps;
+      const int tap = it - chunk * taps;
+      const int ti = tap / p.ks, tj = tap - ti * p.ks;
+      const uint32_t a_dst = smem_u32(smem + s * kStageBytes);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+        tma_load_2d(a_dst + kABytes, &tmB, &full_bar[s], chunk * kBlockK, tap * p.Cout + n0);
+      }
+      for (int c = lane; c < ncols; c += 32) {
+        const int q = q0 + c;
+        const int b = q / p.Wo;
+        const int wo = q - b * p.Wo;
+        int w_in = p.stride * wo + ti - p.pad_lo;
+        if (p.circular) {   // wrap on the azimuth axis; otherwise TMA out-of-bounds fill zero-pads
+          if (w_in < 0) w_in += p.W_in;
+          if (w_in >= p.W_in) w_in -= p.W_in;
+        }
+        tma_load_4d(a_dst + c * p.Ho * 128, &tmA, &full_bar[s], chunk * kBlockK, tj - p.pad_lo,
+                    w_in, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) ============================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BLOCK_N);
+      for (int i = 0; i < n_it; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+        const uint64_t a_desc = umma_desc_sw128(a_addr);
+        const uint64_t b_desc = umma_desc_sw128(a_addr + kABytes);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          // advancing K by 16 fp16 = 32 B inside the 128 B swizzle row: +2 in the (addr>>4) field
+          umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (i | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global ==============================
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const bool valid = m < p.M_total;
+    const bool lead = blockIdx.z == 0;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int b = valid ? m / p.pix_per_img : 0;
+    float* out_row = p.out + static_cast<size_t>(m) * p.Cout + n0;
+    const float* res_row = p.residual ? p.residual + static_cast<size_t>(m) * p.Cout + n0 : nullptr;
+    const float* temb_row = p.temb ? p.temb + static_cast<size_t>(b) * p.temb_stride + n0 : nullptr;
+    const float* bias_row = p.bias ? p.bias + n0 : nullptr;
+#pragma unroll 1
+    for (int nc = 0; nc < BLOCK_N / 32; ++nc) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + nc * 32, r);
+      tmem_ld_wait();
+      if (valid) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (lead) {
+          if (bias_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(bias_row + nc * 32 + j);
+          }
+          if (temb_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(temb_row + nc * 32 + j);
+          }
+          if (res_row) {
+            const float4* r4 = reinterpret_cast<const float4*>(res_row + nc * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = __ldg(r4 + j);
+              v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            }
+          }
+        }
+        if (gridDim.z == 1) {
+          float4* o4 = reinterpret_cast<float4*>(out_row + nc * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(out_row + nc * 32 + j, v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BLOCK_N>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p,
+                       int split, cudaStream_t st) {
+  constexpr int smem = STAGES * (kABytes + BLOCK_N * kBlockK * 2) + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid((p.M_total + kBlockM - 1) / kBlockM, p.Cout / BLOCK_N, split);
+  conv_tc_kernel<BLOCK_N, STAGES><<<grid, 192, smem, st>>>(tmA, tmB, p);
+  RLDM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace rldm
+
+using namespace rldm;
+
+extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* wgt, const float* bias,
+                            const float* temb, int temb_stride, const float* residual, float* out,
+                            int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
+                            int circular, int split_k, void* stream) {
+  RLDM_CHECK(ks == 1 || ks == 3, "conv_tc: ks must be 1 or 3 (got %d)", ks);
+  RLDM_CHECK(stride == 1 || stride == 2, "conv_tc: stride must be 1 or 2 (got %d)", stride);
+  RLDM_CHECK(Cin % 64 == 0, "conv_tc: Cin %% 64 != 0 (got %d)", Cin);
+  RLDM_CHECK(Cout % 64 == 0, "conv_tc: Cout %% 64 != 0 (got %d)", Cout);
+  RLDM_CHECK(W % stride == 0 && H % stride == 0, "conv_tc: W,H must divide by stride");
+  const int Wo = W / stride, Ho = H / stride;
+  RLDM_CHECK(Ho >= 1 && Ho <= 128 && (Ho & (Ho - 1)) == 0, "conv_tc: Ho must be a power of two <= 128 (got %d)", Ho);
+  RLDM_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wgt) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(out) & 15) == 0, "conv_tc: pointers must be 16 B aligned");
+  EncodeTiledFn encode = get_encode();
+  RLDM_CHECK(encode != nullptr, "conv_tc: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+
+  const int BN = (Cout % 128 == 0) ? 128 : 64;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)H, (cuuint64_t)W, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)H * Cin * 2, (cuuint64_t)W * H * Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(Ho * stride), 1, 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, 1, 1};
+    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<uint16_t*>(x), gdim, gstr,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+  }
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)Cin, (cuuint64_t)ks * ks * Cout};
+    cuuint64_t gstr[1] = {(cuuint64_t)Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(wgt), gdim, gstr,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+  }
+  ConvParams p;
+  p.bias = bias; p.temb = temb; p.residual = residual; p.out = out;
+  p.temb_stride = temb_stride;
+  p.M_total = B * Wo * Ho;
+  p.Wo = Wo; p.Ho = Ho; p.W_in = W;
+  p.pix_per_img = Wo * Ho;
+  p.Cout = Cout;
+  p.ks = ks; p.stride = stride; p.pad_lo = pad_lo; p.circular = circular;
+  p.total_iters = (Cin / kBlockK) * ks * ks;
+  const int tiles = ((p.M_total + kBlockM - 1) / kBlockM) * (Cout / BN);
+  int split = split_k;
+  if (split <= 0) {  // auto: fill the 148 SMs (2 CTAs each) when the tile grid is small
+    split = 1;
+    while (tiles * split * 2 <= 296 && p.total_iters / (split * 2) >= 4 && split < 16) split *= 2;
+  }
+  if (split > p.total_iters) split = p.total_iters;
+  p.iters_per_split = (p.total_iters + split - 1) / split;
+  split = (p.total_iters + p.iters_per_split - 1) / p.iters_per_split;
+  cudaStream_t st = as_stream(stream);
+  if (split > 1)
+    RLDM_CUDA(cudaMemsetAsync(out, 0, static_cast<size_t>(p.M_total) * Cout * sizeof(float), st));
+  if (BN == 128) return launch_conv<128, 3>(tmA, tmB, p, split, st);
+  return launch_conv<64, 4>(tmA, tmB, p, split, st);
+}

@@ -1,0 +1,679 @@
+// ops.cu -- the HBM/L2-bound kernels around the tensor-core convolution: GroupNorm statistics,
+// the fused normalise+SiLU+concat+upsample+cast "prep", boundary convolutions, attention core,
+// time embedding, the fused scheduler step, and the program runner.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace rldm {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics.  grid (chunks, B), block 256.  Thread = one float4 of channels, striding
+// over the pixels of its chunk; per-channel partials are folded to per-group doubles in shared
+// memory and leave the block as one atomicAdd(double) per (group, moment).
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
+                double* __restrict__ sums, int P, int G, int pix_per_block) {
+  extern __shared__ double sh[];  // [2][G]
+  const int C = c0 + c1;
+  const int q_per_pix = C >> 2;                 // float4 quads per pixel
+  const int b = blockIdx.y;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(p_begin + pix_per_block, P);
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.0;
+  __syncthreads();
+  const int cpg = C / G;
+  // each thread owns quad (threadIdx.x % q_per_pix) when blockDim is a multiple of q_per_pix;
+  // otherwise it walks quads generically.
+  const int total_q = (p_end - p_begin) * q_per_pix;
+  if (blockDim.x % q_per_pix == 0) {
+    const int quad = threadIdx.x % q_per_pix;
+    const int c = quad << 2;
+    float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+    for (int p = p_begin + threadIdx.x / q_per_pix; p < p_end; p += blockDim.x / q_per_pix) {
+      const size_t pix = static_cast<size_t>(b) * P + p;
+      const float4 v = (c < c0) ? __ldg(reinterpret_cast<const float4*>(x0 + pix * c0 + c))
+                                : __ldg(reinterpret_cast<const float4*>(x1 + pix * c1 + (c - c0)));
+      s[0] += v.x; ss[0] += v.x * v.x;
+      s[1] += v.y; ss[1] += v.y * v.y;
+      s[2] += v.z; ss[2] += v.z * v.z;
+      s[3] += v.w; ss[3] += v.w * v.w;
+    }
+    if (cpg >= 4) {
+      atomicAdd(&sh[c / cpg], (double)s[0] + (double)s[1] + (double)s[2] + (double)s[3]);
+      atomicAdd(&sh[G + c / cpg], (double)ss[0] + (double)ss[1] + (double)ss[2] + (double)ss[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&sh[(c + j) / cpg], (double)s[j]);
+        atomicAdd(&sh[G + (c + j) / cpg], (double)ss[j]);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < total_q; i += blockDim.x) {
+      const int p = p_begin + i / q_per_pix;
+      const int c = (i % q_per_pix) << 2;
+      const size_t pix = static_cast<size_t>(b) * P + p;
+      const float4 v = (c < c0) ? __ldg(reinterpret_cast<const float4*>(x0 + pix * c0 + c))
+                                : __ldg(reinterpret_cast<const float4*>(x1 + pix * c1 + (c - c0)));
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&sh[(c + j) / cpg], (double)vv[j]);
+        atomicAdd(&sh[G + (c + j) / cpg], (double)vv[j] * vv[j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) {
+    const int g = i % G, mom = i / G;
+    atomicAdd(&sums[(static_cast<size_t>(b) * G + g) * 2 + mom], sh[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep: y = [silu]([gn](concat(x0,x1))) cast to fp16, optionally nearest-2x upsampled.
+// grid (ceil(outpix/pix_per_block), B), block 256.  Thread = 8 channels of one OUTPUT pixel
+// (two float4 loads, one 16 B store).
+__global__ void __launch_bounds__(256)
+prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
+            const double* __restrict__ sums, const float* __restrict__ gamma,
+            const float* __restrict__ beta, float eps, int G, int silu, int up,
+            __half* __restrict__ out, int W, int H, int pix_per_block) {
+  extern __shared__ float shf[];  // scale[C], shift[C]
+  const int C = c0 + c1;
+  const int b = blockIdx.y;
+  float* sc = shf;
+  float* sf = shf + C;
+  if (sums) {
+    const int cpg = C / G;
+    const double inv_n = 1.0 / (static_cast<double>(W) * H * cpg);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g = c / cpg;
+      const double s = sums[(static_cast<size_t>(b) * G + g) * 2];
+      const double ss = sums[(static_cast<size_t>(b) * G + g) * 2 + 1];
+      const double mean = s * inv_n;
+      double var = ss * inv_n - mean * mean;
+      if (var < 0) var = 0;
+      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      const float a = rstd * gamma[c];
+      sc[c] = a;
+      sf[c] = beta[c] - static_cast<float>(mean) * a;
+    }
+    __syncthreads();
+  }
+  const int Wo = W * up, Ho = H * up;
+  const int oct_per_pix = C >> 3;
+  const int out_pix = Wo * Ho;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(p_begin + pix_per_block, out_pix);
+  const int total = (p_end - p_begin) * oct_per_pix;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int po = p_begin + i / oct_per_pix;
+    const int c = (i % oct_per_pix) << 3;
+    int pin = po;
+    if (up == 2) {
+      const int wo = po / Ho, ho = po - wo * Ho;
+      pin = (wo >> 1) * H + (ho >> 1);
+    }
+    const size_t pix = static_cast<size_t>(b) * W * H + pin;
+    const float* src = (c < c0) ? x0 + pix * c0 + c : x1 + pix * c1 + (c - c0);
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    if (sums) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[c + j], sf[c + j]);
+    }
+    if (silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+    }
+    __align__(16) __half2 h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * out_pix + po) * C + c) =
+        *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_ref: one thread per (output pixel, output channel); same contract as conv_tc.
+__global__ void conv_ref_kernel(const __half* __restrict__ x, const __half* __restrict__ wgt,
+                                const float* __restrict__ bias, const float* __restrict__ temb,
+                                int temb_stride, const float* __restrict__ residual,
+                                float* __restrict__ out, int B, int W, int H, int Cin, int Cout,
+                                int ks, int stride, int pad_lo, int circular) {
+  const int Wo = W / stride, Ho = H / stride;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(B) * Wo * Ho * Cout;
+  if (idx >= total) return;
+  const int n = idx % Cout;
+  const size_t m = idx / Cout;
+  const int ho = m % Ho;
+  const int wo = (m / Ho) % Wo;
+  const int b = m / (static_cast<size_t>(Ho) * Wo);
+  float acc = 0.f;
+  for (int i = 0; i < ks; ++i) {
+    int w = stride * wo + i - pad_lo;
+    if (circular) w = ((w % W) + W) % W;
+    else if (w < 0 || w >= W) continue;
+    for (int j = 0; j < ks; ++j) {
+      const int h = stride * ho + j - pad_lo;
+      if (h < 0 || h >= H) continue;
+      const __half* xr = x + ((static_cast<size_t>(b) * W + w) * H + h) * Cin;
+      const __half* wr = wgt + (static_cast<size_t>(i * ks + j) * Cout + n) * Cin;
+      for (int c = 0; c < Cin; c += 2) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(xr + c));
+        const float2 w2 = __half22float2(*reinterpret_cast<const __half2*>(wr + c));
+        acc = fmaf(a.x, w2.x, acc);
+        acc = fmaf(a.y, w2.y, acc);
+      }
+    }
+  }
+  if (bias) acc += bias[n];
+  if (temb) acc += temb[static_cast<size_t>(b) * temb_stride + n];
+  if (residual) acc += residual[idx];
+  out[idx] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_in: (B,Cin,W,H) fp32 ref layout -> (B,W,H,Cout) fp32 cl, 3x3 circular/zero, Cin <= 16.
+// block 256 = (256/(Cout/4)) pixels x (Cout/4) channel quads; grid covers all pixels.
+__global__ void __launch_bounds__(256)
+conv_in_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
+               const float* __restrict__ wgt, const float* __restrict__ bias,
+               float* __restrict__ out, int B, int W, int H, int Cout, int circular,
+               int pix_per_block) {
+  const int Cin = c0 + c1;
+  const int q_per_pix = Cout >> 2;
+  const int lanes_pix = blockDim.x / q_per_pix;
+  const int quad = threadIdx.x % q_per_pix;
+  const int co = quad << 2;
+  const size_t total_pix = static_cast<size_t>(B) * W * H;
+  const size_t p_begin = static_cast<size_t>(blockIdx.x) * pix_per_block;
+  const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + co)) : make_float4(0, 0, 0, 0);
+  for (size_t pp = p_begin + threadIdx.x / q_per_pix; pp < min(p_begin + pix_per_block, total_pix);
+       pp += lanes_pix) {
+    const int h = pp % H;
+    const int w = (pp / H) % W;
+    const int b = pp / (static_cast<size_t>(H) * W);
+    float4 acc = bv;
+    for (int i = 0; i < 3; ++i) {
+      int wi = w + i - 1;
+      if (circular) {
+        if (wi < 0) wi += W;
+        if (wi >= W) wi -= W;
+      } else if (wi < 0 || wi >= W) continue;
+      for (int j = 0; j < 3; ++j) {
+        const int hj = h + j - 1;
+        if (hj < 0 || hj >= H) continue;
+        for (int c = 0; c < Cin; ++c) {
+          const float a = (c < c0) ? __ldg(x0 + ((static_cast<size_t>(b) * c0 + c) * W + wi) * H + hj)
+                                   : __ldg(x1 + ((static_cast<size_t>(b) * c1 + (c - c0)) * W + wi) * H + hj);
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(
+              wgt + (static_cast<size_t>(i * 3 + j) * Cin + c) * Cout + co));
+          acc.x = fmaf(a, wv.x, acc.x);
+          acc.y = fmaf(a, wv.y, acc.y);
+          acc.z = fmaf(a, wv.z, acc.z);
+          acc.w = fmaf(a, wv.w, acc.w);
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(out + pp * Cout + co) = acc;
+  }
+}
+
+// conv_out: (B,W,H,Cin) fp16 cl -> (B,Cout,W,H) fp32 ref layout, Cout <= 8.  One warp per pixel:
+// lanes split the input channels, butterfly-reduce the Cout partial sums.
+template <int COUT>
+__global__ void __launch_bounds__(256)
+conv_out_kernel(const __half* __restrict__ x, const float* __restrict__ wgt,
+                const float* __restrict__ bias, float* __restrict__ out, int B, int W, int H,
+                int Cin, int circular) {
+  const int lane = threadIdx.x & 31;
+  const size_t pp = static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t total_pix = static_cast<size_t>(B) * W * H;
+  if (pp >= total_pix) return;
+  const int h = pp % H;
+  const int w = (pp / H) % W;
+  const int b = pp / (static_cast<size_t>(H) * W);
+  float acc[COUT];
+#pragma unroll
+  for (int n = 0; n < COUT; ++n) acc[n] = 0.f;
+  for (int i = 0; i < 3; ++i) {
+    int wi = w + i - 1;
+    if (circular) {
+      if (wi < 0) wi += W;
+      if (wi >= W) wi -= W;
+    } else if (wi < 0 || wi >= W) continue;
+    for (int j = 0; j < 3; ++j) {
+      const int hj = h + j - 1;
+      if (hj < 0 || hj >= H) continue;
+      const __half* xr = x + ((static_cast<size_t>(b) * W + wi) * H + hj) * Cin;
+      const float* wr = wgt + static_cast<size_t>(i * 3 + j) * COUT * Cin;
+      for (int c = lane * 2; c < Cin; c += 64) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(xr + c));
+#pragma unroll
+        for (int n = 0; n < COUT; ++n) {
+          const float2 wv = __ldg(reinterpret_cast<const float2*>(wr + n * Cin + c));
+          acc[n] = fmaf(a.x, wv.x, acc[n]);
+          acc[n] = fmaf(a.y, wv.y, acc[n]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < COUT; ++n) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+  }
+  if (lane < COUT) {
+    float v = 0.f;
+#pragma unroll
+    for (int n = 0; n < COUT; ++n)
+      if (lane == n) v = acc[n];
+    out[((static_cast<size_t>(b) * COUT + lane) * W + w) * H + h] = v + (bias ? bias[lane] : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention core, head_dim 8.  grid (ceil(N/128), C/8, B), block 128: thread = one query.
+// K and V of the (b, head) are staged in shared memory in tiles of KT keys; every thread scans
+// them with broadcast reads (two passes per tile are avoided by an online softmax).
+constexpr int kAttnKT = 512;
+__global__ void __launch_bounds__(128)
+attention_kernel(const float* __restrict__ qkv, __half* __restrict__ out, int N, int C) {
+  __shared__ float4 sk[kAttnKT * 2 + 16];
+  __shared__ float4 sv[kAttnKT * 2 + 16];
+  const int b = blockIdx.z, hd = blockIdx.y;
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t row = 3 * static_cast<size_t>(C);
+  const float* base = qkv + static_cast<size_t>(b) * N * row + hd * 8;
+  // fold softmax scale 1/sqrt(8) and log2(e) into q so the inner loop is one FFMA chain + ex2
+  const float qs = 0.35355339059327373f * 1.4426950408889634f;
+  float q[8];
+  {
+    const int qq = min(qi, N - 1);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(base + qq * row));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(base + qq * row) + 1);
+    q[0] = a.x * qs; q[1] = a.y * qs; q[2] = a.z * qs; q[3] = a.w * qs;
+    q[4] = c.x * qs; q[5] = c.y * qs; q[6] = c.z * qs; q[7] = c.w * qs;
+  }
+  float mx = -INFINITY, l = 0.f;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k0 = 0; k0 < N; k0 += kAttnKT) {
+    const int kt = min(kAttnKT, N - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ((kt + 7) & ~7) * 2; i += blockDim.x) {
+      const int kk = k0 + (i >> 1);
+      const bool in = (i >> 1) < kt;   // pad the tile to a multiple of 8 keys with zeros (masked below)
+      sk[i] = in ? __ldg(reinterpret_cast<const float4*>(base + kk * row + C) + (i & 1)) : make_float4(0, 0, 0, 0);
+      sv[i] = in ? __ldg(reinterpret_cast<const float4*>(base + kk * row + 2 * C) + (i & 1)) : make_float4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    for (int j0 = 0; j0 < kt; j0 += 8) {
+      float s[8];
+      float cmx = mx;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 ka = sk[2 * (j0 + j)], kb = sk[2 * (j0 + j) + 1];
+        float t = q[0] * ka.x;
+        t = fmaf(q[1], ka.y, t); t = fmaf(q[2], ka.z, t); t = fmaf(q[3], ka.w, t);
+        t = fmaf(q[4], kb.x, t); t = fmaf(q[5], kb.y, t); t = fmaf(q[6], kb.z, t);
+        t = fmaf(q[7], kb.w, t);
+        s[j] = (j0 + j < kt) ? t : -INFINITY;
+        cmx = fmaxf(cmx, s[j]);
+      }
+      const float corr = exp2f(mx - cmx);   // mx=-inf on the first block -> 0
+      mx = cmx;
+      l *= corr;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) acc[d] *= corr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pj = exp2f(s[j] - mx);
+        l += pj;
+        const float4 va = sv[2 * (j0 + j)], vb = sv[2 * (j0 + j) + 1];
+        acc[0] = fmaf(pj, va.x, acc[0]); acc[1] = fmaf(pj, va.y, acc[1]);
+        acc[2] = fmaf(pj, va.z, acc[2]); acc[3] = fmaf(pj, va.w, acc[3]);
+        acc[4] = fmaf(pj, vb.x, acc[4]); acc[5] = fmaf(pj, vb.y, acc[5]);
+        acc[6] = fmaf(pj, vb.z, acc[6]); acc[7] = fmaf(pj, vb.w, acc[7]);
+      }
+    }
+  }
+  if (qi < N) {
+    const float inv = 1.0f / l;
+    __align__(16) __half2 h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(acc[2 * j] * inv, acc[2 * j + 1] * inv);
+    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * N + qi) * C + hd * 8) =
+        *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// time embedding.  temb_mlp: grid B, block 512 (16 warps): sinusoid -> linear_1 -> silu ->
+// linear_2 -> silu, warp-per-output-row dot products.  temb_proj: grid (ceil(T/8), B), block 256.
+__global__ void __launch_bounds__(512)
+temb_mlp_kernel(const float* __restrict__ t, const float* __restrict__ w1,
+                const float* __restrict__ b1, const float* __restrict__ w2,
+                const float* __restrict__ b2, float* __restrict__ scratch, int D0, int D4) {
+  extern __shared__ float sh_t[];  // e0[D0], h1[D4]
+  float* e0 = sh_t;
+  float* h1 = sh_t + D0;
+  const int b = blockIdx.x;
+  const float tv = t[b];
+  const int half = D0 / 2;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float f = expf(-9.210340371976184f * static_cast<float>(i) / static_cast<float>(half));
+    const float a = tv * f;
+    e0[i] = cosf(a);           // flip_sin_to_cos=True -> [cos, sin]
+    e0[half + i] = sinf(a);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = warp; r < D4; r += nw) {
+    float s = 0.f;
+    for (int c = lane; c < D0; c += 32) s = fmaf(__ldg(w1 + static_cast<size_t>(r) * D0 + c), e0[c], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      s += b1[r];
+      h1[r] = s / (1.0f + expf(-s));
+    }
+  }
+  __syncthreads();
+  for (int r = warp; r < D4; r += nw) {
+    float s = 0.f;
+    for (int c = lane; c < D4; c += 32) s = fmaf(__ldg(w2 + static_cast<size_t>(r) * D4 + c), h1[c], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      s += b2[r];
+      scratch[static_cast<size_t>(b) * D4 + r] = s / (1.0f + expf(-s));  // silu(emb), shared by all resnets
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+temb_proj_kernel(const float* __restrict__ semb, const float* __restrict__ wp,
+                 const float* __restrict__ bp, float* __restrict__ out, int D4, int T) {
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (r >= T) return;
+  float s = 0.f;
+  for (int c = lane; c < D4; c += 32)
+    s = fmaf(__ldg(wp + static_cast<size_t>(r) * D4 + c), __ldg(semb + static_cast<size_t>(b) * D4 + c), s);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[static_cast<size_t>(b) * T + r] = s + bp[r];
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused scheduler step (float4 vectorised; scalar tail).
+__global__ void __launch_bounds__(256)
+sched_step_kernel(const float* __restrict__ k, const float* __restrict__ x,
+                  const float* __restrict__ eps, const float* __restrict__ x0_prev,
+                  const float* __restrict__ noise, float* __restrict__ x_out,
+                  float* __restrict__ x0_out, int64_t n) {
+  const float k0 = k[0], k1 = k[1], k2 = k[2], k3 = k[3], k4 = k[4], k5 = k[5], k6 = k[6];
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  if (i + 4 <= n) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + i);
+    const float4 ev = *reinterpret_cast<const float4*>(eps + i);
+    const float4 pv = x0_prev ? *reinterpret_cast<const float4*>(x0_prev + i) : make_float4(0, 0, 0, 0);
+    const float4 nv = noise ? *reinterpret_cast<const float4*>(noise + i) : make_float4(0, 0, 0, 0);
+    float4 x0, xo;
+#define RLDM_STEP(f)                                                            \
+  x0.f = fmaf(k0, xv.f, k1 * ev.f);                                             \
+  xo.f = k2 * xv.f + k3 * x0.f + k4 * pv.f + k5 * ev.f + k6 * nv.f;
+    RLDM_STEP(x) RLDM_STEP(y) RLDM_STEP(z) RLDM_STEP(w)
+#undef RLDM_STEP
+    if (x0_out) *reinterpret_cast<float4*>(x0_out + i) = x0;
+    *reinterpret_cast<float4*>(x_out + i) = xo;
+  } else {
+    for (int64_t j = i; j < n; ++j) {
+      const float x0 = fmaf(k0, x[j], k1 * eps[j]);
+      const float xo = k2 * x[j] + k3 * x0 + k4 * (x0_prev ? x0_prev[j] : 0.f) + k5 * eps[j] +
+                       k6 * (noise ? noise[j] : 0.f);
+      if (x0_out) x0_out[j] = x0;
+      x_out[j] = xo;
+    }
+  }
+}
+
+__global__ void scale_kernel(const float* __restrict__ x, float a, float* __restrict__ y, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a * x[i];
+}
+
+// layout helpers: ref (B,C,W,H) <-> cl (B,W,H,C); thread per element (tiny boundary tensors only).
+__global__ void ref_to_cl_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int P,
+                                 size_t total) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // dst index
+  if (i >= total) return;
+  const int c = i % C;
+  const size_t bp = i / C;
+  const int p = bp % P;
+  const size_t b = bp / P;
+  dst[i] = src[(b * C + c) * P + p];
+}
+__global__ void cl_to_ref_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int P,
+                                 size_t total) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // dst index
+  if (i >= total) return;
+  const int p = i % P;
+  const size_t bc = i / P;
+  const int c = bc % C;
+  const size_t b = bc / C;
+  dst[i] = src[(b * P + p) * C + c];
+}
+
+}  // namespace rldm
+
+using namespace rldm;
+
+extern "C" int rldm_version(void) { return RLDM_VERSION; }
+extern "C" const char* rldm_last_error(void) { return g_err; }
+
+extern "C" int rldm_gn_stats(const float* x0, int c0, const float* x1, int c1, double* sums, int B,
+                             int P, int G, void* stream) {
+  const int C = c0 + c1;
+  RLDM_CHECK(c0 % 4 == 0 && c1 % 4 == 0 && C % G == 0, "gn_stats: bad channels c0=%d c1=%d G=%d", c0, c1, G);
+  RLDM_CHECK(x1 != nullptr || c1 == 0, "gn_stats: x1 NULL with c1=%d", c1);
+  // ~4 CTAs per SM over the whole tensor, at least 16 pixels each
+  int chunks = (592 + B - 1) / B;
+  int ppb = (P + chunks - 1) / chunks;
+  if (ppb < 16) ppb = 16;
+  chunks = (P + ppb - 1) / ppb;
+  const int q = C / 4;   // block = whole pixels so each thread keeps one channel quad in registers
+  const int threads = q <= 256 ? (256 / q) * q : 256;
+  gn_stats_kernel<<<dim3(chunks, B), threads, 2 * G * sizeof(double), as_stream(stream)>>>(
+      x0, c0, x1, c1, sums, P, G, ppb);
+  RLDM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rldm_prep(const float* x0, int c0, const float* x1, int c1, const double* sums,
+                         const float* gamma, const float* beta, float eps, int G, int silu, int up,
+                         uint16_t* out, int B, int W, int H, void* stream) {
+  const int C = c0 + c1;
+  RLDM_CHECK(c0 % 8 == 0 && c1 % 8 == 0, "prep: channels must be multiples of 8 (c0=%d c1=%d)", c0, c1);
+  RLDM_CHECK(up == 1 || up == 2, "prep: up must be 1 or 2");
+  RLDM_CHECK(!sums || (gamma && beta && G > 0 && C % G == 0), "prep: GroupNorm needs gamma/beta/G");
+  const int out_pix = W * up * H * up;
+  int chunks = (592 + B - 1) / B;
+  int ppb = (out_pix + chunks - 1) / chunks;
+  if (ppb < 8) ppb = 8;
+  chunks = (out_pix + ppb - 1) / ppb;
+  prep_kernel<<<dim3(chunks, B), 256, 2 * C * sizeof(float), as_stream(stream)>>>(
+      x0, c0, x1, c1, sums, gamma, beta, eps, G, silu, up, reinterpret_cast<__half*>(out), W, H, ppb);
+  RLDM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rldm_conv_ref(const uint16_t* x, const uint16_t* wgt, const float* bias,
+                             const float* temb, int temb_stride, const float* residual, float* out,
+                             int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
+                             int circular, void* stream) {
+  const size_t total = static_cast<size_t>(B) * (W / stride) * (H / stride) * Cout;
+  conv_ref_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(wgt), bias, temb,
+      temb_stride, residual, out, B, W, H, Cin, Cout, ks, stride, pad_lo, circular);
+  RLDM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rldm_conv_in(const float* x0, int c0, const float* x1, int c1, const float* wgt,
+                            const float* bias, float* out, int B, int W, int H, int Cout,
+                            int circular, void* stream) {
+  RLDM_CHECK(x1 != nullptr || c1 == 0, "conv_in: x1 NULL with c1=%d", c1);
+  RLDM_CHECK(Cout % 4 == 0 && Cout <= 1024 && 256 % (Cout / 4) == 0, "conv_in: unsupported Cout=%d", Cout);
+  const size_t total_pix = static_cast<size_t>(B) * W * H;
+  const int ppb = 32;
+  conv_in_kernel<<<static_cast<unsigned>((total_pix + ppb - 1) / ppb), 256, 0, as_stream(stream)>>>(
+      x0, c0, x1, c1, wgt, bias, out, B, W, H, Cout, circular, ppb);
+  RLDM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rldm_conv_out(const uint16_t* x, const float* wgt, const float* bias, float* out,
+                             int B, int W, int H, int Cin, int Cout, int circular, void* stream) {
+  RLDM_CHECK(Cin % 2 == 0, "conv_out: Cin must be even");
+  const size_t total_pix = static_cast<size_t>(B) * W * H;
+  const unsigned grid = static_cast<unsigned>((total_pix + 7) / 8);
+  const __half* xh = reinterpret_cast<const __half*>(x);
+  cudaStream_t st = as_stream(stream);
+  switch (Cout) {
+    case 2: conv_out_kernel<2><<<grid, 256, 0, st>>>(xh, wgt, bias, out, B, W, H, Cin, circular); break;
+    case 4: conv_out_kernel<4><<<grid, 256, 0, st>>>(xh, wgt, bias, out, B, W, H, Cin, circular); break;
+    case 8: conv_out_kernel<8><<<grid, 256, 0, st>>>(xh, wgt, bias, out, B, W, H, Cin, circular); break;
+    default: RLDM_CHECK(false, "conv_out: Cout must be 2, 4 or 8 (got %d)", Cout);
+  }
+  RLDM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rldm_attention(const float* qkv, uint16_t* out, int B, int N, int C, void* stream) {
+  RLDM_CHECK(C % 8 == 0, "attention: C %% 8 != 0");
+  const int threads = N >= 128 ? 128 : ((N + 31) / 32) * 32;
+  attention_kernel<<<dim3((N + threads - 1) / threads, C / 8, B), threads, 0, as_stream(stream)>>>(
+      qkv, reinterpret_cast<__half*>(out), N, C);
+  RLDM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rldm_temb(const float* t, const float* w1, const float* b1, const float* w2,
+                         const float* b2, const float* wp, const float* bp, float* scratch,
+                         float* out, int B, int D0, int D4, int T, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  temb_mlp_kernel<<<B, 512, (D0 + D4) * sizeof(float), st>>>(t, w1, b1, w2, b2, scratch, D0, D4);
+  RLDM_LAUNCH_CHECK();
+  if (T > 0) {
+    temb_proj_kernel<<<dim3((T + 7) / 8, B), 256, 0, st>>>(scratch, wp, bp, out, D4, T);
+    RLDM_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int rldm_sched_step(const float* k, const float* x, const float* eps,
+                               const float* x0_prev, const float* noise, float* x_out,
+                               float* x0_out, int64_t n, void* stream) {
+  const int64_t nthreads = (n + 3) / 4;
+  sched_step_kernel<<<static_cast<unsigned>((nthreads + 255) / 256), 256, 0, as_stream(stream)>>>(
+      k, x, eps, x0_prev, noise, x_out, x0_out, n);
+  RLDM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rldm_scale(const float* x, float a, float* y, int64_t n, void* stream) {
+  scale_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(x, a, y, n);
+  RLDM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rldm_ref_to_cl(const float* src, float* dst, int B, int C, int W, int H, void* stream) {
+  const size_t total = static_cast<size_t>(B) * C * W * H;
+  ref_to_cl_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, as_stream(stream)>>>(src, dst, C, W * H, total);
+  RLDM_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int rldm_cl_to_ref(const float* src, float* dst, int B, int C, int W, int H, void* stream) {
+  const size_t total = static_cast<size_t>(B) * C * W * H;
+  cl_to_ref_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, as_stream(stream)>>>(src, dst, C, W * H, total);
+  RLDM_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int rldm_run(const rldm_op* ops, int n_ops, void* stream) {
+  for (int k = 0; k < n_ops; ++k) {
+    const rldm_op& o = ops[k];
+    int rc = 0;
+    switch (o.kind) {
+      case RLDM_OP_GN_STATS:
+        rc = rldm_gn_stats((const float*)o.p[0], o.i[0], (const float*)o.p[1], o.i[1], (double*)o.p[2],
+                           o.i[2], o.i[3], o.i[4], stream);
+        break;
+      case RLDM_OP_PREP:
+        rc = rldm_prep((const float*)o.p[0], o.i[0], (const float*)o.p[1], o.i[1], (const double*)o.p[2],
+                       (const float*)o.p[3], (const float*)o.p[4], o.f[0], o.i[2], o.i[3], o.i[4],
+                       (uint16_t*)o.p[5], o.i[5], o.i[6], o.i[7], stream);
+        break;
+      case RLDM_OP_CONV_TC:
+        rc = rldm_conv_tc((const uint16_t*)o.p[0], (const uint16_t*)o.p[1], (const float*)o.p[2],
+                          (const float*)o.p[3], o.i[0], (const float*)o.p[4], (float*)o.p[5], o.i[1],
+                          o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], o.i[7], o.i[8], o.i[9], o.i[10], stream);
+        break;
+      case RLDM_OP_CONV_REF:
+        rc = rldm_conv_ref((const uint16_t*)o.p[0], (const uint16_t*)o.p[1], (const float*)o.p[2],
+                           (const float*)o.p[3], o.i[0], (const float*)o.p[4], (float*)o.p[5], o.i[1],
+                           o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], o.i[7], o.i[8], o.i[9], stream);
+        break;
+      case RLDM_OP_CONV_IN:
+        rc = rldm_conv_in((const float*)o.p[0], o.i[0], (const float*)o.p[1], o.i[1], (const float*)o.p[2],
+                          (const float*)o.p[3], (float*)o.p[4], o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], stream);
+        break;
+      case RLDM_OP_CONV_OUT:
+        rc = rldm_conv_out((const uint16_t*)o.p[0], (const float*)o.p[1], (const float*)o.p[2],
+                           (float*)o.p[3], o.i[0], o.i[1], o.i[2], o.i[3], o.i[4], o.i[5], stream);
+        break;
+      case RLDM_OP_ATTENTION:
+        rc = rldm_attention((const float*)o.p[0], (uint16_t*)o.p[1], o.i[0], o.i[1], o.i[2], stream);
+        break;
+      case RLDM_OP_TEMB:
+        rc = rldm_temb((const float*)o.p[0], (const float*)o.p[1], (const float*)o.p[2],
+                       (const float*)o.p[3], (const float*)o.p[4], (const float*)o.p[5],
+                       (const float*)o.p[6], (float*)o.p[7], (float*)o.p[8], o.i[0], o.i[1], o.i[2],
+                       o.i[3], stream);
+        break;
+      case RLDM_OP_SCHED_STEP:
+        rc = rldm_sched_step((const float*)o.p[0], (const float*)o.p[1], (const float*)o.p[2],
+                             (const float*)o.p[3], (const float*)o.p[4], (float*)o.p[5], (float*)o.p[6],
+                             o.n, stream);
+        break;
+      case RLDM_OP_MEMSET: {
+        cudaError_t e = cudaMemsetAsync(o.p[0], 0, static_cast<size_t>(o.n), as_stream(stream));
+        if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); rc = 2; }
+        break;
+      }
+      case RLDM_OP_AXPY:
+        rc = rldm_scale((const float*)o.p[0], o.f[0], (float*)o.p[1], o.n, stream);
+        break;
+      default:
+        set_error("rldm_run: unknown op kind %d at index %d", o.kind, k);
+        rc = 3;
+    }
+    if (rc) return rc;
+  }
+  return 0;
+}

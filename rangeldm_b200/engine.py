@@ -1,0 +1,454 @@
+"""Plan compiler: turns a `UNet2DModel` / `AutoencoderKL` module tree into a flat program of
+librldm kernel launches (`rldm_op` records, include/rldm.h) over statically allocated HBM buffers.
+
+Data layout in HBM (per plan, allocated once):
+  * boundary tensors keep the reference layout (B, C, W, H) fp32 (`ldm/dataset.py:230`);
+  * every internal activation is channels-last (B, W, H, C): the fp32 "residual stream" written by
+    conv epilogues, and the fp16 tensor-core operand written by `prep` (GroupNorm-apply + SiLU +
+    skip-concat + nearest-upsample + cast in one pass);
+  * weights are repacked once to [tap][Cout][Cin] fp16 (tap = kW*3 + kH), projections of an
+    attention block are stacked into one [3C][C] GEMM, all `time_emb_proj` rows into one matrix;
+  * GroupNorm moments for all layers live in one double arena cleared by a single memset per forward.
+
+The program is replayed with one `rldm_run` call (no host work between launches) and is CUDA-graph
+capturable.  Reference semantics followed: SURVEY.md App. A.1/A.2, `ldm/utils.py:40-58,107-116`,
+`vae/sgm/modules/diffusionmodules/model.py:342-362,1024-1057`.
+"""
+import ctypes
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import RldmOp
+
+# debug switch used by the GPU tests to run the CUDA-core restatement of the conv (never the default)
+CONV_KIND = _lib.OP_CONV_TC
+
+
+def _require_cuda_device(dev, what):
+    """Plans hold device pointers; compiling one for a CPU model is only allowed as a DRY RUN
+    (RLDM_DRYRUN=1: host-logic tests count ops and check shapes; `run()` then refuses)."""
+    if dev.type != "cuda" and os.environ.get("RLDM_DRYRUN") != "1":
+        raise RuntimeError(f"{what} must be on a CUDA device: rangeldm_b200 has no CPU fallback")
+
+
+class Program:
+    def __init__(self, device):
+        self.device = device
+        self.ops = []
+        self.keep = []          # every tensor the program points into
+        self._free = {}         # (nbytes) -> [tensor]
+        self.arr = None
+        self.n_launch = 0
+
+    # ---- buffers ---------------------------------------------------------------------------
+    def alloc(self, shape, dtype=torch.float32):
+        n = 1
+        for s in shape:
+            n *= int(s)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        lst = self._free.get(nbytes)
+        if lst:
+            raw = lst.pop()
+        else:
+            raw = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.keep.append(raw)
+        return raw.view(dtype).view(*shape)
+
+    def free(self, t):
+        if t is None:
+            return
+        raw = t.view(-1).view(torch.uint8)
+        self._free.setdefault(raw.numel(), []).append(raw)
+
+    def hold(self, t):
+        self.keep.append(t)
+        return t
+
+    # ---- ops -------------------------------------------------------------------------------
+    def add(self, kind, i=(), f=(), p=(), n=0, launches=1):
+        op = RldmOp()
+        op.kind = kind
+        for k, v in enumerate(i):
+            op.i[k] = int(v)
+        for k, v in enumerate(f):
+            op.f[k] = float(v)
+        for k, v in enumerate(p):
+            op.p[k] = None if v is None else (v if isinstance(v, int) else v.data_ptr())
+        op.n = int(n)
+        self.ops.append(op)
+        self.n_launch += launches
+        return op
+
+    def extend(self, other):
+        """Append another program's ops (sharing its buffers)."""
+        self.ops.extend(other.ops)
+        self.keep.append(other)
+        self.n_launch += other.n_launch
+
+    def finalize(self):
+        self.arr = (RldmOp * len(self.ops))(*self.ops)
+        return self
+
+    def run(self):
+        if self.device.type != "cuda":
+            raise RuntimeError("dry-run program (built on CPU) cannot execute: no CPU fallback")
+        if self.arr is None:
+            self.finalize()
+        _lib.check(_lib.lib().rldm_run(self.arr, len(self.ops), _lib.stream_ptr()))
+
+
+class Act:
+    """Channels-last fp32 activation (B, W, H, C)."""
+    __slots__ = ("t", "B", "W", "H", "C")
+
+    def __init__(self, t, B, W, H, C):
+        self.t, self.B, self.W, self.H, self.C = t, B, W, H, C
+
+
+def _is_identity_attn(m):
+    return m is None or not hasattr(m, "to_q")
+
+
+class Builder:
+    """Emits ops for the building blocks shared by the UNet and the VAE."""
+
+    def __init__(self, prog, batch, max_gn=1024, groups=32):
+        self.pg = prog
+        self.B = batch
+        self.gn_arena = prog.hold(torch.zeros(max_gn * batch * groups * 2, dtype=torch.float64, device=prog.device))
+        self.gn_used = 0
+        self.memset_op = prog.add(_lib.OP_MEMSET, p=(self.gn_arena,), n=0)
+        self.temb = None         # (tensor (B,T), T)
+        self.temb_rows = {}      # id(resnet) -> row offset
+
+    def finish(self):
+        self.memset_op.n = self.gn_used * 8
+
+    # ---- weights ---------------------------------------------------------------------------
+    def f32(self, t):
+        return self.pg.hold(t.detach().to(self.pg.device, torch.float32).contiguous())
+
+    def pack_conv(self, conv):
+        w = conv.weight.detach().to(self.pg.device, torch.float32)       # (Cout, Cin, kW, kH)
+        co, ci, k0, k1 = w.shape
+        wt = w.permute(2, 3, 0, 1).reshape(k0 * k1, co, ci).to(torch.float16).contiguous()
+        b = self.f32(conv.bias) if conv.bias is not None else None
+        return self.pg.hold(wt), b
+
+    def pack_linear(self, lins):
+        w = torch.cat([l.weight.detach().to(self.pg.device, torch.float32) for l in lins], 0)
+        b = torch.cat([l.bias.detach().to(self.pg.device, torch.float32) for l in lins], 0)
+        return self.pg.hold(w.to(torch.float16).contiguous()), self.pg.hold(b.contiguous())
+
+    # ---- primitive emitters ----------------------------------------------------------------
+    def gn_stats(self, x0, x1, groups):
+        n = self.B * groups * 2
+        off = self.gn_used
+        self.gn_used += n
+        assert self.gn_used <= self.gn_arena.numel(), "GroupNorm arena exhausted"
+        sums = self.gn_arena[off:off + n]
+        c1 = x1.C if x1 is not None else 0
+        self.pg.add(_lib.OP_GN_STATS, i=(x0.C, c1, self.B, x0.W * x0.H, groups),
+                    p=(x0.t, x1.t if x1 is not None else None, sums))
+        return sums
+
+    def prep(self, x0, x1=None, norm=None, silu=False, up=1):
+        """-> fp16 cl tensor (B, W*up, H*up, C0+C1)."""
+        c1 = x1.C if x1 is not None else 0
+        C = x0.C + c1
+        sums = gamma = beta = None
+        eps, G = 0.0, 0
+        if norm is not None:
+            G = norm.num_groups
+            sums = self.gn_stats(x0, x1, G)
+            gamma, beta, eps = self.f32(norm.weight), self.f32(norm.bias), norm.eps
+        out = self.pg.alloc((self.B, x0.W * up, x0.H * up, C), torch.float16)
+        self.pg.add(_lib.OP_PREP, i=(x0.C, c1, G, int(silu), up, self.B, x0.W, x0.H), f=(eps,),
+                    p=(x0.t, x1.t if x1 is not None else None, sums, gamma, beta, out))
+        return out
+
+    def conv(self, xh, W, H, conv=None, packed=None, cin=None, cout=None, ks=3, stride=1, pad_lo=1, circular=True,
+             temb=None, residual=None):
+        """fp16 cl (B,W,H,Cin) -> fp32 cl Act (B,W/stride,H/stride,Cout)."""
+        if conv is not None:
+            wt, bias = self.pack_conv(conv)
+            cout, cin, ks = conv.out_channels, conv.in_channels, conv.kernel_size[0]
+            stride, pad_lo = conv.stride[0], conv.padding[0]
+            circular = bool(getattr(conv, "circular", False))
+            if conv.padding_mode != "zeros" or conv.groups != 1 or conv.dilation[0] != 1:
+                raise NotImplementedError("conv with groups/dilation/padding_mode is outside the reference path")
+        else:
+            wt, bias = packed
+        Wo, Ho = W // stride, H // stride
+        out = self.pg.alloc((self.B, Wo, Ho, cout))
+        temb_t, temb_stride = (None, 0)
+        if temb is not None:
+            temb_t, temb_stride = temb
+        kind = CONV_KIND
+        ints = [temb_stride, self.B, W, H, cin, cout, ks, stride, pad_lo, int(circular)]
+        if kind == _lib.OP_CONV_TC:
+            ints.append(0)   # split_k: auto
+        self.pg.add(kind, i=ints, p=(xh, wt, bias, temb_t, residual.t if residual is not None else None, out),
+                    launches=1)
+        return Act(out, self.B, Wo, Ho, cout)
+
+    # ---- blocks ----------------------------------------------------------------------------
+    def resnet(self, rb, x0, x1=None, free_inputs=True):
+        """ResnetBlock2D on the virtual concat (x0 | x1) (App. A.1; `model.py:342-362`)."""
+        pg = self.pg
+        a1 = self.prep(x0, x1, rb.norm1, silu=True)
+        temb = None
+        if rb.time_emb_proj is not None and self.temb is not None:
+            t, T = self.temb
+            off = self.temb_rows[id(rb)]
+            temb = (t.view(-1)[off:], T)
+        h = self.conv(a1, x0.W, x0.H, rb.conv1, temb=temb)
+        pg.free(a1)
+        a2 = self.prep(h, None, rb.norm2, silu=True)
+        pg.free(h.t)
+        if rb.conv_shortcut is not None:
+            xr = self.prep(x0, x1, None, silu=False)
+            sc = self.conv(xr, x0.W, x0.H, rb.conv_shortcut)
+            pg.free(xr)
+            out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=sc)
+            pg.free(sc.t)
+        else:
+            assert x1 is None
+            out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=x0)
+        pg.free(a2)
+        if free_inputs:
+            pg.free(x0.t)
+            if x1 is not None:
+                pg.free(x1.t)
+        return out
+
+    def attention(self, at, x, free_input=True):
+        """Attention block with residual (App. A.1): GN -> qkv GEMM -> SDPA(d=8) -> out GEMM + x."""
+        pg = self.pg
+        if at.dim_head != 8:
+            raise NotImplementedError(f"attention head_dim {at.dim_head}: the sm_100a attention kernel implements the "
+                                      "reference's attention_head_dim=8")
+        C = x.C
+        a = self.prep(x, None, at.group_norm, silu=False)
+        qkv = self.conv(a, x.W, x.H, packed=self.pack_linear([at.to_q, at.to_k, at.to_v]), cin=C, cout=3 * C, ks=1,
+                        pad_lo=0)
+        pg.free(a)
+        o = pg.alloc((self.B, x.W, x.H, C), torch.float16)
+        pg.add(_lib.OP_ATTENTION, i=(self.B, x.W * x.H, C), p=(qkv.t, o))
+        pg.free(qkv.t)
+        out = self.conv(o, x.W, x.H, packed=self.pack_linear([at.to_out[0]]), cin=C, cout=C, ks=1, pad_lo=0,
+                        residual=x)
+        pg.free(o)
+        if free_input:
+            pg.free(x.t)
+        return out
+
+    def downsample(self, ds, x, free_input=True):
+        """Patched Downsample2D (`ldm/utils.py:107-116`): raw cast + stride-2 conv; padding=0 is the
+        VAE-encoder asymmetric pad (pad_lo = 0)."""
+        xr = self.prep(x, None, None)
+        out = self.conv(xr, x.W, x.H, ds.conv)
+        self.pg.free(xr)
+        if free_input:
+            self.pg.free(x.t)
+        return out
+
+    def upsample(self, us, x):
+        """Upsample2D (`model.py:120-125`): nearest 2x folded into the cast, then 3x3 conv."""
+        xr = self.prep(x, None, None, up=2)
+        out = self.conv(xr, x.W * 2, x.H * 2, us.conv)
+        self.pg.free(xr)
+        self.pg.free(x.t)
+        return out
+
+    def conv_in(self, conv, x0, c0, x1, c1, W, H):
+        w = conv.weight.detach().to(self.pg.device, torch.float32)      # (Cout, Cin, kW, kH)
+        wt = self.pg.hold(w.permute(2, 3, 1, 0).contiguous())           # [9][Cin][Cout]
+        out = self.pg.alloc((self.B, W, H, conv.out_channels))
+        assert conv.in_channels == c0 + c1 and conv.kernel_size == (3, 3) and conv.padding == (1, 1)
+        self.pg.add(_lib.OP_CONV_IN, i=(c0, c1, self.B, W, H, conv.out_channels, int(getattr(conv, "circular", False))),
+                    p=(x0, x1, wt, self.f32(conv.bias), out))
+        return Act(out, self.B, W, H, conv.out_channels)
+
+    def conv_out(self, norm, conv, x, out_ref):
+        a = self.prep(x, None, norm, silu=True)
+        w = conv.weight.detach().to(self.pg.device, torch.float32)
+        wt = self.pg.hold(w.permute(2, 3, 0, 1).contiguous())           # [9][Cout][Cin]
+        assert conv.kernel_size == (3, 3) and conv.padding == (1, 1)
+        self.pg.add(_lib.OP_CONV_OUT, i=(self.B, x.W, x.H, x.C, conv.out_channels, int(getattr(conv, "circular", False))),
+                    p=(a, wt, self.f32(conv.bias), out_ref))
+        self.pg.free(a)
+        self.pg.free(x.t)
+
+
+def _timestep_to_float(timestep, B, device):
+    if torch.is_tensor(timestep):
+        t = timestep.detach().to(device=device, dtype=torch.float32).reshape(-1)
+        return t.expand(B) if t.numel() == 1 else t
+    return torch.full((B,), float(timestep), dtype=torch.float32, device=device)
+
+
+class UNetPlan:
+    """Compiled `UNet2DModel.forward` (App. A.1) for a fixed (batch, W, H).
+
+    `x_in`  : (B, in_channels - cond_channels, W, H) fp32 ref layout (static input buffer)
+    `cond`  : (B, cond_channels, W, H) or None -- second conv_in source (pos-encoding / condition),
+              so samplers never materialise torch.cat([latents, cond], 1)
+    `t_buf` : (B,) fp32 timesteps;  `out`: (B, out_channels, W, H) fp32 ref layout."""
+
+    def __init__(self, model, batch, W, H, cond_channels=0):
+        dev = model.device
+        _require_cuda_device(dev, "UNet2DModel")
+        cfg = model.config
+        self.B, self.W, self.H = batch, W, H
+        L = len(cfg.block_out_channels)
+        if W % (1 << (L - 1)) or H % (1 << (L - 1)):
+            raise ValueError(f"sample size {(W, H)} must be divisible by {1 << (L - 1)}")
+        pg = self.prog = Program(dev)
+        bd = Builder(pg, batch, groups=cfg.norm_num_groups)
+        cin = cfg.in_channels
+        self.x_in = pg.hold(torch.zeros(batch, cin - cond_channels, W, H, device=dev))
+        self.cond = pg.hold(torch.zeros(batch, cond_channels, W, H, device=dev)) if cond_channels else None
+        self.t_buf = pg.hold(torch.zeros(batch, device=dev))
+        self.out = pg.hold(torch.zeros(batch, cfg.out_channels, W, H, device=dev))
+
+        # ---- time embedding: MLP + every resnet projection in one stacked matrix ----
+        resnets = [m for m in model.modules() if hasattr(m, "time_emb_proj") and m.time_emb_proj is not None]
+        D0 = cfg.block_out_channels[0]
+        D4 = model.time_embedding.linear_1.out_features
+        rows, off = [], 0
+        for r in resnets:
+            bd.temb_rows[id(r)] = off
+            rows.append(r.time_emb_proj)
+            off += r.time_emb_proj.out_features
+        T = off
+        wp = pg.hold(torch.cat([r.weight.detach().float() for r in rows], 0).to(dev).contiguous())
+        bp = pg.hold(torch.cat([r.bias.detach().float() for r in rows], 0).to(dev).contiguous())
+        te = model.time_embedding
+        scratch = pg.hold(torch.zeros(batch, D4, device=dev))
+        temb_out = pg.hold(torch.zeros(batch, T, device=dev))
+        pg.add(_lib.OP_TEMB, i=(batch, D0, D4, T),
+               p=(self.t_buf, bd.f32(te.linear_1.weight), bd.f32(te.linear_1.bias), bd.f32(te.linear_2.weight),
+                  bd.f32(te.linear_2.bias), wp, bp, scratch, temb_out), launches=2)
+        bd.temb = (temb_out, T)
+
+        # ---- network ----
+        h = bd.conv_in(model.conv_in, self.x_in, cin - cond_channels, self.cond, cond_channels, W, H)
+        skips = [h]
+        for blk in model.down_blocks:
+            for j, rb in enumerate(blk.resnets):
+                h = bd.resnet(rb, h, free_inputs=False)          # input is a skip (or feeds attention below)
+                if getattr(blk, "attentions", None) is not None and not _is_identity_attn(blk.attentions[j]):
+                    h = bd.attention(blk.attentions[j], h, free_input=True)
+                skips.append(h)
+            if blk.downsamplers is not None:
+                h = bd.downsample(blk.downsamplers[0], h, free_input=False)
+                skips.append(h)
+        mb = model.mid_block
+        h = bd.resnet(mb.resnets[0], h, free_inputs=False)       # h is still on the skip stack
+        if not _is_identity_attn(mb.attentions[0]):
+            h = bd.attention(mb.attentions[0], h)
+        h = bd.resnet(mb.resnets[1], h)
+        for blk in model.up_blocks:
+            for j, rb in enumerate(blk.resnets):
+                h = bd.resnet(rb, h, skips.pop())                # frees both inputs
+                if getattr(blk, "attentions", None) is not None and not _is_identity_attn(blk.attentions[j]):
+                    h = bd.attention(blk.attentions[j], h)
+            if blk.upsamplers is not None:
+                h = bd.upsample(blk.upsamplers[0], h)
+        assert not skips
+        bd.conv_out(model.conv_norm_out, model.conv_out, h, self.out)
+        bd.finish()
+        pg.finalize()
+
+    def run(self, sample, timestep):
+        if self.cond is not None:
+            c0 = self.x_in.shape[1]
+            self.x_in.copy_(sample[:, :c0])
+            self.cond.copy_(sample[:, c0:])
+        else:
+            self.x_in.copy_(sample)
+        self.t_buf.copy_(_timestep_to_float(timestep, self.B, self.t_buf.device))
+        self.prog.run()
+        return self.out.clone()
+
+
+def _check_vae_identity(m, name):
+    if not isinstance(m, nn.Identity):
+        raise NotImplementedError(f"AutoencoderKL.{name} must be nn.Identity (as `ldm/inference.py:90-92` sets it for "
+                                  "the reference checkpoints); a learned 1x1 quant conv is not implemented")
+
+
+class VaeDecoderPlan:
+    """Compiled `AutoencoderKL.decode` == sgm `Decoder.forward` (`model.py:1024-1057`)."""
+
+    def __init__(self, vae, batch, W, H):
+        dev = vae.device
+        _require_cuda_device(dev, "AutoencoderKL")
+        _check_vae_identity(vae.post_quant_conv, "post_quant_conv")
+        dec = vae.decoder
+        self.B = batch
+        pg = self.prog = Program(dev)
+        bd = Builder(pg, batch, groups=vae.config.norm_num_groups)
+        zc = vae.config.latent_channels
+        n_up = sum(1 for b in dec.up_blocks if b.upsamplers is not None)
+        self.z_in = pg.hold(torch.zeros(batch, zc, W, H, device=dev))
+        self.out = pg.hold(torch.zeros(batch, vae.config.out_channels, W << n_up, H << n_up, device=dev))
+        h = bd.conv_in(dec.conv_in, self.z_in, zc, None, 0, W, H)
+        mb = dec.mid_block
+        h = bd.resnet(mb.resnets[0], h)
+        if not _is_identity_attn(mb.attentions[0]):
+            h = bd.attention(mb.attentions[0], h)
+        h = bd.resnet(mb.resnets[1], h)
+        for blk in dec.up_blocks:
+            for rb in blk.resnets:
+                h = bd.resnet(rb, h)
+            if blk.upsamplers is not None:
+                h = bd.upsample(blk.upsamplers[0], h)
+        bd.conv_out(dec.conv_norm_out, dec.conv_out, h, self.out)
+        bd.finish()
+        pg.finalize()
+
+    def run(self, z):
+        self.z_in.copy_(z)
+        self.prog.run()
+        return self.out.clone()
+
+
+class VaeEncoderPlan:
+    """Compiled `AutoencoderKL.encode` moments == sgm `Encoder.forward` (`model.py:852-896`)."""
+
+    def __init__(self, vae, batch, W, H):
+        dev = vae.device
+        _require_cuda_device(dev, "AutoencoderKL")
+        _check_vae_identity(vae.quant_conv, "quant_conv")
+        enc = vae.encoder
+        self.B = batch
+        pg = self.prog = Program(dev)
+        bd = Builder(pg, batch, groups=vae.config.norm_num_groups)
+        ic = vae.config.in_channels
+        n_down = sum(1 for b in enc.down_blocks if b.downsamplers is not None)
+        self.x_in = pg.hold(torch.zeros(batch, ic, W, H, device=dev))
+        self.out = pg.hold(torch.zeros(batch, enc.conv_out.out_channels, W >> n_down, H >> n_down, device=dev))
+        h = bd.conv_in(enc.conv_in, self.x_in, ic, None, 0, W, H)
+        for blk in enc.down_blocks:
+            for rb in blk.resnets:
+                h = bd.resnet(rb, h)
+            if blk.downsamplers is not None:
+                h = bd.downsample(blk.downsamplers[0], h)
+        mb = enc.mid_block
+        h = bd.resnet(mb.resnets[0], h)
+        if not _is_identity_attn(mb.attentions[0]):
+            h = bd.attention(mb.attentions[0], h)
+        h = bd.resnet(mb.resnets[1], h)
+        bd.conv_out(enc.conv_norm_out, enc.conv_out, h, self.out)
+        bd.finish()
+        pg.finalize()
+
+    def run(self, x):
+        self.x_in.copy_(x)
+        self.prog.run()
+        return self.out.clone()

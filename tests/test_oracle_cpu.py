@@ -1,0 +1,112 @@
+"""CPU tests: the oracle against the reference's own code (golden vectors in tests/golden generated
+by oracle/make_golden.py; live comparison when /root/reference is present)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import relerr
+from oracle import nets, pipeline, refshim, schedulers
+from oracle.make_golden import TINY_UNET, TINY_UNET_PIXEL, TINY_VAE, seeded, toy_eps_matrix
+
+
+def test_param_counts_match_survey_anchors():
+    # 113.67 M (RangeDM), 30.14 M (RangeLDM), VAE enc 5.34 M + dec 7.99 M
+    n = lambda m: sum(p.numel() for p in m.parameters())
+    assert n(nets.OracleUNet2DModel(**nets.UNET_C3)) == 30135684
+    assert n(nets.OracleUNet2DModel(**nets.UNET_C2)) == 113672066
+    vae = nets.OracleAutoencoderKL()
+    assert n(vae.decoder) == 7989570 and n(vae.encoder) == 5341320
+
+
+def test_vae_decoder_matches_reference_golden(golden):
+    g = golden("vae_decoder.pt")
+    vae = seeded(nets.OracleAutoencoderKL, 1234, **TINY_VAE)
+    with torch.no_grad():
+        assert relerr(vae.decode(g["z"]), g["out"]) < 1e-5
+
+
+def test_vae_encoder_matches_reference_golden(golden):
+    g = golden("vae_encoder.pt")
+    vae = seeded(nets.OracleAutoencoderKL, 1234, **TINY_VAE)
+    with torch.no_grad():
+        assert relerr(vae.encode_moments(g["x"]), g["out"]) < 1e-5
+
+
+def test_circular_conv_matches_reference_golden(golden):
+    g = golden("circ_conv.pt")
+    assert relerr(nets.circ_conv2d(g["x"], g["w1"], g["b1"], 1, 1), g["y1"]) < 1e-6
+    assert relerr(nets.circ_conv2d(g["x"], g["w2"], g["b2"], 2, 1), g["y2"]) < 1e-6
+    # the wrap is on dim 2 only: rolling the input along W rolls the output, along H it does not
+    y = nets.circ_conv2d(g["x"], g["w1"], g["b1"], 1, 1)
+    yr = nets.circ_conv2d(torch.roll(g["x"], 3, dims=2), g["w1"], g["b1"], 1, 1)
+    assert torch.allclose(torch.roll(y, 3, dims=2), yr, atol=1e-5)
+
+
+def test_dpmpp2m_matches_reference_sampler_golden(golden):
+    g = golden("dpmpp2m.pt")
+    s = schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading")
+    s.set_timesteps(20)
+    assert torch.equal(s.timesteps, g["timesteps"])          # integer table: bit exact
+    assert torch.equal(s.sigmas, g["sigmas"])
+    Wm = toy_eps_matrix()
+    x = g["x"].clone()
+    for i, t in enumerate(s.timesteps):
+        x = s.step(torch.tanh(x @ Wm), t, x)
+        assert relerr(x, g["traj"][i]) < 5e-6, i
+
+
+def test_scheduler_timestep_tables():
+    # SURVEY.md App. A.4
+    d = schedulers.OracleDDIMScheduler(); d.set_timesteps(50)
+    assert d.timesteps.tolist() == list(range(980, -1, -20))
+    s = schedulers.OracleDPMSolverMultistepScheduler(); s.set_timesteps(20)
+    assert s.timesteps.tolist() == [999, 949, 899, 849, 799, 749, 699, 649, 599, 549, 500, 450, 400, 350, 300,
+                                    250, 200, 150, 100, 50]
+    s = schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading"); s.set_timesteps(20)
+    assert s.timesteps.tolist() == list(range(940, 0, -47))
+
+
+def test_pipeline_loops_match_reference_pipelines_golden(golden):
+    """oracle/pipeline.py against the reference's ldm/pipelines.py run on the same oracle nets."""
+    g = golden("ldm_pipeline.pt")
+    vae = seeded(nets.OracleAutoencoderKL, 1234, **TINY_VAE)
+    unet = seeded(nets.OracleUNet2DModel, 4321, **TINY_UNET)
+    for name, sch in (("dpm", schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading")),
+                      ("ddim", schedulers.OracleDDIMScheduler())):
+        noise = torch.randn((2, 4, 32, 8), generator=torch.Generator().manual_seed(3))
+        img = pipeline.ldm_sample(unet, vae, sch, noise, 5, pos_encoding=True)
+        assert relerr(img, g[f"ldm_{name}"]) < 1e-5, name
+    upix = seeded(nets.OracleUNet2DModel, 4322, **TINY_UNET_PIXEL)
+    noise = torch.randn((2, 2, 32, 8), generator=torch.Generator().manual_seed(3))
+    img = pipeline.pixel_sample(upix, schedulers.OracleDDIMScheduler(), noise, 5, pos_encoding=True)
+    assert relerr(img, g["pixel_ddim"]) < 1e-5
+
+
+def test_sparse_encoder2_golden(golden):
+    g = golden("sparse_encoder2.pt")
+    assert torch.equal(pipeline.sparse_encoder2(g["x"]), g["y"])
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+def test_full_size_decoder_matches_live_reference():
+    model, _, _ = refshim.load()
+    vae = seeded(nets.OracleAutoencoderKL, 1)
+    rd = refshim.make_decoder(model)
+    rd.load_state_dict(nets.to_sgm_state_dict({k: v for k, v in vae.state_dict().items() if k.startswith("decoder.")},
+                                              nets.sgm_decoder_key_map()), strict=True)
+    z = torch.randn(1, 4, 64, 16, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        assert relerr(vae.decode(z), rd(z)) < 1e-5
+
+
+def test_ddpm_ddim_consistency():
+    """DDIM(eta=1) and DDPM share the posterior mean; DDIM(eta=0) x0 prediction inverts add-noise."""
+    d = schedulers.OracleDDIMScheduler(); d.set_timesteps(50)
+    x0 = torch.randn(2, 4, 8, 4)
+    eps = torch.randn_like(x0)
+    t = 500
+    a = d.alphas_cumprod[t]
+    xt = a.sqrt() * x0 + (1 - a).sqrt() * eps
+    prev = d.step(eps, t, xt)
+    ap = d.alphas_cumprod[t - 20]
+    assert torch.allclose(prev, ap.sqrt() * x0 + (1 - ap).sqrt() * eps, atol=1e-5)
