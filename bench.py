@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- range-images/sec (64x1024, 20-step DPM-Solver++) on N B200s, next to the CPU oracle.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[2], "C3"): RangeLDM KITTI-360 -- 5->4 channel latent UNet
+[128,128,256,256] on 256x16 latents (30.14 M params), 20-step DPM-Solver++(2M), AutoencoderKL 4x
+decoder to a (2,1024,64) range image; per-GPU batch 8 (global batch 64 on 8 GPUs, weak scaling);
+synthetic N(0,1) noise, random-init weights.  One "step" = one batch: the whole trajectory
+(20 x (time-embedding + UNet + scheduler step) + rescale + VAE decode), replayed as one CUDA graph.
+
+  value : images/s, device-timed (CUDA events, max over ranks), noise already resident in HBM
+  e2e   : the same through the public call `LDMPipelineRange.__call__` (CPU randn like the reference,
+          H2D of the noise, sampling, D2H of the finished images into host memory)
+  roofline : tcgen05 conv kernel: algorithmic FLOPs / CUDA-event time of its launches (per-op pass)
+  cpu_baseline : the fp32 PyTorch oracle (restated diffusers modules, reference loop) on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+UNET_C3 = dict(sample_size=[256, 16], in_channels=5, out_channels=4, layers_per_block=2,
+               block_out_channels=[128, 128, 256, 256],
+               down_block_types=["DownBlock2D", "AttnDownBlock2D", "AttnDownBlock2D", "AttnDownBlock2D"],
+               up_block_types=["AttnUpBlock2D", "AttnUpBlock2D", "AttnUpBlock2D", "UpBlock2D"])
+VAE_KITTI = dict(in_channels=2, out_channels=2, down_block_types=["DownEncoderBlock2D"] * 3,
+                 up_block_types=["UpDecoderBlock2D"] * 3, block_out_channels=[64, 128, 256], layers_per_block=2,
+                 latent_channels=4, scaling_factor=0.18215)
+STEPS = 20
+PER_GPU_BATCH = 8
+GFLOP_PER_IMAGE = 20 * 34.07 + 157.46
+METRIC = "range-images/sec (64x1024, 20-step DPM-Solver)"
+WORKLOAD = ("C3 RangeLDM KITTI-360: latent 4x256x16 UNet[128,128,256,256] x 20-step DPM-Solver++(2M, leading) "
+            "+ AutoencoderKL 4x decode -> 2x1024x64")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(gpu_index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().strip().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "power_w_max": max(power), "samples": len(sm)}
+        return out
+
+
+def build_pipeline(dev):
+    import rangeldm_b200 as R
+    torch.manual_seed(0)
+    unet = R.UNet2DModel(**UNET_C3)
+    vae = R.AutoencoderKL(**VAE_KITTI)
+    vae.quant_conv = torch.nn.Identity()
+    vae.post_quant_conv = torch.nn.Identity()
+    for m in (unet, vae):                       # the surgery every shipped config applies (all_circonv)
+        R.replace_down(m)
+        R.replace_conv(m)
+    R.replace_attn(vae)
+    sch = R.DPMSolverMultistepScheduler(timestep_spacing="leading")   # from_config(training DDPM config) -> leading
+    return R.LDMPipelineRange(vae, unet, sch, pos_encoding=True).to(dev)
+
+
+def conv_flops(op):
+    i = op.i
+    B, W, H, Cin, Cout, ks, stride = i[1], i[2], i[3], i[4], i[5], i[6], i[7]
+    return 2.0 * B * (W // stride) * (H // stride) * Cout * Cin * ks * ks
+
+
+def per_op_profile(sampler):
+    """One pass over ONE UNet forward + the decoder, each op bracketed by CUDA events on the launch
+    stream (warm, serialised).  Returns per-kind milliseconds and the conv kernel's FLOPs."""
+    from rangeldm_b200 import _lib
+    lib = _lib.lib()
+    names = {1: "gn_stats", 2: "prep", 3: "conv_tc", 4: "conv_in", 5: "conv_out", 6: "attention", 7: "temb",
+             8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale"}
+    ops = list(sampler.plan.prog.ops) + (list(sampler.dec.prog.ops) if sampler.dec is not None else [])
+    st = _lib.stream_ptr()
+    ms, cnt, flops = {}, {}, 0.0
+    import ctypes
+    for rep in range(2):                        # first repetition warms caches / instruction memory
+        ms, cnt, flops = {}, {}, 0.0
+        for op in ops:
+            arr = (_lib.RldmOp * 1)(op)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(lib.rldm_run(arr, 1, st))
+            e1.record()
+            e1.synchronize()
+            k = names.get(op.kind, str(op.kind))
+            ms[k] = ms.get(k, 0.0) + e0.elapsed_time(e1)
+            cnt[k] = cnt.get(k, 0) + 1
+            if op.kind == _lib.OP_CONV_TC:
+                flops += conv_flops(op)
+    return ms, cnt, flops
+
+
+def run_native(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = PER_GPU_BATCH
+    pipe = build_pipeline(dev)
+    pipe.set_progress_bar_config(disable=True)
+    pipe.scheduler.set_timesteps(STEPS)
+    sampler = pipe._sampler(B, 1, pipe.vae)                 # compiles + captures the trajectory graph
+    from rangeldm_b200.pipelines import make_pos_encoding
+    sampler.cond.copy_(make_pos_encoding(B, 256, 16, dev))
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    noise = torch.randn((B, 4, 256, 16), generator=gen, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    gathered = torch.empty((world,) + tuple(sampler.image.shape), device=dev) if world > 1 else None
+
+    def one_step():
+        sampler.latents.copy_(noise)
+        sampler.graph.replay()
+        if world > 1:       # the only collective: collect the finished range images (north star)
+            dist.all_gather_into_tensor(gathered, sampler.image)
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local) if rank == 0 else None
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()                                       # L2 flush between timed iterations (untimed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        one_step()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clk = clocks.stop() if clocks else None
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * args.steps * B / (total_ms / 1e3)
+
+    # ---- end to end through the public pipeline call: CPU randn -> H2D -> sample -> D2H ----
+    host_img = torch.empty(tuple(sampler.image.shape), pin_memory=True)
+    g2 = torch.Generator().manual_seed(1000 + rank)
+    for _ in range(2):
+        host_img.copy_(pipe(batch_size=B, generator=g2, num_inference_steps=STEPS, output_type="torch"))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        img = pipe(batch_size=B, generator=g2, num_inference_steps=STEPS, output_type="torch")
+        host_img.copy_(img, non_blocking=False)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps * B / float(t.item())
+
+    out = None
+    if rank == 0:
+        burst, sustained, hbm, src = peaks()
+        ms, cnt, flops = per_op_profile(sampler)
+        conv_ms = ms.get("conv_tc", 0.0)
+        all_ms = sum(ms.values())
+        achieved = flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+        launches_per_step = sampler.gpu_launches
+        out = {
+            "metric": METRIC, "value": round(value, 3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp16 x fp16 -> fp32 (tcgen05 kind::f16), fp32 elsewhere",
+            "data": "synthetic N(0,1) noise, random-init weights",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "sampler_steps": STEPS,
+                       "parallelism": f"dp{world} (batch-axis shards, no hot-path collective; "
+                                      f"all_gather of finished images)" if world > 1 else "single GPU",
+                       "l2": "256 MiB L2 flush between timed iterations; working set ~1 GB > 126 MB L2",
+                       "gflop_per_image": GFLOP_PER_IMAGE},
+            "e2e": {"value": round(e2e_value, 3), "unit": "images/s",
+                    "h2d_bytes_per_step": int(noise.numel() * 4), "d2h_bytes_per_step": int(host_img.numel() * 4)},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "achieved_tflops_whole_job": round(value / world * GFLOP_PER_IMAGE / 1e3, 2),
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM circular conv)",
+                         "achieved": round(achieved, 2), "peak": burst, "unit": "TFLOP/s",
+                         "frac": round(achieved / burst, 4), "peak_source": f"{src} bf16 burst (per-op timed pass)",
+                         "frac_of_sustained": round(achieved / sustained, 4), "traffic": None,
+                         "launches": cnt.get("conv_tc", 0), "avg_launch_us": round(1e3 * conv_ms / max(cnt.get("conv_tc", 1), 1), 2),
+                         "share_of_step": round(conv_ms / all_ms, 4) if all_ms else None,
+                         "per_kind_ms_one_unet_plus_decoder": {k: round(v, 4) for k, v in sorted(ms.items())}},
+            "clocks": clk,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_reference(samples=args.cpu_samples)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+def cpu_reference(samples=2, threads=None):
+    """The fp32 PyTorch oracle of the reference path (restated diffusers UNet2DModel + DPM-Solver++,
+    sgm-equivalent Decoder, `ldm/pipelines.py` loop) on the host cores: whole C3 trajectories, batch 1."""
+    from oracle import nets, pipeline, schedulers
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    unet = nets.OracleUNet2DModel(**nets.UNET_C3).eval()
+    vae = nets.OracleAutoencoderKL().eval()
+    sch = schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading")
+    g = torch.Generator().manual_seed(0)
+    pipeline.ldm_sample(unet, vae, sch, torch.randn((1, 4, 256, 16), generator=g), 2)        # warm-up (2 steps)
+    t0 = time.perf_counter()
+    for _ in range(samples):
+        pipeline.ldm_sample(unet, vae, sch, torch.randn((1, 4, 256, 16), generator=g), STEPS)
+    dt = time.perf_counter() - t0
+    return {"value": round(samples / dt, 4), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{samples} full C3 images (batch 1, 20 DPM-Solver++ steps + VAE decode), fp32 torch "
+                      f"{torch.__version__}, {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    n = max(1, min(args.steps, 4))
+    t_all = time.perf_counter()
+    base = cpu_reference(samples=n)
+    out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "images/s", "n_gpus": args.gpus,
+           "steps": n, "warmup": 1, "ms_per_step": round(1e3 / base["value"], 2), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic N(0,1) noise, random-init weights",
+           "config": {"workload": WORKLOAD, "per_gpu_batch": 1, "note": "CPU oracle port of the reference path; "
+                      "diffusers is not installable here (SURVEY.md 8c); one step = one full image"},
+           "cpu_baseline": base,
+           "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": round(time.perf_counter() - t_all, 1)}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-samples", type=int, default=2)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

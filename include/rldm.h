@@ -46,16 +46,21 @@ int rldm_gn_stats(const float* x0, int c0, const float* x1, int c1, double* sums
  * Replaces F.group_norm's normalise half + F.silu (`model.py:343-345,351-352`), torch.cat of the
  * skip connection (UpBlock2D) and F.interpolate(scale_factor=2, "nearest") (`model.py:121-122`).
  * x0:(B,W,H,C0) [+x1:(B,W,H,C1)] fp32 cl.  sums==NULL -> no normalisation (raw cast).
- * out:(B,W*up,H*up,C0+C1) fp16 cl, up in {1,2}. */
+ * out:(B,W*up,H*up,C0+C1) fp16 cl, up in {1,2}.  out_lo (optional, same shape): the residual
+ * y - fp16(y), so that out + out_lo carries ~22 significant bits (split-fp16 operand). */
 int rldm_prep(const float* x0, int c0, const float* x1, int c1, const double* sums,
               const float* gamma, const float* beta, float eps, int G, int silu, int up,
-              uint16_t* out, int B, int W, int H, void* stream);
+              uint16_t* out, uint16_t* out_lo, int B, int W, int H, void* stream);
 
 /* ---- the hot op: circular implicit-GEMM convolution on tcgen05 ------------------------------
  * Replaces `Conv2d._conv_forward` (`ldm/utils.py:40-58`, twin `vae/sgm/.../model.py:93-108`):
  * wrap-pad W, zero-pad H, F.conv2d(pad 0); and the nn.Linear projections of Attention (ks=1).
  *   x   : (B, W, H, Cin) fp16 cl, Cin % 64 == 0
- *   wgt : [ks*ks][Cout][Cin] fp16, tap = kw_index_along_W * ks + k_index_along_H
+ *   x_lo: NULL -> plain fp16 operands (1 MMA per K step, 11-bit significands);
+ *         else the low-order half of a split-fp16 activation (see rldm_prep) and `wgt` must hold
+ *         TWO planes [hi|lo]: the kernel issues Ah*Wh + Al*Wh + Ah*Wl into one fp32 accumulator
+ *         ("fp16x3", ~fp32-accurate products; the default of the engine)
+ *   wgt : [planes][ks*ks][Cout][Cin] fp16, tap = index_along_W * ks + index_along_H
  *         (torch weight (Cout,Cin,kh,kw): kh <-> W, kw <-> H)
  *   out : (B, Wo, Ho, Cout) fp32 cl;  Wo = W/stride, Ho = H/stride
  *   pad_lo: taps read input (stride*wo + i - pad_lo) mod W, stride*ho + j - pad_lo (0 outside H).
@@ -67,13 +72,13 @@ int rldm_prep(const float* x0, int c0, const float* x1, int c1, const double* su
  *         split_k CTAs per tile which atomically accumulate into `out` (zeroed by this call);
  *         `residual` must then not alias `out`.
  * Requires Ho a power of two <= 128 and Cout % 64 == 0. */
-int rldm_conv_tc(const uint16_t* x, const uint16_t* wgt, const float* bias, const float* temb,
+int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias, const float* temb,
                  int temb_stride, const float* residual, float* out, int B, int W, int H, int Cin,
                  int Cout, int ks, int stride, int pad_lo, int circular, int split_k, void* stream);
 
 /* CUDA-core restatement of rldm_conv_tc with the identical contract (split_k ignored); used by the
  * GPU tests to isolate tensor-core descriptor bugs from precision, never by the product path. */
-int rldm_conv_ref(const uint16_t* x, const uint16_t* wgt, const float* bias, const float* temb,
+int rldm_conv_ref(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias, const float* temb,
                   int temb_stride, const float* residual, float* out, int B, int W, int H, int Cin,
                   int Cout, int ks, int stride, int pad_lo, int circular, void* stream);
 
@@ -84,16 +89,16 @@ int rldm_conv_ref(const uint16_t* x, const uint16_t* wgt, const float* bias, con
 int rldm_conv_in(const float* x0, int c0, const float* x1, int c1, const float* wgt,
                  const float* bias, float* out, int B, int W, int H, int Cout, int circular,
                  void* stream);
-/* conv_out: x (B,W,H,Cin) fp16 cl (already GN+SiLU'd by rldm_prep) -> out (B,Cout,W,H) fp32 REF
- * layout, Cout <= 8.  wgt [9][Cout][Cin] fp32. */
-int rldm_conv_out(const uint16_t* x, const float* wgt, const float* bias, float* out, int B, int W,
+/* conv_out: x (+ optional x_lo) (B,W,H,Cin) fp16 cl (already GN+SiLU'd by rldm_prep) -> out
+ * (B,Cout,W,H) fp32 REF layout, Cout in {2,4,8}.  wgt [9][Cout][Cin] fp32. */
+int rldm_conv_out(const uint16_t* x, const uint16_t* x_lo, const float* wgt, const float* bias, float* out, int B, int W,
                   int H, int Cin, int Cout, int circular, void* stream);
 
 /* ---- attention core ----------------------------------------------------------------------
  * Replaces F.scaled_dot_product_attention in AttnProcessor2_0: heads of
  * dim 8, softmax(QK^T/sqrt(8))V, no mask.  qkv:(B,N,3C) fp32 (q|k|v along the last dim, head h at
- * channels [8h,8h+8)); out:(B,N,C) fp16 (feeds the to_out projection). */
-int rldm_attention(const float* qkv, uint16_t* out, int B, int N, int C, void* stream);
+ * channels [8h,8h+8)); out (+ optional out_lo, split-fp16):(B,N,C) fp16 (feeds the to_out projection). */
+int rldm_attention(const float* qkv, uint16_t* out, uint16_t* out_lo, int B, int N, int C, void* stream);
 
 /* ---- time embedding -----------------------------------------------------------------------
  * Replaces Timesteps + TimestepEmbedding + every ResnetBlock2D.time_emb_proj(silu(emb))

@@ -48,7 +48,7 @@ gn_stats_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ 
       s[2] += v.z; ss[2] += v.z * v.z;
       s[3] += v.w; ss[3] += v.w * v.w;
     }
-    if (cpg >= 4) {
+    if ((cpg & 3) == 0) {   // the whole quad lies in one group
       atomicAdd(&sh[c / cpg], (double)s[0] + (double)s[1] + (double)s[2] + (double)s[3]);
       atomicAdd(&sh[G + c / cpg], (double)ss[0] + (double)ss[1] + (double)ss[2] + (double)ss[3]);
     } else {
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256)
 prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
             const double* __restrict__ sums, const float* __restrict__ gamma,
             const float* __restrict__ beta, float eps, int G, int silu, int up,
-            __half* __restrict__ out, int W, int H, int pix_per_block) {
+            __half* __restrict__ out, __half* __restrict__ out_lo, int W, int H, int pix_per_block) {
   extern __shared__ float shf[];  // scale[C], shift[C]
   const int C = c0 + c1;
   const int b = blockIdx.y;
@@ -141,14 +141,24 @@ prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, 
     __align__(16) __half2 h[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * out_pix + po) * C + c) =
-        *reinterpret_cast<const uint4*>(h);
+    const size_t o = (static_cast<size_t>(b) * out_pix + po) * C + c;
+    *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(h);
+    if (out_lo) {   // residual of the fp16 rounding: x = hi + lo to ~22 bits
+      __align__(16) __half2 l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 hf = __half22float2(h[j]);
+        l[j] = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+      }
+      *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(l);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // conv_ref: one thread per (output pixel, output channel); same contract as conv_tc.
-__global__ void conv_ref_kernel(const __half* __restrict__ x, const __half* __restrict__ wgt,
+__global__ void conv_ref_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo,
+                                const __half* __restrict__ wgt,
                                 const float* __restrict__ bias, const float* __restrict__ temb,
                                 int temb_stride, const float* __restrict__ residual,
                                 float* __restrict__ out, int B, int W, int H, int Cin, int Cout,
@@ -170,11 +180,17 @@ __global__ void conv_ref_kernel(const __half* __restrict__ x, const __half* __re
     for (int j = 0; j < ks; ++j) {
       const int h = stride * ho + j - pad_lo;
       if (h < 0 || h >= H) continue;
-      const __half* xr = x + ((static_cast<size_t>(b) * W + w) * H + h) * Cin;
+      const size_t xo = ((static_cast<size_t>(b) * W + w) * H + h) * Cin;
       const __half* wr = wgt + (static_cast<size_t>(i * ks + j) * Cout + n) * Cin;
+      const __half* wl = wr + static_cast<size_t>(ks) * ks * Cout * Cin;   // low-order plane
       for (int c = 0; c < Cin; c += 2) {
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(xr + c));
-        const float2 w2 = __half22float2(*reinterpret_cast<const __half2*>(wr + c));
+        float2 a = __half22float2(*reinterpret_cast<const __half2*>(x + xo + c));
+        float2 w2 = __half22float2(*reinterpret_cast<const __half2*>(wr + c));
+        if (x_lo) {
+          const float2 al = __half22float2(*reinterpret_cast<const __half2*>(x_lo + xo + c));
+          const float2 wl2 = __half22float2(*reinterpret_cast<const __half2*>(wl + c));
+          a.x += al.x; a.y += al.y; w2.x += wl2.x; w2.y += wl2.y;
+        }
         acc = fmaf(a.x, w2.x, acc);
         acc = fmaf(a.y, w2.y, acc);
       }
@@ -237,7 +253,7 @@ conv_in_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x
 // lanes split the input channels, butterfly-reduce the Cout partial sums.
 template <int COUT>
 __global__ void __launch_bounds__(256)
-conv_out_kernel(const __half* __restrict__ x, const float* __restrict__ wgt,
+conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, const float* __restrict__ wgt,
                 const float* __restrict__ bias, float* __restrict__ out, int B, int W, int H,
                 int Cin, int circular) {
   const int lane = threadIdx.x & 31;
@@ -259,10 +275,14 @@ conv_out_kernel(const __half* __restrict__ x, const float* __restrict__ wgt,
     for (int j = 0; j < 3; ++j) {
       const int hj = h + j - 1;
       if (hj < 0 || hj >= H) continue;
-      const __half* xr = x + ((static_cast<size_t>(b) * W + wi) * H + hj) * Cin;
+      const size_t xo = ((static_cast<size_t>(b) * W + wi) * H + hj) * Cin;
       const float* wr = wgt + static_cast<size_t>(i * 3 + j) * COUT * Cin;
       for (int c = lane * 2; c < Cin; c += 64) {
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(xr + c));
+        float2 a = __half22float2(*reinterpret_cast<const __half2*>(x + xo + c));
+        if (x_lo) {
+          const float2 al = __half22float2(*reinterpret_cast<const __half2*>(x_lo + xo + c));
+          a.x += al.x; a.y += al.y;
+        }
 #pragma unroll
         for (int n = 0; n < COUT; ++n) {
           const float2 wv = __ldg(reinterpret_cast<const float2*>(wr + n * Cin + c));
@@ -292,7 +312,8 @@ conv_out_kernel(const __half* __restrict__ x, const float* __restrict__ wgt,
 // them with broadcast reads (two passes per tile are avoided by an online softmax).
 constexpr int kAttnKT = 512;
 __global__ void __launch_bounds__(128)
-attention_kernel(const float* __restrict__ qkv, __half* __restrict__ out, int N, int C) {
+attention_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half* __restrict__ out_lo, int N,
+                 int C) {
   __shared__ float4 sk[kAttnKT * 2 + 16];
   __shared__ float4 sv[kAttnKT * 2 + 16];
   const int b = blockIdx.z, hd = blockIdx.y;
@@ -356,8 +377,17 @@ attention_kernel(const float* __restrict__ qkv, __half* __restrict__ out, int N,
     __align__(16) __half2 h[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(acc[2 * j] * inv, acc[2 * j + 1] * inv);
-    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * N + qi) * C + hd * 8) =
-        *reinterpret_cast<const uint4*>(h);
+    const size_t o = (static_cast<size_t>(b) * N + qi) * C + hd * 8;
+    *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(h);
+    if (out_lo) {
+      __align__(16) __half2 l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 hf = __half22float2(h[j]);
+        l[j] = __floats2half2_rn(acc[2 * j] * inv - hf.x, acc[2 * j + 1] * inv - hf.y);
+      }
+      *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(l);
+    }
   }
 }
 
@@ -505,7 +535,7 @@ extern "C" int rldm_gn_stats(const float* x0, int c0, const float* x1, int c1, d
 
 extern "C" int rldm_prep(const float* x0, int c0, const float* x1, int c1, const double* sums,
                          const float* gamma, const float* beta, float eps, int G, int silu, int up,
-                         uint16_t* out, int B, int W, int H, void* stream) {
+                         uint16_t* out, uint16_t* out_lo, int B, int W, int H, void* stream) {
   const int C = c0 + c1;
   RLDM_CHECK(c0 % 8 == 0 && c1 % 8 == 0, "prep: channels must be multiples of 8 (c0=%d c1=%d)", c0, c1);
   RLDM_CHECK(up == 1 || up == 2, "prep: up must be 1 or 2");
@@ -516,18 +546,20 @@ extern "C" int rldm_prep(const float* x0, int c0, const float* x1, int c1, const
   if (ppb < 8) ppb = 8;
   chunks = (out_pix + ppb - 1) / ppb;
   prep_kernel<<<dim3(chunks, B), 256, 2 * C * sizeof(float), as_stream(stream)>>>(
-      x0, c0, x1, c1, sums, gamma, beta, eps, G, silu, up, reinterpret_cast<__half*>(out), W, H, ppb);
+      x0, c0, x1, c1, sums, gamma, beta, eps, G, silu, up, reinterpret_cast<__half*>(out),
+      reinterpret_cast<__half*>(out_lo), W, H, ppb);
   RLDM_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int rldm_conv_ref(const uint16_t* x, const uint16_t* wgt, const float* bias,
+extern "C" int rldm_conv_ref(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias,
                              const float* temb, int temb_stride, const float* residual, float* out,
                              int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
                              int circular, void* stream) {
   const size_t total = static_cast<size_t>(B) * (W / stride) * (H / stride) * Cout;
   conv_ref_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(wgt), bias, temb,
+      reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(x_lo),
+      reinterpret_cast<const __half*>(wgt), bias, temb,
       temb_stride, residual, out, B, W, H, Cin, Cout, ks, stride, pad_lo, circular);
   RLDM_LAUNCH_CHECK();
   return 0;
@@ -546,28 +578,30 @@ extern "C" int rldm_conv_in(const float* x0, int c0, const float* x1, int c1, co
   return 0;
 }
 
-extern "C" int rldm_conv_out(const uint16_t* x, const float* wgt, const float* bias, float* out,
+extern "C" int rldm_conv_out(const uint16_t* x, const uint16_t* x_lo, const float* wgt, const float* bias, float* out,
                              int B, int W, int H, int Cin, int Cout, int circular, void* stream) {
   RLDM_CHECK(Cin % 2 == 0, "conv_out: Cin must be even");
   const size_t total_pix = static_cast<size_t>(B) * W * H;
   const unsigned grid = static_cast<unsigned>((total_pix + 7) / 8);
   const __half* xh = reinterpret_cast<const __half*>(x);
+  const __half* xl = reinterpret_cast<const __half*>(x_lo);
   cudaStream_t st = as_stream(stream);
   switch (Cout) {
-    case 2: conv_out_kernel<2><<<grid, 256, 0, st>>>(xh, wgt, bias, out, B, W, H, Cin, circular); break;
-    case 4: conv_out_kernel<4><<<grid, 256, 0, st>>>(xh, wgt, bias, out, B, W, H, Cin, circular); break;
-    case 8: conv_out_kernel<8><<<grid, 256, 0, st>>>(xh, wgt, bias, out, B, W, H, Cin, circular); break;
+    case 2: conv_out_kernel<2><<<grid, 256, 0, st>>>(xh, xl, wgt, bias, out, B, W, H, Cin, circular); break;
+    case 4: conv_out_kernel<4><<<grid, 256, 0, st>>>(xh, xl, wgt, bias, out, B, W, H, Cin, circular); break;
+    case 8: conv_out_kernel<8><<<grid, 256, 0, st>>>(xh, xl, wgt, bias, out, B, W, H, Cin, circular); break;
     default: RLDM_CHECK(false, "conv_out: Cout must be 2, 4 or 8 (got %d)", Cout);
   }
   RLDM_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int rldm_attention(const float* qkv, uint16_t* out, int B, int N, int C, void* stream) {
+extern "C" int rldm_attention(const float* qkv, uint16_t* out, uint16_t* out_lo, int B, int N, int C,
+                              void* stream) {
   RLDM_CHECK(C % 8 == 0, "attention: C %% 8 != 0");
   const int threads = N >= 128 ? 128 : ((N + 31) / 32) * 32;
   attention_kernel<<<dim3((N + threads - 1) / threads, C / 8, B), threads, 0, as_stream(stream)>>>(
-      qkv, reinterpret_cast<__half*>(out), N, C);
+      qkv, reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C);
   RLDM_LAUNCH_CHECK();
   return 0;
 }
@@ -627,15 +661,15 @@ extern "C" int rldm_run(const rldm_op* ops, int n_ops, void* stream) {
       case RLDM_OP_PREP:
         rc = rldm_prep((const float*)o.p[0], o.i[0], (const float*)o.p[1], o.i[1], (const double*)o.p[2],
                        (const float*)o.p[3], (const float*)o.p[4], o.f[0], o.i[2], o.i[3], o.i[4],
-                       (uint16_t*)o.p[5], o.i[5], o.i[6], o.i[7], stream);
+                       (uint16_t*)o.p[5], (uint16_t*)o.p[6], o.i[5], o.i[6], o.i[7], stream);
         break;
       case RLDM_OP_CONV_TC:
-        rc = rldm_conv_tc((const uint16_t*)o.p[0], (const uint16_t*)o.p[1], (const float*)o.p[2],
+        rc = rldm_conv_tc((const uint16_t*)o.p[0], (const uint16_t*)o.p[6], (const uint16_t*)o.p[1], (const float*)o.p[2],
                           (const float*)o.p[3], o.i[0], (const float*)o.p[4], (float*)o.p[5], o.i[1],
                           o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], o.i[7], o.i[8], o.i[9], o.i[10], stream);
         break;
       case RLDM_OP_CONV_REF:
-        rc = rldm_conv_ref((const uint16_t*)o.p[0], (const uint16_t*)o.p[1], (const float*)o.p[2],
+        rc = rldm_conv_ref((const uint16_t*)o.p[0], (const uint16_t*)o.p[6], (const uint16_t*)o.p[1], (const float*)o.p[2],
                            (const float*)o.p[3], o.i[0], (const float*)o.p[4], (float*)o.p[5], o.i[1],
                            o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], o.i[7], o.i[8], o.i[9], stream);
         break;
@@ -644,11 +678,11 @@ extern "C" int rldm_run(const rldm_op* ops, int n_ops, void* stream) {
                           (const float*)o.p[3], (float*)o.p[4], o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], stream);
         break;
       case RLDM_OP_CONV_OUT:
-        rc = rldm_conv_out((const uint16_t*)o.p[0], (const float*)o.p[1], (const float*)o.p[2],
+        rc = rldm_conv_out((const uint16_t*)o.p[0], (const uint16_t*)o.p[4], (const float*)o.p[1], (const float*)o.p[2],
                            (float*)o.p[3], o.i[0], o.i[1], o.i[2], o.i[3], o.i[4], o.i[5], stream);
         break;
       case RLDM_OP_ATTENTION:
-        rc = rldm_attention((const float*)o.p[0], (uint16_t*)o.p[1], o.i[0], o.i[1], o.i[2], stream);
+        rc = rldm_attention((const float*)o.p[0], (uint16_t*)o.p[1], (uint16_t*)o.p[2], o.i[0], o.i[1], o.i[2], stream);
         break;
       case RLDM_OP_TEMB:
         rc = rldm_temb((const float*)o.p[0], (const float*)o.p[1], (const float*)o.p[2],

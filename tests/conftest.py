@@ -30,7 +30,17 @@ def golden():
     return load
 
 
-def relerr(a, b):
-    """The parity metric of SURVEY.md 8d: max|a-b| / max|b|."""
+def relerr(a, b, name=None):
+    """The parity metric of SURVEY.md 8d: max|a-b| / max|b|.  Named measurements are appended to
+    gpurun_out/parity.jsonl so the achieved margins can be quoted."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
-    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+    e = ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+    if name is not None:
+        try:
+            import json
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "parity.jsonl"), "a") as f:
+                f.write(json.dumps({"name": name, "relerr": e}) + "\n")
+        except OSError:
+            pass
+    return e

@@ -1,0 +1,276 @@
+"""GPU parity tests of the individual sm_100a kernels, called through the C ABI (ctypes), against
+the CPU oracle / plain torch fp32 on the same seeded inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from rangeldm_b200 import _lib
+    _lib.lib()
+    return _lib
+
+
+def cl(x):      # (B,C,W,H) -> (B,W,H,C)
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def ref_layout(x):   # (B,W,H,C) -> (B,C,W,H)
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def pack_w(w, split=False):  # (Cout,Cin,kW,kH) -> [planes][tap][Cout][Cin] fp16
+    co, ci, k0, k1 = w.shape
+    t = w.permute(2, 3, 0, 1).reshape(k0 * k1, co, ci)
+    hi = t.half()
+    if not split:
+        return hi.contiguous()
+    return torch.cat([hi, (t - hi.float()).half()], 0).contiguous()
+
+
+def split_half(x):
+    hi = x.half()
+    return hi, (x - hi.float()).half()
+
+
+def oracle_conv(x, w, b, stride, pad_lo, ks, circular=True):
+    """x (B,C,W,H) fp32; reference semantics `ldm/utils.py:46-49` (+ asymmetric `:109-111`)."""
+    if ks == 1:
+        return F.conv2d(x, w, b, stride)
+    if pad_lo == 1:
+        if circular:
+            x = F.pad(x, (0, 0, 1, 1), mode="circular")
+            x = F.pad(x, (1, 1, 0, 0))
+        else:
+            x = F.pad(x, (1, 1, 1, 1))
+    else:
+        x = F.pad(x, (0, 0, 0, 1), mode="circular") if circular else F.pad(x, (0, 0, 0, 1))
+        x = F.pad(x, (0, 1, 0, 0))
+    return F.conv2d(x, w, b, stride)
+
+
+CONV_CASES = [
+    # B, W, H, Cin, Cout, ks, stride, pad_lo, split_k, circular
+    (2, 16, 16, 64, 64, 3, 1, 1, 1, 1),
+    (1, 32, 8, 128, 128, 3, 1, 1, 1, 1),
+    (1, 32, 8, 128, 128, 3, 1, 1, 3, 1),
+    (2, 16, 4, 128, 256, 3, 1, 1, 0, 1),      # Ho = 4: column boxes smaller than a swizzle atom
+    (3, 8, 2, 256, 128, 3, 1, 1, 0, 1),       # Ho = 2, partial last tile (M = 48)
+    (1, 4, 64, 64, 64, 3, 1, 1, 1, 1),        # Ho = 64 (decoder top level geometry)
+    (1, 32, 16, 128, 128, 3, 2, 1, 1, 1),     # UNet Downsample2D(padding=1)
+    (1, 32, 16, 64, 64, 3, 2, 0, 1, 1),       # VAE-encoder Downsample2D(padding=0), asymmetric pad
+    (2, 16, 8, 128, 384, 1, 1, 0, 1, 1),      # attention qkv projection as a 1x1 "conv"
+    (1, 16, 8, 384, 128, 3, 1, 1, 0, 1),      # skip-concat width
+    (1, 16, 8, 64, 64, 3, 1, 1, 1, 0),        # zero padding on W as well (no surgery)
+    (8, 256, 16, 128, 128, 3, 1, 1, 0, 1),    # C3 top-level layer at full size
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_tc_matches_cuda_core_restatement_and_oracle(L, case):
+    B, W, H, Cin, Cout, ks, stride, pad_lo, split, circ = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(B, Cin, W, H, generator=g)
+    w = torch.randn(Cout, Cin, ks, ks, generator=g) / (Cin * ks * ks) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    temb = torch.randn(B, Cout + 8, generator=g)
+    Wo, Ho = W // stride, H // stride
+    res = torch.randn(B, Cout, Wo, Ho, generator=g)
+    xh = cl(x).half().cuda()
+    wt = pack_w(w).cuda()
+    bd, td, rd = b.cuda(), temb.cuda(), cl(res).cuda()
+    out_tc = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
+    out_rf = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
+    L.call("rldm_conv_tc", L.ptr(xh), None, L.ptr(wt), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out_tc),
+           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split)
+    L.call("rldm_conv_ref", L.ptr(xh), None, L.ptr(wt), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out_rf),
+           B, W, H, Cin, Cout, ks, stride, pad_lo, circ)
+    torch.cuda.synchronize()
+    # same fp16 operands on both sides: only the fp32 summation order differs
+    assert relerr(out_tc, out_rf) < 2e-5
+    # oracle with fp16-rounded operands (exact products in fp32)
+    y = oracle_conv(xh.float().cpu().permute(0, 3, 1, 2), wt.float().cpu().reshape(ks, ks, Cout, Cin).permute(2, 3, 0, 1),
+                    b, stride, pad_lo, ks, bool(circ)) + temb[:, :Cout, None, None] + res
+    assert relerr(ref_layout(out_tc.cpu()), y) < 2e-5
+    # and against the un-rounded fp32 oracle within the north-star tolerance
+    y32 = oracle_conv(x, w, b, stride, pad_lo, ks, bool(circ)) + temb[:, :Cout, None, None] + res
+    assert relerr(ref_layout(out_tc.cpu()), y32) < 1e-3
+    # split-fp16 ("fp16x3", the engine default): hi+lo operands, 3 MMAs per K step -> ~fp32 accuracy
+    xh2, xl2 = split_half(cl(x))
+    xh2, xl2, wt2 = xh2.cuda(), xl2.cuda(), pack_w(w, split=True).cuda()
+    out3 = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
+    out3r = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
+    L.call("rldm_conv_tc", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out3),
+           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split)
+    L.call("rldm_conv_ref", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd),
+           L.ptr(out3r), B, W, H, Cin, Cout, ks, stride, pad_lo, circ)
+    assert relerr(out3, out3r) < 1e-5
+    assert relerr(ref_layout(out3.cpu()), y32) < 1e-5
+
+
+def test_conv_tc_golden_reference_conv(L, golden):
+    g = golden("circ_conv.pt")                # produced by the reference's own Conv2d
+    for wk, bk, yk, stride in (("w1", "b1", "y1", 1), ("w2", "b2", "y2", 2)):
+        x, w, b, y = g["x"], g[wk], g[bk], g[yk]
+        B, Cin, W, H = x.shape
+        Cout = w.shape[0]
+        out = torch.empty(B, W // stride, H // stride, Cout, device="cuda")
+        xh, wt, bd = cl(x).half().cuda(), pack_w(w).cuda(), b.cuda()     # keep the operands alive across the call
+        L.call("rldm_conv_tc", L.ptr(xh), None, L.ptr(wt), L.ptr(bd), None, 0, None,
+               L.ptr(out), B, W, H, Cin, Cout, 3, stride, 1, 1, 0)
+        assert relerr(ref_layout(out.cpu()), y) < 1e-3
+        xh2, xl2 = split_half(cl(x))
+        xh2, xl2, wt2 = xh2.cuda(), xl2.cuda(), pack_w(w, split=True).cuda()
+        L.call("rldm_conv_tc", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), None, 0, None,
+               L.ptr(out), B, W, H, Cin, Cout, 3, stride, 1, 1, 0)
+        assert relerr(ref_layout(out.cpu()), y) < 1e-5
+
+
+def test_conv_tc_rejects_bad_shapes(L):
+    x = torch.zeros(1, 8, 8, 48, dtype=torch.half, device="cuda")
+    with pytest.raises(L.RldmError):
+        L.call("rldm_conv_tc", L.ptr(x), None, L.ptr(x), None, None, 0, None, L.ptr(x), 1, 8, 8, 48, 64, 3, 1, 1, 1, 0)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 0, 16, 8, 1), (2, 128, 256, 8, 4, 1), (1, 256, 128, 16, 2, 2),
+                                   (2, 64, 0, 32, 64, 1), (3, 512, 512, 4, 2, 1)])
+def test_gn_stats_and_prep(L, shape):
+    B, C0, C1, W, H, up = shape
+    g = torch.Generator().manual_seed(C0 + C1 + W)
+    x0 = torch.randn(B, C0, W, H, generator=g) * 2 + 0.5
+    x1 = torch.randn(B, C1, W, H, generator=g) - 1 if C1 else None
+    C = C0 + C1
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    G, eps = 32, 1e-5
+    sums = torch.zeros(B, G, 2, dtype=torch.float64, device="cuda")
+    x0d = cl(x0).cuda()
+    x1d = cl(x1).cuda() if C1 else None
+    L.call("rldm_gn_stats", L.ptr(x0d), C0, L.ptr(x1d), C1, L.ptr(sums), B, W * H, G)
+    xc = torch.cat([x0, x1], 1) if C1 else x0
+    xg = xc.double().reshape(B, G, -1)
+    assert torch.allclose(sums[:, :, 0].cpu(), xg.sum(-1), rtol=1e-6, atol=1e-4)
+    assert torch.allclose(sums[:, :, 1].cpu(), (xg * xg).sum(-1), rtol=1e-6, atol=1e-4)
+    out = torch.empty(B, W * up, H * up, C, dtype=torch.half, device="cuda")
+    gd, bd = gamma.cuda(), beta.cuda()
+    out_lo = torch.empty_like(out)
+    L.call("rldm_prep", L.ptr(x0d), C0, L.ptr(x1d), C1, L.ptr(sums), L.ptr(gd), L.ptr(bd), eps, G, 1,
+           up, L.ptr(out), L.ptr(out_lo), B, W, H)
+    y = F.silu(F.group_norm(xc, G, gamma, beta, eps))
+    if up == 2:
+        y = F.interpolate(y, scale_factor=2.0, mode="nearest")
+    assert relerr(ref_layout(out.float().cpu()), y) < 1.5e-3          # fp16 output rounding
+    assert relerr(ref_layout((out.float() + out_lo.float()).cpu()), y) < 5e-6      # hi + lo: split-fp16
+    # raw cast path (no norm, no silu)
+    L.call("rldm_prep", L.ptr(x0d), C0, L.ptr(x1d), C1, None, None, None, 0.0, 0, 0, up, L.ptr(out), None, B, W, H)
+    yr = F.interpolate(xc, scale_factor=2.0, mode="nearest") if up == 2 else xc
+    assert torch.equal(ref_layout(out.cpu()), yr.half())
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64), (1, 256, 128), (2, 1024, 128), (1, 40, 64)])
+def test_attention_core(L, shape):
+    B, N, C = shape
+    g = torch.Generator().manual_seed(N)
+    qkv = torch.randn(B, N, 3 * C, generator=g)
+    out = torch.empty(B, N, C, dtype=torch.half, device="cuda")
+    qd = qkv.cuda()
+    out_lo = torch.empty_like(out)
+    L.call("rldm_attention", L.ptr(qd), L.ptr(out), L.ptr(out_lo), B, N, C)
+    q, k, v = qkv.split(C, dim=-1)
+    sp = lambda t: t.view(B, N, C // 8, 8).transpose(1, 2)
+    y = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(B, N, C)
+    assert relerr(out.float().cpu(), y) < 1e-3
+    assert relerr((out.float() + out_lo.float()).cpu(), y) < 1e-5
+
+
+def test_time_embedding(L):
+    from oracle import nets
+    torch.manual_seed(0)
+    B, D0, D4 = 3, 128, 512
+    te = nets.TimestepEmbedding(D0, D4)
+    projs = [torch.nn.Linear(D4, c) for c in (128, 256, 128)]
+    t = torch.tensor([999.0, 47.0, 0.0])
+    wp = torch.cat([p.weight for p in projs]).detach()
+    bp = torch.cat([p.bias for p in projs]).detach()
+    T = wp.shape[0]
+    scratch = torch.empty(B, D4, device="cuda")
+    out = torch.empty(B, T, device="cuda")
+    dv = [x.detach().cuda().contiguous() for x in (t, te.linear_1.weight, te.linear_1.bias, te.linear_2.weight,
+                                                   te.linear_2.bias, wp, bp)]
+    L.call("rldm_temb", *[L.ptr(x) for x in dv], L.ptr(scratch), L.ptr(out), B, D0, D4, T)
+    with torch.no_grad():
+        emb = te(nets.sinusoidal_timestep(t, D0))
+        y = torch.cat([p(F.silu(emb)) for p in projs], dim=1)
+    assert relerr(out.cpu(), y) < 2e-5
+
+
+def test_conv_in_and_conv_out(L):
+    g = torch.Generator().manual_seed(9)
+    B, W, H = 2, 16, 8
+    lat, pe = torch.randn(B, 4, W, H, generator=g), torch.randn(B, 1, W, H, generator=g)
+    w = torch.randn(128, 5, 3, 3, generator=g) * 0.2
+    b = torch.randn(128, generator=g)
+    out = torch.empty(B, W, H, 128, device="cuda")
+    ld, pd, wd, bd = lat.cuda(), pe.cuda(), w.permute(2, 3, 1, 0).contiguous().cuda(), b.cuda()
+    L.call("rldm_conv_in", L.ptr(ld), 4, L.ptr(pd), 1, L.ptr(wd), L.ptr(bd), L.ptr(out), B, W, H, 128, 1)
+    y = oracle_conv(torch.cat([lat, pe], 1), w, b, 1, 1, 3)
+    assert relerr(ref_layout(out.cpu()), y) < 1e-5
+    for Cout, Cin in ((4, 128), (2, 64)):
+        x = torch.randn(B, Cin, W, H, generator=g)
+        w = torch.randn(Cout, Cin, 3, 3, generator=g) * 0.1
+        b = torch.randn(Cout, generator=g)
+        xh = cl(x).half().cuda()
+        out = torch.empty(B, Cout, W, H, device="cuda")
+        wd, bd = w.permute(2, 3, 0, 1).contiguous().cuda(), b.cuda()
+        L.call("rldm_conv_out", L.ptr(xh), None, L.ptr(wd), L.ptr(bd), L.ptr(out), B, W, H, Cin, Cout, 1)
+        y = oracle_conv(xh.float().cpu().permute(0, 3, 1, 2), w, b, 1, 1, 3)
+        assert relerr(out.cpu(), y) < 1e-5
+        xh2, xl2 = split_half(cl(x))
+        xh2, xl2 = xh2.cuda(), xl2.cuda()
+        L.call("rldm_conv_out", L.ptr(xh2), L.ptr(xl2), L.ptr(wd), L.ptr(bd), L.ptr(out), B, W, H, Cin, Cout, 1)
+        assert relerr(out.cpu(), oracle_conv(x, w, b, 1, 1, 3)) < 1e-5
+
+
+def test_layout_helpers(L):
+    x = torch.randn(2, 5, 8, 4)
+    d = torch.empty(2, 8, 4, 5, device="cuda")
+    xd = x.cuda()
+    L.call("rldm_ref_to_cl", L.ptr(xd), L.ptr(d), 2, 5, 8, 4)
+    assert torch.equal(d.cpu(), cl(x))
+    r = torch.empty(2, 5, 8, 4, device="cuda")
+    L.call("rldm_cl_to_ref", L.ptr(d), L.ptr(r), 2, 5, 8, 4)
+    assert torch.equal(r.cpu(), x)
+
+
+@pytest.mark.parametrize("kind", ["ddim", "ddpm", "dpm"])
+def test_scheduler_step_matches_oracle(kind):
+    import rangeldm_b200 as R
+    from oracle import schedulers as O
+    n = 20
+    if kind == "ddim":
+        s, o = R.DDIMScheduler(clip_sample=False), O.OracleDDIMScheduler()
+    elif kind == "ddpm":
+        s, o = R.DDPMScheduler(clip_sample=False), O.OracleDDPMScheduler()
+    else:
+        s, o = R.DPMSolverMultistepScheduler(timestep_spacing="leading"), O.OracleDPMSolverMultistepScheduler(
+            timestep_spacing="leading")
+    s.set_timesteps(n)
+    o.set_timesteps(n)
+    assert torch.equal(s.timesteps, o.timesteps)             # integer table: bit exact
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 4, 16, 6, generator=g)
+    xa, xb = x.cuda(), x.clone()
+    for t in s.timesteps:
+        eps = torch.randn(x.shape, generator=g)
+        noise = torch.randn(x.shape, generator=g)
+        if kind == "ddpm":
+            xa = s.step(eps.cuda(), t, xa, variance_noise=noise.cuda()).prev_sample
+            xb = o.step(eps, t, xb, variance_noise=noise)
+        else:
+            xa = s.step(eps.cuda(), t, xa).prev_sample
+            xb = o.step(eps, t, xb)
+        assert relerr(xa, xb) < 1e-5, int(t)

@@ -1,0 +1,208 @@
+"""GPU parity tests of whole modules and pipelines against the CPU oracle and the golden vectors
+produced by the reference's own code (tests/golden, oracle/make_golden.py).
+
+Tolerance: BASELINE.json's north star -- max|a-b|/max|b| <= 1e-3 on seed-matched outputs; integer
+timestep tables bit exact."""
+import pytest
+import torch
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3          # the north-star tolerance; the default split-fp16 engine lands ~100x inside it
+
+
+def make_unet(cfg, oracle_net, dev="cuda"):
+    import rangeldm_b200 as R
+    u = R.UNet2DModel(**cfg)
+    R.replace_down(u)
+    R.replace_conv(u)
+    u.load_state_dict(oracle_net.state_dict())
+    return u.to(dev)
+
+
+def make_vae(oracle_vae, boc, layers, dev="cuda"):
+    import rangeldm_b200 as R
+    n = len(boc)
+    v = R.AutoencoderKL(in_channels=2, out_channels=2, down_block_types=["DownEncoderBlock2D"] * n,
+                        up_block_types=["UpDecoderBlock2D"] * n, block_out_channels=boc, layers_per_block=layers,
+                        latent_channels=4)
+    v.quant_conv = torch.nn.Identity()
+    v.post_quant_conv = torch.nn.Identity()
+    R.replace_down(v)
+    R.replace_conv(v)
+    R.replace_attn(v)
+    v.load_state_dict(oracle_vae.state_dict())
+    return v.to(dev)
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    from oracle import nets
+    from oracle.make_golden import TINY_UNET, TINY_UNET_PIXEL, TINY_VAE, seeded
+    ou = seeded(nets.OracleUNet2DModel, 4321, **TINY_UNET)
+    oup = seeded(nets.OracleUNet2DModel, 4322, **TINY_UNET_PIXEL)
+    ov = seeded(nets.OracleAutoencoderKL, 1234, **TINY_VAE)
+    return dict(ou=ou, oup=oup, ov=ov, u=make_unet(TINY_UNET, ou), up=make_unet(TINY_UNET_PIXEL, oup),
+                v=make_vae(ov, [64, 128], 1))
+
+
+def test_unet_forward_tiny(tiny):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 5, 32, 8, generator=g)
+    for t in (torch.tensor(940), 47, torch.tensor([3, 500])):
+        with torch.no_grad():
+            ref = tiny["ou"](x, t)
+        out = tiny["u"](x.cuda(), t).sample
+        assert out.shape == ref.shape
+        assert relerr(out, ref, f"unet_tiny_t{t}") < TOL
+
+
+def test_unet_forward_cuda_core_conv_path_agrees(tiny):
+    """Same program with the CUDA-core conv restatement: isolates tensor-core issues from precision."""
+    from rangeldm_b200 import _lib, engine
+    x = torch.randn(2, 5, 32, 8, generator=torch.Generator().manual_seed(1))
+    a = tiny["u"](x.cuda(), 500).sample
+    engine.CONV_KIND = _lib.OP_CONV_REF
+    try:
+        tiny["u"].invalidate_plans()
+        b = tiny["u"](x.cuda(), 500).sample
+    finally:
+        engine.CONV_KIND = _lib.OP_CONV_TC
+        tiny["u"].invalidate_plans()
+    assert relerr(a, b, "unet_tiny_tc_vs_cudacore") < 1e-4
+
+
+def test_vae_decode_golden_from_reference_decoder(tiny, golden):
+    g = golden("vae_decoder.pt")
+    out = tiny["v"].decode(g["z"].cuda()).sample
+    assert relerr(out, g["out"], "vae_decoder_golden") < TOL
+
+
+def test_vae_encode_golden_from_reference_encoder(tiny, golden):
+    g = golden("vae_encoder.pt")
+    dist = tiny["v"].encode(g["x"].cuda()).latent_dist
+    assert relerr(dist.parameters, g["out"], "vae_encoder_golden") < TOL
+    s = dist.sample(generator=torch.Generator().manual_seed(0))
+    assert s.shape == (2, 4, 32, 8)
+
+
+def test_ldm_pipeline_golden_from_reference_pipeline(tiny, golden):
+    """Our fused, graph-captured trajectory against the image the REFERENCE's ldm/pipelines.py loop
+    produced on the oracle nets with the same generator seed."""
+    import rangeldm_b200 as R
+    g = golden("ldm_pipeline.pt")
+    for name, sch in (("dpm", R.DPMSolverMultistepScheduler(timestep_spacing="leading")),
+                      ("ddim", R.DDIMScheduler(clip_sample=False))):
+        pipe = R.LDMPipelineRange(tiny["v"], tiny["u"], sch, pos_encoding=True)
+        img = pipe(batch_size=2, generator=torch.Generator().manual_seed(3), num_inference_steps=5,
+                   output_type="torch")
+        assert relerr(img, g[f"ldm_{name}"], f"ldm_pipeline_golden_{name}") < TOL, name
+        # replaying the captured graph with the same seed is bit-stable up to split-K atomics
+        img2 = pipe(batch_size=2, generator=torch.Generator().manual_seed(3), num_inference_steps=5)
+        assert relerr(img2, img, "graph_replay_stability") < 1e-4
+
+
+def test_pixel_pipeline_golden_from_reference_pipeline(tiny, golden):
+    import rangeldm_b200 as R
+    g = golden("ldm_pipeline.pt")
+    pipe = R.DDIMPipelineRange(tiny["up"], R.DDPMScheduler(clip_sample=False), pos_encoding=True)
+    assert isinstance(pipe.scheduler, R.DDIMScheduler)
+    img = pipe(batch_size=2, generator=torch.Generator().manual_seed(3), num_inference_steps=5, output_type="torch")
+    assert relerr(img, g["pixel_ddim"], "pixel_pipeline_golden") < TOL
+
+
+def test_step_by_step_module_api_matches_fused(tiny):
+    import rangeldm_b200 as R
+    sch = R.DPMSolverMultistepScheduler(timestep_spacing="leading")
+    pipe = R.LDMPipelineRange(tiny["v"], tiny["u"], sch, pos_encoding=True)
+    a = pipe(batch_size=1, generator=torch.Generator().manual_seed(5), num_inference_steps=4)
+    imgs = pipe(batch_size=1, generator=torch.Generator().manual_seed(5), num_inference_steps=4, final_only=False)
+    assert len(imgs) == 5
+    assert relerr(imgs[-1], a, "stepwise_vs_fused") < 1e-4
+
+
+def test_upscale_pipeline_matches_oracle(tiny):
+    import rangeldm_b200 as R
+    from oracle import nets, pipeline, schedulers
+    from oracle.make_golden import TINY_UNET, seeded
+    cfg = dict(TINY_UNET, in_channels=12)
+    ou = seeded(nets.OracleUNet2DModel, 77, **cfg)
+    u = make_unet(cfg, ou)
+    pipe = R.LDMUpscalePipelineRange(tiny["v"], u, R.DPMSolverMultistepScheduler(timestep_spacing="leading"))
+    sparse = torch.randn(2, 2, 128, 8, generator=torch.Generator().manual_seed(8)).clamp(-1, 1)
+    img = pipe(image=sparse.cuda(), condition_encoder=R.SparseRangeImageEncoder2(), batch_size=2,
+               num_inference_steps=4, generator=torch.Generator().manual_seed(2))
+    noise = torch.randn((2, 4, 32, 8), generator=torch.Generator().manual_seed(2))
+    ref = pipeline.upscale_sample(ou, tiny["ov"], schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading"),
+                                  noise, pipeline.sparse_encoder2(sparse), 4)
+    assert relerr(img, ref, "upscale_pipeline") < TOL
+    with pytest.raises(ValueError):
+        pipe(image=None)
+
+
+def test_ddpm_stochastic_pipeline_matches_oracle_with_injected_noise(tiny):
+    """`ldm/inference.py` drives LDMPipelineRange with a DDPMScheduler (stochastic): same noise stream."""
+    import rangeldm_b200 as R
+    from oracle import pipeline, schedulers
+    n = 4
+    pipe = R.LDMPipelineRange(tiny["v"], tiny["u"], R.DDPMScheduler(clip_sample=False), pos_encoding=True)
+    gen = torch.Generator().manual_seed(21)
+    img = pipe(batch_size=1, generator=gen, num_inference_steps=n)
+    gen = torch.Generator().manual_seed(21)
+    noise = torch.randn((1, 4, 32, 8), generator=gen)
+    osch = schedulers.OracleDDPMScheduler()
+    osch.set_timesteps(n)
+    var = [torch.randn((1, 4, 32, 8), generator=gen) if int(t) > 0 else None for t in osch.timesteps]
+    ref = pipeline.ldm_sample(tiny["ou"], tiny["ov"], osch, noise, n, pos_encoding=True, variance_noise=var)
+    assert relerr(img, ref, "ddpm_pipeline") < TOL
+
+
+def test_c3_unet_full_size_one_forward():
+    """BASELINE config C3 UNet (30.14 M params) on a (2,5,256,16) input against the fp32 oracle."""
+    from oracle import nets
+    from oracle.make_golden import seeded
+    ou = seeded(nets.OracleUNet2DModel, 0, **nets.UNET_C3)
+    u = make_unet(nets.UNET_C3, ou)
+    x = torch.randn(2, 5, 256, 16, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        ref = ou(x, torch.tensor(500))
+    out = u(x.cuda(), torch.tensor(500)).sample
+    assert relerr(out, ref, "c3_unet_forward") < TOL
+
+
+def test_c3_trajectory_20_step_dpm_solver_full_size():
+    """Seed-matched 20-step DPM-Solver++ trajectory + KITTI VAE decode at full C3 size, batch 1."""
+    import rangeldm_b200 as R
+    from oracle import nets, pipeline, schedulers
+    from oracle.make_golden import seeded
+    ou = seeded(nets.OracleUNet2DModel, 0, **nets.UNET_C3)
+    ov = seeded(nets.OracleAutoencoderKL, 1)
+    u = make_unet(nets.UNET_C3, ou)
+    v = make_vae(ov, [64, 128, 256], 2)
+    pipe = R.LDMPipelineRange(v, u, R.DPMSolverMultistepScheduler(timestep_spacing="leading"), pos_encoding=True)
+    img = pipe(batch_size=1, generator=torch.Generator().manual_seed(0), num_inference_steps=20)
+    noise = torch.randn((1, 4, 256, 16), generator=torch.Generator().manual_seed(0))
+    ref = pipeline.ldm_sample(ou, ov, schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading"), noise, 20)
+    assert img.shape == (1, 2, 1024, 64)
+    assert relerr(img, ref, "c3_trajectory_20step_dpm") < TOL
+
+
+def test_batch_sharding_is_index_stable(tiny):
+    """Multi-GPU contract (`ldm/inference.py:159,174-183`): image of global index k depends only on
+    its own seed -- generating it inside a batch of 2 or alone gives the same image."""
+    import rangeldm_b200 as R
+    pipe = R.LDMPipelineRange(tiny["v"], tiny["u"], R.DPMSolverMultistepScheduler(timestep_spacing="leading"),
+                              pos_encoding=True)
+    gens = [torch.Generator().manual_seed(100), torch.Generator().manual_seed(101)]
+    both = pipe(batch_size=2, generator=gens, num_inference_steps=3)
+    one = pipe(batch_size=1, generator=[torch.Generator().manual_seed(101)], num_inference_steps=3)
+    assert relerr(both[1:], one, "batch_index_stability") < 1e-4
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from rangeldm_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/librldm.so")
+    with pytest.raises(_lib.RldmError):
+        _lib.lib()
