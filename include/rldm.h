@@ -46,16 +46,21 @@ int rldm_gn_stats(const float* x0, int c0, const float* x1, int c1, double* sums
  * Replaces F.group_norm's normalise half + F.silu (`model.py:343-345,351-352`), torch.cat of the
  * skip connection (UpBlock2D) and F.interpolate(scale_factor=2, "nearest") (`model.py:121-122`).
  * x0:(B,W,H,C0) [+x1:(B,W,H,C1)] fp32 cl.  sums==NULL -> no normalisation (raw cast).
- * out:(B,W*up,H*up,C0+C1) fp16 cl, up in {1,2}.  out_lo (optional, same shape): the residual
- * y - fp16(y), so that out + out_lo carries ~22 significant bits (split-fp16 operand). */
+ * out: the tensor-core OPERAND layout "clp": (B, W*up + 2, H*up, C0+C1) fp16, channels-last and
+ * W-PADDED -- padded column wp holds image column (wp-1) mod W*up, so the circular halo of
+ * `ldm/utils.py:47` (F.pad(..., mode="circular")) is materialised by the producer for free
+ * (circular=0: zero halo) and every conv tap is one plain TMA box.  up in {1,2}.
+ * out_lo (optional, same shape): the residual y - fp16(y), so that out + out_lo carries ~22
+ * significant bits (split-fp16 operand). */
 int rldm_prep(const float* x0, int c0, const float* x1, int c1, const double* sums,
               const float* gamma, const float* beta, float eps, int G, int silu, int up,
-              uint16_t* out, uint16_t* out_lo, int B, int W, int H, void* stream);
+              int circular, uint16_t* out, uint16_t* out_lo, int B, int W, int H, void* stream);
 
 /* ---- the hot op: circular implicit-GEMM convolution on tcgen05 ------------------------------
  * Replaces `Conv2d._conv_forward` (`ldm/utils.py:40-58`, twin `vae/sgm/.../model.py:93-108`):
  * wrap-pad W, zero-pad H, F.conv2d(pad 0); and the nn.Linear projections of Attention (ks=1).
- *   x   : (B, W, H, Cin) fp16 cl, Cin % 64 == 0
+ *   x   : (B, W+2, H, Cin) fp16 clp (W-padded operand layout written by rldm_prep / rldm_attention),
+ *         Cin % 64 == 0
  *   x_lo: NULL -> plain fp16 operands (1 MMA per K step, 11-bit significands);
  *         else the low-order half of a split-fp16 activation (see rldm_prep) and `wgt` must hold
  *         TWO planes [hi|lo]: the kernel issues Ah*Wh + Al*Wh + Ah*Wl into one fp32 accumulator
@@ -66,12 +71,13 @@ int rldm_prep(const float* x0, int c0, const float* x1, int c1, const double* su
  *   pad_lo: taps read input (stride*wo + i - pad_lo) mod W, stride*ho + j - pad_lo (0 outside H).
  *         ks=3,pad_lo=1: the symmetric circular conv; ks=3,stride=2,pad_lo=0: the VAE-encoder
  *         Downsample2D(padding=0) asymmetric pad (`ldm/utils.py:109-111`).
- *   circular: 1 = wrap on W (every shipped config, `all_circonv: True`); 0 = zero pad on W too.
+ *   circular: informational (1 = the producer wrote wrap halos, 0 = zero halos); the kernel reads
+ *         whatever the halo columns of `x` hold.
  *   epilogue: out = acc + bias[c] + temb[b*temb_stride + c] + residual[b,wo,ho,c] (NULL = skip)
  *   split_k: 0 = choose automatically; > 1: the K loop (taps x channel chunks) is split over
  *         split_k CTAs per tile which atomically accumulate into `out` (zeroed by this call);
  *         `residual` must then not alias `out`.
- * Requires Ho a power of two <= 128 and Cout % 64 == 0. */
+ * Requires Ho a power of two <= 128, Wo*Ho a multiple or a divisor of 128, Cout % 64 == 0. */
 int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias, const float* temb,
                  int temb_stride, const float* residual, float* out, int B, int W, int H, int Cin,
                  int Cout, int ks, int stride, int pad_lo, int circular, int split_k, void* stream);
@@ -89,7 +95,7 @@ int rldm_conv_ref(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, 
 int rldm_conv_in(const float* x0, int c0, const float* x1, int c1, const float* wgt,
                  const float* bias, float* out, int B, int W, int H, int Cout, int circular,
                  void* stream);
-/* conv_out: x (+ optional x_lo) (B,W,H,Cin) fp16 cl (already GN+SiLU'd by rldm_prep) -> out
+/* conv_out: x (+ optional x_lo) (B,W+2,H,Cin) fp16 clp (already GN+SiLU'd by rldm_prep) -> out
  * (B,Cout,W,H) fp32 REF layout, Cout in {2,4,8}.  wgt [9][Cout][Cin] fp32. */
 int rldm_conv_out(const uint16_t* x, const uint16_t* x_lo, const float* wgt, const float* bias, float* out, int B, int W,
                   int H, int Cin, int Cout, int circular, void* stream);
@@ -97,8 +103,10 @@ int rldm_conv_out(const uint16_t* x, const uint16_t* x_lo, const float* wgt, con
 /* ---- attention core ----------------------------------------------------------------------
  * Replaces F.scaled_dot_product_attention in AttnProcessor2_0: heads of
  * dim 8, softmax(QK^T/sqrt(8))V, no mask.  qkv:(B,N,3C) fp32 (q|k|v along the last dim, head h at
- * channels [8h,8h+8)); out (+ optional out_lo, split-fp16):(B,N,C) fp16 (feeds the to_out projection). */
-int rldm_attention(const float* qkv, uint16_t* out, uint16_t* out_lo, int B, int N, int C, void* stream);
+ * channels [8h,8h+8)); out (+ optional out_lo, split-fp16): fp16 clp (B, N/H + 2, H, C) -- the W-padded
+ * operand layout of the to_out projection (halo columns are not written; a 1x1 conv never reads them). */
+int rldm_attention(const float* qkv, uint16_t* out, uint16_t* out_lo, int B, int N, int C, int H,
+                   void* stream);
 
 /* ---- time embedding -----------------------------------------------------------------------
  * Replaces Timesteps + TimestepEmbedding + every ResnetBlock2D.time_emb_proj(silu(emb))

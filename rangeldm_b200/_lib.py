@@ -28,7 +28,7 @@ SIGNATURES = {
     "rldm_last_error": (ctypes.c_char_p, []),
     "rldm_gn_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rldm_prep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int,
-                          c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+                          c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rldm_conv_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
                      + [c_int] * 10 + [c_void_p]),
     "rldm_conv_ref": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
@@ -36,7 +36,7 @@ SIGNATURES = {
     "rldm_conv_in": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 5
                      + [c_void_p]),
     "rldm_conv_out": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
-    "rldm_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "rldm_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rldm_temb": (c_int, [c_void_p] * 9 + [c_int] * 4 + [c_void_p]),
     "rldm_sched_step": (c_int, [c_void_p] * 7 + [c_i64, c_void_p]),
     "rldm_scale": (c_int, [c_void_p, c_float, c_void_p, c_i64, c_void_p]),

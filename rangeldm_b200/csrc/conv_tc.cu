@@ -89,8 +89,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer (whole warp: lanes share the column loads) =============
     const int taps = p.ks * p.ks;
-    const int ncols = kBlockM / p.Ho;
-    const int q0 = m0 / p.Ho;
+    // tile = `ncols` whole azimuth columns of `nb` consecutive images (nb > 1 only when an image has < 128 px)
+    const int q0 = m0 / p.Ho;                     // global column index of the tile's first column
+    const int b0 = q0 / p.Wo;
+    const int wo0 = q0 - b0 * p.Wo;
     for (int i = 0; i < n_it; ++i) {
       const int s = i % STAGES;
       const uint32_t ph = (i / STAGES) & 1;
@@ -107,20 +109,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_2d(a_dst + kBOff + kBBytes, &tmB, &full_bar[s], chunk * kBlockK,
                       (taps + tap) * p.Cout + n0);
       }
-      for (int c = lane; c < ncols; c += 32) {
-        const int q = q0 + c;
-        const int b = q / p.Wo;
-        const int wo = q - b * p.Wo;
-        int w_in = p.stride * wo + ti - p.pad_lo;
-        if (p.circular) {   // wrap on the azimuth axis; otherwise TMA out-of-bounds fill zero-pads
-          if (w_in < 0) w_in += p.W_in;
-          if (w_in >= p.W_in) w_in -= p.W_in;
-        }
-        tma_load_4d(a_dst + c * p.Ho * 128, &tmA, &full_bar[s], chunk * kBlockK, tj - p.pad_lo,
-                    w_in, b);
-        if (TERMS > 1)
-          tma_load_4d(a_dst + kABytes + c * p.Ho * 128, &tmAlo, &full_bar[s], chunk * kBlockK,
-                      tj - p.pad_lo, w_in, b);
+      if (lane == (TERMS == 1 ? 0 : 1)) {
+        // ONE box per operand part: the activation tensor is W-padded (halo columns hold the circular wrap,
+        // written by rldm_prep), H zero padding is TMA out-of-bounds fill, stride 2 is the map's element stride.
+        const int w_in = p.stride * wo0 + ti - p.pad_lo + 1;
+        tma_load_4d(a_dst, &tmA, &full_bar[s], chunk * kBlockK, tj - p.pad_lo, w_in, b0);
+      }
+      if (TERMS > 1 && lane == 2) {
+        const int w_in = p.stride * wo0 + ti - p.pad_lo + 1;
+        tma_load_4d(a_dst + kABytes, &tmAlo, &full_bar[s], chunk * kBlockK, tj - p.pad_lo, w_in, b0);
       }
       __syncwarp();
     }
@@ -269,13 +266,19 @@ extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint1
   RLDM_CHECK(encode != nullptr, "conv_tc: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
 
   const int BN = (Cout % 128 == 0) ? 128 : 64;
+  // M tile = 128 output pixels = ncols whole columns x nb images
+  const int pix = Wo * Ho;
+  RLDM_CHECK(pix % 128 == 0 || 128 % pix == 0, "conv_tc: Wo*Ho=%d must divide or be a multiple of 128", pix);
+  const int nb = pix >= 128 ? 1 : 128 / pix;
+  const int ncols = pix >= 128 ? 128 / Ho : Wo;
+  RLDM_CHECK(ncols * stride <= 256, "conv_tc: tile of %d columns exceeds the TMA box limit", ncols);
   const int parts = x_lo ? 2 : 1;
   CUtensorMap tmA, tmAlo, tmB;
   for (int part = 0; part < parts; ++part) {
-    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)H, (cuuint64_t)W, (cuuint64_t)B};
-    cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)H * Cin * 2, (cuuint64_t)W * H * Cin * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(Ho * stride), 1, 1};
-    cuuint32_t estr[4] = {1, (cuuint32_t)stride, 1, 1};
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)H, (cuuint64_t)(W + 2), (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)H * Cin * 2, (cuuint64_t)(W + 2) * H * Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(Ho * stride), (cuuint32_t)(ncols * stride), (cuuint32_t)nb};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = encode(part ? &tmAlo : &tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
                         const_cast<uint16_t*>(part ? x_lo : x), gdim, gstr,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

@@ -87,7 +87,7 @@ gn_stats_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
             const double* __restrict__ sums, const float* __restrict__ gamma,
-            const float* __restrict__ beta, float eps, int G, int silu, int up,
+            const float* __restrict__ beta, float eps, int G, int silu, int up, int circular,
             __half* __restrict__ out, __half* __restrict__ out_lo, int W, int H, int pix_per_block) {
   extern __shared__ float shf[];  // scale[C], shift[C]
   const int C = c0 + c1;
@@ -111,20 +111,30 @@ prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, 
     }
     __syncthreads();
   }
+  // Output is W-PADDED: (B, Wo+2, Ho, C); padded column wp holds image column (wp-1) mod Wo, i.e. the
+  // circular halo of `ldm/utils.py:47` is materialised here for free (zeros when !circular), so every
+  // conv tap is a plain TMA box.
   const int Wo = W * up, Ho = H * up;
   const int oct_per_pix = C >> 3;
-  const int out_pix = Wo * Ho;
+  const int out_pix = (Wo + 2) * Ho;
   const int p_begin = blockIdx.x * pix_per_block;
   const int p_end = min(p_begin + pix_per_block, out_pix);
   const int total = (p_end - p_begin) * oct_per_pix;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int po = p_begin + i / oct_per_pix;
     const int c = (i % oct_per_pix) << 3;
-    int pin = po;
-    if (up == 2) {
-      const int wo = po / Ho, ho = po - wo * Ho;
-      pin = (wo >> 1) * H + (ho >> 1);
+    const int wp = po / Ho, ho = po - wp * Ho;
+    int wo = wp - 1;
+    const bool halo = wo < 0 || wo >= Wo;
+    if (wo < 0) wo += Wo;
+    if (wo >= Wo) wo -= Wo;
+    const size_t o = (static_cast<size_t>(b) * out_pix + po) * C + c;
+    if (halo && !circular) {
+      *reinterpret_cast<uint4*>(out + o) = make_uint4(0, 0, 0, 0);
+      if (out_lo) *reinterpret_cast<uint4*>(out_lo + o) = make_uint4(0, 0, 0, 0);
+      continue;
     }
+    const int pin = (up == 2) ? (wo >> 1) * H + (ho >> 1) : wo * H + ho;
     const size_t pix = static_cast<size_t>(b) * W * H + pin;
     const float* src = (c < c0) ? x0 + pix * c0 + c : x1 + pix * c1 + (c - c0);
     const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
@@ -141,7 +151,6 @@ prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, 
     __align__(16) __half2 h[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-    const size_t o = (static_cast<size_t>(b) * out_pix + po) * C + c;
     *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(h);
     if (out_lo) {   // residual of the fp16 rounding: x = hi + lo to ~22 bits
       __align__(16) __half2 l[4];
@@ -174,13 +183,11 @@ __global__ void conv_ref_kernel(const __half* __restrict__ x, const __half* __re
   const int b = m / (static_cast<size_t>(Ho) * Wo);
   float acc = 0.f;
   for (int i = 0; i < ks; ++i) {
-    int w = stride * wo + i - pad_lo;
-    if (circular) w = ((w % W) + W) % W;
-    else if (w < 0 || w >= W) continue;
+    const int w = stride * wo + i - pad_lo + 1;     // column in the W-padded operand (halo = wrap or zeros)
     for (int j = 0; j < ks; ++j) {
       const int h = stride * ho + j - pad_lo;
       if (h < 0 || h >= H) continue;
-      const size_t xo = ((static_cast<size_t>(b) * W + w) * H + h) * Cin;
+      const size_t xo = ((static_cast<size_t>(b) * (W + 2) + w) * H + h) * Cin;
       const __half* wr = wgt + (static_cast<size_t>(i * ks + j) * Cout + n) * Cin;
       const __half* wl = wr + static_cast<size_t>(ks) * ks * Cout * Cin;   // low-order plane
       for (int c = 0; c < Cin; c += 2) {
@@ -267,15 +274,11 @@ conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, c
 #pragma unroll
   for (int n = 0; n < COUT; ++n) acc[n] = 0.f;
   for (int i = 0; i < 3; ++i) {
-    int wi = w + i - 1;
-    if (circular) {
-      if (wi < 0) wi += W;
-      if (wi >= W) wi -= W;
-    } else if (wi < 0 || wi >= W) continue;
+    const int wi = w + i;                             // W-padded operand: halo columns hold the wrap (or zeros)
     for (int j = 0; j < 3; ++j) {
       const int hj = h + j - 1;
       if (hj < 0 || hj >= H) continue;
-      const size_t xo = ((static_cast<size_t>(b) * W + wi) * H + hj) * Cin;
+      const size_t xo = ((static_cast<size_t>(b) * (W + 2) + wi) * H + hj) * Cin;
       const float* wr = wgt + static_cast<size_t>(i * 3 + j) * COUT * Cin;
       for (int c = lane * 2; c < Cin; c += 64) {
         float2 a = __half22float2(*reinterpret_cast<const __half2*>(x + xo + c));
@@ -313,7 +316,7 @@ conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, c
 constexpr int kAttnKT = 512;
 __global__ void __launch_bounds__(128)
 attention_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half* __restrict__ out_lo, int N,
-                 int C) {
+                 int C, int H) {
   __shared__ float4 sk[kAttnKT * 2 + 16];
   __shared__ float4 sv[kAttnKT * 2 + 16];
   const int b = blockIdx.z, hd = blockIdx.y;
@@ -377,7 +380,8 @@ attention_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half
     __align__(16) __half2 h[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(acc[2 * j] * inv, acc[2 * j + 1] * inv);
-    const size_t o = (static_cast<size_t>(b) * N + qi) * C + hd * 8;
+    // W-padded operand layout (B, W+2, H, C): token n = w*H + h lands at padded pixel H + n
+    const size_t o = (static_cast<size_t>(b) * (N + 2 * H) + H + qi) * C + hd * 8;
     *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(h);
     if (out_lo) {
       __align__(16) __half2 l[4];
@@ -535,18 +539,18 @@ extern "C" int rldm_gn_stats(const float* x0, int c0, const float* x1, int c1, d
 
 extern "C" int rldm_prep(const float* x0, int c0, const float* x1, int c1, const double* sums,
                          const float* gamma, const float* beta, float eps, int G, int silu, int up,
-                         uint16_t* out, uint16_t* out_lo, int B, int W, int H, void* stream) {
+                         int circular, uint16_t* out, uint16_t* out_lo, int B, int W, int H, void* stream) {
   const int C = c0 + c1;
   RLDM_CHECK(c0 % 8 == 0 && c1 % 8 == 0, "prep: channels must be multiples of 8 (c0=%d c1=%d)", c0, c1);
   RLDM_CHECK(up == 1 || up == 2, "prep: up must be 1 or 2");
   RLDM_CHECK(!sums || (gamma && beta && G > 0 && C % G == 0), "prep: GroupNorm needs gamma/beta/G");
-  const int out_pix = W * up * H * up;
+  const int out_pix = (W * up + 2) * H * up;
   int chunks = (592 + B - 1) / B;
   int ppb = (out_pix + chunks - 1) / chunks;
   if (ppb < 8) ppb = 8;
   chunks = (out_pix + ppb - 1) / ppb;
   prep_kernel<<<dim3(chunks, B), 256, 2 * C * sizeof(float), as_stream(stream)>>>(
-      x0, c0, x1, c1, sums, gamma, beta, eps, G, silu, up, reinterpret_cast<__half*>(out),
+      x0, c0, x1, c1, sums, gamma, beta, eps, G, silu, up, circular, reinterpret_cast<__half*>(out),
       reinterpret_cast<__half*>(out_lo), W, H, ppb);
   RLDM_LAUNCH_CHECK();
   return 0;
@@ -597,11 +601,11 @@ extern "C" int rldm_conv_out(const uint16_t* x, const uint16_t* x_lo, const floa
 }
 
 extern "C" int rldm_attention(const float* qkv, uint16_t* out, uint16_t* out_lo, int B, int N, int C,
-                              void* stream) {
+                              int H, void* stream) {
   RLDM_CHECK(C % 8 == 0, "attention: C %% 8 != 0");
   const int threads = N >= 128 ? 128 : ((N + 31) / 32) * 32;
   attention_kernel<<<dim3((N + threads - 1) / threads, C / 8, B), threads, 0, as_stream(stream)>>>(
-      qkv, reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C);
+      qkv, reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H);
   RLDM_LAUNCH_CHECK();
   return 0;
 }
@@ -660,7 +664,7 @@ extern "C" int rldm_run(const rldm_op* ops, int n_ops, void* stream) {
         break;
       case RLDM_OP_PREP:
         rc = rldm_prep((const float*)o.p[0], o.i[0], (const float*)o.p[1], o.i[1], (const double*)o.p[2],
-                       (const float*)o.p[3], (const float*)o.p[4], o.f[0], o.i[2], o.i[3], o.i[4],
+                       (const float*)o.p[3], (const float*)o.p[4], o.f[0], o.i[2], o.i[3], o.i[4], o.i[8],
                        (uint16_t*)o.p[5], (uint16_t*)o.p[6], o.i[5], o.i[6], o.i[7], stream);
         break;
       case RLDM_OP_CONV_TC:
@@ -682,7 +686,7 @@ extern "C" int rldm_run(const rldm_op* ops, int n_ops, void* stream) {
                            (float*)o.p[3], o.i[0], o.i[1], o.i[2], o.i[3], o.i[4], o.i[5], stream);
         break;
       case RLDM_OP_ATTENTION:
-        rc = rldm_attention((const float*)o.p[0], (uint16_t*)o.p[1], (uint16_t*)o.p[2], o.i[0], o.i[1], o.i[2], stream);
+        rc = rldm_attention((const float*)o.p[0], (uint16_t*)o.p[1], (uint16_t*)o.p[2], o.i[0], o.i[1], o.i[2], o.i[3], stream);
         break;
       case RLDM_OP_TEMB:
         rc = rldm_temb((const float*)o.p[0], (const float*)o.p[1], (const float*)o.p[2],

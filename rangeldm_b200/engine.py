@@ -184,8 +184,8 @@ class Builder:
                     p=(x0.t, x1.t if x1 is not None else None, sums))
         return sums
 
-    def prep(self, x0, x1=None, norm=None, silu=False, up=1):
-        """-> fp16 cl tensor (B, W*up, H*up, C0+C1)."""
+    def prep(self, x0, x1=None, norm=None, silu=False, up=1, circular=True):
+        """-> fp16 operand pair in the W-padded layout (B, W*up + 2, H*up, C0+C1)."""
         c1 = x1.C if x1 is not None else 0
         C = x0.C + c1
         sums = gamma = beta = None
@@ -194,8 +194,8 @@ class Builder:
             G = norm.num_groups
             sums = self.gn_stats(x0, x1, G)
             gamma, beta, eps = self.f32(norm.weight), self.f32(norm.bias), norm.eps
-        out = self.alloc_half((self.B, x0.W * up, x0.H * up, C))
-        self.pg.add(_lib.OP_PREP, i=(x0.C, c1, G, int(silu), up, self.B, x0.W, x0.H), f=(eps,),
+        out = self.alloc_half((self.B, x0.W * up + 2, x0.H * up, C))
+        self.pg.add(_lib.OP_PREP, i=(x0.C, c1, G, int(silu), up, self.B, x0.W, x0.H, int(circular)), f=(eps,),
                     p=(x0.t, x1.t if x1 is not None else None, sums, gamma, beta, out[0], out[1]))
         return out
 
@@ -228,7 +228,8 @@ class Builder:
     def resnet(self, rb, x0, x1=None, free_inputs=True):
         """ResnetBlock2D on the virtual concat (x0 | x1) (App. A.1; `model.py:342-362`)."""
         pg = self.pg
-        a1 = self.prep(x0, x1, rb.norm1, silu=True)
+        circ = lambda conv: bool(getattr(conv, "circular", False))
+        a1 = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1))
         temb = None
         if rb.time_emb_proj is not None and self.temb is not None:
             t, T = self.temb
@@ -236,7 +237,7 @@ class Builder:
             temb = (t.view(-1)[off:], T)
         h = self.conv(a1, x0.W, x0.H, rb.conv1, temb=temb)
         self.free_half(a1)
-        a2 = self.prep(h, None, rb.norm2, silu=True)
+        a2 = self.prep(h, None, rb.norm2, silu=True, circular=circ(rb.conv2))
         pg.free(h.t)
         if rb.conv_shortcut is not None:
             xr = self.prep(x0, x1, None, silu=False)
@@ -266,8 +267,8 @@ class Builder:
         qkv = self.conv(a, x.W, x.H, packed=self.pack_linear([at.to_q, at.to_k, at.to_v]), cin=C, cout=3 * C, ks=1,
                         pad_lo=0)
         self.free_half(a)
-        o = self.alloc_half((self.B, x.W, x.H, C))
-        pg.add(_lib.OP_ATTENTION, i=(self.B, x.W * x.H, C), p=(qkv.t, o[0], o[1]))
+        o = self.alloc_half((self.B, x.W + 2, x.H, C))
+        pg.add(_lib.OP_ATTENTION, i=(self.B, x.W * x.H, C, x.H), p=(qkv.t, o[0], o[1]))
         pg.free(qkv.t)
         out = self.conv(o, x.W, x.H, packed=self.pack_linear([at.to_out[0]]), cin=C, cout=C, ks=1, pad_lo=0,
                         residual=x)
@@ -280,7 +281,7 @@ class Builder:
     def downsample(self, ds, x, free_input=True):
         """Patched Downsample2D (`ldm/utils.py:107-116`): raw cast + stride-2 conv; padding=0 is the
         VAE-encoder asymmetric pad (pad_lo = 0)."""
-        xr = self.prep(x, None, None)
+        xr = self.prep(x, None, None, circular=bool(getattr(ds.conv, "circular", False)))
         out = self.conv(xr, x.W, x.H, ds.conv)
         self.free_half(xr)
         self.pg.taps.append((ds, out))
@@ -290,7 +291,7 @@ class Builder:
 
     def upsample(self, us, x):
         """Upsample2D (`model.py:120-125`): nearest 2x folded into the cast, then 3x3 conv."""
-        xr = self.prep(x, None, None, up=2)
+        xr = self.prep(x, None, None, up=2, circular=bool(getattr(us.conv, "circular", False)))
         out = self.conv(xr, x.W * 2, x.H * 2, us.conv)
         self.free_half(xr)
         self.pg.taps.append((us, out))
@@ -309,7 +310,7 @@ class Builder:
         return act
 
     def conv_out(self, norm, conv, x, out_ref):
-        a = self.prep(x, None, norm, silu=True)
+        a = self.prep(x, None, norm, silu=True, circular=bool(getattr(conv, "circular", False)))
         w = conv.weight.detach().to(self.pg.device, torch.float32)
         wt = self.pg.hold(w.permute(2, 3, 0, 1).contiguous())           # [9][Cout][Cin]
         assert conv.kernel_size == (3, 3) and conv.padding == (1, 1)

@@ -33,6 +33,18 @@ def pack_w(w, split=False):  # (Cout,Cin,kW,kH) -> [planes][tap][Cout][Cin] fp16
     return torch.cat([hi, (t - hi.float()).half()], 0).contiguous()
 
 
+def padw(x, circular=True):
+    """(B,W,H,C) -> the W-padded operand layout (B,W+2,H,C): wrap (or zero) halo columns."""
+    if circular:
+        return torch.cat([x[:, -1:], x, x[:, :1]], dim=1).contiguous()
+    z = torch.zeros_like(x[:, :1])
+    return torch.cat([z, x, z], dim=1).contiguous()
+
+
+def unpadw(x):
+    return x[:, 1:-1].contiguous()
+
+
 def split_half(x):
     hi = x.half()
     return hi, (x - hi.float()).half()
@@ -81,7 +93,7 @@ def test_conv_tc_matches_cuda_core_restatement_and_oracle(L, case):
     temb = torch.randn(B, Cout + 8, generator=g)
     Wo, Ho = W // stride, H // stride
     res = torch.randn(B, Cout, Wo, Ho, generator=g)
-    xh = cl(x).half().cuda()
+    xh = padw(cl(x).half(), bool(circ)).cuda()
     wt = pack_w(w).cuda()
     bd, td, rd = b.cuda(), temb.cuda(), cl(res).cuda()
     out_tc = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
@@ -94,7 +106,7 @@ def test_conv_tc_matches_cuda_core_restatement_and_oracle(L, case):
     # same fp16 operands on both sides: only the fp32 summation order differs
     assert relerr(out_tc, out_rf) < 2e-5
     # oracle with fp16-rounded operands (exact products in fp32)
-    y = oracle_conv(xh.float().cpu().permute(0, 3, 1, 2), wt.float().cpu().reshape(ks, ks, Cout, Cin).permute(2, 3, 0, 1),
+    y = oracle_conv(unpadw(xh).float().cpu().permute(0, 3, 1, 2), wt.float().cpu().reshape(ks, ks, Cout, Cin).permute(2, 3, 0, 1),
                     b, stride, pad_lo, ks, bool(circ)) + temb[:, :Cout, None, None] + res
     assert relerr(ref_layout(out_tc.cpu()), y) < 2e-5
     # and against the un-rounded fp32 oracle within the north-star tolerance
@@ -102,7 +114,7 @@ def test_conv_tc_matches_cuda_core_restatement_and_oracle(L, case):
     assert relerr(ref_layout(out_tc.cpu()), y32) < 1e-3
     # split-fp16 ("fp16x3", the engine default): hi+lo operands, 3 MMAs per K step -> ~fp32 accuracy
     xh2, xl2 = split_half(cl(x))
-    xh2, xl2, wt2 = xh2.cuda(), xl2.cuda(), pack_w(w, split=True).cuda()
+    xh2, xl2, wt2 = padw(xh2, bool(circ)).cuda(), padw(xl2, bool(circ)).cuda(), pack_w(w, split=True).cuda()
     out3 = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
     out3r = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
     L.call("rldm_conv_tc", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out3),
@@ -120,19 +132,19 @@ def test_conv_tc_golden_reference_conv(L, golden):
         B, Cin, W, H = x.shape
         Cout = w.shape[0]
         out = torch.empty(B, W // stride, H // stride, Cout, device="cuda")
-        xh, wt, bd = cl(x).half().cuda(), pack_w(w).cuda(), b.cuda()     # keep the operands alive across the call
+        xh, wt, bd = padw(cl(x).half()).cuda(), pack_w(w).cuda(), b.cuda()     # keep the operands alive across the call
         L.call("rldm_conv_tc", L.ptr(xh), None, L.ptr(wt), L.ptr(bd), None, 0, None,
                L.ptr(out), B, W, H, Cin, Cout, 3, stride, 1, 1, 0)
         assert relerr(ref_layout(out.cpu()), y) < 1e-3
         xh2, xl2 = split_half(cl(x))
-        xh2, xl2, wt2 = xh2.cuda(), xl2.cuda(), pack_w(w, split=True).cuda()
+        xh2, xl2, wt2 = padw(xh2).cuda(), padw(xl2).cuda(), pack_w(w, split=True).cuda()
         L.call("rldm_conv_tc", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), None, 0, None,
                L.ptr(out), B, W, H, Cin, Cout, 3, stride, 1, 1, 0)
         assert relerr(ref_layout(out.cpu()), y) < 1e-5
 
 
 def test_conv_tc_rejects_bad_shapes(L):
-    x = torch.zeros(1, 8, 8, 48, dtype=torch.half, device="cuda")
+    x = torch.zeros(1, 10, 8, 48, dtype=torch.half, device="cuda")
     with pytest.raises(L.RldmError):
         L.call("rldm_conv_tc", L.ptr(x), None, L.ptr(x), None, None, 0, None, L.ptr(x), 1, 8, 8, 48, 64, 3, 1, 1, 1, 0)
 
@@ -155,20 +167,22 @@ def test_gn_stats_and_prep(L, shape):
     xg = xc.double().reshape(B, G, -1)
     assert torch.allclose(sums[:, :, 0].cpu(), xg.sum(-1), rtol=1e-6, atol=1e-4)
     assert torch.allclose(sums[:, :, 1].cpu(), (xg * xg).sum(-1), rtol=1e-6, atol=1e-4)
-    out = torch.empty(B, W * up, H * up, C, dtype=torch.half, device="cuda")
+    out = torch.empty(B, W * up + 2, H * up, C, dtype=torch.half, device="cuda")
     gd, bd = gamma.cuda(), beta.cuda()
     out_lo = torch.empty_like(out)
     L.call("rldm_prep", L.ptr(x0d), C0, L.ptr(x1d), C1, L.ptr(sums), L.ptr(gd), L.ptr(bd), eps, G, 1,
-           up, L.ptr(out), L.ptr(out_lo), B, W, H)
+           up, 1, L.ptr(out), L.ptr(out_lo), B, W, H)
     y = F.silu(F.group_norm(xc, G, gamma, beta, eps))
     if up == 2:
         y = F.interpolate(y, scale_factor=2.0, mode="nearest")
-    assert relerr(ref_layout(out.float().cpu()), y) < 1.5e-3          # fp16 output rounding
-    assert relerr(ref_layout((out.float() + out_lo.float()).cpu()), y) < 5e-6      # hi + lo: split-fp16
-    # raw cast path (no norm, no silu)
-    L.call("rldm_prep", L.ptr(x0d), C0, L.ptr(x1d), C1, None, None, None, 0.0, 0, 0, up, L.ptr(out), None, B, W, H)
+    assert relerr(ref_layout(unpadw(out).float().cpu()), y) < 1.5e-3          # fp16 output rounding
+    assert relerr(ref_layout(unpadw(out.float() + out_lo.float()).cpu()), y) < 5e-6      # hi + lo: split-fp16
+    assert torch.equal(out[:, 0], out[:, -2]) and torch.equal(out[:, -1], out[:, 1])   # circular halo columns
+    # raw cast path (no norm, no silu), zero halo
+    L.call("rldm_prep", L.ptr(x0d), C0, L.ptr(x1d), C1, None, None, None, 0.0, 0, 0, up, 0, L.ptr(out), None, B, W, H)
     yr = F.interpolate(xc, scale_factor=2.0, mode="nearest") if up == 2 else xc
-    assert torch.equal(ref_layout(out.cpu()), yr.half())
+    assert torch.equal(ref_layout(unpadw(out).cpu()), yr.half())
+    assert float(out[:, 0].abs().max()) == 0.0 and float(out[:, -1].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 64), (1, 256, 128), (2, 1024, 128), (1, 40, 64)])
@@ -176,10 +190,12 @@ def test_attention_core(L, shape):
     B, N, C = shape
     g = torch.Generator().manual_seed(N)
     qkv = torch.randn(B, N, 3 * C, generator=g)
-    out = torch.empty(B, N, C, dtype=torch.half, device="cuda")
+    Hh = 8                                                 # tokens are (w, h) with H = 8; output is W-padded
+    outp = torch.zeros(B, N // Hh + 2, Hh, C, dtype=torch.half, device="cuda")
     qd = qkv.cuda()
-    out_lo = torch.empty_like(out)
-    L.call("rldm_attention", L.ptr(qd), L.ptr(out), L.ptr(out_lo), B, N, C)
+    outp_lo = torch.zeros_like(outp)
+    L.call("rldm_attention", L.ptr(qd), L.ptr(outp), L.ptr(outp_lo), B, N, C, Hh)
+    out, out_lo = unpadw(outp).reshape(B, N, C), unpadw(outp_lo).reshape(B, N, C)
     q, k, v = qkv.split(C, dim=-1)
     sp = lambda t: t.view(B, N, C // 8, 8).transpose(1, 2)
     y = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(B, N, C)
@@ -223,14 +239,14 @@ def test_conv_in_and_conv_out(L):
         x = torch.randn(B, Cin, W, H, generator=g)
         w = torch.randn(Cout, Cin, 3, 3, generator=g) * 0.1
         b = torch.randn(Cout, generator=g)
-        xh = cl(x).half().cuda()
+        xh = padw(cl(x).half()).cuda()
         out = torch.empty(B, Cout, W, H, device="cuda")
         wd, bd = w.permute(2, 3, 0, 1).contiguous().cuda(), b.cuda()
         L.call("rldm_conv_out", L.ptr(xh), None, L.ptr(wd), L.ptr(bd), L.ptr(out), B, W, H, Cin, Cout, 1)
-        y = oracle_conv(xh.float().cpu().permute(0, 3, 1, 2), w, b, 1, 1, 3)
+        y = oracle_conv(unpadw(xh).float().cpu().permute(0, 3, 1, 2), w, b, 1, 1, 3)
         assert relerr(out.cpu(), y) < 1e-5
         xh2, xl2 = split_half(cl(x))
-        xh2, xl2 = xh2.cuda(), xl2.cuda()
+        xh2, xl2 = padw(xh2).cuda(), padw(xl2).cuda()
         L.call("rldm_conv_out", L.ptr(xh2), L.ptr(xl2), L.ptr(wd), L.ptr(bd), L.ptr(out), B, W, H, Cin, Cout, 1)
         assert relerr(out.cpu(), oracle_conv(x, w, b, 1, 1, 3)) < 1e-5
 
