@@ -227,7 +227,7 @@ class DPMSolverMultistepScheduler(_SchedulerBase):
             ts = np.arange(N, 0, -N / n).round().copy().astype(np.int64) - 1
         else:
             raise ValueError(c.timestep_spacing)
-        sig_all = np.sqrt((1 - self._ac) / self._ac)
+        sig_all = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()    # fp32, as diffusers
         sig = np.interp(ts, np.arange(0, N), sig_all)
         last = math.sqrt((1 - self._ac[0]) / self._ac[0]) if c.final_sigmas_type == "sigma_min" else 0.0
         sig = np.concatenate([sig, [last]]).astype(np.float32).astype(np.float64)   # reference keeps fp32 sigmas
