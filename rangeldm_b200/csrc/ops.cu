@@ -2,6 +2,7 @@
 // the fused normalise+SiLU+concat+upsample+cast "prep", boundary convolutions, attention core,
 // time embedding, the fused scheduler step, and the program runner.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -396,6 +397,145 @@ attention_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half
 }
 
 // ------------------------------------------------------------------------------------------------
+// attention core on the legacy tensor path (mma.sync m16n8k16, fp16 x fp16 -> fp32), split-fp16 operands.
+// head_dim 8 is too thin for tcgen05 (K >= 16, N >= 16 per instruction would be mostly padding), so the
+// d = 8 contraction is packed as K = [hi | lo]:  S = [q_hi|q_lo] . [k_hi;k_hi] + [q_hi|q_lo] . [k_lo;k_lo],
+// and P.V is issued as P_hi.V_hi + P_lo.V_hi + P_hi.V_lo with the FlashAttention-2 register trick (the C
+// fragments of two 8-key score blocks ARE the A fragment of one 16-key P block).  ~22-bit operands throughout.
+// grid (N/64, C/8, B), block 128 = 4 warps x 16 queries; K/V of the (b, head) staged per 256-key chunk.
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+// split (x, y) into fp16 hi and lo words
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x, y);
+  const float2 hf = __half22float2(h);
+  hi = pack_h2(h);
+  lo = pack_h2(__floats2half2_rn(x - hf.x, y - hf.y));
+}
+
+constexpr int kAtKT = 256;            // keys per shared-memory chunk
+constexpr int kAtVP = kAtKT + 8;      // padded pitch of the transposed V rows (bank-conflict-free B fragments)
+__global__ void __launch_bounds__(128)
+attention_tc_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half* __restrict__ out_lo,
+                    int N, int C, int H) {
+  __shared__ __align__(16) __half sk_hi[kAtKT * 8];
+  __shared__ __align__(16) __half sk_lo[kAtKT * 8];
+  __shared__ __align__(16) __half sv_hi[8 * kAtVP];      // transposed: [d][key]
+  __shared__ __align__(16) __half sv_lo[8 * kAtVP];
+  const int b = blockIdx.z, hd = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t row = 3 * static_cast<size_t>(C);
+  const float* base = qkv + static_cast<size_t>(b) * N * row + hd * 8;
+  const int q0 = blockIdx.x * 64 + warp * 16;
+  // Q fragment (constant over the key loop); softmax scale 1/sqrt(8) and log2(e) folded in
+  const float qs = 0.35355339059327373f * 1.4426950408889634f;
+  uint32_t qa[4];
+  {
+    const float2 x0 = __ldg(reinterpret_cast<const float2*>(base + (q0 + g) * row + 2 * t));
+    const float2 x1 = __ldg(reinterpret_cast<const float2*>(base + (q0 + g + 8) * row + 2 * t));
+    split2(x0.x * qs, x0.y * qs, qa[0], qa[2]);     // a0 = hi(row g), a2 = lo(row g)   (K cols 8.. = lo part)
+    split2(x1.x * qs, x1.y * qs, qa[1], qa[3]);     // a1 = hi(row g+8), a3 = lo(row g+8)
+  }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < N; k0 += kAtKT) {
+    const int kt = min(kAtKT, N - k0);             // multiple of 64 (checked on the host)
+    __syncthreads();
+    for (int i = threadIdx.x; i < kt; i += blockDim.x) {
+      const float* kp = base + (k0 + i) * row + C;
+      const float* vp = base + (k0 + i) * row + 2 * C;
+      const float4 ka = __ldg(reinterpret_cast<const float4*>(kp)), kb = __ldg(reinterpret_cast<const float4*>(kp) + 1);
+      const float4 va = __ldg(reinterpret_cast<const float4*>(vp)), vb = __ldg(reinterpret_cast<const float4*>(vp) + 1);
+      uint32_t h[4], l[4];
+      split2(ka.x, ka.y, h[0], l[0]); split2(ka.z, ka.w, h[1], l[1]);
+      split2(kb.x, kb.y, h[2], l[2]); split2(kb.z, kb.w, h[3], l[3]);
+      *reinterpret_cast<uint4*>(sk_hi + i * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(sk_lo + i * 8) = make_uint4(l[0], l[1], l[2], l[3]);
+      const float vv[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        const __half hh = __float2half_rn(vv[d]);
+        sv_hi[d * kAtVP + i] = hh;
+        sv_lo[d * kAtVP + i] = __float2half_rn(vv[d] - __half2float(hh));
+      }
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < kt; c0 += 64) {
+      // ---- S = Q K^T for 64 keys: 8 blocks of 8 keys, 2 MMAs each
+      float sfr[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sfr[j][0] = sfr[j][1] = sfr[j][2] = sfr[j][3] = 0.f;
+        const int key = c0 + j * 8 + g;
+        const uint32_t kh = *reinterpret_cast<const uint32_t*>(sk_hi + key * 8 + 2 * t);
+        const uint32_t kl = *reinterpret_cast<const uint32_t*>(sk_lo + key * 8 + 2 * t);
+        mma_f16_16816(sfr[j], qa, kh, kh);          // q_hi.k_hi + q_lo.k_hi
+        mma_f16_16816(sfr[j], qa, kl, kl);          // q_hi.k_lo (+ q_lo.k_lo)
+      }
+      // ---- online softmax (rows g and g+8; a row is spread over the 4 threads of a quad)
+      float r0 = sfr[0][0], r1 = sfr[0][2];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        r0 = fmaxf(r0, fmaxf(sfr[j][0], sfr[j][1]));
+        r1 = fmaxf(r1, fmaxf(sfr[j][2], sfr[j][3]));
+      }
+      r0 = fmaxf(r0, __shfl_xor_sync(0xffffffffu, r0, 1)); r0 = fmaxf(r0, __shfl_xor_sync(0xffffffffu, r0, 2));
+      r1 = fmaxf(r1, __shfl_xor_sync(0xffffffffu, r1, 1)); r1 = fmaxf(r1, __shfl_xor_sync(0xffffffffu, r1, 2));
+      const float n0 = fmaxf(m0, r0), n1 = fmaxf(m1, r1);
+      const float cr0 = exp2f(m0 - n0), cr1 = exp2f(m1 - n1);
+      m0 = n0; m1 = n1;
+      l0 *= cr0; l1 *= cr1;
+      o[0] *= cr0; o[1] *= cr0; o[2] *= cr1; o[3] *= cr1;
+      // ---- P = exp2(S - m), O += P V : 4 blocks of 16 keys, 3 MMAs each
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint32_t ph[4], pl[4];
+        {
+          const float p0 = exp2f(sfr[2 * jj][0] - m0), p1 = exp2f(sfr[2 * jj][1] - m0);
+          const float p2 = exp2f(sfr[2 * jj][2] - m1), p3 = exp2f(sfr[2 * jj][3] - m1);
+          const float p4 = exp2f(sfr[2 * jj + 1][0] - m0), p5 = exp2f(sfr[2 * jj + 1][1] - m0);
+          const float p6 = exp2f(sfr[2 * jj + 1][2] - m1), p7 = exp2f(sfr[2 * jj + 1][3] - m1);
+          l0 += (p0 + p1) + (p4 + p5);
+          l1 += (p2 + p3) + (p6 + p7);
+          split2(p0, p1, ph[0], pl[0]);   // row g,   keys 2t,2t+1
+          split2(p2, p3, ph[1], pl[1]);   // row g+8, keys 2t,2t+1
+          split2(p4, p5, ph[2], pl[2]);   // row g,   keys 8+2t,..
+          split2(p6, p7, ph[3], pl[3]);   // row g+8, keys 8+2t,..
+        }
+        const int kb16 = c0 + jj * 16;
+        const uint32_t vh0 = *reinterpret_cast<const uint32_t*>(sv_hi + g * kAtVP + kb16 + 2 * t);
+        const uint32_t vh1 = *reinterpret_cast<const uint32_t*>(sv_hi + g * kAtVP + kb16 + 8 + 2 * t);
+        const uint32_t vl0 = *reinterpret_cast<const uint32_t*>(sv_lo + g * kAtVP + kb16 + 2 * t);
+        const uint32_t vl1 = *reinterpret_cast<const uint32_t*>(sv_lo + g * kAtVP + kb16 + 8 + 2 * t);
+        mma_f16_16816(o, ph, vh0, vh1);
+        mma_f16_16816(o, pl, vh0, vh1);
+        mma_f16_16816(o, ph, vl0, vl1);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  // W-padded operand layout (B, W+2, H, C): token n lands at padded pixel H + n
+  const size_t ob = (static_cast<size_t>(b) * (N + 2 * H) + H) * C + hd * 8 + 2 * t;
+  uint32_t h0, lo0, h1, lo1;
+  split2(o[0] * i0, o[1] * i0, h0, lo0);
+  split2(o[2] * i1, o[3] * i1, h1, lo1);
+  *reinterpret_cast<uint32_t*>(out + ob + static_cast<size_t>(q0 + g) * C) = h0;
+  *reinterpret_cast<uint32_t*>(out + ob + static_cast<size_t>(q0 + g + 8) * C) = h1;
+  if (out_lo) {
+    *reinterpret_cast<uint32_t*>(out_lo + ob + static_cast<size_t>(q0 + g) * C) = lo0;
+    *reinterpret_cast<uint32_t*>(out_lo + ob + static_cast<size_t>(q0 + g + 8) * C) = lo1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // time embedding.  temb_mlp: grid B, block 512 (16 warps): sinusoid -> linear_1 -> silu ->
 // linear_2 -> silu, warp-per-output-row dot products.  temb_proj: grid (ceil(T/8), B), block 256.
 __global__ void __launch_bounds__(512)
@@ -603,6 +743,12 @@ extern "C" int rldm_conv_out(const uint16_t* x, const uint16_t* x_lo, const floa
 extern "C" int rldm_attention(const float* qkv, uint16_t* out, uint16_t* out_lo, int B, int N, int C,
                               int H, void* stream) {
   RLDM_CHECK(C % 8 == 0, "attention: C %% 8 != 0");
+  if (N % 64 == 0 && !getenv("RLDM_ATTN_CUDACORE")) {   // tensor-path kernel; the CUDA-core kernel covers ragged N
+    attention_tc_kernel<<<dim3(N / 64, C / 8, B), 128, 0, as_stream(stream)>>>(
+        qkv, reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H);
+    RLDM_LAUNCH_CHECK();
+    return 0;
+  }
   const int threads = N >= 128 ? 128 : ((N + 31) / 32) * 32;
   attention_kernel<<<dim3((N + threads - 1) / threads, C / 8, B), threads, 0, as_stream(stream)>>>(
       qkv, reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H);

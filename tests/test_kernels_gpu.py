@@ -185,9 +185,12 @@ def test_gn_stats_and_prep(L, shape):
     assert float(out[:, 0].abs().max()) == 0.0 and float(out[:, -1].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("shape", [(2, 64, 64), (1, 256, 128), (2, 1024, 128), (1, 40, 64)])
-def test_attention_core(L, shape):
+@pytest.mark.parametrize("cuda_core", [False, True], ids=["mma", "cudacore"])
+@pytest.mark.parametrize("shape", [(2, 64, 64), (1, 256, 128), (2, 1024, 128), (1, 40, 64), (1, 320, 64)])
+def test_attention_core(L, shape, cuda_core, monkeypatch):
     B, N, C = shape
+    if cuda_core:
+        monkeypatch.setenv("RLDM_ATTN_CUDACORE", "1")     # the ragged-N kernel, forced for every shape
     g = torch.Generator().manual_seed(N)
     qkv = torch.randn(B, N, 3 * C, generator=g)
     Hh = 8                                                 # tokens are (w, h) with H = 8; output is W-padded
