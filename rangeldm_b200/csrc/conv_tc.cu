@@ -21,6 +21,8 @@
 
 namespace rldm {
 
+int zero_fill(void* p, size_t bytes, cudaStream_t st);
+
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // fp16 elements = one 128 B swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
@@ -69,6 +71,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int it1 = min(it0 + p.iters_per_split, p.total_iters);
   const int n_it = it1 - it0;
 
+  pdl_trigger();     // let the next kernel's CTAs launch and run their prologue while this grid drains
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     if (TERMS > 1) tma_prefetch_desc(&tmAlo);
@@ -85,6 +88,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();        // everything above overlapped the previous kernel; below we touch its outputs
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp: lanes share the column loads) =============
@@ -239,8 +243,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const C
     attr_set = true;
   }
   dim3 grid((p.M_total + kBlockM - 1) / kBlockM, p.Cout / BLOCK_N, split);
-  conv_tc_kernel<BLOCK_N, STAGES, TERMS><<<grid, 192, smem, st>>>(tmA, tmAlo, tmB, p);
-  RLDM_LAUNCH_CHECK();
+  RLDM_CUDA(launch_pdl(conv_tc_kernel<BLOCK_N, STAGES, TERMS>, grid, dim3(192), smem, st, tmA, tmAlo, tmB, p));
   return 0;
 }
 
@@ -315,8 +318,10 @@ extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint1
   p.iters_per_split = (p.total_iters + split - 1) / split;
   split = (p.total_iters + p.iters_per_split - 1) / p.iters_per_split;
   cudaStream_t st = as_stream(stream);
-  if (split > 1)
-    RLDM_CUDA(cudaMemsetAsync(out, 0, static_cast<size_t>(p.M_total) * Cout * sizeof(float), st));
+  if (split > 1) {
+    const int rc = zero_fill(out, static_cast<size_t>(p.M_total) * Cout * sizeof(float), st);
+    if (rc) return rc;
+  }
   if (parts == 2) {
     if (BN == 128) return launch_conv<128, 3, 3>(tmA, tmAlo, tmB, p, split, st);
     return launch_conv<64, 4, 3>(tmA, tmAlo, tmB, p, split, st);

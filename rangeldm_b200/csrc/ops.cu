@@ -16,6 +16,11 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("RLDM_NO_PDL") ? 0 : 1;
+  return v == 1;
+}
 
 // ------------------------------------------------------------------------------------------------
 // GroupNorm statistics.  grid (chunks, B), block 256.  Thread = one float4 of channels, striding
@@ -24,6 +29,7 @@ void set_error(const char* fmt, ...) {
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
                 double* __restrict__ sums, int P, int G, int pix_per_block) {
+  pdl_entry();
   extern __shared__ double sh[];  // [2][G]
   const int C = c0 + c1;
   const int q_per_pix = C >> 2;                 // float4 quads per pixel
@@ -90,6 +96,7 @@ prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, 
             const double* __restrict__ sums, const float* __restrict__ gamma,
             const float* __restrict__ beta, float eps, int G, int silu, int up, int circular,
             __half* __restrict__ out, __half* __restrict__ out_lo, int W, int H, int pix_per_block) {
+  pdl_entry();
   extern __shared__ float shf[];  // scale[C], shift[C]
   const int C = c0 + c1;
   const int b = blockIdx.y;
@@ -173,6 +180,7 @@ __global__ void conv_ref_kernel(const __half* __restrict__ x, const __half* __re
                                 int temb_stride, const float* __restrict__ residual,
                                 float* __restrict__ out, int B, int W, int H, int Cin, int Cout,
                                 int ks, int stride, int pad_lo, int circular) {
+  pdl_entry();
   const int Wo = W / stride, Ho = H / stride;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t total = static_cast<size_t>(B) * Wo * Ho * Cout;
@@ -219,6 +227,7 @@ conv_in_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x
                float* __restrict__ out, int B, int W, int H, int Cout, int circular,
                int pix_per_block) {
   const int Cin = c0 + c1;
+  pdl_entry();
   const int q_per_pix = Cout >> 2;
   const int lanes_pix = blockDim.x / q_per_pix;
   const int quad = threadIdx.x % q_per_pix;
@@ -264,6 +273,7 @@ __global__ void __launch_bounds__(256)
 conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, const float* __restrict__ wgt,
                 const float* __restrict__ bias, float* __restrict__ out, int B, int W, int H,
                 int Cin, int circular) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const size_t pp = static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const size_t total_pix = static_cast<size_t>(B) * W * H;
@@ -318,6 +328,7 @@ constexpr int kAttnKT = 512;
 __global__ void __launch_bounds__(128)
 attention_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half* __restrict__ out_lo, int N,
                  int C, int H) {
+  pdl_entry();
   __shared__ float4 sk[kAttnKT * 2 + 16];
   __shared__ float4 sv[kAttnKT * 2 + 16];
   const int b = blockIdx.z, hd = blockIdx.y;
@@ -423,6 +434,7 @@ constexpr int kAtVP = kAtKT + 8;      // padded pitch of the transposed V rows (
 __global__ void __launch_bounds__(128)
 attention_tc_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half* __restrict__ out_lo,
                     int N, int C, int H) {
+  pdl_entry();
   __shared__ __align__(16) __half sk_hi[kAtKT * 8];
   __shared__ __align__(16) __half sk_lo[kAtKT * 8];
   __shared__ __align__(16) __half sv_hi[8 * kAtVP];      // transposed: [d][key]
@@ -542,6 +554,7 @@ __global__ void __launch_bounds__(512)
 temb_mlp_kernel(const float* __restrict__ t, const float* __restrict__ w1,
                 const float* __restrict__ b1, const float* __restrict__ w2,
                 const float* __restrict__ b2, float* __restrict__ scratch, int D0, int D4) {
+  pdl_entry();
   extern __shared__ float sh_t[];  // e0[D0], h1[D4]
   float* e0 = sh_t;
   float* h1 = sh_t + D0;
@@ -580,6 +593,7 @@ temb_mlp_kernel(const float* __restrict__ t, const float* __restrict__ w1,
 __global__ void __launch_bounds__(256)
 temb_proj_kernel(const float* __restrict__ semb, const float* __restrict__ wp,
                  const float* __restrict__ bp, float* __restrict__ out, int D4, int T) {
+  pdl_entry();
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -598,6 +612,7 @@ sched_step_kernel(const float* __restrict__ k, const float* __restrict__ x,
                   const float* __restrict__ eps, const float* __restrict__ x0_prev,
                   const float* __restrict__ noise, float* __restrict__ x_out,
                   float* __restrict__ x0_out, int64_t n) {
+  pdl_entry();
   const float k0 = k[0], k1 = k[1], k2 = k[2], k3 = k[3], k4 = k[4], k5 = k[5], k6 = k[6];
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
@@ -625,7 +640,29 @@ sched_step_kernel(const float* __restrict__ k, const float* __restrict__ x,
   }
 }
 
+// zero fill (replaces cudaMemsetAsync so the launch chain stays kernel -> kernel for PDL); n16 = 16-byte units
+__global__ void zero_kernel(uint4* __restrict__ p, size_t n16) {
+  pdl_entry();
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    p[i] = make_uint4(0, 0, 0, 0);
+}
+int zero_fill(void* p, size_t bytes, cudaStream_t st) {
+  if (bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(p) & 15) != 0) {
+    cudaError_t e = cudaMemsetAsync(p, 0, bytes, st);
+    if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return 2; }
+    return 0;
+  }
+  const size_t n16 = bytes / 16;
+  unsigned grid = static_cast<unsigned>((n16 + 255) / 256);
+  if (grid > 1184) grid = 1184;
+  if (grid == 0) return 0;
+  RLDM_CUDA(launch_pdl(zero_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<uint4*>(p), n16));
+  return 0;
+}
+
 __global__ void scale_kernel(const float* __restrict__ x, float a, float* __restrict__ y, int64_t n) {
+  pdl_entry();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) y[i] = a * x[i];
 }
@@ -633,6 +670,7 @@ __global__ void scale_kernel(const float* __restrict__ x, float a, float* __rest
 // layout helpers: ref (B,C,W,H) <-> cl (B,W,H,C); thread per element (tiny boundary tensors only).
 __global__ void ref_to_cl_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int P,
                                  size_t total) {
+  pdl_entry();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // dst index
   if (i >= total) return;
   const int c = i % C;
@@ -643,6 +681,7 @@ __global__ void ref_to_cl_kernel(const float* __restrict__ src, float* __restric
 }
 __global__ void cl_to_ref_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int P,
                                  size_t total) {
+  pdl_entry();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // dst index
   if (i >= total) return;
   const int p = i % P;
@@ -671,8 +710,7 @@ extern "C" int rldm_gn_stats(const float* x0, int c0, const float* x1, int c1, d
   chunks = (P + ppb - 1) / ppb;
   const int q = C / 4;   // block = whole pixels so each thread keeps one channel quad in registers
   const int threads = q <= 256 ? (256 / q) * q : 256;
-  gn_stats_kernel<<<dim3(chunks, B), threads, 2 * G * sizeof(double), as_stream(stream)>>>(
-      x0, c0, x1, c1, sums, P, G, ppb);
+  RLDM_CUDA(launch_pdl(gn_stats_kernel, dim3(chunks, B), dim3(threads), 2 * G * sizeof(double), as_stream(stream), x0, c0, x1, c1, sums, P, G, ppb));
   RLDM_LAUNCH_CHECK();
   return 0;
 }
@@ -689,9 +727,8 @@ extern "C" int rldm_prep(const float* x0, int c0, const float* x1, int c1, const
   int ppb = (out_pix + chunks - 1) / chunks;
   if (ppb < 8) ppb = 8;
   chunks = (out_pix + ppb - 1) / ppb;
-  prep_kernel<<<dim3(chunks, B), 256, 2 * C * sizeof(float), as_stream(stream)>>>(
-      x0, c0, x1, c1, sums, gamma, beta, eps, G, silu, up, circular, reinterpret_cast<__half*>(out),
-      reinterpret_cast<__half*>(out_lo), W, H, ppb);
+  RLDM_CUDA(launch_pdl(prep_kernel, dim3(chunks, B), dim3(256), 2 * C * sizeof(float), as_stream(stream), x0, c0, x1, c1, sums, gamma, beta, eps, G, silu, up, circular, reinterpret_cast<__half*>(out),
+      reinterpret_cast<__half*>(out_lo), W, H, ppb));
   RLDM_LAUNCH_CHECK();
   return 0;
 }
@@ -701,10 +738,9 @@ extern "C" int rldm_conv_ref(const uint16_t* x, const uint16_t* x_lo, const uint
                              int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
                              int circular, void* stream) {
   const size_t total = static_cast<size_t>(B) * (W / stride) * (H / stride) * Cout;
-  conv_ref_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(x_lo),
+  RLDM_CUDA(launch_pdl(conv_ref_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, as_stream(stream), reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(x_lo),
       reinterpret_cast<const __half*>(wgt), bias, temb,
-      temb_stride, residual, out, B, W, H, Cin, Cout, ks, stride, pad_lo, circular);
+      temb_stride, residual, out, B, W, H, Cin, Cout, ks, stride, pad_lo, circular));
   RLDM_LAUNCH_CHECK();
   return 0;
 }
@@ -716,8 +752,7 @@ extern "C" int rldm_conv_in(const float* x0, int c0, const float* x1, int c1, co
   RLDM_CHECK(Cout % 4 == 0 && Cout <= 1024 && 256 % (Cout / 4) == 0, "conv_in: unsupported Cout=%d", Cout);
   const size_t total_pix = static_cast<size_t>(B) * W * H;
   const int ppb = 32;
-  conv_in_kernel<<<static_cast<unsigned>((total_pix + ppb - 1) / ppb), 256, 0, as_stream(stream)>>>(
-      x0, c0, x1, c1, wgt, bias, out, B, W, H, Cout, circular, ppb);
+  RLDM_CUDA(launch_pdl(conv_in_kernel, dim3(static_cast<unsigned>((total_pix + ppb - 1) / ppb)), dim3(256), 0, as_stream(stream), x0, c0, x1, c1, wgt, bias, out, B, W, H, Cout, circular, ppb));
   RLDM_LAUNCH_CHECK();
   return 0;
 }
@@ -731,9 +766,9 @@ extern "C" int rldm_conv_out(const uint16_t* x, const uint16_t* x_lo, const floa
   const __half* xl = reinterpret_cast<const __half*>(x_lo);
   cudaStream_t st = as_stream(stream);
   switch (Cout) {
-    case 2: conv_out_kernel<2><<<grid, 256, 0, st>>>(xh, xl, wgt, bias, out, B, W, H, Cin, circular); break;
-    case 4: conv_out_kernel<4><<<grid, 256, 0, st>>>(xh, xl, wgt, bias, out, B, W, H, Cin, circular); break;
-    case 8: conv_out_kernel<8><<<grid, 256, 0, st>>>(xh, xl, wgt, bias, out, B, W, H, Cin, circular); break;
+    case 2: RLDM_CUDA(launch_pdl(conv_out_kernel<2>, dim3(grid), dim3(256), 0, st, xh, xl, wgt, bias, out, B, W, H, Cin, circular)); break;
+    case 4: RLDM_CUDA(launch_pdl(conv_out_kernel<4>, dim3(grid), dim3(256), 0, st, xh, xl, wgt, bias, out, B, W, H, Cin, circular)); break;
+    case 8: RLDM_CUDA(launch_pdl(conv_out_kernel<8>, dim3(grid), dim3(256), 0, st, xh, xl, wgt, bias, out, B, W, H, Cin, circular)); break;
     default: RLDM_CHECK(false, "conv_out: Cout must be 2, 4 or 8 (got %d)", Cout);
   }
   RLDM_LAUNCH_CHECK();
@@ -744,14 +779,12 @@ extern "C" int rldm_attention(const float* qkv, uint16_t* out, uint16_t* out_lo,
                               int H, void* stream) {
   RLDM_CHECK(C % 8 == 0, "attention: C %% 8 != 0");
   if (N % 64 == 0 && !getenv("RLDM_ATTN_CUDACORE")) {   // tensor-path kernel; the CUDA-core kernel covers ragged N
-    attention_tc_kernel<<<dim3(N / 64, C / 8, B), 128, 0, as_stream(stream)>>>(
-        qkv, reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H);
+    RLDM_CUDA(launch_pdl(attention_tc_kernel, dim3(N / 64, C / 8, B), dim3(128), 0, as_stream(stream), qkv, reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H));
     RLDM_LAUNCH_CHECK();
     return 0;
   }
   const int threads = N >= 128 ? 128 : ((N + 31) / 32) * 32;
-  attention_kernel<<<dim3((N + threads - 1) / threads, C / 8, B), threads, 0, as_stream(stream)>>>(
-      qkv, reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H);
+  RLDM_CUDA(launch_pdl(attention_kernel, dim3((N + threads - 1) / threads, C / 8, B), dim3(threads), 0, as_stream(stream), qkv, reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H));
   RLDM_LAUNCH_CHECK();
   return 0;
 }
@@ -760,10 +793,10 @@ extern "C" int rldm_temb(const float* t, const float* w1, const float* b1, const
                          const float* b2, const float* wp, const float* bp, float* scratch,
                          float* out, int B, int D0, int D4, int T, void* stream) {
   cudaStream_t st = as_stream(stream);
-  temb_mlp_kernel<<<B, 512, (D0 + D4) * sizeof(float), st>>>(t, w1, b1, w2, b2, scratch, D0, D4);
+  RLDM_CUDA(launch_pdl(temb_mlp_kernel, dim3(B), dim3(512), (D0 + D4) * sizeof(float), st, t, w1, b1, w2, b2, scratch, D0, D4));
   RLDM_LAUNCH_CHECK();
   if (T > 0) {
-    temb_proj_kernel<<<dim3((T + 7) / 8, B), 256, 0, st>>>(scratch, wp, bp, out, D4, T);
+    RLDM_CUDA(launch_pdl(temb_proj_kernel, dim3((T + 7) / 8, B), dim3(256), 0, st, scratch, wp, bp, out, D4, T));
     RLDM_LAUNCH_CHECK();
   }
   return 0;
@@ -773,27 +806,26 @@ extern "C" int rldm_sched_step(const float* k, const float* x, const float* eps,
                                const float* x0_prev, const float* noise, float* x_out,
                                float* x0_out, int64_t n, void* stream) {
   const int64_t nthreads = (n + 3) / 4;
-  sched_step_kernel<<<static_cast<unsigned>((nthreads + 255) / 256), 256, 0, as_stream(stream)>>>(
-      k, x, eps, x0_prev, noise, x_out, x0_out, n);
+  RLDM_CUDA(launch_pdl(sched_step_kernel, dim3(static_cast<unsigned>((nthreads + 255) / 256)), dim3(256), 0, as_stream(stream), k, x, eps, x0_prev, noise, x_out, x0_out, n));
   RLDM_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int rldm_scale(const float* x, float a, float* y, int64_t n, void* stream) {
-  scale_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(x, a, y, n);
+  RLDM_CUDA(launch_pdl(scale_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, as_stream(stream), x, a, y, n));
   RLDM_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int rldm_ref_to_cl(const float* src, float* dst, int B, int C, int W, int H, void* stream) {
   const size_t total = static_cast<size_t>(B) * C * W * H;
-  ref_to_cl_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, as_stream(stream)>>>(src, dst, C, W * H, total);
+  RLDM_CUDA(launch_pdl(ref_to_cl_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, as_stream(stream), src, dst, C, W * H, total));
   RLDM_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int rldm_cl_to_ref(const float* src, float* dst, int B, int C, int W, int H, void* stream) {
   const size_t total = static_cast<size_t>(B) * C * W * H;
-  cl_to_ref_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, as_stream(stream)>>>(src, dst, C, W * H, total);
+  RLDM_CUDA(launch_pdl(cl_to_ref_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, as_stream(stream), src, dst, C, W * H, total));
   RLDM_LAUNCH_CHECK();
   return 0;
 }
@@ -845,11 +877,9 @@ extern "C" int rldm_run(const rldm_op* ops, int n_ops, void* stream) {
                              (const float*)o.p[3], (const float*)o.p[4], (float*)o.p[5], (float*)o.p[6],
                              o.n, stream);
         break;
-      case RLDM_OP_MEMSET: {
-        cudaError_t e = cudaMemsetAsync(o.p[0], 0, static_cast<size_t>(o.n), as_stream(stream));
-        if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); rc = 2; }
+      case RLDM_OP_MEMSET:
+        rc = zero_fill(o.p[0], static_cast<size_t>(o.n), as_stream(stream));
         break;
-      }
       case RLDM_OP_AXPY:
         rc = rldm_scale((const float*)o.p[0], o.f[0], (float*)o.p[1], o.n, stream);
         break;
