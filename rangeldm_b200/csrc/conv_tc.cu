@@ -202,8 +202,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         } else {
+          float4* o4 = reinterpret_cast<float4*>(out_row + nc * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(out_row + nc * 32 + j, v[j]);
+          for (int j = 0; j < 8; ++j)   // red.global.add.v4.f32: one 16 B reduction instead of four scalar ones
+            atomicAdd(o4 + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
         }
       }
     }
@@ -312,7 +314,8 @@ extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint1
   int split = split_k;
   if (split <= 0) {  // auto: fill the 148 SMs (2 CTAs each) when the tile grid is small
     split = 1;
-    while (tiles * split * 2 <= 296 && p.total_iters / (split * 2) >= 4 && split < 16) split *= 2;
+    const int cap = parts == 2 ? 160 : 296;   // resident CTAs: 1 per SM in split-fp16 mode, 2 otherwise
+    while (tiles * split * 2 <= cap && p.total_iters / (split * 2) >= 4 && split < 16) split *= 2;
   }
   if (split > p.total_iters) split = p.total_iters;
   p.iters_per_split = (p.total_iters + split - 1) / split;

@@ -220,47 +220,69 @@ __global__ void conv_ref_kernel(const __half* __restrict__ x, const __half* __re
 
 // ------------------------------------------------------------------------------------------------
 // conv_in: (B,Cin,W,H) fp32 ref layout -> (B,W,H,Cout) fp32 cl, 3x3 circular/zero, Cin <= 16.
-// block 256 = (256/(Cout/4)) pixels x (Cout/4) channel quads; grid covers all pixels.
+// One block = kCinPix consecutive pixels.  The im2col rows of those pixels (9*Cin floats each, wrap and zero
+// pad resolved once) and the whole weight matrix [9*Cin][Cout] are staged in shared memory; then thread =
+// (pixel, 4 output channels) runs a K-long FMA chain on broadcast/conflict-free shared loads.
+constexpr int kCinPix = 32;
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
                const float* __restrict__ wgt, const float* __restrict__ bias,
-               float* __restrict__ out, int B, int W, int H, int Cout, int circular,
-               int pix_per_block) {
+               float* __restrict__ out, int B, int W, int H, int Cout, int circular) {
+  extern __shared__ float sh_ci[];
   const int Cin = c0 + c1;
-  pdl_entry();
+  const int K = 9 * Cin;
+  float* w_s = sh_ci;                    // [K][Cout]
+  float* in_s = sh_ci + K * Cout;        // [kCinPix][K]
+  pdl_trigger();
+  for (int i = threadIdx.x * 4; i < K * Cout; i += blockDim.x * 4)    // weights do not depend on prior kernels
+    *reinterpret_cast<float4*>(w_s + i) = __ldg(reinterpret_cast<const float4*>(wgt + i));
+  pdl_wait();
+  const size_t total_pix = static_cast<size_t>(B) * W * H;
+  const size_t p_begin = static_cast<size_t>(blockIdx.x) * kCinPix;
+  for (int idx = threadIdx.x; idx < kCinPix * K; idx += blockDim.x) {
+    const int p = idx / K, k = idx - p * K;
+    const int tap = k / Cin, c = k - tap * Cin;
+    const int i = tap / 3, j = tap - i * 3;
+    const size_t pp = p_begin + p;
+    float a = 0.f;
+    if (pp < total_pix) {
+      const int h = pp % H;
+      const int w = (pp / H) % W;
+      const int b = pp / (static_cast<size_t>(H) * W);
+      int wi = w + i - 1;
+      const int hj = h + j - 1;
+      bool ok = hj >= 0 && hj < H;
+      if (circular) {
+        if (wi < 0) wi += W;
+        if (wi >= W) wi -= W;
+      } else {
+        ok = ok && wi >= 0 && wi < W;
+      }
+      if (ok)
+        a = (c < c0) ? __ldg(x0 + ((static_cast<size_t>(b) * c0 + c) * W + wi) * H + hj)
+                     : __ldg(x1 + ((static_cast<size_t>(b) * c1 + (c - c0)) * W + wi) * H + hj);
+    }
+    in_s[idx] = a;
+  }
+  __syncthreads();
   const int q_per_pix = Cout >> 2;
   const int lanes_pix = blockDim.x / q_per_pix;
   const int quad = threadIdx.x % q_per_pix;
   const int co = quad << 2;
-  const size_t total_pix = static_cast<size_t>(B) * W * H;
-  const size_t p_begin = static_cast<size_t>(blockIdx.x) * pix_per_block;
   const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + co)) : make_float4(0, 0, 0, 0);
-  for (size_t pp = p_begin + threadIdx.x / q_per_pix; pp < min(p_begin + pix_per_block, total_pix);
-       pp += lanes_pix) {
-    const int h = pp % H;
-    const int w = (pp / H) % W;
-    const int b = pp / (static_cast<size_t>(H) * W);
+  for (int p = threadIdx.x / q_per_pix; p < kCinPix; p += lanes_pix) {
+    const size_t pp = p_begin + p;
+    if (pp >= total_pix) break;
     float4 acc = bv;
-    for (int i = 0; i < 3; ++i) {
-      int wi = w + i - 1;
-      if (circular) {
-        if (wi < 0) wi += W;
-        if (wi >= W) wi -= W;
-      } else if (wi < 0 || wi >= W) continue;
-      for (int j = 0; j < 3; ++j) {
-        const int hj = h + j - 1;
-        if (hj < 0 || hj >= H) continue;
-        for (int c = 0; c < Cin; ++c) {
-          const float a = (c < c0) ? __ldg(x0 + ((static_cast<size_t>(b) * c0 + c) * W + wi) * H + hj)
-                                   : __ldg(x1 + ((static_cast<size_t>(b) * c1 + (c - c0)) * W + wi) * H + hj);
-          const float4 wv = __ldg(reinterpret_cast<const float4*>(
-              wgt + (static_cast<size_t>(i * 3 + j) * Cin + c) * Cout + co));
-          acc.x = fmaf(a, wv.x, acc.x);
-          acc.y = fmaf(a, wv.y, acc.y);
-          acc.z = fmaf(a, wv.z, acc.z);
-          acc.w = fmaf(a, wv.w, acc.w);
-        }
-      }
+    const float* ip = in_s + p * K;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const float a = ip[k];
+      const float4 wv = *reinterpret_cast<const float4*>(w_s + k * Cout + co);
+      acc.x = fmaf(a, wv.x, acc.x);
+      acc.y = fmaf(a, wv.y, acc.y);
+      acc.z = fmaf(a, wv.z, acc.z);
+      acc.w = fmaf(a, wv.w, acc.w);
     }
     *reinterpret_cast<float4*>(out + pp * Cout + co) = acc;
   }
@@ -751,8 +773,16 @@ extern "C" int rldm_conv_in(const float* x0, int c0, const float* x1, int c1, co
   RLDM_CHECK(x1 != nullptr || c1 == 0, "conv_in: x1 NULL with c1=%d", c1);
   RLDM_CHECK(Cout % 4 == 0 && Cout <= 1024 && 256 % (Cout / 4) == 0, "conv_in: unsupported Cout=%d", Cout);
   const size_t total_pix = static_cast<size_t>(B) * W * H;
-  const int ppb = 32;
-  RLDM_CUDA(launch_pdl(conv_in_kernel, dim3(static_cast<unsigned>((total_pix + ppb - 1) / ppb)), dim3(256), 0, as_stream(stream), x0, c0, x1, c1, wgt, bias, out, B, W, H, Cout, circular, ppb));
+  const int K = 9 * (c0 + c1);
+  const size_t smem = (static_cast<size_t>(K) * Cout + static_cast<size_t>(kCinPix) * K) * sizeof(float);
+  RLDM_CHECK(smem <= 200 * 1024, "conv_in: 9*Cin*Cout too large for shared memory (Cin=%d Cout=%d)", c0 + c1, Cout);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    RLDM_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    smem_set = 200 * 1024;
+  }
+  RLDM_CUDA(launch_pdl(conv_in_kernel, dim3(static_cast<unsigned>((total_pix + kCinPix - 1) / kCinPix)), dim3(256), smem,
+                       as_stream(stream), x0, c0, x1, c1, wgt, bias, out, B, W, H, Cout, circular));
   RLDM_LAUNCH_CHECK();
   return 0;
 }

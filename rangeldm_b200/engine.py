@@ -370,6 +370,7 @@ class UNetPlan:
                p=(self.t_buf, bd.f32(te.linear_1.weight), bd.f32(te.linear_1.bias), bd.f32(te.linear_2.weight),
                   bd.f32(te.linear_2.bias), wp, bp, scratch, temb_out), launches=2)
         bd.temb = (temb_out, T)
+        self.temb_out, self.temb_T = temb_out, T
 
         # ---- network ----
         h = bd.conv_in(model.conv_in, self.x_in, cin - cond_channels, self.cond, cond_channels, W, H)

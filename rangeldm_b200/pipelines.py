@@ -162,13 +162,29 @@ class FusedSampler:
         if bool((host_coef[:, 6] != 0).any()):
             self.noise = pg.hold(torch.zeros((self.steps,) + tuple(self.latents.shape), device=dev))
         uses_prev = bool((host_coef[:, 4] != 0).any())
+        # The time-embedding MLP and all per-resnet projections depend only on the timestep table: evaluate them
+        # for every step ONCE here (same kernel, rldm_temb) and let step i's convs read row i of the table.
+        T = self.plan.temb_T
+        temb_all = pg.hold(torch.zeros(self.steps, batch, T, device=dev))
+        temb_base = self.plan.temb_out.data_ptr()
+        if dev.type == "cuda":
+            for i in range(self.steps):
+                for op in self.plan.prog.ops:
+                    if op.kind == _lib.OP_TEMB:
+                        cp = RldmOp.from_buffer_copy(op)
+                        cp.p[0] = ttab[i].data_ptr()
+                        cp.p[8] = temb_all[i].data_ptr()
+                        _lib.check(_lib.lib().rldm_run((RldmOp * 1)(cp), 1, _lib.stream_ptr()))
+            torch.cuda.synchronize()
         for i in range(self.steps):
             for op in self.plan.prog.ops:
+                if op.kind == _lib.OP_TEMB:
+                    continue
                 cp = RldmOp.from_buffer_copy(op)
-                if cp.kind == _lib.OP_TEMB:
-                    cp.p[0] = ttab[i].data_ptr()
+                if cp.kind in (_lib.OP_CONV_TC, _lib.OP_CONV_REF) and cp.p[3]:
+                    cp.p[3] = temb_all[i].data_ptr() + (cp.p[3] - temb_base)
                 pg.ops.append(cp)
-            pg.n_launch += self.plan.prog.n_launch
+            pg.n_launch += self.plan.prog.n_launch - 2
             noise_i = self.noise[i] if (self.noise is not None and float(host_coef[i, 6]) != 0.0) else None
             pg.add(_lib.OP_SCHED_STEP, p=(coef[i], self.latents, self.plan.out,
                                           x0buf if (uses_prev and i > 0) else None, noise_i, self.latents,
