@@ -74,13 +74,18 @@ int rldm_prep(const float* x0, int c0, const float* x1, int c1, const double* su
  *   circular: informational (1 = the producer wrote wrap halos, 0 = zero halos); the kernel reads
  *         whatever the halo columns of `x` hold.
  *   epilogue: out = acc + bias[c] + temb[b*temb_stride + c] + residual[b,wo,ho,c] (NULL = skip)
- *   split_k: 0 = choose automatically; > 1: the K loop (taps x channel chunks) is split over
- *         split_k CTAs per tile which atomically accumulate into `out` (zeroed by this call);
- *         `residual` must then not alias `out`.
+ *   split_k: 0 = choose automatically; 2, 4 or 8: the K loop (taps x channel chunks) is split over a
+ *         thread-block CLUSTER of split_k CTAs per tile; partial tiles are reduced through distributed
+ *         shared memory in a fixed order (deterministic; no atomics, no zero fill).
+ *   stats / stats_groups: optional fused GroupNorm statistics of the finished output: (sum, sum of
+ *         squares) per (image, group) are ADDED into stats[B][stats_groups][2] (double, zeroed by the
+ *         caller), replacing the rldm_gn_stats pass of the next normalisation.  Needs
+ *         Cout/stats_groups in {2,4,8,16} and Wo*Ho >= 64.
  * Requires Ho a power of two <= 128, Wo*Ho a multiple or a divisor of 128, Cout % 64 == 0. */
 int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias, const float* temb,
                  int temb_stride, const float* residual, float* out, int B, int W, int H, int Cin,
-                 int Cout, int ks, int stride, int pad_lo, int circular, int split_k, void* stream);
+                 int Cout, int ks, int stride, int pad_lo, int circular, int split_k, double* stats,
+                 int stats_groups, void* stream);
 
 /* CUDA-core restatement of rldm_conv_tc with the identical contract (split_k ignored); used by the
  * GPU tests to isolate tensor-core descriptor bugs from precision, never by the product path. */

@@ -30,7 +30,7 @@ SIGNATURES = {
     "rldm_prep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int,
                           c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rldm_conv_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
-                     + [c_int] * 10 + [c_void_p]),
+                     + [c_int] * 10 + [c_void_p, c_int, c_void_p]),
     "rldm_conv_ref": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
                       + [c_int] * 9 + [c_void_p]),
     "rldm_conv_in": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 5

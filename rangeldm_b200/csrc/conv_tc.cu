@@ -21,8 +21,6 @@
 
 namespace rldm {
 
-int zero_fill(void* p, size_t bytes, cudaStream_t st);
-
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // fp16 elements = one 128 B swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
@@ -39,8 +37,25 @@ struct ConvParams {
   int Cout;
   int ks, stride, pad_lo, circular;
   int total_iters;  // (Cin/64) * ks*ks
-  int iters_per_split;
+  double* stats;    // optional GroupNorm moments of the output: [B][stats_G][2]
+  int stats_cpg, stats_G;
 };
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 // TERMS = 1: D += A*W with fp16 operands (11-bit significands).
 // TERMS = 3: split-fp16 ("fp16x3"): A = Ah + Al, W = Wh + Wl (each part fp16), D += Ah*Wh + Al*Wh + Ah*Wl --
@@ -54,6 +69,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int kParts = TERMS == 1 ? 1 : 2;
   constexpr int kStageBytes = kParts * (kABytes + kBBytes);   // [A_hi][A_lo][B_hi][B_lo]
   constexpr int kBOff = kParts * kABytes;
+  constexpr int kStagePitch = BLOCK_N + 4;                     // floats per row of the epilogue staging tile
+  static_assert(kBlockM * kStagePitch * 4 <= STAGES * kStageBytes, "staging tile must fit in the pipeline stages");
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024 B alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -67,9 +84,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kBlockM;
   const int n0 = blockIdx.y * BLOCK_N;
-  const int it0 = blockIdx.z * p.iters_per_split;
-  const int it1 = min(it0 + p.iters_per_split, p.total_iters);
-  const int n_it = it1 - it0;
+  const int it0 = static_cast<int>(static_cast<long long>(blockIdx.z) * p.total_iters / gridDim.z);
+  const int it1 = static_cast<int>(static_cast<long long>(blockIdx.z + 1) * p.total_iters / gridDim.z);
+  const int n_it = it1 - it0;                    // >= 1: the host keeps gridDim.z <= total_iters
 
   pdl_trigger();     // let the next kernel's CTAs launch and run their prologue while this grid drains
   if (warp == 0 && lane == 0) {
@@ -157,59 +174,150 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else {
-    // ===================== epilogue: TMEM -> registers -> global ==============================
+    // ===================== epilogue phase 1: TMEM -> registers -> shared staging tile =========
+    // The pipeline stages are dead once tmem_full fires (all TMA writes consumed, all MMA reads done), so the
+    // fp32 accumulator tile [128][BLOCK_N] is staged over them (row pitch +4 floats: conflict-free float4).
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;
-    const int m = m0 + row;
-    const bool valid = m < p.M_total;
-    const bool lead = blockIdx.z == 0;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int b = valid ? m / p.pix_per_img : 0;
-    float* out_row = p.out + static_cast<size_t>(m) * p.Cout + n0;
-    const float* res_row = p.residual ? p.residual + static_cast<size_t>(m) * p.Cout + n0 : nullptr;
-    const float* temb_row = p.temb ? p.temb + static_cast<size_t>(b) * p.temb_stride + n0 : nullptr;
-    const float* bias_row = p.bias ? p.bias + n0 : nullptr;
+    float* stage_row = reinterpret_cast<float*>(smem) + row * kStagePitch;
 #pragma unroll 1
     for (int nc = 0; nc < BLOCK_N / 32; ++nc) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + nc * 32, r);
       tmem_ld_wait();
-      if (valid) {
-        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (lead) {
-          if (bias_row) {
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(stage_row + nc * 32 + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    }
+  }
+  // ======================= epilogue phase 2: (cluster) reduce + bias/temb/residual + stats + store ============
+  // split-K: the `nsplit` CTAs of a cluster (same tile, different K slices) each staged a partial tile; CTA `rank`
+  // now owns rows [rank*128/nsplit, ...) and sums them over all ranks through distributed shared memory in a
+  // fixed order (deterministic, no atomics, no zero-fill).  nsplit == 1: same code on the local tile.
+  const int nsplit = gridDim.z;
+  tc_fence_before();
+  if (nsplit > 1) {
+    cluster_sync_all();
+  } else {
+    __syncthreads();
+  }
+  if (warp >= 2) {
+    const int ew = warp - 2;                              // 0..3
+    constexpr int kLanesPerRow = BLOCK_N / 4;             // 32 (BN=128) or 16 (BN=64)
+    constexpr int kRowsPerIter = 32 / kLanesPerRow;       // 1 or 2
+    const int rows_cta = kBlockM / nsplit;                // rows this CTA finalises
+    const int rows_warp = rows_cta / 4;                   // contiguous rows per epilogue warp (>= 4)
+    const int r_begin = blockIdx.z * rows_cta + ew * rows_warp;
+    const int col = (lane % kLanesPerRow) * 4;
+    const int rsub = lane / kLanesPerRow;
+    const uint32_t stage_u32 = smem_u32(smem);
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col));
+    // all rows of one warp lie in one image (pix_per_img is a power of two >= 64 >= rows_warp*kRowsPerIter... see host)
+    const int m_first = m0 + r_begin;
+    const int bimg = min(m_first, p.M_total - 1) / p.pix_per_img;
+    if (p.temb) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.temb + static_cast<size_t>(bimg) * p.temb_stride + n0 + col));
+      bias4.x += t4.x; bias4.y += t4.y; bias4.z += t4.z; bias4.w += t4.w;
+    }
+    float s01 = 0.f, q01 = 0.f, s23 = 0.f, q23 = 0.f;     // moments of channel pairs (0,1) and (2,3)
+    constexpr int kU = 4;                                 // rows in flight per lane: residual loads issued together
+    for (int rr0 = rsub; rr0 < rows_warp; rr0 += kRowsPerIter * kU) {
+      float4 res[kU], acc[kU];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(bias_row + nc * 32 + j);
-          }
-          if (temb_row) {
+      for (int u = 0; u < kU; ++u) {
+        const int rr = rr0 + u * kRowsPerIter;
+        const int m = m0 + r_begin + rr;
+        res[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.residual && rr < rows_warp && m < p.M_total)
+          res[u] = __ldg(reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(m) * p.Cout + n0 + col));
+      }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(temb_row + nc * 32 + j);
-          }
-          if (res_row) {
-            const float4* r4 = reinterpret_cast<const float4*>(res_row + nc * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 t = __ldg(r4 + j);
-              v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+      for (int u = 0; u < kU; ++u) {
+        const int rr = rr0 + u * kRowsPerIter;
+        acc[u] = bias4;
+        if (rr < rows_warp) {
+          const int r = r_begin + rr;
+          if (nsplit > 1) {
+            const uint32_t local = stage_u32 + (r * kStagePitch + col) * 4;
+            for (int sidx = 0; sidx < nsplit; ++sidx) {
+              const float4 v = ld_dsmem_f4(mapa_u32(local, sidx));
+              acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
             }
+          } else {
+            const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem) + r * kStagePitch + col);
+            acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
           }
         }
-        if (gridDim.z == 1) {
-          float4* o4 = reinterpret_cast<float4*>(out_row + nc * 32);
+      }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-          float4* o4 = reinterpret_cast<float4*>(out_row + nc * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)   // red.global.add.v4.f32: one 16 B reduction instead of four scalar ones
-            atomicAdd(o4 + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+      for (int u = 0; u < kU; ++u) {
+        const int rr = rr0 + u * kRowsPerIter;
+        const int m = m0 + r_begin + rr;
+        if (rr < rows_warp && m < p.M_total) {
+          float4 v = acc[u];
+          v.x += res[u].x; v.y += res[u].y; v.z += res[u].z; v.w += res[u].w;
+          *reinterpret_cast<float4*>(p.out + static_cast<size_t>(m) * p.Cout + n0 + col) = v;
+          s01 += v.x + v.y; q01 += v.x * v.x + v.y * v.y;
+          s23 += v.z + v.w; q23 += v.z * v.z + v.w * v.w;
+        }
+      }
+    }
+    if (p.stats) {
+      // GroupNorm moments of the finished output, per (image, group): channel pairs -> lanes -> the 4 epilogue
+      // warps (shared memory) -> ONE double atomic per (group, moment) and image for the whole CTA.
+      __shared__ float red_s[4][BLOCK_N / 2], red_q[4][BLOCK_N / 2];
+      __shared__ int red_b[4];
+      const int cpg = p.stats_cpg;                        // 2, 4, 8 or 16 channels per group
+      if (kRowsPerIter == 2) {
+        s01 += __shfl_xor_sync(0xffffffffu, s01, 16); q01 += __shfl_xor_sync(0xffffffffu, q01, 16);
+        s23 += __shfl_xor_sync(0xffffffffu, s23, 16); q23 += __shfl_xor_sync(0xffffffffu, q23, 16);
+      }
+      const bool writer_row = (kRowsPerIter == 1) || rsub == 0;
+      int nslots;
+      if (cpg == 2) {
+        nslots = BLOCK_N / 2;
+        if (writer_row) {
+          red_s[ew][col / 2] = s01; red_q[ew][col / 2] = q01;
+          red_s[ew][col / 2 + 1] = s23; red_q[ew][col / 2 + 1] = q23;
+        }
+      } else {
+        nslots = BLOCK_N / cpg;
+        float sg = s01 + s23, qg = q01 + q23;
+        for (int o = 1; o < cpg / 4; o <<= 1) {
+          sg += __shfl_xor_sync(0xffffffffu, sg, o);
+          qg += __shfl_xor_sync(0xffffffffu, qg, o);
+        }
+        if (writer_row && (lane % (cpg / 4)) == 0) { red_s[ew][col / cpg] = sg; red_q[ew][col / cpg] = qg; }
+      }
+      if (lane == 0) red_b[ew] = m_first < p.M_total ? bimg : -1;
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps only
+      const int t = ew * 32 + lane;
+      if (t < nslots) {
+        const int g = (n0 / (cpg == 2 ? 2 : cpg)) + t;
+        double ds = 0.0, dq = 0.0;
+        int cur = red_b[0];
+        for (int e = 0; e < 4; ++e) {
+          const int be = red_b[e];
+          if (be != cur) {
+            if (cur >= 0) {
+              double* st = p.stats + (static_cast<size_t>(cur) * p.stats_G + g) * 2;
+              atomicAdd(st, ds); atomicAdd(st + 1, dq);
+            }
+            cur = be; ds = 0.0; dq = 0.0;
+          }
+          ds += static_cast<double>(red_s[e][t]); dq += static_cast<double>(red_q[e][t]);
+        }
+        if (cur >= 0) {
+          double* st = p.stats + (static_cast<size_t>(cur) * p.stats_G + g) * 2;
+          atomicAdd(st, ds); atomicAdd(st + 1, dq);
         }
       }
     }
   }
+  if (nsplit > 1) cluster_sync_all();     // nobody leaves while a peer may still read its staging tile
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<BLOCK_N>(tmem_base);
@@ -245,7 +353,28 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const C
     attr_set = true;
   }
   dim3 grid((p.M_total + kBlockM - 1) / kBlockM, p.Cout / BLOCK_N, split);
-  RLDM_CUDA(launch_pdl(conv_tc_kernel<BLOCK_N, STAGES, TERMS>, grid, dim3(192), smem, st, tmA, tmAlo, tmB, p));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (split > 1) {   // the K splits of one tile form a thread-block cluster (DSMEM reduction in the epilogue)
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = split;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  RLDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, STAGES, TERMS>, tmA, tmAlo, tmB, p));
   return 0;
 }
 
@@ -256,7 +385,7 @@ using namespace rldm;
 extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias,
                             const float* temb, int temb_stride, const float* residual, float* out,
                             int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
-                            int circular, int split_k, void* stream) {
+                            int circular, int split_k, double* stats, int stats_groups, void* stream) {
   RLDM_CHECK(ks == 1 || ks == 3, "conv_tc: ks must be 1 or 3 (got %d)", ks);
   RLDM_CHECK(stride == 1 || stride == 2, "conv_tc: stride must be 1 or 2 (got %d)", stride);
   RLDM_CHECK(Cin % 64 == 0, "conv_tc: Cin %% 64 != 0 (got %d)", Cin);
@@ -310,21 +439,23 @@ extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint1
   p.Cout = Cout;
   p.ks = ks; p.stride = stride; p.pad_lo = pad_lo; p.circular = circular;
   p.total_iters = (Cin / kBlockK) * ks * ks;
+  p.stats = stats;
+  p.stats_G = stats_groups;
+  p.stats_cpg = stats_groups > 0 ? Cout / stats_groups : 0;
+  RLDM_CHECK(!stats || (Cout % stats_groups == 0 && (p.stats_cpg == 2 || p.stats_cpg == 4 || p.stats_cpg == 8 ||
+                                                     p.stats_cpg == 16)),
+             "conv_tc: fused GroupNorm statistics need 2, 4, 8 or 16 channels per group (Cout=%d, G=%d)", Cout, stats_groups);
+  RLDM_CHECK(pix >= 64 || !stats, "conv_tc: fused statistics need >= 64 pixels per image");
   const int tiles = ((p.M_total + kBlockM - 1) / kBlockM) * (Cout / BN);
   int split = split_k;
-  if (split <= 0) {  // auto: fill the 148 SMs (2 CTAs each) when the tile grid is small
+  if (split <= 0) {  // auto: fill the 148 SMs when the tile grid is small (clusters of <= 8 CTAs along K)
     split = 1;
     const int cap = parts == 2 ? 160 : 296;   // resident CTAs: 1 per SM in split-fp16 mode, 2 otherwise
-    while (tiles * split * 2 <= cap && p.total_iters / (split * 2) >= 4 && split < 16) split *= 2;
+    while (tiles * split * 2 <= cap && p.total_iters / (split * 2) >= 4 && split < 8) split *= 2;
   }
-  if (split > p.total_iters) split = p.total_iters;
-  p.iters_per_split = (p.total_iters + split - 1) / split;
-  split = (p.total_iters + p.iters_per_split - 1) / p.iters_per_split;
+  RLDM_CHECK(split == 1 || split == 2 || split == 4 || split == 8, "conv_tc: split_k must be 1, 2, 4 or 8 (got %d)", split);
+  while (split > p.total_iters) split /= 2;
   cudaStream_t st = as_stream(stream);
-  if (split > 1) {
-    const int rc = zero_fill(out, static_cast<size_t>(p.M_total) * Cout * sizeof(float), st);
-    if (rc) return rc;
-  }
   if (parts == 2) {
     if (BN == 128) return launch_conv<128, 3, 3>(tmA, tmAlo, tmB, p, split, st);
     return launch_conv<64, 4, 3>(tmA, tmAlo, tmB, p, split, st);

@@ -33,6 +33,8 @@ CONV_KIND = _lib.OP_CONV_TC
 #   "fp16":   plain fp16 operands (1 MMA per K step).  ~3x less tensor work, but the 11-bit operand rounding puts
 #             whole-trajectory parity at 0.6-1.0e-3, i.e. AT the tolerance -- opt-in only.
 PRECISION = os.environ.get("RLDM_PRECISION", "fp16x3")
+# GroupNorm moments accumulated in the conv epilogue (RLDM_FUSE_STATS=0 forces the separate rldm_gn_stats pass)
+FUSE_STATS = os.environ.get("RLDM_FUSE_STATS", "1") != "0"
 
 
 def _require_cuda_device(dev, what):
@@ -111,11 +113,12 @@ class Program:
 
 
 class Act:
-    """Channels-last fp32 activation (B, W, H, C)."""
-    __slots__ = ("t", "B", "W", "H", "C")
+    """Channels-last fp32 activation (B, W, H, C).  `stats` = (arena slice, G) when the producing conv already
+    accumulated the GroupNorm moments of this tensor in its epilogue."""
+    __slots__ = ("t", "B", "W", "H", "C", "stats")
 
-    def __init__(self, t, B, W, H, C):
-        self.t, self.B, self.W, self.H, self.C = t, B, W, H, C
+    def __init__(self, t, B, W, H, C, stats=None):
+        self.t, self.B, self.W, self.H, self.C, self.stats = t, B, W, H, C, stats
 
 
 def _is_identity_attn(m):
@@ -131,6 +134,7 @@ class Builder:
         self.split = PRECISION == "fp16x3"
         self.pg = prog
         self.B = batch
+        self.groups = groups
         self.gn_arena = prog.hold(torch.zeros(max_gn * batch * groups * 2, dtype=torch.float64, device=prog.device))
         self.gn_used = 0
         self.memset_op = prog.add(_lib.OP_MEMSET, p=(self.gn_arena,), n=0)
@@ -173,12 +177,17 @@ class Builder:
         self.pg.free(pair[1])
 
     # ---- primitive emitters ----------------------------------------------------------------
-    def gn_stats(self, x0, x1, groups):
+    def stats_slot(self, groups):
         n = self.B * groups * 2
         off = self.gn_used
         self.gn_used += n
         assert self.gn_used <= self.gn_arena.numel(), "GroupNorm arena exhausted"
-        sums = self.gn_arena[off:off + n]
+        return self.gn_arena[off:off + n]
+
+    def gn_stats(self, x0, x1, groups):
+        if x1 is None and x0.stats is not None and x0.stats[1] == groups:
+            return x0.stats[0]                  # already accumulated by the producing conv's epilogue
+        sums = self.stats_slot(groups)
         c1 = x1.C if x1 is not None else 0
         self.pg.add(_lib.OP_GN_STATS, i=(x0.C, c1, self.B, x0.W * x0.H, groups),
                     p=(x0.t, x1.t if x1 is not None else None, sums))
@@ -200,8 +209,9 @@ class Builder:
         return out
 
     def conv(self, xh, W, H, conv=None, packed=None, cin=None, cout=None, ks=3, stride=1, pad_lo=1, circular=True,
-             temb=None, residual=None):
-        """fp16 cl (B,W,H,Cin) -> fp32 cl Act (B,W/stride,H/stride,Cout)."""
+             temb=None, residual=None, stats=False):
+        """fp16 clp operand pair -> fp32 cl Act (B,W/stride,H/stride,Cout).  stats=True: the epilogue also
+        accumulates the GroupNorm moments of the output (consumed by the next prep instead of a gn_stats pass)."""
         if conv is not None:
             wt, bias = self.pack_conv(conv)
             cout, cin, ks = conv.out_channels, conv.in_channels, conv.kernel_size[0]
@@ -218,11 +228,15 @@ class Builder:
             temb_t, temb_stride = temb
         kind = CONV_KIND
         ints = [temb_stride, self.B, W, H, cin, cout, ks, stride, pad_lo, int(circular)]
+        st = None
         if kind == _lib.OP_CONV_TC:
-            ints.append(0)   # split_k: auto
+            G = self.groups
+            if stats and FUSE_STATS and Wo * Ho >= 64 and cout % G == 0 and cout // G in (2, 4, 8, 16):
+                st = (self.stats_slot(G), G)
+            ints += [0, G if st else 0]   # split_k: auto; stats groups
         self.pg.add(kind, i=ints, p=(xh[0], wt, bias, temb_t, residual.t if residual is not None else None, out,
-                                     xh[1]), launches=1)
-        return Act(out, self.B, Wo, Ho, cout)
+                                     xh[1], st[0] if st else None), launches=1)
+        return Act(out, self.B, Wo, Ho, cout, st)
 
     # ---- blocks ----------------------------------------------------------------------------
     def resnet(self, rb, x0, x1=None, free_inputs=True):
@@ -235,7 +249,7 @@ class Builder:
             t, T = self.temb
             off = self.temb_rows[id(rb)]
             temb = (t.view(-1)[off:], T)
-        h = self.conv(a1, x0.W, x0.H, rb.conv1, temb=temb)
+        h = self.conv(a1, x0.W, x0.H, rb.conv1, temb=temb, stats=True)
         self.free_half(a1)
         a2 = self.prep(h, None, rb.norm2, silu=True, circular=circ(rb.conv2))
         pg.free(h.t)
@@ -243,11 +257,11 @@ class Builder:
             xr = self.prep(x0, x1, None, silu=False)
             sc = self.conv(xr, x0.W, x0.H, rb.conv_shortcut)
             self.free_half(xr)
-            out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=sc)
+            out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=sc, stats=True)
             pg.free(sc.t)
         else:
             assert x1 is None
-            out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=x0)
+            out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=x0, stats=True)
         self.free_half(a2)
         pg.taps.append((rb, out))
         if free_inputs:
@@ -271,7 +285,7 @@ class Builder:
         pg.add(_lib.OP_ATTENTION, i=(self.B, x.W * x.H, C, x.H), p=(qkv.t, o[0], o[1]))
         pg.free(qkv.t)
         out = self.conv(o, x.W, x.H, packed=self.pack_linear([at.to_out[0]]), cin=C, cout=C, ks=1, pad_lo=0,
-                        residual=x)
+                        residual=x, stats=True)
         self.free_half(o)
         pg.taps.append((at, out))
         if free_input:
@@ -282,7 +296,7 @@ class Builder:
         """Patched Downsample2D (`ldm/utils.py:107-116`): raw cast + stride-2 conv; padding=0 is the
         VAE-encoder asymmetric pad (pad_lo = 0)."""
         xr = self.prep(x, None, None, circular=bool(getattr(ds.conv, "circular", False)))
-        out = self.conv(xr, x.W, x.H, ds.conv)
+        out = self.conv(xr, x.W, x.H, ds.conv, stats=True)
         self.free_half(xr)
         self.pg.taps.append((ds, out))
         if free_input:
@@ -292,7 +306,7 @@ class Builder:
     def upsample(self, us, x):
         """Upsample2D (`model.py:120-125`): nearest 2x folded into the cast, then 3x3 conv."""
         xr = self.prep(x, None, None, up=2, circular=bool(getattr(us.conv, "circular", False)))
-        out = self.conv(xr, x.W * 2, x.H * 2, us.conv)
+        out = self.conv(xr, x.W * 2, x.H * 2, us.conv, stats=True)
         self.free_half(xr)
         self.pg.taps.append((us, out))
         self.pg.free(x.t)

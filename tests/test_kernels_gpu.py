@@ -70,7 +70,9 @@ CONV_CASES = [
     # B, W, H, Cin, Cout, ks, stride, pad_lo, split_k, circular
     (2, 16, 16, 64, 64, 3, 1, 1, 1, 1),
     (1, 32, 8, 128, 128, 3, 1, 1, 1, 1),
-    (1, 32, 8, 128, 128, 3, 1, 1, 3, 1),
+    (1, 32, 8, 128, 128, 3, 1, 1, 2, 1),      # cluster split-K x2 (DSMEM reduction)
+    (2, 16, 8, 256, 128, 3, 1, 1, 8, 1),      # cluster split-K x8
+    (4, 32, 2, 256, 256, 3, 1, 1, 4, 1),      # 64-pixel images: one tile spans two images
     (2, 16, 4, 128, 256, 3, 1, 1, 0, 1),      # Ho = 4: column boxes smaller than a swizzle atom
     (3, 8, 2, 256, 128, 3, 1, 1, 0, 1),       # Ho = 2, partial last tile (M = 48)
     (1, 4, 64, 64, 64, 3, 1, 1, 1, 1),        # Ho = 64 (decoder top level geometry)
@@ -99,7 +101,7 @@ def test_conv_tc_matches_cuda_core_restatement_and_oracle(L, case):
     out_tc = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
     out_rf = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
     L.call("rldm_conv_tc", L.ptr(xh), None, L.ptr(wt), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out_tc),
-           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split)
+           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, None, 0)
     L.call("rldm_conv_ref", L.ptr(xh), None, L.ptr(wt), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out_rf),
            B, W, H, Cin, Cout, ks, stride, pad_lo, circ)
     torch.cuda.synchronize()
@@ -117,8 +119,20 @@ def test_conv_tc_matches_cuda_core_restatement_and_oracle(L, case):
     xh2, xl2, wt2 = padw(xh2, bool(circ)).cuda(), padw(xl2, bool(circ)).cuda(), pack_w(w, split=True).cuda()
     out3 = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
     out3r = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
+    G = 32
+    fused = Wo * Ho >= 64 and Cout // G in (2, 4, 8, 16)
+    stats = torch.zeros(B, G, 2, dtype=torch.float64, device="cuda")
     L.call("rldm_conv_tc", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out3),
-           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split)
+           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, L.ptr(stats) if fused else None, G if fused else 0)
+    if fused:     # GroupNorm moments accumulated by the epilogue == moments of the tensor it wrote
+        og = out3.double().reshape(B, Wo * Ho, G, Cout // G)
+        assert torch.allclose(stats[:, :, 0], og.sum((1, 3)), rtol=1e-5, atol=1e-3)
+        assert torch.allclose(stats[:, :, 1], (og * og).sum((1, 3)), rtol=1e-5, atol=1e-3)
+    # split-K through the cluster/DSMEM reduction is deterministic: a second launch is bit-identical
+    out3b = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
+    L.call("rldm_conv_tc", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out3b),
+           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, None, 0)
+    assert torch.equal(out3, out3b)
     L.call("rldm_conv_ref", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd),
            L.ptr(out3r), B, W, H, Cin, Cout, ks, stride, pad_lo, circ)
     assert relerr(out3, out3r) < 1e-5
@@ -134,19 +148,20 @@ def test_conv_tc_golden_reference_conv(L, golden):
         out = torch.empty(B, W // stride, H // stride, Cout, device="cuda")
         xh, wt, bd = padw(cl(x).half()).cuda(), pack_w(w).cuda(), b.cuda()     # keep the operands alive across the call
         L.call("rldm_conv_tc", L.ptr(xh), None, L.ptr(wt), L.ptr(bd), None, 0, None,
-               L.ptr(out), B, W, H, Cin, Cout, 3, stride, 1, 1, 0)
+               L.ptr(out), B, W, H, Cin, Cout, 3, stride, 1, 1, 0, None, 0)
         assert relerr(ref_layout(out.cpu()), y) < 1e-3
         xh2, xl2 = split_half(cl(x))
         xh2, xl2, wt2 = padw(xh2).cuda(), padw(xl2).cuda(), pack_w(w, split=True).cuda()
         L.call("rldm_conv_tc", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), None, 0, None,
-               L.ptr(out), B, W, H, Cin, Cout, 3, stride, 1, 1, 0)
+               L.ptr(out), B, W, H, Cin, Cout, 3, stride, 1, 1, 0, None, 0)
         assert relerr(ref_layout(out.cpu()), y) < 1e-5
 
 
 def test_conv_tc_rejects_bad_shapes(L):
     x = torch.zeros(1, 10, 8, 48, dtype=torch.half, device="cuda")
     with pytest.raises(L.RldmError):
-        L.call("rldm_conv_tc", L.ptr(x), None, L.ptr(x), None, None, 0, None, L.ptr(x), 1, 8, 8, 48, 64, 3, 1, 1, 1, 0)
+        L.call("rldm_conv_tc", L.ptr(x), None, L.ptr(x), None, None, 0, None, L.ptr(x), 1, 8, 8, 48, 64, 3, 1, 1, 1, 0,
+               None, 0)
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 0, 16, 8, 1), (2, 128, 256, 8, 4, 1), (1, 256, 128, 16, 2, 2),

@@ -98,9 +98,10 @@ def test_ldm_pipeline_golden_from_reference_pipeline(tiny, golden):
         img = pipe(batch_size=2, generator=torch.Generator().manual_seed(3), num_inference_steps=5,
                    output_type="torch")
         assert relerr(img, g[f"ldm_{name}"], f"ldm_pipeline_golden_{name}") < TOL, name
-        # replaying the captured graph with the same seed is bit-stable up to split-K atomics
+        # replaying the captured graph with the same seed: only the double-precision GroupNorm-moment atomics
+        # are order dependent (split-K is a deterministic cluster reduction)
         img2 = pipe(batch_size=2, generator=torch.Generator().manual_seed(3), num_inference_steps=5)
-        assert relerr(img2, img, "graph_replay_stability") < 1e-4
+        assert relerr(img2, img, "graph_replay_stability") < 1e-5
 
 
 def test_pixel_pipeline_golden_from_reference_pipeline(tiny, golden):
