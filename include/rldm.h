@@ -51,10 +51,13 @@ int rldm_gn_stats(const float* x0, int c0, const float* x1, int c1, double* sums
  * `ldm/utils.py:47` (F.pad(..., mode="circular")) is materialised by the producer for free
  * (circular=0: zero halo) and every conv tap is one plain TMA box.  up in {1,2}.
  * out_lo (optional, same shape): the residual y - fp16(y), so that out + out_lo carries ~22
- * significant bits (split-fp16 operand). */
+ * significant bits (split-fp16 operand).  raw / raw_lo (optional, same shape): a second output
+ * holding the UN-normalised, un-activated input (the operand of a ResnetBlock2D's 1x1
+ * conv_shortcut), produced from the same read. */
 int rldm_prep(const float* x0, int c0, const float* x1, int c1, const double* sums,
               const float* gamma, const float* beta, float eps, int G, int silu, int up,
-              int circular, uint16_t* out, uint16_t* out_lo, int B, int W, int H, void* stream);
+              int circular, uint16_t* out, uint16_t* out_lo, uint16_t* raw, uint16_t* raw_lo, int B,
+              int W, int H, void* stream);
 
 /* ---- the hot op: circular implicit-GEMM convolution on tcgen05 ------------------------------
  * Replaces `Conv2d._conv_forward` (`ldm/utils.py:40-58`, twin `vae/sgm/.../model.py:93-108`):

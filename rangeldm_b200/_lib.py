@@ -28,7 +28,7 @@ SIGNATURES = {
     "rldm_last_error": (ctypes.c_char_p, []),
     "rldm_gn_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rldm_prep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int,
-                          c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+                          c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rldm_conv_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
                      + [c_int] * 10 + [c_void_p, c_int, c_void_p]),
     "rldm_conv_ref": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]

@@ -88,6 +88,23 @@ gn_stats_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// 8 fp32 values -> fp16 hi (+ optional lo residual), one 16 B store each
+__device__ __forceinline__ void store_split8(const float (&v)[8], __half* out, __half* out_lo, size_t o) {
+  __align__(16) __half2 h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+  *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(h);
+  if (out_lo) {   // residual of the fp16 rounding: x = hi + lo to ~22 bits
+    __align__(16) __half2 l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 hf = __half22float2(h[j]);
+      l[j] = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+    }
+    *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
 // prep: y = [silu]([gn](concat(x0,x1))) cast to fp16, optionally nearest-2x upsampled.
 // grid (ceil(outpix/pix_per_block), B), block 256.  Thread = 8 channels of one OUTPUT pixel
 // (two float4 loads, one 16 B store).
@@ -95,7 +112,8 @@ __global__ void __launch_bounds__(256)
 prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
             const double* __restrict__ sums, const float* __restrict__ gamma,
             const float* __restrict__ beta, float eps, int G, int silu, int up, int circular,
-            __half* __restrict__ out, __half* __restrict__ out_lo, int W, int H, int pix_per_block) {
+            __half* __restrict__ out, __half* __restrict__ out_lo, __half* __restrict__ raw,
+            __half* __restrict__ raw_lo, int W, int H, int pix_per_block) {
   pdl_entry();
   extern __shared__ float shf[];  // scale[C], shift[C]
   const int C = c0 + c1;
@@ -140,6 +158,8 @@ prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, 
     if (halo && !circular) {
       *reinterpret_cast<uint4*>(out + o) = make_uint4(0, 0, 0, 0);
       if (out_lo) *reinterpret_cast<uint4*>(out_lo + o) = make_uint4(0, 0, 0, 0);
+      if (raw) *reinterpret_cast<uint4*>(raw + o) = make_uint4(0, 0, 0, 0);
+      if (raw_lo) *reinterpret_cast<uint4*>(raw_lo + o) = make_uint4(0, 0, 0, 0);
       continue;
     }
     const int pin = (up == 2) ? (wo >> 1) * H + (ho >> 1) : wo * H + ho;
@@ -148,6 +168,7 @@ prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, 
     const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
     const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
     float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    if (raw) store_split8(v, raw, raw_lo, o);      // second output: the un-normalised operand (1x1 shortcut input)
     if (sums) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[c + j], sf[c + j]);
@@ -156,19 +177,7 @@ prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, 
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
     }
-    __align__(16) __half2 h[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-    *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(h);
-    if (out_lo) {   // residual of the fp16 rounding: x = hi + lo to ~22 bits
-      __align__(16) __half2 l[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 hf = __half22float2(h[j]);
-        l[j] = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
-      }
-      *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(l);
-    }
+    store_split8(v, out, out_lo, o);
   }
 }
 
@@ -288,42 +297,68 @@ conv_in_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x
   }
 }
 
-// conv_out: (B,W,H,Cin) fp16 cl -> (B,Cout,W,H) fp32 ref layout, Cout <= 8.  One warp per pixel:
-// lanes split the input channels, butterfly-reduce the Cout partial sums.
-template <int COUT>
-__global__ void __launch_bounds__(256)
+// conv_out: (B,W+2,H,Cin) fp16 clp (hi [+ lo]) -> (B,Cout,W,H) fp32 ref layout, Cout in {2,4,8}.
+// Thread = one output pixel (consecutive threads = consecutive beams h, so the 9 neighbour rows are shared
+// through L1 and the ref-layout stores are coalesced); weights [9][Cout][Cin] sit in shared memory and are read
+// as warp-wide broadcasts.
+// LPP lanes share one pixel (splitting the channel loop, butterfly-reduced) when there are too few pixels to
+// fill the machine with one thread each.
+template <int COUT, int LPP>
+__global__ void __launch_bounds__(128)
 conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, const float* __restrict__ wgt,
                 const float* __restrict__ bias, float* __restrict__ out, int B, int W, int H,
                 int Cin, int circular) {
-  pdl_entry();
-  const int lane = threadIdx.x & 31;
-  const size_t pp = static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  extern __shared__ float w_s[];     // [9][COUT][Cin]
+  pdl_trigger();
+  for (int i = threadIdx.x * 4; i < 9 * COUT * Cin; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(w_s + i) = __ldg(reinterpret_cast<const float4*>(wgt + i));
+  pdl_wait();
+  __syncthreads();
   const size_t total_pix = static_cast<size_t>(B) * W * H;
-  if (pp >= total_pix) return;
+  const int sub = threadIdx.x % LPP;
+  const size_t pp = min((static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPP, total_pix - 1);
+  const bool live = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPP < total_pix;
   const int h = pp % H;
   const int w = (pp / H) % W;
   const int b = pp / (static_cast<size_t>(H) * W);
   float acc[COUT];
 #pragma unroll
-  for (int n = 0; n < COUT; ++n) acc[n] = 0.f;
+  for (int n = 0; n < COUT; ++n) acc[n] = (bias && sub == 0) ? __ldg(bias + n) : 0.f;
   for (int i = 0; i < 3; ++i) {
     const int wi = w + i;                             // W-padded operand: halo columns hold the wrap (or zeros)
     for (int j = 0; j < 3; ++j) {
       const int hj = h + j - 1;
       if (hj < 0 || hj >= H) continue;
       const size_t xo = ((static_cast<size_t>(b) * (W + 2) + wi) * H + hj) * Cin;
-      const float* wr = wgt + static_cast<size_t>(i * 3 + j) * COUT * Cin;
-      for (int c = lane * 2; c < Cin; c += 64) {
-        float2 a = __half22float2(*reinterpret_cast<const __half2*>(x + xo + c));
+      const float* wt = w_s + (i * 3 + j) * COUT * Cin;
+      for (int c = sub * 8; c < Cin; c += 8 * LPP) {
+        const uint4 hv = __ldg(reinterpret_cast<const uint4*>(x + xo + c));
+        float a[8];
+        {
+          const __half2* hp = reinterpret_cast<const __half2*>(&hv);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(hp[k]);
+            a[2 * k] = f.x; a[2 * k + 1] = f.y;
+          }
+        }
         if (x_lo) {
-          const float2 al = __half22float2(*reinterpret_cast<const __half2*>(x_lo + xo + c));
-          a.x += al.x; a.y += al.y;
+          const uint4 lv = __ldg(reinterpret_cast<const uint4*>(x_lo + xo + c));
+          const __half2* lp = reinterpret_cast<const __half2*>(&lv);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(lp[k]);
+            a[2 * k] += f.x; a[2 * k + 1] += f.y;
+          }
         }
 #pragma unroll
         for (int n = 0; n < COUT; ++n) {
-          const float2 wv = __ldg(reinterpret_cast<const float2*>(wr + n * Cin + c));
-          acc[n] = fmaf(a.x, wv.x, acc[n]);
-          acc[n] = fmaf(a.y, wv.y, acc[n]);
+          const float4 w0 = *reinterpret_cast<const float4*>(wt + n * Cin + c);
+          const float4 w1 = *reinterpret_cast<const float4*>(wt + n * Cin + c + 4);
+          acc[n] = fmaf(a[0], w0.x, acc[n]); acc[n] = fmaf(a[1], w0.y, acc[n]);
+          acc[n] = fmaf(a[2], w0.z, acc[n]); acc[n] = fmaf(a[3], w0.w, acc[n]);
+          acc[n] = fmaf(a[4], w1.x, acc[n]); acc[n] = fmaf(a[5], w1.y, acc[n]);
+          acc[n] = fmaf(a[6], w1.z, acc[n]); acc[n] = fmaf(a[7], w1.w, acc[n]);
         }
       }
     }
@@ -331,14 +366,8 @@ conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, c
 #pragma unroll
   for (int n = 0; n < COUT; ++n) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
-  }
-  if (lane < COUT) {
-    float v = 0.f;
-#pragma unroll
-    for (int n = 0; n < COUT; ++n)
-      if (lane == n) v = acc[n];
-    out[((static_cast<size_t>(b) * COUT + lane) * W + w) * H + h] = v + (bias ? bias[lane] : 0.f);
+    for (int o = LPP / 2; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+    if (live && sub == 0) out[((static_cast<size_t>(b) * COUT + n) * W + w) * H + h] = acc[n];
   }
 }
 
@@ -739,7 +768,8 @@ extern "C" int rldm_gn_stats(const float* x0, int c0, const float* x1, int c1, d
 
 extern "C" int rldm_prep(const float* x0, int c0, const float* x1, int c1, const double* sums,
                          const float* gamma, const float* beta, float eps, int G, int silu, int up,
-                         int circular, uint16_t* out, uint16_t* out_lo, int B, int W, int H, void* stream) {
+                         int circular, uint16_t* out, uint16_t* out_lo, uint16_t* raw, uint16_t* raw_lo, int B,
+                         int W, int H, void* stream) {
   const int C = c0 + c1;
   RLDM_CHECK(c0 % 8 == 0 && c1 % 8 == 0, "prep: channels must be multiples of 8 (c0=%d c1=%d)", c0, c1);
   RLDM_CHECK(up == 1 || up == 2, "prep: up must be 1 or 2");
@@ -750,7 +780,7 @@ extern "C" int rldm_prep(const float* x0, int c0, const float* x1, int c1, const
   if (ppb < 8) ppb = 8;
   chunks = (out_pix + ppb - 1) / ppb;
   RLDM_CUDA(launch_pdl(prep_kernel, dim3(chunks, B), dim3(256), 2 * C * sizeof(float), as_stream(stream), x0, c0, x1, c1, sums, gamma, beta, eps, G, silu, up, circular, reinterpret_cast<__half*>(out),
-      reinterpret_cast<__half*>(out_lo), W, H, ppb));
+      reinterpret_cast<__half*>(out_lo), reinterpret_cast<__half*>(raw), reinterpret_cast<__half*>(raw_lo), W, H, ppb));
   RLDM_LAUNCH_CHECK();
   return 0;
 }
@@ -789,18 +819,25 @@ extern "C" int rldm_conv_in(const float* x0, int c0, const float* x1, int c1, co
 
 extern "C" int rldm_conv_out(const uint16_t* x, const uint16_t* x_lo, const float* wgt, const float* bias, float* out,
                              int B, int W, int H, int Cin, int Cout, int circular, void* stream) {
-  RLDM_CHECK(Cin % 2 == 0, "conv_out: Cin must be even");
+  RLDM_CHECK(Cin % 8 == 0, "conv_out: Cin must be a multiple of 8");
   const size_t total_pix = static_cast<size_t>(B) * W * H;
-  const unsigned grid = static_cast<unsigned>((total_pix + 7) / 8);
   const __half* xh = reinterpret_cast<const __half*>(x);
   const __half* xl = reinterpret_cast<const __half*>(x_lo);
   cudaStream_t st = as_stream(stream);
+  const size_t smem = static_cast<size_t>(9) * Cout * Cin * sizeof(float);
+  RLDM_CHECK(smem <= 48 * 1024, "conv_out: 9*Cout*Cin weights exceed 48 KB of shared memory");
+  const bool wide = total_pix < 200000 && Cin % 64 == 0;        // 8 lanes per pixel when pixels are scarce
+  const unsigned grid = static_cast<unsigned>((total_pix * (wide ? 8 : 1) + 127) / 128);
+#define RLDM_CO(N)                                                                                              \
+  if (wide) RLDM_CUDA(launch_pdl(conv_out_kernel<N, 8>, dim3(grid), dim3(128), smem, st, xh, xl, wgt, bias, out, B, W, H, Cin, circular)); \
+  else RLDM_CUDA(launch_pdl(conv_out_kernel<N, 1>, dim3(grid), dim3(128), smem, st, xh, xl, wgt, bias, out, B, W, H, Cin, circular));
   switch (Cout) {
-    case 2: RLDM_CUDA(launch_pdl(conv_out_kernel<2>, dim3(grid), dim3(256), 0, st, xh, xl, wgt, bias, out, B, W, H, Cin, circular)); break;
-    case 4: RLDM_CUDA(launch_pdl(conv_out_kernel<4>, dim3(grid), dim3(256), 0, st, xh, xl, wgt, bias, out, B, W, H, Cin, circular)); break;
-    case 8: RLDM_CUDA(launch_pdl(conv_out_kernel<8>, dim3(grid), dim3(256), 0, st, xh, xl, wgt, bias, out, B, W, H, Cin, circular)); break;
+    case 2: RLDM_CO(2) break;
+    case 4: RLDM_CO(4) break;
+    case 8: RLDM_CO(8) break;
     default: RLDM_CHECK(false, "conv_out: Cout must be 2, 4 or 8 (got %d)", Cout);
   }
+#undef RLDM_CO
   RLDM_LAUNCH_CHECK();
   return 0;
 }
@@ -873,7 +910,8 @@ extern "C" int rldm_run(const rldm_op* ops, int n_ops, void* stream) {
       case RLDM_OP_PREP:
         rc = rldm_prep((const float*)o.p[0], o.i[0], (const float*)o.p[1], o.i[1], (const double*)o.p[2],
                        (const float*)o.p[3], (const float*)o.p[4], o.f[0], o.i[2], o.i[3], o.i[4], o.i[8],
-                       (uint16_t*)o.p[5], (uint16_t*)o.p[6], o.i[5], o.i[6], o.i[7], stream);
+                       (uint16_t*)o.p[5], (uint16_t*)o.p[6], (uint16_t*)o.p[7], (uint16_t*)o.p[8], o.i[5], o.i[6], o.i[7],
+                       stream);
         break;
       case RLDM_OP_CONV_TC:
         rc = rldm_conv_tc((const uint16_t*)o.p[0], (const uint16_t*)o.p[6], (const uint16_t*)o.p[1], (const float*)o.p[2],

@@ -193,8 +193,9 @@ class Builder:
                     p=(x0.t, x1.t if x1 is not None else None, sums))
         return sums
 
-    def prep(self, x0, x1=None, norm=None, silu=False, up=1, circular=True):
-        """-> fp16 operand pair in the W-padded layout (B, W*up + 2, H*up, C0+C1)."""
+    def prep(self, x0, x1=None, norm=None, silu=False, up=1, circular=True, also_raw=False):
+        """-> fp16 operand pair in the W-padded layout (B, W*up + 2, H*up, C0+C1); also_raw=True returns a
+        second pair holding the un-normalised input (1x1 shortcut operand) written by the same launch."""
         c1 = x1.C if x1 is not None else 0
         C = x0.C + c1
         sums = gamma = beta = None
@@ -204,9 +205,10 @@ class Builder:
             sums = self.gn_stats(x0, x1, G)
             gamma, beta, eps = self.f32(norm.weight), self.f32(norm.bias), norm.eps
         out = self.alloc_half((self.B, x0.W * up + 2, x0.H * up, C))
+        raw = self.alloc_half((self.B, x0.W * up + 2, x0.H * up, C)) if also_raw else (None, None)
         self.pg.add(_lib.OP_PREP, i=(x0.C, c1, G, int(silu), up, self.B, x0.W, x0.H, int(circular)), f=(eps,),
-                    p=(x0.t, x1.t if x1 is not None else None, sums, gamma, beta, out[0], out[1]))
-        return out
+                    p=(x0.t, x1.t if x1 is not None else None, sums, gamma, beta, out[0], out[1], raw[0], raw[1]))
+        return (out, raw) if also_raw else out
 
     def conv(self, xh, W, H, conv=None, packed=None, cin=None, cout=None, ks=3, stride=1, pad_lo=1, circular=True,
              temb=None, residual=None, stats=False):
@@ -243,7 +245,11 @@ class Builder:
         """ResnetBlock2D on the virtual concat (x0 | x1) (App. A.1; `model.py:342-362`)."""
         pg = self.pg
         circ = lambda conv: bool(getattr(conv, "circular", False))
-        a1 = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1))
+        xr = None
+        if rb.conv_shortcut is not None:
+            a1, xr = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1), also_raw=True)
+        else:
+            a1 = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1))
         temb = None
         if rb.time_emb_proj is not None and self.temb is not None:
             t, T = self.temb
@@ -254,7 +260,6 @@ class Builder:
         a2 = self.prep(h, None, rb.norm2, silu=True, circular=circ(rb.conv2))
         pg.free(h.t)
         if rb.conv_shortcut is not None:
-            xr = self.prep(x0, x1, None, silu=False)
             sc = self.conv(xr, x0.W, x0.H, rb.conv_shortcut)
             self.free_half(xr)
             out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=sc, stats=True)

@@ -186,7 +186,7 @@ def test_gn_stats_and_prep(L, shape):
     gd, bd = gamma.cuda(), beta.cuda()
     out_lo = torch.empty_like(out)
     L.call("rldm_prep", L.ptr(x0d), C0, L.ptr(x1d), C1, L.ptr(sums), L.ptr(gd), L.ptr(bd), eps, G, 1,
-           up, 1, L.ptr(out), L.ptr(out_lo), B, W, H)
+           up, 1, L.ptr(out), L.ptr(out_lo), None, None, B, W, H)
     y = F.silu(F.group_norm(xc, G, gamma, beta, eps))
     if up == 2:
         y = F.interpolate(y, scale_factor=2.0, mode="nearest")
@@ -194,10 +194,17 @@ def test_gn_stats_and_prep(L, shape):
     assert relerr(ref_layout(unpadw(out.float() + out_lo.float()).cpu()), y) < 5e-6      # hi + lo: split-fp16
     assert torch.equal(out[:, 0], out[:, -2]) and torch.equal(out[:, -1], out[:, 1])   # circular halo columns
     # raw cast path (no norm, no silu), zero halo
-    L.call("rldm_prep", L.ptr(x0d), C0, L.ptr(x1d), C1, None, None, None, 0.0, 0, 0, up, 0, L.ptr(out), None, B, W, H)
+    L.call("rldm_prep", L.ptr(x0d), C0, L.ptr(x1d), C1, None, None, None, 0.0, 0, 0, up, 0, L.ptr(out), None, None, None,
+           B, W, H)
     yr = F.interpolate(xc, scale_factor=2.0, mode="nearest") if up == 2 else xc
     assert torch.equal(ref_layout(unpadw(out).cpu()), yr.half())
     assert float(out[:, 0].abs().max()) == 0.0 and float(out[:, -1].abs().max()) == 0.0
+    # dual output: normalised+SiLU operand and the raw operand from one launch
+    raw, raw_lo = torch.empty_like(out), torch.empty_like(out)
+    L.call("rldm_prep", L.ptr(x0d), C0, L.ptr(x1d), C1, L.ptr(sums), L.ptr(gd), L.ptr(bd), eps, G, 1,
+           up, 1, L.ptr(out), L.ptr(out_lo), L.ptr(raw), L.ptr(raw_lo), B, W, H)
+    assert relerr(ref_layout(unpadw(out.float() + out_lo.float()).cpu()), y) < 5e-6
+    assert relerr(ref_layout(unpadw(raw.float() + raw_lo.float()).cpu()), yr) < 5e-6
 
 
 @pytest.mark.parametrize("cuda_core", [False, True], ids=["mma", "cudacore"])
