@@ -16,10 +16,13 @@
 // * 4 epilogue warps read TMEM (tcgen05.ld), add bias + time-embedding + residual and store fp32
 //   channels-last (or atomically accumulate when the K loop is split across CTAs).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace rldm {
+
+static long long* g_conv_dbg = nullptr;
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // fp16 elements = one 128 B swizzle row
@@ -39,6 +42,11 @@ struct ConvParams {
   int total_iters;  // (Cin/64) * ks*ks
   double* stats;    // optional GroupNorm moments of the output: [B][stats_G][2]
   int stats_cpg, stats_G;
+  // halo-reuse 3x3 kernel only
+  int a_part_bytes; // bytes of one operand part of an A stage: (MT*128 + 2*Ho) rows x 128 B
+  int nb_stages;    // depth of the weight (B) ring
+  int units;        // (Cin/64) * 3 : one unit = (channel chunk, kernel column tj) = 3 taps
+  long long* dbg;   // optional: 8 clock64 timestamps written by CTA (0,0,0) (profiling aid, normally NULL)
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
@@ -57,135 +65,24 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// TERMS = 1: D += A*W with fp16 operands (11-bit significands).
-// TERMS = 3: split-fp16 ("fp16x3"): A = Ah + Al, W = Wh + Wl (each part fp16), D += Ah*Wh + Al*Wh + Ah*Wl --
-//            ~22-bit operand significands on the fp16 tensor pipe, fp32 accumulation in TMEM.  This is the
-//            default: it keeps 20-step trajectories within the 1e-3 parity tolerance with >100x margin.
-template <int BLOCK_N, int STAGES, int TERMS>
-__global__ void __launch_bounds__(192, TERMS == 1 ? 2 : 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
-               const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
-  constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  constexpr int kParts = TERMS == 1 ? 1 : 2;
-  constexpr int kStageBytes = kParts * (kABytes + kBBytes);   // [A_hi][A_lo][B_hi][B_lo]
-  constexpr int kBOff = kParts * kABytes;
+// ------------------------------------------------------------------------------------------------
+// Epilogue of one 128 x BLOCK_N accumulator tile, called by ALL 192 threads (warps 0/1 only take part in the
+// barriers).  tmem_acc = TMEM address of the accumulator (lane 0, first column); m0 = first output pixel.
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_tile(uint8_t* smem, uint32_t tmem_acc, int m0, int n0, const ConvParams& p,
+                                              int warp, int lane) {
   constexpr int kStagePitch = BLOCK_N + 4;                     // floats per row of the epilogue staging tile
-  static_assert(kBlockM * kStagePitch * 4 <= STAGES * kStageBytes, "staging tile must fit in the pipeline stages");
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B atoms need 1024 B alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBlockM;
-  const int n0 = blockIdx.y * BLOCK_N;
-  const int it0 = static_cast<int>(static_cast<long long>(blockIdx.z) * p.total_iters / gridDim.z);
-  const int it1 = static_cast<int>(static_cast<long long>(blockIdx.z + 1) * p.total_iters / gridDim.z);
-  const int n_it = it1 - it0;                    // >= 1: the host keeps gridDim.z <= total_iters
-
-  pdl_trigger();     // let the next kernel's CTAs launch and run their prologue while this grid drains
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    if (TERMS > 1) tma_prefetch_desc(&tmAlo);
-    tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    mbar_fence_init();
-  }
-  if (warp == 1) tmem_alloc<BLOCK_N>(tmem_ptr);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  pdl_wait();        // everything above overlapped the previous kernel; below we touch its outputs
-
-  if (warp == 0) {
-    // ===================== TMA producer (whole warp: lanes share the column loads) =============
-    const int taps = p.ks * p.ks;
-    // tile = `ncols` whole azimuth columns of `nb` consecutive images (nb > 1 only when an image has < 128 px)
-    const int q0 = m0 / p.Ho;                     // global column index of the tile's first column
-    const int b0 = q0 / p.Wo;
-    const int wo0 = q0 - b0 * p.Wo;
-    for (int i = 0; i < n_it; ++i) {
-      const int s = i % STAGES;
-      const uint32_t ph = (i / STAGES) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      const int it = it0 + i;
-      const int chunk = it / taps;
-      const int tap = it - chunk * taps;
-      const int ti = tap / p.ks, tj = tap - ti * p.ks;
-      const uint32_t a_dst = smem_u32(smem + s * kStageBytes);
-      if (lane == 0) {
-        mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-        tma_load_2d(a_dst + kBOff, &tmB, &full_bar[s], chunk * kBlockK, tap * p.Cout + n0);
-        if (TERMS > 1)   // low-order weight plane follows the high-order one: rows [taps*Cout, 2*taps*Cout)
-          tma_load_2d(a_dst + kBOff + kBBytes, &tmB, &full_bar[s], chunk * kBlockK,
-                      (taps + tap) * p.Cout + n0);
-      }
-      if (lane == (TERMS == 1 ? 0 : 1)) {
-        // ONE box per operand part: the activation tensor is W-padded (halo columns hold the circular wrap,
-        // written by rldm_prep), H zero padding is TMA out-of-bounds fill, stride 2 is the map's element stride.
-        const int w_in = p.stride * wo0 + ti - p.pad_lo + 1;
-        tma_load_4d(a_dst, &tmA, &full_bar[s], chunk * kBlockK, tj - p.pad_lo, w_in, b0);
-      }
-      if (TERMS > 1 && lane == 2) {
-        const int w_in = p.stride * wo0 + ti - p.pad_lo + 1;
-        tma_load_4d(a_dst + kABytes, &tmAlo, &full_bar[s], chunk * kBlockK, tj - p.pad_lo, w_in, b0);
-      }
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) ============================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BLOCK_N);
-      for (int i = 0; i < n_it; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
-        const uint64_t a_desc = umma_desc_sw128(a_addr);
-        const uint64_t b_desc = umma_desc_sw128(a_addr + kBOff);
-#pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          // advancing K by 16 fp16 = 32 B inside the 128 B swizzle row: +2 in the (addr>>4) field
-          umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (i | k) != 0);
-        }
-        if (TERMS > 1) {
-          const uint64_t al_desc = umma_desc_sw128(a_addr + kABytes);
-          const uint64_t bl_desc = umma_desc_sw128(a_addr + kBOff + kBBytes);
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            umma_f16(tmem_base, al_desc + 2 * k, b_desc + 2 * k, idesc, 1u);   // A_lo * W_hi
-            umma_f16(tmem_base, a_desc + 2 * k, bl_desc + 2 * k, idesc, 1u);   // A_hi * W_lo
-          }
-        }
-        umma_commit(&empty_bar[s]);
-      }
-      umma_commit(tmem_full_bar);
-    }
-    __syncwarp();
-  } else {
+  if (warp >= 2) {
     // ===================== epilogue phase 1: TMEM -> registers -> shared staging tile =========
     // The pipeline stages are dead once tmem_full fires (all TMA writes consumed, all MMA reads done), so the
     // fp32 accumulator tile [128][BLOCK_N] is staged over them (row pitch +4 floats: conflict-free float4).
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     float* stage_row = reinterpret_cast<float*>(smem) + row * kStagePitch;
 #pragma unroll 1
     for (int nc = 0; nc < BLOCK_N / 32; ++nc) {
       uint32_t r[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + nc * 32, r);
+      tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + nc * 32, r);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -197,12 +94,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // now owns rows [rank*128/nsplit, ...) and sums them over all ranks through distributed shared memory in a
   // fixed order (deterministic, no atomics, no zero-fill).  nsplit == 1: same code on the local tile.
   const int nsplit = gridDim.z;
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64;
+  if (dbg) p.dbg[6] = clock64();
   tc_fence_before();
   if (nsplit > 1) {
     cluster_sync_all();
   } else {
     __syncthreads();
   }
+  if (dbg) p.dbg[7] = clock64();
   if (warp >= 2) {
     const int ew = warp - 2;                              // 0..3
     constexpr int kLanesPerRow = BLOCK_N / 4;             // 32 (BN=128) or 16 (BN=64)
@@ -223,48 +123,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       bias4.x += t4.x; bias4.y += t4.y; bias4.z += t4.z; bias4.w += t4.w;
     }
     float s01 = 0.f, q01 = 0.f, s23 = 0.f, q23 = 0.f;     // moments of channel pairs (0,1) and (2,3)
-    constexpr int kU = 4;                                 // rows in flight per lane: residual loads issued together
+    // The residual rows come from L2 (~800 cycles): issue up to kU row loads per lane before consuming any.
+    constexpr int kU = 16;
     for (int rr0 = rsub; rr0 < rows_warp; rr0 += kRowsPerIter * kU) {
-      float4 res[kU], acc[kU];
+      float4 res[kU];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int rr = rr0 + u * kRowsPerIter;
         const int m = m0 + r_begin + rr;
-        res[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.residual && rr < rows_warp && m < p.M_total)
-          res[u] = __ldg(reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(m) * p.Cout + n0 + col));
+        res[u] = bias4;
+        if (p.residual && rr < rows_warp && m < p.M_total) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(m) * p.Cout + n0 + col));
+          res[u].x += t.x; res[u].y += t.y; res[u].z += t.z; res[u].w += t.w;
+        }
       }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int rr = rr0 + u * kRowsPerIter;
-        acc[u] = bias4;
+        const int m = m0 + r_begin + rr;
         if (rr < rows_warp) {
           const int r = r_begin + rr;
+          float4 v = res[u];
           if (nsplit > 1) {
             const uint32_t local = stage_u32 + (r * kStagePitch + col) * 4;
             for (int sidx = 0; sidx < nsplit; ++sidx) {
-              const float4 v = ld_dsmem_f4(mapa_u32(local, sidx));
-              acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+              const float4 t = ld_dsmem_f4(mapa_u32(local, sidx));
+              v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
             }
           } else {
-            const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem) + r * kStagePitch + col);
-            acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+            const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem) + r * kStagePitch + col);
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+          }
+          if (m < p.M_total) {
+            *reinterpret_cast<float4*>(p.out + static_cast<size_t>(m) * p.Cout + n0 + col) = v;
+            s01 += v.x + v.y; q01 += v.x * v.x + v.y * v.y;
+            s23 += v.z + v.w; q23 += v.z * v.z + v.w * v.w;
           }
         }
       }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int rr = rr0 + u * kRowsPerIter;
-        const int m = m0 + r_begin + rr;
-        if (rr < rows_warp && m < p.M_total) {
-          float4 v = acc[u];
-          v.x += res[u].x; v.y += res[u].y; v.z += res[u].z; v.w += res[u].w;
-          *reinterpret_cast<float4*>(p.out + static_cast<size_t>(m) * p.Cout + n0 + col) = v;
-          s01 += v.x + v.y; q01 += v.x * v.x + v.y * v.y;
-          s23 += v.z + v.w; q23 += v.z * v.z + v.w * v.w;
-        }
-      }
     }
+    if (dbg) p.dbg[8] = clock64();
     if (p.stats) {
       // GroupNorm moments of the finished output, per (image, group): channel pairs -> lanes -> the 4 epilogue
       // warps (shared memory) -> ONE double atomic per (group, moment) and image for the whole CTA.
@@ -317,10 +215,300 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   }
-  if (nsplit > 1) cluster_sync_all();     // nobody leaves while a peer may still read its staging tile
+  if (nsplit > 1) cluster_sync_all();     // nobody moves on while a peer may still read its staging tile
+  else if (warp >= 2) asm volatile("bar.sync 1, 128;" ::: "memory");   // staging tile may be reused by a next pass
+}
+
+// TERMS = 1: D += A*W with fp16 operands (11-bit significands).
+// TERMS = 3: split-fp16 ("fp16x3"): A = Ah + Al, W = Wh + Wl (each part fp16), D += Ah*Wh + Al*Wh + Ah*Wl --
+//            ~22-bit operand significands on the fp16 tensor pipe, fp32 accumulation in TMEM.  This is the
+//            default: it keeps 20-step trajectories within the 1e-3 parity tolerance with >100x margin.
+template <int BLOCK_N, int STAGES, int TERMS>
+__global__ void __launch_bounds__(192, TERMS == 1 ? 2 : 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+  constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  constexpr int kParts = TERMS == 1 ? 1 : 2;
+  constexpr int kStageBytes = kParts * (kABytes + kBBytes);   // [A_hi][A_lo][B_hi][B_lo]
+  constexpr int kBOff = kParts * kABytes;
+  constexpr int kStagePitch = BLOCK_N + 4;                     // floats per row of the epilogue staging tile
+  static_assert(kBlockM * kStagePitch * 4 <= STAGES * kStageBytes, "staging tile must fit in the pipeline stages");
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms need 1024 B alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBlockM;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int it0 = static_cast<int>(static_cast<long long>(blockIdx.z) * p.total_iters / gridDim.z);
+  const int it1 = static_cast<int>(static_cast<long long>(blockIdx.z + 1) * p.total_iters / gridDim.z);
+  const int n_it = it1 - it0;                    // >= 1: the host keeps gridDim.z <= total_iters
+
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
+  pdl_trigger();     // let the next kernel's CTAs launch and run their prologue while this grid drains
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    if (TERMS > 1) tma_prefetch_desc(&tmAlo);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<BLOCK_N>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  // Weights never depend on the previous kernel: the producer arms the first STAGES barriers and starts their
+  // weight tiles BEFORE griddepcontrol.wait, so they land while the previous grid is still draining.
+  if (warp == 0 && lane == 0) {
+    const int taps = p.ks * p.ks;
+    for (int i = 0; i < n_it && i < STAGES; ++i) {
+      const int it = it0 + i;
+      const int chunk = it / taps;
+      const int tap = it - chunk * taps;
+      const uint32_t a_dst = smem_u32(smem + i * kStageBytes);
+      mbar_arrive_expect_tx(&full_bar[i], kStageBytes);
+      tma_load_2d(a_dst + kBOff, &tmB, &full_bar[i], chunk * kBlockK, tap * p.Cout + n0);
+      if (TERMS > 1)
+        tma_load_2d(a_dst + kBOff + kBBytes, &tmB, &full_bar[i], chunk * kBlockK, (taps + tap) * p.Cout + n0);
+    }
+  }
+  pdl_wait();        // everything above overlapped the previous kernel; below we touch its outputs
+  if (dbg && threadIdx.x == 0) p.dbg[1] = clock64();
+
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp: lanes share the column loads) =============
+    const int taps = p.ks * p.ks;
+    // tile = `ncols` whole azimuth columns of `nb` consecutive images (nb > 1 only when an image has < 128 px)
+    const int q0 = m0 / p.Ho;                     // global column index of the tile's first column
+    const int b0 = q0 / p.Wo;
+    const int wo0 = q0 - b0 * p.Wo;
+    for (int i = 0; i < n_it; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      const int it = it0 + i;
+      const int chunk = it / taps;
+      const int tap = it - chunk * taps;
+      const int ti = tap / p.ks, tj = tap - ti * p.ks;
+      const uint32_t a_dst = smem_u32(smem + s * kStageBytes);
+      if (lane == 0 && i >= STAGES) {   // (the first STAGES weight tiles were issued before griddepcontrol.wait)
+        mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+        tma_load_2d(a_dst + kBOff, &tmB, &full_bar[s], chunk * kBlockK, tap * p.Cout + n0);
+        if (TERMS > 1)   // low-order weight plane follows the high-order one: rows [taps*Cout, 2*taps*Cout)
+          tma_load_2d(a_dst + kBOff + kBBytes, &tmB, &full_bar[s], chunk * kBlockK,
+                      (taps + tap) * p.Cout + n0);
+      }
+      if (lane == (TERMS == 1 ? 0 : 1)) {
+        // ONE box per operand part: the activation tensor is W-padded (halo columns hold the circular wrap,
+        // written by rldm_prep), H zero padding is TMA out-of-bounds fill, stride 2 is the map's element stride.
+        const int w_in = p.stride * wo0 + ti - p.pad_lo + 1;
+        tma_load_4d(a_dst, &tmA, &full_bar[s], chunk * kBlockK, tj - p.pad_lo, w_in, b0);
+      }
+      if (TERMS > 1 && lane == 2) {
+        const int w_in = p.stride * wo0 + ti - p.pad_lo + 1;
+        tma_load_4d(a_dst + kABytes, &tmAlo, &full_bar[s], chunk * kBlockK, tj - p.pad_lo, w_in, b0);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) ============================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BLOCK_N);
+      for (int i = 0; i < n_it; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (dbg && i == 0) p.dbg[2] = clock64();
+        const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+        const uint64_t a_desc = umma_desc_sw128(a_addr);
+        const uint64_t b_desc = umma_desc_sw128(a_addr + kBOff);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          // advancing K by 16 fp16 = 32 B inside the 128 B swizzle row: +2 in the (addr>>4) field
+          umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (i | k) != 0);
+        }
+        if (TERMS > 1) {
+          const uint64_t al_desc = umma_desc_sw128(a_addr + kABytes);
+          const uint64_t bl_desc = umma_desc_sw128(a_addr + kBOff + kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            umma_f16(tmem_base, al_desc + 2 * k, b_desc + 2 * k, idesc, 1u);   // A_lo * W_hi
+            umma_f16(tmem_base, a_desc + 2 * k, bl_desc + 2 * k, idesc, 1u);   // A_hi * W_lo
+          }
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+      if (dbg) p.dbg[3] = clock64();
+    }
+    __syncwarp();
+  } else {
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    if (dbg && threadIdx.x == 64) p.dbg[4] = clock64();
+  }
+  epilogue_tile<BLOCK_N>(smem, tmem_base, m0, n0, p, warp, lane);
+  if (dbg && threadIdx.x == 64) p.dbg[5] = clock64();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<BLOCK_N>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Halo-reuse kernel for the 3x3 / stride-1 convolutions that carry ~95 % of the FLOPs.
+//
+// In the per-tap kernel above every one of the 9 taps re-reads its A tile from L2 and every 128-pixel tile
+// re-reads all weights: 64 KB per K step, which makes the kernel operand-ingest bound.  Here
+//   * one TMA box per (64-channel chunk, kernel column tj) brings MT*128 output pixels PLUS one halo column on
+//     each side: (MT*ncols + 2) columns x Ho rows.  The three taps ti = 0,1,2 of that kernel column are the same
+//     shared-memory tile shifted by ti*Ho rows (a multiple of the 1024 B swizzle atom for Ho >= 8), i.e. just
+//     three UMMA descriptors -- A traffic drops 3x;
+//   * MT = 2 accumulators (2 x 128 pixels, TMEM columns [0,BN) and [BN,2BN)) share every weight tile -- B traffic
+//     per output halves;
+//   * A stages (2) and weight stages (p.nb_stages) live in separate mbarrier rings.
+template <int BLOCK_N, int MT, int TERMS>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+  constexpr int kParts = TERMS == 1 ? 1 : 2;
+  constexpr int kBBytes = BLOCK_N * kBlockK * 2;      // one part of one weight tile
+  constexpr int kBStage = kParts * kBBytes;
+  constexpr int kMaxNB = 4;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int a_part = p.a_part_bytes;
+  const int a_stage = kParts * a_part;
+  const int NB = p.nb_stages;
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + 2 * a_stage;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + NB * kBStage);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* b_full = a_empty + 2;
+  uint64_t* b_empty = b_full + kMaxNB;
+  uint64_t* tmem_full_bar = b_empty + kMaxNB;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * (MT * kBlockM);
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int u0 = static_cast<int>(static_cast<long long>(blockIdx.z) * p.units / gridDim.z);
+  const int u1 = static_cast<int>(static_cast<long long>(blockIdx.z + 1) * p.units / gridDim.z);
+  const int n_units = u1 - u0;                   // >= 1 (host keeps gridDim.z <= units)
+
+  pdl_trigger();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    if (TERMS > 1) tma_prefetch_desc(&tmAlo);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kMaxNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<MT * BLOCK_N>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =========================================================
+    const int q0 = m0 / p.Ho;                     // first output column of the tile (global column index)
+    const int b0 = q0 / p.Wo;
+    const int wo0 = q0 - b0 * p.Wo;               // == padded column of tap ti = 0
+    int bi = 0;
+    for (int ui = 0; ui < n_units; ++ui) {
+      const int u = u0 + ui;
+      const int chunk = u / 3, tj = u - chunk * 3;
+      const int sa = ui & 1;
+      mbar_wait(&a_empty[sa], ((ui >> 1) & 1) ^ 1);
+      const uint32_t a_dst = smem_u32(a_ring + sa * a_stage);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&a_full[sa], a_stage);
+        tma_load_4d(a_dst, &tmA, &a_full[sa], chunk * kBlockK, tj - 1, wo0, b0);
+      }
+      if (TERMS > 1 && lane == 1) tma_load_4d(a_dst + a_part, &tmAlo, &a_full[sa], chunk * kBlockK, tj - 1, wo0, b0);
+      for (int ti = 0; ti < 3; ++ti, ++bi) {
+        const int sb = bi % NB;
+        mbar_wait(&b_empty[sb], ((bi / NB) & 1) ^ 1);
+        if (lane == 0) {
+          const int tap = ti * 3 + tj;
+          const uint32_t b_dst = smem_u32(b_ring + sb * kBStage);
+          mbar_arrive_expect_tx(&b_full[sb], kBStage);
+          tma_load_2d(b_dst, &tmB, &b_full[sb], chunk * kBlockK, tap * p.Cout + n0);
+          if (TERMS > 1) tma_load_2d(b_dst + kBBytes, &tmB, &b_full[sb], chunk * kBlockK, (9 + tap) * p.Cout + n0);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer ===========================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BLOCK_N);
+      int bi = 0;
+      for (int ui = 0; ui < n_units; ++ui) {
+        const int sa = ui & 1;
+        mbar_wait(&a_full[sa], (ui >> 1) & 1);
+        const uint32_t a_base = smem_u32(a_ring + sa * a_stage);
+        for (int ti = 0; ti < 3; ++ti, ++bi) {
+          const int sb = bi % NB;
+          mbar_wait(&b_full[sb], (bi / NB) & 1);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(b_ring + sb * kBStage);
+          const uint64_t b_desc = umma_desc_sw128(b_addr);
+          const uint64_t bl_desc = umma_desc_sw128(b_addr + kBBytes);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            // tap ti of this kernel column = the staged tile shifted by ti columns (ti*Ho rows); sub-tile mt
+            // starts mt*128 rows further down.  Both offsets are whole 1024 B swizzle atoms.
+            const uint32_t a_addr = a_base + (ti * p.Ho + mt * kBlockM) * 128;
+            const uint64_t a_desc = umma_desc_sw128(a_addr);
+            const uint64_t al_desc = umma_desc_sw128(a_addr + a_part);
+            const uint32_t acc = tmem_base + mt * BLOCK_N;
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (ui | ti | k) != 0);
+            if (TERMS > 1) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                umma_f16(acc, al_desc + 2 * k, b_desc + 2 * k, idesc, 1u);   // A_lo * W_hi
+                umma_f16(acc, a_desc + 2 * k, bl_desc + 2 * k, idesc, 1u);   // A_hi * W_lo
+              }
+            }
+          }
+          umma_commit(&b_empty[sb]);
+        }
+        umma_commit(&a_empty[sa]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+  }
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+    epilogue_tile<BLOCK_N>(smem, tmem_base + mt * BLOCK_N, m0 + mt * kBlockM, n0, p, warp, lane);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<MT * BLOCK_N>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -378,9 +566,49 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const C
   return 0;
 }
 
+template <int BLOCK_N, int MT, int TERMS>
+static int launch_conv3x3(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const CUtensorMap& tmB,
+                          const ConvParams& p, int split, size_t smem, cudaStream_t st) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    RLDM_CUDA(cudaFuncSetAttribute(conv3x3_kernel<BLOCK_N, MT, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+    attr_smem = smem;
+  }
+  dim3 grid((p.M_total + MT * kBlockM - 1) / (MT * kBlockM), p.Cout / BLOCK_N, split);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (split > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = split;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  RLDM_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_kernel<BLOCK_N, MT, TERMS>, tmA, tmAlo, tmB, p));
+  return 0;
+}
+
 }  // namespace rldm
 
 using namespace rldm;
+
+// profiling aid (not part of include/rldm.h): device buffer of 16 int64 that CTA 0 of the per-tap kernel fills with
+// clock64() stamps: [0] entry, [1] prologue done, [2] first stage landed, [3] last MMA issued, [4] accumulator
+// complete, [5] epilogue done.
+extern "C" void rldm_debug_conv_timestamps(long long* dev_buf) { g_conv_dbg = dev_buf; }
 
 extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias,
                             const float* temb, int temb_stride, const float* residual, float* out,
@@ -408,6 +636,89 @@ extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint1
   RLDM_CHECK(ncols * stride <= 256, "conv_tc: tile of %d columns exceeds the TMA box limit", ncols);
   const int parts = x_lo ? 2 : 1;
   CUtensorMap tmA, tmAlo, tmB;
+  // ---- halo-reuse path: 3x3, stride 1, symmetric pad, column pitch a whole number of swizzle atoms ----
+  // (measured on B200: correct but not faster than the per-tap kernel, whose limiter is per-CTA latency rather
+  //  than operand bytes -- kept opt-in with RLDM_HALO=1 until it is made persistent)
+  const bool halo_ok = ks == 3 && stride == 1 && pad_lo == 1 && Ho >= 8 && pix >= 128 && getenv("RLDM_HALO");
+  if (halo_ok) {
+    const size_t limit = 232448 - 1024 - 3328;          // 227 KB minus alignment slack and static shared memory
+    const size_t b_stage = static_cast<size_t>(parts) * BN * 128;
+    const size_t bars = 256;
+    auto a_stage_of = [&](int mt) { return static_cast<size_t>(parts) * (mt * 128 + 2 * Ho) * 128; };
+    int MT = (pix % 256 == 0 && 2 * a_stage_of(2) + 2 * b_stage + bars <= limit) ? 2 : 1;
+    if (getenv("RLDM_HALO_MT1")) MT = 1;
+    const size_t a_stage = a_stage_of(MT);
+    if (2 * a_stage + 2 * b_stage + bars <= limit) {
+      int nbs = static_cast<int>((limit - bars - 2 * a_stage) / b_stage);
+      if (nbs > 4) nbs = 4;
+      size_t smem = 2 * a_stage + nbs * b_stage + bars;
+      const size_t stage_tile = static_cast<size_t>(128) * (BN + 4) * 4;
+      if (smem < stage_tile + bars) smem = stage_tile + bars;
+      smem += 1024;
+      const int cols = MT * (128 / Ho);
+      for (int part = 0; part < parts; ++part) {
+        cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)H, (cuuint64_t)(W + 2), (cuuint64_t)B};
+        cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)H * Cin * 2, (cuuint64_t)(W + 2) * H * Cin * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)Ho, (cuuint32_t)(cols + 2), 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(part ? &tmAlo : &tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                            const_cast<uint16_t*>(part ? x_lo : x), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(A halo) failed: %d", (int)r);
+      }
+      if (parts == 1) tmAlo = tmA;
+      {
+        cuuint64_t gdim[2] = {(cuuint64_t)Cin, (cuuint64_t)parts * 9 * Cout};
+        cuuint64_t gstr[1] = {(cuuint64_t)Cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(wgt), gdim, gstr,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+      }
+      ConvParams p;
+      p.bias = bias; p.temb = temb; p.residual = residual; p.out = out;
+      p.temb_stride = temb_stride;
+      p.M_total = B * pix;
+      p.Wo = Wo; p.Ho = Ho; p.W_in = W;
+      p.pix_per_img = pix;
+      p.Cout = Cout;
+      p.ks = 3; p.stride = 1; p.pad_lo = 1; p.circular = circular;
+      p.total_iters = (Cin / kBlockK) * 9;
+      p.units = (Cin / kBlockK) * 3;
+      p.a_part_bytes = static_cast<int>(a_stage / parts);
+      p.nb_stages = nbs;
+      p.dbg = nullptr;
+      p.stats = stats;
+      p.stats_G = stats_groups;
+      p.stats_cpg = stats_groups > 0 ? Cout / stats_groups : 0;
+      RLDM_CHECK(!stats || (Cout % stats_groups == 0 && (p.stats_cpg == 2 || p.stats_cpg == 4 || p.stats_cpg == 8 ||
+                                                         p.stats_cpg == 16)),
+                 "conv_tc: fused GroupNorm statistics need 2, 4, 8 or 16 channels per group (Cout=%d, G=%d)", Cout,
+                 stats_groups);
+      const int tiles = ((p.M_total + MT * 128 - 1) / (MT * 128)) * (Cout / BN);
+      int split = split_k;
+      if (split <= 0) {
+        split = 1;
+        while (tiles * split * 2 <= 160 && p.units / (split * 2) >= 2 && split < 8) split *= 2;
+      }
+      RLDM_CHECK(split == 1 || split == 2 || split == 4 || split == 8, "conv_tc: split_k must be 1, 2, 4 or 8 (got %d)", split);
+      while (split > p.units) split /= 2;
+      cudaStream_t st = as_stream(stream);
+      if (parts == 2) {
+        if (BN == 128) return MT == 2 ? launch_conv3x3<128, 2, 3>(tmA, tmAlo, tmB, p, split, smem, st)
+                                      : launch_conv3x3<128, 1, 3>(tmA, tmAlo, tmB, p, split, smem, st);
+        return MT == 2 ? launch_conv3x3<64, 2, 3>(tmA, tmAlo, tmB, p, split, smem, st)
+                       : launch_conv3x3<64, 1, 3>(tmA, tmAlo, tmB, p, split, smem, st);
+      }
+      if (BN == 128) return MT == 2 ? launch_conv3x3<128, 2, 1>(tmA, tmAlo, tmB, p, split, smem, st)
+                                    : launch_conv3x3<128, 1, 1>(tmA, tmAlo, tmB, p, split, smem, st);
+      return MT == 2 ? launch_conv3x3<64, 2, 1>(tmA, tmAlo, tmB, p, split, smem, st)
+                     : launch_conv3x3<64, 1, 1>(tmA, tmAlo, tmB, p, split, smem, st);
+    }
+  }
   for (int part = 0; part < parts; ++part) {
     cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)H, (cuuint64_t)(W + 2), (cuuint64_t)B};
     cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)H * Cin * 2, (cuuint64_t)(W + 2) * H * Cin * 2};
@@ -439,6 +750,8 @@ extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint1
   p.Cout = Cout;
   p.ks = ks; p.stride = stride; p.pad_lo = pad_lo; p.circular = circular;
   p.total_iters = (Cin / kBlockK) * ks * ks;
+  p.units = 0; p.a_part_bytes = 0; p.nb_stages = 0;
+  p.dbg = g_conv_dbg;
   p.stats = stats;
   p.stats_G = stats_groups;
   p.stats_cpg = stats_groups > 0 ? Cout / stats_groups : 0;
