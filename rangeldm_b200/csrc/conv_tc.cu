@@ -124,7 +124,7 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, uint32_t tmem_acc, 
     }
     float s01 = 0.f, q01 = 0.f, s23 = 0.f, q23 = 0.f;     // moments of channel pairs (0,1) and (2,3)
     // The residual rows come from L2 (~800 cycles): issue up to kU row loads per lane before consuming any.
-    constexpr int kU = 16;
+    constexpr int kU = 8;
     for (int rr0 = rsub; rr0 < rows_warp; rr0 += kRowsPerIter * kU) {
       float4 res[kU];
 #pragma unroll
@@ -368,6 +368,263 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent variant of the per-tap kernel for layers with more tiles than SMs (no K split).
+//
+// Timeline stamps of the kernel above show the 128x128 epilogue (64 KB of residual reads + 64 KB of stores per
+// CTA, issued by all CTAs of a wave at once) costing ~45 % of the mainloop time.  Here one CTA per SM walks over
+// tiles; the fp32 accumulator is DOUBLE-BUFFERED in TMEM (2 x BLOCK_N columns), so the four epilogue warps drain
+// tile k (TMEM -> 32-column shared staging slab -> coalesced global, bias/temb/residual/GroupNorm moments) while
+// the producer and MMA warps are already running the K loop of tile k+1.  The staging slab is private to the
+// epilogue (not aliased with the pipeline stages).
+template <int BLOCK_N, int STAGES, int TERMS>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                          const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+  constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  constexpr int kParts = TERMS == 1 ? 1 : 2;
+  constexpr int kStageBytes = kParts * (kABytes + kBBytes);
+  constexpr int kBOff = kParts * kABytes;
+  constexpr int kSlabPitch = 36;                                // floats per row of the 32-column staging slab
+  constexpr int kSlabBytes = kBlockM * kSlabPitch * 4;          // 18 KB
+  constexpr int kChunks = BLOCK_N / 32;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  float* slab = reinterpret_cast<float*>(smem + STAGES * kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes + kSlabBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* red_s = reinterpret_cast<float*>(tmem_ptr + 4);       // [4][BLOCK_N/2]
+  float* red_q = red_s + 4 * (BLOCK_N / 2);
+  int* red_b = reinterpret_cast<int*>(red_q + 4 * (BLOCK_N / 2));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_n = p.Cout / BLOCK_N;
+  const int tiles_m = (p.M_total + kBlockM - 1) / kBlockM;
+  const int total_tiles = tiles_m * tiles_n;
+  const int taps = p.ks * p.ks;
+  const int n_it = p.total_iters;
+
+  pdl_trigger();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    if (TERMS > 1) tma_prefetch_desc(&tmAlo);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);          // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<2 * BLOCK_N>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer: one continuous stage ring across tiles =================
+    int g = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int tm = t / tiles_n, tn = t - tm * tiles_n;
+      const int m0 = tm * kBlockM, n0 = tn * BLOCK_N;
+      const int q0 = m0 / p.Ho;
+      const int b0 = q0 / p.Wo;
+      const int wo0 = q0 - b0 * p.Wo;
+      for (int it = 0; it < n_it; ++it, ++g) {
+        const int s = g % STAGES;
+        mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
+        const int chunk = it / taps;
+        const int tap = it - chunk * taps;
+        const int ti = tap / p.ks, tj = tap - ti * p.ks;
+        const uint32_t a_dst = smem_u32(smem + s * kStageBytes);
+        const int w_in = p.stride * wo0 + ti - p.pad_lo + 1;
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+          tma_load_2d(a_dst + kBOff, &tmB, &full_bar[s], chunk * kBlockK, tap * p.Cout + n0);
+          if (TERMS > 1)
+            tma_load_2d(a_dst + kBOff + kBBytes, &tmB, &full_bar[s], chunk * kBlockK, (taps + tap) * p.Cout + n0);
+        }
+        if (lane == (TERMS == 1 ? 0 : 1)) tma_load_4d(a_dst, &tmA, &full_bar[s], chunk * kBlockK, tj - p.pad_lo, w_in, b0);
+        if (TERMS > 1 && lane == 2)
+          tma_load_4d(a_dst + kABytes, &tmAlo, &full_bar[s], chunk * kBlockK, tj - p.pad_lo, w_in, b0);
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: alternates between the two TMEM accumulators ==============
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BLOCK_N);
+      int g = 0, k = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
+        const int acc = k & 1;
+        mbar_wait(&tmem_empty[acc], ((k >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int it = 0; it < n_it; ++it, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(&full_bar[s], (g / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+          const uint64_t a_desc = umma_desc_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_sw128(a_addr + kBOff);
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / 16; ++kk)
+            umma_f16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (it | kk) != 0);
+          if (TERMS > 1) {
+            const uint64_t al_desc = umma_desc_sw128(a_addr + kABytes);
+            const uint64_t bl_desc = umma_desc_sw128(a_addr + kBOff + kBBytes);
+#pragma unroll
+            for (int kk = 0; kk < kBlockK / 16; ++kk) {
+              umma_f16(d_tmem, al_desc + 2 * kk, b_desc + 2 * kk, idesc, 1u);
+              umma_f16(d_tmem, a_desc + 2 * kk, bl_desc + 2 * kk, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps: drain tile k while tile k+1 is being computed =========
+    const int ew = warp - 2;                  // rows ew*32 .. ew*32+31 of the tile in the coalesced phase
+    const int q = warp & 3;                   // TMEM lane quadrant readable by this warp
+    const int rsub = lane >> 3;               // 4 rows per warp instruction in the coalesced phase
+    const int col = (lane & 7) * 4;           // float4 column inside the 32-column slab
+    int k = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
+      const int acc = k & 1;
+      const int tm = t / tiles_n, tn = t - tm * tiles_n;
+      const int m0 = tm * kBlockM, n0 = tn * BLOCK_N;
+      mbar_wait(&tmem_full[acc], (k >> 1) & 1);
+      tc_fence_after();
+      const int m_first = m0 + ew * 32;
+      const int bimg = min(m_first, p.M_total - 1) / p.pix_per_img;   // a warp's 32 rows lie in one image
+      float sg[kChunks], qg[kChunks];         // per-chunk moments of this lane's 4 channels
+      float s23c[kChunks], q23c[kChunks];     // second channel pair (only used when cpg == 2)
+#pragma unroll
+      for (int nc = 0; nc < kChunks; ++nc) {
+        // (1) accumulator slab -> registers -> shared (row = TMEM lane)
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16) + nc * 32, r);
+        tmem_ld_wait();
+        float* srow = slab + (q * 32 + lane) * kSlabPitch;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(srow + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        if (nc == kChunks - 1) {              // last TMEM read of this tile: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // (2) coalesced phase: this warp finalises rows ew*32.. of the tile, 4 rows x 128 B per instruction
+        const int c = n0 + nc * 32 + col;
+        float4 add4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) add4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+        if (p.temb) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.temb + static_cast<size_t>(bimg) * p.temb_stride + c));
+          add4.x += t4.x; add4.y += t4.y; add4.z += t4.z; add4.w += t4.w;
+        }
+        float4 res[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int m = m_first + u * 4 + rsub;
+          res[u] = add4;
+          if (p.residual && m < p.M_total) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(m) * p.Cout + c));
+            res[u].x += t4.x; res[u].y += t4.y; res[u].z += t4.z; res[u].w += t4.w;
+          }
+        }
+        float s01 = 0.f, q01 = 0.f, s23 = 0.f, q23 = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int rr = ew * 32 + u * 4 + rsub;
+          const int m = m0 + rr;
+          const float4 a4 = *reinterpret_cast<const float4*>(slab + rr * kSlabPitch + col);
+          float4 v = res[u];
+          v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
+          if (m < p.M_total) {
+            *reinterpret_cast<float4*>(p.out + static_cast<size_t>(m) * p.Cout + c) = v;
+            s01 += v.x + v.y; q01 += v.x * v.x + v.y * v.y;
+            s23 += v.z + v.w; q23 += v.z * v.z + v.w * v.w;
+          }
+        }
+        // fold the 4 row-groups of the warp (lanes l, l+8, l+16, l+24 hold the same columns)
+        s01 += __shfl_xor_sync(0xffffffffu, s01, 8); q01 += __shfl_xor_sync(0xffffffffu, q01, 8);
+        s23 += __shfl_xor_sync(0xffffffffu, s23, 8); q23 += __shfl_xor_sync(0xffffffffu, q23, 8);
+        s01 += __shfl_xor_sync(0xffffffffu, s01, 16); q01 += __shfl_xor_sync(0xffffffffu, q01, 16);
+        s23 += __shfl_xor_sync(0xffffffffu, s23, 16); q23 += __shfl_xor_sync(0xffffffffu, q23, 16);
+        sg[nc] = s01; qg[nc] = q01; s23c[nc] = s23; q23c[nc] = q23;
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // slab free for the next chunk / next tile
+      }
+      if (p.stats) {
+        // per-CTA fold of the GroupNorm moments, then one double atomic per (group, moment) and image
+        const int cpg = p.stats_cpg;
+        const int nslots = cpg == 2 ? BLOCK_N / 2 : BLOCK_N / cpg;
+        if (lane < 8) {
+#pragma unroll
+          for (int nc = 0; nc < kChunks; ++nc) {
+            const int cc = nc * 32 + col;                  // column of this lane's float4 inside the tile
+            if (cpg == 2) {
+              red_s[ew * (BLOCK_N / 2) + cc / 2] = sg[nc];       red_q[ew * (BLOCK_N / 2) + cc / 2] = qg[nc];
+              red_s[ew * (BLOCK_N / 2) + cc / 2 + 1] = s23c[nc]; red_q[ew * (BLOCK_N / 2) + cc / 2 + 1] = q23c[nc];
+            } else {
+              float a = sg[nc] + s23c[nc], b = qg[nc] + q23c[nc];
+              for (int o = 1; o < cpg / 4; o <<= 1) {      // cpg 8/16: neighbouring float4 columns share a group
+                a += __shfl_xor_sync(0x000000ffu, a, o);
+                b += __shfl_xor_sync(0x000000ffu, b, o);
+              }
+              if (((lane & 7) % (cpg / 4)) == 0) {
+                red_s[ew * (BLOCK_N / 2) + cc / cpg] = a;
+                red_q[ew * (BLOCK_N / 2) + cc / cpg] = b;
+              }
+            }
+          }
+        }
+        if (lane == 0) red_b[ew] = m_first < p.M_total ? bimg : -1;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int tix = ew * 32 + lane;
+        if (tix < nslots) {
+          const int gidx = (n0 / (cpg == 2 ? 2 : cpg)) + tix;
+          double ds = 0.0, dq = 0.0;
+          int cur = red_b[0];
+          for (int e = 0; e < 4; ++e) {
+            const int be = red_b[e];
+            if (be != cur) {
+              if (cur >= 0) {
+                double* st = p.stats + (static_cast<size_t>(cur) * p.stats_G + gidx) * 2;
+                atomicAdd(st, ds); atomicAdd(st + 1, dq);
+              }
+              cur = be; ds = 0.0; dq = 0.0;
+            }
+            ds += static_cast<double>(red_s[e * (BLOCK_N / 2) + tix]);
+            dq += static_cast<double>(red_q[e * (BLOCK_N / 2) + tix]);
+          }
+          if (cur >= 0) {
+            double* st = p.stats + (static_cast<size_t>(cur) * p.stats_G + gidx) * 2;
+            atomicAdd(st, ds); atomicAdd(st + 1, dq);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // red_* reusable by the next tile
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<2 * BLOCK_N>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Halo-reuse kernel for the 3x3 / stride-1 convolutions that carry ~95 % of the FLOPs.
 //
 // In the per-tap kernel above every one of the 9 taps re-reads its A tile from L2 and every 128-pixel tile
@@ -563,6 +820,22 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const C
   cfg.attrs = attr;
   cfg.numAttrs = na;
   RLDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, STAGES, TERMS>, tmA, tmAlo, tmB, p));
+  return 0;
+}
+
+template <int BLOCK_N, int STAGES, int TERMS>
+static int launch_conv_persistent(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const CUtensorMap& tmB,
+                                  const ConvParams& p, int n_ctas, cudaStream_t st) {
+  constexpr int smem = STAGES * (TERMS == 1 ? 1 : 2) * (kABytes + BLOCK_N * kBlockK * 2) + kBlockM * 36 * 4 + 256 +
+                       2 * 4 * (BLOCK_N / 2) * 4 + 64 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLDM_CUDA(cudaFuncSetAttribute(conv_tc_persistent_kernel<BLOCK_N, STAGES, TERMS>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  RLDM_CUDA(launch_pdl(conv_tc_persistent_kernel<BLOCK_N, STAGES, TERMS>, dim3(n_ctas), dim3(192), smem, st, tmA, tmAlo,
+                       tmB, p));
   return 0;
 }
 
@@ -769,6 +1042,18 @@ extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint1
   RLDM_CHECK(split == 1 || split == 2 || split == 4 || split == 8, "conv_tc: split_k must be 1, 2, 4 or 8 (got %d)", split);
   while (split > p.total_iters) split /= 2;
   cudaStream_t st = as_stream(stream);
+  // more tiles than SMs and no K split: persistent CTAs with a double-buffered TMEM accumulator
+  static int n_sms = 0;
+  if (n_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sms <= 0) n_sms = 148;
+  }
+  if (split == 1 && tiles > n_sms && parts == 2 && !getenv("RLDM_NO_PERSISTENT")) {
+    if (BN == 128) return launch_conv_persistent<128, 3, 3>(tmA, tmAlo, tmB, p, n_sms, st);
+    return launch_conv_persistent<64, 4, 3>(tmA, tmAlo, tmB, p, n_sms, st);
+  }
   if (parts == 2) {
     if (BN == 128) return launch_conv<128, 3, 3>(tmA, tmAlo, tmB, p, split, st);
     return launch_conv<64, 4, 3>(tmA, tmAlo, tmB, p, split, st);

@@ -81,7 +81,10 @@ CONV_CASES = [
     (2, 16, 8, 128, 384, 1, 1, 0, 1, 1),      # attention qkv projection as a 1x1 "conv"
     (1, 16, 8, 384, 128, 3, 1, 1, 0, 1),      # skip-concat width
     (1, 16, 8, 64, 64, 3, 1, 1, 1, 0),        # zero padding on W as well (no surgery)
-    (8, 256, 16, 128, 128, 3, 1, 1, 0, 1),    # C3 top-level layer at full size
+    (8, 256, 16, 128, 128, 3, 1, 1, 0, 1),    # C3 top-level layer at full size (persistent kernel: 256 tiles)
+    (8, 256, 16, 64, 256, 3, 1, 1, 0, 1),     # persistent, two N tiles per M tile
+    (2, 512, 32, 64, 64, 3, 1, 1, 0, 1),      # persistent, BLOCK_N = 64 (decoder geometry), 256 tiles
+    (5, 64, 32, 64, 128, 1, 1, 0, 0, 1),      # persistent 1x1, 80 tiles -> not persistent; sanity
 ]
 
 
