@@ -124,6 +124,7 @@ def per_op_profile(sampler):
     lib = _lib.lib()
     names = {1: "gn_stats", 2: "prep", 3: "conv_tc", 4: "conv_in", 5: "conv_out", 6: "attention", 7: "temb",
              8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale"}
+    # (profiles the first sub-batch program: with RLDM_STREAMS=2 that is half of the per-GPU batch)
     ops = list(sampler.plan.prog.ops) + (list(sampler.dec.prog.ops) if sampler.dec is not None else [])
     st = _lib.stream_ptr()
     ms, cnt, flops = {}, {}, 0.0
@@ -163,17 +164,17 @@ def run_native(args):
     pipe.scheduler.set_timesteps(STEPS)
     sampler = pipe._sampler(B, 1, pipe.vae)                 # compiles + captures the trajectory graph
     from rangeldm_b200.pipelines import make_pos_encoding
-    sampler.cond.copy_(make_pos_encoding(B, 256, 16, dev))
+    pos = make_pos_encoding(B, 256, 16, dev)
     gen = torch.Generator(device=dev).manual_seed(rank)
     noise = torch.randn((B, 4, 256, 16), generator=gen, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    gathered = torch.empty((world,) + tuple(sampler.image.shape), device=dev) if world > 1 else None
+    gathered = torch.empty((world, B, 2, 1024, 64), device=dev) if world > 1 else None
 
     def one_step():
-        sampler.latents.copy_(noise)
-        sampler.graph.replay()
+        sampler.load(noise, pos)            # device -> device copies of the (already resident) inputs
+        sampler.replay()
         if world > 1:       # the only collective: collect the finished range images (north star)
-            dist.all_gather_into_tensor(gathered, sampler.image)
+            dist.all_gather_into_tensor(gathered, sampler.result())
 
     for _ in range(max(args.warmup, 3)):
         one_step()
@@ -203,7 +204,7 @@ def run_native(args):
     value = world * args.steps * B / (total_ms / 1e3)
 
     # ---- end to end through the public pipeline call: CPU randn -> H2D -> sample -> D2H ----
-    host_img = torch.empty(tuple(sampler.image.shape), pin_memory=True)
+    host_img = torch.empty((B, 2, 1024, 64), pin_memory=True)
     g2 = torch.Generator().manual_seed(1000 + rank)
     for _ in range(2):
         host_img.copy_(pipe(batch_size=B, generator=g2, num_inference_steps=STEPS, output_type="torch"))

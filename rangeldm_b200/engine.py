@@ -128,7 +128,8 @@ def _is_identity_attn(m):
 class Builder:
     """Emits ops for the building blocks shared by the UNet and the VAE."""
 
-    def __init__(self, prog, batch, max_gn=1024, groups=32):
+    def __init__(self, prog, batch, max_gn=1024, groups=32, cache=None):
+        self.cache = cache if cache is not None else {}      # packed weights shared between plans of a model
         if PRECISION not in ("fp16x3", "fp16"):
             raise ValueError(f"RLDM_PRECISION must be 'fp16x3' or 'fp16', got {PRECISION!r}")
         self.split = PRECISION == "fp16x3"
@@ -145,8 +146,16 @@ class Builder:
         self.memset_op.n = self.gn_used * 8
 
     # ---- weights ---------------------------------------------------------------------------
+    def _cached(self, key, make):
+        key = key + (PRECISION, str(self.pg.device))
+        v = self.cache.get(key)
+        if v is None:
+            v = self.cache[key] = make()
+        self.pg.keep.append(v)
+        return v
+
     def f32(self, t):
-        return self.pg.hold(t.detach().to(self.pg.device, torch.float32).contiguous())
+        return self._cached(("f32", id(t)), lambda: t.detach().to(self.pg.device, torch.float32).contiguous())
 
     def _planes(self, w):
         """fp32 [taps][Cout][Cin] -> fp16 [planes][taps][Cout][Cin]; plane 1 = residual of the fp16 rounding."""
@@ -157,16 +166,20 @@ class Builder:
         return self.pg.hold(torch.cat([hi, lo], 0).contiguous())
 
     def pack_conv(self, conv):
-        w = conv.weight.detach().to(self.pg.device, torch.float32)       # (Cout, Cin, kW, kH)
-        co, ci, k0, k1 = w.shape
-        wt = self._planes(w.permute(2, 3, 0, 1).reshape(k0 * k1, co, ci))
+        def make():
+            w = conv.weight.detach().to(self.pg.device, torch.float32)       # (Cout, Cin, kW, kH)
+            co, ci, k0, k1 = w.shape
+            return self._planes(w.permute(2, 3, 0, 1).reshape(k0 * k1, co, ci))
+        wt = self._cached(("conv", id(conv.weight)), make)
         b = self.f32(conv.bias) if conv.bias is not None else None
         return wt, b
 
     def pack_linear(self, lins):
-        w = torch.cat([l.weight.detach().to(self.pg.device, torch.float32) for l in lins], 0)
-        b = torch.cat([l.bias.detach().to(self.pg.device, torch.float32) for l in lins], 0)
-        return self._planes(w[None]), self.pg.hold(b.contiguous())
+        def make():
+            w = torch.cat([l.weight.detach().to(self.pg.device, torch.float32) for l in lins], 0)
+            b = torch.cat([l.bias.detach().to(self.pg.device, torch.float32) for l in lins], 0)
+            return self._planes(w[None]), b.contiguous()
+        return self._cached(("lin",) + tuple(id(l.weight) for l in lins), make)
 
     def alloc_half(self, shape):
         """(hi, lo) fp16 operand pair; lo is None in plain-fp16 mode."""
@@ -318,8 +331,8 @@ class Builder:
         return out
 
     def conv_in(self, conv, x0, c0, x1, c1, W, H):
-        w = conv.weight.detach().to(self.pg.device, torch.float32)      # (Cout, Cin, kW, kH)
-        wt = self.pg.hold(w.permute(2, 3, 1, 0).contiguous())           # [9][Cin][Cout]
+        wt = self._cached(("conv_in", id(conv.weight)), lambda: conv.weight.detach().to(
+            self.pg.device, torch.float32).permute(2, 3, 1, 0).contiguous())           # [9][Cin][Cout]
         out = self.pg.alloc((self.B, W, H, conv.out_channels))
         assert conv.in_channels == c0 + c1 and conv.kernel_size == (3, 3) and conv.padding == (1, 1)
         self.pg.add(_lib.OP_CONV_IN, i=(c0, c1, self.B, W, H, conv.out_channels, int(getattr(conv, "circular", False))),
@@ -330,8 +343,8 @@ class Builder:
 
     def conv_out(self, norm, conv, x, out_ref):
         a = self.prep(x, None, norm, silu=True, circular=bool(getattr(conv, "circular", False)))
-        w = conv.weight.detach().to(self.pg.device, torch.float32)
-        wt = self.pg.hold(w.permute(2, 3, 0, 1).contiguous())           # [9][Cout][Cin]
+        wt = self._cached(("conv_out", id(conv.weight)), lambda: conv.weight.detach().to(
+            self.pg.device, torch.float32).permute(2, 3, 0, 1).contiguous())           # [9][Cout][Cin]
         assert conv.kernel_size == (3, 3) and conv.padding == (1, 1)
         self.pg.add(_lib.OP_CONV_OUT, i=(self.B, x.W, x.H, x.C, conv.out_channels, int(getattr(conv, "circular", False))),
                     p=(a[0], wt, self.f32(conv.bias), out_ref, a[1]))
@@ -363,7 +376,7 @@ class UNetPlan:
         if W % (1 << (L - 1)) or H % (1 << (L - 1)):
             raise ValueError(f"sample size {(W, H)} must be divisible by {1 << (L - 1)}")
         pg = self.prog = Program(dev)
-        bd = Builder(pg, batch, groups=cfg.norm_num_groups)
+        bd = Builder(pg, batch, groups=cfg.norm_num_groups, cache=model._packed)
         cin = cfg.in_channels
         self.x_in = pg.hold(torch.zeros(batch, cin - cond_channels, W, H, device=dev))
         self.cond = pg.hold(torch.zeros(batch, cond_channels, W, H, device=dev)) if cond_channels else None
@@ -448,7 +461,7 @@ class VaeDecoderPlan:
         dec = vae.decoder
         self.B = batch
         pg = self.prog = Program(dev)
-        bd = Builder(pg, batch, groups=vae.config.norm_num_groups)
+        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed)
         zc = vae.config.latent_channels
         n_up = sum(1 for b in dec.up_blocks if b.upsamplers is not None)
         self.z_in = pg.hold(torch.zeros(batch, zc, W, H, device=dev))
@@ -484,7 +497,7 @@ class VaeEncoderPlan:
         enc = vae.encoder
         self.B = batch
         pg = self.prog = Program(dev)
-        bd = Builder(pg, batch, groups=vae.config.norm_num_groups)
+        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed)
         ic = vae.config.in_channels
         n_down = sum(1 for b in enc.down_blocks if b.downsamplers is not None)
         self.x_in = pg.hold(torch.zeros(batch, ic, W, H, device=dev))

@@ -159,9 +159,11 @@ class _PlannedModel(ModelMixin, nn.Module):
 
     def _init_plans(self):
         object.__setattr__(self, "_plans", {})
+        object.__setattr__(self, "_packed", {})     # repacked weights shared by all plans of this model
 
     def invalidate_plans(self):
         self._plans.clear()
+        self._packed.clear()
 
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)
@@ -237,10 +239,12 @@ class UNet2DModel(_PlannedModel):
         self.conv_out = LoRACompatibleConv(boc[0], out_channels, 3, padding=1)
 
     # ------------------------------------------------------------------------------------------
-    def plan(self, batch, W, H, cond_channels=0):
-        """Compiled kernel program for inputs (batch, in_channels, W, H) (see engine.UNetPlan)."""
+    def plan(self, batch, W, H, cond_channels=0, replica=0):
+        """Compiled kernel program for inputs (batch, in_channels, W, H) (see engine.UNetPlan).  `replica`
+        selects an independent set of activation buffers (weights are shared) so several programs of the same
+        shape can run concurrently on different streams."""
         from .engine import UNetPlan
-        key = (batch, W, H, cond_channels)
+        key = (batch, W, H, cond_channels, replica)
         p = self._plans.get(key)
         if p is None:
             p = UNetPlan(self, batch, W, H, cond_channels)
@@ -361,17 +365,17 @@ class AutoencoderKL(_PlannedModel):
         self.quant_conv = LoRACompatibleConv(2 * latent_channels, 2 * latent_channels, 1)
         self.post_quant_conv = LoRACompatibleConv(latent_channels, latent_channels, 1)
 
-    def _plan(self, kind, batch, W, H):
+    def _plan(self, kind, batch, W, H, replica=0):
         from .engine import VaeDecoderPlan, VaeEncoderPlan
-        key = (kind, batch, W, H)
+        key = (kind, batch, W, H, replica)
         p = self._plans.get(key)
         if p is None:
             p = (VaeDecoderPlan if kind == "dec" else VaeEncoderPlan)(self, batch, W, H)
             self._plans[key] = p
         return p
 
-    def decoder_plan(self, batch, W, H):
-        return self._plan("dec", batch, W, H)
+    def decoder_plan(self, batch, W, H, replica=0):
+        return self._plan("dec", batch, W, H, replica)
 
     @torch.no_grad()
     def decode(self, z: torch.Tensor, return_dict: bool = True, generator=None):

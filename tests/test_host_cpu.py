@@ -128,11 +128,16 @@ def test_dry_run_plans_and_fused_program_launch_counts(monkeypatch):
                         up_block_types=["UpDecoderBlock2D"] * 3, block_out_channels=[64, 128, 256], layers_per_block=2)
     v.quant_conv = torch.nn.Identity(); v.post_quant_conv = torch.nn.Identity()
     R.replace_down(v); R.replace_conv(v); R.replace_attn(v)
-    fs = R.FusedSampler(u, sch, v, 8, 1, use_graph=False)
-    n_sched = sum(1 for op in fs.prog.ops if op.kind == _lib.OP_SCHED_STEP)
-    assert n_sched == 20 and fs.image.shape == (8, 2, 1024, 64)
+    fs = R.FusedSampler(u, sch, v, 8, 1, use_graph=False, streams=2)
+    assert len(fs.parts) == 2 and fs.slices == [slice(0, 4), slice(4, 8)]       # two sub-batch trajectories
+    for part in fs.parts:
+        n_sched = sum(1 for op in part.prog.ops if op.kind == _lib.OP_SCHED_STEP)
+        assert n_sched == 20 and part.image.shape == (4, 2, 1024, 64)
+        assert not any(op.kind == _lib.OP_TEMB for op in part.prog.ops)           # time embedding precomputed
+    assert fs.parts[0].plan is not fs.parts[1].plan                               # own activation buffers ...
+    assert len(u._packed) > 0 and len(fs.parts[0].plan.prog.ops) == len(plan.prog.ops)   # ... shared weights
     with pytest.raises(RuntimeError, match="no CPU fallback"):
-        fs.prog.run()
+        fs.parts[0].prog.run()
     v2 = R.AutoencoderKL(in_channels=2, out_channels=2, down_block_types=["DownEncoderBlock2D"],
                          up_block_types=["UpDecoderBlock2D"], block_out_channels=[64])
     with pytest.raises(NotImplementedError):
