@@ -45,7 +45,9 @@ int rldm_gn_stats(const float* x0, int c0, const float* x1, int c1, double* sums
 /* ---- prep: (GroupNorm-apply) (+SiLU) (+concat) (+nearest 2x upsample) -> fp16 cl -----------
  * Replaces F.group_norm's normalise half + F.silu (`model.py:343-345,351-352`), torch.cat of the
  * skip connection (UpBlock2D) and F.interpolate(scale_factor=2, "nearest") (`model.py:121-122`).
- * x0:(B,W,H,C0) [+x1:(B,W,H,C1)] fp32 cl.  sums==NULL -> no normalisation (raw cast).
+ * x0:(B,W,H,C0) [+x1:(B,W,H,C1)] fp32 cl.  GroupNorm moments come either as `sums` [B][G][2] (from
+ * rldm_gn_stats) or as channel-pair moments `pairs0` [B][C0/2][2] (+ `pairs1` [B][C1/2][2]) accumulated by
+ * the producing rldm_conv_tc epilogues; all NULL -> no normalisation (raw cast).
  * out: the tensor-core OPERAND layout "clp": (B, W*up + 2, H*up, C0+C1) fp16, channels-last and
  * W-PADDED -- padded column wp holds image column (wp-1) mod W*up, so the circular halo of
  * `ldm/utils.py:47` (F.pad(..., mode="circular")) is materialised by the producer for free
@@ -55,6 +57,7 @@ int rldm_gn_stats(const float* x0, int c0, const float* x1, int c1, double* sums
  * holding the UN-normalised, un-activated input (the operand of a ResnetBlock2D's 1x1
  * conv_shortcut), produced from the same read. */
 int rldm_prep(const float* x0, int c0, const float* x1, int c1, const double* sums,
+              const double* pairs0, const double* pairs1,
               const float* gamma, const float* beta, float eps, int G, int silu, int up,
               int circular, uint16_t* out, uint16_t* out_lo, uint16_t* raw, uint16_t* raw_lo, int B,
               int W, int H, void* stream);
@@ -80,15 +83,15 @@ int rldm_prep(const float* x0, int c0, const float* x1, int c1, const double* su
  *   split_k: 0 = choose automatically; 2, 4 or 8: the K loop (taps x channel chunks) is split over a
  *         thread-block CLUSTER of split_k CTAs per tile; partial tiles are reduced through distributed
  *         shared memory in a fixed order (deterministic; no atomics, no zero fill).
- *   stats / stats_groups: optional fused GroupNorm statistics of the finished output: (sum, sum of
- *         squares) per (image, group) are ADDED into stats[B][stats_groups][2] (double, zeroed by the
- *         caller), replacing the rldm_gn_stats pass of the next normalisation.  Needs
- *         Cout/stats_groups in {2,4,8,16} and Wo*Ho >= 64.
+ *   stats: optional fused GroupNorm statistics of the finished output: (sum, sum of squares) per
+ *         (image, channel PAIR) are ADDED into stats[B][Cout/2][2] (double, zeroed by the caller).
+ *         rldm_prep folds pairs into the groups of the consuming GroupNorm (also across a skip concat),
+ *         which replaces the rldm_gn_stats pass.  Needs Wo*Ho >= 64.
  * Requires Ho a power of two <= 128, Wo*Ho a multiple or a divisor of 128, Cout % 64 == 0. */
 int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias, const float* temb,
                  int temb_stride, const float* residual, float* out, int B, int W, int H, int Cin,
                  int Cout, int ks, int stride, int pad_lo, int circular, int split_k, double* stats,
-                 int stats_groups, void* stream);
+                 void* stream);
 
 /* CUDA-core restatement of rldm_conv_tc with the identical contract (split_k ignored); used by the
  * GPU tests to isolate tensor-core descriptor bugs from precision, never by the product path. */
@@ -152,7 +155,7 @@ typedef struct rldm_op {
   int32_t kind;
   int32_t i[15];      /* integer arguments in the order of the matching entry point */
   float f[2];         /* float arguments (eps) */
-  void* p[10];        /* pointer arguments in the order of the matching entry point */
+  void* p[12];        /* pointer arguments in the order of the matching entry point */
   int64_t n;          /* element / byte count where the entry point takes one */
 } rldm_op;
 int rldm_run(const rldm_op* ops, int n_ops, void* stream);

@@ -19,7 +19,7 @@ OP_GN_STATS, OP_PREP, OP_CONV_TC, OP_CONV_IN, OP_CONV_OUT, OP_ATTENTION, OP_TEMB
 
 class RldmOp(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("i", ctypes.c_int32 * 15), ("f", ctypes.c_float * 2),
-                ("p", ctypes.c_void_p * 10), ("n", ctypes.c_int64)]
+                ("p", ctypes.c_void_p * 12), ("n", ctypes.c_int64)]
 
 
 # name -> (restype, argtypes); must list every symbol include/rldm.h declares
@@ -27,10 +27,10 @@ SIGNATURES = {
     "rldm_version": (c_int, []),
     "rldm_last_error": (ctypes.c_char_p, []),
     "rldm_gn_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "rldm_prep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int,
+    "rldm_prep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int,
                           c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rldm_conv_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
-                     + [c_int] * 10 + [c_void_p, c_int, c_void_p]),
+                     + [c_int] * 10 + [c_void_p, c_void_p]),
     "rldm_conv_ref": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
                       + [c_int] * 9 + [c_void_p]),
     "rldm_conv_in": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 5

@@ -164,37 +164,26 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, uint32_t tmem_acc, 
     }
     if (dbg) p.dbg[8] = clock64();
     if (p.stats) {
-      // GroupNorm moments of the finished output, per (image, group): channel pairs -> lanes -> the 4 epilogue
-      // warps (shared memory) -> ONE double atomic per (group, moment) and image for the whole CTA.
+      // Moments of the finished output per (image, channel PAIR): lanes -> the 4 epilogue warps (shared memory) ->
+      // ONE double atomic per (pair, moment) and image for the whole CTA.  Pairs are the finest granularity any
+      // consumer GroupNorm needs (its groups, also over a skip concat, are unions of whole pairs).
       __shared__ float red_s[4][BLOCK_N / 2], red_q[4][BLOCK_N / 2];
       __shared__ int red_b[4];
-      const int cpg = p.stats_cpg;                        // 2, 4, 8 or 16 channels per group
       if (kRowsPerIter == 2) {
         s01 += __shfl_xor_sync(0xffffffffu, s01, 16); q01 += __shfl_xor_sync(0xffffffffu, q01, 16);
         s23 += __shfl_xor_sync(0xffffffffu, s23, 16); q23 += __shfl_xor_sync(0xffffffffu, q23, 16);
       }
       const bool writer_row = (kRowsPerIter == 1) || rsub == 0;
-      int nslots;
-      if (cpg == 2) {
-        nslots = BLOCK_N / 2;
-        if (writer_row) {
-          red_s[ew][col / 2] = s01; red_q[ew][col / 2] = q01;
-          red_s[ew][col / 2 + 1] = s23; red_q[ew][col / 2 + 1] = q23;
-        }
-      } else {
-        nslots = BLOCK_N / cpg;
-        float sg = s01 + s23, qg = q01 + q23;
-        for (int o = 1; o < cpg / 4; o <<= 1) {
-          sg += __shfl_xor_sync(0xffffffffu, sg, o);
-          qg += __shfl_xor_sync(0xffffffffu, qg, o);
-        }
-        if (writer_row && (lane % (cpg / 4)) == 0) { red_s[ew][col / cpg] = sg; red_q[ew][col / cpg] = qg; }
+      constexpr int nslots = BLOCK_N / 2;                 // one slot per channel PAIR of the tile
+      if (writer_row) {
+        red_s[ew][col / 2] = s01; red_q[ew][col / 2] = q01;
+        red_s[ew][col / 2 + 1] = s23; red_q[ew][col / 2 + 1] = q23;
       }
       if (lane == 0) red_b[ew] = m_first < p.M_total ? bimg : -1;
       asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps only
       const int t = ew * 32 + lane;
       if (t < nslots) {
-        const int g = (n0 / (cpg == 2 ? 2 : cpg)) + t;
+        const int g = n0 / 2 + t;
         double ds = 0.0, dq = 0.0;
         int cur = red_b[0];
         for (int e = 0; e < 4; ++e) {
@@ -568,34 +557,21 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         asm volatile("bar.sync 1, 128;" ::: "memory");     // slab free for the next chunk / next tile
       }
       if (p.stats) {
-        // per-CTA fold of the GroupNorm moments, then one double atomic per (group, moment) and image
-        const int cpg = p.stats_cpg;
-        const int nslots = cpg == 2 ? BLOCK_N / 2 : BLOCK_N / cpg;
+        // per-CTA fold of the channel-pair moments, then one double atomic per (pair, moment) and image
+        constexpr int nslots = BLOCK_N / 2;
         if (lane < 8) {
 #pragma unroll
           for (int nc = 0; nc < kChunks; ++nc) {
             const int cc = nc * 32 + col;                  // column of this lane's float4 inside the tile
-            if (cpg == 2) {
-              red_s[ew * (BLOCK_N / 2) + cc / 2] = sg[nc];       red_q[ew * (BLOCK_N / 2) + cc / 2] = qg[nc];
-              red_s[ew * (BLOCK_N / 2) + cc / 2 + 1] = s23c[nc]; red_q[ew * (BLOCK_N / 2) + cc / 2 + 1] = q23c[nc];
-            } else {
-              float a = sg[nc] + s23c[nc], b = qg[nc] + q23c[nc];
-              for (int o = 1; o < cpg / 4; o <<= 1) {      // cpg 8/16: neighbouring float4 columns share a group
-                a += __shfl_xor_sync(0x000000ffu, a, o);
-                b += __shfl_xor_sync(0x000000ffu, b, o);
-              }
-              if (((lane & 7) % (cpg / 4)) == 0) {
-                red_s[ew * (BLOCK_N / 2) + cc / cpg] = a;
-                red_q[ew * (BLOCK_N / 2) + cc / cpg] = b;
-              }
-            }
+            red_s[ew * (BLOCK_N / 2) + cc / 2] = sg[nc];       red_q[ew * (BLOCK_N / 2) + cc / 2] = qg[nc];
+            red_s[ew * (BLOCK_N / 2) + cc / 2 + 1] = s23c[nc]; red_q[ew * (BLOCK_N / 2) + cc / 2 + 1] = q23c[nc];
           }
         }
         if (lane == 0) red_b[ew] = m_first < p.M_total ? bimg : -1;
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int tix = ew * 32 + lane;
         if (tix < nslots) {
-          const int gidx = (n0 / (cpg == 2 ? 2 : cpg)) + tix;
+          const int gidx = n0 / 2 + tix;
           double ds = 0.0, dq = 0.0;
           int cur = red_b[0];
           for (int e = 0; e < 4; ++e) {
@@ -886,7 +862,7 @@ extern "C" void rldm_debug_conv_timestamps(long long* dev_buf) { g_conv_dbg = de
 extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias,
                             const float* temb, int temb_stride, const float* residual, float* out,
                             int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
-                            int circular, int split_k, double* stats, int stats_groups, void* stream) {
+                            int circular, int split_k, double* stats, void* stream) {
   RLDM_CHECK(ks == 1 || ks == 3, "conv_tc: ks must be 1 or 3 (got %d)", ks);
   RLDM_CHECK(stride == 1 || stride == 2, "conv_tc: stride must be 1 or 2 (got %d)", stride);
   RLDM_CHECK(Cin % 64 == 0, "conv_tc: Cin %% 64 != 0 (got %d)", Cin);
@@ -965,12 +941,8 @@ extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint1
       p.nb_stages = nbs;
       p.dbg = nullptr;
       p.stats = stats;
-      p.stats_G = stats_groups;
-      p.stats_cpg = stats_groups > 0 ? Cout / stats_groups : 0;
-      RLDM_CHECK(!stats || (Cout % stats_groups == 0 && (p.stats_cpg == 2 || p.stats_cpg == 4 || p.stats_cpg == 8 ||
-                                                         p.stats_cpg == 16)),
-                 "conv_tc: fused GroupNorm statistics need 2, 4, 8 or 16 channels per group (Cout=%d, G=%d)", Cout,
-                 stats_groups);
+      p.stats_G = Cout / 2;
+      p.stats_cpg = 2;
       const int tiles = ((p.M_total + MT * 128 - 1) / (MT * 128)) * (Cout / BN);
       int split = split_k;
       if (split <= 0) {
@@ -1026,11 +998,8 @@ extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint1
   p.units = 0; p.a_part_bytes = 0; p.nb_stages = 0;
   p.dbg = g_conv_dbg;
   p.stats = stats;
-  p.stats_G = stats_groups;
-  p.stats_cpg = stats_groups > 0 ? Cout / stats_groups : 0;
-  RLDM_CHECK(!stats || (Cout % stats_groups == 0 && (p.stats_cpg == 2 || p.stats_cpg == 4 || p.stats_cpg == 8 ||
-                                                     p.stats_cpg == 16)),
-             "conv_tc: fused GroupNorm statistics need 2, 4, 8 or 16 channels per group (Cout=%d, G=%d)", Cout, stats_groups);
+  p.stats_G = Cout / 2;       // channel pairs per image
+  p.stats_cpg = 2;
   RLDM_CHECK(pix >= 64 || !stats, "conv_tc: fused statistics need >= 64 pixels per image");
   const int tiles = ((p.M_total + kBlockM - 1) / kBlockM) * (Cout / BN);
   int split = split_k;

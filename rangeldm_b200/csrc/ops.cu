@@ -110,7 +110,8 @@ __device__ __forceinline__ void store_split8(const float (&v)[8], __half* out, _
 // (two float4 loads, one 16 B store).
 __global__ void __launch_bounds__(256)
 prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
-            const double* __restrict__ sums, const float* __restrict__ gamma,
+            const double* __restrict__ sums, const double* __restrict__ pairs0,
+            const double* __restrict__ pairs1, const float* __restrict__ gamma,
             const float* __restrict__ beta, float eps, int G, int silu, int up, int circular,
             __half* __restrict__ out, __half* __restrict__ out_lo, __half* __restrict__ raw,
             __half* __restrict__ raw_lo, int W, int H, int pix_per_block) {
@@ -120,13 +121,26 @@ prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, 
   const int b = blockIdx.y;
   float* sc = shf;
   float* sf = shf + C;
-  if (sums) {
+  const bool norm = sums != nullptr || pairs0 != nullptr;
+  if (norm) {
+    // group moments: either the (sum, sum^2) per (image, group) of rldm_gn_stats, or the per channel-PAIR moments
+    // that the producing convolutions accumulated in their epilogues (x0's pairs, then x1's for a skip concat)
     const int cpg = C / G;
     const double inv_n = 1.0 / (static_cast<double>(W) * H * cpg);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const int g = c / cpg;
-      const double s = sums[(static_cast<size_t>(b) * G + g) * 2];
-      const double ss = sums[(static_cast<size_t>(b) * G + g) * 2 + 1];
+      double s = 0.0, ss = 0.0;
+      if (sums) {
+        s = sums[(static_cast<size_t>(b) * G + g) * 2];
+        ss = sums[(static_cast<size_t>(b) * G + g) * 2 + 1];
+      } else {
+        for (int cc = g * cpg; cc < (g + 1) * cpg; cc += 2) {
+          const double* pr = cc < c0 ? pairs0 + (static_cast<size_t>(b) * (c0 / 2) + cc / 2) * 2
+                                     : pairs1 + (static_cast<size_t>(b) * (c1 / 2) + (cc - c0) / 2) * 2;
+          s += pr[0];
+          ss += pr[1];
+        }
+      }
       const double mean = s * inv_n;
       double var = ss * inv_n - mean * mean;
       if (var < 0) var = 0;
@@ -169,7 +183,7 @@ prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, 
     const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
     float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
     if (raw) store_split8(v, raw, raw_lo, o);      // second output: the un-normalised operand (1x1 shortcut input)
-    if (sums) {
+    if (norm) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[c + j], sf[c + j]);
     }
@@ -304,7 +318,7 @@ conv_in_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x
 // LPP lanes share one pixel (splitting the channel loop, butterfly-reduced) when there are too few pixels to
 // fill the machine with one thread each.
 template <int COUT, int LPP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, const float* __restrict__ wgt,
                 const float* __restrict__ bias, float* __restrict__ out, int B, int W, int H,
                 int Cin, int circular) {
@@ -316,8 +330,12 @@ conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, c
   __syncthreads();
   const size_t total_pix = static_cast<size_t>(B) * W * H;
   const int sub = threadIdx.x % LPP;
-  const size_t pp = min((static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPP, total_pix - 1);
-  const bool live = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPP < total_pix;
+  const int ppp = blockDim.x / LPP;                    // pixels per pass of the block
+  // grid-stride over pixel groups: the weights are staged once per block, not once per 16 pixels
+  for (size_t g0 = static_cast<size_t>(blockIdx.x) * ppp; g0 < total_pix; g0 += static_cast<size_t>(gridDim.x) * ppp) {
+  const size_t praw = g0 + threadIdx.x / LPP;
+  const bool live = praw < total_pix;
+  const size_t pp = live ? praw : total_pix - 1;
   const int h = pp % H;
   const int w = (pp / H) % W;
   const int b = pp / (static_cast<size_t>(H) * W);
@@ -368,6 +386,7 @@ conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, c
 #pragma unroll
     for (int o = LPP / 2; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
     if (live && sub == 0) out[((static_cast<size_t>(b) * COUT + n) * W + w) * H + h] = acc[n];
+  }
   }
 }
 
@@ -767,19 +786,22 @@ extern "C" int rldm_gn_stats(const float* x0, int c0, const float* x1, int c1, d
 }
 
 extern "C" int rldm_prep(const float* x0, int c0, const float* x1, int c1, const double* sums,
+                         const double* pairs0, const double* pairs1,
                          const float* gamma, const float* beta, float eps, int G, int silu, int up,
                          int circular, uint16_t* out, uint16_t* out_lo, uint16_t* raw, uint16_t* raw_lo, int B,
                          int W, int H, void* stream) {
   const int C = c0 + c1;
   RLDM_CHECK(c0 % 8 == 0 && c1 % 8 == 0, "prep: channels must be multiples of 8 (c0=%d c1=%d)", c0, c1);
   RLDM_CHECK(up == 1 || up == 2, "prep: up must be 1 or 2");
-  RLDM_CHECK(!sums || (gamma && beta && G > 0 && C % G == 0), "prep: GroupNorm needs gamma/beta/G");
+  RLDM_CHECK(!(sums || pairs0) || (gamma && beta && G > 0 && C % G == 0), "prep: GroupNorm needs gamma/beta/G");
+  RLDM_CHECK(!pairs0 || ((C / G) % 2 == 0 && c0 % 2 == 0 && (c1 == 0 || pairs1)),
+             "prep: channel-pair moments need an even group size and moments for both concat sources");
   const int out_pix = (W * up + 2) * H * up;
   int chunks = (592 + B - 1) / B;
   int ppb = (out_pix + chunks - 1) / chunks;
   if (ppb < 8) ppb = 8;
   chunks = (out_pix + ppb - 1) / ppb;
-  RLDM_CUDA(launch_pdl(prep_kernel, dim3(chunks, B), dim3(256), 2 * C * sizeof(float), as_stream(stream), x0, c0, x1, c1, sums, gamma, beta, eps, G, silu, up, circular, reinterpret_cast<__half*>(out),
+  RLDM_CUDA(launch_pdl(prep_kernel, dim3(chunks, B), dim3(256), 2 * C * sizeof(float), as_stream(stream), x0, c0, x1, c1, sums, pairs0, pairs1, gamma, beta, eps, G, silu, up, circular, reinterpret_cast<__half*>(out),
       reinterpret_cast<__half*>(out_lo), reinterpret_cast<__half*>(raw), reinterpret_cast<__half*>(raw_lo), W, H, ppb));
   RLDM_LAUNCH_CHECK();
   return 0;
@@ -826,11 +848,12 @@ extern "C" int rldm_conv_out(const uint16_t* x, const uint16_t* x_lo, const floa
   cudaStream_t st = as_stream(stream);
   const size_t smem = static_cast<size_t>(9) * Cout * Cin * sizeof(float);
   RLDM_CHECK(smem <= 48 * 1024, "conv_out: 9*Cout*Cin weights exceed 48 KB of shared memory");
-  const bool wide = total_pix < 200000 && Cin % 64 == 0;        // 8 lanes per pixel when pixels are scarce
-  const unsigned grid = static_cast<unsigned>((total_pix * (wide ? 8 : 1) + 127) / 128);
+  const bool wide = Cin % 64 == 0;        // 8 lanes per pixel: each warp load touches 4 full 128 B lines
+  const size_t groups = (total_pix * (wide ? 8 : 1) + 255) / 256;
+  const unsigned grid = static_cast<unsigned>(groups < 1184 ? groups : 1184);
 #define RLDM_CO(N)                                                                                              \
-  if (wide) RLDM_CUDA(launch_pdl(conv_out_kernel<N, 8>, dim3(grid), dim3(128), smem, st, xh, xl, wgt, bias, out, B, W, H, Cin, circular)); \
-  else RLDM_CUDA(launch_pdl(conv_out_kernel<N, 1>, dim3(grid), dim3(128), smem, st, xh, xl, wgt, bias, out, B, W, H, Cin, circular));
+  if (wide) RLDM_CUDA(launch_pdl(conv_out_kernel<N, 8>, dim3(grid), dim3(256), smem, st, xh, xl, wgt, bias, out, B, W, H, Cin, circular)); \
+  else RLDM_CUDA(launch_pdl(conv_out_kernel<N, 1>, dim3(grid), dim3(256), smem, st, xh, xl, wgt, bias, out, B, W, H, Cin, circular));
   switch (Cout) {
     case 2: RLDM_CO(2) break;
     case 4: RLDM_CO(4) break;
@@ -909,14 +932,14 @@ extern "C" int rldm_run(const rldm_op* ops, int n_ops, void* stream) {
         break;
       case RLDM_OP_PREP:
         rc = rldm_prep((const float*)o.p[0], o.i[0], (const float*)o.p[1], o.i[1], (const double*)o.p[2],
-                       (const float*)o.p[3], (const float*)o.p[4], o.f[0], o.i[2], o.i[3], o.i[4], o.i[8],
+                       (const double*)o.p[9], (const double*)o.p[10], (const float*)o.p[3], (const float*)o.p[4], o.f[0], o.i[2], o.i[3], o.i[4], o.i[8],
                        (uint16_t*)o.p[5], (uint16_t*)o.p[6], (uint16_t*)o.p[7], (uint16_t*)o.p[8], o.i[5], o.i[6], o.i[7],
                        stream);
         break;
       case RLDM_OP_CONV_TC:
         rc = rldm_conv_tc((const uint16_t*)o.p[0], (const uint16_t*)o.p[6], (const uint16_t*)o.p[1], (const float*)o.p[2],
                           (const float*)o.p[3], o.i[0], (const float*)o.p[4], (float*)o.p[5], o.i[1],
-                          o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], o.i[7], o.i[8], o.i[9], o.i[10], (double*)o.p[7], o.i[11], stream);
+                          o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], o.i[7], o.i[8], o.i[9], o.i[10], (double*)o.p[7], stream);
         break;
       case RLDM_OP_CONV_REF:
         rc = rldm_conv_ref((const uint16_t*)o.p[0], (const uint16_t*)o.p[6], (const uint16_t*)o.p[1], (const float*)o.p[2],

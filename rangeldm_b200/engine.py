@@ -113,8 +113,8 @@ class Program:
 
 
 class Act:
-    """Channels-last fp32 activation (B, W, H, C).  `stats` = (arena slice, G) when the producing conv already
-    accumulated the GroupNorm moments of this tensor in its epilogue."""
+    """Channels-last fp32 activation (B, W, H, C).  `stats` = arena slice [B][C/2][2] when the producing conv already
+    accumulated the channel-pair moments of this tensor in its epilogue."""
     __slots__ = ("t", "B", "W", "H", "C", "stats")
 
     def __init__(self, t, B, W, H, C, stats=None):
@@ -128,7 +128,7 @@ def _is_identity_attn(m):
 class Builder:
     """Emits ops for the building blocks shared by the UNet and the VAE."""
 
-    def __init__(self, prog, batch, max_gn=1024, groups=32, cache=None):
+    def __init__(self, prog, batch, max_gn=4096, groups=32, cache=None):
         self.cache = cache if cache is not None else {}      # packed weights shared between plans of a model
         if PRECISION not in ("fp16x3", "fp16"):
             raise ValueError(f"RLDM_PRECISION must be 'fp16x3' or 'fp16', got {PRECISION!r}")
@@ -136,7 +136,7 @@ class Builder:
         self.pg = prog
         self.B = batch
         self.groups = groups
-        self.gn_arena = prog.hold(torch.zeros(max_gn * batch * groups * 2, dtype=torch.float64, device=prog.device))
+        self.gn_arena = prog.hold(torch.zeros(max_gn * batch * groups * 2, dtype=torch.float64, device=prog.device))   # 16 MB at batch 8
         self.gn_used = 0
         self.memset_op = prog.add(_lib.OP_MEMSET, p=(self.gn_arena,), n=0)
         self.temb = None         # (tensor (B,T), T)
@@ -191,6 +191,7 @@ class Builder:
 
     # ---- primitive emitters ----------------------------------------------------------------
     def stats_slot(self, groups):
+        """`groups` (sum, sum^2) slots per image from the per-forward arena (zeroed by one fill per forward)."""
         n = self.B * groups * 2
         off = self.gn_used
         self.gn_used += n
@@ -198,8 +199,6 @@ class Builder:
         return self.gn_arena[off:off + n]
 
     def gn_stats(self, x0, x1, groups):
-        if x1 is None and x0.stats is not None and x0.stats[1] == groups:
-            return x0.stats[0]                  # already accumulated by the producing conv's epilogue
         sums = self.stats_slot(groups)
         c1 = x1.C if x1 is not None else 0
         self.pg.add(_lib.OP_GN_STATS, i=(x0.C, c1, self.B, x0.W * x0.H, groups),
@@ -211,16 +210,22 @@ class Builder:
         second pair holding the un-normalised input (1x1 shortcut operand) written by the same launch."""
         c1 = x1.C if x1 is not None else 0
         C = x0.C + c1
-        sums = gamma = beta = None
+        sums = pairs0 = pairs1 = gamma = beta = None
         eps, G = 0.0, 0
         if norm is not None:
             G = norm.num_groups
-            sums = self.gn_stats(x0, x1, G)
+            fused = (x0.stats is not None and (x1 is None or x1.stats is not None) and (C // G) % 2 == 0
+                     and x0.C % 2 == 0)
+            if fused:     # channel-pair moments from the producing conv epilogues (both sources of a skip concat)
+                pairs0, pairs1 = x0.stats, (x1.stats if x1 is not None else None)
+            else:
+                sums = self.gn_stats(x0, x1, G)
             gamma, beta, eps = self.f32(norm.weight), self.f32(norm.bias), norm.eps
         out = self.alloc_half((self.B, x0.W * up + 2, x0.H * up, C))
         raw = self.alloc_half((self.B, x0.W * up + 2, x0.H * up, C)) if also_raw else (None, None)
         self.pg.add(_lib.OP_PREP, i=(x0.C, c1, G, int(silu), up, self.B, x0.W, x0.H, int(circular)), f=(eps,),
-                    p=(x0.t, x1.t if x1 is not None else None, sums, gamma, beta, out[0], out[1], raw[0], raw[1]))
+                    p=(x0.t, x1.t if x1 is not None else None, sums, gamma, beta, out[0], out[1], raw[0], raw[1],
+                       pairs0, pairs1))
         return (out, raw) if also_raw else out
 
     def conv(self, xh, W, H, conv=None, packed=None, cin=None, cout=None, ks=3, stride=1, pad_lo=1, circular=True,
@@ -245,12 +250,11 @@ class Builder:
         ints = [temb_stride, self.B, W, H, cin, cout, ks, stride, pad_lo, int(circular)]
         st = None
         if kind == _lib.OP_CONV_TC:
-            G = self.groups
-            if stats and FUSE_STATS and Wo * Ho >= 64 and cout % G == 0 and cout // G in (2, 4, 8, 16):
-                st = (self.stats_slot(G), G)
-            ints += [0, G if st else 0]   # split_k: auto; stats groups
+            if stats and FUSE_STATS and Wo * Ho >= 64:
+                st = self.stats_slot(cout // 2)          # channel-pair moments [B][Cout/2][2]
+            ints += [0]   # split_k: auto
         self.pg.add(kind, i=ints, p=(xh[0], wt, bias, temb_t, residual.t if residual is not None else None, out,
-                                     xh[1], st[0] if st else None), launches=1)
+                                     xh[1], st), launches=1)
         return Act(out, self.B, Wo, Ho, cout, st)
 
     # ---- blocks ----------------------------------------------------------------------------

@@ -31,7 +31,7 @@ def run(split_mode):
         stats = torch.zeros(B, 32, 2, dtype=torch.float64, device="cuda")
         def call():
             L.call("rldm_conv_tc", L.ptr(x), L.ptr(xl) if split_mode else None, L.ptr(w), L.ptr(bias), None, 0, L.ptr(res),
-                   L.ptr(out), B, W, H, Cin, Cout, ks, stride, 1 if ks == 3 else 0, 1, 0, None, 0)
+                   L.ptr(out), B, W, H, Cin, Cout, ks, stride, 1 if ks == 3 else 0, 1, 0, None)
         for _ in range(5): call()
         torch.cuda.synchronize()
         n = 50
@@ -57,7 +57,7 @@ for (B, W, H, Cin, Cout, ks, stride, name) in SHAPES[:3] + SHAPES[6:7] + SHAPES[
     out = torch.empty(B, W // stride, H // stride, Cout, device="cuda"); res = torch.randn_like(out)
     for _ in range(3):
         L.call("rldm_conv_tc", L.ptr(x), L.ptr(xl), L.ptr(w), None, None, 0, L.ptr(res), L.ptr(out), B, W, H, Cin, Cout, ks,
-               stride, 1 if ks == 3 else 0, 1, 0, None, 0)
+               stride, 1 if ks == 3 else 0, 1, 0, None)
     torch.cuda.synchronize()
     t = buf.cpu().tolist()
     d = [(t[i] - t[0]) for i in range(6)]

@@ -104,7 +104,7 @@ def test_conv_tc_matches_cuda_core_restatement_and_oracle(L, case):
     out_tc = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
     out_rf = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
     L.call("rldm_conv_tc", L.ptr(xh), None, L.ptr(wt), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out_tc),
-           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, None, 0)
+           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, None)
     L.call("rldm_conv_ref", L.ptr(xh), None, L.ptr(wt), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out_rf),
            B, W, H, Cin, Cout, ks, stride, pad_lo, circ)
     torch.cuda.synchronize()
@@ -122,19 +122,18 @@ def test_conv_tc_matches_cuda_core_restatement_and_oracle(L, case):
     xh2, xl2, wt2 = padw(xh2, bool(circ)).cuda(), padw(xl2, bool(circ)).cuda(), pack_w(w, split=True).cuda()
     out3 = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
     out3r = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
-    G = 32
-    fused = Wo * Ho >= 64 and Cout // G in (2, 4, 8, 16)
-    stats = torch.zeros(B, G, 2, dtype=torch.float64, device="cuda")
+    fused = Wo * Ho >= 64
+    stats = torch.zeros(B, Cout // 2, 2, dtype=torch.float64, device="cuda")
     L.call("rldm_conv_tc", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out3),
-           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, L.ptr(stats) if fused else None, G if fused else 0)
-    if fused:     # GroupNorm moments accumulated by the epilogue == moments of the tensor it wrote
-        og = out3.double().reshape(B, Wo * Ho, G, Cout // G)
+           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, L.ptr(stats) if fused else None)
+    if fused:     # channel-pair moments accumulated by the epilogue == moments of the tensor it wrote
+        og = out3.double().reshape(B, Wo * Ho, Cout // 2, 2)
         assert torch.allclose(stats[:, :, 0], og.sum((1, 3)), rtol=1e-5, atol=1e-3)
         assert torch.allclose(stats[:, :, 1], (og * og).sum((1, 3)), rtol=1e-5, atol=1e-3)
     # split-K through the cluster/DSMEM reduction is deterministic: a second launch is bit-identical
     out3b = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
     L.call("rldm_conv_tc", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out3b),
-           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, None, 0)
+           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, None)
     assert torch.equal(out3, out3b)
     L.call("rldm_conv_ref", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd),
            L.ptr(out3r), B, W, H, Cin, Cout, ks, stride, pad_lo, circ)
@@ -151,12 +150,12 @@ def test_conv_tc_golden_reference_conv(L, golden):
         out = torch.empty(B, W // stride, H // stride, Cout, device="cuda")
         xh, wt, bd = padw(cl(x).half()).cuda(), pack_w(w).cuda(), b.cuda()     # keep the operands alive across the call
         L.call("rldm_conv_tc", L.ptr(xh), None, L.ptr(wt), L.ptr(bd), None, 0, None,
-               L.ptr(out), B, W, H, Cin, Cout, 3, stride, 1, 1, 0, None, 0)
+               L.ptr(out), B, W, H, Cin, Cout, 3, stride, 1, 1, 0, None)
         assert relerr(ref_layout(out.cpu()), y) < 1e-3
         xh2, xl2 = split_half(cl(x))
         xh2, xl2, wt2 = padw(xh2).cuda(), padw(xl2).cuda(), pack_w(w, split=True).cuda()
         L.call("rldm_conv_tc", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), None, 0, None,
-               L.ptr(out), B, W, H, Cin, Cout, 3, stride, 1, 1, 0, None, 0)
+               L.ptr(out), B, W, H, Cin, Cout, 3, stride, 1, 1, 0, None)
         assert relerr(ref_layout(out.cpu()), y) < 1e-5
 
 
@@ -164,7 +163,7 @@ def test_conv_tc_rejects_bad_shapes(L):
     x = torch.zeros(1, 10, 8, 48, dtype=torch.half, device="cuda")
     with pytest.raises(L.RldmError):
         L.call("rldm_conv_tc", L.ptr(x), None, L.ptr(x), None, None, 0, None, L.ptr(x), 1, 8, 8, 48, 64, 3, 1, 1, 1, 0,
-               None, 0)
+               None)
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 0, 16, 8, 1), (2, 128, 256, 8, 4, 1), (1, 256, 128, 16, 2, 2),
@@ -188,7 +187,7 @@ def test_gn_stats_and_prep(L, shape):
     out = torch.empty(B, W * up + 2, H * up, C, dtype=torch.half, device="cuda")
     gd, bd = gamma.cuda(), beta.cuda()
     out_lo = torch.empty_like(out)
-    L.call("rldm_prep", L.ptr(x0d), C0, L.ptr(x1d), C1, L.ptr(sums), L.ptr(gd), L.ptr(bd), eps, G, 1,
+    L.call("rldm_prep", L.ptr(x0d), C0, L.ptr(x1d), C1, L.ptr(sums), None, None, L.ptr(gd), L.ptr(bd), eps, G, 1,
            up, 1, L.ptr(out), L.ptr(out_lo), None, None, B, W, H)
     y = F.silu(F.group_norm(xc, G, gamma, beta, eps))
     if up == 2:
@@ -197,17 +196,26 @@ def test_gn_stats_and_prep(L, shape):
     assert relerr(ref_layout(unpadw(out.float() + out_lo.float()).cpu()), y) < 5e-6      # hi + lo: split-fp16
     assert torch.equal(out[:, 0], out[:, -2]) and torch.equal(out[:, -1], out[:, 1])   # circular halo columns
     # raw cast path (no norm, no silu), zero halo
-    L.call("rldm_prep", L.ptr(x0d), C0, L.ptr(x1d), C1, None, None, None, 0.0, 0, 0, up, 0, L.ptr(out), None, None, None,
+    L.call("rldm_prep", L.ptr(x0d), C0, L.ptr(x1d), C1, None, None, None, None, None, 0.0, 0, 0, up, 0, L.ptr(out), None, None, None,
            B, W, H)
     yr = F.interpolate(xc, scale_factor=2.0, mode="nearest") if up == 2 else xc
     assert torch.equal(ref_layout(unpadw(out).cpu()), yr.half())
     assert float(out[:, 0].abs().max()) == 0.0 and float(out[:, -1].abs().max()) == 0.0
     # dual output: normalised+SiLU operand and the raw operand from one launch
     raw, raw_lo = torch.empty_like(out), torch.empty_like(out)
-    L.call("rldm_prep", L.ptr(x0d), C0, L.ptr(x1d), C1, L.ptr(sums), L.ptr(gd), L.ptr(bd), eps, G, 1,
+    L.call("rldm_prep", L.ptr(x0d), C0, L.ptr(x1d), C1, L.ptr(sums), None, None, L.ptr(gd), L.ptr(bd), eps, G, 1,
            up, 1, L.ptr(out), L.ptr(out_lo), L.ptr(raw), L.ptr(raw_lo), B, W, H)
     assert relerr(ref_layout(unpadw(out.float() + out_lo.float()).cpu()), y) < 5e-6
     assert relerr(ref_layout(unpadw(raw.float() + raw_lo.float()).cpu()), yr) < 5e-6
+    # channel-pair moments (what conv epilogues accumulate) instead of group sums: same normalisation
+    if (C // G) % 2 == 0:
+        def pairs(x):
+            xp = x.double().reshape(B, x.shape[1] // 2, -1)
+            return torch.stack([xp.sum(-1), (xp * xp).sum(-1)], -1).contiguous().cuda()
+        p0, p1 = pairs(x0), (pairs(x1) if C1 else None)
+        L.call("rldm_prep", L.ptr(x0d), C0, L.ptr(x1d), C1, None, L.ptr(p0), L.ptr(p1), L.ptr(gd), L.ptr(bd), eps, G, 1,
+               up, 1, L.ptr(out), L.ptr(out_lo), None, None, B, W, H)
+        assert relerr(ref_layout(unpadw(out.float() + out_lo.float()).cpu()), y) < 5e-6
 
 
 @pytest.mark.parametrize("cuda_core", [False, True], ids=["mma", "cudacore"])
