@@ -159,6 +159,10 @@ typedef struct rldm_op {
   int64_t n;          /* element / byte count where the entry point takes one */
 } rldm_op;
 int rldm_run(const rldm_op* ops, int n_ops, void* stream);
+/* Profiling variant: the same launches, with a one-thread kernel after every op (and one before the first) that
+ * writes %globaltimer (ns) into stamps[0..n_ops]; stamps[k+1]-stamps[k] is op k's serialised, cache-warm
+ * duration.  Graph-capturable.  Used by bench.py's roofline pass and scripts/, never by the sampling path. */
+int rldm_run_timed(const rldm_op* ops, int n_ops, unsigned long long* stamps, void* stream);
 
 /* y = a*x (elementwise, fp32), e.g. latents / scaling_factor (`ldm/pipelines.py:365`). */
 int rldm_scale(const float* x, float a, float* y, int64_t n, void* stream);

@@ -43,6 +43,7 @@ SIGNATURES = {
     "rldm_ref_to_cl": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rldm_cl_to_ref": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rldm_run": (c_int, [ctypes.POINTER(RldmOp), c_int, c_void_p]),
+    "rldm_run_timed": (c_int, [ctypes.POINTER(RldmOp), c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -212,8 +212,16 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, uint32_t tmem_acc, 
 // TERMS = 3: split-fp16 ("fp16x3"): A = Ah + Al, W = Wh + Wl (each part fp16), D += Ah*Wh + Al*Wh + Ah*Wl --
 //            ~22-bit operand significands on the fp16 tensor pipe, fp32 accumulation in TMEM.  This is the
 //            default: it keeps 20-step trajectories within the 1e-3 parity tolerance with >100x margin.
-template <int BLOCK_N, int STAGES, int TERMS>
-__global__ void __launch_bounds__(192, TERMS == 1 ? 2 : 1)
+// NSPLIT   : CTAs of the cluster that share one output tile (split K); == gridDim.z.
+//
+// Latency structure (these layers are small: the whole kernel is a handful of microseconds, so every serial
+// round trip counts).  The four epilogue warps are idle during the K loop, so they fetch bias, time embedding and
+// ALL residual rows they will need into registers right after griddepcontrol.wait -- the L2 latency of the
+// residual hides under the mainloop.  The split-K reduction pulls the partial tiles of the peer CTAs through
+// distributed shared memory in batches of 16 independent 16 B loads per lane (fixed summation order:
+// deterministic), instead of one dependent load at a time.
+template <int BLOCK_N, int STAGES, int TERMS, int NSPLIT>
+__global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
@@ -222,6 +230,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int kBOff = kParts * kABytes;
   constexpr int kStagePitch = BLOCK_N + 4;                     // floats per row of the epilogue staging tile
   static_assert(kBlockM * kStagePitch * 4 <= STAGES * kStageBytes, "staging tile must fit in the pipeline stages");
+  // epilogue geometry: a warp instruction covers kRowsPerIter rows of BLOCK_N floats (float4 per lane)
+  constexpr int kLanesPerRow = BLOCK_N / 4;               // 32 (BN=128) or 16 (BN=64)
+  constexpr int kRowsPerIter = 32 / kLanesPerRow;         // 1 or 2
+  constexpr int kRowsCta = kBlockM / NSPLIT;              // rows this CTA finalises
+  constexpr int kRowsWarp = kRowsCta / 4;                 // contiguous rows per epilogue warp
+  constexpr int kPerLane = kRowsWarp / kRowsPerIter;      // float4 per lane: 32, 16, 8, 4 (BN=128); half for BN=64
+  static_assert(kPerLane >= 1, "tile too small for this split");
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024 B alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -230,14 +245,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* red_s = reinterpret_cast<float*>(tmem_ptr + 4);       // [4][BLOCK_N/2]
+  float* red_q = red_s + 4 * (BLOCK_N / 2);
+  int* red_b = reinterpret_cast<int*>(red_q + 4 * (BLOCK_N / 2));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kBlockM;
   const int n0 = blockIdx.y * BLOCK_N;
-  const int it0 = static_cast<int>(static_cast<long long>(blockIdx.z) * p.total_iters / gridDim.z);
-  const int it1 = static_cast<int>(static_cast<long long>(blockIdx.z + 1) * p.total_iters / gridDim.z);
-  const int n_it = it1 - it0;                    // >= 1: the host keeps gridDim.z <= total_iters
+  const int it0 = static_cast<int>(static_cast<long long>(blockIdx.z) * p.total_iters / NSPLIT);
+  const int it1 = static_cast<int>(static_cast<long long>(blockIdx.z + 1) * p.total_iters / NSPLIT);
+  const int n_it = it1 - it0;                    // >= 1: the host keeps NSPLIT <= total_iters
 
   const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
@@ -275,6 +293,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   pdl_wait();        // everything above overlapped the previous kernel; below we touch its outputs
   if (dbg && threadIdx.x == 0) p.dbg[1] = clock64();
+
+  // epilogue coordinates (meaningful for warps >= 2)
+  const int ew = (warp - 2) & 3;
+  const int r_begin = blockIdx.z * kRowsCta + ew * kRowsWarp;     // first tile row this warp finalises
+  const int col = (lane % kLanesPerRow) * 4;
+  const int rsub = lane / kLanesPerRow;
+  const int m_first = m0 + r_begin;
+  // all rows of one warp lie in one image (pix_per_img is a power of two >= 64, or whole images per tile row group)
+  const int bimg = min(m_first, p.M_total - 1) / p.pix_per_img;
+  float4 res[kPerLane];
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp: lanes share the column loads) =============
@@ -345,12 +373,140 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else {
+    // ===================== epilogue warps: prefetch, then TMEM -> shared staging tile ===========
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col));
+    if (p.temb) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.temb + static_cast<size_t>(bimg) * p.temb_stride + n0 + col));
+      bias4.x += t4.x; bias4.y += t4.y; bias4.z += t4.z; bias4.w += t4.w;
+    }
+#pragma unroll
+    for (int u = 0; u < kPerLane; ++u) {
+      const int m = m_first + u * kRowsPerIter + rsub;
+      res[u] = bias4;
+      if (p.residual && m < p.M_total) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(m) * p.Cout + n0 + col));
+        res[u].x += t.x; res[u].y += t.y; res[u].z += t.z; res[u].w += t.w;
+      }
+    }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (dbg && threadIdx.x == 64) p.dbg[4] = clock64();
+    // The pipeline stages are dead once tmem_full fires (all TMA writes consumed, all MMA reads done), so the
+    // fp32 accumulator tile [128][BLOCK_N] is staged over them (row pitch +4 floats: conflict-free float4).
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    float* stage_row = reinterpret_cast<float*>(smem) + (q * 32 + lane) * kStagePitch;
+#pragma unroll 1
+    for (int nc = 0; nc < BLOCK_N / 32; ++nc) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + nc * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(stage_row + nc * 32 + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    }
+    if (dbg && threadIdx.x == 64) p.dbg[6] = clock64();
   }
-  epilogue_tile<BLOCK_N>(smem, tmem_base, m0, n0, p, warp, lane);
-  if (dbg && threadIdx.x == 64) p.dbg[5] = clock64();
+  // ======================= (cluster) reduce + stats + store =====================================================
+  // split-K: the NSPLIT CTAs of a cluster (same tile, different K slices) each staged a partial tile; CTA `rank`
+  // owns rows [rank*128/NSPLIT, ...) and sums them over all ranks through distributed shared memory in a fixed
+  // order (deterministic, no atomics, no zero-fill).
+  tc_fence_before();
+  if (NSPLIT > 1) {
+    cluster_sync_all();
+  } else if (warp >= 2) {
+    asm volatile("bar.sync 1, 128;" ::: "memory");        // only the epilogue warps touch the staging tile
+  }
+  if (warp >= 2) {
+    if (dbg && threadIdx.x == 64) p.dbg[7] = clock64();
+    float s01 = 0.f, q01 = 0.f, s23 = 0.f, q23 = 0.f;     // moments of channel pairs (0,1) and (2,3)
+    const uint32_t stage_u32 = smem_u32(smem);
+    if (NSPLIT == 1) {
+#pragma unroll
+      for (int u = 0; u < kPerLane; ++u) {
+        const int r = r_begin + u * kRowsPerIter + rsub;
+        const int m = m0 + r;
+        const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem) + r * kStagePitch + col);
+        float4 v = res[u];
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        if (m < p.M_total) {
+          *reinterpret_cast<float4*>(p.out + static_cast<size_t>(m) * p.Cout + n0 + col) = v;
+          s01 += v.x + v.y; q01 += v.x * v.x + v.y * v.y;
+          s23 += v.z + v.w; q23 += v.z * v.z + v.w * v.w;
+        }
+      }
+    } else {
+      constexpr int kUB = (16 / NSPLIT) < kPerLane ? (16 / NSPLIT) : kPerLane;   // rows per batch of <= 16 loads
+      uint32_t rbase[NSPLIT];
+#pragma unroll
+      for (int sidx = 0; sidx < NSPLIT; ++sidx) rbase[sidx] = mapa_u32(stage_u32, sidx);
+#pragma unroll
+      for (int u0 = 0; u0 < kPerLane; u0 += kUB) {
+        float4 part[kUB][NSPLIT];
+#pragma unroll
+        for (int ub = 0; ub < kUB; ++ub) {
+          const int r = r_begin + (u0 + ub) * kRowsPerIter + rsub;
+          const uint32_t off = static_cast<uint32_t>(r * kStagePitch + col) * 4u;
+#pragma unroll
+          for (int sidx = 0; sidx < NSPLIT; ++sidx) part[ub][sidx] = ld_dsmem_f4(rbase[sidx] + off);
+        }
+#pragma unroll
+        for (int ub = 0; ub < kUB; ++ub) {
+          const int m = m0 + r_begin + (u0 + ub) * kRowsPerIter + rsub;
+          float4 v = res[u0 + ub];
+#pragma unroll
+          for (int sidx = 0; sidx < NSPLIT; ++sidx) {
+            v.x += part[ub][sidx].x; v.y += part[ub][sidx].y; v.z += part[ub][sidx].z; v.w += part[ub][sidx].w;
+          }
+          if (m < p.M_total) {
+            *reinterpret_cast<float4*>(p.out + static_cast<size_t>(m) * p.Cout + n0 + col) = v;
+            s01 += v.x + v.y; q01 += v.x * v.x + v.y * v.y;
+            s23 += v.z + v.w; q23 += v.z * v.z + v.w * v.w;
+          }
+        }
+      }
+    }
+    if (dbg && threadIdx.x == 64) p.dbg[8] = clock64();
+    if (p.stats) {
+      // Moments of the finished output per (image, channel PAIR): lanes -> the 4 epilogue warps (shared memory) ->
+      // ONE double atomic per (pair, moment) and image for the whole CTA.  Pairs are the finest granularity any
+      // consumer GroupNorm needs (its groups, also over a skip concat, are unions of whole pairs).
+      if (kRowsPerIter == 2) {
+        s01 += __shfl_xor_sync(0xffffffffu, s01, 16); q01 += __shfl_xor_sync(0xffffffffu, q01, 16);
+        s23 += __shfl_xor_sync(0xffffffffu, s23, 16); q23 += __shfl_xor_sync(0xffffffffu, q23, 16);
+      }
+      constexpr int nslots = BLOCK_N / 2;                 // one slot per channel PAIR of the tile
+      if (rsub == 0) {
+        red_s[ew * nslots + col / 2] = s01; red_q[ew * nslots + col / 2] = q01;
+        red_s[ew * nslots + col / 2 + 1] = s23; red_q[ew * nslots + col / 2 + 1] = q23;
+      }
+      if (lane == 0) red_b[ew] = m_first < p.M_total ? bimg : -1;
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps only
+      const int t = ew * 32 + lane;
+      if (t < nslots) {
+        const int g = n0 / 2 + t;
+        double ds = 0.0, dq = 0.0;
+        int cur = red_b[0];
+        for (int e = 0; e < 4; ++e) {
+          const int be = red_b[e];
+          if (be != cur) {
+            if (cur >= 0) {
+              double* st = p.stats + (static_cast<size_t>(cur) * p.stats_G + g) * 2;
+              atomicAdd(st, ds); atomicAdd(st + 1, dq);
+            }
+            cur = be; ds = 0.0; dq = 0.0;
+          }
+          ds += static_cast<double>(red_s[e * nslots + t]); dq += static_cast<double>(red_q[e * nslots + t]);
+        }
+        if (cur >= 0) {
+          double* st = p.stats + (static_cast<size_t>(cur) * p.stats_G + g) * 2;
+          atomicAdd(st, ds); atomicAdd(st + 1, dq);
+        }
+      }
+    }
+    if (dbg && threadIdx.x == 64) p.dbg[5] = clock64();
+  }
+  if (NSPLIT > 1) cluster_sync_all();     // nobody exits while a peer may still read its staging tile
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<BLOCK_N>(tmem_base);
@@ -763,17 +919,19 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-template <int BLOCK_N, int STAGES, int TERMS>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const CUtensorMap& tmB,
-                       const ConvParams& p, int split, cudaStream_t st) {
-  constexpr int smem = STAGES * (TERMS == 1 ? 1 : 2) * (kABytes + BLOCK_N * kBlockK * 2) + 1024 + 256;
+template <int BLOCK_N, int STAGES, int TERMS, int NSPLIT>
+static int launch_conv_n(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const CUtensorMap& tmB,
+                         const ConvParams& p, cudaStream_t st) {
+  // pipeline stages (+ alignment slack) + barriers/TMEM pointer + the per-warp GroupNorm-moment scratch
+  constexpr int smem = STAGES * (TERMS == 1 ? 1 : 2) * (kABytes + BLOCK_N * kBlockK * 2) + 1024 + 256 +
+                       2 * 4 * (BLOCK_N / 2) * 4 + 64;
   static bool attr_set = false;
   if (!attr_set) {
-    RLDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES, TERMS>,
+    RLDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES, TERMS, NSPLIT>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  dim3 grid((p.M_total + kBlockM - 1) / kBlockM, p.Cout / BLOCK_N, split);
+  dim3 grid((p.M_total + kBlockM - 1) / kBlockM, p.Cout / BLOCK_N, NSPLIT);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(192);
@@ -786,17 +944,28 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const C
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (split > 1) {   // the K splits of one tile form a thread-block cluster (DSMEM reduction in the epilogue)
+  if (NSPLIT > 1) {   // the K splits of one tile form a thread-block cluster (DSMEM reduction in the epilogue)
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = 1;
     attr[na].val.clusterDim.y = 1;
-    attr[na].val.clusterDim.z = split;
+    attr[na].val.clusterDim.z = NSPLIT;
     ++na;
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  RLDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, STAGES, TERMS>, tmA, tmAlo, tmB, p));
+  RLDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, STAGES, TERMS, NSPLIT>, tmA, tmAlo, tmB, p));
   return 0;
+}
+
+template <int BLOCK_N, int STAGES, int TERMS>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const CUtensorMap& tmB,
+                       const ConvParams& p, int split, cudaStream_t st) {
+  switch (split) {
+    case 1: return launch_conv_n<BLOCK_N, STAGES, TERMS, 1>(tmA, tmAlo, tmB, p, st);
+    case 2: return launch_conv_n<BLOCK_N, STAGES, TERMS, 2>(tmA, tmAlo, tmB, p, st);
+    case 4: return launch_conv_n<BLOCK_N, STAGES, TERMS, 4>(tmA, tmAlo, tmB, p, st);
+    default: return launch_conv_n<BLOCK_N, STAGES, TERMS, 8>(tmA, tmAlo, tmB, p, st);
+  }
 }
 
 template <int BLOCK_N, int STAGES, int TERMS>

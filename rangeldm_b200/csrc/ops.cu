@@ -921,7 +921,19 @@ extern "C" int rldm_cl_to_ref(const float* src, float* dst, int B, int C, int W,
 }
 
 // ------------------------------------------------------------------------------------------------
-extern "C" int rldm_run(const rldm_op* ops, int n_ops, void* stream) {
+namespace rldm {
+__global__ void stamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  *slot = t;
+}
+}  // namespace rldm
+
+static int run_ops(const rldm_op* ops, int n_ops, unsigned long long* stamps, void* stream) {
+  if (stamps) {
+    stamp_kernel<<<1, 1, 0, as_stream(stream)>>>(stamps);
+    RLDM_LAUNCH_CHECK();
+  }
   for (int k = 0; k < n_ops; ++k) {
     const rldm_op& o = ops[k];
     int rc = 0;
@@ -979,6 +991,17 @@ extern "C" int rldm_run(const rldm_op* ops, int n_ops, void* stream) {
         rc = 3;
     }
     if (rc) return rc;
+    if (stamps) {     // plain (non-PDL) launch: starts only when op k has completed and flushed
+      stamp_kernel<<<1, 1, 0, as_stream(stream)>>>(stamps + k + 1);
+      RLDM_LAUNCH_CHECK();
+    }
   }
   return 0;
+}
+
+extern "C" int rldm_run(const rldm_op* ops, int n_ops, void* stream) { return run_ops(ops, n_ops, nullptr, stream); }
+
+extern "C" int rldm_run_timed(const rldm_op* ops, int n_ops, unsigned long long* stamps, void* stream) {
+  RLDM_CHECK(stamps != nullptr, "rldm_run_timed: stamps must hold n_ops + 1 device uint64 slots");
+  return run_ops(ops, n_ops, stamps, stream);
 }

@@ -32,14 +32,19 @@ def run(split_mode):
         def call():
             L.call("rldm_conv_tc", L.ptr(x), L.ptr(xl) if split_mode else None, L.ptr(w), L.ptr(bias), None, 0, L.ptr(res),
                    L.ptr(out), B, W, H, Cin, Cout, ks, stride, 1 if ks == 3 else 0, 1, 0, None)
-        for _ in range(5): call()
+        for _ in range(3): call()
         torch.cuda.synchronize()
-        n = 50
+        # graph of n back-to-back launches: what the kernel costs inside a trajectory graph (no host work, PDL edges)
+        n = 20
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(n): call()
+        g.replay(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(n): call()
+        for _ in range(5): g.replay()
         e1.record(); torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) * 1e3 / n
+        us = e0.elapsed_time(e1) * 1e3 / (5 * n)
         fl = 2.0 * B * (W // stride) * (H // stride) * Cout * Cin * ks * ks
         print(f"  {name:28s} {us:8.1f} us   {fl / us / 1e6:7.1f} TFLOP/s algorithmic")
 print("split-fp16 (3 MMA terms):"); run(True)

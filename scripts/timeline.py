@@ -1,0 +1,77 @@
+"""GPU box: serialised, cache-warm per-op durations of one C3 UNet forward and one KITTI decode, measured inside a
+CUDA graph with `rldm_run_timed` (a %globaltimer stamp after every op), next to the real graphed time of the
+same program.   python scripts/timeline.py [batch] [--ops]"""
+import os, sys, json, collections
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import bench
+from rangeldm_b200 import _lib
+
+NAMES = {1: "gn_stats", 2: "prep", 3: "conv_tc", 4: "conv_in", 5: "conv_out", 6: "attention", 7: "temb",
+         8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale"}
+
+
+def describe(op):
+    i = op.i
+    if op.kind == 3:
+        return f"conv B{i[1]} {i[2]}x{i[3]} {i[4]}->{i[5]} k{i[6]} s{i[7]}" + (" +res" if op.p[4] else "")
+    if op.kind == 2:
+        return f"prep {i[6]}x{i[7]} C{i[0]}+{i[1]} up{i[4]}" + (" +raw" if op.p[7] else "")
+    if op.kind == 6:
+        return f"attention N{i[1]} C{i[2]}"
+    return NAMES.get(op.kind, str(op.kind))
+
+
+def timed_profile(prog, reps=5):
+    n = len(prog.ops)
+    stamps = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    lib = _lib.lib()
+    run = lambda: _lib.check(lib.rldm_run_timed(prog.arr, n, stamps.data_ptr(), _lib.stream_ptr()))
+    run(); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        run()
+    acc = torch.zeros(n, dtype=torch.float64)
+    for _ in range(reps):
+        g.replay(); torch.cuda.synchronize()
+        t = stamps.cpu().double()
+        acc += (t[1:] - t[:-1]) / 1e3
+    return (acc / reps).tolist()
+
+
+def graphed_ms(prog, reps=10):
+    prog.run(); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        prog.run()
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+if __name__ == "__main__":
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    B = int(args[0]) if args else 8
+    dev = torch.device("cuda:0")
+    pipe = bench.build_pipeline(dev)
+    uplan = pipe.unet.plan(B, 256, 16, 1)
+    dplan = pipe.vae.decoder_plan(B, 256, 16)
+    uplan.x_in.normal_(); uplan.t_buf.fill_(500.0); dplan.z_in.normal_()
+    for name, plan in (("unet", uplan), ("decoder", dplan)):
+        prog = plan.prog
+        us = timed_profile(prog)
+        real = graphed_ms(prog)
+        tot = collections.defaultdict(float); cnt = collections.Counter()
+        for op, u in zip(prog.ops, us):
+            k = NAMES.get(op.kind, str(op.kind)); tot[k] += u; cnt[k] += 1
+        print(f"{name}: batch {B}, {len(prog.ops)} ops; graphed {real * 1e3:.0f} us; serialised+stamped sum {sum(us):.0f} us")
+        for k, v in sorted(tot.items(), key=lambda x: -x[1]):
+            print(f"   {k:10s} n={cnt[k]:3d} total {v:8.1f} us  avg {v / cnt[k]:6.1f}")
+        if "--ops" in sys.argv:
+            for idx, (op, u) in enumerate(zip(prog.ops, us)):
+                print(f"   {idx:3d} {u:7.1f} us  {describe(op)}")
