@@ -117,29 +117,48 @@ def conv_flops(op):
     return 2.0 * B * (W // stride) * (H // stride) * Cout * Cin * ks * ks
 
 
-def per_op_profile(sampler):
-    """One pass over ONE UNet forward + the decoder, each op bracketed by CUDA events on the launch
-    stream (warm, serialised).  Returns per-kind milliseconds and the conv kernel's FLOPs."""
+def timed_profile(prog, reps=5):
+    """Per-op durations (us) of a librldm program: `rldm_run_timed` puts a one-thread %globaltimer stamp kernel after
+    every op; the stamped program is captured in a CUDA graph and replayed, so the numbers are device-side, cache-warm
+    and free of host launch overhead (each includes one ~2 us stamp-kernel launch)."""
     from rangeldm_b200 import _lib
+    n = len(prog.ops)
+    stamps = torch.zeros(n + 1, dtype=torch.int64, device=prog.device)
     lib = _lib.lib()
-    names = {1: "gn_stats", 2: "prep", 3: "conv_tc", 4: "conv_in", 5: "conv_out", 6: "attention", 7: "temb",
-             8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale"}
+    run = lambda: _lib.check(lib.rldm_run_timed(prog.arr, n, stamps.data_ptr(), _lib.stream_ptr()))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        run()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        run()
+    acc = torch.zeros(n, dtype=torch.float64)
+    for _ in range(reps):
+        g.replay()
+        torch.cuda.synchronize()
+        t = stamps.cpu().double()
+        acc += (t[1:] - t[:-1]) / 1e3
+    return (acc / reps).tolist()
+
+
+OP_NAMES = {1: "gn_stats", 2: "prep", 3: "conv_tc", 4: "conv_in", 5: "conv_out", 6: "attention", 7: "temb",
+            8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale"}
+
+
+def per_op_profile(sampler):
+    """One UNet forward + the decoder, every op timed on the device inside a CUDA graph (`timed_profile`).
+    Returns per-kind milliseconds, launch counts and the conv kernel's algorithmic FLOPs."""
+    from rangeldm_b200 import _lib
     # (profiles the first sub-batch program: with RLDM_STREAMS=2 that is half of the per-GPU batch)
-    ops = list(sampler.plan.prog.ops) + (list(sampler.dec.prog.ops) if sampler.dec is not None else [])
-    st = _lib.stream_ptr()
+    progs = [sampler.plan.prog] + ([sampler.dec.prog] if sampler.dec is not None else [])
     ms, cnt, flops = {}, {}, 0.0
-    import ctypes
-    for rep in range(2):                        # first repetition warms caches / instruction memory
-        ms, cnt, flops = {}, {}, 0.0
-        for op in ops:
-            arr = (_lib.RldmOp * 1)(op)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _lib.check(lib.rldm_run(arr, 1, st))
-            e1.record()
-            e1.synchronize()
-            k = names.get(op.kind, str(op.kind))
-            ms[k] = ms.get(k, 0.0) + e0.elapsed_time(e1)
+    for prog in progs:
+        for op, us in zip(prog.ops, timed_profile(prog)):
+            k = OP_NAMES.get(op.kind, str(op.kind))
+            ms[k] = ms.get(k, 0.0) + us / 1e3
             cnt[k] = cnt.get(k, 0) + 1
             if op.kind == _lib.OP_CONV_TC:
                 flops += conv_flops(op)
@@ -246,7 +265,7 @@ def run_native(args):
             "achieved_tflops_whole_job": round(value / world * GFLOP_PER_IMAGE / 1e3, 2),
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM circular conv)",
                          "achieved": round(achieved, 2), "peak": burst, "unit": "TFLOP/s",
-                         "frac": round(achieved / burst, 4), "peak_source": f"{src} bf16 burst (per-op timed pass)",
+                         "frac": round(achieved / burst, 4), "peak_source": f"{src} bf16 burst (kernel timed alone: device-side stamps around every launch, in-graph)",
                          "frac_of_sustained": round(achieved / sustained, 4), "traffic": None,
                          "launches": cnt.get("conv_tc", 0), "avg_launch_us": round(1e3 * conv_ms / max(cnt.get("conv_tc", 1), 1), 2),
                          "share_of_step": round(conv_ms / all_ms, 4) if all_ms else None,

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librldm.so")
+LIB_PATH = os.environ.get("RLDM_LIB") or os.path.join(_HERE, "librldm.so")   # RLDM_LIB: experiment builds
 
 c_int, c_float, c_void_p, c_i64 = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_int64
 

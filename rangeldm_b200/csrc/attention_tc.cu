@@ -1,0 +1,394 @@
+// attention_tc.cu -- softmax(Q K^T / sqrt(8)) V for heads of dimension 8 on tcgen05 tensor cores.
+//
+// Replaces F.scaled_dot_product_attention inside diffusers' AttnProcessor2_0 for the AttentionBlocks of
+// UNet2DModel (call sites `ldm/pipelines.py:239,360`): token grids are short-H x long-W
+// (1024 tokens at 128x8, 256 at 64x4), heads are only 8 wide.
+//
+// One CTA = 128 queries of one (image, head); keys are walked in tiles of 128.
+//   * S = Q K^T: head_dim 8 is padded to a K=32 contraction that carries the split-fp16 terms
+//         A row = [q_hi | q_lo | q_hi | 0],  B row = [k_hi | k_hi | k_lo | 0]   (q pre-scaled by log2(e)/sqrt(8))
+//     -> q_hi.k_hi + q_lo.k_hi + q_hi.k_lo in two tcgen05.mma (M=128, N=128, K=16) into one of three 128-column
+//     TMEM buffers.
+//   * four softmax warps (thread = query row = TMEM lane) take the key tiles one after the other: two cheap passes
+//     over the TMEM row (tcgen05.ld moves a 32-column chunk in a few dozen cycles): row max, then P = exp2(S - max)
+//     (16 K MUFU.EX2 per tile: the bound of this kernel), row sum, and P goes BACK INTO THE SAME TMEM COLUMNS as a
+//     split-fp16 pair with tcgen05.st (chunk c of 32 scores becomes 16 columns of P_hi and 16 of P_lo, two keys per
+//     32-bit column) -- P never touches shared memory.  Every key tile keeps its OWN (max, sum) and its own output
+//     slot, so there is no running rescale.
+//   * O_j = P_hi [V_hi | V_lo] + P_lo [V_hi | V_lo]: the A operand comes from TMEM, the B operand (V^T, hi and lo
+//     halves side by side: N = 16) from shared memory; 16 tcgen05.mma (M=128, N=16, K=16) per key tile -> TMEM slot j.
+//   * the tail combines the tiles: O = sum_j 2^(m_j - m) (O_j[:8] + O_j[8:]) / sum_j 2^(m_j - m) l_j and writes the
+//     split-fp16 operand of the to_out projection (W-padded layout of rldm_conv_tc).
+// Inside one CTA the chain Q K^T -> softmax -> P V is serial (one S/P buffer); TWO CTAs share an SM (256 threads,
+// <= 128 registers, ~85 KB shared memory, 256 TMEM columns each), so one CTA's exponentials overlap the other's MMAs,
+// loads, prologue and tail.
+// Warp roles: 0-3 softmax, 4 MMA issuer + TMEM owner, 5-7 loaders (fp32 q/k/v -> split fp16 -> SWIZZLE_128B shared
+// memory; loader w owns ring slot w and the tiles t = w mod 3).
+// TMEM: columns [0,128) = S/P buffer, [128,256) = eight 16-column output slots (N <= 1024).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace rldm {
+
+constexpr int kAtThreads = 8 * 32;
+constexpr int kAtTile = 128;                    // queries per CTA and keys per tile
+constexpr int kAtRing = 3;                      // K ring and V ring
+constexpr int kAtQBytes = kAtTile * 128;        // 16 KB: 128 rows x 128 B (first 64 B of a row used)
+constexpr int kAtKBytes = kAtTile * 128;        // 16 KB
+constexpr int kAtVAtom = 16 * 128;              // 2 KB: 16 rows (8 v_hi, 8 v_lo) x 64 keys
+constexpr int kAtVBytes = 2 * kAtVAtom;         // 2 K-atoms of 64 keys
+constexpr int kAtMaxTiles = 8;                  // N <= 1024
+constexpr int kAtSlot0 = 128;                   // first output-slot column
+constexpr int kAtTmemCols = 256;
+constexpr int kAtSlot = 16;                     // TMEM columns per output slot
+
+__device__ __forceinline__ uint32_t at_pack(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ void at_split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x, y);
+  const float2 hf = __half22float2(h);
+  hi = at_pack(h);
+  lo = at_pack(__floats2half2_rn(x - hf.x, y - hf.y));
+}
+__device__ __forceinline__ float at_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void at_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void at_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void at_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void at_sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: A is M x 16 fp16, two K-elements per 32-bit TMEM column (8 columns)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct AttnSmem {
+  uint64_t q_full;
+  uint64_t k_full[kAtRing], k_empty[kAtRing], v_full[kAtRing], v_empty[kAtRing];
+  uint64_t s_full, p_full;
+  uint64_t all_done;
+  uint32_t tmem_ptr;
+  uint32_t pad;
+};
+
+// max of the 32 scores of one TMEM chunk
+__device__ __forceinline__ float at_max32(const uint32_t (&r)[32]) {
+  float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
+#pragma unroll
+  for (int e = 4; e < 32; e += 4) {
+    m0 = fmaxf(m0, __uint_as_float(r[e])); m1 = fmaxf(m1, __uint_as_float(r[e + 1]));
+    m2 = fmaxf(m2, __uint_as_float(r[e + 2])); m3 = fmaxf(m3, __uint_as_float(r[e + 3]));
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+// P = 2^(S - m) for the 32 keys of one chunk as split fp16, written over the chunk's own 32 columns:
+// 16 columns of P_hi followed by 16 columns of P_lo; returns the sum of the 32 probabilities
+__device__ __forceinline__ float at_exp_store32(const uint32_t (&r)[32], float m, uint32_t t_chunk) {
+  uint32_t h[16], lo[16];
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const float pa = at_ex2(__uint_as_float(r[2 * e]) - m);
+    const float pb = at_ex2(__uint_as_float(r[2 * e + 1]) - m);
+    l0 += pa; l1 += pb;
+    at_split2(pa, pb, h[e], lo[e]);
+  }
+  tmem_st_32x16(t_chunk, h);
+  tmem_st_32x16(t_chunk + 16, lo);
+  return l0 + l1;
+}
+
+__global__ void __launch_bounds__(kAtThreads, 2)
+attention_umma_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half* __restrict__ out_lo, int N, int C,
+                      int H, long long* dbg) {
+  // profiling aid (normally NULL): clock64 stamps of CTA (0,0,0): [0..31] loader 0, [32..63] MMA, [64..127] softmax
+  if (dbg != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) != 0) dbg = nullptr;
+#define AT_STAMP(idx) do { if (dbg) dbg[idx] = clock64(); } while (0)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kAtQBytes;                           // [3][16 KB]
+  uint8_t* sV = sK + kAtRing * kAtKBytes;                 // [3][4 KB]
+  float2* sML = reinterpret_cast<float2*>(sV + kAtRing * kAtVBytes);     // [tiles][128] (row max, row sum) per key tile
+  const int T = N / kAtTile;
+  AttnSmem* sb = reinterpret_cast<AttnSmem*>(reinterpret_cast<uint8_t*>(sML) + static_cast<size_t>(T) * kAtTile * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, hd = blockIdx.y, q0 = blockIdx.x * kAtTile;
+  const size_t rowf = 3 * static_cast<size_t>(C);
+  const float* base = qkv + static_cast<size_t>(b) * N * rowf + hd * 8;
+
+  pdl_trigger();
+  if (threadIdx.x == 0) AT_STAMP(127);
+  if (threadIdx.x == 0) {
+    mbar_init(&sb->q_full, 96);
+    for (int i = 0; i < kAtRing; ++i) {
+      mbar_init(&sb->k_full[i], 32); mbar_init(&sb->k_empty[i], 1);
+      mbar_init(&sb->v_full[i], 32); mbar_init(&sb->v_empty[i], 1);
+    }
+    mbar_init(&sb->s_full, 1); mbar_init(&sb->p_full, 128);
+    mbar_init(&sb->all_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc<kAtTmemCols>(&sb->tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, sb->tmem_ptr, 0);   // shfl: warp-uniform for the compiler
+  pdl_wait();
+  if (threadIdx.x == 0) AT_STAMP(124);
+
+  if (warp >= 5) {
+    // ===================== loaders ==============================================================
+    const int w = warp - 5;                                // ring slot and tile residue of this warp
+    // first tile's K/V and this thread's Q rows: all loads in flight before anything is stored
+    float4 qa[2], qb[2];
+    const int qt = threadIdx.x - 5 * 32;                   // 0..95: Q rows qt and qt + 96
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int i = qt + rr * 96;
+      if (i < kAtTile) {
+        const float* qp = base + static_cast<size_t>(q0 + i) * rowf;
+        qa[rr] = __ldg(reinterpret_cast<const float4*>(qp)); qb[rr] = __ldg(reinterpret_cast<const float4*>(qp) + 1);
+      }
+    }
+    if (lane == 0 && w == 0) AT_STAMP(0);
+    // K: lane <-> rows lane + 32 rr;  V: lane <-> keys 4 lane .. 4 lane + 3.  The next tile is always in registers.
+    float4 ka[4], kb[4], va[4], vb[4];
+    auto load_tile = [&](int t) {
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const float* kp = base + static_cast<size_t>(t * kAtTile + lane + rr * 32) * rowf + C;
+        ka[rr] = __ldg(reinterpret_cast<const float4*>(kp)); kb[rr] = __ldg(reinterpret_cast<const float4*>(kp) + 1);
+        const float* vp = base + static_cast<size_t>(t * kAtTile + 4 * lane + rr) * rowf + 2 * C;
+        va[rr] = __ldg(reinterpret_cast<const float4*>(vp)); vb[rr] = __ldg(reinterpret_cast<const float4*>(vp) + 1);
+      }
+    };
+    if (w < T) load_tile(w);
+    {
+      // Q rows: [q_hi | q_lo | q_hi | 0], softmax scale 1/sqrt(8) and log2(e) folded in
+      const float qs = 0.35355339059327373f * 1.4426950408889634f;
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int i = qt + rr * 96, sw = i & 7;
+        if (i < kAtTile) {
+          uint32_t h[4], l[4];
+          at_split2(qa[rr].x * qs, qa[rr].y * qs, h[0], l[0]); at_split2(qa[rr].z * qs, qa[rr].w * qs, h[1], l[1]);
+          at_split2(qb[rr].x * qs, qb[rr].y * qs, h[2], l[2]); at_split2(qb[rr].z * qs, qb[rr].w * qs, h[3], l[3]);
+          const uint32_t r = smem_u32(sQ) + i * 128;
+          at_sts128(r + ((0 ^ sw) << 4), h[0], h[1], h[2], h[3]);
+          at_sts128(r + ((1 ^ sw) << 4), l[0], l[1], l[2], l[3]);
+          at_sts128(r + ((2 ^ sw) << 4), h[0], h[1], h[2], h[3]);
+          at_sts128(r + ((3 ^ sw) << 4), 0u, 0u, 0u, 0u);
+        }
+      }
+      at_fence_async();
+      at_arrive(&sb->q_full);
+    }
+    for (int t = w; t < T; t += kAtRing) {
+      const uint32_t ph = ((t / kAtRing) & 1) ^ 1;
+      mbar_wait(&sb->k_empty[w], ph);
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int i = lane + rr * 32, sw = i & 7;
+        uint32_t h[4], l[4];
+        at_split2(ka[rr].x, ka[rr].y, h[0], l[0]); at_split2(ka[rr].z, ka[rr].w, h[1], l[1]);
+        at_split2(kb[rr].x, kb[rr].y, h[2], l[2]); at_split2(kb[rr].z, kb[rr].w, h[3], l[3]);
+        const uint32_t kr = smem_u32(sK + w * kAtKBytes) + i * 128;       // K row: [k_hi | k_hi | k_lo | 0]
+        at_sts128(kr + ((0 ^ sw) << 4), h[0], h[1], h[2], h[3]);
+        at_sts128(kr + ((1 ^ sw) << 4), h[0], h[1], h[2], h[3]);
+        at_sts128(kr + ((2 ^ sw) << 4), l[0], l[1], l[2], l[3]);
+        at_sts128(kr + ((3 ^ sw) << 4), 0u, 0u, 0u, 0u);
+      }
+      at_fence_async();
+      at_arrive(&sb->k_full[w]);
+      mbar_wait(&sb->v_empty[w], ph);
+      {
+        // V^T: row n = d (hi) / 8 + d (lo); this lane's 4 keys are half a 16 B chunk: atom = lane / 16,
+        // chunk = (lane % 16) / 2, byte offset 8 (lane % 2) inside the chunk
+        const uint32_t vbase = smem_u32(sV + w * kAtVBytes) + (lane >> 4) * kAtVAtom + ((lane & 1) << 3);
+        const int chunk = (lane & 15) >> 1;
+        const float v0[8] = {va[0].x, va[0].y, va[0].z, va[0].w, vb[0].x, vb[0].y, vb[0].z, vb[0].w};
+        const float v1[8] = {va[1].x, va[1].y, va[1].z, va[1].w, vb[1].x, vb[1].y, vb[1].z, vb[1].w};
+        const float v2[8] = {va[2].x, va[2].y, va[2].z, va[2].w, vb[2].x, vb[2].y, vb[2].z, vb[2].w};
+        const float v3[8] = {va[3].x, va[3].y, va[3].z, va[3].w, vb[3].x, vb[3].y, vb[3].z, vb[3].w};
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          uint32_t h01, l01, h23, l23;
+          at_split2(v0[d], v1[d], h01, l01);
+          at_split2(v2[d], v3[d], h23, l23);
+          const uint32_t off = static_cast<uint32_t>((chunk ^ d) << 4);   // rows d and 8 + d: (row & 7) == d
+          at_sts64(vbase + d * 128 + off, h01, h23);
+          at_sts64(vbase + (8 + d) * 128 + off, l01, l23);
+        }
+      }
+      at_fence_async();
+      at_arrive(&sb->v_full[w]);
+      if (lane == 0 && w == 0 && t / kAtRing < 8) AT_STAMP(1 + t / kAtRing);
+      if (t + kAtRing < T) load_tile(t + kAtRing);
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer ===========================================================
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, 128);
+      constexpr uint32_t idesc_o = umma_idesc_f16(128, kAtSlot);
+      const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ));
+      auto issue_qk = [&](int j) {                         // after PV(j-1) in program order: MMAs execute in order
+        const int s = j % kAtRing;
+        mbar_wait(&sb->k_full[s], (j / kAtRing) & 1);
+        tc_fence_after();
+        const uint64_t k_desc = umma_desc_sw128(smem_u32(sK + s * kAtKBytes));
+        umma_f16(tmem, q_desc, k_desc, idesc_s, 0u);
+        umma_f16(tmem, q_desc + 2, k_desc + 2, idesc_s, 1u);
+        umma_commit(&sb->s_full);
+        umma_commit(&sb->k_empty[s]);
+        if (j < 15) AT_STAMP(32 + j);
+      };
+      mbar_wait(&sb->q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < T; ++j) {
+        const int s = j % kAtRing;
+        mbar_wait(&sb->v_full[s], (j / kAtRing) & 1);
+        mbar_wait(&sb->p_full, j & 1);
+        tc_fence_after();
+        const uint32_t d = tmem + kAtSlot0 + kAtSlot * j;
+        const uint32_t v_addr = smem_u32(sV + s * kAtVBytes);
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {                 // K step = 16 keys = 8 columns of chunk ks / 2
+            const uint64_t v_desc = umma_desc_sw128(v_addr + (ks >> 2) * kAtVAtom) + 2 * (ks & 3);
+            umma_f16_ts(d, tmem + (ks >> 1) * 32 + part * 16 + (ks & 1) * 8, v_desc, idesc_o, (part | ks) != 0);
+          }
+        }
+        umma_commit(&sb->v_empty[s]);
+        if (j < 15) AT_STAMP(48 + j);
+        if (j + 1 < T) issue_qk(j + 1);
+      }
+      umma_commit(&sb->all_done);
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax warps ========================================================
+    const int row = warp * 32 + lane;                      // query row == TMEM lane
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(&sb->s_full, j & 1);
+      tc_fence_after();
+      if (threadIdx.x == 0 && j < 16) AT_STAMP(64 + 4 * j);
+      float m = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {                        // pass 1: row maximum
+        uint32_t r[32];
+        tmem_ld_32x32(t_lane + c * 32, r);
+        tmem_ld_wait();
+        m = fmaxf(m, at_max32(r));
+      }
+      if (threadIdx.x == 0 && j < 16) AT_STAMP(65 + 4 * j);
+      float l = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {                        // pass 2: exponentials, P written in place
+        uint32_t r[32];
+        tmem_ld_32x32(t_lane + c * 32, r);
+        tmem_ld_wait();
+        l += at_exp_store32(r, m, t_lane + c * 32);
+      }
+      sML[j * kAtTile + row] = make_float2(m, l);
+      tmem_st_wait();
+      tc_fence_before();
+      at_arrive(&sb->p_full);
+      if (threadIdx.x == 0 && j < 16) AT_STAMP(67 + 4 * j);
+    }
+    // ===================== combine the key tiles, normalise, write the operand ==================
+    mbar_wait(&sb->all_done, 0);
+    tc_fence_after();
+    if (threadIdx.x == 0) AT_STAMP(125);
+    float m = -INFINITY;
+    for (int j = 0; j < T; ++j) m = fmaxf(m, sML[j * kAtTile + row].x);
+    float L = 0.f;
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < T; ++j) {
+      const float2 ml = sML[j * kAtTile + row];
+      const float wgt = at_ex2(ml.x - m);
+      L = fmaf(wgt, ml.y, L);
+      uint32_t r[16];
+      tmem_ld_32x16(t_lane + kAtSlot0 + kAtSlot * j, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int d = 0; d < 8; ++d) o[d] = fmaf(wgt, __uint_as_float(r[d]) + __uint_as_float(r[8 + d]), o[d]);
+    }
+    const float inv = 1.0f / L;
+    uint32_t h[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) at_split2(o[2 * e] * inv, o[2 * e + 1] * inv, h[e], lo[e]);
+    // W-padded operand layout (B, W+2, H, C): token n lands at padded pixel H + n
+    const size_t oi = (static_cast<size_t>(b) * (N + 2 * H) + H + q0 + row) * C + hd * 8;
+    *reinterpret_cast<uint4*>(out + oi) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (out_lo) *reinterpret_cast<uint4*>(out_lo + oi) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    if (threadIdx.x == 0) AT_STAMP(126);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<kAtTmemCols>(tmem);
+}
+
+}  // namespace rldm
+
+using namespace rldm;
+
+static long long* g_attn_dbg = nullptr;
+extern "C" void rldm_debug_attn_timestamps(long long* dev_buf) { g_attn_dbg = dev_buf; }
+
+// Host entry used by rldm_attention (ops.cu).  Returns -1 when the shape is outside this kernel's range (the caller
+// then takes the mma.sync / CUDA-core kernels), 0 on success, > 0 on error.
+int rldm_attention_umma(const float* qkv, uint16_t* out, uint16_t* out_lo, int B, int N, int C, int H, void* stream) {
+  // Short sequences (N < 512: two key tiles or fewer) are dominated by the per-CTA prologue and tail; the mma.sync
+  // kernel is faster there (16.6 us vs 19.4 us for N = 256, C = 256, B = 8 on B200).  RLDM_ATTN_TCGEN05=1 forces this one.
+  if (N % kAtTile != 0 || N / kAtTile > kAtMaxTiles || C % 8 != 0) return -1;
+  if (N < 4 * kAtTile && !getenv("RLDM_ATTN_TCGEN05")) return -1;
+  const int T = N / kAtTile;
+  const size_t smem = 1024 + kAtQBytes + kAtRing * (kAtKBytes + kAtVBytes) + static_cast<size_t>(T) * kAtTile * 8 +
+                      sizeof(AttnSmem);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    RLDM_CUDA(cudaFuncSetAttribute(attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+    attr_smem = smem;
+  }
+  RLDM_CUDA(launch_pdl(attention_umma_kernel, dim3(N / kAtTile, C / 8, B), dim3(kAtThreads), smem, as_stream(stream), qkv,
+                       reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H, g_attn_dbg));
+  RLDM_LAUNCH_CHECK();
+  return 0;
+}

@@ -259,7 +259,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
-  pdl_trigger();     // let the next kernel's CTAs launch and run their prologue while this grid drains
+  pdl_trigger_conv_early();     // let the next kernel's CTAs launch and run their prologue while this grid drains
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     if (TERMS > 1) tma_prefetch_desc(&tmAlo);
@@ -275,7 +275,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);   // shfl: tells the compiler it is warp-uniform (UR, no per-MMA R2UR loop)
   // Weights never depend on the previous kernel: the producer arms the first STAGES barriers and starts their
   // weight tiles BEFORE griddepcontrol.wait, so they land while the previous grid is still draining.
   if (warp == 0 && lane == 0) {
@@ -341,7 +341,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) ============================================
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: ptxas knows exactly one lane is active (no per-MMA waterfall loop)
       constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BLOCK_N);
       for (int i = 0; i < n_it; ++i) {
         const int s = i % STAGES;
@@ -407,6 +407,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (dbg && threadIdx.x == 64) p.dbg[6] = clock64();
   }
+  pdl_trigger_conv_late();      // mainloop issued / accumulator staged: dependents may start their prologue
   // ======================= (cluster) reduce + stats + store =====================================================
   // split-K: the NSPLIT CTAs of a cluster (same tile, different K slices) each staged a partial tile; CTA `rank`
   // owns rows [rank*128/NSPLIT, ...) and sums them over all ranks through distributed shared memory in a fixed
@@ -553,7 +554,7 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   const int taps = p.ks * p.ks;
   const int n_it = p.total_iters;
 
-  pdl_trigger();
+  pdl_trigger_conv_early();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     if (TERMS > 1) tma_prefetch_desc(&tmAlo);
@@ -572,13 +573,14 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);   // shfl: tells the compiler it is warp-uniform (UR, no per-MMA R2UR loop)
   pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer: one continuous stage ring across tiles =================
     int g = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      if (t + static_cast<int>(gridDim.x) >= total_tiles) pdl_trigger_conv_late();
       const int tm = t / tiles_n, tn = t - tm * tiles_n;
       const int m0 = tm * kBlockM, n0 = tn * BLOCK_N;
       const int q0 = m0 / p.Ho;
@@ -606,10 +608,11 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: alternates between the two TMEM accumulators ==============
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BLOCK_N);
       int g = 0, k = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
+        if (t + static_cast<int>(gridDim.x) >= total_tiles) pdl_trigger_conv_late();
         const int acc = k & 1;
         mbar_wait(&tmem_empty[acc], ((k >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
         tc_fence_after();
@@ -651,6 +654,7 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       const int tm = t / tiles_n, tn = t - tm * tiles_n;
       const int m0 = tm * kBlockM, n0 = tn * BLOCK_N;
       mbar_wait(&tmem_full[acc], (k >> 1) & 1);
+      if (t + static_cast<int>(gridDim.x) >= total_tiles) pdl_trigger_conv_late();
       tc_fence_after();
       const int m_first = m0 + ew * 32;
       const int bimg = min(m_first, p.M_total - 1) / p.pix_per_img;   // a warp's 32 rows lie in one image
@@ -813,7 +817,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);   // shfl: tells the compiler it is warp-uniform (UR, no per-MMA R2UR loop)
   pdl_wait();
 
   if (warp == 0) {
@@ -848,7 +852,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer ===========================================================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BLOCK_N);
       int bi = 0;
       for (int ui = 0; ui < n_units; ++ui) {

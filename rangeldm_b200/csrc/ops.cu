@@ -18,7 +18,9 @@ void set_error(const char* fmt, ...) {
 }
 bool pdl_enabled() {
   static int v = -1;
-  if (v < 0) v = getenv("RLDM_NO_PDL") ? 0 : 1;
+  // Measured on B200 inside the trajectory graph (scripts/timeline.py): programmatic edges make the C3 UNet 3 % and
+  // the KITTI decoder 8 % SLOWER than plain edges, wherever launch_dependents is fired, so PDL is opt-in.
+  if (v < 0) v = getenv("RLDM_PDL") ? 1 : 0;
   return v == 1;
 }
 
@@ -865,9 +867,15 @@ extern "C" int rldm_conv_out(const uint16_t* x, const uint16_t* x_lo, const floa
   return 0;
 }
 
+int rldm_attention_umma(const float* qkv, uint16_t* out, uint16_t* out_lo, int B, int N, int C, int H, void* stream);
+
 extern "C" int rldm_attention(const float* qkv, uint16_t* out, uint16_t* out_lo, int B, int N, int C,
                               int H, void* stream) {
   RLDM_CHECK(C % 8 == 0, "attention: C %% 8 != 0");
+  if (!getenv("RLDM_ATTN_MMASYNC") && !getenv("RLDM_ATTN_CUDACORE")) {   // tcgen05 kernel: N a multiple of 128, <= 2048
+    const int rc = rldm_attention_umma(qkv, out, out_lo, B, N, C, H, stream);
+    if (rc >= 0) return rc;
+  }
   if (N % 64 == 0 && !getenv("RLDM_ATTN_CUDACORE")) {   // tensor-path kernel; the CUDA-core kernel covers ragged N
     RLDM_CUDA(launch_pdl(attention_tc_kernel, dim3(N / 64, C / 8, B), dim3(128), 0, as_stream(stream), qkv, reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H));
     RLDM_LAUNCH_CHECK();

@@ -23,21 +23,7 @@ def describe(op):
     return NAMES.get(op.kind, str(op.kind))
 
 
-def timed_profile(prog, reps=5):
-    n = len(prog.ops)
-    stamps = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
-    lib = _lib.lib()
-    run = lambda: _lib.check(lib.rldm_run_timed(prog.arr, n, stamps.data_ptr(), _lib.stream_ptr()))
-    run(); torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        run()
-    acc = torch.zeros(n, dtype=torch.float64)
-    for _ in range(reps):
-        g.replay(); torch.cuda.synchronize()
-        t = stamps.cpu().double()
-        acc += (t[1:] - t[:-1]) / 1e3
-    return (acc / reps).tolist()
+timed_profile = bench.timed_profile
 
 
 def graphed_ms(prog, reps=10):

@@ -218,12 +218,21 @@ def test_gn_stats_and_prep(L, shape):
         assert relerr(ref_layout(unpadw(out.float() + out_lo.float()).cpu()), y) < 5e-6
 
 
-@pytest.mark.parametrize("cuda_core", [False, True], ids=["mma", "cudacore"])
-@pytest.mark.parametrize("shape", [(2, 64, 64), (1, 256, 128), (2, 1024, 128), (1, 40, 64), (1, 320, 64)])
-def test_attention_core(L, shape, cuda_core, monkeypatch):
+@pytest.mark.parametrize("kernel", ["tcgen05", "mma", "cudacore"])
+@pytest.mark.parametrize("shape", [(2, 64, 64), (1, 256, 128), (2, 1024, 128), (1, 40, 64), (1, 320, 64), (3, 128, 64),
+                                   (1, 1024, 16), (1, 512, 256)])
+def test_attention_core(L, shape, kernel, monkeypatch):
+    """tcgen05 kernel (N a multiple of 128, <= 1024; other shapes fall through to the mma.sync kernel), the
+    mma.sync kernel (N % 64 == 0) and the CUDA-core kernel (ragged N), each forced where it applies."""
     B, N, C = shape
-    if cuda_core:
+    if kernel == "tcgen05":
+        monkeypatch.setenv("RLDM_ATTN_TCGEN05", "1")      # also for N < 512, where the dispatcher prefers mma.sync
+    elif kernel == "cudacore":
         monkeypatch.setenv("RLDM_ATTN_CUDACORE", "1")     # the ragged-N kernel, forced for every shape
+    if kernel == "mma":
+        monkeypatch.setenv("RLDM_ATTN_MMASYNC", "1")
+    if kernel != "tcgen05" and N > 1024:
+        pytest.skip("large N only exercised on the tcgen05 kernel")
     g = torch.Generator().manual_seed(N)
     qkv = torch.randn(B, N, 3 * C, generator=g)
     Hh = 8                                                 # tokens are (w, h) with H = 8; output is W-padded
