@@ -93,6 +93,17 @@ int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, c
                  int Cout, int ks, int stride, int pad_lo, int circular, int split_k, double* stats,
                  void* stream);
 
+/* rldm_conv_tc with ResnetBlock2D's 1x1 `conv_shortcut` (`model.py:356-360`; diffusers ResnetBlock2D) folded into
+ * the K loop: out = conv(x; wgt) + conv1x1(sc_x; sc_wgt) + bias [+ temb] [+ residual].  sc_x (+ sc_x_lo):
+ * (B, W+2, H, sc_cin) fp16 clp on the same grid as the output (stride must be 1), sc_wgt: [planes][Cout][sc_cin]
+ * fp16; `bias` must already hold conv.bias + conv_shortcut.bias.  Saves one launch and the fp32 round trip of the
+ * shortcut branch per block. */
+int rldm_conv_tc_shortcut(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias,
+                          const float* temb, int temb_stride, const float* residual, float* out, int B, int W, int H,
+                          int Cin, int Cout, int ks, int stride, int pad_lo, int circular, int split_k, double* stats,
+                          const uint16_t* sc_x, const uint16_t* sc_x_lo, const uint16_t* sc_wgt, int sc_cin,
+                          void* stream);
+
 /* CUDA-core restatement of rldm_conv_tc with the identical contract (split_k ignored); used by the
  * GPU tests to isolate tensor-core descriptor bugs from precision, never by the product path. */
 int rldm_conv_ref(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias, const float* temb,

@@ -31,6 +31,8 @@ SIGNATURES = {
                           c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rldm_conv_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
                      + [c_int] * 10 + [c_void_p, c_void_p]),
+    "rldm_conv_tc_shortcut": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+                              + [c_int] * 10 + [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "rldm_conv_ref": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
                       + [c_int] * 9 + [c_void_p]),
     "rldm_conv_in": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 5

@@ -39,7 +39,8 @@ struct ConvParams {
   int pix_per_img;  // Wo*Ho
   int Cout;
   int ks, stride, pad_lo, circular;
-  int total_iters;  // (Cin/64) * ks*ks
+  int total_iters;  // main_iters + shortcut chunks
+  int main_iters;   // (Cin/64) * ks*ks: K steps of the convolution proper; the rest are the fused 1x1 shortcut's
   double* stats;    // optional GroupNorm moments of the output: [B][stats_G][2]
   int stats_cpg, stats_G;
   // halo-reuse 3x3 kernel only
@@ -47,6 +48,13 @@ struct ConvParams {
   int nb_stages;    // depth of the weight (B) ring
   int units;        // (Cin/64) * 3 : one unit = (channel chunk, kernel column tj) = 3 taps
   long long* dbg;   // optional: 8 clock64 timestamps written by CTA (0,0,0) (profiling aid, normally NULL)
+};
+
+// Tensor maps of one launch.  a/alo/b: activation (hi, lo) and weights of the convolution.  a2/a2lo/b2: operand and
+// weights of an optional 1x1 convolution over a second tensor with the same spatial grid whose product is
+// accumulated into the same tile (ResnetBlock2D's conv_shortcut folded into conv2's K loop).
+struct ConvMaps {
+  CUtensorMap a, alo, b, a2, a2lo, b2;
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
@@ -222,8 +230,7 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, uint32_t tmem_acc, 
 // deterministic), instead of one dependent load at a time.
 template <int BLOCK_N, int STAGES, int TERMS, int NSPLIT>
 __global__ void __launch_bounds__(192, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
-               const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   constexpr int kParts = TERMS == 1 ? 1 : 2;
   constexpr int kStageBytes = kParts * (kABytes + kBBytes);   // [A_hi][A_lo][B_hi][B_lo]
@@ -261,9 +268,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
   pdl_trigger_conv_early();     // let the next kernel's CTAs launch and run their prologue while this grid drains
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    if (TERMS > 1) tma_prefetch_desc(&tmAlo);
-    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tm.a);
+    if (TERMS > 1) tma_prefetch_desc(&tm.alo);
+    tma_prefetch_desc(&tm.b);
+    if (p.total_iters > p.main_iters) {
+      tma_prefetch_desc(&tm.a2);
+      if (TERMS > 1) tma_prefetch_desc(&tm.a2lo);
+      tma_prefetch_desc(&tm.b2);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -278,17 +290,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);   // shfl: tells the compiler it is warp-uniform (UR, no per-MMA R2UR loop)
   // Weights never depend on the previous kernel: the producer arms the first STAGES barriers and starts their
   // weight tiles BEFORE griddepcontrol.wait, so they land while the previous grid is still draining.
-  if (warp == 0 && lane == 0) {
+  // weight tiles of K step `it` (hi plane, then lo plane: rows [taps*Cout, 2*taps*Cout) of the packed tensor)
+  auto load_weights = [&](int it, uint32_t b_dst, uint64_t* bar) {
     const int taps = p.ks * p.ks;
-    for (int i = 0; i < n_it && i < STAGES; ++i) {
-      const int it = it0 + i;
+    if (it < p.main_iters) {
       const int chunk = it / taps;
       const int tap = it - chunk * taps;
-      const uint32_t a_dst = smem_u32(smem + i * kStageBytes);
+      tma_load_2d(b_dst, &tm.b, bar, chunk * kBlockK, tap * p.Cout + n0);
+      if (TERMS > 1) tma_load_2d(b_dst + kBBytes, &tm.b, bar, chunk * kBlockK, (taps + tap) * p.Cout + n0);
+    } else {
+      const int chunk = it - p.main_iters;
+      tma_load_2d(b_dst, &tm.b2, bar, chunk * kBlockK, n0);
+      if (TERMS > 1) tma_load_2d(b_dst + kBBytes, &tm.b2, bar, chunk * kBlockK, p.Cout + n0);
+    }
+  };
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < n_it && i < STAGES; ++i) {
       mbar_arrive_expect_tx(&full_bar[i], kStageBytes);
-      tma_load_2d(a_dst + kBOff, &tmB, &full_bar[i], chunk * kBlockK, tap * p.Cout + n0);
-      if (TERMS > 1)
-        tma_load_2d(a_dst + kBOff + kBBytes, &tmB, &full_bar[i], chunk * kBlockK, (taps + tap) * p.Cout + n0);
+      load_weights(it0 + i, smem_u32(smem + i * kStageBytes) + kBOff, &full_bar[i]);
     }
   }
   pdl_wait();        // everything above overlapped the previous kernel; below we touch its outputs
@@ -316,27 +335,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t ph = (i / STAGES) & 1;
       mbar_wait(&empty_bar[s], ph ^ 1);
       const int it = it0 + i;
-      const int chunk = it / taps;
+      const bool main = it < p.main_iters;
+      const int chunk = main ? it / taps : it - p.main_iters;
       const int tap = it - chunk * taps;
       const int ti = tap / p.ks, tj = tap - ti * p.ks;
       const uint32_t a_dst = smem_u32(smem + s * kStageBytes);
       if (lane == 0 && i >= STAGES) {   // (the first STAGES weight tiles were issued before griddepcontrol.wait)
         mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-        tma_load_2d(a_dst + kBOff, &tmB, &full_bar[s], chunk * kBlockK, tap * p.Cout + n0);
-        if (TERMS > 1)   // low-order weight plane follows the high-order one: rows [taps*Cout, 2*taps*Cout)
-          tma_load_2d(a_dst + kBOff + kBBytes, &tmB, &full_bar[s], chunk * kBlockK,
-                      (taps + tap) * p.Cout + n0);
+        load_weights(it, a_dst + kBOff, &full_bar[s]);
       }
-      if (lane == (TERMS == 1 ? 0 : 1)) {
-        // ONE box per operand part: the activation tensor is W-padded (halo columns hold the circular wrap,
-        // written by rldm_prep), H zero padding is TMA out-of-bounds fill, stride 2 is the map's element stride.
-        const int w_in = p.stride * wo0 + ti - p.pad_lo + 1;
-        tma_load_4d(a_dst, &tmA, &full_bar[s], chunk * kBlockK, tj - p.pad_lo, w_in, b0);
-      }
-      if (TERMS > 1 && lane == 2) {
-        const int w_in = p.stride * wo0 + ti - p.pad_lo + 1;
-        tma_load_4d(a_dst + kABytes, &tmAlo, &full_bar[s], chunk * kBlockK, tj - p.pad_lo, w_in, b0);
-      }
+      // ONE box per operand part: the activation tensor is W-padded (halo columns hold the circular wrap,
+      // written by rldm_prep), H zero padding is TMA out-of-bounds fill, stride 2 is the map's element stride.
+      // Shortcut K steps read the centre tap of the second tensor (1x1, stride 1, same grid as the output).
+      const int h_in = main ? tj - p.pad_lo : 0;
+      const int w_in = main ? p.stride * wo0 + ti - p.pad_lo + 1 : wo0 + 1;
+      if (lane == (TERMS == 1 ? 0 : 1)) tma_load_4d(a_dst, main ? &tm.a : &tm.a2, &full_bar[s], chunk * kBlockK, h_in, w_in, b0);
+      if (TERMS > 1 && lane == 2)
+        tma_load_4d(a_dst + kABytes, main ? &tm.alo : &tm.a2lo, &full_bar[s], chunk * kBlockK, h_in, w_in, b0);
       __syncwarp();
     }
   } else if (warp == 1) {
@@ -524,8 +539,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // epilogue (not aliased with the pipeline stages).
 template <int BLOCK_N, int STAGES, int TERMS>
 __global__ void __launch_bounds__(192, 1)
-conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
-                          const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   constexpr int kParts = TERMS == 1 ? 1 : 2;
   constexpr int kStageBytes = kParts * (kABytes + kBBytes);
@@ -556,9 +570,14 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 
   pdl_trigger_conv_early();
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    if (TERMS > 1) tma_prefetch_desc(&tmAlo);
-    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tm.a);
+    if (TERMS > 1) tma_prefetch_desc(&tm.alo);
+    tma_prefetch_desc(&tm.b);
+    if (p.total_iters > p.main_iters) {
+      tma_prefetch_desc(&tm.a2);
+      if (TERMS > 1) tma_prefetch_desc(&tm.a2lo);
+      tma_prefetch_desc(&tm.b2);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -581,28 +600,36 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     int g = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       if (t + static_cast<int>(gridDim.x) >= total_tiles) pdl_trigger_conv_late();
-      const int tm = t / tiles_n, tn = t - tm * tiles_n;
-      const int m0 = tm * kBlockM, n0 = tn * BLOCK_N;
+      const int tmi = t / tiles_n, tn = t - tmi * tiles_n;
+      const int m0 = tmi * kBlockM, n0 = tn * BLOCK_N;
       const int q0 = m0 / p.Ho;
       const int b0 = q0 / p.Wo;
       const int wo0 = q0 - b0 * p.Wo;
       for (int it = 0; it < n_it; ++it, ++g) {
         const int s = g % STAGES;
         mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
-        const int chunk = it / taps;
+        const bool main = it < p.main_iters;
+        const int chunk = main ? it / taps : it - p.main_iters;
         const int tap = it - chunk * taps;
         const int ti = tap / p.ks, tj = tap - ti * p.ks;
         const uint32_t a_dst = smem_u32(smem + s * kStageBytes);
-        const int w_in = p.stride * wo0 + ti - p.pad_lo + 1;
+        // shortcut K steps: centre tap of the second tensor (1x1, stride 1, same grid as the output)
+        const int h_in = main ? tj - p.pad_lo : 0;
+        const int w_in = main ? p.stride * wo0 + ti - p.pad_lo + 1 : wo0 + 1;
         if (lane == 0) {
           mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-          tma_load_2d(a_dst + kBOff, &tmB, &full_bar[s], chunk * kBlockK, tap * p.Cout + n0);
-          if (TERMS > 1)
-            tma_load_2d(a_dst + kBOff + kBBytes, &tmB, &full_bar[s], chunk * kBlockK, (taps + tap) * p.Cout + n0);
+          if (main) {
+            tma_load_2d(a_dst + kBOff, &tm.b, &full_bar[s], chunk * kBlockK, tap * p.Cout + n0);
+            if (TERMS > 1)
+              tma_load_2d(a_dst + kBOff + kBBytes, &tm.b, &full_bar[s], chunk * kBlockK, (taps + tap) * p.Cout + n0);
+          } else {
+            tma_load_2d(a_dst + kBOff, &tm.b2, &full_bar[s], chunk * kBlockK, n0);
+            if (TERMS > 1) tma_load_2d(a_dst + kBOff + kBBytes, &tm.b2, &full_bar[s], chunk * kBlockK, p.Cout + n0);
+          }
         }
-        if (lane == (TERMS == 1 ? 0 : 1)) tma_load_4d(a_dst, &tmA, &full_bar[s], chunk * kBlockK, tj - p.pad_lo, w_in, b0);
+        if (lane == (TERMS == 1 ? 0 : 1)) tma_load_4d(a_dst, main ? &tm.a : &tm.a2, &full_bar[s], chunk * kBlockK, h_in, w_in, b0);
         if (TERMS > 1 && lane == 2)
-          tma_load_4d(a_dst + kABytes, &tmAlo, &full_bar[s], chunk * kBlockK, tj - p.pad_lo, w_in, b0);
+          tma_load_4d(a_dst + kABytes, main ? &tm.alo : &tm.a2lo, &full_bar[s], chunk * kBlockK, h_in, w_in, b0);
         __syncwarp();
       }
     }
@@ -651,8 +678,8 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     int k = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
       const int acc = k & 1;
-      const int tm = t / tiles_n, tn = t - tm * tiles_n;
-      const int m0 = tm * kBlockM, n0 = tn * BLOCK_N;
+      const int tmi = t / tiles_n, tn = t - tmi * tiles_n;
+      const int m0 = tmi * kBlockM, n0 = tn * BLOCK_N;
       mbar_wait(&tmem_full[acc], (k >> 1) & 1);
       if (t + static_cast<int>(gridDim.x) >= total_tiles) pdl_trigger_conv_late();
       tc_fence_after();
@@ -924,8 +951,7 @@ static EncodeTiledFn get_encode() {
 }
 
 template <int BLOCK_N, int STAGES, int TERMS, int NSPLIT>
-static int launch_conv_n(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const CUtensorMap& tmB,
-                         const ConvParams& p, cudaStream_t st) {
+static int launch_conv_n(const ConvMaps& tm, const ConvParams& p, cudaStream_t st) {
   // pipeline stages (+ alignment slack) + barriers/TMEM pointer + the per-warp GroupNorm-moment scratch
   constexpr int smem = STAGES * (TERMS == 1 ? 1 : 2) * (kABytes + BLOCK_N * kBlockK * 2) + 1024 + 256 +
                        2 * 4 * (BLOCK_N / 2) * 4 + 64;
@@ -957,24 +983,22 @@ static int launch_conv_n(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  RLDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, STAGES, TERMS, NSPLIT>, tmA, tmAlo, tmB, p));
+  RLDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, STAGES, TERMS, NSPLIT>, tm, p));
   return 0;
 }
 
 template <int BLOCK_N, int STAGES, int TERMS>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const CUtensorMap& tmB,
-                       const ConvParams& p, int split, cudaStream_t st) {
+static int launch_conv(const ConvMaps& tm, const ConvParams& p, int split, cudaStream_t st) {
   switch (split) {
-    case 1: return launch_conv_n<BLOCK_N, STAGES, TERMS, 1>(tmA, tmAlo, tmB, p, st);
-    case 2: return launch_conv_n<BLOCK_N, STAGES, TERMS, 2>(tmA, tmAlo, tmB, p, st);
-    case 4: return launch_conv_n<BLOCK_N, STAGES, TERMS, 4>(tmA, tmAlo, tmB, p, st);
-    default: return launch_conv_n<BLOCK_N, STAGES, TERMS, 8>(tmA, tmAlo, tmB, p, st);
+    case 1: return launch_conv_n<BLOCK_N, STAGES, TERMS, 1>(tm, p, st);
+    case 2: return launch_conv_n<BLOCK_N, STAGES, TERMS, 2>(tm, p, st);
+    case 4: return launch_conv_n<BLOCK_N, STAGES, TERMS, 4>(tm, p, st);
+    default: return launch_conv_n<BLOCK_N, STAGES, TERMS, 8>(tm, p, st);
   }
 }
 
 template <int BLOCK_N, int STAGES, int TERMS>
-static int launch_conv_persistent(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const CUtensorMap& tmB,
-                                  const ConvParams& p, int n_ctas, cudaStream_t st) {
+static int launch_conv_persistent(const ConvMaps& tm, const ConvParams& p, int n_ctas, cudaStream_t st) {
   constexpr int smem = STAGES * (TERMS == 1 ? 1 : 2) * (kABytes + BLOCK_N * kBlockK * 2) + kBlockM * 36 * 4 + 256 +
                        2 * 4 * (BLOCK_N / 2) * 4 + 64 + 1024;
   static bool attr_set = false;
@@ -983,8 +1007,7 @@ static int launch_conv_persistent(const CUtensorMap& tmA, const CUtensorMap& tmA
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  RLDM_CUDA(launch_pdl(conv_tc_persistent_kernel<BLOCK_N, STAGES, TERMS>, dim3(n_ctas), dim3(192), smem, st, tmA, tmAlo,
-                       tmB, p));
+  RLDM_CUDA(launch_pdl(conv_tc_persistent_kernel<BLOCK_N, STAGES, TERMS>, dim3(n_ctas), dim3(192), smem, st, tm, p));
   return 0;
 }
 
@@ -1032,11 +1055,15 @@ using namespace rldm;
 // complete, [5] epilogue done.
 extern "C" void rldm_debug_conv_timestamps(long long* dev_buf) { g_conv_dbg = dev_buf; }
 
-extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias,
-                            const float* temb, int temb_stride, const float* residual, float* out,
-                            int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
-                            int circular, int split_k, double* stats, void* stream) {
+static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias,
+                        const float* temb, int temb_stride, const float* residual, float* out,
+                        int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
+                        int circular, int split_k, double* stats, const uint16_t* sc_x, const uint16_t* sc_x_lo,
+                        const uint16_t* sc_wgt, int sc_cin, void* stream) {
   RLDM_CHECK(ks == 1 || ks == 3, "conv_tc: ks must be 1 or 3 (got %d)", ks);
+  RLDM_CHECK(!sc_x || (sc_wgt && sc_cin > 0 && sc_cin % 64 == 0 && stride == 1 && (!x_lo == !sc_x_lo)),
+             "conv_tc: fused shortcut needs weights, Cin2 %% 64 == 0 (got %d), stride 1 and the same operand precision",
+             sc_cin);
   RLDM_CHECK(stride == 1 || stride == 2, "conv_tc: stride must be 1 or 2 (got %d)", stride);
   RLDM_CHECK(Cin % 64 == 0, "conv_tc: Cin %% 64 != 0 (got %d)", Cin);
   RLDM_CHECK(Cout % 64 == 0, "conv_tc: Cout %% 64 != 0 (got %d)", Cout);
@@ -1061,7 +1088,7 @@ extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint1
   // ---- halo-reuse path: 3x3, stride 1, symmetric pad, column pitch a whole number of swizzle atoms ----
   // (measured on B200: correct but not faster than the per-tap kernel, whose limiter is per-CTA latency rather
   //  than operand bytes -- kept opt-in with RLDM_HALO=1 until it is made persistent)
-  const bool halo_ok = ks == 3 && stride == 1 && pad_lo == 1 && Ho >= 8 && pix >= 128 && getenv("RLDM_HALO");
+  const bool halo_ok = ks == 3 && stride == 1 && pad_lo == 1 && Ho >= 8 && pix >= 128 && !sc_x && getenv("RLDM_HALO");
   if (halo_ok) {
     const size_t limit = 232448 - 1024 - 3328;          // 227 KB minus alignment slack and static shared memory
     const size_t b_stage = static_cast<size_t>(parts) * BN * 128;
@@ -1108,7 +1135,7 @@ extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint1
       p.pix_per_img = pix;
       p.Cout = Cout;
       p.ks = 3; p.stride = 1; p.pad_lo = 1; p.circular = circular;
-      p.total_iters = (Cin / kBlockK) * 9;
+      p.total_iters = p.main_iters = (Cin / kBlockK) * 9;
       p.units = (Cin / kBlockK) * 3;
       p.a_part_bytes = static_cast<int>(a_stage / parts);
       p.nb_stages = nbs;
@@ -1137,27 +1164,48 @@ extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint1
                      : launch_conv3x3<64, 1, 1>(tmA, tmAlo, tmB, p, split, smem, st);
     }
   }
-  for (int part = 0; part < parts; ++part) {
-    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)H, (cuuint64_t)(W + 2), (cuuint64_t)B};
-    cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)H * Cin * 2, (cuuint64_t)(W + 2) * H * Cin * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(Ho * stride), (cuuint32_t)(ncols * stride), (cuuint32_t)nb};
-    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    CUresult r = encode(part ? &tmAlo : &tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
-                        const_cast<uint16_t*>(part ? x_lo : x), gdim, gstr,
-                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(A) failed: %d", (int)r);
-  }
-  if (parts == 1) tmAlo = tmA;
-  {
-    cuuint64_t gdim[2] = {(cuuint64_t)Cin, (cuuint64_t)parts * ks * ks * Cout};
-    cuuint64_t gstr[1] = {(cuuint64_t)Cin * 2};
+  ConvMaps tm;
+  // activation maps: (C, H, W+2, B) fp16, box = (64 channels, Ho*stride rows, ncols*stride columns, nb images)
+  auto encode_act = [&](CUtensorMap* m, const uint16_t* ptr, int C, int st) -> CUresult {
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)(W + 2), (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)H * C * 2, (cuuint64_t)(W + 2) * H * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(Ho * st), (cuuint32_t)(ncols * st), (cuuint32_t)nb};
+    cuuint32_t estr[4] = {1, (cuuint32_t)st, (cuuint32_t)st, 1};
+    return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<uint16_t*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  // weight maps: [planes*taps*Cout][C] fp16, box = (64 channels, BN rows)
+  auto encode_wgt = [&](CUtensorMap* m, const uint16_t* ptr, int C, int rows) -> CUresult {
+    cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)C * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(wgt), gdim, gstr,
-                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+    return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  CUresult r = encode_act(&tm.a, x, Cin, stride);
+  RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+  if (parts == 2) {
+    r = encode_act(&tm.alo, x_lo, Cin, stride);
+    RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(A lo) failed: %d", (int)r);
+  } else {
+    tm.alo = tm.a;
+  }
+  r = encode_wgt(&tm.b, wgt, Cin, parts * ks * ks * Cout);
+  RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+  tm.a2 = tm.a; tm.a2lo = tm.alo; tm.b2 = tm.b;
+  if (sc_x) {
+    r = encode_act(&tm.a2, sc_x, sc_cin, 1);
+    RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(shortcut A) failed: %d", (int)r);
+    tm.a2lo = tm.a2;
+    if (parts == 2) {
+      r = encode_act(&tm.a2lo, sc_x_lo, sc_cin, 1);
+      RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(shortcut A lo) failed: %d", (int)r);
+    }
+    r = encode_wgt(&tm.b2, sc_wgt, sc_cin, parts * Cout);
+    RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(shortcut B) failed: %d", (int)r);
   }
   ConvParams p;
   p.bias = bias; p.temb = temb; p.residual = residual; p.out = out;
@@ -1167,7 +1215,8 @@ extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint1
   p.pix_per_img = Wo * Ho;
   p.Cout = Cout;
   p.ks = ks; p.stride = stride; p.pad_lo = pad_lo; p.circular = circular;
-  p.total_iters = (Cin / kBlockK) * ks * ks;
+  p.main_iters = (Cin / kBlockK) * ks * ks;
+  p.total_iters = p.main_iters + (sc_x ? sc_cin / kBlockK : 0);
   p.units = 0; p.a_part_bytes = 0; p.nb_stages = 0;
   p.dbg = g_conv_dbg;
   p.stats = stats;
@@ -1193,13 +1242,30 @@ extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint1
     if (n_sms <= 0) n_sms = 148;
   }
   if (split == 1 && tiles > n_sms && parts == 2 && !getenv("RLDM_NO_PERSISTENT")) {
-    if (BN == 128) return launch_conv_persistent<128, 3, 3>(tmA, tmAlo, tmB, p, n_sms, st);
-    return launch_conv_persistent<64, 4, 3>(tmA, tmAlo, tmB, p, n_sms, st);
+    if (BN == 128) return launch_conv_persistent<128, 3, 3>(tm, p, n_sms, st);
+    return launch_conv_persistent<64, 4, 3>(tm, p, n_sms, st);
   }
   if (parts == 2) {
-    if (BN == 128) return launch_conv<128, 3, 3>(tmA, tmAlo, tmB, p, split, st);
-    return launch_conv<64, 4, 3>(tmA, tmAlo, tmB, p, split, st);
+    if (BN == 128) return launch_conv<128, 3, 3>(tm, p, split, st);
+    return launch_conv<64, 4, 3>(tm, p, split, st);
   }
-  if (BN == 128) return launch_conv<128, 3, 1>(tmA, tmAlo, tmB, p, split, st);
-  return launch_conv<64, 4, 1>(tmA, tmAlo, tmB, p, split, st);
+  if (BN == 128) return launch_conv<128, 3, 1>(tm, p, split, st);
+  return launch_conv<64, 4, 1>(tm, p, split, st);
+}
+
+extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias,
+                            const float* temb, int temb_stride, const float* residual, float* out,
+                            int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
+                            int circular, int split_k, double* stats, void* stream) {
+  return conv_tc_impl(x, x_lo, wgt, bias, temb, temb_stride, residual, out, B, W, H, Cin, Cout, ks, stride, pad_lo,
+                      circular, split_k, stats, nullptr, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int rldm_conv_tc_shortcut(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias,
+                                     const float* temb, int temb_stride, const float* residual, float* out,
+                                     int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
+                                     int circular, int split_k, double* stats, const uint16_t* sc_x,
+                                     const uint16_t* sc_x_lo, const uint16_t* sc_wgt, int sc_cin, void* stream) {
+  return conv_tc_impl(x, x_lo, wgt, bias, temb, temb_stride, residual, out, B, W, H, Cin, Cout, ks, stride, pad_lo,
+                      circular, split_k, stats, sc_x, sc_x_lo, sc_wgt, sc_cin, stream);
 }

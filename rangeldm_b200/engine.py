@@ -35,6 +35,8 @@ CONV_KIND = _lib.OP_CONV_TC
 PRECISION = os.environ.get("RLDM_PRECISION", "fp16x3")
 # GroupNorm moments accumulated in the conv epilogue (RLDM_FUSE_STATS=0 forces the separate rldm_gn_stats pass)
 FUSE_STATS = os.environ.get("RLDM_FUSE_STATS", "1") != "0"
+# ResnetBlock2D.conv_shortcut folded into conv2's launch (RLDM_FUSE_SHORTCUT=0: separate 1x1 launch + fp32 residual)
+FUSE_SHORTCUT = os.environ.get("RLDM_FUSE_SHORTCUT", "1") != "0"
 
 
 def _require_cuda_device(dev, what):
@@ -229,9 +231,10 @@ class Builder:
         return (out, raw) if also_raw else out
 
     def conv(self, xh, W, H, conv=None, packed=None, cin=None, cout=None, ks=3, stride=1, pad_lo=1, circular=True,
-             temb=None, residual=None, stats=False):
+             temb=None, residual=None, stats=False, shortcut=None):
         """fp16 clp operand pair -> fp32 cl Act (B,W/stride,H/stride,Cout).  stats=True: the epilogue also
-        accumulates the GroupNorm moments of the output (consumed by the next prep instead of a gn_stats pass)."""
+        accumulates the GroupNorm moments of the output (consumed by the next prep instead of a gn_stats pass).
+        shortcut=(operand pair, 1x1 conv module): that convolution is folded into the K loop of this launch."""
         if conv is not None:
             wt, bias = self.pack_conv(conv)
             cout, cin, ks = conv.out_channels, conv.in_channels, conv.kernel_size[0]
@@ -249,12 +252,25 @@ class Builder:
         kind = CONV_KIND
         ints = [temb_stride, self.B, W, H, cin, cout, ks, stride, pad_lo, int(circular)]
         st = None
+        sc_ptrs = (None, None, None)
         if kind == _lib.OP_CONV_TC:
             if stats and FUSE_STATS and Wo * Ho >= 64:
                 st = self.stats_slot(cout // 2)          # channel-pair moments [B][Cout/2][2]
             ints += [0]   # split_k: auto
+            sc_cin = 0
+            if shortcut is not None:
+                sc_x, sc_conv = shortcut
+                sc_wt, _ = self.pack_conv(sc_conv)
+                assert sc_conv.kernel_size == (1, 1) and sc_conv.out_channels == cout and stride == 1
+                sc_cin = sc_conv.in_channels
+                sc_ptrs = (sc_x[0], sc_x[1], sc_wt)
+                bias = self._cached(("bias_sum", id(conv.bias), id(sc_conv.bias)),
+                                    lambda: (self.f32(conv.bias) + self.f32(sc_conv.bias)).contiguous())
+            ints += [sc_cin]
+        else:
+            assert shortcut is None
         self.pg.add(kind, i=ints, p=(xh[0], wt, bias, temb_t, residual.t if residual is not None else None, out,
-                                     xh[1], st), launches=1)
+                                     xh[1], st) + sc_ptrs, launches=1)
         return Act(out, self.B, Wo, Ho, cout, st)
 
     # ---- blocks ----------------------------------------------------------------------------
@@ -276,7 +292,11 @@ class Builder:
         self.free_half(a1)
         a2 = self.prep(h, None, rb.norm2, silu=True, circular=circ(rb.conv2))
         pg.free(h.t)
-        if rb.conv_shortcut is not None:
+        if rb.conv_shortcut is not None and CONV_KIND == _lib.OP_CONV_TC and FUSE_SHORTCUT:
+            # the 1x1 conv_shortcut rides in conv2's K loop (extra K steps over the raw operand)
+            out = self.conv(a2, x0.W, x0.H, rb.conv2, stats=True, shortcut=(xr, rb.conv_shortcut))
+            self.free_half(xr)
+        elif rb.conv_shortcut is not None:
             sc = self.conv(xr, x0.W, x0.H, rb.conv_shortcut)
             self.free_half(xr)
             out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=sc, stats=True)

@@ -159,6 +159,52 @@ def test_conv_tc_golden_reference_conv(L, golden):
         assert relerr(ref_layout(out.cpu()), y) < 1e-5
 
 
+SHORTCUT_CASES = [
+    # B, W, H, Cin (3x3 operand), Cin2 (1x1 shortcut operand), Cout, split_k
+    (2, 32, 8, 128, 256, 128, 0),       # UNet up-block geometry: K loop 18 + 4 steps
+    (4, 32, 2, 256, 512, 256, 8),       # 64-pixel images, cluster split-K x8 straddling the two operands
+    (1, 16, 8, 256, 128, 256, 4),       # down-block width change 128 -> 256
+    (8, 256, 16, 128, 256, 128, 0),     # C3 top level at full size: persistent kernel
+    (1, 512, 32, 64, 128, 64, 0),       # decoder geometry, BLOCK_N = 64, persistent
+]
+
+
+@pytest.mark.parametrize("case", SHORTCUT_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_tc_with_fused_shortcut(L, case):
+    """ResnetBlock2D tail: conv2(a) + conv_shortcut(x_raw) + biases in ONE launch == the two reference convs."""
+    B, W, H, Cin, Cin2, Cout, split = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    a = torch.randn(B, Cin, W, H, generator=g)
+    xr = torch.randn(B, Cin2, W, H, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    w2 = torch.randn(Cout, Cin2, 1, 1, generator=g) / Cin2 ** 0.5
+    b, b2 = torch.randn(Cout, generator=g), torch.randn(Cout, generator=g)
+    y = oracle_conv(a, w, b, 1, 1, 3) + F.conv2d(xr, w2, b2)
+    ah, al = split_half(cl(a)); xh, xl = split_half(cl(xr))
+    ah, al, xh, xl = padw(ah).cuda(), padw(al).cuda(), padw(xh).cuda(), padw(xl).cuda()
+    wt, wt2, bd = pack_w(w, split=True).cuda(), pack_w(w2, split=True).cuda(), (b + b2).cuda()
+    out = torch.full((B, W, H, Cout), float("nan"), device="cuda")
+    stats = torch.zeros(B, Cout // 2, 2, dtype=torch.float64, device="cuda")
+    L.call("rldm_conv_tc_shortcut", L.ptr(ah), L.ptr(al), L.ptr(wt), L.ptr(bd), None, 0, None, L.ptr(out),
+           B, W, H, Cin, Cout, 3, 1, 1, 1, split, L.ptr(stats) if W * H >= 64 else None,
+           L.ptr(xh), L.ptr(xl), L.ptr(wt2), Cin2)
+    torch.cuda.synchronize()
+    assert relerr(ref_layout(out.cpu()), y) < 1e-5
+    if W * H >= 64:
+        og = out.double().reshape(B, W * H, Cout // 2, 2)
+        assert torch.allclose(stats[:, :, 0], og.sum((1, 3)), rtol=1e-5, atol=1e-3)
+    # plain-fp16 operands (one MMA term) take the same path
+    out1 = torch.full((B, W, H, Cout), float("nan"), device="cuda")
+    w1h, w2h = pack_w(w).cuda(), pack_w(w2).cuda()          # keep the operands alive across the call
+    L.call("rldm_conv_tc_shortcut", L.ptr(ah), None, L.ptr(w1h), L.ptr(bd), None, 0, None, L.ptr(out1),
+           B, W, H, Cin, Cout, 3, 1, 1, 1, split, None, L.ptr(xh), None, L.ptr(w2h), Cin2)
+    torch.cuda.synchronize()
+    assert relerr(ref_layout(out1.cpu()), y) < 2e-3
+    with pytest.raises(L.RldmError):    # stride 2 cannot carry a same-grid shortcut
+        L.call("rldm_conv_tc_shortcut", L.ptr(ah), L.ptr(al), L.ptr(wt), L.ptr(bd), None, 0, None, L.ptr(out),
+               B, W, H, Cin, Cout, 3, 2, 1, 1, split, None, L.ptr(xh), L.ptr(xl), L.ptr(wt2), Cin2)
+
+
 def test_conv_tc_rejects_bad_shapes(L):
     x = torch.zeros(1, 10, 8, 48, dtype=torch.half, device="cuda")
     with pytest.raises(L.RldmError):
