@@ -117,10 +117,24 @@ int rldm_conv_ref(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, 
 int rldm_conv_in(const float* x0, int c0, const float* x1, int c1, const float* wgt,
                  const float* bias, float* out, int B, int W, int H, int Cout, int circular,
                  void* stream);
+/* conv_in that also accumulates the channel-pair moments of its output into stats[B][Cout/2][2] (double, zeroed by
+ * the caller; same contract as rldm_conv_tc's `stats`), so the first GroupNorm needs no statistics pass.
+ * Needs W*H % 32 == 0.  stats == NULL: identical to rldm_conv_in. */
+int rldm_conv_in_stats(const float* x0, int c0, const float* x1, int c1, const float* wgt, const float* bias,
+                       float* out, int B, int W, int H, int Cout, int circular, double* stats, void* stream);
 /* conv_out: x (+ optional x_lo) (B,W+2,H,Cin) fp16 clp (already GN+SiLU'd by rldm_prep) -> out
  * (B,Cout,W,H) fp32 REF layout, Cout in {2,4,8}.  wgt [9][Cout][Cin] fp32. */
 int rldm_conv_out(const uint16_t* x, const uint16_t* x_lo, const float* wgt, const float* bias, float* out, int B, int W,
                   int H, int Cin, int Cout, int circular, void* stream);
+
+/* conv_norm_out + SiLU + conv_out fused (UNet2DModel tail, App. A.1; Decoder tail `model.py:1051-1056`): x (B,W,H,Cin)
+ * fp32 cl -> GroupNorm(G, eps, gamma, beta; moments from `sums` [B][G][2] or channel-pair `pairs` [B][Cin/2][2], both
+ * NULL = no normalisation) -> SiLU (if silu) -> 3x3 circular/zero conv -> out (B,Cout,W,H) fp32 REF layout,
+ * Cout in {2,4,8}.  wgt [9][Cout][Cin] fp32 (tap = kW*3 + kH).  One launch instead of rldm_prep + rldm_conv_out and no
+ * fp16 operand round trip. */
+int rldm_norm_conv_out(const float* x, const double* sums, const double* pairs, const float* gamma, const float* beta,
+                       float eps, int G, int silu, const float* wgt, const float* bias, float* out, int B, int W, int H,
+                       int Cin, int Cout, int circular, void* stream);
 
 /* ---- attention core ----------------------------------------------------------------------
  * Replaces F.scaled_dot_product_attention in AttnProcessor2_0: heads of
@@ -160,7 +174,7 @@ int rldm_cl_to_ref(const float* src, float* dst, int B, int C, int W, int H, voi
 enum {
   RLDM_OP_GN_STATS = 1, RLDM_OP_PREP = 2, RLDM_OP_CONV_TC = 3, RLDM_OP_CONV_IN = 4,
   RLDM_OP_CONV_OUT = 5, RLDM_OP_ATTENTION = 6, RLDM_OP_TEMB = 7, RLDM_OP_SCHED_STEP = 8,
-  RLDM_OP_MEMSET = 9, RLDM_OP_CONV_REF = 10, RLDM_OP_AXPY = 11
+  RLDM_OP_MEMSET = 9, RLDM_OP_CONV_REF = 10, RLDM_OP_AXPY = 11, RLDM_OP_NORM_CONV_OUT = 12
 };
 typedef struct rldm_op {
   int32_t kind;

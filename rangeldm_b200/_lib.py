@@ -14,7 +14,7 @@ c_int, c_float, c_void_p, c_i64 = ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
 
 # kind codes of rldm_op (include/rldm.h)
 OP_GN_STATS, OP_PREP, OP_CONV_TC, OP_CONV_IN, OP_CONV_OUT, OP_ATTENTION, OP_TEMB, OP_SCHED_STEP, \
-    OP_MEMSET, OP_CONV_REF, OP_AXPY = range(1, 12)
+    OP_MEMSET, OP_CONV_REF, OP_AXPY, OP_NORM_CONV_OUT = range(1, 13)
 
 
 class RldmOp(ctypes.Structure):
@@ -37,6 +37,10 @@ SIGNATURES = {
                       + [c_int] * 9 + [c_void_p]),
     "rldm_conv_in": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 5
                      + [c_void_p]),
+    "rldm_norm_conv_out": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p,
+                                   c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
+    "rldm_conv_in_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 5
+                           + [c_void_p, c_void_p]),
     "rldm_conv_out": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
     "rldm_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rldm_temb": (c_int, [c_void_p] * 9 + [c_int] * 4 + [c_void_p]),

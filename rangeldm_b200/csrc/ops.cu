@@ -245,15 +245,20 @@ __global__ void conv_ref_kernel(const __half* __restrict__ x, const __half* __re
 
 // ------------------------------------------------------------------------------------------------
 // conv_in: (B,Cin,W,H) fp32 ref layout -> (B,W,H,Cout) fp32 cl, 3x3 circular/zero, Cin <= 16.
-// One block = kCinPix consecutive pixels.  The im2col rows of those pixels (9*Cin floats each, wrap and zero
-// pad resolved once) and the whole weight matrix [9*Cin][Cout] are staged in shared memory; then thread =
-// (pixel, 4 output channels) runs a K-long FMA chain on broadcast/conflict-free shared loads.
+// Each block owns a CONTIGUOUS range of kCinPix-pixel chunks: the weight matrix [9*Cin][Cout] is staged in shared
+// memory once per block (it used to be re-read for every 32 pixels, which was most of the kernel's traffic); per
+// chunk the im2col columns (9*Cin floats per pixel, wrap and zero pad resolved once) are staged as [K][32 pixels],
+// then thread = (4 pixels, 4 output channels) runs a K-long chain of 16 FMAs per pair of shared float4 loads.
+// stats (optional): channel-pair moments of the output, [B][Cout/2][2] doubles, accumulated per block while the
+// image index stays the same (needs W*H % kCinPix == 0) -- the GroupNorm of the first ResnetBlock2D reads them.
 constexpr int kCinPix = 32;
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
                const float* __restrict__ wgt, const float* __restrict__ bias,
-               float* __restrict__ out, int B, int W, int H, int Cout, int circular) {
+               float* __restrict__ out, int B, int W, int H, int Cout, int circular, double* __restrict__ stats,
+               int chunks_per_block) {
   extern __shared__ float sh_ci[];
+  __shared__ float red_s[512], red_q[512];
   const int Cin = c0 + c1;
   const int K = 9 * Cin;
   float* w_s = sh_ci;                    // [K][Cout]
@@ -263,54 +268,96 @@ conv_in_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x
     *reinterpret_cast<float4*>(w_s + i) = __ldg(reinterpret_cast<const float4*>(wgt + i));
   pdl_wait();
   const size_t total_pix = static_cast<size_t>(B) * W * H;
-  const size_t p_begin = static_cast<size_t>(blockIdx.x) * kCinPix;
-  for (int idx = threadIdx.x; idx < kCinPix * K; idx += blockDim.x) {
-    const int p = idx / K, k = idx - p * K;
-    const int tap = k / Cin, c = k - tap * Cin;
-    const int i = tap / 3, j = tap - i * 3;
-    const size_t pp = p_begin + p;
-    float a = 0.f;
-    if (pp < total_pix) {
-      const int h = pp % H;
-      const int w = (pp / H) % W;
-      const int b = pp / (static_cast<size_t>(H) * W);
-      int wi = w + i - 1;
-      const int hj = h + j - 1;
-      bool ok = hj >= 0 && hj < H;
-      if (circular) {
-        if (wi < 0) wi += W;
-        if (wi >= W) wi -= W;
-      } else {
-        ok = ok && wi >= 0 && wi < W;
-      }
-      if (ok)
-        a = (c < c0) ? __ldg(x0 + ((static_cast<size_t>(b) * c0 + c) * W + wi) * H + hj)
-                     : __ldg(x1 + ((static_cast<size_t>(b) * c1 + (c - c0)) * W + wi) * H + hj);
-    }
-    in_s[idx] = a;
-  }
-  __syncthreads();
+  const size_t pix_per_img = static_cast<size_t>(W) * H;
+  const int n_chunks = static_cast<int>((total_pix + kCinPix - 1) / kCinPix);
   const int q_per_pix = Cout >> 2;
   const int lanes_pix = blockDim.x / q_per_pix;
   const int quad = threadIdx.x % q_per_pix;
+  const int pl = threadIdx.x / q_per_pix;
   const int co = quad << 2;
   const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + co)) : make_float4(0, 0, 0, 0);
-  for (int p = threadIdx.x / q_per_pix; p < kCinPix; p += lanes_pix) {
-    const size_t pp = p_begin + p;
-    if (pp >= total_pix) break;
-    float4 acc = bv;
-    const float* ip = in_s + p * K;
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-      const float a = ip[k];
-      const float4 wv = *reinterpret_cast<const float4*>(w_s + k * Cout + co);
-      acc.x = fmaf(a, wv.x, acc.x);
-      acc.y = fmaf(a, wv.y, acc.y);
-      acc.z = fmaf(a, wv.z, acc.z);
-      acc.w = fmaf(a, wv.w, acc.w);
+  float s01 = 0.f, q01 = 0.f, s23 = 0.f, q23 = 0.f;
+  int cur_img = -1;
+  // fold the per-thread pair moments over the pixel lanes and add them to image `img` (one double atomic per pair)
+  auto flush = [&](int img) {
+    red_s[pl * (Cout >> 1) + (co >> 1)] = s01; red_q[pl * (Cout >> 1) + (co >> 1)] = q01;
+    red_s[pl * (Cout >> 1) + (co >> 1) + 1] = s23; red_q[pl * (Cout >> 1) + (co >> 1) + 1] = q23;
+    __syncthreads();
+    for (int t = threadIdx.x; t < (Cout >> 1); t += blockDim.x) {
+      double ds = 0.0, dq = 0.0;
+      for (int e = 0; e < lanes_pix; ++e) { ds += red_s[e * (Cout >> 1) + t]; dq += red_q[e * (Cout >> 1) + t]; }
+      double* st = stats + (static_cast<size_t>(img) * (Cout >> 1) + t) * 2;
+      atomicAdd(st, ds); atomicAdd(st + 1, dq);
     }
-    *reinterpret_cast<float4*>(out + pp * Cout + co) = acc;
+    __syncthreads();
+    s01 = q01 = s23 = q23 = 0.f;
+  };
+  const int c_begin = blockIdx.x * chunks_per_block;
+  const int c_end = min(n_chunks, c_begin + chunks_per_block);
+  for (int chunk = c_begin; chunk < c_end; ++chunk) {
+    const size_t p_begin = static_cast<size_t>(chunk) * kCinPix;
+    if (stats) {
+      const int img = static_cast<int>(p_begin / pix_per_img);        // uniform over the block
+      if (img != cur_img) {
+        if (cur_img >= 0) flush(cur_img);
+        cur_img = img;
+      }
+    }
+    __syncthreads();                     // previous chunk's in_s fully consumed
+    for (int idx = threadIdx.x; idx < kCinPix * K; idx += blockDim.x) {
+      const int k = idx / kCinPix, p = idx % kCinPix;      // consecutive threads = consecutive pixels: coalesced
+      const int tap = k / Cin, c = k - tap * Cin;
+      const int i = tap / 3, j = tap - i * 3;
+      const size_t pp = p_begin + p;
+      float a = 0.f;
+      if (pp < total_pix) {
+        const int h = pp % H;
+        const int w = (pp / H) % W;
+        const int b = pp / pix_per_img;
+        int wi = w + i - 1;
+        const int hj = h + j - 1;
+        bool ok = hj >= 0 && hj < H;
+        if (circular) {
+          if (wi < 0) wi += W;
+          if (wi >= W) wi -= W;
+        } else {
+          ok = ok && wi >= 0 && wi < W;
+        }
+        if (ok)
+          a = (c < c0) ? __ldg(x0 + ((static_cast<size_t>(b) * c0 + c) * W + wi) * H + hj)
+                       : __ldg(x1 + ((static_cast<size_t>(b) * c1 + (c - c0)) * W + wi) * H + hj);
+      }
+      in_s[idx] = a;                                       // [K][kCinPix]
+    }
+    __syncthreads();
+    // thread = 4 output channels x 4 pixels: every weight float4 read from shared memory feeds 16 FMAs
+    for (int pg = pl; pg < kCinPix / 4; pg += lanes_pix) {
+      float4 acc[4] = {bv, bv, bv, bv};
+#pragma unroll 3
+      for (int k = 0; k < K; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(in_s + k * kCinPix + 4 * pg);
+        const float4 wv = *reinterpret_cast<const float4*>(w_s + k * Cout + co);
+        acc[0].x = fmaf(a.x, wv.x, acc[0].x); acc[0].y = fmaf(a.x, wv.y, acc[0].y);
+        acc[0].z = fmaf(a.x, wv.z, acc[0].z); acc[0].w = fmaf(a.x, wv.w, acc[0].w);
+        acc[1].x = fmaf(a.y, wv.x, acc[1].x); acc[1].y = fmaf(a.y, wv.y, acc[1].y);
+        acc[1].z = fmaf(a.y, wv.z, acc[1].z); acc[1].w = fmaf(a.y, wv.w, acc[1].w);
+        acc[2].x = fmaf(a.z, wv.x, acc[2].x); acc[2].y = fmaf(a.z, wv.y, acc[2].y);
+        acc[2].z = fmaf(a.z, wv.z, acc[2].z); acc[2].w = fmaf(a.z, wv.w, acc[2].w);
+        acc[3].x = fmaf(a.w, wv.x, acc[3].x); acc[3].y = fmaf(a.w, wv.y, acc[3].y);
+        acc[3].z = fmaf(a.w, wv.z, acc[3].z); acc[3].w = fmaf(a.w, wv.w, acc[3].w);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const size_t pp = p_begin + 4 * pg + q;
+        if (pp < total_pix) {
+          *reinterpret_cast<float4*>(out + pp * Cout + co) = acc[q];
+          s01 += acc[q].x + acc[q].y; q01 += acc[q].x * acc[q].x + acc[q].y * acc[q].y;
+          s23 += acc[q].z + acc[q].w; q23 += acc[q].z * acc[q].z + acc[q].w * acc[q].w;
+        }
+      }
+    }
   }
+  if (stats && cur_img >= 0) flush(cur_img);
 }
 
 // conv_out: (B,W+2,H,Cin) fp16 clp (hi [+ lo]) -> (B,Cout,W,H) fp32 ref layout, Cout in {2,4,8}.
@@ -389,6 +436,127 @@ conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, c
     for (int o = LPP / 2; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
     if (live && sub == 0) out[((static_cast<size_t>(b) * COUT + n) * W + w) * H + h] = acc[n];
   }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// norm_conv_out: conv_norm_out (GroupNorm) + SiLU + conv_out (3x3, Cout <= 8) in ONE kernel.
+// x (B,W,H,Cin) fp32 cl -> out (B,Cout,W,H) fp32 ref layout.  grid (ceil(W/TW), B), block 256.
+// A block stages TW output columns plus one halo column on each side -- normalised and activated on the way in
+// (GroupNorm moments as in prep_kernel: group sums or channel-pair moments) -- as fp32 in shared memory with a row
+// pitch of Cin + 4*LPP floats (conflict-free float4 reads), the weights [9][Cout][Cin] next to it, and then
+// LPP lanes per pixel run the 9-tap x Cin FMA chain from shared memory.  Replaces a prep launch, the fp16 hi/lo
+// operand round trip (8 B per element written and 9x re-read through L1) and the old one-thread-per-pixel conv_out.
+template <int COUT>
+__global__ void __launch_bounds__(256)
+norm_conv_out_kernel(const float* __restrict__ x, const double* __restrict__ sums, const double* __restrict__ pairs,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int G, int silu,
+                     const float* __restrict__ wgt, const float* __restrict__ bias, float* __restrict__ out,
+                     int W, int H, int Cin, int circular, int TW, int LPP) {
+  extern __shared__ float sh_no[];
+  const int pitch = Cin + 4 * LPP;
+  float* sc = sh_no;                       // [Cin]
+  float* sf = sc + Cin;                    // [Cin]
+  float* w_s = sf + Cin;                   // [9][COUT][Cin]
+  float* tile = w_s + 9 * COUT * Cin;      // [(TW+2)*H][pitch]
+  pdl_trigger();
+  for (int i = threadIdx.x * 4; i < 9 * COUT * Cin; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(w_s + i) = __ldg(reinterpret_cast<const float4*>(wgt + i));
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int w0 = blockIdx.x * TW;
+  const bool norm = sums != nullptr || pairs != nullptr;
+  if (norm) {
+    const int cpg = Cin / G;
+    const double inv_n = 1.0 / (static_cast<double>(W) * H * cpg);
+    for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
+      const int g = c / cpg;
+      double s = 0.0, ss = 0.0;
+      if (sums) {
+        s = sums[(static_cast<size_t>(b) * G + g) * 2];
+        ss = sums[(static_cast<size_t>(b) * G + g) * 2 + 1];
+      } else {
+        for (int cc = g * cpg; cc < (g + 1) * cpg; cc += 2) {
+          const double* pr = pairs + (static_cast<size_t>(b) * (Cin / 2) + cc / 2) * 2;
+          s += pr[0];
+          ss += pr[1];
+        }
+      }
+      const double mean = s * inv_n;
+      double var = ss * inv_n - mean * mean;
+      if (var < 0) var = 0;
+      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      const float a = rstd * gamma[c];
+      sc[c] = a;
+      sf[c] = beta[c] - static_cast<float>(mean) * a;
+    }
+  }
+  __syncthreads();
+  // ---- stage (TW + 2) columns: normalise + SiLU on the way in; wrap (or zero) outside [0, W)
+  const int c4n = Cin >> 2;
+  const int n_items = (TW + 2) * H * c4n;
+  // H and Cin/4 are powers of two in every reference config: shifts instead of integer divisions (sh < 0: generic)
+  const int sh_c = (c4n & (c4n - 1)) == 0 ? 31 - __clz(c4n) : -1;
+  const int sh_h = (H & (H - 1)) == 0 ? 31 - __clz(H) : -1;
+  for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
+    const int r = sh_c >= 0 ? i >> sh_c : i / c4n;          // row of the tile = col * H + h
+    const int c = (i - r * c4n) << 2;
+    const int col = sh_h >= 0 ? r >> sh_h : r / H;
+    const int h = r - col * H;
+    int wc = w0 - 1 + col;
+    bool ok = true;
+    if (circular) {
+      if (wc < 0) wc += W;
+      if (wc >= W) wc -= W;
+    } else {
+      ok = wc >= 0 && wc < W;
+    }
+    ok = ok && (wc < W);                   // columns past a ragged last block are never consumed
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) {
+      v = __ldg(reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * W + wc) * H + h) * Cin + c));
+      if (norm) {
+        v.x = fmaf(v.x, sc[c], sf[c]); v.y = fmaf(v.y, sc[c + 1], sf[c + 1]);
+        v.z = fmaf(v.z, sc[c + 2], sf[c + 2]); v.w = fmaf(v.w, sc[c + 3], sf[c + 3]);
+      }
+      if (silu) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+    }
+    *reinterpret_cast<float4*>(tile + r * pitch + c) = v;
+  }
+  __syncthreads();
+  // ---- 3x3 conv from shared memory: LPP lanes per output pixel split the channel loop
+  const int sub = threadIdx.x % LPP;
+  const int n_pix = TW * H;
+  for (int p = threadIdx.x / LPP; p < n_pix; p += blockDim.x / LPP) {
+    const int col = sh_h >= 0 ? p >> sh_h : p / H;
+    const int h = p - col * H;
+    const int w = w0 + col;
+    float acc[COUT];
+#pragma unroll
+    for (int n = 0; n < COUT; ++n) acc[n] = 0.f;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) {
+        const int hj = h + j - 1;
+        if (hj < 0 || hj >= H) continue;
+        const float* xr = tile + ((col + i) * H + hj) * pitch;
+        const float* wt = w_s + (i * 3 + j) * COUT * Cin;
+#pragma unroll 4
+        for (int c = sub * 4; c < Cin; c += 4 * LPP) {
+          const float4 a = *reinterpret_cast<const float4*>(xr + c);
+#pragma unroll
+          for (int n = 0; n < COUT; ++n) {
+            const float4 wv = *reinterpret_cast<const float4*>(wt + n * Cin + c);
+            acc[n] = fmaf(a.x, wv.x, acc[n]); acc[n] = fmaf(a.y, wv.y, acc[n]);
+            acc[n] = fmaf(a.z, wv.z, acc[n]); acc[n] = fmaf(a.w, wv.w, acc[n]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < COUT; ++n) {
+      for (int o = LPP >> 1; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+      if (sub == 0 && w < W) out[((static_cast<size_t>(b) * COUT + n) * W + w) * H + h] = acc[n] + (bias ? __ldg(bias + n) : 0.f);
+    }
   }
 }
 
@@ -821,24 +989,43 @@ extern "C" int rldm_conv_ref(const uint16_t* x, const uint16_t* x_lo, const uint
   return 0;
 }
 
-extern "C" int rldm_conv_in(const float* x0, int c0, const float* x1, int c1, const float* wgt,
-                            const float* bias, float* out, int B, int W, int H, int Cout,
-                            int circular, void* stream) {
+static int conv_in_impl(const float* x0, int c0, const float* x1, int c1, const float* wgt, const float* bias, float* out,
+                        int B, int W, int H, int Cout, int circular, double* stats, void* stream) {
   RLDM_CHECK(x1 != nullptr || c1 == 0, "conv_in: x1 NULL with c1=%d", c1);
   RLDM_CHECK(Cout % 4 == 0 && Cout <= 1024 && 256 % (Cout / 4) == 0, "conv_in: unsupported Cout=%d", Cout);
+  RLDM_CHECK(!stats || (W * H) % kCinPix == 0, "conv_in: fused moments need W*H %% %d == 0 (got %d)", kCinPix, W * H);
   const size_t total_pix = static_cast<size_t>(B) * W * H;
   const int K = 9 * (c0 + c1);
   const size_t smem = (static_cast<size_t>(K) * Cout + static_cast<size_t>(kCinPix) * K) * sizeof(float);
   RLDM_CHECK(smem <= 200 * 1024, "conv_in: 9*Cin*Cout too large for shared memory (Cin=%d Cout=%d)", c0 + c1, Cout);
   static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
+  if (smem > 44 * 1024 && smem > smem_set) {
     RLDM_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     smem_set = 200 * 1024;
   }
-  RLDM_CUDA(launch_pdl(conv_in_kernel, dim3(static_cast<unsigned>((total_pix + kCinPix - 1) / kCinPix)), dim3(256), smem,
-                       as_stream(stream), x0, c0, x1, c1, wgt, bias, out, B, W, H, Cout, circular));
+  // contiguous chunk ranges over ~4 blocks per SM (fewer when the weights fill the shared memory)
+  const int n_chunks = static_cast<int>((total_pix + kCinPix - 1) / kCinPix);
+  const int per_sm = smem > 100 * 1024 ? 1 : (smem > 50 * 1024 ? 2 : 4);
+  int blocks = 148 * per_sm;
+  if (blocks > n_chunks) blocks = n_chunks;
+  const int cpb = (n_chunks + blocks - 1) / blocks;
+  blocks = (n_chunks + cpb - 1) / cpb;
+  RLDM_CUDA(launch_pdl(conv_in_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), smem, as_stream(stream), x0, c0, x1, c1,
+                       wgt, bias, out, B, W, H, Cout, circular, stats, cpb));
   RLDM_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int rldm_conv_in(const float* x0, int c0, const float* x1, int c1, const float* wgt,
+                            const float* bias, float* out, int B, int W, int H, int Cout,
+                            int circular, void* stream) {
+  return conv_in_impl(x0, c0, x1, c1, wgt, bias, out, B, W, H, Cout, circular, nullptr, stream);
+}
+
+extern "C" int rldm_conv_in_stats(const float* x0, int c0, const float* x1, int c1, const float* wgt,
+                                  const float* bias, float* out, int B, int W, int H, int Cout,
+                                  int circular, double* stats, void* stream) {
+  return conv_in_impl(x0, c0, x1, c1, wgt, bias, out, B, W, H, Cout, circular, stats, stream);
 }
 
 extern "C" int rldm_conv_out(const uint16_t* x, const uint16_t* x_lo, const float* wgt, const float* bias, float* out,
@@ -863,6 +1050,47 @@ extern "C" int rldm_conv_out(const uint16_t* x, const uint16_t* x_lo, const floa
     default: RLDM_CHECK(false, "conv_out: Cout must be 2, 4 or 8 (got %d)", Cout);
   }
 #undef RLDM_CO
+  RLDM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rldm_norm_conv_out(const float* x, const double* sums, const double* pairs, const float* gamma,
+                                  const float* beta, float eps, int G, int silu, const float* wgt, const float* bias,
+                                  float* out, int B, int W, int H, int Cin, int Cout, int circular, void* stream) {
+  RLDM_CHECK(Cin % 4 == 0, "norm_conv_out: Cin must be a multiple of 4");
+  RLDM_CHECK(!(sums || pairs) || (gamma && beta && G > 0 && Cin % G == 0), "norm_conv_out: GroupNorm needs gamma/beta/G");
+  RLDM_CHECK(!pairs || (Cin / G) % 2 == 0, "norm_conv_out: channel-pair moments need an even group size");
+  RLDM_CHECK(H >= 1 && H <= 256, "norm_conv_out: H out of range (%d)", H);
+  // lanes per pixel: keep ~256 threads busy on a TW x H pixel tile
+  int TW = 8, LPP = 1;
+  size_t smem = 0;
+  for (;; TW >>= 1) {
+    LPP = 1;
+    while (LPP < 8 && TW * H * LPP * 2 <= 256 && Cin % (8 * LPP) == 0) LPP *= 2;
+    smem = (2 * static_cast<size_t>(Cin) + 9 * static_cast<size_t>(Cout) * Cin +
+            static_cast<size_t>(TW + 2) * H * (Cin + 4 * LPP)) * sizeof(float);
+    if (smem <= 110 * 1024 || TW == 1) break;
+  }
+  RLDM_CHECK(smem <= 220 * 1024, "norm_conv_out: tile does not fit shared memory (H=%d Cin=%d Cout=%d)", H, Cin, Cout);
+  cudaStream_t st = as_stream(stream);
+  dim3 grid((W + TW - 1) / TW, B);
+#define RLDM_NCO(N)                                                                                                   \
+  {                                                                                                                   \
+    static size_t smem_set = 0;                                                                                       \
+    if (smem > 44 * 1024 && smem > smem_set) {                                                                        \
+      RLDM_CUDA(cudaFuncSetAttribute(norm_conv_out_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
+      smem_set = 220 * 1024;                                                                                          \
+    }                                                                                                                 \
+    RLDM_CUDA(launch_pdl(norm_conv_out_kernel<N>, grid, dim3(256), smem, st, x, sums, pairs, gamma, beta, eps, G, silu, wgt, \
+                         bias, out, W, H, Cin, circular, TW, LPP));                                                   \
+  }
+  switch (Cout) {
+    case 2: RLDM_NCO(2) break;
+    case 4: RLDM_NCO(4) break;
+    case 8: RLDM_NCO(8) break;
+    default: RLDM_CHECK(false, "norm_conv_out: Cout must be 2, 4 or 8 (got %d)", Cout);
+  }
+#undef RLDM_NCO
   RLDM_LAUNCH_CHECK();
   return 0;
 }
@@ -969,12 +1197,18 @@ static int run_ops(const rldm_op* ops, int n_ops, unsigned long long* stamps, vo
                            o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], o.i[7], o.i[8], o.i[9], stream);
         break;
       case RLDM_OP_CONV_IN:
-        rc = rldm_conv_in((const float*)o.p[0], o.i[0], (const float*)o.p[1], o.i[1], (const float*)o.p[2],
-                          (const float*)o.p[3], (float*)o.p[4], o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], stream);
+        rc = rldm_conv_in_stats((const float*)o.p[0], o.i[0], (const float*)o.p[1], o.i[1], (const float*)o.p[2],
+                                (const float*)o.p[3], (float*)o.p[4], o.i[2], o.i[3], o.i[4], o.i[5], o.i[6],
+                                (double*)o.p[5], stream);
         break;
       case RLDM_OP_CONV_OUT:
         rc = rldm_conv_out((const uint16_t*)o.p[0], (const uint16_t*)o.p[4], (const float*)o.p[1], (const float*)o.p[2],
                            (float*)o.p[3], o.i[0], o.i[1], o.i[2], o.i[3], o.i[4], o.i[5], stream);
+        break;
+      case RLDM_OP_NORM_CONV_OUT:
+        rc = rldm_norm_conv_out((const float*)o.p[0], (const double*)o.p[1], (const double*)o.p[2], (const float*)o.p[3],
+                                (const float*)o.p[4], o.f[0], o.i[0], o.i[1], (const float*)o.p[5], (const float*)o.p[6],
+                                (float*)o.p[7], o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], o.i[7], stream);
         break;
       case RLDM_OP_ATTENTION:
         rc = rldm_attention((const float*)o.p[0], (uint16_t*)o.p[1], (uint16_t*)o.p[2], o.i[0], o.i[1], o.i[2], o.i[3], stream);

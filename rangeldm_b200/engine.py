@@ -37,6 +37,7 @@ PRECISION = os.environ.get("RLDM_PRECISION", "fp16x3")
 FUSE_STATS = os.environ.get("RLDM_FUSE_STATS", "1") != "0"
 # ResnetBlock2D.conv_shortcut folded into conv2's launch (RLDM_FUSE_SHORTCUT=0: separate 1x1 launch + fp32 residual)
 FUSE_SHORTCUT = os.environ.get("RLDM_FUSE_SHORTCUT", "1") != "0"
+FUSE_CONV_OUT = os.environ.get("RLDM_FUSE_CONV_OUT", "1") != "0"
 
 
 def _require_cuda_device(dev, what):
@@ -359,20 +360,34 @@ class Builder:
             self.pg.device, torch.float32).permute(2, 3, 1, 0).contiguous())           # [9][Cin][Cout]
         out = self.pg.alloc((self.B, W, H, conv.out_channels))
         assert conv.in_channels == c0 + c1 and conv.kernel_size == (3, 3) and conv.padding == (1, 1)
+        st = self.stats_slot(conv.out_channels // 2) if (FUSE_STATS and (W * H) % 32 == 0) else None
         self.pg.add(_lib.OP_CONV_IN, i=(c0, c1, self.B, W, H, conv.out_channels, int(getattr(conv, "circular", False))),
-                    p=(x0, x1, wt, self.f32(conv.bias), out))
-        act = Act(out, self.B, W, H, conv.out_channels)
+                    p=(x0, x1, wt, self.f32(conv.bias), out, st))
+        act = Act(out, self.B, W, H, conv.out_channels, st)
         self.pg.taps.append((conv, act))
         return act
 
     def conv_out(self, norm, conv, x, out_ref):
-        a = self.prep(x, None, norm, silu=True, circular=bool(getattr(conv, "circular", False)))
+        """conv_norm_out + SiLU + conv_out: one fused launch straight from the fp32 residual stream
+        (RLDM_FUSE_CONV_OUT=0: rldm_prep + rldm_conv_out over the fp16 operand)."""
         wt = self._cached(("conv_out", id(conv.weight)), lambda: conv.weight.detach().to(
             self.pg.device, torch.float32).permute(2, 3, 0, 1).contiguous())           # [9][Cout][Cin]
         assert conv.kernel_size == (3, 3) and conv.padding == (1, 1)
-        self.pg.add(_lib.OP_CONV_OUT, i=(self.B, x.W, x.H, x.C, conv.out_channels, int(getattr(conv, "circular", False))),
-                    p=(a[0], wt, self.f32(conv.bias), out_ref, a[1]))
-        self.free_half(a)
+        circ = int(getattr(conv, "circular", False))
+        if FUSE_CONV_OUT and conv.out_channels in (2, 4, 8) and x.C % 4 == 0:
+            G = norm.num_groups
+            sums = pairs = None
+            if x.stats is not None and (x.C // G) % 2 == 0:
+                pairs = x.stats
+            else:
+                sums = self.gn_stats(x, None, G)
+            self.pg.add(_lib.OP_NORM_CONV_OUT, i=(G, 1, self.B, x.W, x.H, x.C, conv.out_channels, circ), f=(norm.eps,),
+                        p=(x.t, sums, pairs, self.f32(norm.weight), self.f32(norm.bias), wt, self.f32(conv.bias), out_ref))
+        else:
+            a = self.prep(x, None, norm, silu=True, circular=bool(circ))
+            self.pg.add(_lib.OP_CONV_OUT, i=(self.B, x.W, x.H, x.C, conv.out_channels, circ),
+                        p=(a[0], wt, self.f32(conv.bias), out_ref, a[1]))
+            self.free_half(a)
         self.pg.free(x.t)
 
 

@@ -122,7 +122,8 @@ def test_dry_run_plans_and_fused_program_launch_counts(monkeypatch):
     kinds = [op.kind for op in plan.prog.ops]
     # 95 convolutions / projections, 13 of them 1x1 conv_shortcuts that ride inside their block's conv2 launch
     assert kinds.count(_lib.OP_CONV_TC) == 82 and kinds.count(_lib.OP_ATTENTION) == 16
-    assert kinds.count(_lib.OP_CONV_IN) == 1 and kinds.count(_lib.OP_CONV_OUT) == 1 and kinds[0] == _lib.OP_MEMSET
+    assert kinds.count(_lib.OP_CONV_IN) == 1 and kinds.count(_lib.OP_NORM_CONV_OUT) == 1 and kinds[0] == _lib.OP_MEMSET
+    assert kinds.count(_lib.OP_GN_STATS) == 0          # every GroupNorm reads moments fused into a producing epilogue
     sch = R.DPMSolverMultistepScheduler(timestep_spacing="leading")
     sch.set_timesteps(20)
     v = R.AutoencoderKL(in_channels=2, out_channels=2, down_block_types=["DownEncoderBlock2D"] * 3,

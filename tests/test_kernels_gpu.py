@@ -342,6 +342,53 @@ def test_conv_in_and_conv_out(L):
         assert relerr(out.cpu(), oracle_conv(x, w, b, 1, 1, 3)) < 1e-5
 
 
+def test_conv_in_fused_pair_moments(L):
+    g = torch.Generator().manual_seed(19)
+    for (B, W, H, c0, c1, Cout) in ((3, 32, 8, 4, 1, 128), (2, 64, 16, 4, 0, 256), (2, 16, 16, 2, 0, 64)):
+        x0, x1 = torch.randn(B, c0, W, H, generator=g), torch.randn(B, max(c1, 1), W, H, generator=g)
+        w = torch.randn(Cout, c0 + c1, 3, 3, generator=g) * 0.2
+        b = torch.randn(Cout, generator=g)
+        out = torch.empty(B, W, H, Cout, device="cuda")
+        stats = torch.zeros(B, Cout // 2, 2, dtype=torch.float64, device="cuda")
+        x0d, x1d, wd, bd = x0.cuda(), x1.cuda(), w.permute(2, 3, 1, 0).contiguous().cuda(), b.cuda()
+        L.call("rldm_conv_in_stats", L.ptr(x0d), c0, L.ptr(x1d) if c1 else None, c1, L.ptr(wd), L.ptr(bd), L.ptr(out),
+               B, W, H, Cout, 1, L.ptr(stats))
+        xin = torch.cat([x0, x1], 1) if c1 else x0
+        assert relerr(ref_layout(out.cpu()), oracle_conv(xin, w, b, 1, 1, 3)) < 1e-5
+        og = out.double().reshape(B, W * H, Cout // 2, 2)
+        assert torch.allclose(stats[:, :, 0], og.sum((1, 3)), rtol=1e-5, atol=1e-3)
+        assert torch.allclose(stats[:, :, 1], (og * og).sum((1, 3)), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 8, 128, 4, 1), (1, 64, 16, 128, 4, 1), (2, 32, 64, 64, 2, 1),
+                                   (1, 24, 16, 256, 8, 1), (1, 10, 4, 64, 2, 0), (2, 7, 32, 64, 4, 1)])
+def test_norm_conv_out_fused(L, shape):
+    """GroupNorm + SiLU + 3x3 conv_out in one launch == F.group_norm -> F.silu -> reference circular conv."""
+    B, W, H, Cin, Cout, circ = shape
+    g = torch.Generator().manual_seed(W * 31 + Cin)
+    x = torch.randn(B, Cin, W, H, generator=g) * 1.5 + 0.3
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) * 0.1
+    b = torch.randn(Cout, generator=g)
+    G, eps = 32, 1e-6
+    gamma, beta = torch.randn(Cin, generator=g), torch.randn(Cin, generator=g)
+    y = oracle_conv(F.silu(F.group_norm(x, G, gamma, beta, eps)), w, b, 1, 1, 3, circular=bool(circ))
+    xd, wd, bd, gd, btd = cl(x).cuda(), w.permute(2, 3, 0, 1).contiguous().cuda(), b.cuda(), gamma.cuda(), beta.cuda()
+    xg = x.double().reshape(B, G, -1)
+    sums = torch.stack([xg.sum(-1), (xg * xg).sum(-1)], -1).contiguous().cuda()
+    xp = x.double().reshape(B, Cin // 2, -1)
+    pairs = torch.stack([xp.sum(-1), (xp * xp).sum(-1)], -1).contiguous().cuda()
+    for sm, pr in ((sums, None), (None, pairs)):
+        out = torch.full((B, Cout, W, H), float("nan"), device="cuda")
+        L.call("rldm_norm_conv_out", L.ptr(xd), L.ptr(sm), L.ptr(pr), L.ptr(gd), L.ptr(btd), eps, G, 1, L.ptr(wd), L.ptr(bd),
+               L.ptr(out), B, W, H, Cin, Cout, circ)
+        assert relerr(out.cpu(), y) < 1e-5
+    # no normalisation, no activation: a plain 3x3 conv to the reference layout
+    out = torch.full((B, Cout, W, H), float("nan"), device="cuda")
+    L.call("rldm_norm_conv_out", L.ptr(xd), None, None, None, None, 0.0, 0, 0, L.ptr(wd), L.ptr(bd), L.ptr(out),
+           B, W, H, Cin, Cout, circ)
+    assert relerr(out.cpu(), oracle_conv(x, w, b, 1, 1, 3, circular=bool(circ))) < 1e-5
+
+
 def test_layout_helpers(L):
     x = torch.randn(2, 5, 8, 4)
     d = torch.empty(2, 8, 4, 5, device="cuda")
