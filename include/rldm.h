@@ -189,6 +189,16 @@ int rldm_run(const rldm_op* ops, int n_ops, void* stream);
  * duration.  Graph-capturable.  Used by bench.py's roofline pass and scripts/, never by the sampling path. */
 int rldm_run_timed(const rldm_op* ops, int n_ops, unsigned long long* stamps, void* stream);
 
+/* ---- range image -> point cloud -----------------------------------------
+ * Replaces `point_cloud_to_range_image.to_pc_torch` (`ldm/dataset.py:228-276`), called on every generated batch
+ * (`ldm/inference.py:171`).  img (B,C,W,H) fp32 reference layout, channel 0 = encoded range, channel 1 = remission.
+ * mode 0: r = img*std + mean; 1: r = 2^(6 img) - 1 (`log`); 2: r = 1/max(img, 1e-4) (`inverse`); r < 0 -> fill
+ * (range_fill_value[0]).  incl / height: per-beam inclination and sensor height tables (length H, e.g.
+ * `ldm/kitti360_range_image.py:19-48`).  points (B, W*H, C > 1 ? 4 : 3) fp32 = x, y, z [, remission], point index
+ * w*H + h; depth (optional, B x W*H) = |xyz|, the quantity the .bin writer masks with `< 90` (`inference.py:176-178`). */
+int rldm_range_to_points(const float* img, int B, int C, int W, int H, const float* incl, const float* height, int mode,
+                         float mean, float stdv, float fill, float* points, float* depth, void* stream);
+
 /* y = a*x (elementwise, fp32), e.g. latents / scaling_factor (`ldm/pipelines.py:365`). */
 int rldm_scale(const float* x, float a, float* y, int64_t n, void* stream);
 

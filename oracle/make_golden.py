@@ -12,6 +12,7 @@ rebuild them anywhere without the reference tree and without committing megabyte
   ldm_pipeline.pt  reference `LDMPipelineRange.__call__` / `DDIMPipelineRange.__call__`
                    (`ldm/pipelines.py:282-383,144-258`) driving the oracle nets through the diffusers shim
   sparse_encoder2.pt reference `SparseRangeImageEncoder2.forward` (`ldm/encoders.py:86-95`)
+  range_to_points.pt reference `point_cloud_to_range_image_KITTI.to_pc_torch` (`ldm/dataset.py:228-276`)
 """
 import importlib
 import os
@@ -41,8 +42,41 @@ def toy_eps_matrix():
     return torch.randn(16, 16, generator=g) * 0.3
 
 
+def make_range_to_points():
+    """tests/golden/range_to_points.pt: the reference's own `point_cloud_to_range_image_KITTI.to_pc_torch`
+    (`ldm/dataset.py:228-276`, tables `ldm/kitti360_range_image.py:19-48`) in its three range encodings, plus the
+    depth-masked rows the writer loop of `ldm/inference.py:175-179` stores.  `ldm/dataset.py` imports
+    pytorch_lightning only for `RangeLoader`'s base class: a names-only stub is enough."""
+    import numpy as np
+    if "pytorch_lightning" not in sys.modules:
+        pl = types.ModuleType("pytorch_lightning")
+        pl.LightningDataModule = object
+        sys.modules["pytorch_lightning"] = pl
+    sys.path.insert(0, os.path.join(refshim.REF_ROOT, "ldm"))
+    kri = importlib.import_module("kitti360_range_image")
+    g = torch.Generator().manual_seed(23)
+    img = torch.rand(2, 2, 96, 64, generator=g) * 1.4 - 0.6              # some ranges come out negative -> fill value
+    out = {"image": img}
+    for name, kw in (("linear", {}), ("log", {"log": True}), ("inverse", {"inverse": True})):
+        tr = kri.point_cloud_to_range_image_KITTI(**kw)
+        pc = tr.to_pc_torch(img.clone())
+        out[name] = pc
+        if name == "linear":
+            out["incl"], out["height"] = torch.from_numpy(tr.incl.copy()), torch.from_numpy(tr.height.copy())
+            out["mean"], out["std"], out["fill"] = float(tr.mean), float(tr.std), float(tr.range_fill_value[0])
+            p0 = pc[0].cpu().detach().numpy()
+            depth = np.linalg.norm(p0[:, :3], 2, axis=1)
+            out["masked_rows"] = torch.from_numpy(p0[depth < 90.0, :].copy())
+    torch.save(out, os.path.join(OUT, "range_to_points.pt"))
+    print("range_to_points.pt", {k: tuple(v.shape) for k, v in out.items() if torch.is_tensor(v)})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--geometry-only" in sys.argv:
+        make_range_to_points()
+        return
+    make_range_to_points()
     model, sampling, disc = refshim.load()
     g = torch.Generator().manual_seed(11)
 

@@ -7,5 +7,6 @@ from .pipelines import (DiffusionPipeline, ImagePipelineOutput, DDPMPipelineRang
                         LDMPipelineRange, LDMUpscalePipelineRange, FusedSampler, randn_tensor)
 from .utils import replace_conv, replace_down, replace_attn, attn_identity  # noqa: F401
 from .encoders import SparseRangeImageEncoder2  # noqa: F401
+from .geometry import RangeImageGeometry  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1157,6 +1157,71 @@ extern "C" int rldm_cl_to_ref(const float* src, float* dst, int B, int C, int W,
 }
 
 // ------------------------------------------------------------------------------------------------
+// range image -> point cloud (`ldm/dataset.py:228-276`, point_cloud_to_range_image.to_pc_torch), the step the
+// reference runs on every generated batch right after the decode (`ldm/inference.py:171`).
+// img (B,C,W,H) fp32 ref layout -> points (B, W*H, 3|4) fp32: x, y, z [, remission]; optional depth (B, W*H) =
+// |xyz| for the `depth < 90 m` mask of the .bin writer (`ldm/inference.py:176-178`).  Thread = one pixel
+// (consecutive threads = consecutive beams h: coalesced reads, 16 B stores).  sin/cos of the 64 beam inclinations are
+// staged in shared memory once per block; the azimuth sin/cos is computed per thread (precise sincosf).
+namespace rldm {
+__global__ void __launch_bounds__(256)
+range_to_points_kernel(const float* __restrict__ img, int C, int W, int H, const float* __restrict__ incl,
+                       const float* __restrict__ height, int mode, float mean, float stdv, float fill,
+                       float* __restrict__ points, float* __restrict__ depth, size_t total) {
+  extern __shared__ float sh_rp[];      // sin(incl)[H], cos(incl)[H], height[H]
+  pdl_entry();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    float sv, cv;
+    sincosf(__ldg(incl + i), &sv, &cv);
+    sh_rp[i] = sv; sh_rp[H + i] = cv; sh_rp[2 * H + i] = __ldg(height + i);
+  }
+  __syncthreads();
+  const int P = C > 1 ? 4 : 3;
+  for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int h = idx % H;
+    const int w = (idx / H) % W;
+    const size_t b = idx / (static_cast<size_t>(H) * W);
+    const float v = __ldg(img + (b * C * W + w) * H + h);
+    float r;
+    if (mode == 1) r = exp2f(v * 6.0f) - 1.0f;                    // log encoding      (`:241-242`)
+    else if (mode == 2) r = 1.0f / fmaxf(v, 0.0001f);             // inverse encoding  (`:243-244`)
+    else r = v * stdv + mean;                                     // linear            (`:245-246`)
+    if (r < 0.0f) r = fill;                                       // `:256`
+    const float z = sh_rp[2 * H + h] - r * sh_rp[h];              // `:259`
+    const float xy = r * sh_rp[H + h];                            // `:262`
+    // azi = (W - 0.5 - w) / W * 2 pi - pi                          `:266`, same operation order in fp32
+    const float azi = (static_cast<float>(W) - 0.5f - static_cast<float>(w)) / static_cast<float>(W) * 2.0f * 3.14159265358979323846f - 3.14159265358979323846f;
+    float sa, ca;
+    sincosf(azi, &sa, &ca);
+    const float x = xy * ca, y = xy * sa;                         // `:269-270`
+    if (P == 4) {
+      const float rem = __ldg(img + ((b * C + 1) * W + w) * H + h);
+      *reinterpret_cast<float4*>(points + idx * 4) = make_float4(x, y, z, rem);
+    } else {
+      points[idx * 3] = x; points[idx * 3 + 1] = y; points[idx * 3 + 2] = z;
+    }
+    if (depth) depth[idx] = sqrtf(x * x + y * y + z * z);
+  }
+}
+}  // namespace rldm
+
+extern "C" int rldm_range_to_points(const float* img, int B, int C, int W, int H, const float* incl, const float* height,
+                                    int mode, float mean, float stdv, float fill, float* points, float* depth,
+                                    void* stream) {
+  RLDM_CHECK(C >= 1 && H >= 1 && H <= 1024, "range_to_points: bad shape (C=%d H=%d)", C, H);
+  RLDM_CHECK(mode >= 0 && mode <= 2, "range_to_points: mode must be 0 (linear), 1 (log) or 2 (inverse)");
+  const size_t total = static_cast<size_t>(B) * W * H;
+  if (total == 0) return 0;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  RLDM_CUDA(launch_pdl(range_to_points_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 3 * H * sizeof(float),
+                       as_stream(stream), img, C, W, H, incl, height, mode, mean, stdv, fill, points, depth, total));
+  RLDM_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 namespace rldm {
 __global__ void stamp_kernel(unsigned long long* slot) {
   unsigned long long t;

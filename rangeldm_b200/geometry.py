@@ -1,0 +1,78 @@
+"""Range image -> point cloud on the GPU: the host-side mirror of the reference's
+`point_cloud_to_range_image.to_pc_torch` (`ldm/dataset.py:228-276`) and of the `.bin` writer loop of
+`ldm/inference.py:174-179`.
+
+The sensor tables (`incl`, `height`, e.g. `ldm/kitti360_range_image.py:19-48`) are DATA supplied by the caller:
+`RangeImageGeometry.from_reference(to_range)` copies them -- and `log`, `inverse`, `mean`, `std`,
+`range_fill_value` -- from a reference `point_cloud_to_range_image*` object, so `ldm/inference.py:171`
+(`pc_all = to_range.to_pc_torch(image)`) becomes `pc_all = geom.to_pc_torch(image)`.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+MODE_LINEAR, MODE_LOG, MODE_INVERSE = 0, 1, 2
+
+
+class RangeImageGeometry:
+    def __init__(self, incl, height, log=False, inverse=False, mean=20.0, std=40.0, range_fill_value=(100, 0)):
+        self.incl = np.ascontiguousarray(np.asarray(incl, dtype=np.float32))
+        self.height = np.ascontiguousarray(np.asarray(height, dtype=np.float32))
+        if self.incl.shape != self.height.shape or self.incl.ndim != 1:
+            raise ValueError("incl and height must be 1-D tables of the same length (one entry per beam)")
+        self.log, self.inverse = bool(log), bool(inverse)
+        self.mean, self.std = float(mean), float(std)
+        self.range_fill_value = np.asarray(range_fill_value)
+        self._dev = {}
+
+    @classmethod
+    def from_reference(cls, to_range):
+        """Build from a reference `point_cloud_to_range_image*` instance (`ldm/inference.py:81`)."""
+        return cls(to_range.incl, to_range.height, log=to_range.log, inverse=to_range.inverse, mean=to_range.mean,
+                   std=to_range.std, range_fill_value=to_range.range_fill_value)
+
+    @property
+    def mode(self):
+        return MODE_LOG if self.log else (MODE_INVERSE if self.inverse else MODE_LINEAR)     # `:241-246` precedence
+
+    def _tables(self, device):
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = (torch.from_numpy(self.incl).to(device), torch.from_numpy(self.height).to(device))
+        return self._dev[key]
+
+    def to_pc_torch(self, range_images, return_depth=False):
+        """range_images (B, C, W, H) fp32 on CUDA -> (B, W*H, 3|4) [and depth (B, W*H)].  No CPU fallback."""
+        if not range_images.is_cuda:
+            raise RuntimeError("RangeImageGeometry.to_pc_torch needs a CUDA tensor: rangeldm_b200 has no CPU fallback")
+        B, C, W, H = range_images.shape
+        if H != self.incl.shape[0]:
+            raise AssertionError(f"range image has {H} beams, the sensor tables {self.incl.shape[0]}")
+        x = range_images.to(torch.float32).contiguous()
+        incl, height = self._tables(x.device)
+        pts = torch.empty((B, W * H, 4 if C > 1 else 3), device=x.device)
+        depth = torch.empty((B, W * H), device=x.device) if return_depth else None
+        _lib.call("rldm_range_to_points", _lib.ptr(x), B, C, W, H, _lib.ptr(incl), _lib.ptr(height), self.mode, self.mean,
+                  self.std, float(self.range_fill_value[0]), _lib.ptr(pts), _lib.ptr(depth))
+        return (pts, depth) if return_depth else pts
+
+    def masked_points(self, range_images, max_depth=90.0):
+        """Per sample the float32 (N_i, 3|4) arrays the reference writes (`ldm/inference.py:175-179`): rows with
+        |xyz| < max_depth, original order.  One device pass + one D2H copy for the whole batch."""
+        pts, depth = self.to_pc_torch(range_images, return_depth=True)
+        pts_h, keep = pts.cpu().numpy(), (depth < max_depth).cpu().numpy()
+        return [pts_h[j][keep[j], :] for j in range(pts_h.shape[0])]
+
+    def write_bins(self, range_images, out_dir, first_index=0, max_depth=90.0, limit=None):
+        """`pc[mask, :].tofile(f'{out}/{index}.bin')` for every sample (`ldm/inference.py:174-179`)."""
+        import os
+        os.makedirs(out_dir, exist_ok=True)
+        paths = []
+        for j, pc in enumerate(self.masked_points(range_images, max_depth)):
+            if limit is not None and first_index + j >= limit:
+                break
+            path = os.path.join(out_dir, f"{first_index + j}.bin")
+            pc.tofile(path)
+            paths.append(path)
+        return paths

@@ -428,3 +428,35 @@ def test_scheduler_step_matches_oracle(kind):
             xa = s.step(eps.cuda(), t, xa).prev_sample
             xb = o.step(eps, t, xb)
         assert relerr(xa, xb) < 1e-5, int(t)
+
+
+def test_range_to_points_matches_reference_golden(L, golden, tmp_path):
+    """rldm_range_to_points (through RangeImageGeometry) against the reference's own to_pc_torch outputs, the CPU
+    oracle at KITTI size, and the .bin writer contract (float32 N x 4, |xyz| < 90, original order)."""
+    import numpy as np
+    import rangeldm_b200 as R
+    from oracle import geometry as G
+    d = golden("range_to_points.pt")
+    for name, kw in (("linear", {}), ("log", {"log": True}), ("inverse", {"inverse": True})):
+        geom = R.RangeImageGeometry(d["incl"].numpy(), d["height"].numpy(), mean=d["mean"], std=d["std"], **kw)
+        pts = geom.to_pc_torch(d["image"].cuda())
+        assert pts.shape == d[name].shape
+        assert relerr(pts.cpu(), d[name]) < 1e-5
+    geom = R.RangeImageGeometry(d["incl"].numpy(), d["height"].numpy())
+    # full KITTI size (BASELINE shape 2 x 1024 x 64), against the oracle
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(3, 2, 1024, 64, generator=g) * 1.3 - 0.5
+    pts, depth = geom.to_pc_torch(img.cuda(), return_depth=True)
+    ref = G.to_points(img, d["incl"], d["height"])
+    assert relerr(pts.cpu(), ref) < 1e-5
+    assert torch.allclose(depth.cpu(), ref[..., :3].norm(dim=-1), rtol=1e-5, atol=1e-4)
+    assert torch.equal(pts[..., 3].cpu(), img[:, 1].reshape(3, -1))             # remission is copied bit-exactly
+    # single-channel image -> xyz only; writer: rows with depth < 90 m in order, float32 N x 4 on disk
+    assert geom.to_pc_torch(img[:, :1].cuda()).shape == (3, 65536, 3)
+    paths = geom.write_bins(d["image"].cuda(), str(tmp_path), first_index=7)
+    assert [p.rsplit("/", 1)[1] for p in paths] == ["7.bin", "8.bin"]
+    rows = np.fromfile(paths[0], dtype=np.float32).reshape(-1, 4)
+    want = d["masked_rows"].numpy()
+    assert rows.shape == want.shape and np.allclose(rows, want, rtol=1e-5, atol=1e-4)
+    with pytest.raises(RuntimeError):
+        geom.to_pc_torch(img)                                                    # CPU tensor: no fallback

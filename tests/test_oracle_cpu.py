@@ -110,3 +110,18 @@ def test_ddpm_ddim_consistency():
     prev = d.step(eps, t, xt)
     ap = d.alphas_cumprod[t - 20]
     assert torch.allclose(prev, ap.sqrt() * x0 + (1 - ap).sqrt() * eps, atol=1e-5)
+
+
+def test_geometry_oracle_matches_reference_to_pc_torch(golden):
+    """oracle/geometry.py == the reference's `point_cloud_to_range_image_KITTI.to_pc_torch` (`ldm/dataset.py:228-276`)
+    in its three range encodings, and == the depth-masked rows of the writer loop (`ldm/inference.py:175-179`)."""
+    from oracle import geometry as G
+    d = golden("range_to_points.pt")
+    for name, mode in (("linear", G.MODE_LINEAR), ("log", G.MODE_LOG), ("inverse", G.MODE_INVERSE)):
+        y = G.to_points(d["image"], d["incl"], d["height"], mode, d["mean"], d["std"], d["fill"])
+        assert y.shape == d[name].shape and torch.equal(y, d[name])
+    rows = G.depth_masked(G.to_points(d["image"], d["incl"], d["height"], 0, d["mean"], d["std"], d["fill"])[0])
+    assert rows.dtype.name == "float32" and torch.equal(torch.from_numpy(rows), d["masked_rows"])
+    # edge cases: single channel -> (x, y, z) only; empty batch
+    assert G.to_points(d["image"][:, :1], d["incl"], d["height"]).shape == (2, 96 * 64, 3)
+    assert G.to_points(d["image"][:0], d["incl"], d["height"]).shape == (0, 96 * 64, 4)
