@@ -537,16 +537,25 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
 // tile k (TMEM -> 32-column shared staging slab -> coalesced global, bias/temb/residual/GroupNorm moments) while
 // the producer and MMA warps are already running the K loop of tile k+1.  The staging slab is private to the
 // epilogue (not aliased with the pipeline stages).
-template <int BLOCK_N, int STAGES, int TERMS>
+//
+// MT = 2: a work unit is TWO consecutive 128-pixel M tiles that share every weight tile: a stage holds
+// [A0_hi A0_lo A1_hi A1_lo B_hi B_lo] and feeds 2 x 12 MMAs.  The K loop of these kernels is bound by the operand
+// stream into the SM (~64 B/clk: a 64 KB stage lands in ~1000 cycles while its 12 MMAs need 768); sharing B over two
+// tiles cuts the bytes per MMA by 25 % (48 KB per 12 MMAs), which makes the loop MMA-bound, and it halves the number
+// of units (256 tiles -> 128 units: one wave on 148 SMs instead of 1.73).  TMEM: 2 units x MT x BLOCK_N columns.
+template <int BLOCK_N, int STAGES, int TERMS, int MT>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   constexpr int kParts = TERMS == 1 ? 1 : 2;
-  constexpr int kStageBytes = kParts * (kABytes + kBBytes);
-  constexpr int kBOff = kParts * kABytes;
+  constexpr int kATile = kParts * kABytes;                      // one M tile of a stage: [A_hi][A_lo]
+  constexpr int kStageBytes = MT * kATile + kParts * kBBytes;
+  constexpr int kBOff = MT * kATile;
   constexpr int kSlabPitch = 36;                                // floats per row of the 32-column staging slab
   constexpr int kSlabBytes = kBlockM * kSlabPitch * 4;          // 18 KB
   constexpr int kChunks = BLOCK_N / 32;
+  constexpr int kAccCols = MT * BLOCK_N;                        // TMEM columns of one unit's accumulators
+  static_assert(2 * kAccCols <= 512, "double-buffered accumulators must fit TMEM");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -563,8 +572,8 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_n = p.Cout / BLOCK_N;
-  const int tiles_m = (p.M_total + kBlockM - 1) / kBlockM;
-  const int total_tiles = tiles_m * tiles_n;
+  const int tiles_m = (p.M_total + kBlockM - 1) / kBlockM;      // a multiple of MT (host)
+  const int total_units = (tiles_m / MT) * tiles_n;
   const int taps = p.ks * p.ks;
   const int n_it = p.total_iters;
 
@@ -588,7 +597,7 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<2 * BLOCK_N>(tmem_ptr);
+  if (warp == 1) tmem_alloc<2 * kAccCols>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -596,15 +605,19 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
   pdl_wait();
 
   if (warp == 0) {
-    // ===================== TMA producer: one continuous stage ring across tiles =================
+    // ===================== TMA producer: one continuous stage ring across units =================
     int g = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      if (t + static_cast<int>(gridDim.x) >= total_tiles) pdl_trigger_conv_late();
-      const int tmi = t / tiles_n, tn = t - tmi * tiles_n;
-      const int m0 = tmi * kBlockM, n0 = tn * BLOCK_N;
-      const int q0 = m0 / p.Ho;
-      const int b0 = q0 / p.Wo;
-      const int wo0 = q0 - b0 * p.Wo;
+    for (int t = blockIdx.x; t < total_units; t += gridDim.x) {
+      if (t + static_cast<int>(gridDim.x) >= total_units) pdl_trigger_conv_late();
+      const int um = t / tiles_n, tn = t - um * tiles_n;
+      const int m0 = um * (MT * kBlockM), n0 = tn * BLOCK_N;
+      int b0[MT], wo0[MT];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int q0 = (m0 + mt * kBlockM) / p.Ho;          // global column index of the tile's first column
+        b0[mt] = q0 / p.Wo;
+        wo0[mt] = q0 - b0[mt] * p.Wo;
+      }
       for (int it = 0; it < n_it; ++it, ++g) {
         const int s = g % STAGES;
         mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
@@ -615,7 +628,8 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
         const uint32_t a_dst = smem_u32(smem + s * kStageBytes);
         // shortcut K steps: centre tap of the second tensor (1x1, stride 1, same grid as the output)
         const int h_in = main ? tj - p.pad_lo : 0;
-        const int w_in = main ? p.stride * wo0 + ti - p.pad_lo + 1 : wo0 + 1;
+        const int w_off = main ? ti - p.pad_lo + 1 : 1;
+        const int w_mul = main ? p.stride : 1;
         if (lane == 0) {
           mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
           if (main) {
@@ -627,40 +641,47 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
             if (TERMS > 1) tma_load_2d(a_dst + kBOff + kBBytes, &tm.b2, &full_bar[s], chunk * kBlockK, p.Cout + n0);
           }
         }
-        if (lane == (TERMS == 1 ? 0 : 1)) tma_load_4d(a_dst, main ? &tm.a : &tm.a2, &full_bar[s], chunk * kBlockK, h_in, w_in, b0);
-        if (TERMS > 1 && lane == 2)
-          tma_load_4d(a_dst + kABytes, main ? &tm.alo : &tm.a2lo, &full_bar[s], chunk * kBlockK, h_in, w_in, b0);
+        // lanes 1.. : one box per (M tile, operand part)
+        if (lane >= 1 && lane <= MT * kParts) {
+          const int mt = (lane - 1) / kParts, part = (lane - 1) % kParts;
+          const CUtensorMap* map = main ? (part ? &tm.alo : &tm.a) : (part ? &tm.a2lo : &tm.a2);
+          tma_load_4d(a_dst + mt * kATile + part * kABytes, map, &full_bar[s], chunk * kBlockK, h_in,
+                      w_mul * wo0[mt] + w_off, b0[mt]);
+        }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: alternates between the two TMEM accumulators ==============
+    // ===================== MMA issuer: alternates between the two TMEM accumulator sets ===========
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BLOCK_N);
       int g = 0, k = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
-        if (t + static_cast<int>(gridDim.x) >= total_tiles) pdl_trigger_conv_late();
+      for (int t = blockIdx.x; t < total_units; t += gridDim.x, ++k) {
+        if (t + static_cast<int>(gridDim.x) >= total_units) pdl_trigger_conv_late();
         const int acc = k & 1;
-        mbar_wait(&tmem_empty[acc], ((k >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+        mbar_wait(&tmem_empty[acc], ((k >> 1) & 1) ^ 1);       // epilogue has drained this accumulator set
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int it = 0; it < n_it; ++it, ++g) {
           const int s = g % STAGES;
           mbar_wait(&full_bar[s], (g / STAGES) & 1);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
-          const uint64_t a_desc = umma_desc_sw128(a_addr);
           const uint64_t b_desc = umma_desc_sw128(a_addr + kBOff);
+          const uint64_t bl_desc = umma_desc_sw128(a_addr + kBOff + kBBytes);
 #pragma unroll
-          for (int kk = 0; kk < kBlockK / 16; ++kk)
-            umma_f16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (it | kk) != 0);
-          if (TERMS > 1) {
-            const uint64_t al_desc = umma_desc_sw128(a_addr + kABytes);
-            const uint64_t bl_desc = umma_desc_sw128(a_addr + kBOff + kBBytes);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint32_t d_tmem = tmem_base + acc * kAccCols + mt * BLOCK_N;
+            const uint64_t a_desc = umma_desc_sw128(a_addr + mt * kATile);
 #pragma unroll
-            for (int kk = 0; kk < kBlockK / 16; ++kk) {
-              umma_f16(d_tmem, al_desc + 2 * kk, b_desc + 2 * kk, idesc, 1u);
-              umma_f16(d_tmem, a_desc + 2 * kk, bl_desc + 2 * kk, idesc, 1u);
+            for (int kk = 0; kk < kBlockK / 16; ++kk)
+              umma_f16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (it | kk) != 0);
+            if (TERMS > 1) {
+              const uint64_t al_desc = umma_desc_sw128(a_addr + mt * kATile + kABytes);
+#pragma unroll
+              for (int kk = 0; kk < kBlockK / 16; ++kk) {
+                umma_f16(d_tmem, al_desc + 2 * kk, b_desc + 2 * kk, idesc, 1u);
+                umma_f16(d_tmem, a_desc + 2 * kk, bl_desc + 2 * kk, idesc, 1u);
+              }
             }
           }
           umma_commit(&empty_bar[s]);
@@ -670,34 +691,49 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
     }
     __syncwarp();
   } else {
-    // ===================== epilogue warps: drain tile k while tile k+1 is being computed =========
+    // ===================== epilogue warps: drain unit k while unit k+1 is being computed =========
     const int ew = warp - 2;                  // rows ew*32 .. ew*32+31 of the tile in the coalesced phase
     const int q = warp & 3;                   // TMEM lane quadrant readable by this warp
     const int rsub = lane >> 3;               // 4 rows per warp instruction in the coalesced phase
     const int col = (lane & 7) * 4;           // float4 column inside the 32-column slab
     int k = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
+    for (int t = blockIdx.x; t < total_units; t += gridDim.x, ++k) {
       const int acc = k & 1;
-      const int tmi = t / tiles_n, tn = t - tmi * tiles_n;
-      const int m0 = tmi * kBlockM, n0 = tn * BLOCK_N;
+      const int um = t / tiles_n, tn = t - um * tiles_n;
+      const int n0 = tn * BLOCK_N;
       mbar_wait(&tmem_full[acc], (k >> 1) & 1);
-      if (t + static_cast<int>(gridDim.x) >= total_tiles) pdl_trigger_conv_late();
+      if (t + static_cast<int>(gridDim.x) >= total_units) pdl_trigger_conv_late();
       tc_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+      const int m0 = um * (MT * kBlockM) + mt * kBlockM;
       const int m_first = m0 + ew * 32;
       const int bimg = min(m_first, p.M_total - 1) / p.pix_per_img;   // a warp's 32 rows lie in one image
-      float sg[kChunks], qg[kChunks];         // per-chunk moments of this lane's 4 channels
-      float s23c[kChunks], q23c[kChunks];     // second channel pair (only used when cpg == 2)
+      float sg[kChunks], qg[kChunks];         // per-chunk moments of this lane's first channel pair
+      float s23c[kChunks], q23c[kChunks];     // second channel pair
+      // residual rows of chunk nc+1 are fetched while chunk nc is drained (two chunks of loads in flight per lane)
+      float4 res_nx[8];
+      auto fetch_res = [&](int nc, float4 (&dst)[8]) {
+        const int c = n0 + nc * 32 + col;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int m = m_first + u * 4 + rsub;
+          dst[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < p.M_total) dst[u] = __ldg(reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(m) * p.Cout + c));
+        }
+      };
+      if (p.residual) fetch_res(0, res_nx);
 #pragma unroll
       for (int nc = 0; nc < kChunks; ++nc) {
         // (1) accumulator slab -> registers -> shared (row = TMEM lane)
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16) + nc * 32, r);
+        tmem_ld_32x32(tmem_base + acc * kAccCols + mt * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16) + nc * 32, r);
         tmem_ld_wait();
         float* srow = slab + (q * 32 + lane) * kSlabPitch;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<uint4*>(srow + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        if (nc == kChunks - 1) {              // last TMEM read of this tile: hand the accumulator back
+        if (mt == MT - 1 && nc == kChunks - 1) {   // last TMEM read of this unit: hand the accumulators back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
@@ -714,13 +750,10 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
         float4 res[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int m = m_first + u * 4 + rsub;
           res[u] = add4;
-          if (p.residual && m < p.M_total) {
-            const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(m) * p.Cout + c));
-            res[u].x += t4.x; res[u].y += t4.y; res[u].z += t4.z; res[u].w += t4.w;
-          }
+          if (p.residual) { res[u].x += res_nx[u].x; res[u].y += res_nx[u].y; res[u].z += res_nx[u].z; res[u].w += res_nx[u].w; }
         }
+        if (p.residual && nc + 1 < kChunks) fetch_res(nc + 1, res_nx);
         float s01 = 0.f, q01 = 0.f, s23 = 0.f, q23 = 0.f;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -780,11 +813,12 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");     // red_* reusable by the next tile
       }
+      }   // mt
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<2 * BLOCK_N>(tmem_base);
+  if (warp == 1) tmem_dealloc<2 * kAccCols>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -997,17 +1031,18 @@ static int launch_conv(const ConvMaps& tm, const ConvParams& p, int split, cudaS
   }
 }
 
-template <int BLOCK_N, int STAGES, int TERMS>
+template <int BLOCK_N, int STAGES, int TERMS, int MT>
 static int launch_conv_persistent(const ConvMaps& tm, const ConvParams& p, int n_ctas, cudaStream_t st) {
-  constexpr int smem = STAGES * (TERMS == 1 ? 1 : 2) * (kABytes + BLOCK_N * kBlockK * 2) + kBlockM * 36 * 4 + 256 +
+  constexpr int smem = STAGES * (TERMS == 1 ? 1 : 2) * (MT * kABytes + BLOCK_N * kBlockK * 2) + kBlockM * 36 * 4 + 256 +
                        2 * 4 * (BLOCK_N / 2) * 4 + 64 + 1024;
+  static_assert(smem <= 232448, "persistent conv: shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
-    RLDM_CUDA(cudaFuncSetAttribute(conv_tc_persistent_kernel<BLOCK_N, STAGES, TERMS>,
+    RLDM_CUDA(cudaFuncSetAttribute(conv_tc_persistent_kernel<BLOCK_N, STAGES, TERMS, MT>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  RLDM_CUDA(launch_pdl(conv_tc_persistent_kernel<BLOCK_N, STAGES, TERMS>, dim3(n_ctas), dim3(192), smem, st, tm, p));
+  RLDM_CUDA(launch_pdl(conv_tc_persistent_kernel<BLOCK_N, STAGES, TERMS, MT>, dim3(n_ctas), dim3(192), smem, st, tm, p));
   return 0;
 }
 
@@ -1242,8 +1277,20 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
     if (n_sms <= 0) n_sms = 148;
   }
   if (split == 1 && tiles > n_sms && parts == 2 && !getenv("RLDM_NO_PERSISTENT")) {
-    if (BN == 128) return launch_conv_persistent<128, 3, 3>(tm, p, n_sms, st);
-    return launch_conv_persistent<64, 4, 3>(tm, p, n_sms, st);
+    // two M tiles per unit share the weight tiles when the tile count allows it (RLDM_CONV_MT1=1: one tile per unit)
+    const int tiles_m = (p.M_total + kBlockM - 1) / kBlockM;
+    // (measured: -5..-20 % on layers without a residual operand; with one the drain of two tiles, not the K loop,
+    //  paces the unit, so those keep one tile per unit and three pipeline stages)
+    const bool mt2 = tiles_m % 2 == 0 && p.M_total % kBlockM == 0 && (residual == nullptr || getenv("RLDM_CONV_MT2_RES")) &&
+                     !getenv("RLDM_CONV_MT1");
+    const int units = mt2 ? tiles / 2 : tiles;
+    const int ctas = units < n_sms ? units : n_sms;
+    if (mt2) {
+      if (BN == 128) return launch_conv_persistent<128, 2, 3, 2>(tm, p, ctas, st);
+      return launch_conv_persistent<64, 2, 3, 2>(tm, p, ctas, st);
+    }
+    if (BN == 128) return launch_conv_persistent<128, 3, 3, 1>(tm, p, ctas, st);
+    return launch_conv_persistent<64, 4, 3, 1>(tm, p, ctas, st);
   }
   if (parts == 2) {
     if (BN == 128) return launch_conv<128, 3, 3>(tm, p, split, st);
