@@ -51,6 +51,16 @@ def peaks():
     return 1590.0, 1400.0, 6650.0, "fallback"
 
 
+def conv_traffic():
+    """DRAM bytes (read + write) per conv_tc launch from the committed ncu capture of the same workload
+    (profiles/conv_tc_traffic_r1.json, written by scripts/conv_traffic.py); None when the file is absent."""
+    p = os.path.join(ROOT, "profiles", "conv_tc_traffic_r1.json")
+    try:
+        return round(json.load(open(p))["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -266,7 +276,7 @@ def run_native(args):
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM circular conv)",
                          "achieved": round(achieved, 2), "peak": burst, "unit": "TFLOP/s",
                          "frac": round(achieved / burst, 4), "peak_source": f"{src} bf16 burst (kernel timed alone: device-side stamps around every launch, in-graph)",
-                         "frac_of_sustained": round(achieved / sustained, 4), "traffic": None,
+                         "frac_of_sustained": round(achieved / sustained, 4), "traffic": conv_traffic(),
                          "launches": cnt.get("conv_tc", 0), "avg_launch_us": round(1e3 * conv_ms / max(cnt.get("conv_tc", 1), 1), 2),
                          "share_of_step": round(conv_ms / all_ms, 4) if all_ms else None,
                          "per_kind_ms_one_unet_plus_decoder": {k: round(v, 4) for k, v in sorted(ms.items())}},

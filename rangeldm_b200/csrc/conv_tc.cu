@@ -1279,9 +1279,9 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
   if (split == 1 && tiles > n_sms && parts == 2 && !getenv("RLDM_NO_PERSISTENT")) {
     // two M tiles per unit share the weight tiles when the tile count allows it (RLDM_CONV_MT1=1: one tile per unit)
     const int tiles_m = (p.M_total + kBlockM - 1) / kBlockM;
-    // (measured: -5..-20 % on layers without a residual operand; with one the drain of two tiles, not the K loop,
-    //  paces the unit, so those keep one tile per unit and three pipeline stages)
-    const bool mt2 = tiles_m % 2 == 0 && p.M_total % kBlockM == 0 && (residual == nullptr || getenv("RLDM_CONV_MT2_RES")) &&
+    // (measured: -5..-20 % on layers without a residual operand and on 64-channel layers; 128-wide layers WITH a
+    //  residual are paced by the drain of two tiles, not the K loop: they keep one tile per unit and three stages)
+    const bool mt2 = tiles_m % 2 == 0 && p.M_total % kBlockM == 0 && (residual == nullptr || BN == 64 || getenv("RLDM_CONV_MT2_RES")) &&
                      !getenv("RLDM_CONV_MT1");
     const int units = mt2 ? tiles / 2 : tiles;
     const int ctas = units < n_sms ? units : n_sms;
