@@ -228,6 +228,50 @@ def test_c4_nuscenes_latent_unet_forward():
     assert relerr(out, ref, "c4_nuscenes_unet_forward") < TOL
 
 
+def test_c5_conditional_unet_forward_full_size_batch_4():
+    """BASELINE configs[4] geometry: conditional upsampling UNet (4 latent + 8 condition channels in, 12-channel
+    conv_in) at 256x16, per-GPU batch 4 (`ldm/pipelines.py:498` concat each step)."""
+    from oracle import nets
+    from oracle.make_golden import seeded
+    ou = seeded(nets.OracleUNet2DModel, 5, **nets.UNET_C5)
+    u = make_unet(nets.UNET_C5, ou)
+    x = torch.randn(4, 12, 256, 16, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        ref = ou(x, torch.tensor(300))
+    out = u(x.cuda(), torch.tensor(300)).sample
+    assert relerr(out, ref, "c5_conditional_unet_forward") < TOL
+
+
+def test_c4_nuscenes_decoder_full_size():
+    """nuScenes VAE decode: (B,4,256,8) latent -> (B,2,1024,32) range image (BASELINE configs[3]); batch 3 exercises
+    odd batch sizes on the persistent / two-tile kernels (M not a power of two)."""
+    from oracle import nets
+    from oracle.make_golden import seeded
+    ov = seeded(nets.OracleAutoencoderKL, 2)
+    v = make_vae(ov, [64, 128, 256], 2)
+    z = torch.randn(3, 4, 256, 8, generator=torch.Generator().manual_seed(8))
+    with torch.no_grad():
+        ref = ov.decode(z)
+    out = v.decode(z.cuda()).sample
+    assert out.shape == (3, 2, 1024, 32)
+    assert relerr(out, ref, "c4_nuscenes_decoder") < TOL
+
+
+@pytest.mark.parametrize("batch", [1, 3])
+def test_c3_unet_odd_batches(batch):
+    """Per-GPU batches other than 8: single image (every level under one wave) and 3 images (ragged tile counts)."""
+    from oracle import nets
+    from oracle.make_golden import seeded
+    ou = seeded(nets.OracleUNet2DModel, 0, **nets.UNET_C3)
+    u = make_unet(nets.UNET_C3, ou)
+    x = torch.randn(batch, 5, 256, 16, generator=torch.Generator().manual_seed(10 + batch))
+    t = torch.tensor([17, 500, 999][:batch])
+    with torch.no_grad():
+        ref = ou(x, t)
+    out = u(x.cuda(), t).sample
+    assert relerr(out, ref, f"c3_unet_batch{batch}") < TOL
+
+
 def test_multi_stream_sampler_matches_single(tiny):
     """FusedSampler(streams=2): two sub-batch programs on parallel graph branches give the same images."""
     import rangeldm_b200 as R
