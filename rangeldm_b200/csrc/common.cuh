@@ -32,13 +32,30 @@ void set_error(const char* fmt, ...);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// Programmatic dependent launch (opt-in, RLDM_PDL=1): kernels are then launched with the
-// programmatic-stream-serialization attribute, fire `griddepcontrol.launch_dependents` and execute
-// `griddepcontrol.wait` before their first access to memory a previous kernel may have written (or may still
-// read).  The wait returns only when the preceding grid has completed and flushed, so correctness is that of
-// plain stream order.  Without the attribute both instructions are no-ops.  Inside CUDA graphs on B200 the
-// programmatic edges measured slower than plain edges for this workload, hence the default is off.
+// Programmatic dependent launch: kernels launched with the programmatic-stream-serialization attribute may start
+// while the preceding kernel is still running; they execute `griddepcontrol.wait` before their first access to
+// memory a previous kernel may have written (or may still read) -- the wait returns only when the preceding grid has
+// completed and flushed, so correctness is that of plain stream order -- and every kernel fires
+// `griddepcontrol.launch_dependents` early.  Without the attribute both instructions are no-ops.  Which launches get
+// the attribute is a measured policy (ops.cu: pdl_mode): by default only the latency-bound ones.
 bool pdl_enabled();
+// launches marked latency-bound (small convolutions, small prep passes)
+bool pdl_enabled_small();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_small(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                           cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled_small() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                      cudaStream_t st, Args&&... args) {

@@ -1003,7 +1003,7 @@ static int launch_conv_n(const ConvMaps& tm, const ConvParams& p, cudaStream_t s
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  if (pdl_enabled()) {
+  if (pdl_enabled_small()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;

@@ -16,13 +16,21 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-bool pdl_enabled() {
+// Programmatic dependent launch policy (RLDM_PDL = 0 | 1 | 2, default 2).  Measured on B200 inside the trajectory
+// graph (scripts/timeline.py, scripts/launch_gap.py): programmatic edges save ~1 us per node on the latency-bound
+// launches (small convolutions 9.6 -> 8.8 us, prep + conv pairs 11.5 -> 10.1 us), but make the long persistent
+// convolutions, the attention kernel and the big elementwise passes SLOWER (decoder +8 %) -- early-launched dependents
+// sit on SM resources for the whole primary.  Mode 2 therefore marks only the latency-bound launches; 1 marks all.
+static int pdl_mode() {
   static int v = -1;
-  // Measured on B200 inside the trajectory graph (scripts/timeline.py): programmatic edges make the C3 UNet 3 % and
-  // the KITTI decoder 8 % SLOWER than plain edges, wherever launch_dependents is fired, so PDL is opt-in.
-  if (v < 0) v = getenv("RLDM_PDL") ? 1 : 0;
-  return v == 1;
+  if (v < 0) {
+    const char* e = getenv("RLDM_PDL");
+    v = e ? atoi(e) : 2;
+  }
+  return v;
 }
+bool pdl_enabled() { return pdl_mode() == 1; }
+bool pdl_enabled_small() { return pdl_mode() == 1 || pdl_mode() == 2; }
 
 // ------------------------------------------------------------------------------------------------
 // GroupNorm statistics.  grid (chunks, B), block 256.  Thread = one float4 of channels, striding
@@ -971,8 +979,14 @@ extern "C" int rldm_prep(const float* x0, int c0, const float* x1, int c1, const
   int ppb = (out_pix + chunks - 1) / chunks;
   if (ppb < 8) ppb = 8;
   chunks = (out_pix + ppb - 1) / ppb;
-  RLDM_CUDA(launch_pdl(prep_kernel, dim3(chunks, B), dim3(256), 2 * C * sizeof(float), as_stream(stream), x0, c0, x1, c1, sums, pairs0, pairs1, gamma, beta, eps, G, silu, up, circular, reinterpret_cast<__half*>(out),
+  // small (latency-bound) preps may start under the tail of the producing kernel (RLDM_PDL=2); large ones measured slower
+  if (static_cast<size_t>(B) * out_pix * C <= (1u << 21)) {
+    RLDM_CUDA(launch_pdl_small(prep_kernel, dim3(chunks, B), dim3(256), 2 * C * sizeof(float), as_stream(stream), x0, c0, x1, c1, sums, pairs0, pairs1, gamma, beta, eps, G, silu, up, circular, reinterpret_cast<__half*>(out),
       reinterpret_cast<__half*>(out_lo), reinterpret_cast<__half*>(raw), reinterpret_cast<__half*>(raw_lo), W, H, ppb));
+    } else {
+    RLDM_CUDA(launch_pdl(prep_kernel, dim3(chunks, B), dim3(256), 2 * C * sizeof(float), as_stream(stream), x0, c0, x1, c1, sums, pairs0, pairs1, gamma, beta, eps, G, silu, up, circular, reinterpret_cast<__half*>(out),
+      reinterpret_cast<__half*>(out_lo), reinterpret_cast<__half*>(raw), reinterpret_cast<__half*>(raw_lo), W, H, ppb));
+    }
   RLDM_LAUNCH_CHECK();
   return 0;
 }
