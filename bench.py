@@ -124,7 +124,8 @@ def build_pipeline(dev):
 def conv_flops(op):
     i = op.i
     B, W, H, Cin, Cout, ks, stride = i[1], i[2], i[3], i[4], i[5], i[6], i[7]
-    return 2.0 * B * (W // stride) * (H // stride) * Cout * Cin * ks * ks
+    sc_cin = i[11]                       # 1x1 conv_shortcut folded into this launch (0: none)
+    return 2.0 * B * (W // stride) * (H // stride) * Cout * (Cin * ks * ks + sc_cin)
 
 
 def timed_profile(prog, reps=5):
@@ -155,7 +156,7 @@ def timed_profile(prog, reps=5):
 
 
 OP_NAMES = {1: "gn_stats", 2: "prep", 3: "conv_tc", 4: "conv_in", 5: "conv_out", 6: "attention", 7: "temb",
-            8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale"}
+            8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale", 12: "norm_conv_out"}
 
 
 def per_op_profile(sampler):

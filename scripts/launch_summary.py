@@ -4,6 +4,8 @@ import collections, csv, sys
 lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
 seq = []
 for row in csv.DictReader(lines):
+    if row.get("Metric Name", "gpu__time_duration.sum") != "gpu__time_duration.sum":
+        continue                      # the same list may carry DRAM-byte metrics (scripts/conv_traffic.py)
     v = float(row["Metric Value"].replace(",", ""))
     us = v / 1000 if row["Metric Unit"] in ("ns", "nsecond") else v
     seq.append((row["Kernel Name"].split("(")[0][:44], us, row["Grid Size"]))

@@ -9,7 +9,7 @@ import bench
 from rangeldm_b200 import _lib
 
 NAMES = {1: "gn_stats", 2: "prep", 3: "conv_tc", 4: "conv_in", 5: "conv_out", 6: "attention", 7: "temb",
-         8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale"}
+         8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale", 12: "norm_conv_out"}
 
 
 def describe(op):
