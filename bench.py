@@ -186,6 +186,11 @@ def run_native(args):
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE line (the JSON): library chatter written to fd 1 during the run (e.g. NCCL's
+    # "NCCL version ..." banner at communicator creation) is sent to stderr until the result is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = PER_GPU_BATCH
@@ -288,6 +293,9 @@ def run_native(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if rank == 0:
         print(json.dumps(out), flush=True)
 
