@@ -199,6 +199,16 @@ int rldm_run_timed(const rldm_op* ops, int n_ops, unsigned long long* stamps, vo
 int rldm_range_to_points(const float* img, int B, int C, int W, int H, const float* incl, const float* height, int mode,
                          float mean, float stdv, float fill, float* points, float* depth, void* stream);
 
+/* Point cloud -> bird's-eye-view volume: `to_voxel` (`ldm/dataset.py:278-294`) = `_splat_points_to_volumes`
+ * (`:13-132`, trilinear votes of every point, the reference's 16 scatter_add_ passes) + features / clamp(density, 1e-4)
+ * + log(density + 1) when `normalize`.  points (B,N,P) fp32 with P = 3 or 4 (x, y, z [, remission]) in metres,
+ * pc_range6 HOST pointer {xmin,ymin,zmin,xmax,ymax,zmax}; grid (D,Hh,Ww) = the reference's grid_sizes.
+ * scratch: 2*B*D*Hh*Ww floats (zeroed here); voxel: (B, 2*D, Hh, Ww) fp32 = [densities, features]
+ * (`voxel = torch.cat([volume_densities, volume_features], dim=1)`, `:292`).  Votes are float atomics: sums agree with
+ * the reference to rounding order. */
+int rldm_points_to_voxel(const float* points, int B, int N, int P, const float* pc_range6, int D, int Hh, int Ww,
+                         int normalize, float* scratch, float* voxel, void* stream);
+
 /* y = a*x (elementwise, fp32), e.g. latents / scaling_factor (`ldm/pipelines.py:365`). */
 int rldm_scale(const float* x, float a, float* y, int64_t n, void* stream);
 

@@ -1,7 +1,8 @@
 """CPU restatement of the reference's range-image -> point-cloud geometry (TEST INFRASTRUCTURE ONLY).
 
-Follows `ldm/dataset.py:228-276` (`point_cloud_to_range_image.to_pc_torch`) and the writer loop of
-`ldm/inference.py:174-179` (depth mask < 90 m, float32 N x 4 `.bin`).  Pinned against the reference's own
+Follows `ldm/dataset.py:228-276` (`point_cloud_to_range_image.to_pc_torch`), `:278-294` (`to_voxel`) with
+`_splat_points_to_volumes` (`:13-132`), and the writer loop of `ldm/inference.py:174-179` (depth mask < 90 m,
+float32 N x 4 `.bin`).  Pinned against the reference's own
 `point_cloud_to_range_image_KITTI.to_pc_torch` by `tests/golden/range_to_points.pt` (made by oracle/make_golden.py).
 """
 import math
@@ -41,3 +42,51 @@ def depth_masked(points, max_depth=90.0):
     pc = points.detach().cpu().numpy()
     depth = np.linalg.norm(pc[:, :3], 2, axis=1)
     return pc[depth < max_depth, :]
+
+
+def to_voxel(range_images, incl, height, mode=MODE_LINEAR, mean=20.0, std=40.0, fill=100.0,
+             grid_sizes=(1, 1024, 1024), pc_range=(-25.6, -25.6, -3.0, 25.6, 25.6, 1.0), normalize=True,
+             min_weight=1e-4):
+    """Bird's-eye-view volume of `to_voxel` (`ldm/dataset.py:278-294`): trilinear splat of every point into the
+    (D, H, W) = grid_sizes volume (`_splat_points_to_volumes`, `:13-132`), features = remission divided by the
+    clamped vote weight, densities -> log(d + 1).  Returns (B, 2*D, H, W): [densities, features]."""
+    pc = to_points(range_images, incl, height, mode, mean, std, fill).double()
+    B, N, _ = pc.shape
+    D, Hh, Ww = grid_sizes
+    lo = torch.tensor(pc_range[:3], dtype=torch.float32).double()
+    hi = torch.tensor(pc_range[3:], dtype=torch.float32).double()
+    # the reference does this in fp32 (`:282-283`); the oracle keeps fp32 semantics for the index computation
+    xyz = ((pc[..., :3].float() - ((hi + lo) / 2).float()) / ((hi - lo) / 2).float())
+    feat = pc[..., 3].float()
+    gxyz = torch.tensor([Ww, Hh, D], dtype=torch.float32)
+    idx3 = ((xyz + 1) * 0.5) * (gxyz - 1)                                     # `:66-68`
+    base = idx3.floor()
+    r = idx3 - base                                                           # `:70`
+    base = base.long()
+    n_vox = D * Hh * Ww
+    dens = torch.zeros(B, n_vox, dtype=torch.float32)
+    feats = torch.zeros(B, n_vox, dtype=torch.float32)
+    for xd in (0, 1):                                                         # `:81-123`
+        X_ = base[..., 0] + xd
+        wX = (1 - xd) + (2 * xd - 1) * r[..., 0]
+        for yd in (0, 1):
+            Y_ = base[..., 1] + yd
+            wY = (1 - yd) + (2 * yd - 1) * r[..., 1]
+            for zd in (0, 1):
+                Z_ = base[..., 2] + zd
+                wZ = (1 - zd) + (2 * zd - 1) * r[..., 2]
+                w = wX * wY * wZ
+                valid = (0 <= X_) & (X_ < Ww) & (0 <= Y_) & (Y_ < Hh) & (0 <= Z_) & (Z_ < D)
+                idx = ((Z_ * Hh + Y_) * Ww + X_) * valid                     # invalid votes: weight 0 into voxel 0
+                wv = w * valid
+                dens.scatter_add_(1, idx, wv)
+                feats.scatter_add_(1, idx, wv * feat)
+    feats = feats / dens.clamp(min_weight)                                    # `:126-128`
+    if normalize:
+        dens = torch.log(dens + 1)                                            # `:288-289`
+    return torch.cat([dens.view(B, D, Hh, Ww), feats.view(B, D, Hh, Ww)], dim=1)
+
+
+def bev_image(voxel_j):
+    """uint8 (W, H) preview the reference saves as `<index>.png` (`ldm/inference.py:180-181`)."""
+    return (voxel_j.permute(2, 1, 0).cpu().detach().numpy().clip(0, 1) * 255.0).astype(np.uint8)[:, :, 0]

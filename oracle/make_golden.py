@@ -67,6 +67,11 @@ def make_range_to_points():
             p0 = pc[0].cpu().detach().numpy()
             depth = np.linalg.norm(p0[:, :3], 2, axis=1)
             out["masked_rows"] = torch.from_numpy(p0[depth < 90.0, :].copy())
+    # to_voxel (`ldm/dataset.py:278-294`) on a small BEV grid (the reference's default 1x1024x1024 would be an 8 MB
+    # fixture); points outside pc_range exercise the out-of-bounds votes
+    tv = kri.point_cloud_to_range_image_KITTI(grid_sizes=[1, 96, 128], pc_range=[-25.6, -25.6, -3.0, 25.6, 25.6, 1.0])
+    out["voxel"] = tv.to_voxel(img.clone())
+    out["voxel_grid"], out["voxel_range"] = [1, 96, 128], [-25.6, -25.6, -3.0, 25.6, 25.6, 1.0]
     torch.save(out, os.path.join(OUT, "range_to_points.pt"))
     print("range_to_points.pt", {k: tuple(v.shape) for k, v in out.items() if torch.is_tensor(v)})
 

@@ -47,6 +47,8 @@ SIGNATURES = {
     "rldm_sched_step": (c_int, [c_void_p] * 7 + [c_i64, c_void_p]),
     "rldm_range_to_points": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_float,
                                      c_float, c_void_p, c_void_p, c_void_p]),
+    "rldm_points_to_voxel": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p]),
     "rldm_scale": (c_int, [c_void_p, c_float, c_void_p, c_i64, c_void_p]),
     "rldm_ref_to_cl": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rldm_cl_to_ref": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -1197,18 +1197,22 @@ range_to_points_kernel(const float* __restrict__ img, int C, int W, int H, const
     const int w = (idx / H) % W;
     const size_t b = idx / (static_cast<size_t>(H) * W);
     const float v = __ldg(img + (b * C * W + w) * H + h);
+    // every step is rounded separately (__f*_rn: no FMA contraction), like the op-by-op PyTorch reference -- the
+    // azimuth `t * 2 pi - pi` cancels near zero, where a fused multiply-add would move points by tens of microns
     float r;
-    if (mode == 1) r = exp2f(v * 6.0f) - 1.0f;                    // log encoding      (`:241-242`)
-    else if (mode == 2) r = 1.0f / fmaxf(v, 0.0001f);             // inverse encoding  (`:243-244`)
-    else r = v * stdv + mean;                                     // linear            (`:245-246`)
-    if (r < 0.0f) r = fill;                                       // `:256`
-    const float z = sh_rp[2 * H + h] - r * sh_rp[h];              // `:259`
-    const float xy = r * sh_rp[H + h];                            // `:262`
-    // azi = (W - 0.5 - w) / W * 2 pi - pi                          `:266`, same operation order in fp32
-    const float azi = (static_cast<float>(W) - 0.5f - static_cast<float>(w)) / static_cast<float>(W) * 2.0f * 3.14159265358979323846f - 3.14159265358979323846f;
+    if (mode == 1) r = __fsub_rn(exp2f(__fmul_rn(v, 6.0f)), 1.0f);      // log encoding      (`:241-242`)
+    else if (mode == 2) r = __fdiv_rn(1.0f, fmaxf(v, 0.0001f));         // inverse encoding  (`:243-244`)
+    else r = __fadd_rn(__fmul_rn(v, stdv), mean);                       // linear            (`:245-246`)
+    if (r < 0.0f) r = fill;                                             // `:256`
+    const float z = __fsub_rn(sh_rp[2 * H + h], __fmul_rn(r, sh_rp[h]));             // `:259`
+    const float xy = __fmul_rn(r, sh_rp[H + h]);                                     // `:262`
+    // azi = (W - 0.5 - w) / W * 2 pi - pi                                              `:266`, same operation order
+    const float kPi = 3.14159265358979323846f;
+    const float t = __fdiv_rn(__fsub_rn(__fsub_rn(static_cast<float>(W), 0.5f), static_cast<float>(w)), static_cast<float>(W));
+    const float azi = __fsub_rn(__fmul_rn(__fmul_rn(t, 2.0f), kPi), kPi);
     float sa, ca;
     sincosf(azi, &sa, &ca);
-    const float x = xy * ca, y = xy * sa;                         // `:269-270`
+    const float x = __fmul_rn(xy, ca), y = __fmul_rn(xy, sa);                        // `:269-270`
     if (P == 4) {
       const float rem = __ldg(img + ((b * C + 1) * W + w) * H + h);
       *reinterpret_cast<float4*>(points + idx * 4) = make_float4(x, y, z, rem);
@@ -1219,6 +1223,94 @@ range_to_points_kernel(const float* __restrict__ img, int C, int W, int H, const
   }
 }
 }  // namespace rldm
+
+// ------------------------------------------------------------------------------------------------
+// point cloud -> bird's-eye-view volume (`ldm/dataset.py:278-294` to_voxel, `:13-132` _splat_points_to_volumes).
+// splat: thread = one point; its 8 trilinear votes go to the density and feature volumes with float atomics
+// (the reference's 16 scatter_add_ passes).  finalize: thread = one voxel, features / clamp(density), log(density + 1).
+namespace rldm {
+__global__ void __launch_bounds__(256)
+voxel_splat_kernel(const float* __restrict__ points, int P, size_t total, int N, float cx, float cy, float cz, float hx,
+                   float hy, float hz, int D, int Hh, int Ww, float* __restrict__ dens, float* __restrict__ feat) {
+  pdl_entry();
+  const size_t n_vox = static_cast<size_t>(D) * Hh * Ww;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / N;
+    const float* pt = points + i * P;
+    // local volume coordinates in [-1, 1] (`:282-283`), then continuous voxel indices (`:66-68`)
+    const float fx = ((pt[0] - cx) / hx + 1.0f) * 0.5f * static_cast<float>(Ww - 1);
+    const float fy = ((pt[1] - cy) / hy + 1.0f) * 0.5f * static_cast<float>(Hh - 1);
+    const float fz = ((pt[2] - cz) / hz + 1.0f) * 0.5f * static_cast<float>(D - 1);
+    const float f = P > 3 ? pt[3] : 0.0f;
+    const float bx = floorf(fx), by = floorf(fy), bz = floorf(fz);
+    const float rx = fx - bx, ry = fy - by, rz = fz - bz;
+    // indices as 64-bit integers: far-away points (range fill value, inverse encoding) stay out of bounds
+    const long long X = static_cast<long long>(bx), Y = static_cast<long long>(by), Z = static_cast<long long>(bz);
+    float* db = dens + b * n_vox;
+    float* fb = feat + b * n_vox;
+#pragma unroll
+    for (int xd = 0; xd < 2; ++xd) {
+      const float wx = xd ? rx : 1.0f - rx;
+      const long long X_ = X + xd;
+#pragma unroll
+      for (int yd = 0; yd < 2; ++yd) {
+        const float wy = yd ? ry : 1.0f - ry;
+        const long long Y_ = Y + yd;
+#pragma unroll
+        for (int zd = 0; zd < 2; ++zd) {
+          const float wz = zd ? rz : 1.0f - rz;
+          const long long Z_ = Z + zd;
+          if (X_ < 0 || X_ >= Ww || Y_ < 0 || Y_ >= Hh || Z_ < 0 || Z_ >= D) continue;
+          const float w = wx * wy * wz;
+          const size_t idx = (static_cast<size_t>(Z_) * Hh + Y_) * Ww + X_;
+          atomicAdd(db + idx, w);
+          atomicAdd(fb + idx, w * f);
+        }
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+voxel_finalize_kernel(const float* __restrict__ dens, const float* __restrict__ feat, float* __restrict__ voxel,
+                      size_t n_vox, int B, int normalize, float min_weight) {
+  pdl_entry();
+  const size_t total = n_vox * B;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / n_vox, v = i - b * n_vox;
+    const float d = dens[i];
+    voxel[(2 * b) * n_vox + v] = normalize ? logf(d + 1.0f) : d;         // `:288-289`
+    voxel[(2 * b + 1) * n_vox + v] = feat[i] / fmaxf(d, min_weight);       // `:126-128`
+  }
+}
+}  // namespace rldm
+
+extern "C" int rldm_points_to_voxel(const float* points, int B, int N, int P, const float* pc_range6, int D, int Hh, int Ww,
+                                    int normalize, float* scratch, float* voxel, void* stream) {
+  RLDM_CHECK(P == 3 || P == 4, "points_to_voxel: points must have 3 or 4 columns (got %d)", P);
+  RLDM_CHECK(D >= 1 && Hh >= 1 && Ww >= 1, "points_to_voxel: bad grid");
+  const size_t n_vox = static_cast<size_t>(D) * Hh * Ww;
+  if (B == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  const int rc = zero_fill(scratch, 2 * n_vox * B * sizeof(float), st);
+  if (rc) return rc;
+  const float cx = (pc_range6[3] + pc_range6[0]) / 2, cy = (pc_range6[4] + pc_range6[1]) / 2, cz = (pc_range6[5] + pc_range6[2]) / 2;
+  const float hx = (pc_range6[3] - pc_range6[0]) / 2, hy = (pc_range6[4] - pc_range6[1]) / 2, hz = (pc_range6[5] - pc_range6[2]) / 2;
+  const size_t total = static_cast<size_t>(B) * N;
+  if (total) {
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    RLDM_CUDA(launch_pdl(voxel_splat_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, points, P, total, N, cx, cy,
+                         cz, hx, hy, hz, D, Hh, Ww, scratch, scratch + n_vox * B));
+  }
+  size_t blocks = (n_vox * B + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  RLDM_CUDA(launch_pdl(voxel_finalize_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, scratch,
+                       scratch + n_vox * B, voxel, n_vox, B, normalize, 1e-4f));
+  RLDM_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int rldm_range_to_points(const float* img, int B, int C, int W, int H, const float* incl, const float* height,
                                     int mode, float mean, float stdv, float fill, float* points, float* depth,

@@ -1,5 +1,5 @@
 """Range image -> point cloud on the GPU: the host-side mirror of the reference's
-`point_cloud_to_range_image.to_pc_torch` (`ldm/dataset.py:228-276`) and of the `.bin` writer loop of
+`point_cloud_to_range_image.to_pc_torch` / `to_voxel` (`ldm/dataset.py:228-294`) and of the `.bin` writer loop of
 `ldm/inference.py:174-179`.
 
 The sensor tables (`incl`, `height`, e.g. `ldm/kitti360_range_image.py:19-48`) are DATA supplied by the caller:
@@ -16,7 +16,9 @@ MODE_LINEAR, MODE_LOG, MODE_INVERSE = 0, 1, 2
 
 
 class RangeImageGeometry:
-    def __init__(self, incl, height, log=False, inverse=False, mean=20.0, std=40.0, range_fill_value=(100, 0)):
+    def __init__(self, incl, height, log=False, inverse=False, mean=20.0, std=40.0, range_fill_value=(100, 0),
+                 grid_sizes=(1, 1024, 1024), pc_range=(-25.6, -25.6, -3.0, 25.6, 25.6, 1.0),
+                 normalize_volume_densities=True):
         self.incl = np.ascontiguousarray(np.asarray(incl, dtype=np.float32))
         self.height = np.ascontiguousarray(np.asarray(height, dtype=np.float32))
         if self.incl.shape != self.height.shape or self.incl.ndim != 1:
@@ -24,13 +26,17 @@ class RangeImageGeometry:
         self.log, self.inverse = bool(log), bool(inverse)
         self.mean, self.std = float(mean), float(std)
         self.range_fill_value = np.asarray(range_fill_value)
+        self.grid_sizes = [int(g) for g in grid_sizes]                       # (D, H, W) as in `ldm/dataset.py:137`
+        self.pc_range = [float(v) for v in pc_range]
+        self.normalize_volume_densities = bool(normalize_volume_densities)
         self._dev = {}
 
     @classmethod
     def from_reference(cls, to_range):
         """Build from a reference `point_cloud_to_range_image*` instance (`ldm/inference.py:81`)."""
         return cls(to_range.incl, to_range.height, log=to_range.log, inverse=to_range.inverse, mean=to_range.mean,
-                   std=to_range.std, range_fill_value=to_range.range_fill_value)
+                   std=to_range.std, range_fill_value=to_range.range_fill_value, grid_sizes=to_range.grid_sizes,
+                   pc_range=to_range.pc_range, normalize_volume_densities=to_range.normalize_volume_densities)
 
     @property
     def mode(self):
@@ -56,6 +62,25 @@ class RangeImageGeometry:
         _lib.call("rldm_range_to_points", _lib.ptr(x), B, C, W, H, _lib.ptr(incl), _lib.ptr(height), self.mode, self.mean,
                   self.std, float(self.range_fill_value[0]), _lib.ptr(pts), _lib.ptr(depth))
         return (pts, depth) if return_depth else pts
+
+    def to_voxel(self, range_images):
+        """`to_voxel` (`ldm/dataset.py:278-294`): (B, C, W, H) range images -> (B, 2*D, Hg, Wg) bird's-eye-view volume
+        [log-densities, remission features] by trilinear splatting of the point cloud (`ldm/inference.py:172`)."""
+        import ctypes
+        pts = self.to_pc_torch(range_images)
+        B, N, P = pts.shape
+        D, Hg, Wg = self.grid_sizes
+        scratch = torch.empty((2, B, D * Hg * Wg), device=pts.device)
+        voxel = torch.empty((B, 2 * D, Hg, Wg), device=pts.device)
+        rng = (ctypes.c_float * 6)(*self.pc_range)
+        _lib.call("rldm_points_to_voxel", _lib.ptr(pts), B, N, P, rng, D, Hg, Wg, int(self.normalize_volume_densities),
+                  _lib.ptr(scratch), _lib.ptr(voxel))
+        return voxel
+
+    @staticmethod
+    def bev_image(voxel_j):
+        """uint8 (Wg, Hg) preview image the reference saves as `<index>.png` (`ldm/inference.py:180-181`)."""
+        return (voxel_j.permute(2, 1, 0).cpu().detach().numpy().clip(0, 1) * 255.0).astype(np.uint8)[:, :, 0]
 
     def masked_points(self, range_images, max_depth=90.0):
         """Per sample the float32 (N_i, 3|4) arrays the reference writes (`ldm/inference.py:175-179`): rows with

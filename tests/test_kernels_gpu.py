@@ -460,3 +460,54 @@ def test_range_to_points_matches_reference_golden(L, golden, tmp_path):
     assert rows.shape == want.shape and np.allclose(rows, want, rtol=1e-5, atol=1e-4)
     with pytest.raises(RuntimeError):
         geom.to_pc_torch(img)                                                    # CPU tensor: no fallback
+
+
+def test_points_to_voxel_matches_reference_golden(L, golden):
+    """rldm_points_to_voxel against the reference's own to_voxel output: (1) the splat kernel alone, fed the reference's
+    points: agreement to float-atomic rounding order; (2) chained behind rldm_range_to_points (RangeImageGeometry.to_voxel),
+    where the ~2 ulp libm difference of the point coordinates (CUDA sincosf vs the CPU's cosf, 8e-6 m at 60 m range) is
+    amplified by the voxel pitch; (3) the reference's default 1x1024x1024 BEV grid at KITTI size against the CPU oracle."""
+    import ctypes
+    import rangeldm_b200 as R
+    from oracle import geometry as G
+    d = golden("range_to_points.pt")
+    D, Hg, Wg = d["voxel_grid"]
+
+    def check(v, ref, name, tol):
+        """log-densities to `tol`; features are a ratio that is ill-conditioned where the total vote weight is ~1e-4
+        (a 1e-6-voxel shift of one point moves it by 1e-3 there, in the reference too), so they are compared as the
+        well-conditioned weighted sums feature * clamp(density)."""
+        assert v.shape == ref.shape
+        Dd = v.shape[1] // 2
+        assert relerr(v[:, :Dd].cpu(), ref[:, :Dd], name + "_density") < tol
+        w = torch.expm1(ref[:, :Dd]).clamp(min=1e-4)
+        assert relerr(v[:, Dd:].cpu() * w, ref[:, Dd:] * w, name + "_weighted_feature") < 2 * tol
+
+    # (1) splat + finalize kernels alone
+    pts = d["linear"].cuda().contiguous()
+    B, N, P = pts.shape
+    scratch = torch.empty((2, B, D * Hg * Wg), device="cuda")
+    vox = torch.empty((B, 2 * D, Hg, Wg), device="cuda")
+    rng = (ctypes.c_float * 6)(*d["voxel_range"])
+    L.call("rldm_points_to_voxel", L.ptr(pts), B, N, P, rng, D, Hg, Wg, 1, L.ptr(scratch), L.ptr(vox))
+    check(vox, d["voxel"], "to_voxel_kernel", 1e-6)
+    assert (vox[:, D:].cpu() - d["voxel"][:, D:]).abs().max() < 1e-3
+    # (2) range image -> points -> volume
+    geom = R.RangeImageGeometry(d["incl"].numpy(), d["height"].numpy(), mean=d["mean"], std=d["std"],
+                                grid_sizes=d["voxel_grid"], pc_range=d["voxel_range"])
+    v = geom.to_voxel(d["image"].cuda())
+    check(v, d["voxel"], "to_voxel_golden", 5e-5)
+    assert (R.RangeImageGeometry.bev_image(v[0]) == G.bev_image(d["voxel"][0])).mean() > 0.999   # uint8 truncation ties
+    # (3) default BEV grid (0.05 m pitch), KITTI image size
+    geom = R.RangeImageGeometry(d["incl"].numpy(), d["height"].numpy())
+    img = torch.rand(2, 2, 1024, 64, generator=torch.Generator().manual_seed(3)) * 1.2 - 0.45
+    v = geom.to_voxel(img.cuda())
+    ref = G.to_voxel(img, d["incl"], d["height"])
+    assert v.shape == (2, 2, 1024, 1024)
+    check(v, ref, "to_voxel_kitti", 5e-4)
+    # un-normalised densities: total vote weight == number of points that fall inside the grid (z is a single layer)
+    geom.normalize_volume_densities = False
+    dens = geom.to_voxel(img.cuda())[:, 0]
+    pts = G.to_points(img, d["incl"], d["height"])
+    inside = ((pts[..., 0].abs() <= 25.6) & (pts[..., 1].abs() <= 25.6)).sum(1).float()
+    assert torch.allclose(dens.sum((1, 2)).cpu(), inside, rtol=2e-3)

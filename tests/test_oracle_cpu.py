@@ -125,3 +125,13 @@ def test_geometry_oracle_matches_reference_to_pc_torch(golden):
     # edge cases: single channel -> (x, y, z) only; empty batch
     assert G.to_points(d["image"][:, :1], d["incl"], d["height"]).shape == (2, 96 * 64, 3)
     assert G.to_points(d["image"][:0], d["incl"], d["height"]).shape == (0, 96 * 64, 4)
+
+
+def test_geometry_oracle_matches_reference_to_voxel(golden):
+    """oracle to_voxel == the reference's `to_voxel` / `_splat_points_to_volumes` (`ldm/dataset.py:13-132,278-294`)."""
+    from oracle import geometry as G
+    d = golden("range_to_points.pt")
+    v = G.to_voxel(d["image"], d["incl"], d["height"], G.MODE_LINEAR, d["mean"], d["std"], d["fill"],
+                   tuple(d["voxel_grid"]), tuple(d["voxel_range"]))
+    assert v.shape == d["voxel"].shape and torch.allclose(v, d["voxel"], rtol=0, atol=1e-6)
+    assert G.bev_image(v[0]).shape == (128, 96) and G.bev_image(v[0]).dtype.name == "uint8"
