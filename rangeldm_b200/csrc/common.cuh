@@ -221,6 +221,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B
   return d;
 }
+// The same for SWIZZLE_64B: rows of 64 B (32 fp16), 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);   // start address  [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                      // LBO (ignored for swizzled K-major)
+  d |= static_cast<uint64_t>(512 >> 4) << 32;               // SBO = 512 B    [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                      // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(4) << 61;                      // SWIZZLE_64B
+  return d;
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): fp16 x fp16 -> fp32, K-major A and B.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
   return (1u << 4) /*c=f32*/ | (0u << 7) /*a=f16*/ | (0u << 10) /*b=f16*/ | ((N >> 3) << 17) |

@@ -543,12 +543,17 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
 // stream into the SM (~64 B/clk: a 64 KB stage lands in ~1000 cycles while its 12 MMAs need 768); sharing B over two
 // tiles cuts the bytes per MMA by 25 % (48 KB per 12 MMAs), which makes the loop MMA-bound, and it halves the number
 // of units (256 tiles -> 128 units: one wave on 148 SMs instead of 1.73).  TMEM: 2 units x MT x BLOCK_N columns.
-template <int BLOCK_N, int STAGES, int TERMS, int MT>
+// KB = 32 (opt-in experiment): a stage carries half a 64-channel chunk (SWIZZLE_64B operand tiles, two K steps).  With
+// MT = 2 a 64-wide stage is 96 KB and only two fit; 48 KB half-stages give a 4-deep ring, but measured slower.
+template <int BLOCK_N, int STAGES, int TERMS, int MT, int KB>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
-  constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static_assert(KB == 64 || KB == 32, "stage depth along K: one 128 B swizzle row or half of it");
+  constexpr int kSub = kBlockK / KB;                            // stages per 64-channel chunk
+  constexpr int kAB = kBlockM * KB * 2;                         // one operand part of one M tile
+  constexpr int kBBytes = BLOCK_N * KB * 2;
   constexpr int kParts = TERMS == 1 ? 1 : 2;
-  constexpr int kATile = kParts * kABytes;                      // one M tile of a stage: [A_hi][A_lo]
+  constexpr int kATile = kParts * kAB;                          // one M tile of a stage: [A_hi][A_lo]
   constexpr int kStageBytes = MT * kATile + kParts * kBBytes;
   constexpr int kBOff = MT * kATile;
   constexpr int kSlabPitch = 36;                                // floats per row of the 32-column staging slab
@@ -575,7 +580,7 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
   const int tiles_m = (p.M_total + kBlockM - 1) / kBlockM;      // a multiple of MT (host)
   const int total_units = (tiles_m / MT) * tiles_n;
   const int taps = p.ks * p.ks;
-  const int n_it = p.total_iters;
+  const int n_it = p.total_iters * kSub;
 
   pdl_trigger_conv_early();
   if (warp == 0 && lane == 0) {
@@ -621,10 +626,12 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
       for (int it = 0; it < n_it; ++it, ++g) {
         const int s = g % STAGES;
         mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
-        const bool main = it < p.main_iters;
-        const int chunk = main ? it / taps : it - p.main_iters;
-        const int tap = it - chunk * taps;
+        const int it64 = it / kSub, sub = it - it64 * kSub;      // 64-channel K step and the KB-wide part of it
+        const bool main = it64 < p.main_iters;
+        const int chunk = main ? it64 / taps : it64 - p.main_iters;
+        const int tap = it64 - chunk * taps;
         const int ti = tap / p.ks, tj = tap - ti * p.ks;
+        const int kc = chunk * kBlockK + sub * KB;                 // first channel of this stage
         const uint32_t a_dst = smem_u32(smem + s * kStageBytes);
         // shortcut K steps: centre tap of the second tensor (1x1, stride 1, same grid as the output)
         const int h_in = main ? tj - p.pad_lo : 0;
@@ -633,20 +640,19 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
         if (lane == 0) {
           mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
           if (main) {
-            tma_load_2d(a_dst + kBOff, &tm.b, &full_bar[s], chunk * kBlockK, tap * p.Cout + n0);
+            tma_load_2d(a_dst + kBOff, &tm.b, &full_bar[s], kc, tap * p.Cout + n0);
             if (TERMS > 1)
-              tma_load_2d(a_dst + kBOff + kBBytes, &tm.b, &full_bar[s], chunk * kBlockK, (taps + tap) * p.Cout + n0);
+              tma_load_2d(a_dst + kBOff + kBBytes, &tm.b, &full_bar[s], kc, (taps + tap) * p.Cout + n0);
           } else {
-            tma_load_2d(a_dst + kBOff, &tm.b2, &full_bar[s], chunk * kBlockK, n0);
-            if (TERMS > 1) tma_load_2d(a_dst + kBOff + kBBytes, &tm.b2, &full_bar[s], chunk * kBlockK, p.Cout + n0);
+            tma_load_2d(a_dst + kBOff, &tm.b2, &full_bar[s], kc, n0);
+            if (TERMS > 1) tma_load_2d(a_dst + kBOff + kBBytes, &tm.b2, &full_bar[s], kc, p.Cout + n0);
           }
         }
         // lanes 1.. : one box per (M tile, operand part)
         if (lane >= 1 && lane <= MT * kParts) {
           const int mt = (lane - 1) / kParts, part = (lane - 1) % kParts;
           const CUtensorMap* map = main ? (part ? &tm.alo : &tm.a) : (part ? &tm.a2lo : &tm.a2);
-          tma_load_4d(a_dst + mt * kATile + part * kABytes, map, &full_bar[s], chunk * kBlockK, h_in,
-                      w_mul * wo0[mt] + w_off, b0[mt]);
+          tma_load_4d(a_dst + mt * kATile + part * kAB, map, &full_bar[s], kc, h_in, w_mul * wo0[mt] + w_off, b0[mt]);
         }
         __syncwarp();
       }
@@ -666,19 +672,20 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
           mbar_wait(&full_bar[s], (g / STAGES) & 1);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
-          const uint64_t b_desc = umma_desc_sw128(a_addr + kBOff);
-          const uint64_t bl_desc = umma_desc_sw128(a_addr + kBOff + kBBytes);
+          auto desc = [](uint32_t addr) { return KB == 64 ? umma_desc_sw128(addr) : umma_desc_sw64(addr); };
+          const uint64_t b_desc = desc(a_addr + kBOff);
+          const uint64_t bl_desc = desc(a_addr + kBOff + kBBytes);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             const uint32_t d_tmem = tmem_base + acc * kAccCols + mt * BLOCK_N;
-            const uint64_t a_desc = umma_desc_sw128(a_addr + mt * kATile);
+            const uint64_t a_desc = desc(a_addr + mt * kATile);
 #pragma unroll
-            for (int kk = 0; kk < kBlockK / 16; ++kk)
+            for (int kk = 0; kk < KB / 16; ++kk)
               umma_f16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (it | kk) != 0);
             if (TERMS > 1) {
-              const uint64_t al_desc = umma_desc_sw128(a_addr + mt * kATile + kABytes);
+              const uint64_t al_desc = desc(a_addr + mt * kATile + kAB);
 #pragma unroll
-              for (int kk = 0; kk < kBlockK / 16; ++kk) {
+              for (int kk = 0; kk < KB / 16; ++kk) {
                 umma_f16(d_tmem, al_desc + 2 * kk, b_desc + 2 * kk, idesc, 1u);
                 umma_f16(d_tmem, a_desc + 2 * kk, bl_desc + 2 * kk, idesc, 1u);
               }
@@ -1031,18 +1038,18 @@ static int launch_conv(const ConvMaps& tm, const ConvParams& p, int split, cudaS
   }
 }
 
-template <int BLOCK_N, int STAGES, int TERMS, int MT>
+template <int BLOCK_N, int STAGES, int TERMS, int MT, int KB>
 static int launch_conv_persistent(const ConvMaps& tm, const ConvParams& p, int n_ctas, cudaStream_t st) {
-  constexpr int smem = STAGES * (TERMS == 1 ? 1 : 2) * (MT * kABytes + BLOCK_N * kBlockK * 2) + kBlockM * 36 * 4 + 256 +
+  constexpr int smem = STAGES * (TERMS == 1 ? 1 : 2) * (MT * kBlockM + BLOCK_N) * KB * 2 + kBlockM * 36 * 4 + 256 +
                        2 * 4 * (BLOCK_N / 2) * 4 + 64 + 1024;
   static_assert(smem <= 232448, "persistent conv: shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
-    RLDM_CUDA(cudaFuncSetAttribute(conv_tc_persistent_kernel<BLOCK_N, STAGES, TERMS, MT>,
+    RLDM_CUDA(cudaFuncSetAttribute(conv_tc_persistent_kernel<BLOCK_N, STAGES, TERMS, MT, KB>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  RLDM_CUDA(launch_pdl(conv_tc_persistent_kernel<BLOCK_N, STAGES, TERMS, MT>, dim3(n_ctas), dim3(192), smem, st, tm, p));
+  RLDM_CUDA(launch_pdl(conv_tc_persistent_kernel<BLOCK_N, STAGES, TERMS, MT, KB>, dim3(n_ctas), dim3(192), smem, st, tm, p));
   return 0;
 }
 
@@ -1201,47 +1208,51 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
   }
   ConvMaps tm;
   // activation maps: (C, H, W+2, B) fp16, box = (64 channels, Ho*stride rows, ncols*stride columns, nb images)
+  int KB = kBlockK;     // channels per pipeline stage: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B), chosen below
   auto encode_act = [&](CUtensorMap* m, const uint16_t* ptr, int C, int st) -> CUresult {
     cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)(W + 2), (cuuint64_t)B};
     cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)H * C * 2, (cuuint64_t)(W + 2) * H * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(Ho * st), (cuuint32_t)(ncols * st), (cuuint32_t)nb};
+    cuuint32_t box[4] = {(cuuint32_t)KB, (cuuint32_t)(Ho * st), (cuuint32_t)(ncols * st), (cuuint32_t)nb};
     cuuint32_t estr[4] = {1, (cuuint32_t)st, (cuuint32_t)st, 1};
     return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<uint16_t*>(ptr), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   };
   // weight maps: [planes*taps*Cout][C] fp16, box = (64 channels, BN rows)
   auto encode_wgt = [&](CUtensorMap* m, const uint16_t* ptr, int C, int rows) -> CUresult {
     cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)C * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
+    cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
     return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(ptr), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   };
-  CUresult r = encode_act(&tm.a, x, Cin, stride);
-  RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(A) failed: %d", (int)r);
-  if (parts == 2) {
-    r = encode_act(&tm.alo, x_lo, Cin, stride);
-    RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(A lo) failed: %d", (int)r);
-  } else {
-    tm.alo = tm.a;
-  }
-  r = encode_wgt(&tm.b, wgt, Cin, parts * ks * ks * Cout);
-  RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r);
-  tm.a2 = tm.a; tm.a2lo = tm.alo; tm.b2 = tm.b;
-  if (sc_x) {
-    r = encode_act(&tm.a2, sc_x, sc_cin, 1);
-    RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(shortcut A) failed: %d", (int)r);
-    tm.a2lo = tm.a2;
+  auto build_maps = [&]() -> int {
+    CUresult r = encode_act(&tm.a, x, Cin, stride);
+    RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(A) failed: %d", (int)r);
     if (parts == 2) {
-      r = encode_act(&tm.a2lo, sc_x_lo, sc_cin, 1);
-      RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(shortcut A lo) failed: %d", (int)r);
+      r = encode_act(&tm.alo, x_lo, Cin, stride);
+      RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(A lo) failed: %d", (int)r);
+    } else {
+      tm.alo = tm.a;
     }
-    r = encode_wgt(&tm.b2, sc_wgt, sc_cin, parts * Cout);
-    RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(shortcut B) failed: %d", (int)r);
-  }
+    r = encode_wgt(&tm.b, wgt, Cin, parts * ks * ks * Cout);
+    RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+    tm.a2 = tm.a; tm.a2lo = tm.alo; tm.b2 = tm.b;
+    if (sc_x) {
+      r = encode_act(&tm.a2, sc_x, sc_cin, 1);
+      RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(shortcut A) failed: %d", (int)r);
+      tm.a2lo = tm.a2;
+      if (parts == 2) {
+        r = encode_act(&tm.a2lo, sc_x_lo, sc_cin, 1);
+        RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(shortcut A lo) failed: %d", (int)r);
+      }
+      r = encode_wgt(&tm.b2, sc_wgt, sc_cin, parts * Cout);
+      RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(shortcut B) failed: %d", (int)r);
+    }
+    return 0;
+  };
   ConvParams p;
   p.bias = bias; p.temb = temb; p.residual = residual; p.out = out;
   p.temb_stride = temb_stride;
@@ -1286,12 +1297,24 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
     const int units = mt2 ? tiles / 2 : tiles;
     const int ctas = units < n_sms ? units : n_sms;
     if (mt2) {
-      if (BN == 128) return launch_conv_persistent<128, 2, 3, 2>(tm, p, ctas, st);
-      return launch_conv_persistent<64, 2, 3, 2>(tm, p, ctas, st);
+      // RLDM_CONV_KB32=1: half-chunk stages (SWIZZLE_64B, 48 KB) in a 4-deep ring instead of two 96 KB stages.
+      // Measured slower on B200 (decoder convs 3.24 -> 3.62 ms): 64 B TMA rows move the same bytes less efficiently
+      // than 128 B rows, which costs more than the deeper ring gains.  Kept as an experiment switch.
+      if (getenv("RLDM_CONV_KB32")) {
+        KB = 32;
+        if (int rc = build_maps()) return rc;
+        if (BN == 128) return launch_conv_persistent<128, 4, 3, 2, 32>(tm, p, ctas, st);
+        return launch_conv_persistent<64, 4, 3, 2, 32>(tm, p, ctas, st);
+      }
+      if (int rc = build_maps()) return rc;
+      if (BN == 128) return launch_conv_persistent<128, 2, 3, 2, 64>(tm, p, ctas, st);
+      return launch_conv_persistent<64, 2, 3, 2, 64>(tm, p, ctas, st);
     }
-    if (BN == 128) return launch_conv_persistent<128, 3, 3, 1>(tm, p, ctas, st);
-    return launch_conv_persistent<64, 4, 3, 1>(tm, p, ctas, st);
+    if (int rc = build_maps()) return rc;
+    if (BN == 128) return launch_conv_persistent<128, 3, 3, 1, 64>(tm, p, ctas, st);
+    return launch_conv_persistent<64, 4, 3, 1, 64>(tm, p, ctas, st);
   }
+  if (int rc = build_maps()) return rc;
   if (parts == 2) {
     if (BN == 128) return launch_conv<128, 3, 3>(tm, p, split, st);
     return launch_conv<64, 4, 3>(tm, p, split, st);
