@@ -209,6 +209,17 @@ int rldm_range_to_points(const float* img, int B, int C, int W, int H, const flo
 int rldm_points_to_voxel(const float* points, int B, int N, int P, const float* pc_range6, int D, int Hh, int Ww,
                          int normalize, float* scratch, float* voxel, void* stream);
 
+/* ---- point cloud -> range image --------------------------------------------
+ * Replaces `point_cloud_to_range_image.__call__` + `process_miss_value` + `normalize` (`ldm/dataset.py:159-226`) with
+ * the KITTI beam assignment of `ldm/kitti360_range_image.py:51-61`, i.e. the sample `RangeDataset.__getitem__` builds
+ * (`:327-336`).  pc (N,4) fp32 x,y,z,remission (16 B aligned); incl/height per-beam tables (length H).  The nearest
+ * return of a pixel wins (equal ranges: the lower point index).  keys: H*W uint64 scratch.
+ * image (2, W, H) fp32 = [encoded range (mode as in rldm_range_to_points; linear is (r - mean)/std), remission];
+ * mask, car_window (W, H) uint8 = `range_image_mask`, `car_window_mask`. */
+int rldm_points_to_range(const float* pc, int N, const float* incl, const float* height, int H, int W, int mode,
+                         float mean, float stdv, float fill_range, float fill_rem, unsigned long long* keys,
+                         float* image, unsigned char* mask, unsigned char* car_window, void* stream);
+
 /* y = a*x (elementwise, fp32), e.g. latents / scaling_factor (`ldm/pipelines.py:365`). */
 int rldm_scale(const float* x, float a, float* y, int64_t n, void* stream);
 

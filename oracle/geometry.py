@@ -90,3 +90,65 @@ def to_voxel(range_images, incl, height, mode=MODE_LINEAR, mean=20.0, std=40.0, 
 def bev_image(voxel_j):
     """uint8 (W, H) preview the reference saves as `<index>.png` (`ldm/inference.py:180-181`)."""
     return (voxel_j.permute(2, 1, 0).cpu().detach().numpy().clip(0, 1) * 255.0).astype(np.uint8)[:, :, 0]
+
+
+def kitti_row_inds(pc, incl, height):
+    """`point_cloud_to_range_image_KITTI.get_row_inds` (`ldm/kitti360_range_image.py:51-61`): beam whose inclination is
+    closest to the elevation of the point seen from that beam's height."""
+    xy_norm = np.linalg.norm(pc[:, :2], ord=2, axis=1)
+    err = [np.abs(incl[i] - np.arctan2(height[i] - pc[:, 2], xy_norm)) for i in range(len(incl))]
+    return np.argmin(np.stack(err, axis=-1), axis=-1)
+
+
+def points_to_range_image(pc, incl, height, width=1024, mode=MODE_LINEAR, mean=20.0, std=40.0, fill=(100.0, 0.0)):
+    """Point cloud (N,4) float32 -> the dataset sample of `RangeDataset.__getitem__` (`ldm/dataset.py:327-336`):
+    projection `__call__` (`:159-183`, nearest return wins), `process_miss_value` (`:193-221`), `normalize`
+    (`:223-226`).  Returns (image (2, W, H), mask (W, H), car_window_mask (W, H))."""
+    pc = np.array(pc, dtype=np.float32, copy=True)
+    incl = np.asarray(incl, dtype=np.float32)
+    height = np.asarray(height, dtype=np.float32)
+    fill = np.asarray(fill)
+    H = len(incl)
+    row = kitti_row_inds(pc, incl, height)                                                  # `:160`
+    azi = np.arctan2(pc[:, 1], pc[:, 0])
+    col = width - 1.0 + 0.5 - (azi + np.pi) / (2.0 * np.pi) * width                         # `:163`
+    col = np.round(col).astype(np.int32)
+    col[col == width] = width - 1
+    col[col < 0] = 0
+    img = np.full((H, width, 2), -1, dtype=np.float32)
+    pc[:, 2] -= height[row]                                                                 # `:168`
+    rng = np.linalg.norm(pc[:, :3], axis=1, ord=2)
+    rng[rng > fill[0]] = fill[0]
+    order = np.argsort(-rng, kind="stable")                                                 # `:172` (ties: see tests)
+    if mode == MODE_LOG:
+        val = np.log2(rng[order] + 1) / 6
+    elif mode == MODE_INVERSE:
+        val = 1 / rng[order]
+    else:
+        val = rng[order]
+    img[row[order], col[order], :] = np.concatenate([val[:, None], pc[order][:, 3:4]], axis=1)   # `:183` last wins
+    # ---- process_miss_value (`:193-221`)
+    mask = img[..., 0] > 0
+    miss = img[:, :, 0] == -1
+    shift = list(range(1, width)) + [0]
+    img1 = img.copy()
+    img1[miss, :] = img[:, shift, :][miss, :]
+    mask1 = mask.copy()
+    mask1[miss] = mask[:, shift][miss]
+    still = img1[:, :, 0] == -1
+    r0 = img1[:, :, 0]
+    down = r0[[H - 2, H - 1] + list(range(H - 2)), :]
+    top = r0[list(range(2, H)) + [0, 1], :]
+    right = r0[:, [width - 2, width - 1] + list(range(width - 2))]
+    left = r0[:, list(range(2, width)) + [0, 1]]
+    car = still & ((down != -1) | (top != -1) | (right != -1) | (left != -1))
+    if mode == MODE_LOG:
+        img1[still, :] = np.log2(fill + 1) / 6
+    elif mode == MODE_INVERSE:
+        img1[still, :] = np.array([1 / fill[0], fill[1]])
+    else:
+        img1[still, :] = fill
+    if mode == MODE_LINEAR:                                                                 # `:223-226`
+        img1[..., 0] = (img1[..., 0] - mean) / std
+    return (torch.from_numpy(img1).permute(2, 1, 0).contiguous(), torch.from_numpy(mask1).permute(1, 0).contiguous(),
+            torch.from_numpy(car).permute(1, 0).contiguous())

@@ -72,6 +72,27 @@ def make_range_to_points():
     tv = kri.point_cloud_to_range_image_KITTI(grid_sizes=[1, 96, 128], pc_range=[-25.6, -25.6, -3.0, 25.6, 25.6, 1.0])
     out["voxel"] = tv.to_voxel(img.clone())
     out["voxel_grid"], out["voxel_range"] = [1, 96, 128], [-25.6, -25.6, -3.0, 25.6, 25.6, 1.0]
+    # projection point cloud -> range image (`ldm/dataset.py:159-226,327-336`): a synthetic scan with holes (missing
+    # azimuth sectors and beams), duplicates per pixel (nearest must win) and ranges below the 100 m fill value
+    gp = torch.Generator().manual_seed(31)
+    trp = kri.point_cloud_to_range_image_KITTI(width=128)
+    n = 6000
+    r = torch.rand(n, generator=gp) * 70 + 2
+    beam = torch.randint(4, 60, (n,), generator=gp)
+    az = torch.rand(n, generator=gp) * 5.2 - 2.6                     # leaves an empty sector around +-pi
+    inc = torch.from_numpy(trp.incl.copy())[beam] + (torch.rand(n, generator=gp) - 0.5) * 0.004
+    hb = torch.from_numpy(trp.height.copy())[beam]
+    pts = torch.stack([r * torch.cos(inc) * torch.cos(az), r * torch.cos(inc) * torch.sin(az), hb - r * torch.sin(inc),
+                       torch.rand(n, generator=gp)], 1).numpy().astype("float32")
+    for name, kw in (("linear", {}), ("log", {"log": True}), ("inverse", {"inverse": True})):
+        t = kri.point_cloud_to_range_image_KITTI(width=128, **kw)
+        ri = t(pts.copy())
+        ri, m, cw = t.process_miss_value(ri)
+        ri = t.normalize(ri)
+        out["proj_" + name] = torch.from_numpy(ri).permute(2, 1, 0).contiguous()
+        out["proj_mask_" + name] = torch.from_numpy(m).permute(1, 0).contiguous()
+        out["proj_car_" + name] = torch.from_numpy(cw).permute(1, 0).contiguous()
+    out["proj_points"] = torch.from_numpy(pts)
     torch.save(out, os.path.join(OUT, "range_to_points.pt"))
     print("range_to_points.pt", {k: tuple(v.shape) for k, v in out.items() if torch.is_tensor(v)})
 

@@ -49,6 +49,8 @@ SIGNATURES = {
                                      c_float, c_void_p, c_void_p, c_void_p]),
     "rldm_points_to_voxel": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p]),
+    "rldm_points_to_range": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float,
+                                     c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rldm_scale": (c_int, [c_void_p, c_float, c_void_p, c_i64, c_void_p]),
     "rldm_ref_to_cl": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rldm_cl_to_ref": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -1312,6 +1312,126 @@ extern "C" int rldm_points_to_voxel(const float* points, int B, int N, int P, co
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// point cloud -> range image (`ldm/dataset.py:159-226`: projection, miss-value fill, normalisation).
+// project: thread = one point: beam = argmin |incl_i - atan2(h_i - z, |xy|)| (`kitti360_range_image.py:51-61`), column
+//   from the azimuth (round-half-even like np.round), range with the beam's height removed; the NEAREST return of a
+//   pixel wins (the reference sorts by descending range and lets the last assignment win) = 64-bit atomicMin on
+//   (range bits << 32 | point index).
+// resolve: thread = one pixel: decode the winner, fill holes from the right neighbour (`fill_noise`), remaining holes
+//   get the fill value, car-window mask from the 2-pixel neighbourhood, range encoding + normalisation, written in
+//   the (C, W, H) layout of the dataset sample.
+namespace rldm {
+__global__ void __launch_bounds__(256)
+range_project_kernel(const float* __restrict__ pc, int N, const float* __restrict__ incl, const float* __restrict__ height,
+                     int H, int W, float fill_range, unsigned long long* __restrict__ keys) {
+  extern __shared__ float sh_pr[];      // incl[H], height[H]
+  pdl_entry();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) { sh_pr[i] = __ldg(incl + i); sh_pr[H + i] = __ldg(height + i); }
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const float4 p = __ldg(reinterpret_cast<const float4*>(pc) + i);
+    const float xy = sqrtf(__fadd_rn(__fmul_rn(p.x, p.x), __fmul_rn(p.y, p.y)));
+    int row = 0;
+    float best = INFINITY;
+    for (int r = 0; r < H; ++r) {                       // first minimum, like np.argmin
+      const float e = fabsf(__fsub_rn(sh_pr[r], atan2f(__fsub_rn(sh_pr[H + r], p.z), xy)));
+      if (e < best) { best = e; row = r; }
+    }
+    const float azi = atan2f(p.y, p.x);
+    const float kPi = 3.14159265358979323846f;
+    // col = W - 1.0 + 0.5 - (azi + pi) / (2 pi) * W     (`:163`), rounded half to even (`np.round`)
+    const float cf = __fsub_rn(__fadd_rn(__fsub_rn(static_cast<float>(W), 1.0f), 0.5f),
+                               __fmul_rn(__fdiv_rn(__fadd_rn(azi, kPi), __fmul_rn(2.0f, kPi)), static_cast<float>(W)));
+    int col = static_cast<int>(rintf(cf));
+    if (col == W) col = W - 1;
+    if (col < 0) col = 0;
+    const float z = __fsub_rn(p.z, sh_pr[H + row]);                                      // `:168`
+    float rng = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(p.x, p.x), __fmul_rn(p.y, p.y)), __fmul_rn(z, z)));
+    if (rng > fill_range) rng = fill_range;                                              // `:170`
+    const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(rng)) << 32) | static_cast<unsigned>(i);
+    atomicMin(keys + static_cast<size_t>(row) * W + col, key);
+  }
+}
+__device__ __forceinline__ float2 range_pixel(const unsigned long long* keys, const float* pc, int H, int W, int h, int w,
+                                              int mode) {
+  const unsigned long long k = keys[static_cast<size_t>(h) * W + w];
+  if (k == ~0ull) return make_float2(-1.0f, -1.0f);
+  const float rng = __uint_as_float(static_cast<unsigned>(k >> 32));
+  const float rem = __ldg(pc + static_cast<size_t>(static_cast<unsigned>(k)) * 4 + 3);
+  float v = rng;
+  if (mode == 1) v = __fdiv_rn(log2f(__fadd_rn(rng, 1.0f)), 6.0f);
+  else if (mode == 2) v = __fdiv_rn(1.0f, rng);
+  return make_float2(v, rem);
+}
+// value after `fill_noise` (`:186-190`): a hole takes its right neighbour (circular in w), from the ORIGINAL image
+__device__ __forceinline__ float2 range_filled(const unsigned long long* keys, const float* pc, int H, int W, int h, int w,
+                                               int mode) {
+  const float2 v = range_pixel(keys, pc, H, W, h, w, mode);
+  if (v.x != -1.0f) return v;
+  return range_pixel(keys, pc, H, W, h, w + 1 == W ? 0 : w + 1, mode);
+}
+__global__ void __launch_bounds__(256)
+range_resolve_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ pc, int H, int W, int mode,
+                     float mean, float stdv, float fill_range, float fill_rem, float* __restrict__ image,
+                     unsigned char* __restrict__ mask, unsigned char* __restrict__ car) {
+  pdl_entry();
+  const int total = H * W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int h = i % H, w = i / H;                      // output layout (C, W, H): consecutive threads = consecutive h
+    const float2 orig = range_pixel(keys, pc, H, W, h, w, mode);
+    float2 v = orig;
+    bool m = orig.x > 0.0f;                              // `:194` range_image_mask
+    if (orig.x == -1.0f) {
+      v = range_pixel(keys, pc, H, W, h, w + 1 == W ? 0 : w + 1, mode);
+      m = v.x > 0.0f;
+    }
+    const bool still = v.x == -1.0f;                     // `:201`
+    bool cw = false;
+    if (still) {                                         // `:203-209`: any filled value two pixels away
+      const float d = range_filled(keys, pc, H, W, (h + H - 2) % H, w, mode).x;
+      const float t = range_filled(keys, pc, H, W, (h + 2) % H, w, mode).x;
+      const float r = range_filled(keys, pc, H, W, h, (w + W - 2) % W, mode).x;
+      const float l = range_filled(keys, pc, H, W, h, (w + 2) % W, mode).x;
+      cw = d != -1.0f || t != -1.0f || r != -1.0f || l != -1.0f;
+      if (mode == 1) v = make_float2(__fdiv_rn(log2f(__fadd_rn(fill_range, 1.0f)), 6.0f), __fdiv_rn(log2f(__fadd_rn(fill_rem, 1.0f)), 6.0f));
+      else if (mode == 2) v = make_float2(__fdiv_rn(1.0f, fill_range), fill_rem);
+      else v = make_float2(fill_range, fill_rem);
+    }
+    if (mode == 0) v.x = __fdiv_rn(__fsub_rn(v.x, mean), stdv);                        // `:223-226`
+    image[static_cast<size_t>(w) * H + h] = v.x;
+    image[static_cast<size_t>(total) + static_cast<size_t>(w) * H + h] = v.y;
+    mask[static_cast<size_t>(w) * H + h] = m ? 1 : 0;
+    car[static_cast<size_t>(w) * H + h] = cw ? 1 : 0;
+  }
+}
+__global__ void fill_keys_kernel(unsigned long long* keys, int n) {
+  pdl_entry();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) keys[i] = ~0ull;
+}
+}  // namespace rldm
+
+extern "C" int rldm_points_to_range(const float* pc, int N, const float* incl, const float* height, int H, int W, int mode,
+                                    float mean, float stdv, float fill_range, float fill_rem, unsigned long long* keys,
+                                    float* image, unsigned char* mask, unsigned char* car_window, void* stream) {
+  RLDM_CHECK(H >= 3 && H <= 1024 && W >= 3, "points_to_range: bad image size (H=%d W=%d)", H, W);
+  RLDM_CHECK(mode >= 0 && mode <= 2, "points_to_range: mode must be 0 (linear), 1 (log) or 2 (inverse)");
+  RLDM_CHECK((reinterpret_cast<uintptr_t>(pc) & 15) == 0, "points_to_range: points must be 16 B aligned (N x 4 fp32)");
+  cudaStream_t st = as_stream(stream);
+  const int total = H * W;
+  RLDM_CUDA(launch_pdl(fill_keys_kernel, dim3((total + 255) / 256), dim3(256), 0, st, keys, total));
+  if (N > 0) {
+    int blocks = (N + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    RLDM_CUDA(launch_pdl(range_project_kernel, dim3(blocks), dim3(256), 2 * H * sizeof(float), st, pc, N, incl, height, H, W,
+                         fill_range, keys));
+  }
+  RLDM_CUDA(launch_pdl(range_resolve_kernel, dim3((total + 255) / 256), dim3(256), 0, st, keys, pc, H, W, mode, mean, stdv,
+                       fill_range, fill_rem, image, mask, car_window));
+  RLDM_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int rldm_range_to_points(const float* img, int B, int C, int W, int H, const float* incl, const float* height,
                                     int mode, float mean, float stdv, float fill, float* points, float* depth,
                                     void* stream) {

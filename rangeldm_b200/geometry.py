@@ -63,6 +63,27 @@ class RangeImageGeometry:
                   self.std, float(self.range_fill_value[0]), _lib.ptr(pts), _lib.ptr(depth))
         return (pts, depth) if return_depth else pts
 
+    def from_points(self, pc, width=1024):
+        """Point cloud (N, 4) fp32 CUDA tensor [x, y, z, remission] -> the sample `RangeDataset.__getitem__` builds
+        (`ldm/dataset.py:327-336`): {'jpg': (2, W, H) range image, 'mask': (W, H) bool, 'car_window_mask': (W, H) bool}
+        = projection (`:159-183`, KITTI beam assignment `ldm/kitti360_range_image.py:51-61`) + `process_miss_value`
+        (`:193-221`) + `normalize` (`:223-226`)."""
+        if not pc.is_cuda:
+            raise RuntimeError("RangeImageGeometry.from_points needs a CUDA tensor: rangeldm_b200 has no CPU fallback")
+        if pc.ndim != 2 or pc.shape[1] != 4:
+            raise ValueError("point cloud must be (N, 4): x, y, z, remission")
+        pts = pc.to(torch.float32).contiguous()
+        H = self.incl.shape[0]
+        incl, height = self._tables(pts.device)
+        keys = torch.empty(H * width, dtype=torch.int64, device=pts.device)
+        image = torch.empty((2, width, H), device=pts.device)
+        mask = torch.empty((width, H), dtype=torch.uint8, device=pts.device)
+        car = torch.empty((width, H), dtype=torch.uint8, device=pts.device)
+        _lib.call("rldm_points_to_range", _lib.ptr(pts), pts.shape[0], _lib.ptr(incl), _lib.ptr(height), H, width, self.mode,
+                  self.mean, self.std, float(self.range_fill_value[0]), float(self.range_fill_value[1]), _lib.ptr(keys),
+                  _lib.ptr(image), _lib.ptr(mask), _lib.ptr(car))
+        return {"jpg": image, "mask": mask.bool(), "car_window_mask": car.bool()}
+
     def to_voxel(self, range_images):
         """`to_voxel` (`ldm/dataset.py:278-294`): (B, C, W, H) range images -> (B, 2*D, Hg, Wg) bird's-eye-view volume
         [log-densities, remission features] by trilinear splatting of the point cloud (`ldm/inference.py:172`)."""

@@ -511,3 +511,35 @@ def test_points_to_voxel_matches_reference_golden(L, golden):
     pts = G.to_points(img, d["incl"], d["height"])
     inside = ((pts[..., 0].abs() <= 25.6) & (pts[..., 1].abs() <= 25.6)).sum(1).float()
     assert torch.allclose(dens.sum((1, 2)).cpu(), inside, rtol=2e-3)
+
+
+def test_points_to_range_matches_reference_golden(L, golden):
+    """rldm_points_to_range (RangeImageGeometry.from_points) against the reference's projection + miss-value fill +
+    normalisation: identical pixel assignment (nearest return wins) and masks, values to float rounding; then the
+    round trip range image -> points -> range image at KITTI size reproduces every pixel."""
+    import rangeldm_b200 as R
+    d = golden("range_to_points.pt")
+    pts = d["proj_points"].cuda()
+    for name, kw in (("linear", {}), ("log", {"log": True}), ("inverse", {"inverse": True})):
+        geom = R.RangeImageGeometry(d["incl"].numpy(), d["height"].numpy(), **kw)
+        out = geom.from_points(pts, width=128)
+        assert torch.equal(out["mask"].cpu(), d["proj_mask_" + name])
+        assert torch.equal(out["car_window_mask"].cpu(), d["proj_car_" + name])
+        ref = d["proj_" + name]
+        assert out["jpg"].shape == ref.shape
+        assert torch.equal(out["jpg"][1].cpu(), ref[1])                        # remission of the winning point: exact
+        assert relerr(out["jpg"][0].cpu(), ref[0], "points_to_range_" + name) < 1e-6
+    # round trip at KITTI size: every pixel of a dense range image comes back (beam assignment, column rounding)
+    geom = R.RangeImageGeometry(d["incl"].numpy(), d["height"].numpy())
+    g = torch.Generator().manual_seed(12)
+    img = torch.stack([torch.rand(1024, 64, generator=g) * 1.2 - 0.4, torch.rand(1024, 64, generator=g)])[None]
+    cloud = geom.to_pc_torch(img.cuda())[0]
+    back = geom.from_points(cloud, width=1024)
+    assert bool(back["mask"].all()) and not bool(back["car_window_mask"].any())
+    assert relerr(back["jpg"].cpu(), img[0], "range_round_trip") < 1e-5
+    # empty cloud: everything is the fill value, nothing is a car window
+    empty = geom.from_points(torch.zeros(0, 4, device="cuda"), width=64)
+    assert not bool(empty["mask"].any()) and not bool(empty["car_window_mask"].any())
+    assert torch.allclose(empty["jpg"][0].cpu(), torch.full((64, 64), (100.0 - 20.0) / 40.0))
+    with pytest.raises(RuntimeError):
+        geom.from_points(torch.zeros(4, 4))

@@ -135,3 +135,14 @@ def test_geometry_oracle_matches_reference_to_voxel(golden):
                    tuple(d["voxel_grid"]), tuple(d["voxel_range"]))
     assert v.shape == d["voxel"].shape and torch.allclose(v, d["voxel"], rtol=0, atol=1e-6)
     assert G.bev_image(v[0]).shape == (128, 96) and G.bev_image(v[0]).dtype.name == "uint8"
+
+
+def test_geometry_oracle_matches_reference_projection(golden):
+    """oracle points_to_range_image == the reference's projection + process_miss_value + normalize
+    (`ldm/dataset.py:159-226`, `ldm/kitti360_range_image.py:51-61`) in the three range encodings."""
+    from oracle import geometry as G
+    d = golden("range_to_points.pt")
+    for name, mode in (("linear", G.MODE_LINEAR), ("log", G.MODE_LOG), ("inverse", G.MODE_INVERSE)):
+        img, m, c = G.points_to_range_image(d["proj_points"].numpy(), d["incl"], d["height"], 128, mode)
+        assert torch.equal(img, d["proj_" + name])
+        assert torch.equal(m, d["proj_mask_" + name]) and torch.equal(c, d["proj_car_" + name])
