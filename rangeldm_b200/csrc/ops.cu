@@ -170,10 +170,17 @@ prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, 
   const int p_begin = blockIdx.x * pix_per_block;
   const int p_end = min(p_begin + pix_per_block, out_pix);
   const int total = (p_end - p_begin) * oct_per_pix;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int po = p_begin + i / oct_per_pix;
-    const int c = (i % oct_per_pix) << 3;
-    const int wp = po / Ho, ho = po - wp * Ho;
+  // (pixel, channel octet) of this thread's item advance incrementally: no integer division in the loop; Ho is a
+  // power of two in every reference geometry (shift), otherwise one division per item
+  int pl = threadIdx.x / oct_per_pix, oc = threadIdx.x - pl * oct_per_pix;
+  const int step_p = blockDim.x / oct_per_pix, step_o = blockDim.x - step_p * oct_per_pix;
+  const int sh_h = (Ho & (Ho - 1)) == 0 ? 31 - __clz(Ho) : -1;
+  for (int i = threadIdx.x; i < total; i += blockDim.x, pl += step_p, oc += step_o) {
+    if (oc >= oct_per_pix) { oc -= oct_per_pix; ++pl; }
+    const int po = p_begin + pl;
+    const int c = oc << 3;
+    const int wp = sh_h >= 0 ? po >> sh_h : po / Ho;
+    const int ho = po - wp * Ho;
     int wo = wp - 1;
     const bool halo = wo < 0 || wo >= Wo;
     if (wo < 0) wo += Wo;
@@ -980,7 +987,12 @@ extern "C" int rldm_prep(const float* x0, int c0, const float* x1, int c1, const
   if (ppb < 8) ppb = 8;
   chunks = (out_pix + ppb - 1) / ppb;
   // small (latency-bound) preps may start under the tail of the producing kernel (RLDM_PDL=2); large ones measured slower
-  if (static_cast<size_t>(B) * out_pix * C <= (1u << 21)) {
+  static size_t pdl_max_elems = 0;
+  if (pdl_max_elems == 0) {
+    const char* e = getenv("RLDM_PREP_PDL_MAX");
+    pdl_max_elems = e ? static_cast<size_t>(atoll(e)) : (static_cast<size_t>(1) << 21);
+  }
+  if (static_cast<size_t>(B) * out_pix * C <= pdl_max_elems) {
     RLDM_CUDA(launch_pdl_small(prep_kernel, dim3(chunks, B), dim3(256), 2 * C * sizeof(float), as_stream(stream), x0, c0, x1, c1, sums, pairs0, pairs1, gamma, beta, eps, G, silu, up, circular, reinterpret_cast<__half*>(out),
       reinterpret_cast<__half*>(out_lo), reinterpret_cast<__half*>(raw), reinterpret_cast<__half*>(raw_lo), W, H, ppb));
     } else {
