@@ -319,30 +319,48 @@ conv_in_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x
       }
     }
     __syncthreads();                     // previous chunk's in_s fully consumed
-    for (int idx = threadIdx.x; idx < kCinPix * K; idx += blockDim.x) {
-      const int k = idx / kCinPix, p = idx % kCinPix;      // consecutive threads = consecutive pixels: coalesced
-      const int tap = k / Cin, c = k - tap * Cin;
-      const int i = tap / 3, j = tap - i * 3;
+    // this thread's pixel is fixed (blockDim.x is a multiple of kCinPix): its coordinates are resolved once per chunk,
+    // then the K loop runs in batches of independent loads (the staging is bound by load latency otherwise)
+    {
+      const int p = threadIdx.x % kCinPix;
       const size_t pp = p_begin + p;
-      float a = 0.f;
-      if (pp < total_pix) {
-        const int h = pp % H;
-        const int w = (pp / H) % W;
-        const int b = pp / pix_per_img;
-        int wi = w + i - 1;
-        const int hj = h + j - 1;
-        bool ok = hj >= 0 && hj < H;
-        if (circular) {
-          if (wi < 0) wi += W;
-          if (wi >= W) wi -= W;
-        } else {
-          ok = ok && wi >= 0 && wi < W;
+      const bool live = pp < total_pix;
+      const int h = live ? static_cast<int>(pp % H) : 0;
+      const int w = live ? static_cast<int>((pp / H) % W) : 0;
+      const size_t b = live ? pp / pix_per_img : 0;
+      const float* xb0 = x0 + b * c0 * W * H;
+      const float* xb1 = x1 ? x1 + b * c1 * W * H : nullptr;
+      constexpr int kBatch = 6;
+      const int k_step = blockDim.x / kCinPix;
+      for (int k0 = threadIdx.x / kCinPix; k0 < K; k0 += k_step * kBatch) {
+        float a[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int k = k0 + u * k_step;
+          a[u] = 0.f;
+          if (live && k < K) {
+            const int tap = k / Cin, c = k - tap * Cin;
+            const int i = tap / 3, j = tap - i * 3;
+            int wi = w + i - 1;
+            const int hj = h + j - 1;
+            bool ok = hj >= 0 && hj < H;
+            if (circular) {
+              if (wi < 0) wi += W;
+              if (wi >= W) wi -= W;
+            } else {
+              ok = ok && wi >= 0 && wi < W;
+            }
+            if (ok)
+              a[u] = (c < c0) ? __ldg(xb0 + (static_cast<size_t>(c) * W + wi) * H + hj)
+                              : __ldg(xb1 + (static_cast<size_t>(c - c0) * W + wi) * H + hj);
+          }
         }
-        if (ok)
-          a = (c < c0) ? __ldg(x0 + ((static_cast<size_t>(b) * c0 + c) * W + wi) * H + hj)
-                       : __ldg(x1 + ((static_cast<size_t>(b) * c1 + (c - c0)) * W + wi) * H + hj);
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int k = k0 + u * k_step;
+          if (k < K) in_s[k * kCinPix + p] = a[u];          // [K][kCinPix]
+        }
       }
-      in_s[idx] = a;                                       // [K][kCinPix]
     }
     __syncthreads();
     // thread = 4 output channels x 4 pixels: every weight float4 read from shared memory feeds 16 FMAs
@@ -513,30 +531,47 @@ norm_conv_out_kernel(const float* __restrict__ x, const double* __restrict__ sum
   // H and Cin/4 are powers of two in every reference config: shifts instead of integer divisions (sh < 0: generic)
   const int sh_c = (c4n & (c4n - 1)) == 0 ? 31 - __clz(c4n) : -1;
   const int sh_h = (H & (H - 1)) == 0 ? 31 - __clz(H) : -1;
-  for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
-    const int r = sh_c >= 0 ? i >> sh_c : i / c4n;          // row of the tile = col * H + h
-    const int c = (i - r * c4n) << 2;
-    const int col = sh_h >= 0 ? r >> sh_h : r / H;
-    const int h = r - col * H;
-    int wc = w0 - 1 + col;
-    bool ok = true;
-    if (circular) {
-      if (wc < 0) wc += W;
-      if (wc >= W) wc -= W;
-    } else {
-      ok = wc >= 0 && wc < W;
-    }
-    ok = ok && (wc < W);                   // columns past a ragged last block are never consumed
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ok) {
-      v = __ldg(reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * W + wc) * H + h) * Cin + c));
-      if (norm) {
-        v.x = fmaf(v.x, sc[c], sf[c]); v.y = fmaf(v.y, sc[c + 1], sf[c + 1]);
-        v.z = fmaf(v.z, sc[c + 2], sf[c + 2]); v.w = fmaf(v.w, sc[c + 3], sf[c + 3]);
+  // four independent 16 B loads in flight per thread before any of them is consumed (the loop is bound by the
+  // global-load latency otherwise: one outstanding load per thread)
+  constexpr int kBatch = 4;
+  for (int i0 = threadIdx.x; i0 < n_items; i0 += blockDim.x * kBatch) {
+    float4 v[kBatch];
+    int rr[kBatch], cc[kBatch];
+    bool okk[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = i0 + u * blockDim.x;
+      const int r = sh_c >= 0 ? i >> sh_c : i / c4n;        // row of the tile = col * H + h
+      const int c = (i - r * c4n) << 2;
+      const int col = sh_h >= 0 ? r >> sh_h : r / H;
+      const int h = r - col * H;
+      int wc = w0 - 1 + col;
+      bool ok = i < n_items;
+      if (circular) {
+        if (wc < 0) wc += W;
+        if (wc >= W) wc -= W;
+      } else {
+        ok = ok && wc >= 0;
       }
-      if (silu) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+      ok = ok && wc < W;                   // also: columns past a ragged last block are never consumed
+      rr[u] = r; cc[u] = c; okk[u] = ok;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) v[u] = __ldg(reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * W + wc) * H + h) * Cin + c));
     }
-    *reinterpret_cast<float4*>(tile + r * pitch + c) = v;
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      if (i0 + u * blockDim.x >= n_items) break;
+      const int c = cc[u];
+      float4 t = v[u];
+      if (okk[u]) {
+        if (norm) {
+          t.x = fmaf(t.x, sc[c], sf[c]); t.y = fmaf(t.y, sc[c + 1], sf[c + 1]);
+          t.z = fmaf(t.z, sc[c + 2], sf[c + 2]); t.w = fmaf(t.w, sc[c + 3], sf[c + 3]);
+        }
+        if (silu) { t.x = silu_f(t.x); t.y = silu_f(t.y); t.z = silu_f(t.z); t.w = silu_f(t.w); }
+      }
+      *reinterpret_cast<float4*>(tile + rr[u] * pitch + c) = t;
+    }
   }
   __syncthreads();
   // ---- 3x3 conv from shared memory: LPP lanes per output pixel split the channel loop
