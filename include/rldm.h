@@ -104,6 +104,18 @@ int rldm_conv_tc_shortcut(const uint16_t* x, const uint16_t* x_lo, const uint16_
                           const uint16_t* sc_x, const uint16_t* sc_x_lo, const uint16_t* sc_wgt, int sc_cin,
                           void* stream);
 
+/* rldm_conv_tc_shortcut with a caller-owned split-K workspace: when the K loop is split over a cluster, the partial
+ * tiles are exchanged through `splitk_ws` (global memory, stays in L2; needs tiles * split * 128 * min(Cout,128) * 4
+ * bytes, 16 B aligned; 12 MB covers every automatic split) instead of distributed shared memory, whose ~20 B/clk per
+ * SM makes an 8-way reduction cost ~3000 cycles.  Same fixed summation order (bit-identical results).  NULL or too
+ * small: the DSMEM path.  (Measured on B200 the L2 round trip is slower than DSMEM for the C3 shapes -- 2.33 vs 2.25 ms
+ * per UNet forward -- so the engine does not pass a workspace by default; RLDM_SPLITK_VIA_L2=1 opts in.)  One workspace per stream (launches that share it must be stream-ordered). */
+int rldm_conv_tc_ws(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias, const float* temb,
+                    int temb_stride, const float* residual, float* out, int B, int W, int H, int Cin, int Cout, int ks,
+                    int stride, int pad_lo, int circular, int split_k, double* stats, const uint16_t* sc_x,
+                    const uint16_t* sc_x_lo, const uint16_t* sc_wgt, int sc_cin, float* splitk_ws,
+                    long long splitk_ws_bytes, void* stream);
+
 /* CUDA-core restatement of rldm_conv_tc with the identical contract (split_k ignored); used by the
  * GPU tests to isolate tensor-core descriptor bugs from precision, never by the product path. */
 int rldm_conv_ref(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias, const float* temb,

@@ -33,6 +33,8 @@ SIGNATURES = {
                      + [c_int] * 10 + [c_void_p, c_void_p]),
     "rldm_conv_tc_shortcut": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
                               + [c_int] * 10 + [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "rldm_conv_tc_ws": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+                        + [c_int] * 10 + [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_i64, c_void_p]),
     "rldm_conv_ref": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
                       + [c_int] * 9 + [c_void_p]),
     "rldm_conv_in": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 5

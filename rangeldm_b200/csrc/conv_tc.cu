@@ -48,6 +48,7 @@ struct ConvParams {
   int nb_stages;    // depth of the weight (B) ring
   int units;        // (Cin/64) * 3 : one unit = (channel chunk, kernel column tj) = 3 taps
   long long* dbg;   // optional: 8 clock64 timestamps written by CTA (0,0,0) (profiling aid, normally NULL)
+  float* ws;        // optional split-K workspace in global memory: [tile][rank][128][BLOCK_N] fp32 partial tiles
 };
 
 // Tensor maps of one launch.  a/alo/b: activation (hi, lo) and weights of the convolution.  a2/a2lo/b2: operand and
@@ -227,7 +228,11 @@ __device__ __forceinline__ void epilogue_tile(uint8_t* smem, uint32_t tmem_acc, 
 // ALL residual rows they will need into registers right after griddepcontrol.wait -- the L2 latency of the
 // residual hides under the mainloop.  The split-K reduction pulls the partial tiles of the peer CTAs through
 // distributed shared memory in batches of 16 independent 16 B loads per lane (fixed summation order:
-// deterministic), instead of one dependent load at a time.
+// deterministic), instead of one dependent load at a time.  DSMEM moves only ~17-21 B/clk per SM, so a cluster of 8
+// needs ~3000 cycles to pull its 56 KB; when the caller provides a global workspace (p.ws) the partial tiles go
+// through L2 instead (written straight from TMEM, read back at ~64 B/clk per SM after the cluster barrier; the
+// barrier's release/acquire at cluster scope orders the global stores) -- same fixed summation order.  (Measured
+// slower than DSMEM on the C3 shapes; the engine leaves p.ws NULL unless RLDM_SPLITK_VIA_L2=1.)
 template <int BLOCK_N, int STAGES, int TERMS, int NSPLIT>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
@@ -410,7 +415,10 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
     // The pipeline stages are dead once tmem_full fires (all TMA writes consumed, all MMA reads done), so the
     // fp32 accumulator tile [128][BLOCK_N] is staged over them (row pitch +4 floats: conflict-free float4).
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    float* stage_row = reinterpret_cast<float*>(smem) + (q * 32 + lane) * kStagePitch;
+    const bool via_l2 = NSPLIT > 1 && p.ws != nullptr;
+    float* stage_row = via_l2
+        ? p.ws + ((static_cast<size_t>(blockIdx.y * gridDim.x + blockIdx.x) * NSPLIT + blockIdx.z) * kBlockM + q * 32 + lane) * BLOCK_N
+        : reinterpret_cast<float*>(smem) + (q * 32 + lane) * kStagePitch;
 #pragma unroll 1
     for (int nc = 0; nc < BLOCK_N / 32; ++nc) {
       uint32_t r[32];
@@ -462,9 +470,16 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
 #pragma unroll
         for (int ub = 0; ub < kUB; ++ub) {
           const int r = r_begin + (u0 + ub) * kRowsPerIter + rsub;
-          const uint32_t off = static_cast<uint32_t>(r * kStagePitch + col) * 4u;
+          if (p.ws != nullptr) {             // partial tiles through L2 (written by the peers before the cluster barrier)
+            const float* wrow = p.ws + (static_cast<size_t>(blockIdx.y * gridDim.x + blockIdx.x) * NSPLIT * kBlockM + r) * BLOCK_N + col;
 #pragma unroll
-          for (int sidx = 0; sidx < NSPLIT; ++sidx) part[ub][sidx] = ld_dsmem_f4(rbase[sidx] + off);
+            for (int sidx = 0; sidx < NSPLIT; ++sidx)
+              part[ub][sidx] = __ldcg(reinterpret_cast<const float4*>(wrow + static_cast<size_t>(sidx) * kBlockM * BLOCK_N));
+          } else {
+            const uint32_t off = static_cast<uint32_t>(r * kStagePitch + col) * 4u;
+#pragma unroll
+            for (int sidx = 0; sidx < NSPLIT; ++sidx) part[ub][sidx] = ld_dsmem_f4(rbase[sidx] + off);
+          }
         }
 #pragma unroll
         for (int ub = 0; ub < kUB; ++ub) {
@@ -1101,7 +1116,7 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
                         const float* temb, int temb_stride, const float* residual, float* out,
                         int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
                         int circular, int split_k, double* stats, const uint16_t* sc_x, const uint16_t* sc_x_lo,
-                        const uint16_t* sc_wgt, int sc_cin, void* stream) {
+                        const uint16_t* sc_wgt, int sc_cin, float* splitk_ws, size_t splitk_ws_bytes, void* stream) {
   RLDM_CHECK(ks == 1 || ks == 3, "conv_tc: ks must be 1 or 3 (got %d)", ks);
   RLDM_CHECK(!sc_x || (sc_wgt && sc_cin > 0 && sc_cin % 64 == 0 && stride == 1 && (!x_lo == !sc_x_lo)),
              "conv_tc: fused shortcut needs weights, Cin2 %% 64 == 0 (got %d), stride 1 and the same operand precision",
@@ -1182,6 +1197,7 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
       p.a_part_bytes = static_cast<int>(a_stage / parts);
       p.nb_stages = nbs;
       p.dbg = nullptr;
+      p.ws = nullptr;
       p.stats = stats;
       p.stats_G = Cout / 2;
       p.stats_cpg = 2;
@@ -1265,6 +1281,7 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
   p.total_iters = p.main_iters + (sc_x ? sc_cin / kBlockK : 0);
   p.units = 0; p.a_part_bytes = 0; p.nb_stages = 0;
   p.dbg = g_conv_dbg;
+  p.ws = nullptr;
   p.stats = stats;
   p.stats_G = Cout / 2;       // channel pairs per image
   p.stats_cpg = 2;
@@ -1278,6 +1295,9 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
   }
   RLDM_CHECK(split == 1 || split == 2 || split == 4 || split == 8, "conv_tc: split_k must be 1, 2, 4 or 8 (got %d)", split);
   while (split > p.total_iters) split /= 2;
+  if (split > 1 && splitk_ws != nullptr && (reinterpret_cast<uintptr_t>(splitk_ws) & 15) == 0 &&
+      static_cast<size_t>(tiles) * split * kBlockM * BN * sizeof(float) <= splitk_ws_bytes && !getenv("RLDM_SPLITK_DSMEM"))
+    p.ws = splitk_ws;        // partial tiles through L2 instead of DSMEM
   cudaStream_t st = as_stream(stream);
   // more tiles than SMs and no K split: persistent CTAs with a double-buffered TMEM accumulator
   static int n_sms = 0;
@@ -1328,7 +1348,7 @@ extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint1
                             int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
                             int circular, int split_k, double* stats, void* stream) {
   return conv_tc_impl(x, x_lo, wgt, bias, temb, temb_stride, residual, out, B, W, H, Cin, Cout, ks, stride, pad_lo,
-                      circular, split_k, stats, nullptr, nullptr, nullptr, 0, stream);
+                      circular, split_k, stats, nullptr, nullptr, nullptr, 0, nullptr, 0, stream);
 }
 
 extern "C" int rldm_conv_tc_shortcut(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias,
@@ -1337,5 +1357,16 @@ extern "C" int rldm_conv_tc_shortcut(const uint16_t* x, const uint16_t* x_lo, co
                                      int circular, int split_k, double* stats, const uint16_t* sc_x,
                                      const uint16_t* sc_x_lo, const uint16_t* sc_wgt, int sc_cin, void* stream) {
   return conv_tc_impl(x, x_lo, wgt, bias, temb, temb_stride, residual, out, B, W, H, Cin, Cout, ks, stride, pad_lo,
-                      circular, split_k, stats, sc_x, sc_x_lo, sc_wgt, sc_cin, stream);
+                      circular, split_k, stats, sc_x, sc_x_lo, sc_wgt, sc_cin, nullptr, 0, stream);
+}
+
+extern "C" int rldm_conv_tc_ws(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias,
+                               const float* temb, int temb_stride, const float* residual, float* out,
+                               int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
+                               int circular, int split_k, double* stats, const uint16_t* sc_x,
+                               const uint16_t* sc_x_lo, const uint16_t* sc_wgt, int sc_cin, float* splitk_ws,
+                               long long splitk_ws_bytes, void* stream) {
+  return conv_tc_impl(x, x_lo, wgt, bias, temb, temb_stride, residual, out, B, W, H, Cin, Cout, ks, stride, pad_lo,
+                      circular, split_k, stats, sc_x, sc_x_lo, sc_wgt, sc_cin, splitk_ws,
+                      splitk_ws_bytes > 0 ? static_cast<size_t>(splitk_ws_bytes) : 0, stream);
 }

@@ -1523,11 +1523,11 @@ static int run_ops(const rldm_op* ops, int n_ops, unsigned long long* stamps, vo
                        stream);
         break;
       case RLDM_OP_CONV_TC:
-        rc = rldm_conv_tc_shortcut((const uint16_t*)o.p[0], (const uint16_t*)o.p[6], (const uint16_t*)o.p[1],
-                                   (const float*)o.p[2], (const float*)o.p[3], o.i[0], (const float*)o.p[4],
-                                   (float*)o.p[5], o.i[1], o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], o.i[7], o.i[8], o.i[9],
-                                   o.i[10], (double*)o.p[7], (const uint16_t*)o.p[8], (const uint16_t*)o.p[9],
-                                   (const uint16_t*)o.p[10], o.i[11], stream);
+        rc = rldm_conv_tc_ws((const uint16_t*)o.p[0], (const uint16_t*)o.p[6], (const uint16_t*)o.p[1],
+                             (const float*)o.p[2], (const float*)o.p[3], o.i[0], (const float*)o.p[4],
+                             (float*)o.p[5], o.i[1], o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], o.i[7], o.i[8], o.i[9],
+                             o.i[10], (double*)o.p[7], (const uint16_t*)o.p[8], (const uint16_t*)o.p[9],
+                             (const uint16_t*)o.p[10], o.i[11], (float*)o.p[11], o.n, stream);
         break;
       case RLDM_OP_CONV_REF:
         rc = rldm_conv_ref((const uint16_t*)o.p[0], (const uint16_t*)o.p[6], (const uint16_t*)o.p[1], (const float*)o.p[2],

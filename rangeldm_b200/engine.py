@@ -38,6 +38,8 @@ FUSE_STATS = os.environ.get("RLDM_FUSE_STATS", "1") != "0"
 # ResnetBlock2D.conv_shortcut folded into conv2's launch (RLDM_FUSE_SHORTCUT=0: separate 1x1 launch + fp32 residual)
 FUSE_SHORTCUT = os.environ.get("RLDM_FUSE_SHORTCUT", "1") != "0"
 FUSE_CONV_OUT = os.environ.get("RLDM_FUSE_CONV_OUT", "1") != "0"
+# split-K partial tiles through an L2 workspace instead of DSMEM: measured SLOWER on B200 (C3 UNet 2.33 vs 2.25 ms), opt-in
+SPLITK_VIA_L2 = os.environ.get("RLDM_SPLITK_VIA_L2", "0") == "1"
 
 
 def _require_cuda_device(dev, what):
@@ -141,6 +143,9 @@ class Builder:
         self.groups = groups
         self.gn_arena = prog.hold(torch.zeros(max_gn * batch * groups * 2, dtype=torch.float64, device=prog.device))   # 16 MB at batch 8
         self.gn_used = 0
+        # split-K workspace (partial tiles of clustered small convolutions travel through L2 instead of DSMEM);
+        # one per program: its launches are stream-ordered.  12 MB covers every automatic split (<= 160 CTAs x 64 KB).
+        self.splitk_ws = prog.hold(torch.empty(12 << 20, dtype=torch.uint8, device=prog.device)) if SPLITK_VIA_L2 else None
         self.memset_op = prog.add(_lib.OP_MEMSET, p=(self.gn_arena,), n=0)
         self.temb = None         # (tensor (B,T), T)
         self.temb_rows = {}      # id(resnet) -> row offset
@@ -270,8 +275,9 @@ class Builder:
             ints += [sc_cin]
         else:
             assert shortcut is None
+        ws = self.splitk_ws if kind == _lib.OP_CONV_TC else None
         self.pg.add(kind, i=ints, p=(xh[0], wt, bias, temb_t, residual.t if residual is not None else None, out,
-                                     xh[1], st) + sc_ptrs, launches=1)
+                                     xh[1], st) + sc_ptrs + (ws,), n=(ws.numel() if ws is not None else 0), launches=1)
         return Act(out, self.B, Wo, Ho, cout, st)
 
     # ---- blocks ----------------------------------------------------------------------------

@@ -135,6 +135,12 @@ def test_conv_tc_matches_cuda_core_restatement_and_oracle(L, case):
     L.call("rldm_conv_tc", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out3b),
            B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, None)
     assert torch.equal(out3, out3b)
+    # split-K partial tiles exchanged through a global (L2) workspace instead of DSMEM: same summation order, same bits
+    ws = torch.empty(16 << 20, dtype=torch.uint8, device="cuda")
+    out3w = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
+    L.call("rldm_conv_tc_ws", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out3w),
+           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, None, None, None, None, 0, L.ptr(ws), ws.numel())
+    assert torch.equal(out3, out3w)
     L.call("rldm_conv_ref", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd),
            L.ptr(out3r), B, W, H, Cin, Cout, ks, stride, pad_lo, circ)
     assert relerr(out3, out3r) < 1e-5
