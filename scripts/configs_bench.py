@@ -9,12 +9,13 @@ import rangeldm_b200 as R
 import bench
 from rangeldm_b200.pipelines import FusedSampler, make_pos_encoding
 
-dev = torch.device("cuda:0")
-flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 UNET_C2 = dict(sample_size=[1024, 64], in_channels=3, out_channels=2, layers_per_block=2,
                block_out_channels=[128, 128, 256, 256, 512, 512],
                down_block_types=["DownBlock2D"] * 4 + ["AttnDownBlock2D", "DownBlock2D"],
                up_block_types=["UpBlock2D", "AttnUpBlock2D"] + ["UpBlock2D"] * 4)
+
+
+dev = torch.device("cuda:0")
 
 
 def unet(cfg):
@@ -51,24 +52,35 @@ def report(name, batch, ms, gflop_per_image):
                       "achieved_tflops": round(batch * gflop_per_image / ms, 1)}), flush=True)
 
 
-# C2: RangeDM pixel space, 50-step DDIM, batch 1, no VAE (BASELINE configs[1]); 498.2 GFLOP per UNet forward
-u2 = unet(UNET_C2)
-sch = R.DDIMScheduler(clip_sample=False); sch.set_timesteps(50)
-s = FusedSampler(u2, sch, None, 1, 1)
-s.load(torch.randn(1, 2, 1024, 64, device=dev), make_pos_encoding(1, 1024, 64, dev))
-report("C2 RangeDM pixel 64x1024, 50-step DDIM", 1, timed(s), 50 * 498.2)
-del s, u2
-torch.cuda.empty_cache()
-# C4: nuScenes latent 256x8 -> 32x1024 image, 20-step DPM-Solver, per-GPU batch 16 (BASELINE configs[3])
-u4 = unet(dict(bench.UNET_C3, sample_size=[256, 8])); v = vae()
-sch = R.DPMSolverMultistepScheduler(timestep_spacing="leading"); sch.set_timesteps(20)
-s = FusedSampler(u4, sch, v, 16, 1)
-s.load(torch.randn(16, 4, 256, 8, device=dev), make_pos_encoding(16, 256, 8, dev))
-report("C4 RangeLDM nuScenes 32x1024, 20-step DPM-Solver", 16, timed(s), 20 * 16.28 + 78.73)
-del s, u4
-torch.cuda.empty_cache()
-# C5: conditional upsampling, 4 + 8 channels in, per-GPU batch 4 (BASELINE configs[4])
-u5 = unet(dict(bench.UNET_C3, in_channels=12))
-s = FusedSampler(u5, sch, v, 4, 8)
-s.load(torch.randn(4, 4, 256, 16, device=dev), torch.randn(4, 8, 256, 16, device=dev))
-report("C5 conditional upsample KITTI-360, 20-step DPM-Solver", 4, timed(s), 20 * 34.14 + 157.46)
+flush = None
+
+
+def main():
+    global flush
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # C2: RangeDM pixel space, 50-step DDIM, batch 1, no VAE (BASELINE configs[1]); 498.2 GFLOP per UNet forward
+    u2 = unet(UNET_C2)
+    sch = R.DDIMScheduler(clip_sample=False); sch.set_timesteps(50)
+    s = FusedSampler(u2, sch, None, 1, 1)
+    s.load(torch.randn(1, 2, 1024, 64, device=dev), make_pos_encoding(1, 1024, 64, dev))
+    report("C2 RangeDM pixel 64x1024, 50-step DDIM", 1, timed(s), 50 * 498.2)
+    del s, u2
+    torch.cuda.empty_cache()
+    # C4: nuScenes latent 256x8 -> 32x1024 image, 20-step DPM-Solver, per-GPU batch 16 (BASELINE configs[3])
+    u4 = unet(dict(bench.UNET_C3, sample_size=[256, 8])); v = vae()
+    sch = R.DPMSolverMultistepScheduler(timestep_spacing="leading"); sch.set_timesteps(20)
+    s = FusedSampler(u4, sch, v, 16, 1)
+    s.load(torch.randn(16, 4, 256, 8, device=dev), make_pos_encoding(16, 256, 8, dev))
+    report("C4 RangeLDM nuScenes 32x1024, 20-step DPM-Solver", 16, timed(s), 20 * 16.28 + 78.73)
+    del s, u4
+    torch.cuda.empty_cache()
+    # C5: conditional upsampling, 4 + 8 channels in, per-GPU batch 4 (BASELINE configs[4])
+    u5 = unet(dict(bench.UNET_C3, in_channels=12))
+    s = FusedSampler(u5, sch, v, 4, 8)
+    s.load(torch.randn(4, 4, 256, 16, device=dev), torch.randn(4, 8, 256, 16, device=dev))
+    report("C5 conditional upsample KITTI-360, 20-step DPM-Solver", 4, timed(s), 20 * 34.14 + 157.46)
+
+
+
+if __name__ == "__main__":
+    main()

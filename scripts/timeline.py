@@ -45,10 +45,23 @@ if __name__ == "__main__":
     B = int(args[0]) if args else 8
     dev = torch.device("cuda:0")
     pipe = bench.build_pipeline(dev)
-    uplan = pipe.unet.plan(B, 256, 16, 1)
-    dplan = pipe.vae.decoder_plan(B, 256, 16)
-    uplan.x_in.normal_(); uplan.t_buf.fill_(500.0); dplan.z_in.normal_()
-    for name, plan in (("unet", uplan), ("decoder", dplan)):
+    if "--c2" in sys.argv:          # RangeDM pixel UNet (BASELINE configs[1]), batch 1 unless given
+        import rangeldm_b200 as R
+        from configs_bench import UNET_C2
+        torch.manual_seed(0)
+        u2 = R.UNet2DModel(**UNET_C2)
+        R.replace_down(u2); R.replace_conv(u2)
+        u2 = u2.to(dev)
+        B = int(args[0]) if args else 1
+        uplan = u2.plan(B, 1024, 64, 1)
+        uplan.x_in.normal_(); uplan.t_buf.fill_(500.0)
+        plans = (("unet_c2", uplan),)
+    else:
+        uplan = pipe.unet.plan(B, 256, 16, 1)
+        dplan = pipe.vae.decoder_plan(B, 256, 16)
+        uplan.x_in.normal_(); uplan.t_buf.fill_(500.0); dplan.z_in.normal_()
+        plans = (("unet", uplan), ("decoder", dplan))
+    for name, plan in plans:
         prog = plan.prog
         us = timed_profile(prog)
         real = graphed_ms(prog)
