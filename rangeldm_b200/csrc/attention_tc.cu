@@ -95,7 +95,7 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 }
 
 struct AttnSmem {
-  uint64_t q_full;
+  uint64_t q_full, q_empty;
   uint64_t k_full[kAtRing], k_empty[kAtRing], v_full[kAtRing], v_empty[kAtRing];
   uint64_t s_full, p_full;
   uint64_t all_done;
@@ -130,11 +130,14 @@ __device__ __forceinline__ float at_exp_store32(const uint32_t (&r)[32], float m
   return l0 + l1;
 }
 
+// Persistent: gridDim.x CTAs (two per SM) walk over the work items (image, head, 128-query block); barriers, TMEM and
+// the K/V ring live across items, the loaders run ahead into the next item while the current one is still in its
+// softmax / combine phase, so prologue and tail are paid once per CTA instead of once per item.
 __global__ void __launch_bounds__(kAtThreads, 2)
 attention_umma_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half* __restrict__ out_lo, int N, int C,
-                      int H, long long* dbg) {
-  // profiling aid (normally NULL): clock64 stamps of CTA (0,0,0): [0..31] loader 0, [32..63] MMA, [64..127] softmax
-  if (dbg != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) != 0) dbg = nullptr;
+                      int H, int B, long long* dbg) {
+  // profiling aid (normally NULL): clock64 stamps of CTA 0, first item: [0..31] loader 0, [32..63] MMA, [64..127] softmax
+  if (dbg != nullptr && blockIdx.x != 0) dbg = nullptr;
 #define AT_STAMP(idx) do { if (dbg) dbg[idx] = clock64(); } while (0)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -146,14 +149,21 @@ attention_umma_kernel(const float* __restrict__ qkv, __half* __restrict__ out, _
   AttnSmem* sb = reinterpret_cast<AttnSmem*>(reinterpret_cast<uint8_t*>(sML) + static_cast<size_t>(T) * kAtTile * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, hd = blockIdx.y, q0 = blockIdx.x * kAtTile;
   const size_t rowf = 3 * static_cast<size_t>(C);
-  const float* base = qkv + static_cast<size_t>(b) * N * rowf + hd * 8;
+  const int heads = C / 8;
+  const int n_items = B * heads * T;                       // T query blocks per (image, head)
+  // item -> (image, head, first query); consecutive items = the query blocks of one (image, head): K/V stay in L2
+  auto item_base = [&](int item, int& q0) -> const float* {
+    const int qb = item % T, bh = item / T;
+    q0 = qb * kAtTile;
+    return qkv + static_cast<size_t>(bh / heads) * N * rowf + (bh % heads) * 8;
+  };
 
   pdl_trigger();
   if (threadIdx.x == 0) AT_STAMP(127);
   if (threadIdx.x == 0) {
     mbar_init(&sb->q_full, 96);
+    mbar_init(&sb->q_empty, 1);
     for (int i = 0; i < kAtRing; ++i) {
       mbar_init(&sb->k_full[i], 32); mbar_init(&sb->k_empty[i], 1);
       mbar_init(&sb->v_full[i], 32); mbar_init(&sb->v_empty[i], 1);
@@ -172,22 +182,17 @@ attention_umma_kernel(const float* __restrict__ qkv, __half* __restrict__ out, _
 
   if (warp >= 5) {
     // ===================== loaders ==============================================================
-    const int w = warp - 5;                                // ring slot and tile residue of this warp
-    // first tile's K/V and this thread's Q rows: all loads in flight before anything is stored
-    float4 qa[2], qb[2];
+    const int w = warp - 5;                                // ring slot of this warp: global tiles g = w mod 3
     const int qt = threadIdx.x - 5 * 32;                   // 0..95: Q rows qt and qt + 96
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const int i = qt + rr * 96;
-      if (i < kAtTile) {
-        const float* qp = base + static_cast<size_t>(q0 + i) * rowf;
-        qa[rr] = __ldg(reinterpret_cast<const float4*>(qp)); qb[rr] = __ldg(reinterpret_cast<const float4*>(qp) + 1);
-      }
-    }
     if (lane == 0 && w == 0) AT_STAMP(0);
     // K: lane <-> rows lane + 32 rr;  V: lane <-> keys 4 lane .. 4 lane + 3.  The next tile is always in registers.
     float4 ka[4], kb[4], va[4], vb[4];
-    auto load_tile = [&](int t) {
+    const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int total_tiles = my_items * T;                  // tiles this CTA walks over, all its items
+    auto load_tile = [&](int g) {                          // g: running tile index of this CTA
+      int q0;
+      const float* base = item_base(static_cast<int>(blockIdx.x) + (g / T) * static_cast<int>(gridDim.x), q0);
+      const int t = g % T;
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
         const float* kp = base + static_cast<size_t>(t * kAtTile + lane + rr * 32) * rowf + C;
@@ -196,9 +201,20 @@ attention_umma_kernel(const float* __restrict__ qkv, __half* __restrict__ out, _
         va[rr] = __ldg(reinterpret_cast<const float4*>(vp)); vb[rr] = __ldg(reinterpret_cast<const float4*>(vp) + 1);
       }
     };
-    if (w < T) load_tile(w);
-    {
-      // Q rows: [q_hi | q_lo | q_hi | 0], softmax scale 1/sqrt(8) and log2(e) folded in
+    // Q rows of local item n: [q_hi | q_lo | q_hi | 0], softmax scale 1/sqrt(8) and log2(e) folded in
+    auto load_q = [&](int n) {
+      int q0;
+      const float* base = item_base(static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x), q0);
+      float4 qa[2], qb[2];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int i = qt + rr * 96;
+        if (i < kAtTile) {
+          const float* qp = base + static_cast<size_t>(q0 + i) * rowf;
+          qa[rr] = __ldg(reinterpret_cast<const float4*>(qp)); qb[rr] = __ldg(reinterpret_cast<const float4*>(qp) + 1);
+        }
+      }
+      mbar_wait(&sb->q_empty, (n & 1) ^ 1);               // every Q K^T of the previous item has completed
       const float qs = 0.35355339059327373f * 1.4426950408889634f;
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
@@ -216,9 +232,13 @@ attention_umma_kernel(const float* __restrict__ qkv, __half* __restrict__ out, _
       }
       at_fence_async();
       at_arrive(&sb->q_full);
-    }
-    for (int t = w; t < T; t += kAtRing) {
-      const uint32_t ph = ((t / kAtRing) & 1) ^ 1;
+    };
+    if (w < total_tiles) load_tile(w);
+    int q_next = 0;                                        // next local item whose Q this warp still has to stage
+    for (int g = w; g < total_tiles; g += kAtRing) {
+      // stage the Q of every item up to the one tile g belongs to (all three loader warps take part in each Q)
+      while (q_next <= g / T) load_q(q_next++);
+      const uint32_t ph = ((g / kAtRing) & 1) ^ 1;
       mbar_wait(&sb->k_empty[w], ph);
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
@@ -256,108 +276,123 @@ attention_umma_kernel(const float* __restrict__ qkv, __half* __restrict__ out, _
       }
       at_fence_async();
       at_arrive(&sb->v_full[w]);
-      if (lane == 0 && w == 0 && t / kAtRing < 8) AT_STAMP(1 + t / kAtRing);
-      if (t + kAtRing < T) load_tile(t + kAtRing);
+      if (lane == 0 && w == 0 && g / kAtRing < 8) AT_STAMP(1 + g / kAtRing);
+      if (g + kAtRing < total_tiles) load_tile(g + kAtRing);
     }
+    while (q_next < my_items) load_q(q_next++);            // (only when a warp owns no tile of the last items)
   } else if (warp == 4) {
     // ===================== MMA issuer ===========================================================
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_f16(128, 128);
       constexpr uint32_t idesc_o = umma_idesc_f16(128, kAtSlot);
       const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ));
-      auto issue_qk = [&](int j) {                         // after PV(j-1) in program order: MMAs execute in order
-        const int s = j % kAtRing;
-        mbar_wait(&sb->k_full[s], (j / kAtRing) & 1);
+      const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+      auto issue_qk = [&](int g, bool last_of_item) {      // after the previous PV in program order: MMAs execute in order
+        const int s = g % kAtRing;
+        mbar_wait(&sb->k_full[s], (g / kAtRing) & 1);
         tc_fence_after();
         const uint64_t k_desc = umma_desc_sw128(smem_u32(sK + s * kAtKBytes));
         umma_f16(tmem, q_desc, k_desc, idesc_s, 0u);
         umma_f16(tmem, q_desc + 2, k_desc + 2, idesc_s, 1u);
         umma_commit(&sb->s_full);
         umma_commit(&sb->k_empty[s]);
-        if (j < 15) AT_STAMP(32 + j);
+        if (last_of_item) umma_commit(&sb->q_empty);       // the Q tile may be overwritten with the next item's
+        if (g < 15) AT_STAMP(32 + g);
       };
-      mbar_wait(&sb->q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < T; ++j) {
-        const int s = j % kAtRing;
-        mbar_wait(&sb->v_full[s], (j / kAtRing) & 1);
-        mbar_wait(&sb->p_full, j & 1);
-        tc_fence_after();
-        const uint32_t d = tmem + kAtSlot0 + kAtSlot * j;
-        const uint32_t v_addr = smem_u32(sV + s * kAtVBytes);
+      int g = 0;                                           // running tile index
+      for (int n = 0; n < my_items; ++n) {
+        mbar_wait(&sb->q_full, n & 1);
+        issue_qk(g, T == 1);
+        for (int j = 0; j < T; ++j, ++g) {
+          const int s = g % kAtRing;
+          mbar_wait(&sb->v_full[s], (g / kAtRing) & 1);
+          mbar_wait(&sb->p_full, g & 1);
+          tc_fence_after();
+          const uint32_t d = tmem + kAtSlot0 + kAtSlot * j;
+          const uint32_t v_addr = smem_u32(sV + s * kAtVBytes);
 #pragma unroll
-        for (int part = 0; part < 2; ++part) {
+          for (int part = 0; part < 2; ++part) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {                 // K step = 16 keys = 8 columns of chunk ks / 2
-            const uint64_t v_desc = umma_desc_sw128(v_addr + (ks >> 2) * kAtVAtom) + 2 * (ks & 3);
-            umma_f16_ts(d, tmem + (ks >> 1) * 32 + part * 16 + (ks & 1) * 8, v_desc, idesc_o, (part | ks) != 0);
+            for (int ks = 0; ks < 8; ++ks) {               // K step = 16 keys = 8 columns of chunk ks / 2
+              const uint64_t v_desc = umma_desc_sw128(v_addr + (ks >> 2) * kAtVAtom) + 2 * (ks & 3);
+              umma_f16_ts(d, tmem + (ks >> 1) * 32 + part * 16 + (ks & 1) * 8, v_desc, idesc_o, (part | ks) != 0);
+            }
           }
+          umma_commit(&sb->v_empty[s]);
+          if (g < 15) AT_STAMP(48 + g);
+          if (j + 1 < T) issue_qk(g + 1, j + 2 == T);
         }
-        umma_commit(&sb->v_empty[s]);
-        if (j < 15) AT_STAMP(48 + j);
-        if (j + 1 < T) issue_qk(j + 1);
+        umma_commit(&sb->all_done);                        // every PV of this item has completed
       }
-      umma_commit(&sb->all_done);
     }
     __syncwarp();
   } else {
     // ===================== softmax warps ========================================================
     const int row = warp * 32 + lane;                      // query row == TMEM lane
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-    for (int j = 0; j < T; ++j) {
-      mbar_wait(&sb->s_full, j & 1);
-      tc_fence_after();
-      if (threadIdx.x == 0 && j < 16) AT_STAMP(64 + 4 * j);
-      float m = -INFINITY;
+    const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    int g = 0;                                             // running tile index
+    for (int n = 0; n < my_items; ++n) {
+      for (int j = 0; j < T; ++j, ++g) {
+        mbar_wait(&sb->s_full, g & 1);
+        tc_fence_after();
+        if (threadIdx.x == 0 && g < 16) AT_STAMP(64 + 4 * g);
+        float m = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {                        // pass 1: row maximum
-        uint32_t r[32];
-        tmem_ld_32x32(t_lane + c * 32, r);
-        tmem_ld_wait();
-        m = fmaxf(m, at_max32(r));
-      }
-      if (threadIdx.x == 0 && j < 16) AT_STAMP(65 + 4 * j);
-      float l = 0.f;
+        for (int c = 0; c < 4; ++c) {                      // pass 1: row maximum
+          uint32_t r[32];
+          tmem_ld_32x32(t_lane + c * 32, r);
+          tmem_ld_wait();
+          m = fmaxf(m, at_max32(r));
+        }
+        if (threadIdx.x == 0 && g < 16) AT_STAMP(65 + 4 * g);
+        float l = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {                        // pass 2: exponentials, P written in place
-        uint32_t r[32];
-        tmem_ld_32x32(t_lane + c * 32, r);
-        tmem_ld_wait();
-        l += at_exp_store32(r, m, t_lane + c * 32);
+        for (int c = 0; c < 4; ++c) {                      // pass 2: exponentials, P written in place
+          uint32_t r[32];
+          tmem_ld_32x32(t_lane + c * 32, r);
+          tmem_ld_wait();
+          l += at_exp_store32(r, m, t_lane + c * 32);
+        }
+        sML[j * kAtTile + row] = make_float2(m, l);
+        tmem_st_wait();
+        tc_fence_before();
+        at_arrive(&sb->p_full);
+        if (threadIdx.x == 0 && g < 16) AT_STAMP(67 + 4 * g);
       }
-      sML[j * kAtTile + row] = make_float2(m, l);
-      tmem_st_wait();
+      // ===================== combine the key tiles, normalise, write the operand ================
+      // (the next item's first Q K^T already runs; its first P V waits for this thread's next p_full arrival, i.e.
+      //  until every row has finished reading the output slots below)
+      mbar_wait(&sb->all_done, n & 1);
+      tc_fence_after();
+      if (threadIdx.x == 0 && n == 0) AT_STAMP(125);
+      float m = -INFINITY;
+      for (int j = 0; j < T; ++j) m = fmaxf(m, sML[j * kAtTile + row].x);
+      float L = 0.f;
+      float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < T; ++j) {
+        const float2 ml = sML[j * kAtTile + row];
+        const float wgt = at_ex2(ml.x - m);
+        L = fmaf(wgt, ml.y, L);
+        uint32_t r[16];
+        tmem_ld_32x16(t_lane + kAtSlot0 + kAtSlot * j, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < 8; ++d) o[d] = fmaf(wgt, __uint_as_float(r[d]) + __uint_as_float(r[8 + d]), o[d]);
+      }
       tc_fence_before();
-      at_arrive(&sb->p_full);
-      if (threadIdx.x == 0 && j < 16) AT_STAMP(67 + 4 * j);
-    }
-    // ===================== combine the key tiles, normalise, write the operand ==================
-    mbar_wait(&sb->all_done, 0);
-    tc_fence_after();
-    if (threadIdx.x == 0) AT_STAMP(125);
-    float m = -INFINITY;
-    for (int j = 0; j < T; ++j) m = fmaxf(m, sML[j * kAtTile + row].x);
-    float L = 0.f;
-    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < T; ++j) {
-      const float2 ml = sML[j * kAtTile + row];
-      const float wgt = at_ex2(ml.x - m);
-      L = fmaf(wgt, ml.y, L);
-      uint32_t r[16];
-      tmem_ld_32x16(t_lane + kAtSlot0 + kAtSlot * j, r);
-      tmem_ld_wait();
+      const float inv = 1.0f / L;
+      uint32_t h[4], lo[4];
 #pragma unroll
-      for (int d = 0; d < 8; ++d) o[d] = fmaf(wgt, __uint_as_float(r[d]) + __uint_as_float(r[8 + d]), o[d]);
+      for (int e = 0; e < 4; ++e) at_split2(o[2 * e] * inv, o[2 * e + 1] * inv, h[e], lo[e]);
+      // W-padded operand layout (B, W+2, H, C): token n lands at padded pixel H + n
+      const int item = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
+      const int qb = item % T, bh = item / T;
+      const size_t oi = (static_cast<size_t>(bh / heads) * (N + 2 * H) + H + qb * kAtTile + row) * C + (bh % heads) * 8;
+      *reinterpret_cast<uint4*>(out + oi) = make_uint4(h[0], h[1], h[2], h[3]);
+      if (out_lo) *reinterpret_cast<uint4*>(out_lo + oi) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      if (threadIdx.x == 0 && n == 0) AT_STAMP(126);
     }
-    const float inv = 1.0f / L;
-    uint32_t h[4], lo[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) at_split2(o[2 * e] * inv, o[2 * e + 1] * inv, h[e], lo[e]);
-    // W-padded operand layout (B, W+2, H, C): token n lands at padded pixel H + n
-    const size_t oi = (static_cast<size_t>(b) * (N + 2 * H) + H + q0 + row) * C + hd * 8;
-    *reinterpret_cast<uint4*>(out + oi) = make_uint4(h[0], h[1], h[2], h[3]);
-    if (out_lo) *reinterpret_cast<uint4*>(out_lo + oi) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    if (threadIdx.x == 0) AT_STAMP(126);
   }
   tc_fence_before();
   __syncthreads();
@@ -387,8 +422,17 @@ int rldm_attention_umma(const float* qkv, uint16_t* out, uint16_t* out_lo, int B
                                    static_cast<int>(smem)));
     attr_smem = smem;
   }
-  RLDM_CUDA(launch_pdl(attention_umma_kernel, dim3(N / kAtTile, C / 8, B), dim3(kAtThreads), smem, as_stream(stream), qkv,
-                       reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H, g_attn_dbg));
+  static int n_sms = 0;
+  if (n_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sms <= 0) n_sms = 148;
+  }
+  const int items = B * (C / 8) * T;
+  const int ctas = items < 2 * n_sms ? items : 2 * n_sms;            // two persistent CTAs per SM
+  RLDM_CUDA(launch_pdl(attention_umma_kernel, dim3(ctas), dim3(kAtThreads), smem, as_stream(stream), qkv,
+                       reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H, B, g_attn_dbg));
   RLDM_LAUNCH_CHECK();
   return 0;
 }
