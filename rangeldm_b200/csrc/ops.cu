@@ -175,40 +175,60 @@ prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, 
   int pl = threadIdx.x / oct_per_pix, oc = threadIdx.x - pl * oct_per_pix;
   const int step_p = blockDim.x / oct_per_pix, step_o = blockDim.x - step_p * oct_per_pix;
   const int sh_h = (Ho & (Ho - 1)) == 0 ? 31 - __clz(Ho) : -1;
-  for (int i = threadIdx.x; i < total; i += blockDim.x, pl += step_p, oc += step_o) {
-    if (oc >= oct_per_pix) { oc -= oct_per_pix; ++pl; }
-    const int po = p_begin + pl;
-    const int c = oc << 3;
-    const int wp = sh_h >= 0 ? po >> sh_h : po / Ho;
-    const int ho = po - wp * Ho;
-    int wo = wp - 1;
-    const bool halo = wo < 0 || wo >= Wo;
-    if (wo < 0) wo += Wo;
-    if (wo >= Wo) wo -= Wo;
-    const size_t o = (static_cast<size_t>(b) * out_pix + po) * C + c;
-    if (halo && !circular) {
-      *reinterpret_cast<uint4*>(out + o) = make_uint4(0, 0, 0, 0);
-      if (out_lo) *reinterpret_cast<uint4*>(out_lo + o) = make_uint4(0, 0, 0, 0);
-      if (raw) *reinterpret_cast<uint4*>(raw + o) = make_uint4(0, 0, 0, 0);
-      if (raw_lo) *reinterpret_cast<uint4*>(raw_lo + o) = make_uint4(0, 0, 0, 0);
-      continue;
-    }
-    const int pin = (up == 2) ? (wo >> 1) * H + (ho >> 1) : wo * H + ho;
-    const size_t pix = static_cast<size_t>(b) * W * H + pin;
-    const float* src = (c < c0) ? x0 + pix * c0 + c : x1 + pix * c1 + (c - c0);
-    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
-    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-    float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-    if (raw) store_split8(v, raw, raw_lo, o);      // second output: the un-normalised operand (1x1 shortcut input)
-    if (norm) {
+  // two items per iteration: both items' loads are issued before either is consumed (the loop is latency-bound)
+  for (int i = threadIdx.x; i < total; i += 2 * blockDim.x) {
+    size_t o[2];
+    int cc[2];
+    bool live[2], zero[2];
+    float4 v0[2], v1[2];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[c + j], sf[c + j]);
+    for (int u = 0; u < 2; ++u) {
+      live[u] = i + u * static_cast<int>(blockDim.x) < total;
+      if (oc >= oct_per_pix) { oc -= oct_per_pix; ++pl; }
+      const int po = p_begin + pl;
+      const int c = oc << 3;
+      pl += step_p; oc += step_o;                         // advance to this thread's next item
+      const int wp = sh_h >= 0 ? po >> sh_h : po / Ho;
+      const int ho = po - wp * Ho;
+      int wo = wp - 1;
+      const bool halo = wo < 0 || wo >= Wo;
+      if (wo < 0) wo += Wo;
+      if (wo >= Wo) wo -= Wo;
+      o[u] = (static_cast<size_t>(b) * out_pix + po) * C + c;
+      cc[u] = c;
+      zero[u] = halo && !circular;
+      v0[u] = v1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live[u] && !zero[u]) {
+        const int pin = (up == 2) ? (wo >> 1) * H + (ho >> 1) : wo * H + ho;
+        const size_t pix = static_cast<size_t>(b) * W * H + pin;
+        const float* src = (c < c0) ? x0 + pix * c0 + c : x1 + pix * c1 + (c - c0);
+        v0[u] = __ldg(reinterpret_cast<const float4*>(src));
+        v1[u] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      }
     }
-    if (silu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+    for (int u = 0; u < 2; ++u) {
+      if (!live[u]) continue;
+      if (zero[u]) {
+        *reinterpret_cast<uint4*>(out + o[u]) = make_uint4(0, 0, 0, 0);
+        if (out_lo) *reinterpret_cast<uint4*>(out_lo + o[u]) = make_uint4(0, 0, 0, 0);
+        if (raw) *reinterpret_cast<uint4*>(raw + o[u]) = make_uint4(0, 0, 0, 0);
+        if (raw_lo) *reinterpret_cast<uint4*>(raw_lo + o[u]) = make_uint4(0, 0, 0, 0);
+        continue;
+      }
+      const int c = cc[u];
+      float v[8] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w, v1[u].x, v1[u].y, v1[u].z, v1[u].w};
+      if (raw) store_split8(v, raw, raw_lo, o[u]);    // second output: the un-normalised operand (1x1 shortcut input)
+      if (norm) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[c + j], sf[c + j]);
+      }
+      if (silu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+      }
+      store_split8(v, out, out_lo, o[u]);
     }
-    store_split8(v, out, out_lo, o);
   }
 }
 
