@@ -130,6 +130,29 @@ __device__ __forceinline__ float at_exp_store32(const uint32_t (&r)[32], float m
   return l0 + l1;
 }
 
+// The same with packed fp32 arithmetic (add.f32x2 / fma.f32x2: two lanes per issue slot -- the pipelined kernel is
+// bound by instruction issue, not by MUFU) and without the row sum (the pipelined kernel takes it from the MMA).
+__device__ __forceinline__ void at_exp_store32_packed(const uint32_t (&r)[32], float m, uint32_t t_chunk) {
+  uint32_t h[16], lo[16];
+  const float2 nm = make_float2(-m, -m), neg1 = make_float2(-1.f, -1.f);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const float2 d = __fadd2_rn(make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), nm);
+    const float2 p = make_float2(at_ex2(d.x), at_ex2(d.y));
+    const __half2 hh = __floats2half2_rn(p.x, p.y);
+    const float2 res = __ffma2_rn(__half22float2(hh), neg1, p);       // p - float(hi): exact
+    h[e] = at_pack(hh);
+    lo[e] = at_pack(__floats2half2_rn(res.x, res.y));
+  }
+  tmem_st_32x16(t_chunk, h);
+  tmem_st_32x16(t_chunk + 16, lo);
+}
+__device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
+
 // Persistent: gridDim.x CTAs (two per SM) walk over the work items (image, head, 128-query block); barriers, TMEM and
 // the K/V ring live across items, the loaders run ahead into the next item while the current one is still in its
 // softmax / combine phase, so prologue and tail are paid once per CTA instead of once per item.
@@ -399,6 +422,305 @@ attention_umma_kernel(const float* __restrict__ qkv, __half* __restrict__ out, _
   if (warp == 4) tmem_dealloc<kAtTmemCols>(tmem);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Pipelined variant (default): the same arithmetic with 64-key tiles, THREE S/P buffers (64 TMEM columns each) and
+// the per-tile outputs folded into registers, so Q K^T of tiles j+1..j+3 is already in TMEM while the softmax
+// warps work on tile j -- their MUFU stream never waits for the MMA / barrier round trip.
+//   * TMEM (256 columns per CTA, two CTAs per SM): S/P buffers at columns 0, 64, 128; two 32-column output slots at
+//     192 and 224 (ping-pong).
+//   * the V^T operand carries a row of ONES below [V_hi | V_lo] (N = 32: rows 0-7 v_hi, 8-15 v_lo, 16 ones, 17-31
+//     zeros), so column 16 of an output slot is the tile's row sum: the softmax threads (issue-bound) spend no
+//     instructions on it.
+//   * after P(j) is handed to the MMA warp, the first thread of each row folds the finished slot of tile j-1 into its
+//     running (max, sum, o[8]) registers with the usual 2^(m_old - m_new) rescale -- no per-tile state in shared memory.
+//   * K/V ring of 6 tiles (8 KB + 4 KB each); loader warp w owns the global tiles g = w mod 3.
+constexpr int kApKT = 64;                       // keys per tile
+constexpr int kApRing = 6;
+constexpr int kApKBytes = kApKT * 128;          // 8 KB
+constexpr int kApVBytes = 32 * 128;             // 4 KB: one K-atom of 64 keys x 32 rows (16 written per tile)
+constexpr int kApSlot0 = 192;
+constexpr int kApSlot = 32;                     // TMEM columns per output slot
+constexpr int kApThreads = 12 * 32;            // 8 softmax warps, MMA warp, 3 loader warps
+
+struct AttnPipeSmem {
+  uint64_t q_full, q_empty;
+  uint64_t k_full[kApRing], k_empty[kApRing], v_full[kApRing], v_empty[kApRing];
+  uint64_t s_full[3], p_full[3], o_full[2];
+  uint32_t tmem_ptr;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kApThreads, 2)
+attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half* __restrict__ out_lo, int N,
+                                int C, int H, int B) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kAtQBytes;                           // [6][8 KB]
+  uint8_t* sV = sK + kApRing * kApKBytes;                 // [6][4 KB]
+  float* sX = reinterpret_cast<float*>(sV + kApRing * kApVBytes);   // [2 parities][2 halves][128] row-max exchange
+  AttnPipeSmem* sb = reinterpret_cast<AttnPipeSmem*>(sX + 4 * kAtTile);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t rowf = 3 * static_cast<size_t>(C);
+  const int heads = C / 8;
+  const int QB = N / kAtTile;                              // 128-query blocks per (image, head)
+  const int TS = N / kApKT;                                // key tiles per item
+  const int n_items = B * heads * QB;
+  const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  auto item_base = [&](int item, int& q0) -> const float* {
+    const int qb = item % QB, bh = item / QB;
+    q0 = qb * kAtTile;
+    return qkv + static_cast<size_t>(bh / heads) * N * rowf + (bh % heads) * 8;
+  };
+
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    // one arrival per WARP on the thread-filled barriers (lanes fence, __syncwarp, lane 0 arrives): hundreds of
+    // per-thread arrivals on one shared-memory word would serialise every tile
+    mbar_init(&sb->q_full, 3);
+    mbar_init(&sb->q_empty, 1);
+    for (int i = 0; i < kApRing; ++i) {
+      mbar_init(&sb->k_full[i], 1); mbar_init(&sb->k_empty[i], 1);
+      mbar_init(&sb->v_full[i], 1); mbar_init(&sb->v_empty[i], 1);
+    }
+    for (int i = 0; i < 3; ++i) { mbar_init(&sb->s_full[i], 1); mbar_init(&sb->p_full[i], 8); }
+    for (int i = 0; i < 2; ++i) mbar_init(&sb->o_full[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc<kAtTmemCols>(&sb->tmem_ptr);
+  // rows 16-31 of every V^T tile never change: row 16 = 1.0 (fp16) for all 64 keys, the rest zero
+  for (int i = threadIdx.x; i < kApRing * 128; i += kApThreads) {
+    const uint32_t v = (i & 127) < 8 ? 0x3C003C00u : 0u;
+    at_sts128(smem_u32(sV + (i >> 7) * kApVBytes + 2048) + (i & 127) * 16, v, v, v, v);
+  }
+  at_fence_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, sb->tmem_ptr, 0);
+  pdl_wait();
+
+  if (warp >= 9) {
+    // ===================== loaders ==============================================================
+    const int w = warp - 9;
+    const int qt = threadIdx.x - 9 * 32;                   // 0..95: Q rows qt and qt + 96
+    const int total_tiles = my_items * TS;
+    // K: lane <-> rows lane, lane + 32;  V: lane <-> keys 2 lane, 2 lane + 1.  The next tile is always in registers.
+    float4 ka[2], kb[2], va[2], vb[2];
+    auto load_tile = [&](int g) {
+      int q0;
+      const float* base = item_base(static_cast<int>(blockIdx.x) + (g / TS) * static_cast<int>(gridDim.x), q0);
+      const int t = g % TS;
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const float* kp = base + static_cast<size_t>(t * kApKT + lane + rr * 32) * rowf + C;
+        ka[rr] = __ldg(reinterpret_cast<const float4*>(kp)); kb[rr] = __ldg(reinterpret_cast<const float4*>(kp) + 1);
+        const float* vp = base + static_cast<size_t>(t * kApKT + 2 * lane + rr) * rowf + 2 * C;
+        va[rr] = __ldg(reinterpret_cast<const float4*>(vp)); vb[rr] = __ldg(reinterpret_cast<const float4*>(vp) + 1);
+      }
+    };
+    auto load_q = [&](int n) {                             // Q rows: [q_hi | q_lo | q_hi | 0], scale folded in
+      int q0;
+      const float* base = item_base(static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x), q0);
+      float4 qa[2], qb[2];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int i = qt + rr * 96;
+        if (i < kAtTile) {
+          const float* qp = base + static_cast<size_t>(q0 + i) * rowf;
+          qa[rr] = __ldg(reinterpret_cast<const float4*>(qp)); qb[rr] = __ldg(reinterpret_cast<const float4*>(qp) + 1);
+        }
+      }
+      mbar_wait(&sb->q_empty, (n & 1) ^ 1);               // every Q K^T of the previous item has completed
+      const float qs = 0.35355339059327373f * 1.4426950408889634f;
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int i = qt + rr * 96, sw = i & 7;
+        if (i < kAtTile) {
+          uint32_t h[4], l[4];
+          at_split2(qa[rr].x * qs, qa[rr].y * qs, h[0], l[0]); at_split2(qa[rr].z * qs, qa[rr].w * qs, h[1], l[1]);
+          at_split2(qb[rr].x * qs, qb[rr].y * qs, h[2], l[2]); at_split2(qb[rr].z * qs, qb[rr].w * qs, h[3], l[3]);
+          const uint32_t r = smem_u32(sQ) + i * 128;
+          at_sts128(r + ((0 ^ sw) << 4), h[0], h[1], h[2], h[3]);
+          at_sts128(r + ((1 ^ sw) << 4), l[0], l[1], l[2], l[3]);
+          at_sts128(r + ((2 ^ sw) << 4), h[0], h[1], h[2], h[3]);
+          at_sts128(r + ((3 ^ sw) << 4), 0u, 0u, 0u, 0u);
+        }
+      }
+      at_fence_async();
+      __syncwarp();
+      if (lane == 0) at_arrive(&sb->q_full);
+    };
+    if (w < total_tiles) load_tile(w);
+    int q_next = 0;
+    for (int g = w; g < total_tiles; g += 3) {
+      while (q_next <= g / TS) load_q(q_next++);
+      const int slot = g % kApRing;
+      const uint32_t ph = ((g / kApRing) & 1) ^ 1;
+      mbar_wait(&sb->k_empty[slot], ph);
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int i = lane + rr * 32, sw = i & 7;
+        uint32_t h[4], l[4];
+        at_split2(ka[rr].x, ka[rr].y, h[0], l[0]); at_split2(ka[rr].z, ka[rr].w, h[1], l[1]);
+        at_split2(kb[rr].x, kb[rr].y, h[2], l[2]); at_split2(kb[rr].z, kb[rr].w, h[3], l[3]);
+        const uint32_t kr = smem_u32(sK + slot * kApKBytes) + i * 128;    // K row: [k_hi | k_hi | k_lo | 0]
+        at_sts128(kr + ((0 ^ sw) << 4), h[0], h[1], h[2], h[3]);
+        at_sts128(kr + ((1 ^ sw) << 4), h[0], h[1], h[2], h[3]);
+        at_sts128(kr + ((2 ^ sw) << 4), l[0], l[1], l[2], l[3]);
+        at_sts128(kr + ((3 ^ sw) << 4), 0u, 0u, 0u, 0u);
+      }
+      at_fence_async();
+      __syncwarp();
+      if (lane == 0) at_arrive(&sb->k_full[slot]);
+      mbar_wait(&sb->v_empty[slot], ph);
+      {
+        // V^T: row d holds v_hi[d], row 8 + d holds v_lo[d]; this lane's 2 keys are 4 bytes of chunk lane / 4
+        const uint32_t vbase = smem_u32(sV + slot * kApVBytes) + ((lane & 3) << 2);
+        const int chunk = lane >> 2;
+        const float v0[8] = {va[0].x, va[0].y, va[0].z, va[0].w, vb[0].x, vb[0].y, vb[0].z, vb[0].w};
+        const float v1[8] = {va[1].x, va[1].y, va[1].z, va[1].w, vb[1].x, vb[1].y, vb[1].z, vb[1].w};
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          uint32_t h01, l01;
+          at_split2(v0[d], v1[d], h01, l01);
+          const uint32_t off = static_cast<uint32_t>((chunk ^ d) << 4);   // rows d and 8 + d: (row & 7) == d
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(vbase + d * 128 + off), "r"(h01) : "memory");
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(vbase + (8 + d) * 128 + off), "r"(l01) : "memory");
+        }
+      }
+      at_fence_async();
+      __syncwarp();
+      if (lane == 0) at_arrive(&sb->v_full[slot]);
+      if (g + 3 < total_tiles) load_tile(g + 3);
+    }
+    while (q_next < my_items) load_q(q_next++);
+  } else if (warp == 8) {
+    // ===================== MMA issuer ===========================================================
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, kApKT);
+      constexpr uint32_t idesc_o = umma_idesc_f16(128, kApSlot);
+      const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ));
+      auto issue_qk = [&](int g, bool last_of_item) {      // S buffer g % 3 is free: P V of tile g - 3 was issued before
+        const int slot = g % kApRing, bs = g % 3;
+        mbar_wait(&sb->k_full[slot], (g / kApRing) & 1);
+        tc_fence_after();
+        const uint64_t k_desc = umma_desc_sw128(smem_u32(sK + slot * kApKBytes));
+        const uint32_t d = tmem + bs * kApKT;
+        umma_f16(d, q_desc, k_desc, idesc_s, 0u);
+        umma_f16(d, q_desc + 2, k_desc + 2, idesc_s, 1u);
+        umma_commit(&sb->s_full[bs]);
+        umma_commit(&sb->k_empty[slot]);
+        if (last_of_item) umma_commit(&sb->q_empty);
+      };
+      int g = 0;
+      for (int n = 0; n < my_items; ++n) {
+        mbar_wait(&sb->q_full, n & 1);
+        for (int t = 0; t < 3 && t < TS; ++t) issue_qk(g + t, t + 1 == TS);
+        for (int t = 0; t < TS; ++t, ++g) {
+          const int slot = g % kApRing, bs = g % 3, bo = g & 1;
+          mbar_wait(&sb->v_full[slot], (g / kApRing) & 1);
+          // p_full(g): every softmax thread has written P(g) and, one tile earlier, folded output slot bo of tile g - 2
+          mbar_wait(&sb->p_full[bs], (g / 3) & 1);
+          tc_fence_after();
+          const uint32_t d = tmem + kApSlot0 + kApSlot * bo;
+          const uint64_t v_desc0 = umma_desc_sw128(smem_u32(sV + slot * kApVBytes));
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)                 // K step = 16 keys = 8 columns of chunk ks / 2
+              umma_f16_ts(d, tmem + bs * kApKT + (ks >> 1) * 32 + part * 16 + (ks & 1) * 8, v_desc0 + 2 * ks, idesc_o,
+                          (part | ks) != 0);
+          }
+          umma_commit(&sb->o_full[bo]);
+          umma_commit(&sb->v_empty[slot]);
+          if (t + 3 < TS) issue_qk(g + 3, t + 4 == TS);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax warps ========================================================
+    // warp = (TMEM lane quadrant, key half): 32 query rows x the 32 keys of chunk `hf` of every 64-key tile; two
+    // threads per row -> four softmax warps per SM sub-partition with two CTAs resident.  The hf == 0 thread of a row
+    // also owns the row's running (max, sum, o[8]).
+    const int quad = warp & 3, hf = warp >> 2;
+    const int row = quad * 32 + lane;                      // query row == TMEM lane
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t x_mine = smem_u32(sX) + (hf * kAtTile + row) * 4, x_other = smem_u32(sX) + ((hf ^ 1) * kAtTile + row) * 4;
+    int g = 0;
+    for (int n = 0; n < my_items; ++n) {
+      float m_run = -INFINITY, l_run = 0.f;
+      float2 o[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      float m_prev = 0.f;                                  // max of the tile whose output is still in TMEM
+      auto fold = [&](int gf) {                            // hf == 0 only
+        const float m_new = fmaxf(m_run, m_prev);
+        const float a = at_ex2(m_run - m_new), c = at_ex2(m_prev - m_new);
+        m_run = m_new;
+        mbar_wait(&sb->o_full[gf & 1], (gf >> 1) & 1);
+        tc_fence_after();
+        uint32_t r[16];
+        const uint32_t t_o = t_lane + kApSlot0 + kApSlot * (gf & 1);
+        tmem_ld_32x16(t_o, r);
+        const float l_tile = __uint_as_float(tmem_ld_32x1(t_o + 16));
+        tmem_ld_wait();
+        const float2 a2 = make_float2(a, a), c2 = make_float2(c, c);
+        l_run = fmaf(l_run, a, l_tile * c);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const float2 v = __fadd2_rn(make_float2(__uint_as_float(r[2 * d]), __uint_as_float(r[2 * d + 1])),
+                                      make_float2(__uint_as_float(r[8 + 2 * d]), __uint_as_float(r[9 + 2 * d])));
+          o[d] = __ffma2_rn(o[d], a2, __fmul2_rn(v, c2));
+        }
+      };
+      for (int t = 0; t < TS; ++t, ++g) {
+        const int bs = g % 3;
+        const uint32_t t_s = t_lane + bs * kApKT + hf * 32;      // this warp's 32 score columns
+        mbar_wait(&sb->s_full[bs], (g / 3) & 1);
+        tc_fence_after();
+        uint32_t r[32];                                    // S is read from TMEM once
+        tmem_ld_32x32(t_s, r);
+        tmem_ld_wait();
+        float m = at_max32(r);
+        const uint32_t xo = (g & 1) * 2 * kAtTile * 4;     // exchange the half-row maxima with the partner warp
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(x_mine + xo), "f"(m) : "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        float m_o;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m_o) : "r"(x_other + xo) : "memory");
+        m = fmaxf(m, m_o);
+        at_exp_store32_packed(r, m, t_s);                  // P = 2^(S - m) in place: [hi 16 | lo 16]
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) at_arrive(&sb->p_full[bs]);
+        // the previous tile's P V has long finished; its slot is overwritten by tile g + 1, whose P is handed over
+        // only after this fold (program order + tcgen05.wait::ld)
+        if (hf == 0 && t > 0) fold(g - 1);
+        m_prev = m;
+      }
+      if (hf == 0) {
+        fold(g - 1);
+        tc_fence_before();
+        const float inv = 1.0f / l_run;
+        uint32_t h[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) at_split2(o[e].x * inv, o[e].y * inv, h[e], lo[e]);
+        // W-padded operand layout (B, W+2, H, C): token n lands at padded pixel H + n
+        const int item = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
+        const int qb = item % QB, bh = item / QB;
+        const size_t oi = (static_cast<size_t>(bh / heads) * (N + 2 * H) + H + qb * kAtTile + row) * C + (bh % heads) * 8;
+        *reinterpret_cast<uint4*>(out + oi) = make_uint4(h[0], h[1], h[2], h[3]);
+        if (out_lo) *reinterpret_cast<uint4*>(out_lo + oi) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<kAtTmemCols>(tmem);
+}
+
 }  // namespace rldm
 
 using namespace rldm;
@@ -409,11 +731,34 @@ extern "C" void rldm_debug_attn_timestamps(long long* dev_buf) { g_attn_dbg = de
 // Host entry used by rldm_attention (ops.cu).  Returns -1 when the shape is outside this kernel's range (the caller
 // then takes the mma.sync / CUDA-core kernels), 0 on success, > 0 on error.
 int rldm_attention_umma(const float* qkv, uint16_t* out, uint16_t* out_lo, int B, int N, int C, int H, void* stream) {
-  // Short sequences (N < 512: two key tiles or fewer) are dominated by the per-CTA prologue and tail; the mma.sync
-  // kernel is faster there (16.6 us vs 19.4 us for N = 256, C = 256, B = 8 on B200).  RLDM_ATTN_TCGEN05=1 forces this one.
-  if (N % kAtTile != 0 || N / kAtTile > kAtMaxTiles || C % 8 != 0) return -1;
-  if (N < 4 * kAtTile && !getenv("RLDM_ATTN_TCGEN05")) return -1;
+  // Very short sequences (N = 128: one query block per head) are all prologue and tail; the mma.sync kernel takes
+  // them.  N = 256, C = 256, B = 8 on B200: 16.9 us here vs 18.2 us (mma.sync).  RLDM_ATTN_TCGEN05=1 forces this one.
+  const bool serial = getenv("RLDM_ATTN_SERIAL") != nullptr;      // one-buffer kernel: per-tile output slots, N <= 1024
+  if (N % kAtTile != 0 || C % 8 != 0 || (serial && N / kAtTile > kAtMaxTiles)) return -1;
+  if (N < 2 * kAtTile && !getenv("RLDM_ATTN_TCGEN05")) return -1;
   const int T = N / kAtTile;
+  static int n_sms_p = 0;
+  if (n_sms_p == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sms_p, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sms_p <= 0) n_sms_p = 148;
+  }
+  if (!serial) {                             // pipelined kernel (three S/P buffers, outputs folded into registers)
+    const size_t smem_p = 1024 + kAtQBytes + kApRing * (kApKBytes + kApVBytes) + 4 * kAtTile * 4 + sizeof(AttnPipeSmem);
+    static bool attr_p = false;
+    if (!attr_p) {
+      RLDM_CUDA(cudaFuncSetAttribute(attention_umma_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem_p)));
+      attr_p = true;
+    }
+    const int items_p = B * (C / 8) * T;
+    const int ctas_p = items_p < 2 * n_sms_p ? items_p : 2 * n_sms_p;
+    RLDM_CUDA(launch_pdl(attention_umma_pipelined_kernel, dim3(ctas_p), dim3(kApThreads), smem_p, as_stream(stream), qkv,
+                         reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H, B));
+    RLDM_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = 1024 + kAtQBytes + kAtRing * (kAtKBytes + kAtVBytes) + static_cast<size_t>(T) * kAtTile * 8 +
                       sizeof(AttnSmem);
   static size_t attr_smem = 0;
