@@ -427,13 +427,18 @@ attention_umma_kernel(const float* __restrict__ qkv, __half* __restrict__ out, _
 // Pipelined variant (default): the same arithmetic with 64-key tiles, THREE S/P buffers (64 TMEM columns each) and
 // the per-tile outputs folded into registers, so Q K^T of tiles j+1..j+3 is already in TMEM while the softmax
 // warps work on tile j -- their MUFU stream never waits for the MMA / barrier round trip.
+//   * the key tiles of a CTA form ONE stream across its work items (Q is double-buffered), so Q K^T of the next
+//     item's first tiles is issued while the softmax warps finish the current item.
 //   * TMEM (256 columns per CTA, two CTAs per SM): S/P buffers at columns 0, 64, 128; two 32-column output slots at
-//     192 and 224 (ping-pong).
+//     192 and 224.
+//   * two softmax GROUPS of four warps (thread = query row = TMEM lane in both): group 0 takes the even key tiles and
+//     output slot 0, group 1 the odd tiles and slot 1.  Each group keeps its own running (max, sum, o[8]) in registers
+//     (fold of the group's previous tile, with the usual 2^(m_old - m_new) rescale, right after P of the current tile
+//     is written); the two partial results of a row meet ONCE PER ITEM in shared memory.  No per-tile exchange and
+//     no per-tile state in shared memory.
 //   * the V^T operand carries a row of ONES below [V_hi | V_lo] (N = 32: rows 0-7 v_hi, 8-15 v_lo, 16 ones, 17-31
-//     zeros), so column 16 of an output slot is the tile's row sum: the softmax threads (issue-bound) spend no
-//     instructions on it.
-//   * after P(j) is handed to the MMA warp, the first thread of each row folds the finished slot of tile j-1 into its
-//     running (max, sum, o[8]) registers with the usual 2^(m_old - m_new) rescale -- no per-tile state in shared memory.
+//     zeros), so column 16 of an output slot is the tile's row sum, and the elementwise work uses packed fp32
+//     (add.f32x2 / fma.f32x2): the softmax threads are bound by instruction issue as much as by MUFU.
 //   * K/V ring of 6 tiles (8 KB + 4 KB each); loader warp w owns the global tiles g = w mod 3.
 constexpr int kApKT = 64;                       // keys per tile
 constexpr int kApRing = 6;
@@ -441,12 +446,14 @@ constexpr int kApKBytes = kApKT * 128;          // 8 KB
 constexpr int kApVBytes = 32 * 128;             // 4 KB: one K-atom of 64 keys x 32 rows (16 written per tile)
 constexpr int kApSlot0 = 192;
 constexpr int kApSlot = 32;                     // TMEM columns per output slot
+constexpr int kApXFloats = 10;                  // (max, sum, o[8]) of group 1 per row
 constexpr int kApThreads = 12 * 32;            // 8 softmax warps, MMA warp, 3 loader warps
 
 struct AttnPipeSmem {
-  uint64_t q_full, q_empty;
+  uint64_t q_full[2], q_empty[2];
   uint64_t k_full[kApRing], k_empty[kApRing], v_full[kApRing], v_empty[kApRing];
   uint64_t s_full[3], p_full[3], o_full[2];
+  uint64_t x_full, x_empty;
   uint32_t tmem_ptr;
   uint32_t pad;
 };
@@ -456,19 +463,20 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
                                 int C, int H, int B) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kAtQBytes;                           // [6][8 KB]
+  uint8_t* sQ = smem;                                     // [2][16 KB]
+  uint8_t* sK = sQ + 2 * kAtQBytes;                       // [6][8 KB]
   uint8_t* sV = sK + kApRing * kApKBytes;                 // [6][4 KB]
-  float* sX = reinterpret_cast<float*>(sV + kApRing * kApVBytes);   // [2 parities][2 halves][128] row-max exchange
-  AttnPipeSmem* sb = reinterpret_cast<AttnPipeSmem*>(sX + 4 * kAtTile);
+  float* sX = reinterpret_cast<float*>(sV + kApRing * kApVBytes);   // [10][128]: group 1's partial result of an item
+  AttnPipeSmem* sb = reinterpret_cast<AttnPipeSmem*>(sX + kApXFloats * kAtTile);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t rowf = 3 * static_cast<size_t>(C);
   const int heads = C / 8;
   const int QB = N / kAtTile;                              // 128-query blocks per (image, head)
-  const int TS = N / kApKT;                                // key tiles per item
+  const int TS = N / kApKT;                                // key tiles per item (even, >= 4)
   const int n_items = B * heads * QB;
   const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int total_tiles = my_items * TS;
   auto item_base = [&](int item, int& q0) -> const float* {
     const int qb = item % QB, bh = item / QB;
     q0 = qb * kAtTile;
@@ -479,14 +487,15 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
   if (threadIdx.x == 0) {
     // one arrival per WARP on the thread-filled barriers (lanes fence, __syncwarp, lane 0 arrives): hundreds of
     // per-thread arrivals on one shared-memory word would serialise every tile
-    mbar_init(&sb->q_full, 3);
-    mbar_init(&sb->q_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&sb->q_full[i], 3); mbar_init(&sb->q_empty[i], 1); }
     for (int i = 0; i < kApRing; ++i) {
       mbar_init(&sb->k_full[i], 1); mbar_init(&sb->k_empty[i], 1);
       mbar_init(&sb->v_full[i], 1); mbar_init(&sb->v_empty[i], 1);
     }
-    for (int i = 0; i < 3; ++i) { mbar_init(&sb->s_full[i], 1); mbar_init(&sb->p_full[i], 8); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&sb->s_full[i], 1); mbar_init(&sb->p_full[i], 4); }
     for (int i = 0; i < 2; ++i) mbar_init(&sb->o_full[i], 1);
+    mbar_init(&sb->x_full, 4);
+    mbar_init(&sb->x_empty, 4);
     mbar_fence_init();
   }
   if (warp == 8) tmem_alloc<kAtTmemCols>(&sb->tmem_ptr);
@@ -506,7 +515,6 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
     // ===================== loaders ==============================================================
     const int w = warp - 9;
     const int qt = threadIdx.x - 9 * 32;                   // 0..95: Q rows qt and qt + 96
-    const int total_tiles = my_items * TS;
     // K: lane <-> rows lane, lane + 32;  V: lane <-> keys 2 lane, 2 lane + 1.  The next tile is always in registers.
     float4 ka[2], kb[2], va[2], vb[2];
     auto load_tile = [&](int g) {
@@ -533,8 +541,9 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
           qa[rr] = __ldg(reinterpret_cast<const float4*>(qp)); qb[rr] = __ldg(reinterpret_cast<const float4*>(qp) + 1);
         }
       }
-      mbar_wait(&sb->q_empty, (n & 1) ^ 1);               // every Q K^T of the previous item has completed
+      mbar_wait(&sb->q_empty[n & 1], ((n >> 1) & 1) ^ 1);  // every Q K^T of item n - 2 has completed
       const float qs = 0.35355339059327373f * 1.4426950408889634f;
+      const uint32_t q_base = smem_u32(sQ + (n & 1) * kAtQBytes);
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const int i = qt + rr * 96, sw = i & 7;
@@ -542,7 +551,7 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
           uint32_t h[4], l[4];
           at_split2(qa[rr].x * qs, qa[rr].y * qs, h[0], l[0]); at_split2(qa[rr].z * qs, qa[rr].w * qs, h[1], l[1]);
           at_split2(qb[rr].x * qs, qb[rr].y * qs, h[2], l[2]); at_split2(qb[rr].z * qs, qb[rr].w * qs, h[3], l[3]);
-          const uint32_t r = smem_u32(sQ) + i * 128;
+          const uint32_t r = q_base + i * 128;
           at_sts128(r + ((0 ^ sw) << 4), h[0], h[1], h[2], h[3]);
           at_sts128(r + ((1 ^ sw) << 4), l[0], l[1], l[2], l[3]);
           at_sts128(r + ((2 ^ sw) << 4), h[0], h[1], h[2], h[3]);
@@ -551,12 +560,12 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
       }
       at_fence_async();
       __syncwarp();
-      if (lane == 0) at_arrive(&sb->q_full);
+      if (lane == 0) at_arrive(&sb->q_full[n & 1]);
     };
     if (w < total_tiles) load_tile(w);
     int q_next = 0;
     for (int g = w; g < total_tiles; g += 3) {
-      while (q_next <= g / TS) load_q(q_next++);
+      while (q_next < my_items && q_next <= (g + 3) / TS) load_q(q_next++);   // Q K^T runs three tiles ahead
       const int slot = g % kApRing;
       const uint32_t ph = ((g / kApRing) & 1) ^ 1;
       mbar_wait(&sb->k_empty[slot], ph);
@@ -602,111 +611,102 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_f16(128, kApKT);
       constexpr uint32_t idesc_o = umma_idesc_f16(128, kApSlot);
-      const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ));
-      auto issue_qk = [&](int g, bool last_of_item) {      // S buffer g % 3 is free: P V of tile g - 3 was issued before
+      int qk_n = 0, qk_t = 0;                              // (item, tile) of the next Q K^T
+      auto issue_qk = [&](int g) {      // S buffer g % 3 is free: P V of tile g - 3 was issued before
         const int slot = g % kApRing, bs = g % 3;
+        if (qk_t == 0) mbar_wait(&sb->q_full[qk_n & 1], (qk_n >> 1) & 1);
         mbar_wait(&sb->k_full[slot], (g / kApRing) & 1);
         tc_fence_after();
+        const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ + (qk_n & 1) * kAtQBytes));
         const uint64_t k_desc = umma_desc_sw128(smem_u32(sK + slot * kApKBytes));
         const uint32_t d = tmem + bs * kApKT;
         umma_f16(d, q_desc, k_desc, idesc_s, 0u);
         umma_f16(d, q_desc + 2, k_desc + 2, idesc_s, 1u);
         umma_commit(&sb->s_full[bs]);
         umma_commit(&sb->k_empty[slot]);
-        if (last_of_item) umma_commit(&sb->q_empty);
-      };
-      int g = 0;
-      for (int n = 0; n < my_items; ++n) {
-        mbar_wait(&sb->q_full, n & 1);
-        for (int t = 0; t < 3 && t < TS; ++t) issue_qk(g + t, t + 1 == TS);
-        for (int t = 0; t < TS; ++t, ++g) {
-          const int slot = g % kApRing, bs = g % 3, bo = g & 1;
-          mbar_wait(&sb->v_full[slot], (g / kApRing) & 1);
-          // p_full(g): every softmax thread has written P(g) and, one tile earlier, folded output slot bo of tile g - 2
-          mbar_wait(&sb->p_full[bs], (g / 3) & 1);
-          tc_fence_after();
-          const uint32_t d = tmem + kApSlot0 + kApSlot * bo;
-          const uint64_t v_desc0 = umma_desc_sw128(smem_u32(sV + slot * kApVBytes));
-#pragma unroll
-          for (int part = 0; part < 2; ++part) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)                 // K step = 16 keys = 8 columns of chunk ks / 2
-              umma_f16_ts(d, tmem + bs * kApKT + (ks >> 1) * 32 + part * 16 + (ks & 1) * 8, v_desc0 + 2 * ks, idesc_o,
-                          (part | ks) != 0);
-          }
-          umma_commit(&sb->o_full[bo]);
-          umma_commit(&sb->v_empty[slot]);
-          if (t + 3 < TS) issue_qk(g + 3, t + 4 == TS);
+        if (++qk_t == TS) {
+          umma_commit(&sb->q_empty[qk_n & 1]);
+          qk_t = 0;
+          ++qk_n;
         }
+      };
+      for (int g = 0; g < 3 && g < total_tiles; ++g) issue_qk(g);
+      for (int g = 0; g < total_tiles; ++g) {
+        const int slot = g % kApRing, bs = g % 3, bo = g & 1;
+        mbar_wait(&sb->v_full[slot], (g / kApRing) & 1);
+        // p_full(g): the owning group has written P(g) and, before that, folded output slot bo of tile g - 2
+        mbar_wait(&sb->p_full[bs], (g / 3) & 1);
+        tc_fence_after();
+        const uint32_t d = tmem + kApSlot0 + kApSlot * bo;
+        const uint64_t v_desc0 = umma_desc_sw128(smem_u32(sV + slot * kApVBytes));
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)                   // K step = 16 keys = 8 columns of chunk ks / 2
+            umma_f16_ts(d, tmem + bs * kApKT + (ks >> 1) * 32 + part * 16 + (ks & 1) * 8, v_desc0 + 2 * ks, idesc_o,
+                        (part | ks) != 0);
+        }
+        umma_commit(&sb->o_full[bo]);
+        umma_commit(&sb->v_empty[slot]);
+        if (g + 3 < total_tiles) issue_qk(g + 3);
       }
     }
     __syncwarp();
   } else {
     // ===================== softmax warps ========================================================
-    // warp = (TMEM lane quadrant, key half): 32 query rows x the 32 keys of chunk `hf` of every 64-key tile; two
-    // threads per row -> four softmax warps per SM sub-partition with two CTAs resident.  The hf == 0 thread of a row
-    // also owns the row's running (max, sum, o[8]).
-    const int quad = warp & 3, hf = warp >> 2;
+    const int quad = warp & 3, grp = warp >> 2;
     const int row = quad * 32 + lane;                      // query row == TMEM lane
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quad * 32) << 16);
-    const uint32_t x_mine = smem_u32(sX) + (hf * kAtTile + row) * 4, x_other = smem_u32(sX) + ((hf ^ 1) * kAtTile + row) * 4;
-    int g = 0;
-    for (int n = 0; n < my_items; ++n) {
-      float m_run = -INFINITY, l_run = 0.f;
-      float2 o[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-      float m_prev = 0.f;                                  // max of the tile whose output is still in TMEM
-      auto fold = [&](int gf) {                            // hf == 0 only
-        const float m_new = fmaxf(m_run, m_prev);
-        const float a = at_ex2(m_run - m_new), c = at_ex2(m_prev - m_new);
-        m_run = m_new;
-        mbar_wait(&sb->o_full[gf & 1], (gf >> 1) & 1);
-        tc_fence_after();
-        uint32_t r[16];
-        const uint32_t t_o = t_lane + kApSlot0 + kApSlot * (gf & 1);
-        tmem_ld_32x16(t_o, r);
-        const float l_tile = __uint_as_float(tmem_ld_32x1(t_o + 16));
-        tmem_ld_wait();
-        const float2 a2 = make_float2(a, a), c2 = make_float2(c, c);
-        l_run = fmaf(l_run, a, l_tile * c);
+    const uint32_t t_o = t_lane + kApSlot0 + kApSlot * grp; // this group's output slot
+    const uint32_t x_row = smem_u32(sX) + row * 4;
+    float m_run = -INFINITY, l_run = 0.f;
+    float2 o[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    float m_prev = 0.f;                                    // max of the group's tile whose output is still in TMEM
+    int k = 0;                                             // tiles this group has handed over so far
+    auto fold = [&]() {                                    // tile k - 1 of this group -> running state
+      const float m_new = fmaxf(m_run, m_prev);
+      const float a = at_ex2(m_run - m_new), c = at_ex2(m_prev - m_new);
+      m_run = m_new;
+      mbar_wait(&sb->o_full[grp], (k - 1) & 1);
+      tc_fence_after();
+      uint32_t r[16];
+      tmem_ld_32x16(t_o, r);
+      const float l_tile = __uint_as_float(tmem_ld_32x1(t_o + 16));
+      tmem_ld_wait();
+      const float2 a2 = make_float2(a, a), c2 = make_float2(c, c);
+      l_run = fmaf(l_run, a, l_tile * c);
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-          const float2 v = __fadd2_rn(make_float2(__uint_as_float(r[2 * d]), __uint_as_float(r[2 * d + 1])),
-                                      make_float2(__uint_as_float(r[8 + 2 * d]), __uint_as_float(r[9 + 2 * d])));
-          o[d] = __ffma2_rn(o[d], a2, __fmul2_rn(v, c2));
-        }
-      };
-      for (int t = 0; t < TS; ++t, ++g) {
-        const int bs = g % 3;
-        const uint32_t t_s = t_lane + bs * kApKT + hf * 32;      // this warp's 32 score columns
-        mbar_wait(&sb->s_full[bs], (g / 3) & 1);
-        tc_fence_after();
-        uint32_t r[32];                                    // S is read from TMEM once
-        tmem_ld_32x32(t_s, r);
-        tmem_ld_wait();
-        float m = at_max32(r);
-        const uint32_t xo = (g & 1) * 2 * kAtTile * 4;     // exchange the half-row maxima with the partner warp
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(x_mine + xo), "f"(m) : "memory");
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-        float m_o;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m_o) : "r"(x_other + xo) : "memory");
-        m = fmaxf(m, m_o);
-        at_exp_store32_packed(r, m, t_s);                  // P = 2^(S - m) in place: [hi 16 | lo 16]
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) at_arrive(&sb->p_full[bs]);
-        // the previous tile's P V has long finished; its slot is overwritten by tile g + 1, whose P is handed over
-        // only after this fold (program order + tcgen05.wait::ld)
-        if (hf == 0 && t > 0) fold(g - 1);
-        m_prev = m;
+      for (int d = 0; d < 4; ++d) {
+        const float2 v = __fadd2_rn(make_float2(__uint_as_float(r[2 * d]), __uint_as_float(r[2 * d + 1])),
+                                    make_float2(__uint_as_float(r[8 + 2 * d]), __uint_as_float(r[9 + 2 * d])));
+        o[d] = __ffma2_rn(o[d], a2, __fmul2_rn(v, c2));
       }
-      if (hf == 0) {
-        fold(g - 1);
-        tc_fence_before();
-        const float inv = 1.0f / l_run;
+    };
+    auto finalize = [&](int n) {                           // the two groups' partial results of item n meet
+      if (grp == 1) {
+        mbar_wait(&sb->x_empty, (n & 1) ^ 1);
+        const float vals[kApXFloats] = {m_run, l_run, o[0].x, o[0].y, o[1].x, o[1].y, o[2].x, o[2].y, o[3].x, o[3].y};
+#pragma unroll
+        for (int j = 0; j < kApXFloats; ++j)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(x_row + j * kAtTile * 4), "f"(vals[j]) : "memory");
+        __syncwarp();
+        if (lane == 0) at_arrive(&sb->x_full);
+      } else {
+        mbar_wait(&sb->x_full, n & 1);
+        float v[kApXFloats];
+#pragma unroll
+        for (int j = 0; j < kApXFloats; ++j)
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[j]) : "r"(x_row + j * kAtTile * 4) : "memory");
+        __syncwarp();
+        if (lane == 0) at_arrive(&sb->x_empty);
+        const float m = fmaxf(m_run, v[0]);
+        const float a0 = at_ex2(m_run - m), a1 = at_ex2(v[0] - m);
+        const float inv = 1.0f / fmaf(l_run, a0, v[1] * a1);
+        const float s0 = a0 * inv, s1 = a1 * inv;
         uint32_t h[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) at_split2(o[e].x * inv, o[e].y * inv, h[e], lo[e]);
+        for (int e = 0; e < 4; ++e)
+          at_split2(fmaf(o[e].x, s0, v[2 + 2 * e] * s1), fmaf(o[e].y, s0, v[3 + 2 * e] * s1), h[e], lo[e]);
         // W-padded operand layout (B, W+2, H, C): token n lands at padded pixel H + n
         const int item = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
         const int qb = item % QB, bh = item / QB;
@@ -714,6 +714,43 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
         *reinterpret_cast<uint4*>(out + oi) = make_uint4(h[0], h[1], h[2], h[3]);
         if (out_lo) *reinterpret_cast<uint4*>(out_lo + oi) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
+      m_run = -INFINITY; l_run = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = make_float2(0.f, 0.f);
+    };
+    for (int n = 0; n < my_items; ++n) {
+      for (int t = grp; t < TS; t += 2, ++k) {
+        const int g = n * TS + t, bs = g % 3;
+        const uint32_t t_s = t_lane + bs * kApKT;
+        mbar_wait(&sb->s_full[bs], (g / 3) & 1);
+        tc_fence_after();
+        uint32_t r[32];                                    // two cheap passes over the 64 scores of the row
+        tmem_ld_32x32(t_s, r);
+        tmem_ld_wait();
+        float m = at_max32(r);
+        tmem_ld_32x32(t_s + 32, r);
+        tmem_ld_wait();
+        m = fmaxf(m, at_max32(r));
+        at_exp_store32_packed(r, m, t_s + 32);             // P = 2^(S - m) in place: [hi 16 | lo 16] per 32-key chunk
+        tmem_ld_32x32(t_s, r);
+        tmem_ld_wait();
+        at_exp_store32_packed(r, m, t_s);
+        tmem_st_wait();
+        // the group's previous tile has long finished its P V; its slot is overwritten by P V of this tile, which is
+        // issued only after the arrival below
+        const bool item_done = k > 0 && t == grp;          // that tile was the last one of item n - 1
+        if (k > 0) fold();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) at_arrive(&sb->p_full[bs]);
+        if (item_done) finalize(n - 1);
+        m_prev = m;
+      }
+    }
+    if (k > 0) {
+      fold();
+      tc_fence_before();
+      finalize(my_items - 1);
     }
   }
   tc_fence_before();
@@ -744,8 +781,9 @@ int rldm_attention_umma(const float* qkv, uint16_t* out, uint16_t* out_lo, int B
     cudaDeviceGetAttribute(&n_sms_p, cudaDevAttrMultiProcessorCount, dev);
     if (n_sms_p <= 0) n_sms_p = 148;
   }
-  if (!serial) {                             // pipelined kernel (three S/P buffers, outputs folded into registers)
-    const size_t smem_p = 1024 + kAtQBytes + kApRing * (kApKBytes + kApVBytes) + 4 * kAtTile * 4 + sizeof(AttnPipeSmem);
+  if (!serial && N >= 4 * kApKT) {           // pipelined kernel (three S/P buffers, outputs folded into registers)
+    const size_t smem_p = 1024 + 2 * kAtQBytes + kApRing * (kApKBytes + kApVBytes) + kApXFloats * kAtTile * 4 +
+                          sizeof(AttnPipeSmem);
     static bool attr_p = false;
     if (!attr_p) {
       RLDM_CUDA(cudaFuncSetAttribute(attention_umma_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -272,7 +272,7 @@ def test_gn_stats_and_prep(L, shape):
 
 @pytest.mark.parametrize("kernel", ["tcgen05", "mma", "cudacore"])
 @pytest.mark.parametrize("shape", [(2, 64, 64), (1, 256, 128), (2, 1024, 128), (1, 40, 64), (1, 320, 64), (3, 128, 64),
-                                   (1, 1024, 16), (1, 512, 256)])
+                                   (1, 1024, 16), (1, 512, 256), (1, 2048, 32), (5, 1024, 64)])
 def test_attention_core(L, shape, kernel, monkeypatch):
     """tcgen05 kernel (N a multiple of 128, <= 1024; other shapes fall through to the mma.sync kernel), the
     mma.sync kernel (N % 64 == 0) and the CUDA-core kernel (ragged N), each forced where it applies."""
