@@ -118,7 +118,7 @@ __device__ __forceinline__ void store_split8(const float (&v)[8], __half* out, _
 // prep: y = [silu]([gn](concat(x0,x1))) cast to fp16, optionally nearest-2x upsampled.
 // grid (ceil(outpix/pix_per_block), B), block 256.  Thread = 8 channels of one OUTPUT pixel
 // (two float4 loads, one 16 B store).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
             const double* __restrict__ sums, const double* __restrict__ pairs0,
             const double* __restrict__ pairs1, const float* __restrict__ gamma,
@@ -132,6 +132,58 @@ prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, 
   float* sc = shf;
   float* sf = shf + C;
   const bool norm = sums != nullptr || pairs0 != nullptr;
+  // Output is W-PADDED: (B, Wo+2, Ho, C); padded column wp holds image column (wp-1) mod Wo, i.e. the
+  // circular halo of `ldm/utils.py:47` is materialised here for free (zeros when !circular), so every
+  // conv tap is a plain TMA box.
+  const int Wo = W * up, Ho = H * up;
+  const int oct_per_pix = C >> 3;
+  const int out_pix = (Wo + 2) * Ho;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(p_begin + pix_per_block, out_pix);
+  const int total = (p_end - p_begin) * oct_per_pix;
+  // (pixel, channel octet) of this thread's item advance incrementally: no integer division in the loop; Ho is a
+  // power of two in every reference geometry (shift), otherwise one division per item
+  int pl = threadIdx.x / oct_per_pix, oc = threadIdx.x - pl * oct_per_pix;
+  const int step_p = blockDim.x / oct_per_pix, step_o = blockDim.x - step_p * oct_per_pix;
+  const int sh_h = (Ho & (Ho - 1)) == 0 ? 31 - __clz(Ho) : -1;
+  // Two items per step, software-pipelined one step ahead: the loads of step k+1 are in flight while step k is
+  // consumed, and the loads of the FIRST step are issued before the GroupNorm prologue below (its dependent moment
+  // loads and the first data loads overlap; small passes are pure latency).
+  struct Item {
+    size_t o;
+    int c;
+    bool live, zero;
+    float4 v0, v1;
+  };
+  auto issue = [&](int i, Item (&it)[2]) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      it[u].live = i + u * static_cast<int>(blockDim.x) < total;
+      if (oc >= oct_per_pix) { oc -= oct_per_pix; ++pl; }
+      const int po = p_begin + pl;
+      const int c = oc << 3;
+      pl += step_p; oc += step_o;                         // advance to this thread's next item
+      const int wp = sh_h >= 0 ? po >> sh_h : po / Ho;
+      const int ho = po - wp * Ho;
+      int wo = wp - 1;
+      const bool halo = wo < 0 || wo >= Wo;
+      if (wo < 0) wo += Wo;
+      if (wo >= Wo) wo -= Wo;
+      it[u].o = (static_cast<size_t>(b) * out_pix + po) * C + c;
+      it[u].c = c;
+      it[u].zero = halo && !circular;
+      it[u].v0 = it[u].v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (it[u].live && !it[u].zero) {
+        const int pin = (up == 2) ? (wo >> 1) * H + (ho >> 1) : wo * H + ho;
+        const size_t pix = static_cast<size_t>(b) * W * H + pin;
+        const float* src = (c < c0) ? x0 + pix * c0 + c : x1 + pix * c1 + (c - c0);
+        it[u].v0 = __ldg(reinterpret_cast<const float4*>(src));
+        it[u].v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      }
+    }
+  };
+  Item cur[2];
+  issue(threadIdx.x, cur);
   if (norm) {
     // group moments: either the (sum, sum^2) per (image, group) of rldm_gn_stats, or the per channel-PAIR moments
     // that the producing convolutions accumulated in their epilogues (x0's pairs, then x1's for a skip concat)
@@ -152,83 +204,47 @@ prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, 
         }
       }
       const double mean = s * inv_n;
-      double var = ss * inv_n - mean * mean;
+      double var = ss * inv_n - mean * mean;              // the cancellation is why the moments are doubles
       if (var < 0) var = 0;
-      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      const float rstd = rsqrtf(static_cast<float>(var) + eps);
       const float a = rstd * gamma[c];
       sc[c] = a;
       sf[c] = beta[c] - static_cast<float>(mean) * a;
     }
     __syncthreads();
   }
-  // Output is W-PADDED: (B, Wo+2, Ho, C); padded column wp holds image column (wp-1) mod Wo, i.e. the
-  // circular halo of `ldm/utils.py:47` is materialised here for free (zeros when !circular), so every
-  // conv tap is a plain TMA box.
-  const int Wo = W * up, Ho = H * up;
-  const int oct_per_pix = C >> 3;
-  const int out_pix = (Wo + 2) * Ho;
-  const int p_begin = blockIdx.x * pix_per_block;
-  const int p_end = min(p_begin + pix_per_block, out_pix);
-  const int total = (p_end - p_begin) * oct_per_pix;
-  // (pixel, channel octet) of this thread's item advance incrementally: no integer division in the loop; Ho is a
-  // power of two in every reference geometry (shift), otherwise one division per item
-  int pl = threadIdx.x / oct_per_pix, oc = threadIdx.x - pl * oct_per_pix;
-  const int step_p = blockDim.x / oct_per_pix, step_o = blockDim.x - step_p * oct_per_pix;
-  const int sh_h = (Ho & (Ho - 1)) == 0 ? 31 - __clz(Ho) : -1;
-  // two items per iteration: both items' loads are issued before either is consumed (the loop is latency-bound)
   for (int i = threadIdx.x; i < total; i += 2 * blockDim.x) {
-    size_t o[2];
-    int cc[2];
-    bool live[2], zero[2];
-    float4 v0[2], v1[2];
+    Item nxt[2];
+    nxt[0].live = nxt[1].live = false;
+    if (i + 2 * static_cast<int>(blockDim.x) < total) issue(i + 2 * blockDim.x, nxt);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      live[u] = i + u * static_cast<int>(blockDim.x) < total;
-      if (oc >= oct_per_pix) { oc -= oct_per_pix; ++pl; }
-      const int po = p_begin + pl;
-      const int c = oc << 3;
-      pl += step_p; oc += step_o;                         // advance to this thread's next item
-      const int wp = sh_h >= 0 ? po >> sh_h : po / Ho;
-      const int ho = po - wp * Ho;
-      int wo = wp - 1;
-      const bool halo = wo < 0 || wo >= Wo;
-      if (wo < 0) wo += Wo;
-      if (wo >= Wo) wo -= Wo;
-      o[u] = (static_cast<size_t>(b) * out_pix + po) * C + c;
-      cc[u] = c;
-      zero[u] = halo && !circular;
-      v0[u] = v1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live[u] && !zero[u]) {
-        const int pin = (up == 2) ? (wo >> 1) * H + (ho >> 1) : wo * H + ho;
-        const size_t pix = static_cast<size_t>(b) * W * H + pin;
-        const float* src = (c < c0) ? x0 + pix * c0 + c : x1 + pix * c1 + (c - c0);
-        v0[u] = __ldg(reinterpret_cast<const float4*>(src));
-        v1[u] = __ldg(reinterpret_cast<const float4*>(src) + 1);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (!live[u]) continue;
-      if (zero[u]) {
-        *reinterpret_cast<uint4*>(out + o[u]) = make_uint4(0, 0, 0, 0);
-        if (out_lo) *reinterpret_cast<uint4*>(out_lo + o[u]) = make_uint4(0, 0, 0, 0);
-        if (raw) *reinterpret_cast<uint4*>(raw + o[u]) = make_uint4(0, 0, 0, 0);
-        if (raw_lo) *reinterpret_cast<uint4*>(raw_lo + o[u]) = make_uint4(0, 0, 0, 0);
+      if (!cur[u].live) continue;
+      const size_t o = cur[u].o;
+      if (cur[u].zero) {
+        *reinterpret_cast<uint4*>(out + o) = make_uint4(0, 0, 0, 0);
+        if (out_lo) *reinterpret_cast<uint4*>(out_lo + o) = make_uint4(0, 0, 0, 0);
+        if (raw) *reinterpret_cast<uint4*>(raw + o) = make_uint4(0, 0, 0, 0);
+        if (raw_lo) *reinterpret_cast<uint4*>(raw_lo + o) = make_uint4(0, 0, 0, 0);
         continue;
       }
-      const int c = cc[u];
-      float v[8] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w, v1[u].x, v1[u].y, v1[u].z, v1[u].w};
-      if (raw) store_split8(v, raw, raw_lo, o[u]);    // second output: the un-normalised operand (1x1 shortcut input)
+      const int c = cur[u].c;
+      float v[8] = {cur[u].v0.x, cur[u].v0.y, cur[u].v0.z, cur[u].v0.w, cur[u].v1.x, cur[u].v1.y, cur[u].v1.z, cur[u].v1.w};
+      if (raw) store_split8(v, raw, raw_lo, o);       // second output: the un-normalised operand (1x1 shortcut input)
       if (norm) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[c + j], sf[c + j]);
+        const float4 a0 = *reinterpret_cast<const float4*>(sc + c), a1 = *reinterpret_cast<const float4*>(sc + c + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(sf + c), b1 = *reinterpret_cast<const float4*>(sf + c + 4);
+        v[0] = fmaf(v[0], a0.x, b0.x); v[1] = fmaf(v[1], a0.y, b0.y); v[2] = fmaf(v[2], a0.z, b0.z); v[3] = fmaf(v[3], a0.w, b0.w);
+        v[4] = fmaf(v[4], a1.x, b1.x); v[5] = fmaf(v[5], a1.y, b1.y); v[6] = fmaf(v[6], a1.z, b1.z); v[7] = fmaf(v[7], a1.w, b1.w);
       }
       if (silu) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
       }
-      store_split8(v, out, out_lo, o[u]);
+      store_split8(v, out, out_lo, o);
     }
+    cur[0] = nxt[0];
+    cur[1] = nxt[1];
   }
 }
 
