@@ -560,10 +560,20 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
 // of units (256 tiles -> 128 units: one wave on 148 SMs instead of 1.73).  TMEM: 2 units x MT x BLOCK_N columns.
 // KB = 32 (opt-in experiment): a stage carries half a 64-channel chunk (SWIZZLE_64B operand tiles, two K steps).  With
 // MT = 2 a 64-wide stage is 96 KB and only two fit; 48 KB half-stages give a 4-deep ring, but measured slower.
-template <int BLOCK_N, int STAGES, int TERMS, int MT, int KB>
+//
+// HALO = true (3x3, stride 1, symmetric pad, MT = 2, KB = 64): the A operand of the three taps ti = 0,1,2 of one
+// kernel column tj is ONE shared-memory window of (2*128 + 2*Ho) pixels (the unit's columns plus one halo column on
+// each side; tap ti = the window shifted by ti*Ho rows, a whole number of 1024 B swizzle atoms for Ho >= 8), so the
+// A stream from L2 drops 3x.  Two rings: two A windows ([hi][lo], one per (64-channel chunk, tj)) and p.nb_stages
+// weight entries of ONE operand part each (W_hi of a tap feeds A_hi W_hi + A_lo W_hi of both tiles and is released
+// before W_lo is needed).  Per tap 72/3 + 32 = 56 KB instead of 96 KB per 24 MMAs: the K loop turns MMA-bound.
+template <int BLOCK_N, int STAGES, int TERMS, int MT, int KB, bool HALO = false>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
   static_assert(KB == 64 || KB == 32, "stage depth along K: one 128 B swizzle row or half of it");
+  static_assert(!HALO || (MT == 2 && KB == 64), "halo windows: two M tiles per unit, 64-channel stages");
+  constexpr int kMaxNB = 8;                                     // HALO: upper bound of the weight ring depth
+  constexpr int kRingBars = HALO ? 4 + 2 * kMaxNB : 2 * STAGES;
   constexpr int kSub = kBlockK / KB;                            // stages per 64-channel chunk
   constexpr int kAB = kBlockM * KB * 2;                         // one operand part of one M tile
   constexpr int kBBytes = BLOCK_N * KB * 2;
@@ -579,10 +589,18 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  float* slab = reinterpret_cast<float*>(smem + STAGES * kStageBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes + kSlabBytes);
+  const int a_stage = HALO ? kParts * p.a_part_bytes : 0;       // HALO: one A window stage, [hi][lo]
+  const int NB = HALO ? p.nb_stages : 0;
+  uint8_t* b_ring = smem + 2 * a_stage;                          // HALO: NB entries of kBBytes
+  uint8_t* tail = HALO ? b_ring + NB * kBBytes : smem + STAGES * kStageBytes;
+  float* slab = reinterpret_cast<float*>(tail);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail + kSlabBytes);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;      // [2]
+  uint64_t* a_full = full_bar;                   // HALO: [2] [2] [kMaxNB] [kMaxNB]
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* b_full = a_empty + 2;
+  uint64_t* b_empty = b_full + kMaxNB;
+  uint64_t* tmem_full = full_bar + kRingBars;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* red_s = reinterpret_cast<float*>(tmem_ptr + 4);       // [4][BLOCK_N/2]
@@ -607,10 +625,7 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
       if (TERMS > 1) tma_prefetch_desc(&tm.a2lo);
       tma_prefetch_desc(&tm.b2);
     }
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
+    for (int s = 0; s < kRingBars; ++s) mbar_init(&full_bar[s], 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 4);          // one arrival per epilogue warp
@@ -624,7 +639,103 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);   // shfl: tells the compiler it is warp-uniform (UR, no per-MMA R2UR loop)
   pdl_wait();
 
-  if (warp == 0) {
+  if (HALO && warp == 0) {
+    // ===================== TMA producer (halo windows): A ring of 2, weight ring of NB ============
+    int ga = 0, gb = 0;
+    const int chunks = p.units / 3;
+    for (int t = blockIdx.x; t < total_units; t += gridDim.x) {
+      if (t + static_cast<int>(gridDim.x) >= total_units) pdl_trigger_conv_late();
+      const int um = t / tiles_n, tn = t - um * tiles_n;
+      const int n0 = tn * BLOCK_N;
+      const int q0 = um * (MT * kBlockM) / p.Ho;            // global column index of the unit's first column
+      const int b0 = q0 / p.Wo, wo0 = q0 - b0 * p.Wo;       // wo0 == padded column of tap ti = 0
+      for (int chunk = 0; chunk < chunks; ++chunk) {
+        for (int tj = 0; tj < 3; ++tj, ++ga) {
+          const int sa = ga & 1;
+          mbar_wait(&a_empty[sa], ((ga >> 1) & 1) ^ 1);
+          const uint32_t a_dst = smem_u32(smem + sa * a_stage);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&a_full[sa], a_stage);
+            tma_load_4d(a_dst, &tm.a, &a_full[sa], chunk * kBlockK, tj - 1, wo0, b0);
+            if (TERMS > 1) tma_load_4d(a_dst + p.a_part_bytes, &tm.alo, &a_full[sa], chunk * kBlockK, tj - 1, wo0, b0);
+          }
+          for (int e = 0; e < 3 * kParts; ++e, ++gb) {      // (ti, part): W_hi then W_lo of each tap
+            const int sb = gb % NB;
+            mbar_wait(&b_empty[sb], ((gb / NB) & 1) ^ 1);
+            if (lane == 0) {
+              const int ti = e / kParts, part = e - ti * kParts;
+              const int tap = ti * 3 + tj;
+              mbar_arrive_expect_tx(&b_full[sb], kBBytes);
+              tma_load_2d(smem_u32(b_ring + sb * kBBytes), &tm.b, &b_full[sb], chunk * kBlockK,
+                          (part * 9 + tap) * p.Cout + n0);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (HALO && warp == 1) {
+    // ===================== MMA issuer (halo windows) ============================================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BLOCK_N);
+      int ga = 0, gb = 0, k = 0;
+      for (int t = blockIdx.x; t < total_units; t += gridDim.x, ++k) {
+        if (t + static_cast<int>(gridDim.x) >= total_units) pdl_trigger_conv_late();
+        const int acc = k & 1;
+        mbar_wait(&tmem_empty[acc], ((k >> 1) & 1) ^ 1);       // epilogue has drained this accumulator set
+        tc_fence_after();
+        for (int u = 0; u < p.units; ++u, ++ga) {
+          const int sa = ga & 1;
+          mbar_wait(&a_full[sa], (ga >> 1) & 1);
+          const uint32_t a_base = smem_u32(smem + sa * a_stage);
+          for (int ti = 0; ti < 3; ++ti) {
+            // tap ti of this kernel column = the window shifted by ti columns (ti*Ho rows); tile mt starts mt*128
+            // rows further down.  Both offsets are whole 1024 B swizzle atoms.
+            const uint32_t a_tap = a_base + ti * p.Ho * 128;
+            {
+              const int sb = gb % NB;
+              mbar_wait(&b_full[sb], (gb / NB) & 1);
+              tc_fence_after();
+              const uint64_t b_desc = umma_desc_sw128(smem_u32(b_ring + sb * kBBytes));
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t d_tmem = tmem_base + acc * kAccCols + mt * BLOCK_N;
+                const uint64_t a_desc = umma_desc_sw128(a_tap + mt * kBlockM * 128);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_f16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (u | ti | kk) != 0);
+                if (TERMS > 1) {
+                  const uint64_t al_desc = umma_desc_sw128(a_tap + mt * kBlockM * 128 + p.a_part_bytes);
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk) umma_f16(d_tmem, al_desc + 2 * kk, b_desc + 2 * kk, idesc, 1u);
+                }
+              }
+              umma_commit(&b_empty[sb]);
+              ++gb;
+            }
+            if (TERMS > 1) {
+              const int sb = gb % NB;
+              mbar_wait(&b_full[sb], (gb / NB) & 1);
+              tc_fence_after();
+              const uint64_t bl_desc = umma_desc_sw128(smem_u32(b_ring + sb * kBBytes));
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t d_tmem = tmem_base + acc * kAccCols + mt * BLOCK_N;
+                const uint64_t a_desc = umma_desc_sw128(a_tap + mt * kBlockM * 128);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) umma_f16(d_tmem, a_desc + 2 * kk, bl_desc + 2 * kk, idesc, 1u);
+              }
+              umma_commit(&b_empty[sb]);
+              ++gb;
+            }
+          }
+          umma_commit(&a_empty[sa]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 0) {
     // ===================== TMA producer: one continuous stage ring across units =================
     int g = 0;
     for (int t = blockIdx.x; t < total_units; t += gridDim.x) {
@@ -1068,6 +1179,19 @@ static int launch_conv_persistent(const ConvMaps& tm, const ConvParams& p, int n
   return 0;
 }
 
+// Persistent halo-window variant: shared memory = 2 A windows + nb weight entries + slab + barriers (sized by the caller)
+template <int BLOCK_N, int TERMS>
+static int launch_conv_persistent_halo(const ConvMaps& tm, const ConvParams& p, int n_ctas, size_t smem, cudaStream_t st) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    RLDM_CUDA(cudaFuncSetAttribute(conv_tc_persistent_kernel<BLOCK_N, 2, TERMS, 2, 64, true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_smem = smem;
+  }
+  RLDM_CUDA(launch_pdl(conv_tc_persistent_kernel<BLOCK_N, 2, TERMS, 2, 64, true>, dim3(n_ctas), dim3(192), smem, st, tm, p));
+  return 0;
+}
+
 template <int BLOCK_N, int MT, int TERMS>
 static int launch_conv3x3(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const CUtensorMap& tmB,
                           const ConvParams& p, int split, size_t smem, cudaStream_t st) {
@@ -1142,6 +1266,84 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
   RLDM_CHECK(ncols * stride <= 256, "conv_tc: tile of %d columns exceeds the TMA box limit", ncols);
   const int parts = x_lo ? 2 : 1;
   CUtensorMap tmA, tmAlo, tmB;
+  // ---- persistent halo-window path (opt-in, RLDM_HALO_P=1 | nores): 3x3, stride 1, symmetric pad, split-fp16, more
+  //      128x128 tiles than SMs, two whole M tiles per unit, room for two A windows plus >= 3 weight entries.
+  //      Measured on B200 (C3, batch 8): bit-for-bit the same contract, L2->SM bytes -42 %, but 8-10 % SLOWER than the
+  //      per-tap persistent kernel (UNet 128->128 @256x16: 30.7 -> 33.6 us; decoder 256->256 @256x16: 90 -> 99 us).
+  //      The K loop is paced by shared-memory bandwidth (a 128x128x16 SS MMA reads 8 KB in 64 clk = the whole
+  //      128 B/clk, TMA fills compete for the rest) and the 3 x 16 KB weight ring that fits next to two 72 KB windows
+  //      is too shallow; fewer operand bytes from L2 do not help.  The fix is fewer shared-memory reads per MMA
+  //      (cta_group::2 / N = 256), see DESIGN.md "Next". ----
+  {
+    static int n_sms_h = 0;
+    if (n_sms_h == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sms_h, cudaDevAttrMultiProcessorCount, dev);
+      if (n_sms_h <= 0) n_sms_h = 148;
+    }
+    const char* hp = getenv("RLDM_HALO_P");              // unset / "0": off, "nores": only layers without a residual
+    const int tiles_h = (B * pix / kBlockM) * (Cout / BN);
+    const size_t a_stage = static_cast<size_t>(2) * (2 * kBlockM + 2 * Ho) * 128;
+    const size_t b_entry = static_cast<size_t>(BN) * 128;
+    const size_t fixed = 2 * a_stage + kBlockM * 36 * 4 + (4 + 2 * 8 + 4) * 8 + 16 + 2 * 4 * (BN / 2) * 4 + 64 + 1024;
+    int nbs = fixed + 2 * b_entry <= 232448 ? static_cast<int>((232448 - fixed) / b_entry) : 0;
+    if (nbs > 8) nbs = 8;
+    static int min_nb = 0;
+    if (min_nb == 0) { const char* e = getenv("RLDM_HALO_P_MINNB"); min_nb = e ? atoi(e) : 3; }
+    const bool halo_p = ks == 3 && stride == 1 && pad_lo == 1 && Ho >= 8 && pix % (2 * kBlockM) == 0 && !sc_x && parts == 2 &&
+                        split_k <= 1 && tiles_h > n_sms_h && nbs >= min_nb && hp && hp[0] != '0' &&
+                        !(hp[0] == 'n' && residual) && !getenv("RLDM_NO_PERSISTENT") && !getenv("RLDM_HALO");
+    if (halo_p) {
+      ConvMaps tmh;
+      const int cols = 2 * (kBlockM / Ho);
+      for (int part = 0; part < 2; ++part) {
+        cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)H, (cuuint64_t)(W + 2), (cuuint64_t)B};
+        cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)H * Cin * 2, (cuuint64_t)(W + 2) * H * Cin * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)Ho, (cuuint32_t)(cols + 2), 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(part ? &tmh.alo : &tmh.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                            const_cast<uint16_t*>(part ? x_lo : x), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(A window) failed: %d", (int)r);
+      }
+      {
+        cuuint64_t gdim[2] = {(cuuint64_t)Cin, (cuuint64_t)2 * 9 * Cout};
+        cuuint64_t gstr[1] = {(cuuint64_t)Cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmh.b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(wgt), gdim, gstr,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RLDM_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+      }
+      tmh.a2 = tmh.a; tmh.a2lo = tmh.alo; tmh.b2 = tmh.b;
+      ConvParams p;
+      p.bias = bias; p.temb = temb; p.residual = residual; p.out = out;
+      p.temb_stride = temb_stride;
+      p.M_total = B * pix;
+      p.Wo = Wo; p.Ho = Ho; p.W_in = W;
+      p.pix_per_img = pix;
+      p.Cout = Cout;
+      p.ks = 3; p.stride = 1; p.pad_lo = 1; p.circular = circular;
+      p.total_iters = p.main_iters = (Cin / kBlockK) * 9;
+      p.units = (Cin / kBlockK) * 3;
+      p.a_part_bytes = static_cast<int>(a_stage / 2);
+      p.nb_stages = nbs;
+      p.dbg = nullptr;
+      p.ws = nullptr;
+      p.stats = stats;
+      p.stats_G = Cout / 2;
+      p.stats_cpg = 2;
+      const int units = tiles_h / 2;
+      const int ctas = units < n_sms_h ? units : n_sms_h;
+      const size_t smem = fixed + nbs * b_entry;
+      cudaStream_t st = as_stream(stream);
+      if (BN == 128) return launch_conv_persistent_halo<128, 3>(tmh, p, ctas, smem, st);
+      return launch_conv_persistent_halo<64, 3>(tmh, p, ctas, smem, st);
+    }
+  }
   // ---- halo-reuse path: 3x3, stride 1, symmetric pad, column pitch a whole number of swizzle atoms ----
   // (measured on B200: correct but not faster than the per-tap kernel, whose limiter is per-CTA latency rather
   //  than operand bytes -- kept opt-in with RLDM_HALO=1 until it is made persistent)

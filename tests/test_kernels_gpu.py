@@ -85,6 +85,8 @@ CONV_CASES = [
     (8, 256, 16, 64, 256, 3, 1, 1, 0, 1),     # persistent, two N tiles per M tile
     (2, 512, 32, 64, 64, 3, 1, 1, 0, 1),      # persistent, BLOCK_N = 64 (decoder geometry), 256 tiles
     (5, 64, 32, 64, 128, 1, 1, 0, 0, 1),      # persistent 1x1, 80 tiles -> not persistent; sanity
+    (8, 512, 8, 64, 128, 3, 1, 1, 0, 1),      # persistent halo windows at Ho = 8 (nuScenes latent geometry)
+    (3, 256, 16, 128, 256, 3, 1, 1, 0, 0),    # persistent halo windows, odd batch, zero-padded W
 ]
 
 
@@ -209,6 +211,37 @@ def test_conv_tc_with_fused_shortcut(L, case):
     with pytest.raises(L.RldmError):    # stride 2 cannot carry a same-grid shortcut
         L.call("rldm_conv_tc_shortcut", L.ptr(ah), L.ptr(al), L.ptr(wt), L.ptr(bd), None, 0, None, L.ptr(out),
                B, W, H, Cin, Cout, 3, 2, 1, 1, split, None, L.ptr(xh), L.ptr(xl), L.ptr(wt2), Cin2)
+
+
+@pytest.mark.parametrize("case", [(8, 256, 16, 128, 128, 1), (3, 256, 16, 128, 256, 0), (8, 512, 8, 64, 128, 1)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv_tc_halo_window_variant_matches_default(L, case, monkeypatch):
+    """RLDM_HALO_P=1 (opt-in experiment): persistent kernel whose A operand of the three taps of a kernel column is
+    one shared-memory window.  Same contract as the per-tap persistent kernel; only the fp32 summation order differs."""
+    B, W, H, Cin, Cout, circ = case
+    g = torch.Generator().manual_seed(7 * B + Cin)
+    x = torch.randn(B, Cin, W, H, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    res = torch.randn(B, Cout, W, H, generator=g)
+    xh, xl = split_half(cl(x))
+    xh, xl, wt = padw(xh, bool(circ)).cuda(), padw(xl, bool(circ)).cuda(), pack_w(w, split=True).cuda()
+    bd, rd = b.cuda(), cl(res).cuda()
+    outs, stats = [], []
+    for mode in (None, "1"):
+        if mode:
+            monkeypatch.setenv("RLDM_HALO_P", mode)
+        out = torch.full((B, W, H, Cout), float("nan"), device="cuda")
+        st = torch.zeros(B, Cout // 2, 2, dtype=torch.float64, device="cuda")
+        L.call("rldm_conv_tc", L.ptr(xh), L.ptr(xl), L.ptr(wt), L.ptr(bd), None, 0, L.ptr(rd), L.ptr(out),
+               B, W, H, Cin, Cout, 3, 1, 1, circ, 0, L.ptr(st))
+        torch.cuda.synchronize()
+        outs.append(out)
+        stats.append(st)
+    assert relerr(outs[1], outs[0]) < 2e-6
+    assert torch.allclose(stats[1], stats[0], rtol=1e-6, atol=1e-3)
+    y32 = oracle_conv(x, w, b, 1, 1, 3, bool(circ)) + res
+    assert relerr(ref_layout(outs[1].cpu()), y32) < 1e-5
 
 
 def test_conv_tc_rejects_bad_shapes(L):
