@@ -108,8 +108,8 @@ __device__ __forceinline__ void store_split8(const float (&v)[8], __half* out, _
     __align__(16) __half2 l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 r = __ffma2_rn(__half22float2(h[j]), make_float2(-1.f, -1.f), make_float2(v[2 * j], v[2 * j + 1]));
-      l[j] = __floats2half2_rn(r.x, r.y);               // v - float(hi): exact (packed fp32 FMA)
+      const float2 hf = __half22float2(h[j]);
+      l[j] = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
     }
     *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<const uint4*>(l);
   }
@@ -149,16 +149,8 @@ prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, 
   // Two items per step, software-pipelined one step ahead: the loads of step k+1 are in flight while step k is
   // consumed, and the loads of the FIRST step are issued before the GroupNorm prologue below (its dependent moment
   // loads and the first data loads overlap; small passes are pure latency).
-  // per-image base pointers once (64-bit); everything inside an image is 32-bit offset arithmetic
-  const size_t img_out = static_cast<size_t>(b) * out_pix * C;
-  out += img_out;
-  if (out_lo) out_lo += img_out;
-  if (raw) raw += img_out;
-  if (raw_lo) raw_lo += img_out;
-  x0 += static_cast<size_t>(b) * W * H * c0;
-  if (x1) x1 += static_cast<size_t>(b) * W * H * c1;
   struct Item {
-    int o;
+    size_t o;
     int c;
     bool live, zero;
     float4 v0, v1;
@@ -177,13 +169,14 @@ prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, 
       const bool halo = wo < 0 || wo >= Wo;
       if (wo < 0) wo += Wo;
       if (wo >= Wo) wo -= Wo;
-      it[u].o = po * C + c;
+      it[u].o = (static_cast<size_t>(b) * out_pix + po) * C + c;
       it[u].c = c;
       it[u].zero = halo && !circular;
       it[u].v0 = it[u].v1 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (it[u].live && !it[u].zero) {
         const int pin = (up == 2) ? (wo >> 1) * H + (ho >> 1) : wo * H + ho;
-        const float* src = (c < c0) ? x0 + (pin * c0 + c) : x1 + (pin * c1 + (c - c0));
+        const size_t pix = static_cast<size_t>(b) * W * H + pin;
+        const float* src = (c < c0) ? x0 + pix * c0 + c : x1 + pix * c1 + (c - c0);
         it[u].v0 = __ldg(reinterpret_cast<const float4*>(src));
         it[u].v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
       }
@@ -227,7 +220,7 @@ prep_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, 
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (!cur[u].live) continue;
-      const int o = cur[u].o;
+      const size_t o = cur[u].o;
       if (cur[u].zero) {
         *reinterpret_cast<uint4*>(out + o) = make_uint4(0, 0, 0, 0);
         if (out_lo) *reinterpret_cast<uint4*>(out_lo + o) = make_uint4(0, 0, 0, 0);
