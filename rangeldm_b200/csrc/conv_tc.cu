@@ -955,6 +955,212 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent kernel with the operands' ROLES SWAPPED: D^T[Cout tile, pixels] = W[Cout tile, K] X^T[K, pixels].
+//
+// ncu on the kernel above: a 128x128x16 SS-form MMA reads 4 KB of A and 4 KB of B from shared memory in its 64
+// clocks, i.e. 64 wavefronts of 128 B = the WHOLE shared-memory data pipe (l1tex__data_pipe_tc_wavefronts: 64 per
+// MMA), so every TMA fill of the ring steals tensor cycles: 1.0 (reads) + 0.5 (fills) wavefronts per MMA clock =
+// the measured ~2200 instead of 1536 cycles per K step, tensor pipe 54-69 % active.  Sharing a weight tile between
+// two M tiles (MT = 2) saves L2 traffic but not shared-memory reads (each MMA re-reads its B tile).
+// Here the 128 output CHANNELS are the M side (A operand = weight tile, 128 rows x 64 channels, K-major) and 256
+// PIXELS the N side (B operand = the two 128-pixel activation tiles stored back to back = one 256-row K-major tile):
+// one 128x256x16 MMA reads 4 + 8 KB in 128 clocks = 0.75 wavefronts per clock for the same FLOPs.  The accumulator
+// is [channel lane][pixel column] (2 x 256 TMEM columns, double-buffered), which also makes the epilogue simpler:
+// a thread owns ONE output channel, `tcgen05.ld` hands it 32 pixels, lanes = 32 consecutive channels of one pixel,
+// so stores and residual loads are coalesced 128 B rows straight from registers (no shared staging slab, no
+// bar.sync), bias/temb are per-thread scalars and the GroupNorm channel-pair moments are per-thread sums plus one
+// shuffle.  Stage = [X_hi 256 rows][X_lo 256 rows][W_hi][W_lo] = 96 KB, two stages.
+template <int TERMS>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
+  constexpr int kCoutTile = 128, kPix = 256, STAGES = 2;
+  constexpr int kParts = TERMS == 1 ? 1 : 2;
+  constexpr int kXPart = kPix * kBlockK * 2;                    // 32 KB: 256 pixel rows x 128 B
+  constexpr int kWPart = kCoutTile * kBlockK * 2;               // 16 KB
+  constexpr int kWOff = kParts * kXPart;
+  constexpr int kStageBytes = kParts * (kXPart + kWPart);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_n = p.Cout / kCoutTile;
+  const int total_units = (p.M_total / kPix) * tiles_n;
+  const int taps = p.ks * p.ks;
+  const int n_it = p.total_iters;
+
+  pdl_trigger_conv_early();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm.a);
+    if (TERMS > 1) tma_prefetch_desc(&tm.alo);
+    tma_prefetch_desc(&tm.b);
+    if (p.total_iters > p.main_iters) {
+      tma_prefetch_desc(&tm.a2);
+      if (TERMS > 1) tma_prefetch_desc(&tm.a2lo);
+      tma_prefetch_desc(&tm.b2);
+    }
+    for (int s = 0; s < 2 * STAGES; ++s) mbar_init(&full_bar[s], 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);          // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<2 * kPix>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer: one continuous stage ring across units =================
+    int g = 0;
+    for (int t = blockIdx.x; t < total_units; t += gridDim.x) {
+      if (t + static_cast<int>(gridDim.x) >= total_units) pdl_trigger_conv_late();
+      const int um = t / tiles_n, tn = t - um * tiles_n;
+      const int m0 = um * kPix, n0 = tn * kCoutTile;
+      int b0[2], wo0[2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int q0 = (m0 + mt * kBlockM) / p.Ho;          // global column index of the 128-pixel tile's first column
+        b0[mt] = q0 / p.Wo;
+        wo0[mt] = q0 - b0[mt] * p.Wo;
+      }
+      for (int it = 0; it < n_it; ++it, ++g) {
+        const int s = g % STAGES;
+        mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
+        const bool main = it < p.main_iters;
+        const int chunk = main ? it / taps : it - p.main_iters;
+        const int tap = it - chunk * taps;
+        const int ti = tap / p.ks, tj = tap - ti * p.ks;
+        const int kc = chunk * kBlockK;
+        const uint32_t dst = smem_u32(smem + s * kStageBytes);
+        // shortcut K steps: centre tap of the second tensor (1x1, stride 1, same grid as the output)
+        const int h_in = main ? tj - p.pad_lo : 0;
+        const int w_off = main ? ti - p.pad_lo + 1 : 1;
+        const int w_mul = main ? p.stride : 1;
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+          if (main) {
+            tma_load_2d(dst + kWOff, &tm.b, &full_bar[s], kc, tap * p.Cout + n0);
+            if (TERMS > 1) tma_load_2d(dst + kWOff + kWPart, &tm.b, &full_bar[s], kc, (taps + tap) * p.Cout + n0);
+          } else {
+            tma_load_2d(dst + kWOff, &tm.b2, &full_bar[s], kc, n0);
+            if (TERMS > 1) tma_load_2d(dst + kWOff + kWPart, &tm.b2, &full_bar[s], kc, p.Cout + n0);
+          }
+        }
+        // lanes 1.. : one 128-pixel box per (tile, operand part); the two tiles of a part are adjacent = 256 rows
+        if (lane >= 1 && lane <= 2 * kParts) {
+          const int mt = (lane - 1) & 1, part = (lane - 1) >> 1;
+          const CUtensorMap* map = main ? (part ? &tm.alo : &tm.a) : (part ? &tm.a2lo : &tm.a2);
+          tma_load_4d(dst + part * kXPart + mt * kABytes, map, &full_bar[s], kc, h_in, w_mul * wo0[mt] + w_off, b0[mt]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: alternates between the two TMEM accumulator sets ===========
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(kCoutTile, kPix);
+      int g = 0, k = 0;
+      for (int t = blockIdx.x; t < total_units; t += gridDim.x, ++k) {
+        if (t + static_cast<int>(gridDim.x) >= total_units) pdl_trigger_conv_late();
+        const int acc = k & 1;
+        mbar_wait(&tmem_empty[acc], ((k >> 1) & 1) ^ 1);       // epilogue has drained this accumulator set
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kPix;
+        for (int it = 0; it < n_it; ++it, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(&full_bar[s], (g / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + s * kStageBytes);
+          const uint64_t x_desc = umma_desc_sw128(base), w_desc = umma_desc_sw128(base + kWOff);
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / 16; ++kk)
+            umma_f16(d_tmem, w_desc + 2 * kk, x_desc + 2 * kk, idesc, (it | kk) != 0);
+          if (TERMS > 1) {
+            const uint64_t xl_desc = umma_desc_sw128(base + kXPart), wl_desc = umma_desc_sw128(base + kWOff + kWPart);
+#pragma unroll
+            for (int kk = 0; kk < kBlockK / 16; ++kk) {
+              umma_f16(d_tmem, w_desc + 2 * kk, xl_desc + 2 * kk, idesc, 1u);     // W_hi X_lo
+              umma_f16(d_tmem, wl_desc + 2 * kk, x_desc + 2 * kk, idesc, 1u);     // W_lo X_hi
+            }
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps: thread = output channel, drain unit k under unit k+1 ===
+    const int q = warp & 3;                   // TMEM lane quadrant readable by this warp = channels 32q..32q+31
+    int k = 0;
+    for (int t = blockIdx.x; t < total_units; t += gridDim.x, ++k) {
+      const int acc = k & 1;
+      const int um = t / tiles_n, tn = t - um * tiles_n;
+      const int m0 = um * kPix;
+      const int c = tn * kCoutTile + q * 32 + lane;             // this thread's output channel
+      const int bimg = m0 / p.pix_per_img;                      // a unit lies inside one image (host)
+      float add = p.bias ? __ldg(p.bias + c) : 0.f;
+      if (p.temb) add += __ldg(p.temb + static_cast<size_t>(bimg) * p.temb_stride + c);
+      float* outp = p.out + static_cast<size_t>(m0) * p.Cout + c;
+      const float* resp = p.residual ? p.residual + static_cast<size_t>(m0) * p.Cout + c : nullptr;
+      float rs[32];
+      auto fetch_res = [&](int ch) {                            // 32 coalesced 128 B rows
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rs[j] = __ldg(resp + static_cast<size_t>(ch * 32 + j) * p.Cout);
+      };
+      if (resp) fetch_res(0);
+      mbar_wait(&tmem_full[acc], (k >> 1) & 1);
+      if (t + static_cast<int>(gridDim.x) >= total_units) pdl_trigger_conv_late();
+      tc_fence_after();
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < kPix / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + acc * kPix + (static_cast<uint32_t>(q * 32) << 16) + ch * 32, r);
+        tmem_ld_wait();
+        if (ch == kPix / 32 - 1) {            // last TMEM read of this unit: hand the accumulators back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + add + (resp ? rs[j] : 0.f);
+        if (resp && ch + 1 < kPix / 32) fetch_res(ch + 1);     // next chunk's residual rows fly under these stores
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          outp[static_cast<size_t>(ch * 32 + j) * p.Cout] = v[j];
+          s1 += v[j];
+          s2 = fmaf(v[j], v[j], s2);
+        }
+      }
+      if (p.stats) {                          // channel-pair moments of the finished output: (c, c+1) -> one slot
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+        if ((lane & 1) == 0) {
+          double* st = p.stats + (static_cast<size_t>(bimg) * p.stats_G + c / 2) * 2;
+          atomicAdd(st, static_cast<double>(s1));
+          atomicAdd(st + 1, static_cast<double>(s2));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<2 * kPix>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Halo-reuse kernel for the 3x3 / stride-1 convolutions that carry ~95 % of the FLOPs.
 //
 // In the per-tap kernel above every one of the 9 taps re-reads its A tile from L2 and every 128-pixel tile
@@ -1176,6 +1382,19 @@ static int launch_conv_persistent(const ConvMaps& tm, const ConvParams& p, int n
     attr_set = true;
   }
   RLDM_CUDA(launch_pdl(conv_tc_persistent_kernel<BLOCK_N, STAGES, TERMS, MT, KB>, dim3(n_ctas), dim3(192), smem, st, tm, p));
+  return 0;
+}
+
+template <int TERMS>
+static int launch_conv_wt(const ConvMaps& tm, const ConvParams& p, int n_ctas, cudaStream_t st) {
+  constexpr int smem = 2 * (TERMS == 1 ? 1 : 2) * (256 + 128) * 64 * 2 + 256 + 1024;
+  static_assert(smem <= 232448, "conv_tc_wt: shared memory budget exceeded");
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLDM_CUDA(cudaFuncSetAttribute(conv_tc_wt_kernel<TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  RLDM_CUDA(launch_pdl(conv_tc_wt_kernel<TERMS>, dim3(n_ctas), dim3(192), smem, st, tm, p));
   return 0;
 }
 
@@ -1516,6 +1735,19 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
     //  residual are paced by the drain of two tiles, not the K loop: they keep one tile per unit and three stages)
     const bool mt2 = tiles_m % 2 == 0 && p.M_total % kBlockM == 0 && (residual == nullptr || BN == 64 || getenv("RLDM_CONV_MT2_RES")) &&
                      !getenv("RLDM_CONV_MT1");
+    // Cout tiles of 128 and whole 256-pixel units inside one image: roles swapped (weights = M side, N = 256 pixels),
+    // 25 % fewer shared-memory operand reads per FLOP.  RLDM_CONV_WT=0 switches it off, =nores keeps layers with a
+    // residual operand on the kernels above.
+    {
+      const char* wt_env = getenv("RLDM_CONV_WT");
+      const bool wt = BN == 128 && p.M_total % 256 == 0 && pix % 256 == 0 && !(wt_env && wt_env[0] == '0') &&
+                      !(wt_env && wt_env[0] == 'n' && residual);
+      if (wt) {
+        if (int rc = build_maps()) return rc;
+        const int units_wt = (p.M_total / 256) * (Cout / 128);
+        return launch_conv_wt<3>(tm, p, units_wt < n_sms ? units_wt : n_sms, st);
+      }
+    }
     const int units = mt2 ? tiles / 2 : tiles;
     const int ctas = units < n_sms ? units : n_sms;
     if (mt2) {
