@@ -970,10 +970,19 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
 // so stores and residual loads are coalesced 128 B rows straight from registers (no shared staging slab, no
 // bar.sync), bias/temb are per-thread scalars and the GroupNorm channel-pair moments are per-thread sums plus one
 // shuffle.  Stage = [X_hi 256 rows][X_lo 256 rows][W_hi][W_lo] = 96 KB, two stages.
-template <int TERMS>
+//
+// HALO = true (3x3, stride 1, symmetric pad, Ho in 8..32, no fused shortcut): the pixel operand of the three taps
+// ti = 0,1,2 of one kernel column tj is ONE window of (256 + 2*Ho) rows (the unit's columns plus one halo column on
+// each side; tap ti = the window shifted by ti*Ho rows = whole 1024 B swizzle atoms), so the ring fills drop from
+// 96 KB to 56 KB per tap (0.5 -> 0.29 wavefronts per MMA clock next to 0.75 of operand reads).  Two rings: two pixel
+// windows ([hi][lo], one per (64-channel chunk, tj)) and p.nb_stages weight entries of ONE operand part each: W_hi of
+// a tap feeds W_hi X_hi + W_hi X_lo and is released before W_lo is needed.
+template <int TERMS, bool HALO = false>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
   constexpr int kCoutTile = 128, kPix = 256, STAGES = 2;
+  constexpr int kMaxNW = 8;                                     // HALO: upper bound of the weight ring depth
+  constexpr int kRingBars = HALO ? 4 + 2 * kMaxNW : 2 * STAGES;
   constexpr int kParts = TERMS == 1 ? 1 : 2;
   constexpr int kXPart = kPix * kBlockK * 2;                    // 32 KB: 256 pixel rows x 128 B
   constexpr int kWPart = kCoutTile * kBlockK * 2;               // 16 KB
@@ -982,9 +991,16 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  const int x_stage = HALO ? kParts * p.a_part_bytes : 0;       // HALO: one pixel-window stage, [hi][lo]
+  const int NW = HALO ? p.nb_stages : 0;
+  uint8_t* w_ring = smem + 2 * x_stage;                          // HALO: NW entries of kWPart
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(HALO ? w_ring + NW * kWPart : smem + STAGES * kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;      // [2]
+  uint64_t* x_full = full_bar;                   // HALO: [2] [2] [kMaxNW] [kMaxNW]
+  uint64_t* x_empty = x_full + 2;
+  uint64_t* w_full = x_empty + 2;
+  uint64_t* w_empty = w_full + kMaxNW;
+  uint64_t* tmem_full = full_bar + kRingBars;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -1005,7 +1021,7 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
       if (TERMS > 1) tma_prefetch_desc(&tm.a2lo);
       tma_prefetch_desc(&tm.b2);
     }
-    for (int s = 0; s < 2 * STAGES; ++s) mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < kRingBars; ++s) mbar_init(&full_bar[s], 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 4);          // one arrival per epilogue warp
@@ -1019,7 +1035,92 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
   pdl_wait();
 
-  if (warp == 0) {
+  if (HALO && warp == 0) {
+    // ===================== TMA producer (pixel windows): window ring of 2, weight ring of NW =====
+    int gx = 0, gw = 0;
+    const int chunks = p.units / 3;
+    for (int t = blockIdx.x; t < total_units; t += gridDim.x) {
+      if (t + static_cast<int>(gridDim.x) >= total_units) pdl_trigger_conv_late();
+      const int um = t / tiles_n, tn = t - um * tiles_n;
+      const int n0 = tn * kCoutTile;
+      const int q0 = um * kPix / p.Ho;                      // global column index of the unit's first column
+      const int b0 = q0 / p.Wo, wo0 = q0 - b0 * p.Wo;       // wo0 == padded column of tap ti = 0
+      for (int chunk = 0; chunk < chunks; ++chunk) {
+        for (int tj = 0; tj < 3; ++tj, ++gx) {
+          const int sx = gx & 1;
+          mbar_wait(&x_empty[sx], ((gx >> 1) & 1) ^ 1);
+          const uint32_t x_dst = smem_u32(smem + sx * x_stage);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&x_full[sx], x_stage);
+            tma_load_4d(x_dst, &tm.a, &x_full[sx], chunk * kBlockK, tj - 1, wo0, b0);
+            if (TERMS > 1) tma_load_4d(x_dst + p.a_part_bytes, &tm.alo, &x_full[sx], chunk * kBlockK, tj - 1, wo0, b0);
+          }
+          for (int e = 0; e < 3 * kParts; ++e, ++gw) {      // (ti, part): W_hi then W_lo of each tap
+            const int sw = gw % NW;
+            mbar_wait(&w_empty[sw], ((gw / NW) & 1) ^ 1);
+            if (lane == 0) {
+              const int ti = e / kParts, part = e - ti * kParts;
+              const int tap = ti * 3 + tj;
+              mbar_arrive_expect_tx(&w_full[sw], kWPart);
+              tma_load_2d(smem_u32(w_ring + sw * kWPart), &tm.b, &w_full[sw], chunk * kBlockK,
+                          (part * 9 + tap) * p.Cout + n0);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (HALO && warp == 1) {
+    // ===================== MMA issuer (pixel windows) ===========================================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(kCoutTile, kPix);
+      int gx = 0, gw = 0, k = 0;
+      for (int t = blockIdx.x; t < total_units; t += gridDim.x, ++k) {
+        if (t + static_cast<int>(gridDim.x) >= total_units) pdl_trigger_conv_late();
+        const int acc = k & 1;
+        mbar_wait(&tmem_empty[acc], ((k >> 1) & 1) ^ 1);       // epilogue has drained this accumulator set
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kPix;
+        for (int u = 0; u < p.units; ++u, ++gx) {
+          const int sx = gx & 1;
+          mbar_wait(&x_full[sx], (gx >> 1) & 1);
+          const uint32_t x_base = smem_u32(smem + sx * x_stage);
+          for (int ti = 0; ti < 3; ++ti) {
+            // tap ti of this kernel column = the window shifted by ti columns (ti*Ho rows): whole swizzle atoms
+            const uint64_t x_desc = umma_desc_sw128(x_base + ti * p.Ho * 128);
+            {
+              const int sw = gw % NW;
+              mbar_wait(&w_full[sw], (gw / NW) & 1);
+              tc_fence_after();
+              const uint64_t w_desc = umma_desc_sw128(smem_u32(w_ring + sw * kWPart));
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) umma_f16(d_tmem, w_desc + 2 * kk, x_desc + 2 * kk, idesc, (u | ti | kk) != 0);
+              if (TERMS > 1) {
+                const uint64_t xl_desc = umma_desc_sw128(x_base + ti * p.Ho * 128 + p.a_part_bytes);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) umma_f16(d_tmem, w_desc + 2 * kk, xl_desc + 2 * kk, idesc, 1u);   // W_hi X_lo
+              }
+              umma_commit(&w_empty[sw]);
+              ++gw;
+            }
+            if (TERMS > 1) {
+              const int sw = gw % NW;
+              mbar_wait(&w_full[sw], (gw / NW) & 1);
+              tc_fence_after();
+              const uint64_t wl_desc = umma_desc_sw128(smem_u32(w_ring + sw * kWPart));
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) umma_f16(d_tmem, wl_desc + 2 * kk, x_desc + 2 * kk, idesc, 1u);     // W_lo X_hi
+              umma_commit(&w_empty[sw]);
+              ++gw;
+            }
+          }
+          umma_commit(&x_empty[sx]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 0) {
     // ===================== TMA producer: one continuous stage ring across units =================
     int g = 0;
     for (int t = blockIdx.x; t < total_units; t += gridDim.x) {
@@ -1398,6 +1499,18 @@ static int launch_conv_wt(const ConvMaps& tm, const ConvParams& p, int n_ctas, c
   return 0;
 }
 
+template <int TERMS>
+static int launch_conv_wt_halo(const ConvMaps& tm, const ConvParams& p, int n_ctas, size_t smem, cudaStream_t st) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    RLDM_CUDA(cudaFuncSetAttribute(conv_tc_wt_kernel<TERMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+    attr_smem = smem;
+  }
+  RLDM_CUDA(launch_pdl(conv_tc_wt_kernel<TERMS, true>, dim3(n_ctas), dim3(192), smem, st, tm, p));
+  return 0;
+}
+
 // Persistent halo-window variant: shared memory = 2 A windows + nb weight entries + slab + barriers (sized by the caller)
 template <int BLOCK_N, int TERMS>
 static int launch_conv_persistent_halo(const ConvMaps& tm, const ConvParams& p, int n_ctas, size_t smem, cudaStream_t st) {
@@ -1510,10 +1623,18 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
     if (nbs > 8) nbs = 8;
     static int min_nb = 0;
     if (min_nb == 0) { const char* e = getenv("RLDM_HALO_P_MINNB"); min_nb = e ? atoi(e) : 3; }
-    const bool halo_p = ks == 3 && stride == 1 && pad_lo == 1 && Ho >= 8 && pix % (2 * kBlockM) == 0 && !sc_x && parts == 2 &&
-                        split_k <= 1 && tiles_h > n_sms_h && nbs >= min_nb && hp && hp[0] != '0' &&
-                        !(hp[0] == 'n' && residual) && !getenv("RLDM_NO_PERSISTENT") && !getenv("RLDM_HALO");
-    if (halo_p) {
+    const bool halo_geom = ks == 3 && stride == 1 && pad_lo == 1 && Ho >= 8 && pix % (2 * kBlockM) == 0 && !sc_x && parts == 2 &&
+                           split_k <= 1 && tiles_h > n_sms_h && !getenv("RLDM_NO_PERSISTENT") && !getenv("RLDM_HALO");
+    const bool halo_p = halo_geom && nbs >= min_nb && hp && hp[0] != '0' && !(hp[0] == 'n' && residual);
+    // role-swapped kernel with pixel windows (default where it applies): no staging slab, so the weight ring is 4-5 deep
+    const char* wh = getenv("RLDM_CONV_WT_HALO");         // "0": off, "nores": only layers without a residual operand
+    const char* wt_env_h = getenv("RLDM_CONV_WT");
+    const size_t fixed_wt = 2 * a_stage + (4 + 2 * 8 + 4) * 8 + 16 + 1024;
+    int nws = fixed_wt + 2 * 16384 <= 232448 ? static_cast<int>((232448 - fixed_wt) / 16384) : 0;
+    if (nws > 8) nws = 8;
+    const bool halo_wt = halo_geom && !halo_p && BN == 128 && nws >= min_nb && !(wh && wh[0] == '0') &&
+                         !(wh && wh[0] == 'n' && residual) && !(wt_env_h && wt_env_h[0] == '0');
+    if (halo_p || halo_wt) {
       ConvMaps tmh;
       const int cols = 2 * (kBlockM / Ho);
       for (int part = 0; part < 2; ++part) {
@@ -1557,8 +1678,12 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
       p.stats_cpg = 2;
       const int units = tiles_h / 2;
       const int ctas = units < n_sms_h ? units : n_sms_h;
-      const size_t smem = fixed + nbs * b_entry;
       cudaStream_t st = as_stream(stream);
+      if (halo_wt) {
+        p.nb_stages = nws;
+        return launch_conv_wt_halo<3>(tmh, p, ctas, fixed_wt + static_cast<size_t>(nws) * 16384, st);
+      }
+      const size_t smem = fixed + nbs * b_entry;
       if (BN == 128) return launch_conv_persistent_halo<128, 3>(tmh, p, ctas, smem, st);
       return launch_conv_persistent_halo<64, 3>(tmh, p, ctas, smem, st);
     }
