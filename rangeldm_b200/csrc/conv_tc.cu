@@ -977,8 +977,10 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
 // 96 KB to 56 KB per tap (0.5 -> 0.29 wavefronts per MMA clock next to 0.75 of operand reads).  Two rings: two pixel
 // windows ([hi][lo], one per (64-channel chunk, tj)) and p.nb_stages weight entries of ONE operand part each: W_hi of
 // a tap feeds W_hi X_hi + W_hi X_lo and is released before W_lo is needed.
+constexpr int kWtEpiWarps = 8;                  // two warps per TMEM lane quadrant, four 32-pixel chunks each
+constexpr int kWtThreads = 64 + 32 * kWtEpiWarps;
 template <int TERMS, bool HALO = false>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kWtThreads, 1)
 conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
   constexpr int kCoutTile = 128, kPix = 256, STAGES = 2;
   constexpr int kMaxNW = 8;                                     // HALO: upper bound of the weight ring depth
@@ -1011,6 +1013,10 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
   const int taps = p.ks * p.ks;
   const int n_it = p.total_iters;
 
+  // profiling aid (normally NULL): clock64 stamps of CTA 0 -- [0] entry, [1] setup done, [2] first stage landed,
+  // [3] last MMA issued, [4] accumulators complete, [6] this warp's first chunk in registers, [8] stores issued, [5] done
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
+  if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
   pdl_trigger_conv_early();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm.a);
@@ -1024,7 +1030,7 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
     for (int s = 0; s < kRingBars; ++s) mbar_init(&full_bar[s], 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);          // one arrival per epilogue warp
+      mbar_init(&tmem_empty[a], kWtEpiWarps);   // one arrival per epilogue warp
     }
     mbar_fence_init();
   }
@@ -1034,6 +1040,7 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
   pdl_wait();
+  if (dbg && threadIdx.x == 0) p.dbg[1] = clock64();
 
   if (HALO && warp == 0) {
     // ===================== TMA producer (pixel windows): window ring of 2, weight ring of NW =====
@@ -1084,6 +1091,7 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
         for (int u = 0; u < p.units; ++u, ++gx) {
           const int sx = gx & 1;
           mbar_wait(&x_full[sx], (gx >> 1) & 1);
+          if (dbg && gx == 0) p.dbg[2] = clock64();
           const uint32_t x_base = smem_u32(smem + sx * x_stage);
           for (int ti = 0; ti < 3; ++ti) {
             // tap ti of this kernel column = the window shifted by ti columns (ti*Ho rows): whole swizzle atoms
@@ -1117,6 +1125,7 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
           umma_commit(&x_empty[sx]);
         }
         umma_commit(&tmem_full[acc]);
+        if (dbg && k == 0) p.dbg[3] = clock64();
       }
     }
     __syncwarp();
@@ -1180,6 +1189,7 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
         for (int it = 0; it < n_it; ++it, ++g) {
           const int s = g % STAGES;
           mbar_wait(&full_bar[s], (g / STAGES) & 1);
+          if (dbg && g == 0) p.dbg[2] = clock64();
           tc_fence_after();
           const uint32_t base = smem_u32(smem + s * kStageBytes);
           const uint64_t x_desc = umma_desc_sw128(base), w_desc = umma_desc_sw128(base + kWOff);
@@ -1197,12 +1207,15 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&tmem_full[acc]);
+        if (dbg && k == 0) p.dbg[3] = clock64();
       }
     }
     __syncwarp();
   } else {
     // ===================== epilogue warps: thread = output channel, drain unit k under unit k+1 ===
     const int q = warp & 3;                   // TMEM lane quadrant readable by this warp = channels 32q..32q+31
+    constexpr int kChunksPerWarp = (kPix / 32) / (kWtEpiWarps / 4);
+    const int ch0 = ((warp - 2) >> 2) * kChunksPerWarp;       // this warp's first 32-pixel chunk of every unit
     int k = 0;
     for (int t = blockIdx.x; t < total_units; t += gridDim.x, ++k) {
       const int acc = k & 1;
@@ -1219,17 +1232,20 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) rs[j] = __ldg(resp + static_cast<size_t>(ch * 32 + j) * p.Cout);
       };
-      if (resp) fetch_res(0);
+      if (resp) fetch_res(ch0);
       mbar_wait(&tmem_full[acc], (k >> 1) & 1);
+      const bool dbg_e = dbg && k == 0 && threadIdx.x == 64;
+      if (dbg_e) p.dbg[4] = clock64();
       if (t + static_cast<int>(gridDim.x) >= total_units) pdl_trigger_conv_late();
       tc_fence_after();
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-      for (int ch = 0; ch < kPix / 32; ++ch) {
+      for (int ch = ch0; ch < ch0 + kChunksPerWarp; ++ch) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * kPix + (static_cast<uint32_t>(q * 32) << 16) + ch * 32, r);
         tmem_ld_wait();
-        if (ch == kPix / 32 - 1) {            // last TMEM read of this unit: hand the accumulators back
+        if (dbg_e && ch == ch0) p.dbg[6] = p.dbg[7] = clock64();
+        if (ch == ch0 + kChunksPerWarp - 1) {  // this warp's last TMEM read of the unit: hand the accumulators back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
@@ -1237,7 +1253,7 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + add + (resp ? rs[j] : 0.f);
-        if (resp && ch + 1 < kPix / 32) fetch_res(ch + 1);     // next chunk's residual rows fly under these stores
+        if (resp && ch + 1 < ch0 + kChunksPerWarp) fetch_res(ch + 1);   // next chunk's residual rows fly under these stores
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           outp[static_cast<size_t>(ch * 32 + j) * p.Cout] = v[j];
@@ -1245,6 +1261,7 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
           s2 = fmaf(v[j], v[j], s2);
         }
       }
+      if (dbg_e) p.dbg[8] = clock64();
       if (p.stats) {                          // channel-pair moments of the finished output: (c, c+1) -> one slot
         s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
         s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
@@ -1254,6 +1271,7 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
           atomicAdd(st + 1, static_cast<double>(s2));
         }
       }
+      if (dbg_e) { __threadfence(); p.dbg[5] = clock64(); }
     }
   }
   tc_fence_before();
@@ -1495,7 +1513,7 @@ static int launch_conv_wt(const ConvMaps& tm, const ConvParams& p, int n_ctas, c
     RLDM_CUDA(cudaFuncSetAttribute(conv_tc_wt_kernel<TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  RLDM_CUDA(launch_pdl(conv_tc_wt_kernel<TERMS>, dim3(n_ctas), dim3(192), smem, st, tm, p));
+  RLDM_CUDA(launch_pdl(conv_tc_wt_kernel<TERMS>, dim3(n_ctas), dim3(kWtThreads), smem, st, tm, p));
   return 0;
 }
 
@@ -1507,7 +1525,7 @@ static int launch_conv_wt_halo(const ConvMaps& tm, const ConvParams& p, int n_ct
                                    static_cast<int>(smem)));
     attr_smem = smem;
   }
-  RLDM_CUDA(launch_pdl(conv_tc_wt_kernel<TERMS, true>, dim3(n_ctas), dim3(192), smem, st, tm, p));
+  RLDM_CUDA(launch_pdl(conv_tc_wt_kernel<TERMS, true>, dim3(n_ctas), dim3(kWtThreads), smem, st, tm, p));
   return 0;
 }
 
@@ -1671,7 +1689,7 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
       p.units = (Cin / kBlockK) * 3;
       p.a_part_bytes = static_cast<int>(a_stage / 2);
       p.nb_stages = nbs;
-      p.dbg = nullptr;
+      p.dbg = g_conv_dbg;
       p.ws = nullptr;
       p.stats = stats;
       p.stats_G = Cout / 2;
