@@ -449,6 +449,29 @@ constexpr int kApSlot = 32;                     // TMEM columns per output slot
 constexpr int kApXFloats = 10;                  // (max, sum, o[8]) of group 1 per row
 constexpr int kApThreads = 12 * 32;            // 8 softmax warps, MMA warp, 3 loader warps
 
+// 32-bit shared-window addresses for the per-tile barrier traffic (no generic-pointer arithmetic in the hot loops)
+__device__ __forceinline__ void ap_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if (++spins > (1u << 24)) {
+      printf("rldm: attention mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void ap_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ap_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+#define AP_BAR(field) (sb_a + static_cast<uint32_t>(offsetof(AttnPipeSmem, field)))
+
 struct AttnPipeSmem {
   uint64_t q_full[2], q_empty[2];
   uint64_t k_full[kApRing], k_empty[kApRing], v_full[kApRing], v_empty[kApRing];
@@ -468,6 +491,9 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
   uint8_t* sV = sK + kApRing * kApKBytes;                 // [6][4 KB]
   float* sX = reinterpret_cast<float*>(sV + kApRing * kApVBytes);   // [10][128]: group 1's partial result of an item
   AttnPipeSmem* sb = reinterpret_cast<AttnPipeSmem*>(sX + kApXFloats * kAtTile);
+  const uint32_t sQ_a = (smem_u32(smem_raw) + 1023u) & ~1023u;          // the same carve-up as 32-bit shared addresses
+  const uint32_t sK_a = sQ_a + 2 * kAtQBytes, sV_a = sK_a + kApRing * kApKBytes;
+  const uint32_t sX_a = sV_a + kApRing * kApVBytes, sb_a = sX_a + kApXFloats * kAtTile * 4;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t rowf = 3 * static_cast<size_t>(C);
@@ -608,47 +634,54 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
     while (q_next < my_items) load_q(q_next++);
   } else if (warp == 8) {
     // ===================== MMA issuer ===========================================================
+    // (all ring positions and barrier parities advance incrementally: no division in the per-tile path)
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_f16(128, kApKT);
       constexpr uint32_t idesc_o = umma_idesc_f16(128, kApSlot);
-      int qk_n = 0, qk_t = 0;                              // (item, tile) of the next Q K^T
-      auto issue_qk = [&](int g) {      // S buffer g % 3 is free: P V of tile g - 3 was issued before
-        const int slot = g % kApRing, bs = g % 3;
-        if (qk_t == 0) mbar_wait(&sb->q_full[qk_n & 1], (qk_n >> 1) & 1);
-        mbar_wait(&sb->k_full[slot], (g / kApRing) & 1);
+      uint32_t qk_slot = 0, qk_ring_par = 0, qk_bs = 0, qk_buf = 0, qk_buf_par = 0;
+      int qk_t = 0;                                        // tile of the next Q K^T inside its item
+      auto issue_qk = [&]() {           // S buffer qk_bs is free: P V of the tile three back was issued before
+        if (qk_t == 0) ap_wait(AP_BAR(q_full) + qk_buf * 8, qk_buf_par);
+        ap_wait(AP_BAR(k_full) + qk_slot * 8, qk_ring_par);
         tc_fence_after();
-        const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ + (qk_n & 1) * kAtQBytes));
-        const uint64_t k_desc = umma_desc_sw128(smem_u32(sK + slot * kApKBytes));
-        const uint32_t d = tmem + bs * kApKT;
+        const uint64_t q_desc = umma_desc_sw128(sQ_a + qk_buf * kAtQBytes);
+        const uint64_t k_desc = umma_desc_sw128(sK_a + qk_slot * kApKBytes);
+        const uint32_t d = tmem + qk_bs * kApKT;
         umma_f16(d, q_desc, k_desc, idesc_s, 0u);
         umma_f16(d, q_desc + 2, k_desc + 2, idesc_s, 1u);
-        umma_commit(&sb->s_full[bs]);
-        umma_commit(&sb->k_empty[slot]);
+        ap_commit(AP_BAR(s_full) + qk_bs * 8);
+        ap_commit(AP_BAR(k_empty) + qk_slot * 8);
         if (++qk_t == TS) {
-          umma_commit(&sb->q_empty[qk_n & 1]);
+          ap_commit(AP_BAR(q_empty) + qk_buf * 8);
           qk_t = 0;
-          ++qk_n;
+          qk_buf ^= 1;
+          if (qk_buf == 0) qk_buf_par ^= 1;
         }
+        if (++qk_slot == kApRing) { qk_slot = 0; qk_ring_par ^= 1; }
+        if (++qk_bs == 3) qk_bs = 0;
       };
-      for (int g = 0; g < 3 && g < total_tiles; ++g) issue_qk(g);
+      for (int g = 0; g < 3 && g < total_tiles; ++g) issue_qk();
+      uint32_t slot = 0, ring_par = 0, bs = 0, bs_par = 0, bo = 0;
       for (int g = 0; g < total_tiles; ++g) {
-        const int slot = g % kApRing, bs = g % 3, bo = g & 1;
-        mbar_wait(&sb->v_full[slot], (g / kApRing) & 1);
+        ap_wait(AP_BAR(v_full) + slot * 8, ring_par);
         // p_full(g): the owning group has written P(g) and, before that, folded output slot bo of tile g - 2
-        mbar_wait(&sb->p_full[bs], (g / 3) & 1);
+        ap_wait(AP_BAR(p_full) + bs * 8, bs_par);
         tc_fence_after();
         const uint32_t d = tmem + kApSlot0 + kApSlot * bo;
-        const uint64_t v_desc0 = umma_desc_sw128(smem_u32(sV + slot * kApVBytes));
+        const uint32_t p_tm = tmem + bs * kApKT;
+        const uint64_t v_desc0 = umma_desc_sw128(sV_a + slot * kApVBytes);
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)                   // K step = 16 keys = 8 columns of chunk ks / 2
-            umma_f16_ts(d, tmem + bs * kApKT + (ks >> 1) * 32 + part * 16 + (ks & 1) * 8, v_desc0 + 2 * ks, idesc_o,
-                        (part | ks) != 0);
+            umma_f16_ts(d, p_tm + (ks >> 1) * 32 + part * 16 + (ks & 1) * 8, v_desc0 + 2 * ks, idesc_o, (part | ks) != 0);
         }
-        umma_commit(&sb->o_full[bo]);
-        umma_commit(&sb->v_empty[slot]);
-        if (g + 3 < total_tiles) issue_qk(g + 3);
+        ap_commit(AP_BAR(o_full) + bo * 8);
+        ap_commit(AP_BAR(v_empty) + slot * 8);
+        if (g + 3 < total_tiles) issue_qk();
+        if (++slot == kApRing) { slot = 0; ring_par ^= 1; }
+        if (++bs == 3) { bs = 0; bs_par ^= 1; }
+        bo ^= 1;
       }
     }
     __syncwarp();
@@ -658,7 +691,7 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
     const int row = quad * 32 + lane;                      // query row == TMEM lane
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quad * 32) << 16);
     const uint32_t t_o = t_lane + kApSlot0 + kApSlot * grp; // this group's output slot
-    const uint32_t x_row = smem_u32(sX) + row * 4;
+    const uint32_t x_row = sX_a + row * 4;
     float m_run = -INFINITY, l_run = 0.f;
     float2 o[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     float m_prev = 0.f;                                    // max of the group's tile whose output is still in TMEM
@@ -667,7 +700,7 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
       const float m_new = fmaxf(m_run, m_prev);
       const float a = at_ex2(m_run - m_new), c = at_ex2(m_prev - m_new);
       m_run = m_new;
-      mbar_wait(&sb->o_full[grp], (k - 1) & 1);
+      ap_wait(AP_BAR(o_full) + grp * 8, (k - 1) & 1);
       tc_fence_after();
       uint32_t r[16];
       tmem_ld_32x16(t_o, r);
@@ -684,21 +717,21 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
     };
     auto finalize = [&](int n) {                           // the two groups' partial results of item n meet
       if (grp == 1) {
-        mbar_wait(&sb->x_empty, (n & 1) ^ 1);
+        ap_wait(AP_BAR(x_empty), (n & 1) ^ 1);
         const float vals[kApXFloats] = {m_run, l_run, o[0].x, o[0].y, o[1].x, o[1].y, o[2].x, o[2].y, o[3].x, o[3].y};
 #pragma unroll
         for (int j = 0; j < kApXFloats; ++j)
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(x_row + j * kAtTile * 4), "f"(vals[j]) : "memory");
         __syncwarp();
-        if (lane == 0) at_arrive(&sb->x_full);
+        if (lane == 0) ap_arrive(AP_BAR(x_full));
       } else {
-        mbar_wait(&sb->x_full, n & 1);
+        ap_wait(AP_BAR(x_full), n & 1);
         float v[kApXFloats];
 #pragma unroll
         for (int j = 0; j < kApXFloats; ++j)
           asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[j]) : "r"(x_row + j * kAtTile * 4) : "memory");
         __syncwarp();
-        if (lane == 0) at_arrive(&sb->x_empty);
+        if (lane == 0) ap_arrive(AP_BAR(x_empty));
         const float m = fmaxf(m_run, v[0]);
         const float a0 = at_ex2(m_run - m), a1 = at_ex2(v[0] - m);
         const float inv = 1.0f / fmaf(l_run, a0, v[1] * a1);
@@ -718,39 +751,44 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[e] = make_float2(0.f, 0.f);
     };
-    for (int n = 0; n < my_items; ++n) {
-      for (int t = grp; t < TS; t += 2, ++k) {
-        const int g = n * TS + t, bs = g % 3;
-        const uint32_t t_s = t_lane + bs * kApKT;
-        mbar_wait(&sb->s_full[bs], (g / 3) & 1);
-        tc_fence_after();
-        uint32_t r[32];                                    // two cheap passes over the 64 scores of the row
-        tmem_ld_32x32(t_s, r);
-        tmem_ld_wait();
-        float m = at_max32(r);
-        tmem_ld_32x32(t_s + 32, r);
-        tmem_ld_wait();
-        m = fmaxf(m, at_max32(r));
-        at_exp_store32_packed(r, m, t_s + 32);             // P = 2^(S - m) in place: [hi 16 | lo 16] per 32-key chunk
-        tmem_ld_32x32(t_s, r);
-        tmem_ld_wait();
-        at_exp_store32_packed(r, m, t_s);
-        tmem_st_wait();
-        // the group's previous tile has long finished its P V; its slot is overwritten by P V of this tile, which is
-        // issued only after the arrival below
-        const bool item_done = k > 0 && t == grp;          // that tile was the last one of item n - 1
-        if (k > 0) fold();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) at_arrive(&sb->p_full[bs]);
-        if (item_done) finalize(n - 1);
-        m_prev = m;
-      }
+    // own tiles g = grp, grp + 2, ...: one stream across items (TS is even); S buffer g % 3 and the parity of g / 3
+    // advance incrementally
+    const int own_total = total_tiles >> 1, own_per_item = TS >> 1;
+    uint32_t bs = grp, s_par = 0;
+    int left = own_per_item, n_done = 0;                   // own tiles left in the current item; finished items
+    for (; k < own_total; ++k) {
+      const uint32_t t_s = t_lane + bs * kApKT;
+      ap_wait(AP_BAR(s_full) + bs * 8, s_par);
+      tc_fence_after();
+      uint32_t r[32];                                      // two cheap passes over the 64 scores of the row
+      tmem_ld_32x32(t_s, r);
+      tmem_ld_wait();
+      float m = at_max32(r);
+      tmem_ld_32x32(t_s + 32, r);
+      tmem_ld_wait();
+      m = fmaxf(m, at_max32(r));
+      at_exp_store32_packed(r, m, t_s + 32);               // P = 2^(S - m) in place: [hi 16 | lo 16] per 32-key chunk
+      tmem_ld_32x32(t_s, r);
+      tmem_ld_wait();
+      at_exp_store32_packed(r, m, t_s);
+      tmem_st_wait();
+      // the group's previous tile has long finished its P V; its slot is overwritten by P V of this tile, which is
+      // issued only after the arrival below
+      const bool item_done = k > 0 && left == own_per_item;   // that tile was the last one of the previous item
+      if (k > 0) fold();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ap_arrive(AP_BAR(p_full) + bs * 8);
+      if (item_done) finalize(n_done++);
+      m_prev = m;
+      bs += 2;
+      if (bs >= 3) { bs -= 3; s_par ^= 1; }
+      if (--left == 0) left = own_per_item;
     }
     if (k > 0) {
       fold();
       tc_fence_before();
-      finalize(my_items - 1);
+      finalize(n_done);
     }
   }
   tc_fence_before();
