@@ -446,7 +446,7 @@ constexpr int kApKBytes = kApKT * 128;          // 8 KB
 constexpr int kApVBytes = 32 * 128;             // 4 KB: one K-atom of 64 keys x 32 rows (16 written per tile)
 constexpr int kApSlot0 = 192;
 constexpr int kApSlot = 32;                     // TMEM columns per output slot
-constexpr int kApXFloats = 10;                  // (max, sum, o[8]) of group 1 per row
+constexpr int kApXFloats = 10;                  // (max, sum, o[8]) of group 0 per row
 constexpr int kApThreads = 12 * 32;            // 8 softmax warps, MMA warp, 3 loader warps
 
 // 32-bit shared-window addresses for the per-tile barrier traffic (no generic-pointer arithmetic in the hot loops)
@@ -489,7 +489,7 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
   uint8_t* sQ = smem;                                     // [2][16 KB]
   uint8_t* sK = sQ + 2 * kAtQBytes;                       // [6][8 KB]
   uint8_t* sV = sK + kApRing * kApKBytes;                 // [6][4 KB]
-  float* sX = reinterpret_cast<float*>(sV + kApRing * kApVBytes);   // [10][128]: group 1's partial result of an item
+  float* sX = reinterpret_cast<float*>(sV + kApRing * kApVBytes);   // [10][128]: group 0's partial result of an item
   AttnPipeSmem* sb = reinterpret_cast<AttnPipeSmem*>(sX + kApXFloats * kAtTile);
   const uint32_t sQ_a = (smem_u32(smem_raw) + 1023u) & ~1023u;          // the same carve-up as 32-bit shared addresses
   const uint32_t sK_a = sQ_a + 2 * kAtQBytes, sV_a = sK_a + kApRing * kApKBytes;
@@ -716,7 +716,9 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
       }
     };
     auto finalize = [&](int n) {                           // the two groups' partial results of item n meet
-      if (grp == 1) {
+      // group 0 owns the even tiles, so it is done with an item one tile EARLIER than group 1: it deposits its partial
+      // result and moves on; group 1 (which would otherwise be waited for) merges and writes the output
+      if (grp == 0) {
         ap_wait(AP_BAR(x_empty), (n & 1) ^ 1);
         const float vals[kApXFloats] = {m_run, l_run, o[0].x, o[0].y, o[1].x, o[1].y, o[2].x, o[2].y, o[3].x, o[3].y};
 #pragma unroll
