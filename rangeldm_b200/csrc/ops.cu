@@ -521,9 +521,9 @@ __global__ void __launch_bounds__(256)
 norm_conv_out_kernel(const float* __restrict__ x, const double* __restrict__ sums, const double* __restrict__ pairs,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int G, int silu,
                      const float* __restrict__ wgt, const float* __restrict__ bias, float* __restrict__ out,
-                     int W, int H, int Cin, int circular, int TW, int LPP) {
+                     int W, int H, int Cin, int circular, int TW, int LPP, int PP) {
   extern __shared__ float sh_no[];
-  const int pitch = Cin + 4 * LPP;
+  const int pitch = PP > 1 ? Cin + 4 : Cin + 4 * LPP;
   float* sc = sh_no;                       // [Cin]
   float* sf = sc + Cin;                    // [Cin]
   float* w_s = sf + Cin;                   // [9][COUT][Cin]
@@ -610,8 +610,66 @@ norm_conv_out_kernel(const float* __restrict__ x, const double* __restrict__ sum
     }
   }
   __syncthreads();
-  // ---- 3x3 conv from shared memory: LPP lanes per output pixel split the channel loop
   const int sub = threadIdx.x % LPP;
+  if (PP == 4) {
+    // ---- 3x3 conv from shared memory, register-blocked: a thread owns FOUR vertically adjacent output pixels (and
+    // LPP lanes split the channel loop).  Per (kernel column, channel quad) it loads the 6 input rows once and every
+    // weight quad once for all four pixels: 18 LDS.128 per 192 FMA instead of 5 per 16 -- the one-pixel loop below is
+    // bound by the shared-memory load pipe, not by the FMAs.
+    const int hq = H >> 2;
+    const int n_grp = TW * hq;
+    for (int pg = threadIdx.x / LPP; pg < n_grp; pg += blockDim.x / LPP) {
+      const int col = pg / hq, h0 = (pg - col * hq) << 2;
+      const int w = w0 + col;
+      float acc[4][COUT];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int n = 0; n < COUT; ++n) acc[q][n] = 0.f;
+      for (int i = 0; i < 3; ++i) {
+        const float* xcol = tile + (col + i) * H * pitch;
+        const float* wt = w_s + i * 3 * COUT * Cin;
+        for (int c = sub * 4; c < Cin; c += 4 * LPP) {
+          float4 xr[6];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            const int hj = h0 - 1 + r;
+            xr[r] = (hj >= 0 && hj < H) ? *reinterpret_cast<const float4*>(xcol + hj * pitch + c)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+#pragma unroll
+            for (int n = 0; n < COUT; ++n) {
+              const float4 wv = *reinterpret_cast<const float4*>(wt + (j * COUT + n) * Cin + c);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 a = xr[q + j];
+                acc[q][n] = fmaf(a.x, wv.x, acc[q][n]); acc[q][n] = fmaf(a.y, wv.y, acc[q][n]);
+                acc[q][n] = fmaf(a.z, wv.z, acc[q][n]); acc[q][n] = fmaf(a.w, wv.w, acc[q][n]);
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < COUT; ++n) {
+        const float bn = bias ? __ldg(bias + n) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v = acc[q][n];
+          for (int o = LPP >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          acc[q][n] = v + bn;
+        }
+        // out is (B, Cout, W, H): the four pixels are contiguous along H
+        if (sub == 0 && w < W)
+          *reinterpret_cast<float4*>(out + ((static_cast<size_t>(b) * COUT + n) * W + w) * H + h0) =
+              make_float4(acc[0][n], acc[1][n], acc[2][n], acc[3][n]);
+      }
+    }
+    return;
+  }
+  // ---- 3x3 conv from shared memory: LPP lanes per output pixel split the channel loop
   const int n_pix = TW * H;
   for (int p = threadIdx.x / LPP; p < n_pix; p += blockDim.x / LPP) {
     const int col = sh_h >= 0 ? p >> sh_h : p / H;
@@ -1160,13 +1218,15 @@ extern "C" int rldm_norm_conv_out(const float* x, const double* sums, const doub
   RLDM_CHECK(!pairs || (Cin / G) % 2 == 0, "norm_conv_out: channel-pair moments need an even group size");
   RLDM_CHECK(H >= 1 && H <= 256, "norm_conv_out: H out of range (%d)", H);
   // lanes per pixel: keep ~256 threads busy on a TW x H pixel tile
+  // four pixels per thread (register-blocked inner loop) whenever H allows it; RLDM_NCO_PP1=1: one pixel per thread
+  const int PP = (H % 4 == 0 && Cout <= 4 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && !getenv("RLDM_NCO_PP1")) ? 4 : 1;
   int TW = 8, LPP = 1;
   size_t smem = 0;
   for (;; TW >>= 1) {
     LPP = 1;
-    while (LPP < 8 && TW * H * LPP * 2 <= 256 && Cin % (8 * LPP) == 0) LPP *= 2;
+    while (LPP < 8 && (TW * H / PP) * LPP * 2 <= 256 && Cin % (8 * LPP) == 0) LPP *= 2;
     smem = (2 * static_cast<size_t>(Cin) + 9 * static_cast<size_t>(Cout) * Cin +
-            static_cast<size_t>(TW + 2) * H * (Cin + 4 * LPP)) * sizeof(float);
+            static_cast<size_t>(TW + 2) * H * (PP > 1 ? Cin + 4 : Cin + 4 * LPP)) * sizeof(float);
     if (smem <= 110 * 1024 || TW == 1) break;
   }
   RLDM_CHECK(smem <= 220 * 1024, "norm_conv_out: tile does not fit shared memory (H=%d Cin=%d Cout=%d)", H, Cin, Cout);
@@ -1180,7 +1240,7 @@ extern "C" int rldm_norm_conv_out(const float* x, const double* sums, const doub
       smem_set = 220 * 1024;                                                                                          \
     }                                                                                                                 \
     RLDM_CUDA(launch_pdl(norm_conv_out_kernel<N>, grid, dim3(256), smem, st, x, sums, pairs, gamma, beta, eps, G, silu, wgt, \
-                         bias, out, W, H, Cin, circular, TW, LPP));                                                   \
+                         bias, out, W, H, Cin, circular, TW, LPP, PP));                                               \
   }
   switch (Cout) {
     case 2: RLDM_NCO(2) break;
