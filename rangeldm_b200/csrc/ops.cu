@@ -567,9 +567,9 @@ norm_conv_out_kernel(const float* __restrict__ x, const double* __restrict__ sum
   // H and Cin/4 are powers of two in every reference config: shifts instead of integer divisions (sh < 0: generic)
   const int sh_c = (c4n & (c4n - 1)) == 0 ? 31 - __clz(c4n) : -1;
   const int sh_h = (H & (H - 1)) == 0 ? 31 - __clz(H) : -1;
-  // four independent 16 B loads in flight per thread before any of them is consumed (the loop is bound by the
-  // global-load latency otherwise: one outstanding load per thread)
-  constexpr int kBatch = 4;
+  // eight independent 16 B loads in flight per thread before any of them is consumed (the staging is bound by the
+  // global-load latency: 20-24 items per thread = three round trips instead of six with four in flight)
+  constexpr int kBatch = 8;
   for (int i0 = threadIdx.x; i0 < n_items; i0 += blockDim.x * kBatch) {
     float4 v[kBatch];
     int rr[kBatch], cc[kBatch];
