@@ -1525,7 +1525,15 @@ static int launch_conv_wt_halo(const ConvMaps& tm, const ConvParams& p, int n_ct
                                    static_cast<int>(smem)));
     attr_smem = smem;
   }
-  RLDM_CUDA(launch_pdl(conv_tc_wt_kernel<TERMS, true>, dim3(n_ctas), dim3(kWtThreads), smem, st, tm, p));
+  // single-wave launches (one unit per CTA: the top-level UNet layers) may start under the tail of the producing
+  // pass: setup, TMEM allocation and descriptor prefetch overlap it (RLDM_WT_PDL=1; measured before adoption)
+  static int wt_pdl = -1;
+  if (wt_pdl < 0) { const char* e = getenv("RLDM_WT_PDL"); wt_pdl = e ? atoi(e) : 0; }
+  const int units = (p.M_total / 256) * (p.Cout / 128);
+  if (wt_pdl && units <= n_ctas)
+    RLDM_CUDA(launch_pdl_small(conv_tc_wt_kernel<TERMS, true>, dim3(n_ctas), dim3(kWtThreads), smem, st, tm, p));
+  else
+    RLDM_CUDA(launch_pdl(conv_tc_wt_kernel<TERMS, true>, dim3(n_ctas), dim3(kWtThreads), smem, st, tm, p));
   return 0;
 }
 
