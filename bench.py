@@ -14,6 +14,9 @@ synthetic N(0,1) noise, random-init weights.  One "step" = one batch: the whole 
           H2D of the noise, sampling, D2H of the finished images into host memory)
   roofline : tcgen05 conv kernel: algorithmic FLOPs / CUDA-event time of its launches (per-op pass)
   cpu_baseline : the fp32 PyTorch oracle (restated diffusers modules, reference loop) on the host cores
+  gpu_library_baseline : the SAME oracle modules (stock PyTorch ops: cuDNN convolutions, F.group_norm, SDPA -- what
+          the reference's diffusers/sgm modules call) on this B200 at the same batch: strict fp32, PyTorch defaults
+          (TF32 convolutions), bf16 autocast; eager and as one CUDA graph (the bar for the kernels)
 """
 import argparse
 import json
@@ -39,6 +42,8 @@ STEPS = 20
 PER_GPU_BATCH = 8
 GFLOP_PER_IMAGE = 20 * 34.07 + 157.46
 METRIC = "range-images/sec (64x1024, 20-step DPM-Solver)"
+DTYPE = ("split-fp16 x3 (activations and weights as hi+lo fp16 pairs; Ah*Wh + Al*Wh + Ah*Wl on tcgen05 kind::f16 into "
+         "fp32 TMEM: ~22-bit operands, 3 MMAs per algorithmic MAC), fp32 elsewhere")
 WORKLOAD = ("C3 RangeLDM KITTI-360: latent 4x256x16 UNet[128,128,256,256] x 20-step DPM-Solver++(2M, leading) "
             "+ AutoencoderKL 4x decode -> 2x1024x64")
 
@@ -268,7 +273,7 @@ def run_native(args):
         out = {
             "metric": METRIC, "value": round(value, 3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "fp16 x fp16 -> fp32 (tcgen05 kind::f16), fp32 elsewhere",
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
             "data": "synthetic N(0,1) noise, random-init weights",
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "sampler_steps": STEPS,
                        "parallelism": f"dp{world} (batch-axis shards, no hot-path collective; "
@@ -288,6 +293,8 @@ def run_native(args):
                          "per_kind_ms_one_unet_plus_decoder": {k: round(v, 4) for k, v in sorted(ms.items())}},
             "clocks": clk,
         }
+        if not args.no_library_baseline and world == 1:
+            out["gpu_library_baseline"] = gpu_library_baseline(dev, B)
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_reference(samples=args.cpu_samples)
     if world > 1:
@@ -321,6 +328,67 @@ def cpu_reference(samples=2, threads=None):
                       f"{torch.__version__}, {dt:.1f} s"}
 
 
+def gpu_library_baseline(dev, B, reps=3):
+    """What stock PyTorch 2.11 + cuDNN does with the reference's op graph on the same B200 (VERDICT r1
+    item 3): the oracle modules (restated diffusers UNet2DModel / sgm Decoder / DPM-Solver++ loop, `ldm/pipelines.py:
+    353-367`) moved to the device, C3 at per-GPU batch `B`, random-init weights.  Variants: strict fp32; PyTorch
+    defaults (cudnn.allow_tf32 = True: TF32 convolutions, fp32 matmuls); bf16 autocast.  Each eager (the reference's
+    Python loop, ~4000 launches per batch) and captured as ONE CUDA graph (its launch overhead removed)."""
+    from oracle import nets, pipeline, schedulers
+    torch.manual_seed(0)
+    unet = nets.OracleUNet2DModel(**nets.UNET_C3).eval().to(dev)
+    vae = nets.OracleAutoencoderKL().eval().to(dev)
+    sch = schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading")
+    noise = torch.randn((B, 4, 256, 16), device=dev)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    out = {"unit": "images/s", "per_gpu_batch": B, "torch": torch.__version__, "cudnn": torch.backends.cudnn.version()}
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return round(reps * B / (e0.elapsed_time(e1) / 1e3), 2)
+
+    try:
+        torch.backends.cudnn.benchmark = True
+        for name, conv_tf32, mm_tf32, ac in (("fp32_strict", False, False, None), ("tf32_default", True, False, None),
+                                             ("bf16_autocast", True, True, torch.bfloat16)):
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = conv_tf32, mm_tf32
+
+            def sample():
+                if ac is None:
+                    return pipeline.ldm_sample(unet, vae, sch, noise, STEPS)
+                with torch.autocast("cuda", dtype=ac):
+                    return pipeline.ldm_sample(unet, vae, sch, noise, STEPS)
+            try:
+                out[name + "_eager"] = timed(sample)
+            except Exception as e:          # noqa: BLE001
+                out[name + "_eager"] = f"failed: {type(e).__name__}: {e}"[:200]
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    sample()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    sample()
+                out[name + "_graph"] = timed(g.replay)
+                del g
+            except Exception as e:          # noqa: BLE001
+                out[name + "_graph"] = f"failed: {type(e).__name__}: {e}"[:200]
+                torch.cuda.synchronize()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -346,6 +414,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--cpu-samples", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -158,9 +158,11 @@ int rldm_attention(const float* qkv, uint16_t* out, uint16_t* out_lo, int B, int
 
 /* ---- time embedding -----------------------------------------------------------------------
  * Replaces Timesteps + TimestepEmbedding + every ResnetBlock2D.time_emb_proj(silu(emb))
- * (SURVEY.md App. A.1 steps 1 and ResnetBlock2D).  t:(B) fp32 timesteps.
+ * (SURVEY.md App. A.1 steps 1 and ResnetBlock2D).  t:(B) fp32 timesteps -- B rows: the batch of one forward, or
+ * the whole timestep table of a trajectory (one row per sampling step; the conv epilogues then read row `step`
+ * for every image, temb_stride 0).
  * w1:[D4][D0] b1:[D4] w2:[D4][D4] b2:[D4]; wp:[T][D4] bp:[T] = all projections stacked row-wise.
- * scratch:(B,D4) fp32; out:(B,T) fp32. */
+ * scratch:(2,B,D4) fp32; out:(B,T) fp32.  D0, D4 multiples of 32, <= 1024.  Three launches. */
 int rldm_temb(const float* t, const float* w1, const float* b1, const float* w2, const float* b2,
               const float* wp, const float* bp, float* scratch, float* out, int B, int D0, int D4,
               int T, void* stream);

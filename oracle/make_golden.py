@@ -12,6 +12,10 @@ rebuild them anywhere without the reference tree and without committing megabyte
   ldm_pipeline.pt  reference `LDMPipelineRange.__call__` / `DDIMPipelineRange.__call__`
                    (`ldm/pipelines.py:282-383,144-258`) driving the oracle nets through the diffusers shim
   sparse_encoder2.pt reference `SparseRangeImageEncoder2.forward` (`ldm/encoders.py:86-95`)
+  unet_blocks.pt   reference sgm `ResnetBlock` WITH temb (`model.py:301-362`), `AttnBlock` (`:372-412`) and
+                   `get_timestep_embedding` (`:28-46`): pins of the oracle's ResnetBlock2D/Attention/sinusoid
+  samplers.pt      reference `EulerEDMSampler` (== DDIM eta 0), `EulerAncestralSampler` (== DDPM ancestral) and
+                   `DPMPP2MSampler` with n = 5 (< 15 steps) trajectories (`sampling.py:88-134,240-247,290-345`)
   range_to_points.pt reference `point_cloud_to_range_image_KITTI.to_pc_torch` (`ldm/dataset.py:228-276`)
 """
 import importlib
@@ -97,6 +101,105 @@ def make_range_to_points():
     print("range_to_points.pt", {k: tuple(v.shape) for k, v in out.items() if torch.is_tensor(v)})
 
 
+def make_block_pins(model, sampling):
+    """tests/golden/unet_blocks.pt and samplers.pt: the arithmetic the oracle restates from diffusers, pinned to the
+    reference's in-tree twins (ResnetBlock with temb, AttnBlock == Attention(heads=1), timestep
+    embedding; DDIM/DDPM steps through the k-diffusion style samplers in VE form)."""
+    g = torch.Generator().manual_seed(19)
+    out = {}
+    # ---- ResnetBlock with a time embedding (`model.py:342-362`), 64 -> 128 with the 1x1 nin_shortcut and 128 -> 128
+    for name, cin, cout, seed in (("res_sc", 64, 128, 901), ("res_id", 128, 128, 902)):
+        ob = seeded(nets.ResnetBlock2D, seed, cin=cin, cout=cout, temb_ch=512, eps=1e-6)
+        rb = model.ResnetBlock(in_channels=cin, out_channels=cout, dropout=0.0, temb_channels=512, act="silu",
+                               circular=True).eval()
+        sd = {k.replace("time_emb_proj", "temb_proj").replace("conv_shortcut", "nin_shortcut"): v
+              for k, v in ob.state_dict().items()}
+        rb.load_state_dict(sd, strict=True)
+        x = torch.randn(2, cin, 16, 8, generator=g)
+        temb = torch.randn(2, 512, generator=g)
+        with torch.no_grad():
+            out[name] = {"x": x, "temb": temb, "y": rb(x, temb), "seed": seed, "cin": cin, "cout": cout}
+    # ---- AttnBlock (`model.py:372-412`) == diffusers Attention with ONE head of dim C
+    oa = seeded(nets.Attention, 903, ch=64, head_dim=64, eps=1e-6)
+    ra = model.AttnBlock(64).eval()
+    sd = {}
+    for k, v in oa.state_dict().items():
+        k2 = (k.replace("group_norm", "norm").replace("to_q", "q").replace("to_k", "k").replace("to_v", "v")
+               .replace("to_out.0", "proj_out"))
+        sd[k2] = v[:, :, None, None] if (v.ndim == 2) else v
+    ra.load_state_dict(sd, strict=True)
+    x = torch.randn(2, 64, 16, 8, generator=g)
+    with torch.no_grad():
+        out["attn"] = {"x": x, "y": ra(x), "seed": 903}
+    # ---- sinusoidal timestep embedding (`model.py:28-46`)
+    t = torch.tensor([0, 1, 47, 500, 940, 999])
+    out["temb"] = {"t": t, "y": model.get_timestep_embedding(t, 128)}
+    torch.save(out, os.path.join(OUT, "unet_blocks.pt"))
+
+    # ---- samplers: VP <-> VE map x_VE = x / alpha, sigma = sqrt((1 - ac) / ac)
+    guiders = importlib.import_module("sgm.modules.diffusionmodules.guiders")
+    Wm = toy_eps_matrix()
+    eps_model = lambda v: torch.tanh(v @ Wm)
+    so = {}
+    n = 10
+    d = schedulers.OracleDDIMScheduler()
+    d.set_timesteps(n)
+    ac = d.alphas_cumprod.double()
+    ts = d.timesteps.tolist()
+    step = d.num_train_timesteps // n
+    a_of = lambda tt: ac[tt] if tt >= 0 else torch.tensor(1.0, dtype=torch.double)
+    sig_of = lambda tt: ((1 - a_of(tt)) / a_of(tt)).sqrt()
+    x0 = torch.randn(4, 16, generator=g)
+    ones = torch.ones(4, dtype=torch.double)
+    # DDIM eta = 0  ==  Euler step of the probability-flow ODE (`EulerEDMSampler.sampler_step`, gamma = 0)
+    eul = sampling.EulerEDMSampler.__new__(sampling.EulerEDMSampler)
+    eul.guider, eul.s_noise = guiders.IdentityGuider(), 1.0
+    xv = x0.double() / a_of(ts[0]).sqrt()
+    traj = []
+    for tt in ts:
+        a = a_of(tt).sqrt()
+        den = lambda xin, sigma, c, a=a: xin - sigma.view(-1, 1) * eps_model((xin * a).float()).double()
+        xv = eul.sampler_step(ones * sig_of(tt), ones * sig_of(tt - step), den, xv, {}, None, gamma=0.0)
+        traj.append((xv * a_of(tt - step).sqrt()).float())
+    so["ddim"] = {"x": x0, "n": n, "traj": torch.stack(traj), "timesteps": d.timesteps.clone()}
+    # DDPM ancestral  ==  `EulerAncestralSampler.sampler_step` with eta = 1 and the same unit noise
+    anc = sampling.EulerAncestralSampler.__new__(sampling.EulerAncestralSampler)
+    anc.guider, anc.eta, anc.s_noise = guiders.IdentityGuider(), 1.0, 1.0
+    zs = torch.randn(n, 4, 16, generator=g)
+    xv = x0.double() / a_of(ts[0]).sqrt()
+    traj = []
+    for i, tt in enumerate(ts):
+        a = a_of(tt).sqrt()
+        den = lambda xin, sigma, c, a=a: xin - sigma.view(-1, 1) * eps_model((xin * a).float()).double()
+        anc.noise_sampler = lambda xx, i=i: zs[i].double()
+        xv = anc.sampler_step(ones * sig_of(tt), ones * sig_of(tt - step), den, xv, {}, None)
+        traj.append((xv * a_of(tt - step).sqrt()).float())
+    so["ddpm"] = {"x": x0, "n": n, "noise": zs, "traj": torch.stack(traj), "timesteps": d.timesteps.clone()}
+    # DPM-Solver++(2M) with n = 5 < 15 steps: step n-2 stays second order, only the last is first order
+    so["dpm5"] = dpm_golden(sampling, guiders, 5, x0)
+    torch.save(so, os.path.join(OUT, "samplers.pt"))
+
+
+def dpm_golden(sampling, guiders, n, x0):
+    """The reference's `DPMPP2MSampler.sampler_step` (`sampling.py:290-345`) driven over the oracle's sigma table."""
+    s = schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading")
+    s.set_timesteps(n)
+    Wm = toy_eps_matrix()
+    eps_model = lambda v: torch.tanh(v @ Wm)
+    samp = sampling.DPMPP2MSampler.__new__(sampling.DPMPP2MSampler)
+    samp.guider = guiders.IdentityGuider()
+    sig = s.sigmas.double()
+    alpha = 1 / (sig ** 2 + 1).sqrt()
+    xv, old, ones = x0.double() / alpha[0], None, torch.ones(x0.shape[0], dtype=torch.double)
+    traj = []
+    for i in range(n):
+        den = lambda xin, sigma, c, a=alpha[i]: xin - sigma.view(-1, 1) * eps_model((xin * a).float()).double()
+        xv, old = samp.sampler_step(old, None if i == 0 else ones * sig[i - 1], ones * sig[i], ones * sig[i + 1],
+                                    den, xv, {}, None)
+        traj.append((xv * alpha[i + 1]).float())          # back to the VP parameterisation
+    return {"x": x0, "n": n, "traj": torch.stack(traj), "timesteps": s.timesteps.clone(), "sigmas": s.sigmas.clone()}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if "--geometry-only" in sys.argv:
@@ -132,24 +235,9 @@ def main():
 
     # ---- DPM-Solver++(2M): the reference's in-tree sampler on a toy eps model
     guiders = importlib.import_module("sgm.modules.diffusionmodules.guiders")
-    s = schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading")
-    s.set_timesteps(20)
-    Wm = toy_eps_matrix()
-    eps_model = lambda v: torch.tanh(v @ Wm)
     x0 = torch.randn(4, 16, generator=g)
-    samp = sampling.DPMPP2MSampler.__new__(sampling.DPMPP2MSampler)
-    samp.guider = guiders.IdentityGuider()
-    sig = s.sigmas.double()
-    alpha = 1 / (sig ** 2 + 1).sqrt()
-    xv, old, ones = x0.double() / alpha[0], None, torch.ones(4, dtype=torch.double)
-    traj = []
-    for i in range(20):
-        den = lambda xin, sigma, c, a=alpha[i]: xin - sigma.view(-1, 1) * eps_model((xin * a).float()).double()
-        xv, old = samp.sampler_step(old, None if i == 0 else ones * sig[i - 1], ones * sig[i], ones * sig[i + 1],
-                                    den, xv, {}, None)
-        traj.append((xv * alpha[i + 1]).float())          # back to the VP parameterisation
-    torch.save({"x": x0, "traj": torch.stack(traj), "timesteps": s.timesteps.clone(), "sigmas": s.sigmas.clone()},
-               os.path.join(OUT, "dpmpp2m.pt"))
+    torch.save(dpm_golden(sampling, guiders, 20, x0), os.path.join(OUT, "dpmpp2m.pt"))
+    make_block_pins(model, sampling)
 
     # ---- the reference's pipeline loops, driving oracle nets through a names-only diffusers shim
     class _Out:

@@ -181,12 +181,17 @@ class TimestepEmbedding(nn.Module):
         return self.linear_2(F.silu(self.linear_1(x)))
 
 
-def sinusoidal_timestep(t, dim):
-    """diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): cat([cos, sin]) (App. A.1 step 1)."""
+def sinusoidal_timestep(t, dim, flip_sin_to_cos=True, freq_shift=0.0):
+    """diffusers `get_timestep_embedding` as `Timesteps(dim, flip_sin_to_cos=True, freq_shift=0)` calls it:
+    cat([cos, sin]) with divisor `half` (App. A.1 step 1).  With flip_sin_to_cos=False, freq_shift=1 it is the
+    in-tree `get_timestep_embedding` (`vae/sgm/modules/diffusionmodules/model.py:28-46`: cat([sin, cos]), divisor
+    `half - 1`) -- the pin used by tests/test_oracle_cpu.py."""
     half = dim // 2
-    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / (half - 0.0))
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / (half - freq_shift))
     a = t.float()[:, None] * freqs[None]
-    return torch.cat([torch.cos(a), torch.sin(a)], dim=-1)
+    if flip_sin_to_cos:
+        return torch.cat([torch.cos(a), torch.sin(a)], dim=-1)
+    return torch.cat([torch.sin(a), torch.cos(a)], dim=-1)
 
 
 UNET_DEFAULTS = dict(
@@ -241,7 +246,9 @@ class OracleUNet2DModel(nn.Module):
         t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep], dtype=torch.long)
         if t.ndim == 0:
             t = t[None]
-        t = t * torch.ones(B, dtype=t.dtype)
+        if t.device != sample.device:       # (bench.py's GPU library baseline runs these modules on the device)
+            t = torch.full((t.numel(),), int(t[0]), dtype=t.dtype, device=sample.device) if t.numel() == 1 else t.to(sample.device)
+        t = t * torch.ones(B, dtype=t.dtype, device=sample.device)
         emb = self.time_embedding(sinusoidal_timestep(t, self.cfg["block_out_channels"][0]))
         h = self.conv_in(sample)
         skips = (h,)

@@ -13,7 +13,7 @@ import torch
 
 def pos_encoding_like(x):
     """`ldm/pipelines.py:346-349`: zeros(B,1,W,H) with azimuth row w=0 set to one."""
-    pe = torch.zeros([x.shape[0], 1, x.shape[2], x.shape[3]], dtype=x.dtype)
+    pe = torch.zeros([x.shape[0], 1, x.shape[2], x.shape[3]], dtype=x.dtype, device=x.device)
     pe[:, :, 0, :] = 1
     return pe
 

@@ -932,70 +932,70 @@ attention_tc_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __h
 }
 
 // ------------------------------------------------------------------------------------------------
-// time embedding.  temb_mlp: grid B, block 512 (16 warps): sinusoid -> linear_1 -> silu ->
-// linear_2 -> silu, warp-per-output-row dot products.  temb_proj: grid (ceil(T/8), B), block 256.
-__global__ void __launch_bounds__(512)
-temb_mlp_kernel(const float* __restrict__ t, const float* __restrict__ w1,
-                const float* __restrict__ b1, const float* __restrict__ w2,
-                const float* __restrict__ b2, float* __restrict__ scratch, int D0, int D4) {
-  pdl_entry();
-  extern __shared__ float sh_t[];  // e0[D0], h1[D4]
-  float* e0 = sh_t;
-  float* h1 = sh_t + D0;
-  const int b = blockIdx.x;
-  const float tv = t[b];
-  const int half = D0 / 2;
-  for (int i = threadIdx.x; i < half; i += blockDim.x) {
-    const float f = expf(-9.210340371976184f * static_cast<float>(i) / static_cast<float>(half));
-    const float a = tv * f;
-    e0[i] = cosf(a);           // flip_sin_to_cos=True -> [cos, sin]
-    e0[half + i] = sinf(a);
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int r = warp; r < D4; r += nw) {
-    float s = 0.f;
-    for (int c = lane; c < D0; c += 32) s = fmaf(__ldg(w1 + static_cast<size_t>(r) * D0 + c), e0[c], s);
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-      s += b1[r];
-      h1[r] = s / (1.0f + expf(-s));
-    }
-  }
-  __syncthreads();
-  for (int r = warp; r < D4; r += nw) {
-    float s = 0.f;
-    for (int c = lane; c < D4; c += 32) s = fmaf(__ldg(w2 + static_cast<size_t>(r) * D4 + c), h1[c], s);
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-      s += b2[r];
-      scratch[static_cast<size_t>(b) * D4 + r] = s / (1.0f + expf(-s));  // silu(emb), shared by all resnets
-    }
-  }
-}
-
+// time embedding: three launches of ONE small-GEMM kernel over R rows (R = batch for a single forward, R = number of
+// sampling steps when a trajectory evaluates the embedding of its whole timestep table at once):
+//   (1) sinusoid(t) -> linear_1 -> SiLU        K = D0,  N = D4
+//   (2)             -> linear_2 -> SiLU        K = D4,  N = D4      (silu(emb) is what every resnet projects)
+//   (3)             -> all time_emb_proj rows  K = D4,  N = T
+// grid = ceil(N / 8), block 256: warp = one output column n (its weight row lives in registers, K/32 per lane), the
+// R input rows are staged in shared memory in chunks; a dot product is a per-lane FMA chain + one butterfly.  Every
+// weight is read exactly once per launch (9.7 MB for the C3 projections) by ~N/8 CTAs in parallel; the old kernels
+// walked all rows of a matrix with ONE CTA per batch row (84 us for 8 rows).
+constexpr int kTembMaxK = 1024;          // weight row in registers: K/32 <= 32 per lane
+constexpr int kTembRowsChunk = 16;       // input rows staged per pass: 16 x 1024 floats = 64 KB max
 __global__ void __launch_bounds__(256)
-temb_proj_kernel(const float* __restrict__ semb, const float* __restrict__ wp,
-                 const float* __restrict__ bp, float* __restrict__ out, int D4, int T) {
+temb_linear_kernel(const float* __restrict__ in, const float* __restrict__ t, const float* __restrict__ w,
+                   const float* __restrict__ bias, float* __restrict__ out, int R, int K, int N, int silu_out) {
+  extern __shared__ float sh_t[];        // [rows chunk][K]
   pdl_entry();
-  const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (r >= T) return;
-  float s = 0.f;
-  for (int c = lane; c < D4; c += 32)
-    s = fmaf(__ldg(wp + static_cast<size_t>(r) * D4 + c), __ldg(semb + static_cast<size_t>(b) * D4 + c), s);
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) out[static_cast<size_t>(b) * T + r] = s + bp[r];
+  const int n = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int kpl = K >> 5;                // K % 32 == 0 (host)
+  float wr[kTembMaxK / 32];
+#pragma unroll
+  for (int j = 0; j < kTembMaxK / 32; ++j) wr[j] = (j < kpl && n < N) ? __ldg(w + static_cast<size_t>(n) * K + lane + 32 * j) : 0.f;
+  const float bn = (n < N && bias) ? __ldg(bias + n) : 0.f;
+  for (int r0 = 0; r0 < R; r0 += kTembRowsChunk) {
+    const int rows = min(kTembRowsChunk, R - r0);
+    __syncthreads();
+    if (t != nullptr) {                  // sinusoidal embedding of the timestep (flip_sin_to_cos: [cos | sin], divisor half)
+      const int half = K >> 1;
+      for (int i = threadIdx.x; i < rows * half; i += blockDim.x) {
+        const int r = i / half, c = i - r * half;
+        const float f = expf(-9.210340371976184f * static_cast<float>(c) / static_cast<float>(half));
+        const float a = t[r0 + r] * f;
+        sh_t[r * K + c] = cosf(a);
+        sh_t[r * K + half + c] = sinf(a);
+      }
+    } else {
+      for (int i = threadIdx.x; i < rows * K; i += blockDim.x) sh_t[i] = in[static_cast<size_t>(r0) * K + i];
+    }
+    __syncthreads();
+    if (n < N) {
+      for (int r = 0; r < rows; ++r) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < kTembMaxK / 32; ++j)
+          if (j < kpl) s = fmaf(wr[j], sh_t[r * K + lane + 32 * j], s);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+          s += bn;
+          out[static_cast<size_t>(r0 + r) * N + n] = silu_out ? s / (1.0f + expf(-s)) : s;
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // fused scheduler step (float4 vectorised; scalar tail).
 __global__ void __launch_bounds__(256)
-sched_step_kernel(const float* __restrict__ k, const float* __restrict__ x,
-                  const float* __restrict__ eps, const float* __restrict__ x0_prev,
-                  const float* __restrict__ noise, float* __restrict__ x_out,
-                  float* __restrict__ x0_out, int64_t n) {
+sched_step_kernel(const float* __restrict__ k, const float* x,
+                  const float* __restrict__ eps, const float* x0_prev,
+                  const float* __restrict__ noise, float* x_out,
+                  float* x0_out, int64_t n) {
+  // x / x_out and x0_prev / x0_out may alias (the trajectory program updates the latents and the previous x0 in
+  // place: every thread reads its own elements before it writes them), so those four carry no __restrict__
   pdl_entry();
   const float k0 = k[0], k1 = k[1], k2 = k[2], k3 = k[3], k4 = k[4], k5 = k[5], k6 = k[6];
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
@@ -1273,16 +1273,32 @@ extern "C" int rldm_attention(const float* qkv, uint16_t* out, uint16_t* out_lo,
   return 0;
 }
 
+static int temb_linear(const float* in, const float* t, const float* w, const float* b, float* out, int R, int K, int N,
+                       int silu_out, cudaStream_t st) {
+  RLDM_CHECK(K % 32 == 0 && K <= kTembMaxK, "temb: inner dimension %d must be a multiple of 32 and <= %d", K, kTembMaxK);
+  const size_t smem = static_cast<size_t>(kTembRowsChunk) * K * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 44 * 1024 && smem > smem_set) {
+    RLDM_CUDA(cudaFuncSetAttribute(temb_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    smem_set = 64 * 1024;
+  }
+  RLDM_CUDA(launch_pdl(temb_linear_kernel, dim3((N + 7) / 8), dim3(256), smem, st, in, t, w, b, out, R, K, N, silu_out));
+  return 0;
+}
+
 extern "C" int rldm_temb(const float* t, const float* w1, const float* b1, const float* w2,
                          const float* b2, const float* wp, const float* bp, float* scratch,
                          float* out, int B, int D0, int D4, int T, void* stream) {
+  // scratch: [2][B][D4] floats (hidden layer, then silu(emb))
   cudaStream_t st = as_stream(stream);
-  RLDM_CUDA(launch_pdl(temb_mlp_kernel, dim3(B), dim3(512), (D0 + D4) * sizeof(float), st, t, w1, b1, w2, b2, scratch, D0, D4));
+  if (B <= 0) return 0;
+  float* h1 = scratch;
+  float* semb = scratch + static_cast<size_t>(B) * D4;
+  if (int rc = temb_linear(nullptr, t, w1, b1, h1, B, D0, D4, 1, st)) return rc;
+  if (int rc = temb_linear(h1, nullptr, w2, b2, semb, B, D4, D4, 1, st)) return rc;
+  if (T > 0)
+    if (int rc = temb_linear(semb, nullptr, wp, bp, out, B, D4, T, 0, st)) return rc;
   RLDM_LAUNCH_CHECK();
-  if (T > 0) {
-    RLDM_CUDA(launch_pdl(temb_proj_kernel, dim3((T + 7) / 8, B), dim3(256), 0, st, scratch, wp, bp, out, D4, T));
-    RLDM_LAUNCH_CHECK();
-  }
   return 0;
 }
 

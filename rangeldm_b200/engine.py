@@ -441,11 +441,12 @@ class UNetPlan:
         wp = pg.hold(torch.cat([r.weight.detach().float() for r in rows], 0).to(dev).contiguous())
         bp = pg.hold(torch.cat([r.bias.detach().float() for r in rows], 0).to(dev).contiguous())
         te = model.time_embedding
-        scratch = pg.hold(torch.zeros(batch, D4, device=dev))
+        scratch = pg.hold(torch.zeros(2, batch, D4, device=dev))
         temb_out = pg.hold(torch.zeros(batch, T, device=dev))
         pg.add(_lib.OP_TEMB, i=(batch, D0, D4, T),
                p=(self.t_buf, bd.f32(te.linear_1.weight), bd.f32(te.linear_1.bias), bd.f32(te.linear_2.weight),
-                  bd.f32(te.linear_2.bias), wp, bp, scratch, temb_out), launches=2)
+                  bd.f32(te.linear_2.bias), wp, bp, scratch, temb_out), launches=3)
+        self.temb_dims = (D0, D4)
         bd.temb = (temb_out, T)
         self.temb_out, self.temb_T = temb_out, T
 

@@ -160,10 +160,16 @@ class _PlannedModel(ModelMixin, nn.Module):
     def _init_plans(self):
         object.__setattr__(self, "_plans", {})
         object.__setattr__(self, "_packed", {})     # repacked weights shared by all plans of this model
+        object.__setattr__(self, "_plan_version", 0)
 
     def invalidate_plans(self):
+        """Drop every compiled plan and repacked weight copy, and bump `_plan_version` (part of the pipelines'
+        FusedSampler cache key, so a captured trajectory graph is never replayed over stale weights).  Called by
+        `load_state_dict`, `safetensors.torch.load_model`, `.to()` and the surgery helpers; IN-PLACE parameter edits
+        (e.g. EMA `copy_to`) are invisible to it and need an explicit `invalidate_plans()`."""
         self._plans.clear()
         self._packed.clear()
+        object.__setattr__(self, "_plan_version", self._plan_version + 1)
 
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)

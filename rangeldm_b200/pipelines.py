@@ -148,7 +148,6 @@ class _Trajectory:
         pg = self.prog = Program(dev)
         pg.keep += [self.plan, scheduler]
         coef = pg.hold(scheduler.coef_table(dev).clone())
-        ttab = pg.hold(scheduler.timesteps.to(dev, torch.float32)[:, None].expand(self.steps, batch).contiguous())
         n = self.latents.numel()
         x0buf = pg.hold(torch.zeros_like(self.latents))
         host_coef = scheduler._coef_host
@@ -156,20 +155,23 @@ class _Trajectory:
         if bool((host_coef[:, 6] != 0).any()):
             self.noise = pg.hold(torch.zeros((self.steps,) + tuple(self.latents.shape), device=dev))
         uses_prev = bool((host_coef[:, 4] != 0).any())
-        # The time-embedding MLP and all per-resnet projections depend only on the timestep table: evaluate them
-        # for every step ONCE here (same kernel, rldm_temb) and let step i's convs read row i of the table.
+        # The time-embedding MLP and all per-resnet projections depend only on the timestep table: the FIRST op of the
+        # trajectory evaluates them for every step in one batched pass (rldm_temb over `steps` rows, inside the
+        # captured graph and the timed step), and step i's conv epilogues read row i for every image of the batch
+        # (temb_stride 0) -- instead of 20 x (MLP + 22 projections) spread over the loop.
         T = self.plan.temb_T
-        temb_all = pg.hold(torch.zeros(self.steps, batch, T, device=dev))
+        tvec = pg.hold(scheduler.timesteps.to(dev, torch.float32).contiguous())
+        temb_all = pg.hold(torch.zeros(self.steps, T, device=dev))
         temb_base = self.plan.temb_out.data_ptr()
-        if dev.type == "cuda":
-            for i in range(self.steps):
-                for op in self.plan.prog.ops:
-                    if op.kind == _lib.OP_TEMB:
-                        cp = RldmOp.from_buffer_copy(op)
-                        cp.p[0] = ttab[i].data_ptr()
-                        cp.p[8] = temb_all[i].data_ptr()
-                        _lib.check(_lib.lib().rldm_run((RldmOp * 1)(cp), 1, _lib.stream_ptr()))
-            torch.cuda.synchronize()
+        D0, D4 = self.plan.temb_dims
+        temb_scratch = pg.hold(torch.zeros(2, self.steps, D4, device=dev))
+        for op in self.plan.prog.ops:
+            if op.kind == _lib.OP_TEMB:
+                cp = RldmOp.from_buffer_copy(op)
+                cp.i[0] = self.steps
+                cp.p[0], cp.p[7], cp.p[8] = tvec.data_ptr(), temb_scratch.data_ptr(), temb_all.data_ptr()
+                pg.ops.append(cp)
+                pg.n_launch += 3
         for i in range(self.steps):
             for op in self.plan.prog.ops:
                 if op.kind == _lib.OP_TEMB:
@@ -177,8 +179,9 @@ class _Trajectory:
                 cp = RldmOp.from_buffer_copy(op)
                 if cp.kind in (_lib.OP_CONV_TC, _lib.OP_CONV_REF) and cp.p[3]:
                     cp.p[3] = temb_all[i].data_ptr() + (cp.p[3] - temb_base)
+                    cp.i[0] = 0                       # every image of the batch shares the step's row
                 pg.ops.append(cp)
-            pg.n_launch += self.plan.prog.n_launch - 2
+            pg.n_launch += self.plan.prog.n_launch - 3
             noise_i = self.noise[i] if (self.noise is not None and float(host_coef[i, 6]) != 0.0) else None
             pg.add(_lib.OP_SCHED_STEP, p=(coef[i], self.latents, self.plan.out,
                                           x0buf if (uses_prev and i > 0) else None, noise_i, self.latents,
@@ -300,13 +303,39 @@ class _RangePipeline(DiffusionPipeline):
     def _sampler(self, batch, cond_channels, vae):
         """FusedSampler cache: keyed by everything that is baked into the program."""
         sch = self.scheduler
+        ver = lambda m: None if m is None else (id(m), getattr(m, "_plan_version", 0), str(m.device))
         key = (batch, cond_channels, type(sch).__name__, tuple(sch.timesteps.tolist()),
-               tuple(sch._coef_host.flatten().tolist()), id(vae))
+               tuple(sch._coef_host.flatten().tolist()), ver(self.unet), ver(vae))
         cache = self.__dict__.setdefault("_fused", {})
         if key not in cache:
             cache.clear()                     # one live trajectory program per pipeline
             cache[key] = FusedSampler(self.unet, sch, vae, batch, cond_channels)
         return cache[key]
+
+    # A fused trajectory unrolls every step into one program / CUDA graph and, for stochastic schedulers, holds the
+    # per-step noise of the whole trajectory in HBM.  Long ancestral runs (DDPMPipelineRange defaults to 1000 steps
+    # on (B,2,1024,64) pixels: 8.4 GB of noise at B = 16 and several 10^5 graph nodes) take the per-step path, which
+    # needs O(1) extra memory like the reference loop.
+    MAX_UNROLLED_STEPS = 250
+    MAX_UNROLLED_NOISE_BYTES = 1 << 30
+
+    def _fusable(self, steps, numel):
+        if not _is_native_scheduler(self.scheduler) or steps > self.MAX_UNROLLED_STEPS:
+            return False
+        stochastic = bool((self.scheduler._coef_host[:, 6] != 0).any())
+        return not (stochastic and steps * numel * 4 > self.MAX_UNROLLED_NOISE_BYTES)
+
+    def _stepwise(self, latents, cond, generator, extra=None):
+        """The reference's loop body (`ldm/pipelines.py:101-106,234-246,353-362,496-502`) over the module API."""
+        extra = dict(extra or {})
+        if "generator" in set(inspect.signature(self.scheduler.step).parameters.keys()):
+            extra["generator"] = generator
+        for t in self.progress_bar(self.scheduler.timesteps):
+            x = self.scheduler.scale_model_input(latents, t)
+            if cond is not None:
+                x = torch.cat([x, cond], dim=1)
+            latents = self.scheduler.step(self.unet(x, t).sample, t, latents, **extra).prev_sample
+        return latents
 
     def _draw_step_noise(self, sampler, generator, shape, device):
         if sampler.noise is None:
@@ -358,6 +387,8 @@ class DDPMPipelineRange(_RangePipeline):
         shape = (batch_size, self.unet.config.in_channels, W, H)
         image = randn_tensor(shape, generator=generator, device=self.device)
         self._set_steps(num_inference_steps)
+        if not self._fusable(num_inference_steps, image.numel()):
+            return self._finish(self._stepwise(image, None, generator), output_type, return_dict)
         sampler = self._sampler(batch_size, 0, None)
         noise = self._draw_step_noise(sampler, generator, shape, self.device)
         return self._finish(sampler.run(image, None, noise), output_type, return_dict)
@@ -384,8 +415,10 @@ class DDIMPipelineRange(_RangePipeline):
         image = randn_tensor(shape, generator=generator, device=self._execution_device, dtype=self.unet.dtype)
         self._set_steps(num_inference_steps, eta)
         cc = 1 if self.pos_encoding else 0
-        sampler = self._sampler(batch_size, cc, None)
         cond = make_pos_encoding(batch_size, W, H, self.device) if cc else None
+        if not self._fusable(num_inference_steps, image.numel()):
+            return self._finish(self._stepwise(image, cond, generator, {"eta": eta}), output_type, return_dict)
+        sampler = self._sampler(batch_size, cc, None)
         noise = self._draw_step_noise(sampler, generator, shape, self.device)
         return self._finish(sampler.run(image, cond, noise), output_type, return_dict)
 
@@ -409,13 +442,15 @@ class LDMPipelineRange(_RangePipeline):
         self._set_steps(num_inference_steps, eta if accepts_eta else 0.0)
         cc = 1 if self.pos_encoding else 0
         cond = make_pos_encoding(batch_size, W, H, self.device) if cc else None
-        if final_only and _is_native_scheduler(self.scheduler):
+        if final_only and self._fusable(num_inference_steps, latents.numel()):
             sampler = self._sampler(batch_size, cc, self.vae)
             noise = self._draw_step_noise(sampler, generator, shape, self.device)
             return self._finish(sampler.run(latents, cond, noise), output_type, return_dict)
         # step-by-step path (intermediate decodes, or a foreign scheduler object)
         assert final_only or output_type == "torch"
         extra = {"eta": eta} if accepts_eta else {}
+        if "generator" in set(inspect.signature(self.scheduler.step).parameters.keys()):
+            extra["generator"] = generator
         image_list = []
         for t in self.progress_bar(self.scheduler.timesteps):
             if not final_only:
@@ -467,6 +502,9 @@ class LDMUpscalePipelineRange(_RangePipeline):
         latents = latents * self.scheduler.init_noise_sigma
         accepts_eta = "eta" in set(inspect.signature(self.scheduler.step).parameters.keys())
         self._set_steps(num_inference_steps, eta if accepts_eta else 0.0)
+        if not self._fusable(num_inference_steps, latents.numel()):
+            latents = self._stepwise(latents, cond, generator, {"eta": eta} if accepts_eta else {})
+            return self._finish(self.vae.decode(latents / self.vae.config.scaling_factor).sample, output_type, return_dict)
         sampler = self._sampler(batch_size, cond.shape[1], self.vae)
         noise = self._draw_step_noise(sampler, generator, shape, self.unet.device)
         return self._finish(sampler.run(latents, cond, noise), output_type, return_dict)

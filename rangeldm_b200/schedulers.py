@@ -239,12 +239,13 @@ class DPMSolverMultistepScheduler(_SchedulerBase):
         coefs = []
         for i in range(n):
             final = (i == n - 1) and ((c.lower_order_final and n < 15) or c.final_sigmas_type == "zero")
-            second_last = (i == n - 2) and c.lower_order_final and n < 15
             a_s, s_s, a_t, s_t = alpha[i], sigma[i], alpha[i + 1], sigma[i + 1]
             h = lam[i + 1] - lam[i]
             cc = -a_t * math.expm1(-h) if np.isfinite(h) else a_t      # -(alpha_t (e^{-h} - 1))
             k = [1 / a_s, -s_s / a_s, s_t / s_s, cc, 0.0, 0.0, 0.0, 0.0]
-            if not (i == 0 or final or second_last):
+            # solver_order == 2: diffusers' `lower_order_second` only demotes a THIRD-order solver, so step n-2 stays
+            # second order; only the first step and the final step are first order (== in-tree DPMPP2MSampler)
+            if not (i == 0 or final):
                 r0 = (lam[i] - lam[i - 1]) / h
                 k[3] = cc * (1 + 0.5 / r0)
                 k[4] = -cc * 0.5 / r0

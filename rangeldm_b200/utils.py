@@ -17,9 +17,11 @@ class attn_identity(torch.nn.Identity):
 
 
 def replace_conv(module, name="Conv2d"):
-    """Mark every convolution under `module` horizontally circular (`ldm/utils.py:125-146`)."""
+    """Mark every convolution under `module` horizontally circular (`ldm/utils.py:125-146`).  Like the reference --
+    which swaps conv-typed ATTRIBUTES and children of the module it is given -- a bare convolution passed as the root
+    is left alone: `replace_conv(model.conv_in)` in the `sub_circonv` path (`ldm/inference.py:110-119`) is a no-op."""
     for m in module.modules():
-        if isinstance(m, torch.nn.Conv2d):
+        if isinstance(m, torch.nn.Conv2d) and m is not module:
             m.circular = True
     if hasattr(module, "invalidate_plans"):
         module.invalidate_plans()

@@ -135,7 +135,11 @@ def test_dry_run_plans_and_fused_program_launch_counts(monkeypatch):
     for part in fs.parts:
         n_sched = sum(1 for op in part.prog.ops if op.kind == _lib.OP_SCHED_STEP)
         assert n_sched == 20 and part.image.shape == (4, 2, 1024, 64)
-        assert not any(op.kind == _lib.OP_TEMB for op in part.prog.ops)           # time embedding precomputed
+        # the time embedding of the whole timestep table is ONE op at the head of the (timed, graph-captured) program
+        assert [k for k, op in enumerate(part.prog.ops) if op.kind == _lib.OP_TEMB] == [0]
+        assert part.prog.ops[0].i[0] == 20
+        convs_with_temb = [op for op in part.prog.ops if op.kind == _lib.OP_CONV_TC and op.p[3]]
+        assert len(convs_with_temb) == 20 * 22 and all(op.i[0] == 0 for op in convs_with_temb)
     assert fs.parts[0].plan is not fs.parts[1].plan                               # own activation buffers ...
     assert len(u._packed) > 0 and len(fs.parts[0].plan.prog.ops) == len(plan.prog.ops)   # ... shared weights
     with pytest.raises(RuntimeError, match="no CPU fallback"):
@@ -144,6 +148,38 @@ def test_dry_run_plans_and_fused_program_launch_counts(monkeypatch):
                          up_block_types=["UpDecoderBlock2D"], block_out_channels=[64])
     with pytest.raises(NotImplementedError):
         v2.decoder_plan(1, 16, 8)                    # learned quant convs are not implemented
+
+
+def test_sampler_cache_follows_weight_reloads_and_surgery(monkeypatch):
+    """a cached FusedSampler must not outlive `load_state_dict` / `.to()` / surgery of its models."""
+    monkeypatch.setenv("RLDM_DRYRUN", "1")
+    import rangeldm_b200 as R
+    from oracle.make_golden import TINY_UNET
+    u = R.UNet2DModel(**TINY_UNET)
+    R.replace_down(u); R.replace_conv(u)
+    sch = R.DDIMScheduler(clip_sample=False)
+    pipe = R.DDIMPipelineRange(u, sch, pos_encoding=True)
+    pipe.scheduler.set_timesteps(3)
+    monkeypatch.setattr(R.pipelines.FusedSampler, "_capture", lambda self: None)
+    a = pipe._sampler(2, 1, None)
+    assert pipe._sampler(2, 1, None) is a
+    v0 = u._plan_version
+    u.load_state_dict(u.state_dict())
+    assert u._plan_version > v0
+    b = pipe._sampler(2, 1, None)
+    assert b is not a and pipe._sampler(2, 1, None) is b
+    R.replace_conv(u)
+    assert pipe._sampler(2, 1, None) is not b
+    # replace_conv on a bare convolution is a no-op, like the reference's (`ldm/utils.py:125-146`)
+    c = R.UNet2DModel(**TINY_UNET).conv_in
+    R.replace_conv(c)
+    assert not c.circular
+    # long ancestral trajectories do not unroll (O(1) extra memory like the reference loop)
+    ddpm = R.DDPMPipelineRange(u, R.DDPMScheduler(clip_sample=False))
+    ddpm.scheduler.set_timesteps(1000)
+    assert not ddpm._fusable(1000, 16 * 2 * 1024 * 64)
+    ddpm.scheduler.set_timesteps(50)
+    assert ddpm._fusable(50, 2 * 2 * 1024 * 64)
 
 
 def test_scheduler_tables_bit_exact_with_oracle():
@@ -163,23 +199,54 @@ def test_scheduler_tables_bit_exact_with_oracle():
 
 
 def test_dpm_coefficient_table_reproduces_oracle_update_on_cpu():
-    """The 7-coefficient affine form the fused step kernel evaluates == the oracle's DPM-Solver++ update."""
+    """The 7-coefficient affine form the fused step kernel evaluates == the oracle's DPM-Solver++ update, for the
+    20-step benchmark table and for n < 15 (where only the FINAL step is first order)."""
     import rangeldm_b200 as R
     from oracle import schedulers as O
-    a = R.DPMSolverMultistepScheduler(timestep_spacing="leading")
-    b = O.OracleDPMSolverMultistepScheduler(timestep_spacing="leading")
-    a.set_timesteps(20); b.set_timesteps(20)
-    g = torch.Generator().manual_seed(0)
-    x = torch.randn(64, generator=g)
-    xa, xb, prev = x.clone(), x.clone(), torch.zeros(64)
-    for i, t in enumerate(b.timesteps):
-        eps = torch.randn(64, generator=g)
-        k = a._coef_host[i]
-        x0 = k[0] * xa + k[1] * eps
-        xa = k[2] * xa + k[3] * x0 + k[4] * prev + k[5] * eps
-        prev = x0
-        xb = b.step(eps, t, xb)
-        assert torch.allclose(xa, xb, rtol=2e-5, atol=2e-5), i
+    for n in (20, 5, 3, 14):
+        a = R.DPMSolverMultistepScheduler(timestep_spacing="leading")
+        b = O.OracleDPMSolverMultistepScheduler(timestep_spacing="leading")
+        a.set_timesteps(n); b.set_timesteps(n)
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn(64, generator=g)
+        xa, xb, prev = x.clone(), x.clone(), torch.zeros(64)
+        for i, t in enumerate(b.timesteps):
+            eps = torch.randn(64, generator=g)
+            k = a._coef_host[i]
+            x0 = k[0] * xa + k[1] * eps
+            xa = k[2] * xa + k[3] * x0 + k[4] * prev + k[5] * eps
+            prev = x0
+            xb = b.step(eps, t, xb)
+            assert torch.allclose(xa, xb, rtol=2e-5, atol=2e-5), (n, i)
+        # second-order everywhere except the first and the last step
+        assert [bool(k[4] != 0) for k in a._coef_host] == [False] + [True] * (n - 2) + [False]
+
+
+def test_scheduler_coefficient_tables_reproduce_reference_sampler_goldens(golden):
+    """The PRODUCT's host coefficient tables (what `rldm_sched_step` evaluates) against trajectories of the reference's
+    own samplers (`vae/sgm/modules/diffusionmodules/sampling.py`: DPMPP2MSampler n=5 and n=20, EulerEDMSampler == DDIM,
+    EulerAncestralSampler == DDPM; fixtures made by oracle/make_golden.py)."""
+    import rangeldm_b200 as R
+    from oracle.make_golden import toy_eps_matrix
+    Wm = toy_eps_matrix()
+    sam = golden("samplers.pt")
+    cases = [(R.DPMSolverMultistepScheduler(timestep_spacing="leading"), sam["dpm5"], None),
+             (R.DPMSolverMultistepScheduler(timestep_spacing="leading"), golden("dpmpp2m.pt"), None),
+             (R.DDIMScheduler(clip_sample=False), sam["ddim"], None),
+             (R.DDPMScheduler(clip_sample=False), sam["ddpm"], sam["ddpm"]["noise"])]
+    for sch, g, noise in cases:
+        n = g["traj"].shape[0]
+        sch.set_timesteps(n)
+        assert torch.equal(sch.timesteps, g["timesteps"])
+        x, prev = g["x"].clone(), torch.zeros_like(g["x"])
+        for i in range(n):
+            eps = torch.tanh(x @ Wm)
+            k = sch._coef_host[i]
+            x0 = k[0] * x + k[1] * eps
+            x = k[2] * x + k[3] * x0 + k[4] * prev + k[5] * eps + (k[6] * noise[i] if noise is not None else 0)
+            prev = x0
+            e = ((x - g["traj"][i]).abs().max() / g["traj"][i].abs().max()).item()
+            assert e < 2e-5, (type(sch).__name__, n, i, e)
 
 
 def test_sparse_encoder2_golden(golden):

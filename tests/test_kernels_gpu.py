@@ -333,17 +333,20 @@ def test_attention_core(L, shape, kernel, monkeypatch):
     assert relerr((out.float() + out_lo.float()).cpu(), y) < 1e-5
 
 
-def test_time_embedding(L):
+@pytest.mark.parametrize("rows", [3, 20, 37])
+def test_time_embedding(L, rows):
+    """rows = the batch of one forward, or the timestep table of a trajectory (one row per sampling step); 37 rows
+    exercise more than two shared-memory row chunks."""
     from oracle import nets
     torch.manual_seed(0)
-    B, D0, D4 = 3, 128, 512
+    B, D0, D4 = rows, 128, 512
     te = nets.TimestepEmbedding(D0, D4)
-    projs = [torch.nn.Linear(D4, c) for c in (128, 256, 128)]
-    t = torch.tensor([999.0, 47.0, 0.0])
+    projs = [torch.nn.Linear(D4, c) for c in (128, 256, 128, 4)]       # T = 516: a ragged last block of output rows
+    t = torch.tensor([999.0, 47.0, 0.0] + [float(940 - 23 * i) for i in range(rows - 3)])
     wp = torch.cat([p.weight for p in projs]).detach()
     bp = torch.cat([p.bias for p in projs]).detach()
     T = wp.shape[0]
-    scratch = torch.empty(B, D4, device="cuda")
+    scratch = torch.empty(2, B, D4, device="cuda")
     out = torch.empty(B, T, device="cuda")
     dv = [x.detach().cuda().contiguous() for x in (t, te.linear_1.weight, te.linear_1.bias, te.linear_2.weight,
                                                    te.linear_2.bias, wp, bp)]
@@ -351,7 +354,7 @@ def test_time_embedding(L):
     with torch.no_grad():
         emb = te(nets.sinusoidal_timestep(t, D0))
         y = torch.cat([p(F.silu(emb)) for p in projs], dim=1)
-    assert relerr(out.cpu(), y) < 2e-5
+    assert relerr(out.cpu(), y, f"temb_rows{rows}") < 2e-5
 
 
 def test_conv_in_and_conv_out(L):

@@ -159,6 +159,168 @@ def test_ddpm_stochastic_pipeline_matches_oracle_with_injected_noise(tiny):
     assert relerr(img, ref, "ddpm_pipeline") < TOL
 
 
+def test_ddpm_pixel_pipeline_matches_reference_loop_with_injected_noise(tiny):
+    """`DDPMPipelineRange.__call__` (`ldm/pipelines.py:34-117`): pixel-space ancestral sampling, NO pos-encoding
+    (image channels == unet.in_channels), scheduler.step(..., generator=generator) draws in loop order.  Fused
+    trajectory graph and the per-step fallback (long trajectories) against the oracle loop on the same noise stream."""
+    import rangeldm_b200 as R
+    from oracle import nets, schedulers
+    from oracle.make_golden import TINY_UNET, seeded
+    cfg = dict(TINY_UNET, in_channels=2, out_channels=2)
+    ou = seeded(nets.OracleUNet2DModel, 91, **cfg)
+    u = make_unet(cfg, ou)
+    n = 6
+    pipe = R.DDPMPipelineRange(u, R.DDPMScheduler(clip_sample=False))
+    with pytest.raises(TypeError):
+        R.DDPMPipelineRange(u, R.DDPMScheduler(clip_sample=False), pos_encoding=True)   # like the reference's __init__
+    img = pipe(batch_size=2, generator=torch.Generator().manual_seed(33), num_inference_steps=n, output_type="torch")
+    gen = torch.Generator().manual_seed(33)
+    x = torch.randn((2, 2, 32, 8), generator=gen)
+    osch = schedulers.OracleDDPMScheduler()
+    osch.set_timesteps(n)
+    with torch.no_grad():
+        for t in osch.timesteps:
+            eps = ou(x, t)
+            z = torch.randn((2, 2, 32, 8), generator=gen) if int(t) > 0 else None
+            x = osch.step(eps, t, x, variance_noise=z)
+    assert relerr(img, x, "ddpm_pixel_pipeline") < TOL
+    # per-step path (what 1000-step runs take): same stream, same result
+    pipe.MAX_UNROLLED_STEPS = 1
+    img2 = pipe(batch_size=2, generator=torch.Generator().manual_seed(33), num_inference_steps=n, output_type="torch")
+    assert relerr(img2, x, "ddpm_pixel_pipeline_stepwise") < TOL
+    out = pipe(batch_size=1, generator=torch.Generator().manual_seed(1), num_inference_steps=2, output_type="numpy")
+    assert out.images.shape == (1, 32, 8, 2) and out.images.min() >= 0 and out.images.max() <= 1
+
+
+def test_upscale_pipeline_inpainting_mask_branch_matches_oracle(tiny):
+    """`LDMUpscalePipelineRange` with `mask=` (`ldm/pipelines.py:406-412`, `ldm/inference_conditional.py:137-152`):
+    condition = vae.encode(masked image).latent_dist.sample() * scaling_factor ++ nearest-resized mask (5 channels,
+    UNet in_channels 9).  The posterior sample draws on the device default generator: re-seeding it reproduces the draw."""
+    import rangeldm_b200 as R
+    from oracle import nets, pipeline, schedulers
+    from oracle.make_golden import TINY_UNET, seeded
+    cfg = dict(TINY_UNET, in_channels=9)
+    ou = seeded(nets.OracleUNet2DModel, 78, **cfg)
+    u = make_unet(cfg, ou)
+    pipe = R.LDMUpscalePipelineRange(tiny["v"], u, R.DPMSolverMultistepScheduler(timestep_spacing="leading"))
+    g = torch.Generator().manual_seed(12)
+    masked = torch.randn(2, 2, 64, 16, generator=g).clamp(-1, 1)          # tiny VAE: 2x down -> (2,4,32,8)
+    mask = (torch.rand(2, 1, 64, 16, generator=g) > 0.4).float()
+    masked = masked * mask
+    torch.cuda.manual_seed(555)
+    img = pipe(image=masked, mask=mask, batch_size=2, num_inference_steps=4, generator=torch.Generator().manual_seed(2))
+    torch.cuda.manual_seed(555)
+    enc_noise = torch.randn((2, 4, 32, 8), device="cuda", dtype=torch.float32).cpu()    # the same device draw
+    noise = torch.randn((2, 4, 32, 8), generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        lat = tiny["ov"].encode_sample(masked, enc_noise) * tiny["ov"].scaling_factor
+        cond = torch.cat([lat, torch.nn.functional.interpolate(mask, size=lat.shape[-2:])], dim=1)
+        # the condition itself (our VAE encoder + DiagonalGaussianDistribution + nearest resize)
+        torch.cuda.manual_seed(555)
+        ours = pipe.encode_masked_image(masked, mask)
+        assert ours.shape == (2, 5, 32, 8)
+        assert relerr(ours, cond, "inpainting_condition") < TOL
+        ref = pipeline.upscale_sample(ou, tiny["ov"], schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading"),
+                                      noise, cond, 4)
+    assert relerr(img, ref, "upscale_pipeline_inpainting") < TOL
+    with pytest.raises(AssertionError):          # channel contract of `ldm/pipelines.py:480`
+        R.LDMUpscalePipelineRange(tiny["v"], tiny["u"], R.DDIMScheduler(clip_sample=False))(
+            image=masked, mask=mask, batch_size=2, num_inference_steps=2)
+
+
+def _trajectory_with_latents(u, v, noise, cond, steps):
+    """Our per-step module API (unet(x, t).sample, scheduler.step) collecting every intermediate latent, plus the
+    fused one-graph pipeline image for the same noise."""
+    import rangeldm_b200 as R
+    sch = R.DPMSolverMultistepScheduler(timestep_spacing="leading")
+    sch.set_timesteps(steps)
+    lat = noise.cuda()
+    lats = []
+    for t in sch.timesteps:
+        eps = u(torch.cat([lat, cond.cuda()], dim=1), t).sample
+        lat = sch.step(eps, t, lat).prev_sample
+        lats.append(lat.cpu())
+    return lats
+
+
+def test_c3_trajectory_batch_8_every_intermediate_latent():
+    """SURVEY 8(d) parity protocol at the BENCH shape: C3, per-GPU batch 8, 20-step DPM-Solver++: EVERY intermediate
+    latent of the per-step path and the final image of the fused graph against `oracle.pipeline.ldm_sample`."""
+    import rangeldm_b200 as R
+    from oracle import nets, pipeline, schedulers
+    from oracle.make_golden import seeded
+    ou = seeded(nets.OracleUNet2DModel, 0, **nets.UNET_C3)
+    ov = seeded(nets.OracleAutoencoderKL, 1)
+    u, v = make_unet(nets.UNET_C3, ou), make_vae(ov, [64, 128, 256], 2)
+    B = 8
+    noise = torch.randn((B, 4, 256, 16), generator=torch.Generator().manual_seed(7))
+    ref, traj = pipeline.ldm_sample(ou, ov, schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading"),
+                                    noise, 20, return_latents=True)
+    lats = _trajectory_with_latents(u, v, noise, pipeline.pos_encoding_like(noise), 20)
+    worst = max(relerr(a, b) for a, b in zip(lats, traj))
+    relerr(lats[-1], traj[-1], "c3_b8_final_latent")
+    assert worst < TOL, worst
+    pipe = R.LDMPipelineRange(v, u, R.DPMSolverMultistepScheduler(timestep_spacing="leading"), pos_encoding=True)
+    img = pipe(batch_size=B, generator=torch.Generator().manual_seed(7), num_inference_steps=20)
+    assert img.shape == (B, 2, 1024, 64)
+    assert relerr(img, ref, "c3_trajectory_batch8_fused_image") < TOL
+    import json, os
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity.jsonl"), "a") as f:
+        f.write(json.dumps({"name": "c3_b8_worst_intermediate_latent", "relerr": worst}) + "\n")
+
+
+def test_c4_nuscenes_trajectory_batch_16():
+    """BASELINE configs[3] at its per-GPU batch: nuScenes latent 4x256x8, 20-step DPM-Solver++, decode to (16,2,1024,32)."""
+    import rangeldm_b200 as R
+    from oracle import nets, pipeline, schedulers
+    from oracle.make_golden import seeded
+    ou = seeded(nets.OracleUNet2DModel, 3, **nets.UNET_C4)
+    ov = seeded(nets.OracleAutoencoderKL, 2)
+    u, v = make_unet(nets.UNET_C4, ou), make_vae(ov, [64, 128, 256], 2)
+    pipe = R.LDMPipelineRange(v, u, R.DPMSolverMultistepScheduler(timestep_spacing="leading"), pos_encoding=True)
+    img = pipe(batch_size=16, generator=torch.Generator().manual_seed(4), num_inference_steps=20)
+    noise = torch.randn((16, 4, 256, 8), generator=torch.Generator().manual_seed(4))
+    ref = pipeline.ldm_sample(ou, ov, schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading"), noise, 20)
+    assert img.shape == (16, 2, 1024, 32)
+    assert relerr(img, ref, "c4_trajectory_batch16") < TOL
+
+
+def test_c5_conditional_trajectory_batch_4():
+    """BASELINE configs[4] at its per-GPU batch: sparse 16-beam condition -> SparseRangeImageEncoder2 (8 channels),
+    12-channel UNet, 20-step DPM-Solver++, KITTI decode (`ldm/inference_conditional.py:125-170`)."""
+    import rangeldm_b200 as R
+    from oracle import nets, pipeline, schedulers
+    from oracle.make_golden import seeded
+    ou = seeded(nets.OracleUNet2DModel, 5, **nets.UNET_C5)
+    ov = seeded(nets.OracleAutoencoderKL, 1)
+    u, v = make_unet(nets.UNET_C5, ou), make_vae(ov, [64, 128, 256], 2)
+    pipe = R.LDMUpscalePipelineRange(v, u, R.DPMSolverMultistepScheduler(timestep_spacing="leading"))
+    sparse = torch.randn(4, 2, 1024, 16, generator=torch.Generator().manual_seed(8)).clamp(-1, 1)
+    img = pipe(image=sparse.cuda(), condition_encoder=R.SparseRangeImageEncoder2(), batch_size=4,
+               num_inference_steps=20, generator=torch.Generator().manual_seed(6))
+    noise = torch.randn((4, 4, 256, 16), generator=torch.Generator().manual_seed(6))
+    ref = pipeline.upscale_sample(ou, ov, schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading"),
+                                  noise, pipeline.sparse_encoder2(sparse), 20)
+    assert img.shape == (4, 2, 1024, 64)
+    assert relerr(img, ref, "c5_trajectory_batch4") < TOL
+
+
+def test_c2_pixel_ddim_trajectory_10_steps_full_size():
+    """BASELINE configs[1]: RangeDM pixel UNet (113.67 M params) on 2(+1)x1024x64, DDIM, batch 1 -- a 10-step
+    seed-matched trajectory through `DDIMPipelineRange` (the 50-step run is the same loop; 10 keeps the CPU oracle
+    at ~5 TFLOP)."""
+    import rangeldm_b200 as R
+    from oracle import nets, pipeline, schedulers
+    from oracle.make_golden import seeded
+    ou = seeded(nets.OracleUNet2DModel, 0, **nets.UNET_C2)
+    u = make_unet(nets.UNET_C2, ou)
+    pipe = R.DDIMPipelineRange(u, R.DDPMScheduler(clip_sample=False), pos_encoding=True)
+    img = pipe(batch_size=1, generator=torch.Generator().manual_seed(11), num_inference_steps=10, output_type="torch")
+    noise = torch.randn((1, 2, 1024, 64), generator=torch.Generator().manual_seed(11))
+    ref = pipeline.pixel_sample(ou, schedulers.OracleDDIMScheduler(), noise, 10, pos_encoding=True)
+    assert relerr(img, ref, "c2_pixel_ddim_10step") < TOL
+
+
 def test_c3_unet_full_size_one_forward():
     """BASELINE config C3 UNet (30.14 M params) on a (2,5,256,16) input against the fp32 oracle."""
     from oracle import nets

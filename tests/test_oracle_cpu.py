@@ -55,6 +55,81 @@ def test_dpmpp2m_matches_reference_sampler_golden(golden):
         assert relerr(x, g["traj"][i]) < 5e-6, i
 
 
+def test_dpmpp2m_fewer_than_15_steps_matches_reference_sampler_golden(golden):
+    """n = 5 < 15: with solver_order 2 diffusers keeps step n-2 SECOND order (`lower_order_second` only demotes a
+    third-order solver) and makes only the final step first order -- what the in-tree DPMPP2MSampler does."""
+    g = golden("samplers.pt")["dpm5"]
+    s = schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading")
+    s.set_timesteps(5)
+    assert torch.equal(s.timesteps, g["timesteps"]) and torch.equal(s.sigmas, g["sigmas"])
+    Wm = toy_eps_matrix()
+    x = g["x"].clone()
+    for i, t in enumerate(s.timesteps):
+        x = s.step(torch.tanh(x @ Wm), t, x)
+        assert relerr(x, g["traj"][i]) < 5e-6, i
+
+
+def test_ddim_step_matches_reference_euler_sampler_golden(golden):
+    """DDIM(eta=0) == the Euler step of the probability-flow ODE: pinned to the reference's `EulerEDMSampler`
+    (`vae/sgm/modules/diffusionmodules/sampling.py:88-134`) through x_VE = x / sqrt(alphas_cumprod)."""
+    g = golden("samplers.pt")["ddim"]
+    d = schedulers.OracleDDIMScheduler()
+    d.set_timesteps(g["n"])
+    assert torch.equal(d.timesteps, g["timesteps"])
+    Wm = toy_eps_matrix()
+    x = g["x"].clone()
+    for i, t in enumerate(d.timesteps):
+        x = d.step(torch.tanh(x @ Wm), t, x)
+        assert relerr(x, g["traj"][i]) < 5e-6, i
+
+
+def test_ddpm_step_matches_reference_ancestral_sampler_golden(golden):
+    """DDPM ancestral step (posterior mean + fixed_small variance) == `EulerAncestralSampler` with eta = 1
+    (`sampling.py:136-155,240-247`, `sampling_utils.py:27-37`) on the same unit noise."""
+    g = golden("samplers.pt")["ddpm"]
+    d = schedulers.OracleDDPMScheduler()
+    d.set_timesteps(g["n"])
+    Wm = toy_eps_matrix()
+    x = g["x"].clone()
+    for i, t in enumerate(d.timesteps):
+        x = d.step(torch.tanh(x @ Wm), t, x, variance_noise=g["noise"][i])
+        assert relerr(x, g["traj"][i]) < 5e-6, i
+
+
+def test_resnet_block_with_temb_matches_reference_golden(golden):
+    """oracle ResnetBlock2D WITH the time-embedding projection == sgm `ResnetBlock(temb_channels=512)`
+    (`vae/sgm/modules/diffusionmodules/model.py:301-362`), with and without the 1x1 shortcut."""
+    g = golden("unet_blocks.pt")
+    for name in ("res_sc", "res_id"):
+        d = g[name]
+        rb = seeded(nets.ResnetBlock2D, d["seed"], cin=d["cin"], cout=d["cout"], temb_ch=512, eps=1e-6)
+        with torch.no_grad():
+            assert relerr(rb(d["x"], d["temb"]), d["y"]) < 5e-6, name
+
+
+def test_attention_single_head_matches_reference_attn_block_golden(golden):
+    """oracle Attention (GN -> q,k,v -> softmax(QK^T/sqrt(d))V -> out + residual) with one head of dim C == sgm
+    `AttnBlock` (`model.py:372-412`)."""
+    d = golden("unet_blocks.pt")["attn"]
+    at = seeded(nets.Attention, d["seed"], ch=64, head_dim=64, eps=1e-6)
+    with torch.no_grad():
+        assert relerr(at(d["x"]), d["y"]) < 5e-6
+
+
+def test_timestep_embedding_matches_reference_golden(golden):
+    """`sinusoidal_timestep` == sgm `get_timestep_embedding` (`model.py:28-46`) under (flip_sin_to_cos=False,
+    freq_shift=1); the UNet2DModel flavour differs only by those two documented knobs (cos first, divisor half)."""
+    d = golden("unet_blocks.pt")["temb"]
+    y = nets.sinusoidal_timestep(d["t"], 128, flip_sin_to_cos=False, freq_shift=1)
+    # arguments reach 999 rad, where one fp32 ulp is 6e-5: the two orders of forming `t * exp(-ln(1e4) i / d)` differ by that
+    assert relerr(y, d["y"]) < 1e-4
+    u = nets.sinusoidal_timestep(d["t"], 128)
+    half = 64
+    f = torch.exp(-np.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    a = d["t"].float()[:, None] * f[None]
+    assert torch.allclose(u[:, :half], torch.cos(a), atol=1e-6) and torch.allclose(u[:, half:], torch.sin(a), atol=1e-6)
+
+
 def test_scheduler_timestep_tables():
     # SURVEY.md App. A.4
     d = schedulers.OracleDDIMScheduler(); d.set_timesteps(50)
