@@ -32,6 +32,8 @@ extern "C" {
 
 int rldm_version(void);
 const char* rldm_last_error(void);
+/* The RLDM_* environment switches are read once at first use; this re-reads them. */
+void rldm_reload_env(void);
 
 /* ---- GroupNorm statistics ------------------------------------------------------------------
  * Replaces the reduction half of F.group_norm in ResnetBlock2D.norm1/norm2, Attention.group_norm,
@@ -104,17 +106,16 @@ int rldm_conv_tc_shortcut(const uint16_t* x, const uint16_t* x_lo, const uint16_
                           const uint16_t* sc_x, const uint16_t* sc_x_lo, const uint16_t* sc_wgt, int sc_cin,
                           void* stream);
 
-/* rldm_conv_tc_shortcut with a caller-owned split-K workspace: when the K loop is split over a cluster, the partial
- * tiles are exchanged through `splitk_ws` (global memory, stays in L2; needs tiles * split * 128 * min(Cout,128) * 4
- * bytes, 16 B aligned; 12 MB covers every automatic split) instead of distributed shared memory, whose ~20 B/clk per
- * SM makes an 8-way reduction cost ~3000 cycles.  Same fixed summation order (bit-identical results).  NULL or too
- * small: the DSMEM path.  (Measured on B200 the L2 round trip is slower than DSMEM for the C3 shapes -- 2.33 vs 2.25 ms
- * per UNet forward -- so the engine does not pass a workspace by default; RLDM_SPLITK_VIA_L2=1 opts in.)  One workspace per stream (launches that share it must be stream-ordered). */
-int rldm_conv_tc_ws(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias, const float* temb,
+/* rldm_conv_tc_shortcut with an explicit operand precision (`terms`; the engine chooses it per layer):
+ *   3: split-fp16 x3 -- x + x_lo and two weight planes [hi|lo]: Xh*Wh + Xl*Wh + Xh*Wl (~22-bit operands);
+ *   2: activations single fp16 (x_lo ignored), two weight planes: Xh*Wh + Xh*Wl -- no low-order activation plane is
+ *      written or read (half the activation operand bytes), the weights keep ~22 bits;
+ *   1: plain fp16, one weight plane;
+ *   0: infer from x_lo (3 when given, else 1), like rldm_conv_tc / rldm_conv_tc_shortcut. */
+int rldm_conv_tc_ex(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias, const float* temb,
                     int temb_stride, const float* residual, float* out, int B, int W, int H, int Cin, int Cout, int ks,
                     int stride, int pad_lo, int circular, int split_k, double* stats, const uint16_t* sc_x,
-                    const uint16_t* sc_x_lo, const uint16_t* sc_wgt, int sc_cin, float* splitk_ws,
-                    long long splitk_ws_bytes, void* stream);
+                    const uint16_t* sc_x_lo, const uint16_t* sc_wgt, int sc_cin, int terms, void* stream);
 
 /* CUDA-core restatement of rldm_conv_tc with the identical contract (split_k ignored); used by the
  * GPU tests to isolate tensor-core descriptor bugs from precision, never by the product path. */

@@ -26,6 +26,7 @@ class RldmOp(ctypes.Structure):
 SIGNATURES = {
     "rldm_version": (c_int, []),
     "rldm_last_error": (ctypes.c_char_p, []),
+    "rldm_reload_env": (None, []),
     "rldm_gn_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rldm_prep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int,
                           c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -33,8 +34,8 @@ SIGNATURES = {
                      + [c_int] * 10 + [c_void_p, c_void_p]),
     "rldm_conv_tc_shortcut": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
                               + [c_int] * 10 + [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
-    "rldm_conv_tc_ws": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
-                        + [c_int] * 10 + [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_i64, c_void_p]),
+    "rldm_conv_tc_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+                        + [c_int] * 10 + [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "rldm_conv_ref": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
                       + [c_int] * 9 + [c_void_p]),
     "rldm_conv_in": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 5

@@ -4,27 +4,16 @@
 // UNet2DModel (call sites `ldm/pipelines.py:239,360`): token grids are short-H x long-W
 // (1024 tokens at 128x8, 256 at 64x4), heads are only 8 wide.
 //
-// One CTA = 128 queries of one (image, head); keys are walked in tiles of 128.
+// A work item = 128 queries of one (image, head); see attention_umma_pipelined_kernel below for the pipeline.
 //   * S = Q K^T: head_dim 8 is padded to a K=32 contraction that carries the split-fp16 terms
 //         A row = [q_hi | q_lo | q_hi | 0],  B row = [k_hi | k_hi | k_lo | 0]   (q pre-scaled by log2(e)/sqrt(8))
-//     -> q_hi.k_hi + q_lo.k_hi + q_hi.k_lo in two tcgen05.mma (M=128, N=128, K=16) into one of three 128-column
-//     TMEM buffers.
-//   * four softmax warps (thread = query row = TMEM lane) take the key tiles one after the other: two cheap passes
-//     over the TMEM row (tcgen05.ld moves a 32-column chunk in a few dozen cycles): row max, then P = exp2(S - max)
-//     (16 K MUFU.EX2 per tile: the bound of this kernel), row sum, and P goes BACK INTO THE SAME TMEM COLUMNS as a
-//     split-fp16 pair with tcgen05.st (chunk c of 32 scores becomes 16 columns of P_hi and 16 of P_lo, two keys per
-//     32-bit column) -- P never touches shared memory.  Every key tile keeps its OWN (max, sum) and its own output
-//     slot, so there is no running rescale.
-//   * O_j = P_hi [V_hi | V_lo] + P_lo [V_hi | V_lo]: the A operand comes from TMEM, the B operand (V^T, hi and lo
-//     halves side by side: N = 16) from shared memory; 16 tcgen05.mma (M=128, N=16, K=16) per key tile -> TMEM slot j.
-//   * the tail combines the tiles: O = sum_j 2^(m_j - m) (O_j[:8] + O_j[8:]) / sum_j 2^(m_j - m) l_j and writes the
-//     split-fp16 operand of the to_out projection (W-padded layout of rldm_conv_tc).
-// Inside one CTA the chain Q K^T -> softmax -> P V is serial (one S/P buffer); TWO CTAs share an SM (256 threads,
-// <= 128 registers, ~85 KB shared memory, 256 TMEM columns each), so one CTA's exponentials overlap the other's MMAs,
-// loads, prologue and tail.
-// Warp roles: 0-3 softmax, 4 MMA issuer + TMEM owner, 5-7 loaders (fp32 q/k/v -> split fp16 -> SWIZZLE_128B shared
-// memory; loader w owns ring slot w and the tiles t = w mod 3).
-// TMEM: columns [0,128) = S/P buffer, [128,256) = eight 16-column output slots (N <= 1024).
+//     -> q_hi.k_hi + q_lo.k_hi + q_hi.k_lo in two tcgen05.mma (K=16 each) into a TMEM score buffer.
+//   * softmax warps (thread = query row = TMEM lane): row max, P = exp2(S - max), and P goes BACK INTO THE SAME TMEM
+//     COLUMNS as a split-fp16 pair with tcgen05.st (a chunk of 32 scores becomes 16 columns of P_hi and 16 of P_lo, two
+//     keys per 32-bit column) -- P never touches shared memory.
+//   * O = P_hi [V_hi | V_lo] + P_lo [V_hi | V_lo]: the A operand comes from TMEM (TS form of tcgen05.mma), the B
+//     operand (V^T, hi and lo halves side by side) from shared memory.
+//   * the result is written as the split-fp16 operand of the to_out projection (W-padded layout of rldm_conv_tc).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -32,17 +21,9 @@
 
 namespace rldm {
 
-constexpr int kAtThreads = 8 * 32;
 constexpr int kAtTile = 128;                    // queries per CTA and keys per tile
-constexpr int kAtRing = 3;                      // K ring and V ring
 constexpr int kAtQBytes = kAtTile * 128;        // 16 KB: 128 rows x 128 B (first 64 B of a row used)
-constexpr int kAtKBytes = kAtTile * 128;        // 16 KB
-constexpr int kAtVAtom = 16 * 128;              // 2 KB: 16 rows (8 v_hi, 8 v_lo) x 64 keys
-constexpr int kAtVBytes = 2 * kAtVAtom;         // 2 K-atoms of 64 keys
-constexpr int kAtMaxTiles = 8;                  // N <= 1024
-constexpr int kAtSlot0 = 128;                   // first output-slot column
 constexpr int kAtTmemCols = 256;
-constexpr int kAtSlot = 16;                     // TMEM columns per output slot
 
 __device__ __forceinline__ uint32_t at_pack(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ void at_split2(float x, float y, uint32_t& hi, uint32_t& lo) {
@@ -94,15 +75,6 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       : "memory");
 }
 
-struct AttnSmem {
-  uint64_t q_full, q_empty;
-  uint64_t k_full[kAtRing], k_empty[kAtRing], v_full[kAtRing], v_empty[kAtRing];
-  uint64_t s_full, p_full;
-  uint64_t all_done;
-  uint32_t tmem_ptr;
-  uint32_t pad;
-};
-
 // max of the 32 scores of one TMEM chunk
 __device__ __forceinline__ float at_max32(const uint32_t (&r)[32]) {
   float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
@@ -113,25 +85,9 @@ __device__ __forceinline__ float at_max32(const uint32_t (&r)[32]) {
   }
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
-// P = 2^(S - m) for the 32 keys of one chunk as split fp16, written over the chunk's own 32 columns:
-// 16 columns of P_hi followed by 16 columns of P_lo; returns the sum of the 32 probabilities
-__device__ __forceinline__ float at_exp_store32(const uint32_t (&r)[32], float m, uint32_t t_chunk) {
-  uint32_t h[16], lo[16];
-  float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    const float pa = at_ex2(__uint_as_float(r[2 * e]) - m);
-    const float pb = at_ex2(__uint_as_float(r[2 * e + 1]) - m);
-    l0 += pa; l1 += pb;
-    at_split2(pa, pb, h[e], lo[e]);
-  }
-  tmem_st_32x16(t_chunk, h);
-  tmem_st_32x16(t_chunk + 16, lo);
-  return l0 + l1;
-}
-
-// The same with packed fp32 arithmetic (add.f32x2 / fma.f32x2: two lanes per issue slot -- the pipelined kernel is
-// bound by instruction issue, not by MUFU) and without the row sum (the pipelined kernel takes it from the MMA).
+// P = 2^(S - m) for the 32 keys of one chunk as split fp16, written over the chunk's own 32 columns (16 columns of
+// P_hi followed by 16 of P_lo), with packed fp32 arithmetic (add.f32x2 / fma.f32x2: two lanes per issue slot -- the
+// kernel is bound by instruction issue as much as by MUFU); the row sum comes from the MMA (ones row of V^T).
 __device__ __forceinline__ void at_exp_store32_packed(const uint32_t (&r)[32], float m, uint32_t t_chunk) {
   uint32_t h[16], lo[16];
   const float2 nm = make_float2(-m, -m), neg1 = make_float2(-1.f, -1.f);
@@ -153,278 +109,8 @@ __device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
   return r;
 }
 
-// Persistent: gridDim.x CTAs (two per SM) walk over the work items (image, head, 128-query block); barriers, TMEM and
-// the K/V ring live across items, the loaders run ahead into the next item while the current one is still in its
-// softmax / combine phase, so prologue and tail are paid once per CTA instead of once per item.
-__global__ void __launch_bounds__(kAtThreads, 2)
-attention_umma_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half* __restrict__ out_lo, int N, int C,
-                      int H, int B, long long* dbg) {
-  // profiling aid (normally NULL): clock64 stamps of CTA 0, first item: [0..31] loader 0, [32..63] MMA, [64..127] softmax
-  if (dbg != nullptr && blockIdx.x != 0) dbg = nullptr;
-#define AT_STAMP(idx) do { if (dbg) dbg[idx] = clock64(); } while (0)
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kAtQBytes;                           // [3][16 KB]
-  uint8_t* sV = sK + kAtRing * kAtKBytes;                 // [3][4 KB]
-  float2* sML = reinterpret_cast<float2*>(sV + kAtRing * kAtVBytes);     // [tiles][128] (row max, row sum) per key tile
-  const int T = N / kAtTile;
-  AttnSmem* sb = reinterpret_cast<AttnSmem*>(reinterpret_cast<uint8_t*>(sML) + static_cast<size_t>(T) * kAtTile * 8);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t rowf = 3 * static_cast<size_t>(C);
-  const int heads = C / 8;
-  const int n_items = B * heads * T;                       // T query blocks per (image, head)
-  // item -> (image, head, first query); consecutive items = the query blocks of one (image, head): K/V stay in L2
-  auto item_base = [&](int item, int& q0) -> const float* {
-    const int qb = item % T, bh = item / T;
-    q0 = qb * kAtTile;
-    return qkv + static_cast<size_t>(bh / heads) * N * rowf + (bh % heads) * 8;
-  };
-
-  pdl_trigger();
-  if (threadIdx.x == 0) AT_STAMP(127);
-  if (threadIdx.x == 0) {
-    mbar_init(&sb->q_full, 96);
-    mbar_init(&sb->q_empty, 1);
-    for (int i = 0; i < kAtRing; ++i) {
-      mbar_init(&sb->k_full[i], 32); mbar_init(&sb->k_empty[i], 1);
-      mbar_init(&sb->v_full[i], 32); mbar_init(&sb->v_empty[i], 1);
-    }
-    mbar_init(&sb->s_full, 1); mbar_init(&sb->p_full, 128);
-    mbar_init(&sb->all_done, 1);
-    mbar_fence_init();
-  }
-  if (warp == 4) tmem_alloc<kAtTmemCols>(&sb->tmem_ptr);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = __shfl_sync(0xffffffffu, sb->tmem_ptr, 0);   // shfl: warp-uniform for the compiler
-  pdl_wait();
-  if (threadIdx.x == 0) AT_STAMP(124);
-
-  if (warp >= 5) {
-    // ===================== loaders ==============================================================
-    const int w = warp - 5;                                // ring slot of this warp: global tiles g = w mod 3
-    const int qt = threadIdx.x - 5 * 32;                   // 0..95: Q rows qt and qt + 96
-    if (lane == 0 && w == 0) AT_STAMP(0);
-    // K: lane <-> rows lane + 32 rr;  V: lane <-> keys 4 lane .. 4 lane + 3.  The next tile is always in registers.
-    float4 ka[4], kb[4], va[4], vb[4];
-    const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    const int total_tiles = my_items * T;                  // tiles this CTA walks over, all its items
-    auto load_tile = [&](int g) {                          // g: running tile index of this CTA
-      int q0;
-      const float* base = item_base(static_cast<int>(blockIdx.x) + (g / T) * static_cast<int>(gridDim.x), q0);
-      const int t = g % T;
-#pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const float* kp = base + static_cast<size_t>(t * kAtTile + lane + rr * 32) * rowf + C;
-        ka[rr] = __ldg(reinterpret_cast<const float4*>(kp)); kb[rr] = __ldg(reinterpret_cast<const float4*>(kp) + 1);
-        const float* vp = base + static_cast<size_t>(t * kAtTile + 4 * lane + rr) * rowf + 2 * C;
-        va[rr] = __ldg(reinterpret_cast<const float4*>(vp)); vb[rr] = __ldg(reinterpret_cast<const float4*>(vp) + 1);
-      }
-    };
-    // Q rows of local item n: [q_hi | q_lo | q_hi | 0], softmax scale 1/sqrt(8) and log2(e) folded in
-    auto load_q = [&](int n) {
-      int q0;
-      const float* base = item_base(static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x), q0);
-      float4 qa[2], qb[2];
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int i = qt + rr * 96;
-        if (i < kAtTile) {
-          const float* qp = base + static_cast<size_t>(q0 + i) * rowf;
-          qa[rr] = __ldg(reinterpret_cast<const float4*>(qp)); qb[rr] = __ldg(reinterpret_cast<const float4*>(qp) + 1);
-        }
-      }
-      mbar_wait(&sb->q_empty, (n & 1) ^ 1);               // every Q K^T of the previous item has completed
-      const float qs = 0.35355339059327373f * 1.4426950408889634f;
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int i = qt + rr * 96, sw = i & 7;
-        if (i < kAtTile) {
-          uint32_t h[4], l[4];
-          at_split2(qa[rr].x * qs, qa[rr].y * qs, h[0], l[0]); at_split2(qa[rr].z * qs, qa[rr].w * qs, h[1], l[1]);
-          at_split2(qb[rr].x * qs, qb[rr].y * qs, h[2], l[2]); at_split2(qb[rr].z * qs, qb[rr].w * qs, h[3], l[3]);
-          const uint32_t r = smem_u32(sQ) + i * 128;
-          at_sts128(r + ((0 ^ sw) << 4), h[0], h[1], h[2], h[3]);
-          at_sts128(r + ((1 ^ sw) << 4), l[0], l[1], l[2], l[3]);
-          at_sts128(r + ((2 ^ sw) << 4), h[0], h[1], h[2], h[3]);
-          at_sts128(r + ((3 ^ sw) << 4), 0u, 0u, 0u, 0u);
-        }
-      }
-      at_fence_async();
-      at_arrive(&sb->q_full);
-    };
-    if (w < total_tiles) load_tile(w);
-    int q_next = 0;                                        // next local item whose Q this warp still has to stage
-    for (int g = w; g < total_tiles; g += kAtRing) {
-      // stage the Q of every item up to the one tile g belongs to (all three loader warps take part in each Q)
-      while (q_next <= g / T) load_q(q_next++);
-      const uint32_t ph = ((g / kAtRing) & 1) ^ 1;
-      mbar_wait(&sb->k_empty[w], ph);
-#pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const int i = lane + rr * 32, sw = i & 7;
-        uint32_t h[4], l[4];
-        at_split2(ka[rr].x, ka[rr].y, h[0], l[0]); at_split2(ka[rr].z, ka[rr].w, h[1], l[1]);
-        at_split2(kb[rr].x, kb[rr].y, h[2], l[2]); at_split2(kb[rr].z, kb[rr].w, h[3], l[3]);
-        const uint32_t kr = smem_u32(sK + w * kAtKBytes) + i * 128;       // K row: [k_hi | k_hi | k_lo | 0]
-        at_sts128(kr + ((0 ^ sw) << 4), h[0], h[1], h[2], h[3]);
-        at_sts128(kr + ((1 ^ sw) << 4), h[0], h[1], h[2], h[3]);
-        at_sts128(kr + ((2 ^ sw) << 4), l[0], l[1], l[2], l[3]);
-        at_sts128(kr + ((3 ^ sw) << 4), 0u, 0u, 0u, 0u);
-      }
-      at_fence_async();
-      at_arrive(&sb->k_full[w]);
-      mbar_wait(&sb->v_empty[w], ph);
-      {
-        // V^T: row n = d (hi) / 8 + d (lo); this lane's 4 keys are half a 16 B chunk: atom = lane / 16,
-        // chunk = (lane % 16) / 2, byte offset 8 (lane % 2) inside the chunk
-        const uint32_t vbase = smem_u32(sV + w * kAtVBytes) + (lane >> 4) * kAtVAtom + ((lane & 1) << 3);
-        const int chunk = (lane & 15) >> 1;
-        const float v0[8] = {va[0].x, va[0].y, va[0].z, va[0].w, vb[0].x, vb[0].y, vb[0].z, vb[0].w};
-        const float v1[8] = {va[1].x, va[1].y, va[1].z, va[1].w, vb[1].x, vb[1].y, vb[1].z, vb[1].w};
-        const float v2[8] = {va[2].x, va[2].y, va[2].z, va[2].w, vb[2].x, vb[2].y, vb[2].z, vb[2].w};
-        const float v3[8] = {va[3].x, va[3].y, va[3].z, va[3].w, vb[3].x, vb[3].y, vb[3].z, vb[3].w};
-#pragma unroll
-        for (int d = 0; d < 8; ++d) {
-          uint32_t h01, l01, h23, l23;
-          at_split2(v0[d], v1[d], h01, l01);
-          at_split2(v2[d], v3[d], h23, l23);
-          const uint32_t off = static_cast<uint32_t>((chunk ^ d) << 4);   // rows d and 8 + d: (row & 7) == d
-          at_sts64(vbase + d * 128 + off, h01, h23);
-          at_sts64(vbase + (8 + d) * 128 + off, l01, l23);
-        }
-      }
-      at_fence_async();
-      at_arrive(&sb->v_full[w]);
-      if (lane == 0 && w == 0 && g / kAtRing < 8) AT_STAMP(1 + g / kAtRing);
-      if (g + kAtRing < total_tiles) load_tile(g + kAtRing);
-    }
-    while (q_next < my_items) load_q(q_next++);            // (only when a warp owns no tile of the last items)
-  } else if (warp == 4) {
-    // ===================== MMA issuer ===========================================================
-    if (elect_one()) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(128, 128);
-      constexpr uint32_t idesc_o = umma_idesc_f16(128, kAtSlot);
-      const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ));
-      const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-      auto issue_qk = [&](int g, bool last_of_item) {      // after the previous PV in program order: MMAs execute in order
-        const int s = g % kAtRing;
-        mbar_wait(&sb->k_full[s], (g / kAtRing) & 1);
-        tc_fence_after();
-        const uint64_t k_desc = umma_desc_sw128(smem_u32(sK + s * kAtKBytes));
-        umma_f16(tmem, q_desc, k_desc, idesc_s, 0u);
-        umma_f16(tmem, q_desc + 2, k_desc + 2, idesc_s, 1u);
-        umma_commit(&sb->s_full);
-        umma_commit(&sb->k_empty[s]);
-        if (last_of_item) umma_commit(&sb->q_empty);       // the Q tile may be overwritten with the next item's
-        if (g < 15) AT_STAMP(32 + g);
-      };
-      int g = 0;                                           // running tile index
-      for (int n = 0; n < my_items; ++n) {
-        mbar_wait(&sb->q_full, n & 1);
-        issue_qk(g, T == 1);
-        for (int j = 0; j < T; ++j, ++g) {
-          const int s = g % kAtRing;
-          mbar_wait(&sb->v_full[s], (g / kAtRing) & 1);
-          mbar_wait(&sb->p_full, g & 1);
-          tc_fence_after();
-          const uint32_t d = tmem + kAtSlot0 + kAtSlot * j;
-          const uint32_t v_addr = smem_u32(sV + s * kAtVBytes);
-#pragma unroll
-          for (int part = 0; part < 2; ++part) {
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {               // K step = 16 keys = 8 columns of chunk ks / 2
-              const uint64_t v_desc = umma_desc_sw128(v_addr + (ks >> 2) * kAtVAtom) + 2 * (ks & 3);
-              umma_f16_ts(d, tmem + (ks >> 1) * 32 + part * 16 + (ks & 1) * 8, v_desc, idesc_o, (part | ks) != 0);
-            }
-          }
-          umma_commit(&sb->v_empty[s]);
-          if (g < 15) AT_STAMP(48 + g);
-          if (j + 1 < T) issue_qk(g + 1, j + 2 == T);
-        }
-        umma_commit(&sb->all_done);                        // every PV of this item has completed
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===================== softmax warps ========================================================
-    const int row = warp * 32 + lane;                      // query row == TMEM lane
-    const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-    const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    int g = 0;                                             // running tile index
-    for (int n = 0; n < my_items; ++n) {
-      for (int j = 0; j < T; ++j, ++g) {
-        mbar_wait(&sb->s_full, g & 1);
-        tc_fence_after();
-        if (threadIdx.x == 0 && g < 16) AT_STAMP(64 + 4 * g);
-        float m = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {                      // pass 1: row maximum
-          uint32_t r[32];
-          tmem_ld_32x32(t_lane + c * 32, r);
-          tmem_ld_wait();
-          m = fmaxf(m, at_max32(r));
-        }
-        if (threadIdx.x == 0 && g < 16) AT_STAMP(65 + 4 * g);
-        float l = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {                      // pass 2: exponentials, P written in place
-          uint32_t r[32];
-          tmem_ld_32x32(t_lane + c * 32, r);
-          tmem_ld_wait();
-          l += at_exp_store32(r, m, t_lane + c * 32);
-        }
-        sML[j * kAtTile + row] = make_float2(m, l);
-        tmem_st_wait();
-        tc_fence_before();
-        at_arrive(&sb->p_full);
-        if (threadIdx.x == 0 && g < 16) AT_STAMP(67 + 4 * g);
-      }
-      // ===================== combine the key tiles, normalise, write the operand ================
-      // (the next item's first Q K^T already runs; its first P V waits for this thread's next p_full arrival, i.e.
-      //  until every row has finished reading the output slots below)
-      mbar_wait(&sb->all_done, n & 1);
-      tc_fence_after();
-      if (threadIdx.x == 0 && n == 0) AT_STAMP(125);
-      float m = -INFINITY;
-      for (int j = 0; j < T; ++j) m = fmaxf(m, sML[j * kAtTile + row].x);
-      float L = 0.f;
-      float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int j = 0; j < T; ++j) {
-        const float2 ml = sML[j * kAtTile + row];
-        const float wgt = at_ex2(ml.x - m);
-        L = fmaf(wgt, ml.y, L);
-        uint32_t r[16];
-        tmem_ld_32x16(t_lane + kAtSlot0 + kAtSlot * j, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int d = 0; d < 8; ++d) o[d] = fmaf(wgt, __uint_as_float(r[d]) + __uint_as_float(r[8 + d]), o[d]);
-      }
-      tc_fence_before();
-      const float inv = 1.0f / L;
-      uint32_t h[4], lo[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) at_split2(o[2 * e] * inv, o[2 * e + 1] * inv, h[e], lo[e]);
-      // W-padded operand layout (B, W+2, H, C): token n lands at padded pixel H + n
-      const int item = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
-      const int qb = item % T, bh = item / T;
-      const size_t oi = (static_cast<size_t>(bh / heads) * (N + 2 * H) + H + qb * kAtTile + row) * C + (bh % heads) * 8;
-      *reinterpret_cast<uint4*>(out + oi) = make_uint4(h[0], h[1], h[2], h[3]);
-      if (out_lo) *reinterpret_cast<uint4*>(out_lo + oi) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      if (threadIdx.x == 0 && n == 0) AT_STAMP(126);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) tmem_dealloc<kAtTmemCols>(tmem);
-}
-
-
 // ------------------------------------------------------------------------------------------------
-// Pipelined variant (default): the same arithmetic with 64-key tiles, THREE S/P buffers (64 TMEM columns each) and
+// Persistent, pipelined kernel: 64-key tiles, THREE S/P buffers (64 TMEM columns each) and
 // the per-tile outputs folded into registers, so Q K^T of tiles j+1..j+3 is already in TMEM while the softmax
 // warps work on tile j -- their MUFU stream never waits for the MMA / barrier round trip.
 //   * the key tiles of a CTA form ONE stream across its work items (Q is double-buffered), so Q K^T of the next
@@ -802,17 +488,12 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
 
 using namespace rldm;
 
-static long long* g_attn_dbg = nullptr;
-extern "C" void rldm_debug_attn_timestamps(long long* dev_buf) { g_attn_dbg = dev_buf; }
-
 // Host entry used by rldm_attention (ops.cu).  Returns -1 when the shape is outside this kernel's range (the caller
 // then takes the mma.sync / CUDA-core kernels), 0 on success, > 0 on error.
 int rldm_attention_umma(const float* qkv, uint16_t* out, uint16_t* out_lo, int B, int N, int C, int H, void* stream) {
-  // Very short sequences (N = 128: one query block per head) are all prologue and tail; the mma.sync kernel takes
-  // them.  N = 256, C = 256, B = 8 on B200: 16.9 us here vs 18.2 us (mma.sync).  RLDM_ATTN_TCGEN05=1 forces this one.
-  const bool serial = getenv("RLDM_ATTN_SERIAL") != nullptr;      // one-buffer kernel: per-tile output slots, N <= 1024
-  if (N % kAtTile != 0 || C % 8 != 0 || (serial && N / kAtTile > kAtMaxTiles)) return -1;
-  if (N < 2 * kAtTile && !getenv("RLDM_ATTN_TCGEN05")) return -1;
+  // N a multiple of 128 and at least four 64-key tiles.  Shorter sequences (N = 128: one query block per head) are all
+  // prologue and tail; the mma.sync kernel takes them.
+  if (N % kAtTile != 0 || C % 8 != 0 || N < 4 * kApKT) return -1;
   const int T = N / kAtTile;
   static int n_sms_p = 0;
   if (n_sms_p == 0) {
@@ -821,41 +502,18 @@ int rldm_attention_umma(const float* qkv, uint16_t* out, uint16_t* out_lo, int B
     cudaDeviceGetAttribute(&n_sms_p, cudaDevAttrMultiProcessorCount, dev);
     if (n_sms_p <= 0) n_sms_p = 148;
   }
-  if (!serial && N >= 4 * kApKT) {           // pipelined kernel (three S/P buffers, outputs folded into registers)
-    const size_t smem_p = 1024 + 2 * kAtQBytes + kApRing * (kApKBytes + kApVBytes) + kApXFloats * kAtTile * 4 +
-                          sizeof(AttnPipeSmem);
-    static bool attr_p = false;
-    if (!attr_p) {
-      RLDM_CUDA(cudaFuncSetAttribute(attention_umma_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem_p)));
-      attr_p = true;
-    }
-    const int items_p = B * (C / 8) * T;
-    const int ctas_p = items_p < 2 * n_sms_p ? items_p : 2 * n_sms_p;
-    RLDM_CUDA(launch_pdl(attention_umma_pipelined_kernel, dim3(ctas_p), dim3(kApThreads), smem_p, as_stream(stream), qkv,
-                         reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H, B));
-    RLDM_LAUNCH_CHECK();
-    return 0;
+  const size_t smem_p = 1024 + 2 * kAtQBytes + kApRing * (kApKBytes + kApVBytes) + kApXFloats * kAtTile * 4 +
+                        sizeof(AttnPipeSmem);
+  static bool attr_p = false;
+  if (!attr_p) {
+    RLDM_CUDA(cudaFuncSetAttribute(attention_umma_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem_p)));
+    attr_p = true;
   }
-  const size_t smem = 1024 + kAtQBytes + kAtRing * (kAtKBytes + kAtVBytes) + static_cast<size_t>(T) * kAtTile * 8 +
-                      sizeof(AttnSmem);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    RLDM_CUDA(cudaFuncSetAttribute(attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(smem)));
-    attr_smem = smem;
-  }
-  static int n_sms = 0;
-  if (n_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sms <= 0) n_sms = 148;
-  }
-  const int items = B * (C / 8) * T;
-  const int ctas = items < 2 * n_sms ? items : 2 * n_sms;            // two persistent CTAs per SM
-  RLDM_CUDA(launch_pdl(attention_umma_kernel, dim3(ctas), dim3(kAtThreads), smem, as_stream(stream), qkv,
-                       reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H, B, g_attn_dbg));
+  const int items_p = B * (C / 8) * T;
+  const int ctas_p = items_p < 2 * n_sms_p ? items_p : 2 * n_sms_p;      // two persistent CTAs per SM
+  RLDM_CUDA(launch_pdl(attention_umma_pipelined_kernel, dim3(ctas_p), dim3(kApThreads), smem_p, as_stream(stream), qkv,
+                       reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H, B));
   RLDM_LAUNCH_CHECK();
   return 0;
 }

@@ -38,6 +38,25 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 // completed and flushed, so correctness is that of plain stream order -- and every kernel fires
 // `griddepcontrol.launch_dependents` early.  Without the attribute both instructions are no-ops.  Which launches get
 // the attribute is a measured policy (ops.cu: pdl_mode): by default only the latency-bound ones.
+// Environment switches of librldm.so, read ONCE at first use (rldm_reload_env() re-reads them: the GPU tests flip
+// them between cases).  Defaults are the measured best; every other setting exists so a number in DESIGN.md can be
+// re-checked.
+struct EnvSwitches {
+  int pdl;                  // RLDM_PDL = 0 | 1 | 2 (default 2: only latency-bound launches carry the PDL attribute)
+  size_t prep_pdl_max;      // RLDM_PREP_PDL_MAX: largest prep pass (elements) that carries it (default 2e7)
+  int conv_wt;              // RLDM_CONV_WT:      1 role-swapped conv kernel (default) | 0 off | 2 ("nores")
+  int conv_wt_halo;         // RLDM_CONV_WT_HALO: 1 pixel windows inside it (default) | 0 off | 2 ("nores")
+  bool conv_persistent;     // RLDM_NO_PERSISTENT unset
+  bool conv_mt1;            // RLDM_CONV_MT1:     pixel-M persistent kernel with one tile per unit
+  bool conv_mt2_res;        // RLDM_CONV_MT2_RES: two tiles per unit also for 128-wide layers with a residual
+  bool wt_pdl;              // RLDM_WT_PDL != 0:  PDL on single-wave role-swapped launches (default on)
+  bool attn_mmasync;        // RLDM_ATTN_MMASYNC: mma.sync attention kernel for every shape it covers
+  bool attn_cudacore;       // RLDM_ATTN_CUDACORE: CUDA-core attention kernel for every shape
+  bool nco_pp1;             // RLDM_NCO_PP1:      norm_conv_out with one pixel per thread
+  int n_sms;
+};
+const EnvSwitches& env();
+
 bool pdl_enabled();
 // launches marked latency-bound (small convolutions, small prep passes)
 bool pdl_enabled_small();

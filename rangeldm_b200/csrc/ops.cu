@@ -16,21 +16,41 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-// Programmatic dependent launch policy (RLDM_PDL = 0 | 1 | 2, default 2).  Measured on B200 inside the trajectory
-// graph (scripts/timeline.py, scripts/launch_gap.py): programmatic edges save ~1 us per node on the latency-bound
-// launches (small convolutions 9.6 -> 8.8 us, prep + conv pairs 11.5 -> 10.1 us), but make the long persistent
-// convolutions, the attention kernel and the big elementwise passes SLOWER (decoder +8 %) -- early-launched dependents
-// sit on SM resources for the whole primary.  Mode 2 therefore marks only the latency-bound launches; 1 marks all.
-static int pdl_mode() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("RLDM_PDL");
-    v = e ? atoi(e) : 2;
-  }
-  return v;
+static EnvSwitches g_env;
+static bool g_env_loaded = false;
+static void load_env() {
+  auto tri = [](const char* name) { const char* e = getenv(name); return !e ? 1 : (e[0] == '0' ? 0 : (e[0] == 'n' ? 2 : 1)); };
+  const char* e = getenv("RLDM_PDL");
+  g_env.pdl = e ? atoi(e) : 2;
+  e = getenv("RLDM_PREP_PDL_MAX");
+  g_env.prep_pdl_max = e ? static_cast<size_t>(atoll(e)) : static_cast<size_t>(20000000);   // UNet forward 1988 -> 1965 us vs 2^21
+  g_env.conv_wt = tri("RLDM_CONV_WT");
+  g_env.conv_wt_halo = tri("RLDM_CONV_WT_HALO");
+  g_env.conv_persistent = getenv("RLDM_NO_PERSISTENT") == nullptr;
+  g_env.conv_mt1 = getenv("RLDM_CONV_MT1") != nullptr;
+  g_env.conv_mt2_res = getenv("RLDM_CONV_MT2_RES") != nullptr;
+  e = getenv("RLDM_WT_PDL");
+  g_env.wt_pdl = e ? atoi(e) != 0 : true;
+  g_env.attn_mmasync = getenv("RLDM_ATTN_MMASYNC") != nullptr;
+  g_env.attn_cudacore = getenv("RLDM_ATTN_CUDACORE") != nullptr;
+  g_env.nco_pp1 = getenv("RLDM_NCO_PP1") != nullptr;
+  int dev = 0;
+  g_env.n_sms = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&g_env.n_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (g_env.n_sms <= 0) g_env.n_sms = 148;
+  g_env_loaded = true;
 }
-bool pdl_enabled() { return pdl_mode() == 1; }
-bool pdl_enabled_small() { return pdl_mode() == 1 || pdl_mode() == 2; }
+const EnvSwitches& env() {
+  if (!g_env_loaded) load_env();
+  return g_env;
+}
+// Programmatic dependent launch policy (RLDM_PDL = 0 | 1 | 2, default 2).  Measured on B200 inside the trajectory
+// graph (scripts/launch_gap.py): programmatic edges save ~1 us per node on the latency-bound launches (small
+// convolutions 9.6 -> 8.8 us, prep + conv pairs 11.5 -> 10.1 us), but make the long persistent convolutions, the
+// attention kernel and the big elementwise passes SLOWER (decoder +8 %) -- early-launched dependents sit on SM
+// resources for the whole primary.  Mode 2 therefore marks only the latency-bound launches; 1 marks all.
+bool pdl_enabled() { return env().pdl == 1; }
+bool pdl_enabled_small() { return env().pdl == 1 || env().pdl == 2; }
 
 // ------------------------------------------------------------------------------------------------
 // GroupNorm statistics.  grid (chunks, B), block 256.  Thread = one float4 of channels, striding
@@ -1080,6 +1100,7 @@ __global__ void cl_to_ref_kernel(const float* __restrict__ src, float* __restric
 using namespace rldm;
 
 extern "C" int rldm_version(void) { return RLDM_VERSION; }
+extern "C" void rldm_reload_env(void) { load_env(); }
 extern "C" const char* rldm_last_error(void) { return g_err; }
 
 extern "C" int rldm_gn_stats(const float* x0, int c0, const float* x1, int c1, double* sums, int B,
@@ -1117,12 +1138,7 @@ extern "C" int rldm_prep(const float* x0, int c0, const float* x1, int c1, const
   chunks = (out_pix + ppb - 1) / ppb;
   // preps up to the top-level UNet tensors may start under the tail of the producing kernel (RLDM_PDL=2); the
   // full-resolution decoder passes measured slower with it
-  static size_t pdl_max_elems = 0;
-  if (pdl_max_elems == 0) {
-    const char* e = getenv("RLDM_PREP_PDL_MAX");
-    pdl_max_elems = e ? static_cast<size_t>(atoll(e)) : static_cast<size_t>(20000000);   // UNet forward 1988 -> 1965 us vs 2^21
-  }
-  if (static_cast<size_t>(B) * out_pix * C <= pdl_max_elems) {
+  if (static_cast<size_t>(B) * out_pix * C <= env().prep_pdl_max) {
     RLDM_CUDA(launch_pdl_small(prep_kernel, dim3(chunks, B), dim3(256), 2 * C * sizeof(float), as_stream(stream), x0, c0, x1, c1, sums, pairs0, pairs1, gamma, beta, eps, G, silu, up, circular, reinterpret_cast<__half*>(out),
       reinterpret_cast<__half*>(out_lo), reinterpret_cast<__half*>(raw), reinterpret_cast<__half*>(raw_lo), W, H, ppb));
     } else {
@@ -1219,7 +1235,7 @@ extern "C" int rldm_norm_conv_out(const float* x, const double* sums, const doub
   RLDM_CHECK(H >= 1 && H <= 256, "norm_conv_out: H out of range (%d)", H);
   // lanes per pixel: keep ~256 threads busy on a TW x H pixel tile
   // four pixels per thread (register-blocked inner loop) whenever H allows it; RLDM_NCO_PP1=1: one pixel per thread
-  const int PP = (H % 4 == 0 && Cout <= 4 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && !getenv("RLDM_NCO_PP1")) ? 4 : 1;
+  const int PP = (H % 4 == 0 && Cout <= 4 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && !env().nco_pp1) ? 4 : 1;
   int TW = 8, LPP = 1;
   size_t smem = 0;
   for (;; TW >>= 1) {
@@ -1258,11 +1274,11 @@ int rldm_attention_umma(const float* qkv, uint16_t* out, uint16_t* out_lo, int B
 extern "C" int rldm_attention(const float* qkv, uint16_t* out, uint16_t* out_lo, int B, int N, int C,
                               int H, void* stream) {
   RLDM_CHECK(C % 8 == 0, "attention: C %% 8 != 0");
-  if (!getenv("RLDM_ATTN_MMASYNC") && !getenv("RLDM_ATTN_CUDACORE")) {   // tcgen05 kernel: N a multiple of 128, <= 2048
+  if (!env().attn_mmasync && !env().attn_cudacore) {   // tcgen05 kernel: N a multiple of 128, >= 256
     const int rc = rldm_attention_umma(qkv, out, out_lo, B, N, C, H, stream);
     if (rc >= 0) return rc;
   }
-  if (N % 64 == 0 && !getenv("RLDM_ATTN_CUDACORE")) {   // tensor-path kernel; the CUDA-core kernel covers ragged N
+  if (N % 64 == 0 && !env().attn_cudacore) {   // tensor-path kernel; the CUDA-core kernel covers ragged N
     RLDM_CUDA(launch_pdl(attention_tc_kernel, dim3(N / 64, C / 8, B), dim3(128), 0, as_stream(stream), qkv, reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H));
     RLDM_LAUNCH_CHECK();
     return 0;
@@ -1636,11 +1652,11 @@ static int run_ops(const rldm_op* ops, int n_ops, unsigned long long* stamps, vo
                        stream);
         break;
       case RLDM_OP_CONV_TC:
-        rc = rldm_conv_tc_ws((const uint16_t*)o.p[0], (const uint16_t*)o.p[6], (const uint16_t*)o.p[1],
+        rc = rldm_conv_tc_ex((const uint16_t*)o.p[0], (const uint16_t*)o.p[6], (const uint16_t*)o.p[1],
                              (const float*)o.p[2], (const float*)o.p[3], o.i[0], (const float*)o.p[4],
                              (float*)o.p[5], o.i[1], o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], o.i[7], o.i[8], o.i[9],
                              o.i[10], (double*)o.p[7], (const uint16_t*)o.p[8], (const uint16_t*)o.p[9],
-                             (const uint16_t*)o.p[10], o.i[11], (float*)o.p[11], o.n, stream);
+                             (const uint16_t*)o.p[10], o.i[11], o.i[12], stream);
         break;
       case RLDM_OP_CONV_REF:
         rc = rldm_conv_ref((const uint16_t*)o.p[0], (const uint16_t*)o.p[6], (const uint16_t*)o.p[1], (const float*)o.p[2],

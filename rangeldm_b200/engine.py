@@ -26,20 +26,33 @@ from ._lib import RldmOp
 # debug switch used by the GPU tests to run the CUDA-core restatement of the conv (never the default)
 CONV_KIND = _lib.OP_CONV_TC
 
-# Tensor-core operand precision.
-#   "fp16x3" (default): split-fp16 -- activations and weights are carried as hi+lo fp16 pairs and every K step
-#             issues Ah*Wh + Al*Wh + Ah*Wl into the fp32 TMEM accumulator (~22-bit operands).  Seed-matched
-#             20-step trajectories agree with the fp32 oracle to ~1e-5, far inside the 1e-3 tolerance.
-#   "fp16":   plain fp16 operands (1 MMA per K step).  ~3x less tensor work, but the 11-bit operand rounding puts
-#             whole-trajectory parity at 0.6-1.0e-3, i.e. AT the tolerance -- opt-in only.
-PRECISION = os.environ.get("RLDM_PRECISION", "fp16x3")
+# Tensor-core operand precision, chosen PER LAYER (`terms` of rldm_conv_tc_ex):
+#   3 "fp16x3": split-fp16 -- activations and weights are carried as hi+lo fp16 pairs and every K step issues
+#               Xh*Wh + Xl*Wh + Xh*Wl into the fp32 TMEM accumulator (~22-bit operands).
+#   2 "fp16x2": activations single fp16, weights hi+lo: Xh*Wh + Xh*Wl.  No low-order activation plane exists: the
+#               producer pass writes, and the conv reads, half the operand bytes; 2/3 of the tensor work.
+#   1 "fp16":   plain fp16 operands (1 MMA per K step).
+# Errors of the 20-step UNet loop compound, the VAE decoder runs once: the defaults below are the measured Pareto
+# choice (parity table); RLDM_PRECISION / _TOP / _DEC override the UNet lower levels, the UNet
+# full-resolution level and the VAE.
+_TERMS = {"fp16x3": 3, "fp16x2": 2, "fp16": 1}
+
+
+def _terms_env(name, default):
+    v = os.environ.get(name, default)
+    if v not in _TERMS:
+        raise ValueError(f"{name} must be one of {sorted(_TERMS)}, got {v!r}")
+    return _TERMS[v]
+
+
+PRECISION = _terms_env("RLDM_PRECISION", "fp16x3")                                    # UNet levels 1..n
+PRECISION_TOP = _terms_env("RLDM_PRECISION_TOP", os.environ.get("RLDM_PRECISION", "fp16x3"))   # UNet full resolution
+PRECISION_DEC = _terms_env("RLDM_PRECISION_DEC", os.environ.get("RLDM_PRECISION", "fp16x3"))   # VAE decoder / encoder
 # GroupNorm moments accumulated in the conv epilogue (RLDM_FUSE_STATS=0 forces the separate rldm_gn_stats pass)
 FUSE_STATS = os.environ.get("RLDM_FUSE_STATS", "1") != "0"
 # ResnetBlock2D.conv_shortcut folded into conv2's launch (RLDM_FUSE_SHORTCUT=0: separate 1x1 launch + fp32 residual)
 FUSE_SHORTCUT = os.environ.get("RLDM_FUSE_SHORTCUT", "1") != "0"
 FUSE_CONV_OUT = os.environ.get("RLDM_FUSE_CONV_OUT", "1") != "0"
-# split-K partial tiles through an L2 workspace instead of DSMEM: measured SLOWER on B200 (C3 UNet 2.33 vs 2.25 ms), opt-in
-SPLITK_VIA_L2 = os.environ.get("RLDM_SPLITK_VIA_L2", "0") == "1"
 
 
 def _require_cuda_device(dev, what):
@@ -133,19 +146,15 @@ def _is_identity_attn(m):
 class Builder:
     """Emits ops for the building blocks shared by the UNet and the VAE."""
 
-    def __init__(self, prog, batch, max_gn=4096, groups=32, cache=None):
+    def __init__(self, prog, batch, max_gn=4096, groups=32, cache=None, terms_of=None):
         self.cache = cache if cache is not None else {}      # packed weights shared between plans of a model
-        if PRECISION not in ("fp16x3", "fp16"):
-            raise ValueError(f"RLDM_PRECISION must be 'fp16x3' or 'fp16', got {PRECISION!r}")
-        self.split = PRECISION == "fp16x3"
+        # terms_of(W) -> 1 | 2 | 3: operand precision of a convolution whose INPUT grid is W columns wide
+        self.terms_of = terms_of if terms_of is not None else (lambda W: PRECISION)
         self.pg = prog
         self.B = batch
         self.groups = groups
         self.gn_arena = prog.hold(torch.zeros(max_gn * batch * groups * 2, dtype=torch.float64, device=prog.device))   # 16 MB at batch 8
         self.gn_used = 0
-        # split-K workspace (partial tiles of clustered small convolutions travel through L2 instead of DSMEM);
-        # one per program: its launches are stream-ordered.  12 MB covers every automatic split (<= 160 CTAs x 64 KB).
-        self.splitk_ws = prog.hold(torch.empty(12 << 20, dtype=torch.uint8, device=prog.device)) if SPLITK_VIA_L2 else None
         self.memset_op = prog.add(_lib.OP_MEMSET, p=(self.gn_arena,), n=0)
         self.temb = None         # (tensor (B,T), T)
         self.temb_rows = {}      # id(resnet) -> row offset
@@ -154,8 +163,14 @@ class Builder:
         self.memset_op.n = self.gn_used * 8
 
     # ---- weights ---------------------------------------------------------------------------
+    def terms(self, W):
+        t = self.terms_of(W)
+        if CONV_KIND == _lib.OP_CONV_REF and t == 2:         # the CUDA-core restatement knows 1 and 3 only
+            t = 3
+        return t
+
     def _cached(self, key, make):
-        key = key + (PRECISION, str(self.pg.device))
+        key = key + (str(self.pg.device),)
         v = self.cache.get(key)
         if v is None:
             v = self.cache[key] = make()
@@ -165,33 +180,34 @@ class Builder:
     def f32(self, t):
         return self._cached(("f32", id(t)), lambda: t.detach().to(self.pg.device, torch.float32).contiguous())
 
-    def _planes(self, w):
-        """fp32 [taps][Cout][Cin] -> fp16 [planes][taps][Cout][Cin]; plane 1 = residual of the fp16 rounding."""
+    def _planes(self, w, terms):
+        """fp32 [taps][Cout][Cin] -> fp16 [planes][taps][Cout][Cin]; plane 1 = residual of the fp16 rounding
+        (present for terms >= 2)."""
         hi = w.to(torch.float16)
-        if not self.split:
+        if terms < 2:
             return self.pg.hold(hi.contiguous())
         lo = (w - hi.float()).to(torch.float16)
         return self.pg.hold(torch.cat([hi, lo], 0).contiguous())
 
-    def pack_conv(self, conv):
+    def pack_conv(self, conv, terms):
         def make():
             w = conv.weight.detach().to(self.pg.device, torch.float32)       # (Cout, Cin, kW, kH)
             co, ci, k0, k1 = w.shape
-            return self._planes(w.permute(2, 3, 0, 1).reshape(k0 * k1, co, ci))
-        wt = self._cached(("conv", id(conv.weight)), make)
+            return self._planes(w.permute(2, 3, 0, 1).reshape(k0 * k1, co, ci), terms)
+        wt = self._cached(("conv", id(conv.weight), min(terms, 2)), make)
         b = self.f32(conv.bias) if conv.bias is not None else None
         return wt, b
 
-    def pack_linear(self, lins):
+    def pack_linear(self, lins, terms):
         def make():
             w = torch.cat([l.weight.detach().to(self.pg.device, torch.float32) for l in lins], 0)
             b = torch.cat([l.bias.detach().to(self.pg.device, torch.float32) for l in lins], 0)
-            return self._planes(w[None]), b.contiguous()
-        return self._cached(("lin",) + tuple(id(l.weight) for l in lins), make)
+            return self._planes(w[None], terms), b.contiguous()
+        return self._cached(("lin", min(terms, 2)) + tuple(id(l.weight) for l in lins), make)
 
-    def alloc_half(self, shape):
-        """(hi, lo) fp16 operand pair; lo is None in plain-fp16 mode."""
-        return (self.pg.alloc(shape, torch.float16), self.pg.alloc(shape, torch.float16) if self.split else None)
+    def alloc_half(self, shape, terms):
+        """(hi, lo) fp16 operand pair; lo only exists for a split-fp16 x3 consumer."""
+        return (self.pg.alloc(shape, torch.float16), self.pg.alloc(shape, torch.float16) if terms == 3 else None)
 
     def free_half(self, pair):
         self.pg.free(pair[0])
@@ -213,9 +229,10 @@ class Builder:
                     p=(x0.t, x1.t if x1 is not None else None, sums))
         return sums
 
-    def prep(self, x0, x1=None, norm=None, silu=False, up=1, circular=True, also_raw=False):
+    def prep(self, x0, x1=None, norm=None, silu=False, up=1, circular=True, also_raw=False, terms=3, raw_terms=3):
         """-> fp16 operand pair in the W-padded layout (B, W*up + 2, H*up, C0+C1); also_raw=True returns a
-        second pair holding the un-normalised input (1x1 shortcut operand) written by the same launch."""
+        second pair holding the un-normalised input (1x1 shortcut operand) written by the same launch.  `terms` /
+        `raw_terms`: precision of the consuming convolutions (the lo plane is written for 3 only)."""
         c1 = x1.C if x1 is not None else 0
         C = x0.C + c1
         sums = pairs0 = pairs1 = gamma = beta = None
@@ -229,20 +246,20 @@ class Builder:
             else:
                 sums = self.gn_stats(x0, x1, G)
             gamma, beta, eps = self.f32(norm.weight), self.f32(norm.bias), norm.eps
-        out = self.alloc_half((self.B, x0.W * up + 2, x0.H * up, C))
-        raw = self.alloc_half((self.B, x0.W * up + 2, x0.H * up, C)) if also_raw else (None, None)
+        out = self.alloc_half((self.B, x0.W * up + 2, x0.H * up, C), terms)
+        raw = self.alloc_half((self.B, x0.W * up + 2, x0.H * up, C), raw_terms) if also_raw else (None, None)
         self.pg.add(_lib.OP_PREP, i=(x0.C, c1, G, int(silu), up, self.B, x0.W, x0.H, int(circular)), f=(eps,),
                     p=(x0.t, x1.t if x1 is not None else None, sums, gamma, beta, out[0], out[1], raw[0], raw[1],
                        pairs0, pairs1))
         return (out, raw) if also_raw else out
 
     def conv(self, xh, W, H, conv=None, packed=None, cin=None, cout=None, ks=3, stride=1, pad_lo=1, circular=True,
-             temb=None, residual=None, stats=False, shortcut=None):
+             temb=None, residual=None, stats=False, shortcut=None, terms=3):
         """fp16 clp operand pair -> fp32 cl Act (B,W/stride,H/stride,Cout).  stats=True: the epilogue also
         accumulates the GroupNorm moments of the output (consumed by the next prep instead of a gn_stats pass).
         shortcut=(operand pair, 1x1 conv module): that convolution is folded into the K loop of this launch."""
         if conv is not None:
-            wt, bias = self.pack_conv(conv)
+            wt, bias = self.pack_conv(conv, terms)
             cout, cin, ks = conv.out_channels, conv.in_channels, conv.kernel_size[0]
             stride, pad_lo = conv.stride[0], conv.padding[0]
             circular = bool(getattr(conv, "circular", False))
@@ -266,18 +283,18 @@ class Builder:
             sc_cin = 0
             if shortcut is not None:
                 sc_x, sc_conv = shortcut
-                sc_wt, _ = self.pack_conv(sc_conv)
+                sc_wt, _ = self.pack_conv(sc_conv, terms)
                 assert sc_conv.kernel_size == (1, 1) and sc_conv.out_channels == cout and stride == 1
                 sc_cin = sc_conv.in_channels
                 sc_ptrs = (sc_x[0], sc_x[1], sc_wt)
                 bias = self._cached(("bias_sum", id(conv.bias), id(sc_conv.bias)),
                                     lambda: (self.f32(conv.bias) + self.f32(sc_conv.bias)).contiguous())
-            ints += [sc_cin]
+            ints += [sc_cin, terms]
         else:
             assert shortcut is None
-        ws = self.splitk_ws if kind == _lib.OP_CONV_TC else None
+        assert (xh[1] is not None) == (terms == 3), "operand planes do not match the layer's precision"
         self.pg.add(kind, i=ints, p=(xh[0], wt, bias, temb_t, residual.t if residual is not None else None, out,
-                                     xh[1], st) + sc_ptrs + (ws,), n=(ws.numel() if ws is not None else 0), launches=1)
+                                     xh[1], st) + sc_ptrs, launches=1)
         return Act(out, self.B, Wo, Ho, cout, st)
 
     # ---- blocks ----------------------------------------------------------------------------
@@ -285,32 +302,33 @@ class Builder:
         """ResnetBlock2D on the virtual concat (x0 | x1) (App. A.1; `model.py:342-362`)."""
         pg = self.pg
         circ = lambda conv: bool(getattr(conv, "circular", False))
+        t = self.terms(x0.W)
         xr = None
         if rb.conv_shortcut is not None:
-            a1, xr = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1), also_raw=True)
+            a1, xr = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1), also_raw=True, terms=t, raw_terms=t)
         else:
-            a1 = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1))
+            a1 = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1), terms=t)
         temb = None
         if rb.time_emb_proj is not None and self.temb is not None:
-            t, T = self.temb
+            tt, T = self.temb
             off = self.temb_rows[id(rb)]
-            temb = (t.view(-1)[off:], T)
-        h = self.conv(a1, x0.W, x0.H, rb.conv1, temb=temb, stats=True)
+            temb = (tt.view(-1)[off:], T)
+        h = self.conv(a1, x0.W, x0.H, rb.conv1, temb=temb, stats=True, terms=t)
         self.free_half(a1)
-        a2 = self.prep(h, None, rb.norm2, silu=True, circular=circ(rb.conv2))
+        a2 = self.prep(h, None, rb.norm2, silu=True, circular=circ(rb.conv2), terms=t)
         pg.free(h.t)
         if rb.conv_shortcut is not None and CONV_KIND == _lib.OP_CONV_TC and FUSE_SHORTCUT:
             # the 1x1 conv_shortcut rides in conv2's K loop (extra K steps over the raw operand)
-            out = self.conv(a2, x0.W, x0.H, rb.conv2, stats=True, shortcut=(xr, rb.conv_shortcut))
+            out = self.conv(a2, x0.W, x0.H, rb.conv2, stats=True, shortcut=(xr, rb.conv_shortcut), terms=t)
             self.free_half(xr)
         elif rb.conv_shortcut is not None:
-            sc = self.conv(xr, x0.W, x0.H, rb.conv_shortcut)
+            sc = self.conv(xr, x0.W, x0.H, rb.conv_shortcut, terms=t)
             self.free_half(xr)
-            out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=sc, stats=True)
+            out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=sc, stats=True, terms=t)
             pg.free(sc.t)
         else:
             assert x1 is None
-            out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=x0, stats=True)
+            out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=x0, stats=True, terms=t)
         self.free_half(a2)
         pg.taps.append((rb, out))
         if free_inputs:
@@ -326,15 +344,16 @@ class Builder:
             raise NotImplementedError(f"attention head_dim {at.dim_head}: the sm_100a attention kernel implements the "
                                       "reference's attention_head_dim=8")
         C = x.C
-        a = self.prep(x, None, at.group_norm, silu=False)
-        qkv = self.conv(a, x.W, x.H, packed=self.pack_linear([at.to_q, at.to_k, at.to_v]), cin=C, cout=3 * C, ks=1,
-                        pad_lo=0)
+        t = self.terms(x.W)
+        a = self.prep(x, None, at.group_norm, silu=False, terms=t)
+        qkv = self.conv(a, x.W, x.H, packed=self.pack_linear([at.to_q, at.to_k, at.to_v], t), cin=C, cout=3 * C, ks=1,
+                        pad_lo=0, terms=t)
         self.free_half(a)
-        o = self.alloc_half((self.B, x.W + 2, x.H, C))
+        o = self.alloc_half((self.B, x.W + 2, x.H, C), t)
         pg.add(_lib.OP_ATTENTION, i=(self.B, x.W * x.H, C, x.H), p=(qkv.t, o[0], o[1]))
         pg.free(qkv.t)
-        out = self.conv(o, x.W, x.H, packed=self.pack_linear([at.to_out[0]]), cin=C, cout=C, ks=1, pad_lo=0,
-                        residual=x, stats=True)
+        out = self.conv(o, x.W, x.H, packed=self.pack_linear([at.to_out[0]], t), cin=C, cout=C, ks=1, pad_lo=0,
+                        residual=x, stats=True, terms=t)
         self.free_half(o)
         pg.taps.append((at, out))
         if free_input:
@@ -344,8 +363,9 @@ class Builder:
     def downsample(self, ds, x, free_input=True):
         """Patched Downsample2D (`ldm/utils.py:107-116`): raw cast + stride-2 conv; padding=0 is the
         VAE-encoder asymmetric pad (pad_lo = 0)."""
-        xr = self.prep(x, None, None, circular=bool(getattr(ds.conv, "circular", False)))
-        out = self.conv(xr, x.W, x.H, ds.conv, stats=True)
+        t = self.terms(x.W)
+        xr = self.prep(x, None, None, circular=bool(getattr(ds.conv, "circular", False)), terms=t)
+        out = self.conv(xr, x.W, x.H, ds.conv, stats=True, terms=t)
         self.free_half(xr)
         self.pg.taps.append((ds, out))
         if free_input:
@@ -354,8 +374,9 @@ class Builder:
 
     def upsample(self, us, x):
         """Upsample2D (`model.py:120-125`): nearest 2x folded into the cast, then 3x3 conv."""
-        xr = self.prep(x, None, None, up=2, circular=bool(getattr(us.conv, "circular", False)))
-        out = self.conv(xr, x.W * 2, x.H * 2, us.conv, stats=True)
+        t = self.terms(x.W * 2)
+        xr = self.prep(x, None, None, up=2, circular=bool(getattr(us.conv, "circular", False)), terms=t)
+        out = self.conv(xr, x.W * 2, x.H * 2, us.conv, stats=True, terms=t)
         self.free_half(xr)
         self.pg.taps.append((us, out))
         self.pg.free(x.t)
@@ -390,7 +411,7 @@ class Builder:
             self.pg.add(_lib.OP_NORM_CONV_OUT, i=(G, 1, self.B, x.W, x.H, x.C, conv.out_channels, circ), f=(norm.eps,),
                         p=(x.t, sums, pairs, self.f32(norm.weight), self.f32(norm.bias), wt, self.f32(conv.bias), out_ref))
         else:
-            a = self.prep(x, None, norm, silu=True, circular=bool(circ))
+            a = self.prep(x, None, norm, silu=True, circular=bool(circ), terms=3)
             self.pg.add(_lib.OP_CONV_OUT, i=(self.B, x.W, x.H, x.C, conv.out_channels, circ),
                         p=(a[0], wt, self.f32(conv.bias), out_ref, a[1]))
             self.free_half(a)
@@ -421,7 +442,8 @@ class UNetPlan:
         if W % (1 << (L - 1)) or H % (1 << (L - 1)):
             raise ValueError(f"sample size {(W, H)} must be divisible by {1 << (L - 1)}")
         pg = self.prog = Program(dev)
-        bd = Builder(pg, batch, groups=cfg.norm_num_groups, cache=model._packed)
+        bd = Builder(pg, batch, groups=cfg.norm_num_groups, cache=model._packed,
+                     terms_of=lambda w: PRECISION_TOP if w >= W else PRECISION)
         cin = cfg.in_channels
         self.x_in = pg.hold(torch.zeros(batch, cin - cond_channels, W, H, device=dev))
         self.cond = pg.hold(torch.zeros(batch, cond_channels, W, H, device=dev)) if cond_channels else None
@@ -507,7 +529,7 @@ class VaeDecoderPlan:
         dec = vae.decoder
         self.B = batch
         pg = self.prog = Program(dev)
-        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed)
+        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed, terms_of=lambda w: PRECISION_DEC)
         zc = vae.config.latent_channels
         n_up = sum(1 for b in dec.up_blocks if b.upsamplers is not None)
         self.z_in = pg.hold(torch.zeros(batch, zc, W, H, device=dev))
@@ -543,7 +565,7 @@ class VaeEncoderPlan:
         enc = vae.encoder
         self.B = batch
         pg = self.prog = Program(dev)
-        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed)
+        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed, terms_of=lambda w: PRECISION_DEC)
         ic = vae.config.in_channels
         n_down = sum(1 for b in enc.down_blocks if b.downsamplers is not None)
         self.x_in = pg.hold(torch.zeros(batch, ic, W, H, device=dev))

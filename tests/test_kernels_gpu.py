@@ -137,12 +137,32 @@ def test_conv_tc_matches_cuda_core_restatement_and_oracle(L, case):
     L.call("rldm_conv_tc", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out3b),
            B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, None)
     assert torch.equal(out3, out3b)
-    # split-K partial tiles exchanged through a global (L2) workspace instead of DSMEM: same summation order, same bits
-    ws = torch.empty(16 << 20, dtype=torch.uint8, device="cuda")
-    out3w = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
-    L.call("rldm_conv_tc_ws", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out3w),
-           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, None, None, None, None, 0, L.ptr(ws), ws.numel())
-    assert torch.equal(out3, out3w)
+    # explicit precision through rldm_conv_tc_ex: terms = 3 is the call above, bit for bit ...
+    out3e = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
+    L.call("rldm_conv_tc_ex", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out3e),
+           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, None, None, None, None, 0, 3)
+    assert torch.equal(out3, out3e)
+    # ... terms = 2 ("fp16x2": activations single fp16, weights hi+lo -> Xh*Wh + Xh*Wl): exact for the fp16-rounded
+    # activations and the un-rounded weights
+    out2 = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
+    st2 = torch.zeros(B, Cout // 2, 2, dtype=torch.float64, device="cuda")
+    L.call("rldm_conv_tc_ex", L.ptr(xh2), None, L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out2),
+           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, L.ptr(st2) if fused else None, None, None, None, 0, 2)
+    y2 = oracle_conv(unpadw(xh2).float().cpu().permute(0, 3, 1, 2), w, b, stride, pad_lo, ks, bool(circ)) \
+        + temb[:, :Cout, None, None] + res
+    assert relerr(ref_layout(out2.cpu()), y2) < 1e-5
+    assert relerr(ref_layout(out2.cpu()), y32) < 1e-3
+    if fused:
+        og = out2.double().reshape(B, Wo * Ho, Cout // 2, 2)
+        assert torch.allclose(st2[:, :, 0], og.sum((1, 3)), rtol=1e-5, atol=1e-3)
+    # ... terms = 1 == the legacy plain-fp16 call
+    out1 = torch.full((B, Wo, Ho, Cout), float("nan"), device="cuda")
+    L.call("rldm_conv_tc_ex", L.ptr(xh), None, L.ptr(wt), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd), L.ptr(out1),
+           B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, None, None, None, None, 0, 1)
+    assert torch.equal(out1, out_tc)
+    with pytest.raises(L.RldmError):      # x3 needs the low-order activation plane
+        L.call("rldm_conv_tc_ex", L.ptr(xh2), None, L.ptr(wt2), L.ptr(bd), None, 0, None, L.ptr(out1),
+               B, W, H, Cin, Cout, ks, stride, pad_lo, circ, split, None, None, None, None, 0, 3)
     L.call("rldm_conv_ref", L.ptr(xh2), L.ptr(xl2), L.ptr(wt2), L.ptr(bd), L.ptr(td), Cout + 8, L.ptr(rd),
            L.ptr(out3r), B, W, H, Cin, Cout, ks, stride, pad_lo, circ)
     assert relerr(out3, out3r) < 1e-5
@@ -213,37 +233,6 @@ def test_conv_tc_with_fused_shortcut(L, case):
                B, W, H, Cin, Cout, 3, 2, 1, 1, split, None, L.ptr(xh), L.ptr(xl), L.ptr(wt2), Cin2)
 
 
-@pytest.mark.parametrize("case", [(8, 256, 16, 128, 128, 1), (3, 256, 16, 128, 256, 0), (8, 512, 8, 64, 128, 1)],
-                         ids=lambda c: "x".join(map(str, c)))
-def test_conv_tc_halo_window_variant_matches_default(L, case, monkeypatch):
-    """RLDM_HALO_P=1 (opt-in experiment): persistent kernel whose A operand of the three taps of a kernel column is
-    one shared-memory window.  Same contract as the per-tap persistent kernel; only the fp32 summation order differs."""
-    B, W, H, Cin, Cout, circ = case
-    g = torch.Generator().manual_seed(7 * B + Cin)
-    x = torch.randn(B, Cin, W, H, generator=g)
-    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
-    b = torch.randn(Cout, generator=g)
-    res = torch.randn(B, Cout, W, H, generator=g)
-    xh, xl = split_half(cl(x))
-    xh, xl, wt = padw(xh, bool(circ)).cuda(), padw(xl, bool(circ)).cuda(), pack_w(w, split=True).cuda()
-    bd, rd = b.cuda(), cl(res).cuda()
-    outs, stats = [], []
-    for mode in (None, "1"):
-        if mode:
-            monkeypatch.setenv("RLDM_HALO_P", mode)
-        out = torch.full((B, W, H, Cout), float("nan"), device="cuda")
-        st = torch.zeros(B, Cout // 2, 2, dtype=torch.float64, device="cuda")
-        L.call("rldm_conv_tc", L.ptr(xh), L.ptr(xl), L.ptr(wt), L.ptr(bd), None, 0, L.ptr(rd), L.ptr(out),
-               B, W, H, Cin, Cout, 3, 1, 1, circ, 0, L.ptr(st))
-        torch.cuda.synchronize()
-        outs.append(out)
-        stats.append(st)
-    assert relerr(outs[1], outs[0]) < 2e-6
-    assert torch.allclose(stats[1], stats[0], rtol=1e-6, atol=1e-3)
-    y32 = oracle_conv(x, w, b, 1, 1, 3, bool(circ)) + res
-    assert relerr(ref_layout(outs[1].cpu()), y32) < 1e-5
-
-
 def test_conv_tc_rejects_bad_shapes(L):
     x = torch.zeros(1, 10, 8, 48, dtype=torch.half, device="cuda")
     with pytest.raises(L.RldmError):
@@ -307,16 +296,17 @@ def test_gn_stats_and_prep(L, shape):
 @pytest.mark.parametrize("shape", [(2, 64, 64), (1, 256, 128), (2, 1024, 128), (1, 40, 64), (1, 320, 64), (3, 128, 64),
                                    (1, 1024, 16), (1, 512, 256), (1, 2048, 32), (5, 1024, 64)])
 def test_attention_core(L, shape, kernel, monkeypatch):
-    """tcgen05 kernel (N a multiple of 128, <= 1024; other shapes fall through to the mma.sync kernel), the
-    mma.sync kernel (N % 64 == 0) and the CUDA-core kernel (ragged N), each forced where it applies."""
+    """Default dispatch (tcgen05 kernel for N a multiple of 128 and >= 256; other shapes fall through to the mma.sync
+    and CUDA-core kernels), the mma.sync kernel (N % 64 == 0) and the CUDA-core kernel (ragged N) forced where they apply."""
     B, N, C = shape
-    if kernel == "tcgen05":
-        monkeypatch.setenv("RLDM_ATTN_TCGEN05", "1")      # also for N < 512, where the dispatcher prefers mma.sync
-    elif kernel == "cudacore":
+    if kernel == "cudacore":
         monkeypatch.setenv("RLDM_ATTN_CUDACORE", "1")     # the ragged-N kernel, forced for every shape
     if kernel == "mma":
         monkeypatch.setenv("RLDM_ATTN_MMASYNC", "1")
+    L.lib().rldm_reload_env()                              # switches are read once; re-read after changing them
     if kernel != "tcgen05" and N > 1024:
+        monkeypatch.undo()
+        L.lib().rldm_reload_env()
         pytest.skip("large N only exercised on the tcgen05 kernel")
     g = torch.Generator().manual_seed(N)
     qkv = torch.randn(B, N, 3 * C, generator=g)
@@ -329,6 +319,8 @@ def test_attention_core(L, shape, kernel, monkeypatch):
     q, k, v = qkv.split(C, dim=-1)
     sp = lambda t: t.view(B, N, C // 8, 8).transpose(1, 2)
     y = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(B, N, C)
+    monkeypatch.undo()
+    L.lib().rldm_reload_env()
     assert relerr(out.float().cpu(), y) < 1e-3
     assert relerr((out.float() + out_lo.float()).cpu(), y) < 1e-5
 
