@@ -138,7 +138,9 @@ def timed_profile(prog, reps=5):
     every op; the stamped program is captured in a CUDA graph and replayed, so the numbers are device-side, cache-warm
     and free of host launch overhead (each includes one ~2 us stamp-kernel launch)."""
     from rangeldm_b200 import _lib
-    n = len(prog.ops)
+    if prog.arr is None:
+        prog.finalize()
+    n = len(prog.exec_ops)
     stamps = torch.zeros(n + 1, dtype=torch.int64, device=prog.device)
     lib = _lib.lib()
     run = lambda: _lib.check(lib.rldm_run_timed(prog.arr, n, stamps.data_ptr(), _lib.stream_ptr()))
@@ -161,7 +163,7 @@ def timed_profile(prog, reps=5):
 
 
 OP_NAMES = {1: "gn_stats", 2: "prep", 3: "conv_tc", 4: "conv_in", 5: "conv_out", 6: "attention", 7: "temb",
-            8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale", 12: "norm_conv_out"}
+            8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale", 12: "norm_conv_out", 13: "fused_levels"}
 
 
 def per_op_profile(sampler):
@@ -170,15 +172,17 @@ def per_op_profile(sampler):
     from rangeldm_b200 import _lib
     # (profiles the first sub-batch program: with RLDM_STREAMS=2 that is half of the per-GPU batch)
     progs = [sampler.plan.prog] + ([sampler.dec.prog] if sampler.dec is not None else [])
-    ms, cnt, flops = {}, {}, 0.0
+    ms, cnt, flops, fused_flops = {}, {}, 0.0, 0.0
     for prog in progs:
-        for op, us in zip(prog.ops, timed_profile(prog)):
+        for op, (i, j), us in zip(prog.exec_ops, prog.exec_src, timed_profile(prog)):
             k = OP_NAMES.get(op.kind, str(op.kind))
             ms[k] = ms.get(k, 0.0) + us / 1e3
             cnt[k] = cnt.get(k, 0) + 1
             if op.kind == _lib.OP_CONV_TC:
                 flops += conv_flops(op)
-    return ms, cnt, flops
+            if op.kind == _lib.OP_FUSED:          # convolutions inside a fused run of small layers
+                fused_flops += sum(conv_flops(o) for o in prog.ops[i:j] if o.kind == _lib.OP_CONV_TC)
+    return ms, cnt, flops, fused_flops
 
 
 def run_native(args):
@@ -265,7 +269,7 @@ def run_native(args):
     out = None
     if rank == 0:
         burst, sustained, hbm, src = peaks()
-        ms, cnt, flops = per_op_profile(sampler)
+        ms, cnt, flops, fused_flops = per_op_profile(sampler)
         conv_ms = ms.get("conv_tc", 0.0)
         all_ms = sum(ms.values())
         achieved = flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0

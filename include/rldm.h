@@ -189,7 +189,8 @@ int rldm_cl_to_ref(const float* src, float* dst, int B, int C, int W, int H, voi
 enum {
   RLDM_OP_GN_STATS = 1, RLDM_OP_PREP = 2, RLDM_OP_CONV_TC = 3, RLDM_OP_CONV_IN = 4,
   RLDM_OP_CONV_OUT = 5, RLDM_OP_ATTENTION = 6, RLDM_OP_TEMB = 7, RLDM_OP_SCHED_STEP = 8,
-  RLDM_OP_MEMSET = 9, RLDM_OP_CONV_REF = 10, RLDM_OP_AXPY = 11, RLDM_OP_NORM_CONV_OUT = 12
+  RLDM_OP_MEMSET = 9, RLDM_OP_CONV_REF = 10, RLDM_OP_AXPY = 11, RLDM_OP_NORM_CONV_OUT = 12,
+  RLDM_OP_FUSED = 13     /* p[0] = rldm_fused handle: a compiled run of small ops (below) */
 };
 typedef struct rldm_op {
   int32_t kind;
@@ -199,6 +200,26 @@ typedef struct rldm_op {
   int64_t n;          /* element / byte count where the entry point takes one */
 } rldm_op;
 int rldm_run(const rldm_op* ops, int n_ops, void* stream);
+
+/* ---- fused runs of small layers -------------------------------------------------------------
+ * Levels 1..n of the UNet are chains of tiny dependent ops (GroupNorm-apply passes, 3x3 / 1x1 convolutions of a few
+ * K steps, short attention).  A maximal run of consecutive PREP / CONV_TC / ATTENTION ops that rldm_fused_supported()
+ * accepts can be compiled into ONE persistent launch: all SMs walk the run phase by phase, separated by grid-wide
+ * barriers instead of kernel boundaries; barriers, TMEM and the TMA ring are set up once.  Same operand layouts and
+ * results as the stand-alone entry points up to the fp32 summation order of the K split (which is fixed:
+ * deterministic).  The launch needs every CTA resident at once: do not run two fused handles concurrently on
+ * different streams of one device.
+ *   rldm_fused_supported : 1 when the op can be part of a run
+ *   rldm_fused_ws_bytes  : bytes of split-K workspace the run needs (shared by all runs of one stream)
+ *   rldm_fused_create    : compiles the run (device-side phase table + tensor maps; synchronous, not capturable)
+ *   rldm_fused_run       : one launch, stream-ordered, CUDA-graph capturable
+ */
+typedef struct rldm_fused rldm_fused;
+int rldm_fused_supported(const rldm_op* op);
+long long rldm_fused_ws_bytes(const rldm_op* ops, int n_ops);
+int rldm_fused_create(const rldm_op* ops, int n_ops, float* ws, long long ws_bytes, rldm_fused** out);
+int rldm_fused_run(rldm_fused* h, void* stream);
+void rldm_fused_destroy(rldm_fused* h);
 /* Profiling variant: the same launches, with a one-thread kernel after every op (and one before the first) that
  * writes %globaltimer (ns) into stamps[0..n_ops]; stamps[k+1]-stamps[k] is op k's serialised, cache-warm
  * duration.  Graph-capturable.  Used by bench.py's roofline pass and scripts/, never by the sampling path. */

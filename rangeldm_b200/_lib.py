@@ -14,7 +14,7 @@ c_int, c_float, c_void_p, c_i64 = ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
 
 # kind codes of rldm_op (include/rldm.h)
 OP_GN_STATS, OP_PREP, OP_CONV_TC, OP_CONV_IN, OP_CONV_OUT, OP_ATTENTION, OP_TEMB, OP_SCHED_STEP, \
-    OP_MEMSET, OP_CONV_REF, OP_AXPY, OP_NORM_CONV_OUT = range(1, 13)
+    OP_MEMSET, OP_CONV_REF, OP_AXPY, OP_NORM_CONV_OUT, OP_FUSED = range(1, 14)
 
 
 class RldmOp(ctypes.Structure):
@@ -58,6 +58,11 @@ SIGNATURES = {
     "rldm_ref_to_cl": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rldm_cl_to_ref": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rldm_run": (c_int, [ctypes.POINTER(RldmOp), c_int, c_void_p]),
+    "rldm_fused_supported": (c_int, [ctypes.POINTER(RldmOp)]),
+    "rldm_fused_ws_bytes": (ctypes.c_longlong, [ctypes.POINTER(RldmOp), c_int]),
+    "rldm_fused_create": (c_int, [ctypes.POINTER(RldmOp), c_int, c_void_p, ctypes.c_longlong, ctypes.POINTER(c_void_p)]),
+    "rldm_fused_run": (c_int, [c_void_p, c_void_p]),
+    "rldm_fused_destroy": (None, [c_void_p]),
     "rldm_run_timed": (c_int, [ctypes.POINTER(RldmOp), c_int, c_void_p, c_void_p]),
 }
 

@@ -4,7 +4,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["conv_tc.cu", "attention_tc.cu", "ops.cu"]
+SOURCES = ["conv_tc.cu", "attention_tc.cu", "fused_levels.cu", "ops.cu"]
 OUT = os.path.join(HERE, "librldm.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

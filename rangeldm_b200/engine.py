@@ -45,14 +45,33 @@ def _terms_env(name, default):
     return _TERMS[v]
 
 
+def _terms_list_env(name, default):
+    """one setting, or a comma list per resolution level from the LATENT resolution upwards (the last entry repeats)"""
+    v = os.environ.get(name, default)
+    out = []
+    for item in v.split(","):
+        if item.strip() not in _TERMS:
+            raise ValueError(f"{name} must be a comma list of {sorted(_TERMS)}, got {v!r}")
+        out.append(_TERMS[item.strip()])
+    return out
+
+
 PRECISION = _terms_env("RLDM_PRECISION", "fp16x3")                                    # UNet levels 1..n
 PRECISION_TOP = _terms_env("RLDM_PRECISION_TOP", os.environ.get("RLDM_PRECISION", "fp16x3"))   # UNet full resolution
-PRECISION_DEC = _terms_env("RLDM_PRECISION_DEC", os.environ.get("RLDM_PRECISION", "fp16x3"))   # VAE decoder / encoder
+PRECISION_DEC = _terms_list_env("RLDM_PRECISION_DEC", os.environ.get("RLDM_PRECISION", "fp16x3"))   # VAE, per level
+
+
+def _vae_terms(w, w_latent):
+    lv = max(0, (max(w, 1) // max(w_latent, 1)).bit_length() - 1)
+    return PRECISION_DEC[min(lv, len(PRECISION_DEC) - 1)]
 # GroupNorm moments accumulated in the conv epilogue (RLDM_FUSE_STATS=0 forces the separate rldm_gn_stats pass)
 FUSE_STATS = os.environ.get("RLDM_FUSE_STATS", "1") != "0"
 # ResnetBlock2D.conv_shortcut folded into conv2's launch (RLDM_FUSE_SHORTCUT=0: separate 1x1 launch + fp32 residual)
 FUSE_SHORTCUT = os.environ.get("RLDM_FUSE_SHORTCUT", "1") != "0"
 FUSE_CONV_OUT = os.environ.get("RLDM_FUSE_CONV_OUT", "1") != "0"
+# runs of small consecutive ops (UNet levels 1..n) compiled into ONE persistent launch each (csrc/fused_levels.cu);
+# RLDM_FUSE_LEVELS=0 keeps one launch per op
+FUSE_LEVELS = os.environ.get("RLDM_FUSE_LEVELS", "1") != "0"
 
 
 def _require_cuda_device(dev, what):
@@ -63,15 +82,26 @@ def _require_cuda_device(dev, what):
 
 
 class Program:
-    def __init__(self, device):
+    """A flat list of `rldm_op` records over statically allocated buffers.  `ops` is what the builders emit (one record
+    per kernel-level operation); `finalize()` compiles maximal runs of small ops into fused persistent launches
+    (`rldm_fused_*`, include/rldm.h) and `exec_ops` / `arr` is what `run()` replays."""
+
+    def __init__(self, device, fuse=True):
         self.device = device
         self.ops = []
+        self.launches = []      # kernel launches of each op (parallel to `ops`)
         self.keep = []          # every tensor the program points into
         self._free = {}         # (nbytes) -> [tensor]
         self.arr = None
-        self.n_launch = 0
+        self.exec_ops, self.exec_launches = None, None
+        self.fuse = fuse        # False for programs that run CONCURRENTLY with others (a fused launch needs all SMs)
+        self._fused_handles = []
         self.no_reuse = os.environ.get("RLDM_NOFREE") == "1"   # debugging: keep every intermediate alive
         self.taps = []          # (module, Act) pairs recorded by the Builder (debugging / tests)
+
+    @property
+    def n_launch(self):
+        return sum(self.exec_launches if self.exec_launches is not None else self.launches)
 
     # ---- buffers ---------------------------------------------------------------------------
     def alloc(self, shape, dtype=torch.float32):
@@ -109,25 +139,84 @@ class Program:
             op.p[k] = None if v is None else (v if isinstance(v, int) else v.data_ptr())
         op.n = int(n)
         self.ops.append(op)
-        self.n_launch += launches
+        self.launches.append(launches)
         return op
+
+    def append(self, op, launches=1):
+        """Append an already built record (a patched copy of another program's op)."""
+        self.ops.append(op)
+        self.launches.append(launches)
 
     def extend(self, other):
         """Append another program's ops (sharing its buffers)."""
         self.ops.extend(other.ops)
+        self.launches.extend(other.launches)
         self.keep.append(other)
-        self.n_launch += other.n_launch
+
+    def _segments(self):
+        """Maximal runs [i, j) of consecutive ops the fused-levels kernel accepts (at least two ops, one of them a
+        convolution: a lone op gains nothing from a persistent launch)."""
+        if not (FUSE_LEVELS and self.fuse and CONV_KIND == _lib.OP_CONV_TC):
+            return []
+        lib = _lib.lib()
+        segs, i, n = [], 0, len(self.ops)
+        while i < n:
+            j = i
+            while j < n and lib.rldm_fused_supported(ctypes.byref(self.ops[j])):
+                j += 1
+            if j - i >= 2 and any(self.ops[k].kind == _lib.OP_CONV_TC for k in range(i, j)):
+                segs.append((i, j))
+            i = max(j, i + 1)
+        return segs
 
     def finalize(self):
-        self.arr = (RldmOp * len(self.ops))(*self.ops)
+        self._release_fused()
+        segs = self._segments()
+        lib = _lib.lib() if segs else None
+        ws, ws_bytes = None, 0
+        if segs and self.device.type == "cuda":
+            for i, j in segs:
+                arr = (RldmOp * (j - i))(*self.ops[i:j])
+                ws_bytes = max(ws_bytes, int(lib.rldm_fused_ws_bytes(arr, j - i)))
+            ws = self.hold(torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=self.device))
+        ex, el, src, pos = [], [], [], 0
+        for i, j in segs:
+            ex.extend(self.ops[pos:i]); el.extend(self.launches[pos:i]); src.extend((k, k + 1) for k in range(pos, i))
+            op = RldmOp()
+            op.kind = _lib.OP_FUSED
+            op.n = j - i
+            if self.device.type == "cuda":
+                arr = (RldmOp * (j - i))(*self.ops[i:j])
+                h = ctypes.c_void_p()
+                with torch.cuda.device(self.device):
+                    _lib.check(lib.rldm_fused_create(arr, j - i, ws.data_ptr(), ws_bytes, ctypes.byref(h)))
+                self._fused_handles.append(h)
+                op.p[0] = h.value
+            ex.append(op); el.append(1); src.append((i, j))
+            pos = j
+        ex.extend(self.ops[pos:]); el.extend(self.launches[pos:]); src.extend((k, k + 1) for k in range(pos, len(self.ops)))
+        self.exec_ops, self.exec_launches = ex, el
+        self.exec_src = src     # exec op k stands for ops[src[k][0]:src[k][1]]
+        self.arr = (RldmOp * len(ex))(*ex)
         return self
+
+    def _release_fused(self):
+        hs, self._fused_handles = self._fused_handles, []
+        for h in hs:
+            try:
+                _lib.lib().rldm_fused_destroy(h)
+            except Exception:      # interpreter shutdown
+                pass
+
+    def __del__(self):
+        self._release_fused()
 
     def run(self):
         if self.device.type != "cuda":
             raise RuntimeError("dry-run program (built on CPU) cannot execute: no CPU fallback")
         if self.arr is None:
             self.finalize()
-        _lib.check(_lib.lib().rldm_run(self.arr, len(self.ops), _lib.stream_ptr()))
+        _lib.check(_lib.lib().rldm_run(self.arr, len(self.exec_ops), _lib.stream_ptr()))
 
 
 class Act:
@@ -529,7 +618,7 @@ class VaeDecoderPlan:
         dec = vae.decoder
         self.B = batch
         pg = self.prog = Program(dev)
-        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed, terms_of=lambda w: PRECISION_DEC)
+        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed, terms_of=lambda w: _vae_terms(w, W))
         zc = vae.config.latent_channels
         n_up = sum(1 for b in dec.up_blocks if b.upsamplers is not None)
         self.z_in = pg.hold(torch.zeros(batch, zc, W, H, device=dev))
@@ -565,9 +654,10 @@ class VaeEncoderPlan:
         enc = vae.encoder
         self.B = batch
         pg = self.prog = Program(dev)
-        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed, terms_of=lambda w: PRECISION_DEC)
-        ic = vae.config.in_channels
         n_down = sum(1 for b in enc.down_blocks if b.downsamplers is not None)
+        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed,
+                     terms_of=lambda w: _vae_terms(w, W >> n_down))
+        ic = vae.config.in_channels
         self.x_in = pg.hold(torch.zeros(batch, ic, W, H, device=dev))
         self.out = pg.hold(torch.zeros(batch, enc.conv_out.out_channels, W >> n_down, H >> n_down, device=dev))
         h = bd.conv_in(enc.conv_in, self.x_in, ic, None, 0, W, H)

@@ -138,14 +138,14 @@ class _Trajectory:
     """One whole trajectory program for a sub-batch: N x (UNet + scheduler.step) [+ rescale + vae.decode] as a
     flat librldm program over static buffers (`latents`, `cond`, `noise`, `image`)."""
 
-    def __init__(self, unet, scheduler, vae, batch, cond_channels, replica=0):
+    def __init__(self, unet, scheduler, vae, batch, cond_channels, replica=0, fuse=True):
         dev = unet.device
         cfg = unet.config
         W, H = cfg.sample_size if not isinstance(cfg.sample_size, int) else (cfg.sample_size, cfg.sample_size)
         self.B, self.steps = batch, len(scheduler.timesteps)
         self.plan = unet.plan(batch, W, H, cond_channels, replica=replica)
         self.latents, self.cond = self.plan.x_in, self.plan.cond
-        pg = self.prog = Program(dev)
+        pg = self.prog = Program(dev, fuse=fuse)
         pg.keep += [self.plan, scheduler]
         coef = pg.hold(scheduler.coef_table(dev).clone())
         n = self.latents.numel()
@@ -170,18 +170,16 @@ class _Trajectory:
                 cp = RldmOp.from_buffer_copy(op)
                 cp.i[0] = self.steps
                 cp.p[0], cp.p[7], cp.p[8] = tvec.data_ptr(), temb_scratch.data_ptr(), temb_all.data_ptr()
-                pg.ops.append(cp)
-                pg.n_launch += 3
+                pg.append(cp, 3)
         for i in range(self.steps):
-            for op in self.plan.prog.ops:
+            for op, nl in zip(self.plan.prog.ops, self.plan.prog.launches):
                 if op.kind == _lib.OP_TEMB:
                     continue
                 cp = RldmOp.from_buffer_copy(op)
                 if cp.kind in (_lib.OP_CONV_TC, _lib.OP_CONV_REF) and cp.p[3]:
                     cp.p[3] = temb_all[i].data_ptr() + (cp.p[3] - temb_base)
                     cp.i[0] = 0                       # every image of the batch shares the step's row
-                pg.ops.append(cp)
-            pg.n_launch += self.plan.prog.n_launch - 3
+                pg.append(cp, nl)
             noise_i = self.noise[i] if (self.noise is not None and float(host_coef[i, 6]) != 0.0) else None
             pg.add(_lib.OP_SCHED_STEP, p=(coef[i], self.latents, self.plan.out,
                                           x0buf if (uses_prev and i > 0) else None, noise_i, self.latents,
@@ -218,7 +216,10 @@ class FusedSampler:
             streams -= 1
         sub = batch // streams
         self.B, self.steps = batch, len(scheduler.timesteps)
-        self.parts = [_Trajectory(unet, scheduler, vae, sub, cond_channels, replica=r) for r in range(streams)]
+        # sub-batch programs on parallel graph branches run CONCURRENTLY: no fused-levels launches there (each one
+        # needs every SM)
+        self.parts = [_Trajectory(unet, scheduler, vae, sub, cond_channels, replica=r, fuse=streams == 1)
+                      for r in range(streams)]
         self.slices = [slice(r * sub, (r + 1) * sub) for r in range(streams)]
         self.noise = self.parts[0].noise          # None for deterministic schedulers
         self.has_cond = self.parts[0].cond is not None

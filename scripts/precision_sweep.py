@@ -16,7 +16,12 @@ from oracle.make_golden import seeded
 from test_models_gpu import make_unet, make_vae
 from timeline import graphed_ms
 
-NAME = {3: "fp16x3", 2: "fp16x2", 1: "fp16"}
+class _N(dict):
+    def __getitem__(self, k):
+        return "/".join(dict.__getitem__(self, x) for x in k) if isinstance(k, tuple) else dict.__getitem__(self, k)
+
+
+NAME = _N({3: "fp16x3", 2: "fp16x2", 1: "fp16"})
 
 
 def rel(a, b):
@@ -38,10 +43,13 @@ if __name__ == "__main__":
                 (2, 2, 2), (2, 2, 1), (1, 1, 1)]
     if quick:
         settings = [(3, 3, 3), (3, 3, 1), (3, 2, 1)]
+    if "dec" in sys.argv:      # per-level decoder sweep (latent 256x16 level, 512x32 level, 1024x64 level), UNet at fp16x2
+        settings = [(2, 2, d) for d in ((3, 3, 3), (2, 3, 3), (3, 2, 3), (3, 3, 2), (1, 3, 3), (3, 1, 3), (3, 3, 1), (2, 2, 3),
+                                        (1, 1, 3), (1, 2, 3), (2, 2, 2), (1, 1, 1))] + [(1, 1, (3, 3, 3)), (1, 1, (1, 1, 3))]
     out = []
     times = {}
     for low, top, dec in settings:
-        engine.PRECISION, engine.PRECISION_TOP, engine.PRECISION_DEC = low, top, dec
+        engine.PRECISION, engine.PRECISION_TOP, engine.PRECISION_DEC = low, top, (list(dec) if isinstance(dec, tuple) else [dec])
         u.invalidate_plans(); v.invalidate_plans()
         # parity: final latent via the per-step API of a no-VAE pipeline is awkward; run the fused sampler without
         # and with the VAE

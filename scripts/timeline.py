@@ -9,7 +9,7 @@ import bench
 from rangeldm_b200 import _lib
 
 NAMES = {1: "gn_stats", 2: "prep", 3: "conv_tc", 4: "conv_in", 5: "conv_out", 6: "attention", 7: "temb",
-         8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale", 12: "norm_conv_out"}
+         8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale", 12: "norm_conv_out", 13: "fused_levels"}
 
 
 def describe(op):
@@ -20,6 +20,8 @@ def describe(op):
         return f"prep {i[6]}x{i[7]} C{i[0]}+{i[1]} up{i[4]}" + (" +raw" if op.p[7] else "")
     if op.kind == 6:
         return f"attention N{i[1]} C{i[2]}"
+    if op.kind == 13:
+        return f"fused run of {op.n} ops"
     return NAMES.get(op.kind, str(op.kind))
 
 
@@ -66,11 +68,11 @@ if __name__ == "__main__":
         us = timed_profile(prog)
         real = graphed_ms(prog)
         tot = collections.defaultdict(float); cnt = collections.Counter()
-        for op, u in zip(prog.ops, us):
+        for op, u in zip(prog.exec_ops, us):
             k = NAMES.get(op.kind, str(op.kind)); tot[k] += u; cnt[k] += 1
-        print(f"{name}: batch {B}, {len(prog.ops)} ops; graphed {real * 1e3:.0f} us; serialised+stamped sum {sum(us):.0f} us")
+        print(f"{name}: batch {B}, {len(prog.ops)} ops in {len(prog.exec_ops)} launches-nodes; graphed {real * 1e3:.0f} us; serialised+stamped sum {sum(us):.0f} us")
         for k, v in sorted(tot.items(), key=lambda x: -x[1]):
             print(f"   {k:10s} n={cnt[k]:3d} total {v:8.1f} us  avg {v / cnt[k]:6.1f}")
         if "--ops" in sys.argv:
-            for idx, (op, u) in enumerate(zip(prog.ops, us)):
+            for idx, (op, u) in enumerate(zip(prog.exec_ops, us)):
                 print(f"   {idx:3d} {u:7.1f} us  {describe(op)}")

@@ -1,0 +1,102 @@
+"""GPU tests of the fused multi-layer kernel (csrc/fused_levels.cu): a run of small ops as ONE persistent launch must
+give what the same ops give as separate launches (same operands, same arithmetic; only the fp32 summation order of
+the K split differs), and both must match the fp32 oracle."""
+import ctypes
+
+import pytest
+import torch
+
+from conftest import relerr
+from test_models_gpu import make_unet, make_vae
+
+pytestmark = pytest.mark.gpu
+
+
+def _forward_both(u, x, t, monkeypatch):
+    from rangeldm_b200 import _lib, engine
+    outs, nodes = [], []
+    for fuse in (True, False):
+        monkeypatch.setattr(engine, "FUSE_LEVELS", fuse)
+        u.invalidate_plans()
+        outs.append(u(x, t).sample)
+        prog = u.plan(x.shape[0], x.shape[2], x.shape[3]).prog
+        nodes.append((len(prog.exec_ops), sum(1 for o in prog.exec_ops if o.kind == _lib.OP_FUSED)))
+    u.invalidate_plans()
+    return outs, nodes
+
+
+def test_fused_levels_tiny_unet_matches_unfused_and_oracle(monkeypatch):
+    from oracle import nets
+    from oracle.make_golden import TINY_UNET, seeded
+    ou = seeded(nets.OracleUNet2DModel, 4321, **TINY_UNET)
+    u = make_unet(TINY_UNET, ou)
+    x = torch.randn(2, 5, 32, 8, generator=torch.Generator().manual_seed(0))
+    (a, b), nodes = _forward_both(u, x.cuda(), torch.tensor(500), monkeypatch)
+    assert nodes[0][1] >= 1 and nodes[1][1] == 0 and nodes[0][0] < nodes[1][0]
+    assert relerr(a, b, "fused_vs_unfused_tiny") < 5e-6
+    with torch.no_grad():
+        ref = ou(x, torch.tensor(500))
+    assert relerr(a, ref, "fused_tiny_vs_oracle") < 1e-4
+    # replays of the same compiled run (the grid barrier's generation word keeps counting across launches)
+    c = u(x.cuda(), torch.tensor(500)).sample
+    d = u(x.cuda(), torch.tensor(500)).sample
+    assert relerr(c, d) < 1e-6
+
+
+@pytest.mark.parametrize("batch", [8, 3, 1])
+def test_fused_levels_c3_unet_matches_unfused_and_oracle(batch, monkeypatch):
+    """BENCH shape (batch 8), a ragged batch (partial 128-pixel tiles at the 32x2 level) and a single image."""
+    from oracle import nets
+    from oracle.make_golden import seeded
+    ou = seeded(nets.OracleUNet2DModel, 0, **nets.UNET_C3)
+    u = make_unet(nets.UNET_C3, ou)
+    x = torch.randn(batch, 5, 256, 16, generator=torch.Generator().manual_seed(20 + batch))
+    t = torch.tensor([17, 500, 999, 47, 940, 3, 250, 800][:batch])
+    (a, b), nodes = _forward_both(u, x.cuda(), t, monkeypatch)
+    assert nodes[0][1] >= 3 and nodes[0][0] <= 40, nodes          # <= 40 graph nodes per forward instead of 168
+    assert relerr(a, b, f"fused_vs_unfused_c3_b{batch}") < 1e-5
+    with torch.no_grad():
+        ref = ou(x, t)
+    assert relerr(a, ref, f"fused_c3_b{batch}_vs_oracle") < 1e-3
+
+
+def test_fused_levels_reduced_precision_and_graph_replay(monkeypatch):
+    """fp16x2 / fp16 operands inside a fused run (1 or 2 weight planes, no activation lo plane), captured in a CUDA
+    graph and replayed: identical to the unfused program of the same precision up to summation order."""
+    from rangeldm_b200 import engine
+    from oracle import nets
+    from oracle.make_golden import TINY_UNET, seeded
+    ou = seeded(nets.OracleUNet2DModel, 4321, **TINY_UNET)
+    u = make_unet(TINY_UNET, ou)
+    x = torch.randn(2, 5, 32, 8, generator=torch.Generator().manual_seed(1)).cuda()
+    for terms in (2, 1):
+        monkeypatch.setattr(engine, "PRECISION", terms)
+        monkeypatch.setattr(engine, "PRECISION_TOP", terms)
+        (a, b), nodes = _forward_both(u, x, 300, monkeypatch)
+        assert nodes[0][1] >= 1
+        assert relerr(a, b, f"fused_vs_unfused_terms{terms}") < 1e-5
+        monkeypatch.setattr(engine, "FUSE_LEVELS", True)
+        u.invalidate_plans()
+        plan = u.plan(2, 32, 8)
+        plan.x_in.copy_(x); plan.t_buf.fill_(300.0)
+        plan.prog.run(); torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            plan.prog.run()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        assert relerr(plan.out, a) < 1e-6
+    u.invalidate_plans()
+
+
+def test_fused_create_rejects_unsupported_ops():
+    from rangeldm_b200 import _lib
+    from rangeldm_b200._lib import RldmOp
+    op = RldmOp()
+    op.kind = _lib.OP_SCHED_STEP
+    assert _lib.lib().rldm_fused_supported(ctypes.byref(op)) == 0
+    h = ctypes.c_void_p()
+    arr = (RldmOp * 1)(op)
+    assert _lib.lib().rldm_fused_create(arr, 1, None, 0, ctypes.byref(h)) != 0 and not h.value
+    assert b"cannot run inside a fused segment" in _lib.lib().rldm_last_error()
