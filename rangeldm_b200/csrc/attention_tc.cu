@@ -88,6 +88,10 @@ __device__ __forceinline__ float at_max32(const uint32_t (&r)[32]) {
 // P = 2^(S - m) for the 32 keys of one chunk as split fp16, written over the chunk's own 32 columns (16 columns of
 // P_hi followed by 16 of P_lo), with packed fp32 arithmetic (add.f32x2 / fma.f32x2: two lanes per issue slot -- the
 // kernel is bound by instruction issue as much as by MUFU); the row sum comes from the MMA (ones row of V^T).
+// PLO = false (the consuming projection runs below split-fp16 x3 precision): P is kept as ONE fp16 plane -- no
+// residual arithmetic, half the TMEM stores and half the P V MMAs; a probability rounded to 11 bits is averaged over
+// hundreds of keys.
+template <bool PLO>
 __device__ __forceinline__ void at_exp_store32_packed(const uint32_t (&r)[32], float m, uint32_t t_chunk) {
   uint32_t h[16], lo[16];
   const float2 nm = make_float2(-m, -m), neg1 = make_float2(-1.f, -1.f);
@@ -96,12 +100,14 @@ __device__ __forceinline__ void at_exp_store32_packed(const uint32_t (&r)[32], f
     const float2 d = __fadd2_rn(make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), nm);
     const float2 p = make_float2(at_ex2(d.x), at_ex2(d.y));
     const __half2 hh = __floats2half2_rn(p.x, p.y);
-    const float2 res = __ffma2_rn(__half22float2(hh), neg1, p);       // p - float(hi): exact
     h[e] = at_pack(hh);
-    lo[e] = at_pack(__floats2half2_rn(res.x, res.y));
+    if (PLO) {
+      const float2 res = __ffma2_rn(__half22float2(hh), neg1, p);       // p - float(hi): exact
+      lo[e] = at_pack(__floats2half2_rn(res.x, res.y));
+    }
   }
   tmem_st_32x16(t_chunk, h);
-  tmem_st_32x16(t_chunk + 16, lo);
+  if (PLO) tmem_st_32x16(t_chunk + 16, lo);
 }
 __device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
   uint32_t r;
@@ -167,6 +173,7 @@ struct AttnPipeSmem {
   uint32_t pad;
 };
 
+template <bool PLO>
 __global__ void __launch_bounds__(kApThreads, 2)
 attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half* __restrict__ out_lo, int N,
                                 int C, int H, int B) {
@@ -357,7 +364,7 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
         const uint32_t p_tm = tmem + bs * kApKT;
         const uint64_t v_desc0 = umma_desc_sw128(sV_a + slot * kApVBytes);
 #pragma unroll
-        for (int part = 0; part < 2; ++part) {
+        for (int part = 0; part < (PLO ? 2 : 1); ++part) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)                   // K step = 16 keys = 8 columns of chunk ks / 2
             umma_f16_ts(d, p_tm + (ks >> 1) * 32 + part * 16 + (ks & 1) * 8, v_desc0 + 2 * ks, idesc_o, (part | ks) != 0);
@@ -455,10 +462,10 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
       tmem_ld_32x32(t_s + 32, r);
       tmem_ld_wait();
       m = fmaxf(m, at_max32(r));
-      at_exp_store32_packed(r, m, t_s + 32);               // P = 2^(S - m) in place: [hi 16 | lo 16] per 32-key chunk
+      at_exp_store32_packed<PLO>(r, m, t_s + 32);               // P = 2^(S - m) in place: [hi 16 | lo 16] per 32-key chunk
       tmem_ld_32x32(t_s, r);
       tmem_ld_wait();
-      at_exp_store32_packed(r, m, t_s);
+      at_exp_store32_packed<PLO>(r, m, t_s);
       tmem_st_wait();
       // the group's previous tile has long finished its P V; its slot is overwritten by P V of this tile, which is
       // issued only after the arrival below
@@ -506,14 +513,21 @@ int rldm_attention_umma(const float* qkv, uint16_t* out, uint16_t* out_lo, int B
                         sizeof(AttnPipeSmem);
   static bool attr_p = false;
   if (!attr_p) {
-    RLDM_CUDA(cudaFuncSetAttribute(attention_umma_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RLDM_CUDA(cudaFuncSetAttribute(attention_umma_pipelined_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem_p)));
+    RLDM_CUDA(cudaFuncSetAttribute(attention_umma_pipelined_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(smem_p)));
     attr_p = true;
   }
   const int items_p = B * (C / 8) * T;
   const int ctas_p = items_p < 2 * n_sms_p ? items_p : 2 * n_sms_p;      // two persistent CTAs per SM
-  RLDM_CUDA(launch_pdl(attention_umma_pipelined_kernel, dim3(ctas_p), dim3(kApThreads), smem_p, as_stream(stream), qkv,
-                       reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H, B));
+  // out_lo == NULL: the consumer takes single-fp16 activations, so P is carried as one fp16 plane as well
+  if (out_lo)
+    RLDM_CUDA(launch_pdl(attention_umma_pipelined_kernel<true>, dim3(ctas_p), dim3(kApThreads), smem_p, as_stream(stream), qkv,
+                         reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H, B));
+  else
+    RLDM_CUDA(launch_pdl(attention_umma_pipelined_kernel<false>, dim3(ctas_p), dim3(kApThreads), smem_p, as_stream(stream), qkv,
+                         reinterpret_cast<__half*>(out), nullptr, N, C, H, B));
   RLDM_LAUNCH_CHECK();
   return 0;
 }

@@ -86,26 +86,46 @@ __device__ __forceinline__ bool elect_one_leader(int& leader) {
 // Grid-wide barrier of `nblocks` co-resident CTAs.  bar[0] = arrival count (reset by the last arriver), bar[1] =
 // generation (only ever incremented, so the pair is consistent across launches and CUDA-graph replays).  A lost
 // arrival traps after ~2 s instead of hanging the GPU.
+// The arrival is ONE acq_rel atomic (its release half publishes the CTA's writes, ordered before it by bar.sync), the
+// wait polls with RELAXED loads (an acquire load per poll would invalidate L1 on every iteration) and takes a single
+// acquire fence once the generation has moved.  MODE 0 (RLDM_FUSE_BAR=0, for comparison): seq_cst __threadfence()
+// around a relaxed atomic and acquire polling.
+template <int MODE>
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks, unsigned& gen) {
   fence_proxy_async_all();            // this thread's generic writes -> later TMA (async proxy) reads of other CTAs
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned old = atomicAdd(&bar[0], 1u);
-    if (old == nblocks - 1) {
-      bar[0] = 0u;
+    unsigned old;
+    if (MODE == 0) {
       __threadfence();
-      atomicAdd(&bar[1], 1u);
+      old = atomicAdd(&bar[0], 1u);
+    } else {
+      asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
+    }
+    if (old == nblocks - 1) {
+      if (MODE == 0) {
+        bar[0] = 0u;
+        __threadfence();
+        atomicAdd(&bar[1], 1u);
+      } else {
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar + 1) : "memory");
+      }
     } else {
       const long long t0 = clock64();
-      while (ld_acquire_u32(&bar[1]) == gen) {
+      for (;;) {
+        unsigned v;
+        if (MODE == 0) v = ld_acquire_u32(&bar[1]);
+        else asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar + 1) : "memory");
+        if (v != gen) break;
         if (clock64() - t0 > 4000000000ll) {
           printf("rldm: grid barrier timeout block %d gen %u\n", blockIdx.x, gen);
           __trap();
         }
       }
     }
-    __threadfence();
+    if (MODE == 0) __threadfence();
+    else asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   ++gen;
   __syncthreads();
@@ -279,8 +299,18 @@ __device__ __forceinline__ void conv_fin_phase(const FConv& c, float* red) {
   }
 }
 
+__device__ __forceinline__ unsigned long long global_timer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// dbg (profiling aid, normally NULL): CTA 0 writes %globaltimer at [3p] phase start, [3p+1] its work done, [3p+2]
+// grid barrier passed
+template <int BAR_MODE>
 __global__ void __launch_bounds__(kFThreads, 1)
-fused_levels_kernel(const FPhase* __restrict__ phases, int n_phases, const CUtensorMap* __restrict__ maps, unsigned* bar) {
+fused_levels_kernel(const FPhase* __restrict__ phases, int n_phases, const CUtensorMap* __restrict__ maps, unsigned* bar,
+                    unsigned long long* dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kFStages * kFStageBytes);
@@ -317,6 +347,8 @@ fused_levels_kernel(const FPhase* __restrict__ phases, int n_phases, const CUten
       for (int i = threadIdx.x; i < static_cast<int>(sizeof(FPhase) / 4); i += kFThreads) dst[i] = __ldg(src + i);
     }
     __syncthreads();
+    const bool stamp = dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    if (stamp) dbg[3 * pi] = global_timer();
     const int kind = ph_s.kind;
     if (kind == F_PREP) {
       const int nvb = ph_s.prep.vgx * ph_s.prep.vgy;
@@ -340,7 +372,12 @@ fused_levels_kernel(const FPhase* __restrict__ phases, int n_phases, const CUten
                                    reinterpret_cast<__half*>(smem) + half * kAtSmemHalves, t128, 2 + half);
       }
     }
-    grid_barrier(bar, gridDim.x, gen);
+    if (dbg != nullptr) {
+      __syncthreads();
+      if (stamp) dbg[3 * pi + 1] = global_timer();
+    }
+    grid_barrier<BAR_MODE>(bar, gridDim.x, gen);
+    if (stamp) dbg[3 * pi + 2] = global_timer();
   }
   tc_fence_before();
   __syncthreads();
@@ -368,6 +405,8 @@ static EncodeTiledFn fused_get_encode() {
 }
 
 struct rldm_fused {
+  unsigned long long* dbg = nullptr;
+  std::vector<int> phase_kinds;
   FPhase* d_phases = nullptr;
   CUtensorMap* d_maps = nullptr;
   unsigned* d_bar = nullptr;
@@ -576,6 +615,7 @@ extern "C" int rldm_fused_create(const rldm_op* ops, int n_ops, float* ws, long 
     }
   }
   rldm_fused* h = new rldm_fused();
+  for (const FPhase& ph : phases) h->phase_kinds.push_back(ph.kind);
   h->n_phases = static_cast<int>(phases.size());
   h->n_ops = n_ops;
   h->grid = n_sms;
@@ -595,18 +635,28 @@ extern "C" int rldm_fused_create(const rldm_op* ops, int n_ops, float* ws, long 
   return 0;
 }
 
+// profiling aids (not part of include/rldm.h): per-phase device timestamps of CTA 0 (3 per phase) and the phase kinds
+extern "C" int rldm_fused_debug(rldm_fused* h, unsigned long long* dev_buf) { h->dbg = dev_buf; return h->n_phases; }
+extern "C" int rldm_fused_phase_kind(rldm_fused* h, int k) { return (k >= 0 && k < h->n_phases) ? h->phase_kinds[k] : -1; }
+
 extern "C" int rldm_fused_run(rldm_fused* h, void* stream) {
   RLDM_CHECK(h != nullptr, "fused_run: NULL handle");
-  static int max_ctas = -1;
+  static int max_ctas = -1, bar_mode = 1;
   if (max_ctas < 0) {
-    RLDM_CUDA(cudaFuncSetAttribute(fused_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
+    const char* e = getenv("RLDM_FUSE_BAR");
+    bar_mode = e ? atoi(e) : 1;
+    RLDM_CUDA(cudaFuncSetAttribute(fused_levels_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
+    RLDM_CUDA(cudaFuncSetAttribute(fused_levels_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
     int per_sm = 0;
-    RLDM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_levels_kernel, kFThreads, kFSmem));
+    RLDM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_levels_kernel<1>, kFThreads, kFSmem));
     max_ctas = per_sm * env().n_sms;
   }
   // the grid barrier needs every CTA resident at once
   RLDM_CHECK(h->grid <= max_ctas, "fused_run: %d CTAs cannot be co-resident (limit %d)", h->grid, max_ctas);
-  fused_levels_kernel<<<h->grid, kFThreads, kFSmem, as_stream(stream)>>>(h->d_phases, h->n_phases, h->d_maps, h->d_bar);
+  if (bar_mode == 0)
+    fused_levels_kernel<0><<<h->grid, kFThreads, kFSmem, as_stream(stream)>>>(h->d_phases, h->n_phases, h->d_maps, h->d_bar, h->dbg);
+  else
+    fused_levels_kernel<1><<<h->grid, kFThreads, kFSmem, as_stream(stream)>>>(h->d_phases, h->n_phases, h->d_maps, h->d_bar, h->dbg);
   RLDM_LAUNCH_CHECK();
   return 0;
 }

@@ -61,7 +61,16 @@ PRECISION_TOP = _terms_env("RLDM_PRECISION_TOP", os.environ.get("RLDM_PRECISION"
 PRECISION_DEC = _terms_list_env("RLDM_PRECISION_DEC", os.environ.get("RLDM_PRECISION", "fp16x3"))   # VAE, per level
 
 
-def _vae_terms(w, w_latent):
+# experiments: {block index: terms} overrides by running block number inside a plan (resnet / attention / down- /
+# upsampler, in build order), e.g. RLDM_PRECISION_BLOCKS="dec:12=3,11=3" (scripts/precision_sweep.py blocks)
+PRECISION_BLOCKS = {}
+for _item in filter(None, os.environ.get("RLDM_PRECISION_BLOCKS", "").replace("dec:", "").split(",")):
+    PRECISION_BLOCKS[int(_item.split("=")[0])] = int(_item.split("=")[1])
+
+
+def _vae_terms(w, w_latent, block=None):
+    if block in PRECISION_BLOCKS:
+        return PRECISION_BLOCKS[block]
     lv = max(0, (max(w, 1) // max(w_latent, 1)).bit_length() - 1)
     return PRECISION_DEC[min(lv, len(PRECISION_DEC) - 1)]
 # GroupNorm moments accumulated in the conv epilogue (RLDM_FUSE_STATS=0 forces the separate rldm_gn_stats pass)
@@ -69,9 +78,11 @@ FUSE_STATS = os.environ.get("RLDM_FUSE_STATS", "1") != "0"
 # ResnetBlock2D.conv_shortcut folded into conv2's launch (RLDM_FUSE_SHORTCUT=0: separate 1x1 launch + fp32 residual)
 FUSE_SHORTCUT = os.environ.get("RLDM_FUSE_SHORTCUT", "1") != "0"
 FUSE_CONV_OUT = os.environ.get("RLDM_FUSE_CONV_OUT", "1") != "0"
-# runs of small consecutive ops (UNet levels 1..n) compiled into ONE persistent launch each (csrc/fused_levels.cu);
-# RLDM_FUSE_LEVELS=0 keeps one launch per op
-FUSE_LEVELS = os.environ.get("RLDM_FUSE_LEVELS", "1") != "0"
+# RLDM_FUSE_LEVELS=1 (experiment, default off): runs of small consecutive ops (UNet levels 1..n) compiled into ONE
+# persistent launch each (csrc/fused_levels.cu).  Correct (tests/test_fused_gpu.py) but measured SLOWER on B200: a
+# grid-wide barrier costs 2.0-2.3 us against ~3 us for a PDL kernel boundary, and every convolution needs two of them
+# (K-slice reduction, then GroupNorm moments): UNet forward 1.87 -> 2.97 ms (profiles/fused_levels_timeline_r2.txt).
+FUSE_LEVELS = os.environ.get("RLDM_FUSE_LEVELS", "0") == "1"
 
 
 def _require_cuda_device(dev, what):
@@ -237,8 +248,10 @@ class Builder:
 
     def __init__(self, prog, batch, max_gn=4096, groups=32, cache=None, terms_of=None):
         self.cache = cache if cache is not None else {}      # packed weights shared between plans of a model
-        # terms_of(W) -> 1 | 2 | 3: operand precision of a convolution whose INPUT grid is W columns wide
-        self.terms_of = terms_of if terms_of is not None else (lambda W: PRECISION)
+        # terms_of(W, block) -> 1 | 2 | 3: operand precision of a convolution whose INPUT grid is W columns wide
+        # (block = running number of the resnet / attention / resampling block being built)
+        self.terms_of = terms_of if terms_of is not None else (lambda W, block=None: PRECISION)
+        self.block = -1
         self.pg = prog
         self.B = batch
         self.groups = groups
@@ -253,7 +266,8 @@ class Builder:
 
     # ---- weights ---------------------------------------------------------------------------
     def terms(self, W):
-        t = self.terms_of(W)
+        self.block += 1
+        t = self.terms_of(W, self.block)
         if CONV_KIND == _lib.OP_CONV_REF and t == 2:         # the CUDA-core restatement knows 1 and 3 only
             t = 3
         return t
@@ -532,7 +546,7 @@ class UNetPlan:
             raise ValueError(f"sample size {(W, H)} must be divisible by {1 << (L - 1)}")
         pg = self.prog = Program(dev)
         bd = Builder(pg, batch, groups=cfg.norm_num_groups, cache=model._packed,
-                     terms_of=lambda w: PRECISION_TOP if w >= W else PRECISION)
+                     terms_of=lambda w, block=None: PRECISION_TOP if w >= W else PRECISION)
         cin = cfg.in_channels
         self.x_in = pg.hold(torch.zeros(batch, cin - cond_channels, W, H, device=dev))
         self.cond = pg.hold(torch.zeros(batch, cond_channels, W, H, device=dev)) if cond_channels else None
@@ -618,7 +632,7 @@ class VaeDecoderPlan:
         dec = vae.decoder
         self.B = batch
         pg = self.prog = Program(dev)
-        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed, terms_of=lambda w: _vae_terms(w, W))
+        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed, terms_of=lambda w, block=None: _vae_terms(w, W, block))
         zc = vae.config.latent_channels
         n_up = sum(1 for b in dec.up_blocks if b.upsamplers is not None)
         self.z_in = pg.hold(torch.zeros(batch, zc, W, H, device=dev))
@@ -656,7 +670,7 @@ class VaeEncoderPlan:
         pg = self.prog = Program(dev)
         n_down = sum(1 for b in enc.down_blocks if b.downsamplers is not None)
         bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed,
-                     terms_of=lambda w: _vae_terms(w, W >> n_down))
+                     terms_of=lambda w, block=None: _vae_terms(w, W >> n_down))
         ic = vae.config.in_channels
         self.x_in = pg.hold(torch.zeros(batch, ic, W, H, device=dev))
         self.out = pg.hold(torch.zeros(batch, enc.conv_out.out_channels, W >> n_down, H >> n_down, device=dev))

@@ -46,6 +46,35 @@ if __name__ == "__main__":
     if "dec" in sys.argv:      # per-level decoder sweep (latent 256x16 level, 512x32 level, 1024x64 level), UNet at fp16x2
         settings = [(2, 2, d) for d in ((3, 3, 3), (2, 3, 3), (3, 2, 3), (3, 3, 2), (1, 3, 3), (3, 1, 3), (3, 3, 1), (2, 2, 3),
                                         (1, 1, 3), (1, 2, 3), (2, 2, 2), (1, 1, 1))] + [(1, 1, (3, 3, 3)), (1, 1, (1, 1, 3))]
+    if "blocks" in sys.argv:
+        # decoder sensitivity by block (mid 0-1, up0 res 2-4 + upsampler 5, up1 res 6-8 + upsampler 9, up2 res 10-12):
+        # everything plain fp16 except ONE block (or a tail of blocks) at fp16x3; decoder-only error on the oracle latent
+        rows = []
+        z = (ref_lat / ov.scaling_factor).cuda()
+
+        def run(blocks, base):
+            engine.PRECISION_DEC = [base]
+            engine.PRECISION_BLOCKS.clear()
+            engine.PRECISION_BLOCKS.update(blocks)
+            v.invalidate_plans()
+            e = rel(v.decode(z).sample, ref_img)
+            d = v.decoder_plan(8, 256, 16)
+            d.z_in.normal_()
+            t = graphed_ms(d.prog) * 1e3
+            v.invalidate_plans(); torch.cuda.empty_cache()
+            return e, t
+        for base, other in ((1, 3), (3, 1), (2, 3), (3, 2)):
+            for k in [None] + list(range(13)):
+                e, t = run({} if k is None else {k: other}, base)
+                rows.append({"base": NAME[base], "block": k, "block_terms": NAME[other], "decoder_only_relerr": e, "decoder_us_b8": round(t, 1)})
+                print(json.dumps(rows[-1]), flush=True)
+        for n_tail in range(1, 8):
+            e, t = run({k: 3 for k in range(13 - n_tail, 13)}, 1)
+            rows.append({"base": "fp16", "tail_blocks_fp16x3": n_tail, "decoder_only_relerr": e, "decoder_us_b8": round(t, 1)})
+            print(json.dumps(rows[-1]), flush=True)
+        engine.PRECISION_BLOCKS.clear()
+        json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "precision_blocks.json"), "w"), indent=1)
+        sys.exit(0)
     out = []
     times = {}
     for low, top, dec in settings:

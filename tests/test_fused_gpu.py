@@ -62,19 +62,26 @@ def test_fused_levels_c3_unet_matches_unfused_and_oracle(batch, monkeypatch):
 
 def test_fused_levels_reduced_precision_and_graph_replay(monkeypatch):
     """fp16x2 / fp16 operands inside a fused run (1 or 2 weight planes, no activation lo plane), captured in a CUDA
-    graph and replayed: identical to the unfused program of the same precision up to summation order."""
+    graph and replayed.  With single-fp16 activations the summation-order noise of the K split (1e-7) flips the odd
+    fp16 rounding of an activation (2^-11 of that element), so fused and unfused programs agree to ~1e-4 rather than to
+    1e-6; both stay inside the tolerance against the fp32 oracle.  (The bit-level check of the reduced-precision conv
+    path is test_fused_conv_matches_standalone_conv below.)"""
     from rangeldm_b200 import engine
     from oracle import nets
     from oracle.make_golden import TINY_UNET, seeded
     ou = seeded(nets.OracleUNet2DModel, 4321, **TINY_UNET)
     u = make_unet(TINY_UNET, ou)
-    x = torch.randn(2, 5, 32, 8, generator=torch.Generator().manual_seed(1)).cuda()
+    x = torch.randn(2, 5, 32, 8, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ref = ou(x, torch.tensor(300))
+    x = x.cuda()
     for terms in (2, 1):
         monkeypatch.setattr(engine, "PRECISION", terms)
         monkeypatch.setattr(engine, "PRECISION_TOP", terms)
         (a, b), nodes = _forward_both(u, x, 300, monkeypatch)
         assert nodes[0][1] >= 1
-        assert relerr(a, b, f"fused_vs_unfused_terms{terms}") < 1e-5
+        assert relerr(a, b, f"fused_vs_unfused_terms{terms}") < 2e-3
+        assert relerr(a, ref, f"fused_terms{terms}_vs_oracle") < 1e-3 and relerr(b, ref) < 1e-3
         monkeypatch.setattr(engine, "FUSE_LEVELS", True)
         u.invalidate_plans()
         plan = u.plan(2, 32, 8)
@@ -88,6 +95,58 @@ def test_fused_levels_reduced_precision_and_graph_replay(monkeypatch):
         torch.cuda.synchronize()
         assert relerr(plan.out, a) < 1e-6
     u.invalidate_plans()
+
+
+FUSED_CONV_CASES = [
+    # B, W, H, Cin, Cout, ks, stride, residual, temb
+    (8, 32, 2, 256, 256, 3, 1, True, True),      # level 3 of C3: 64-pixel images, two per tile, K split 12 ways
+    (3, 32, 2, 512, 256, 3, 1, False, False),    # ragged batch: partial last tile
+    (2, 64, 4, 128, 256, 3, 1, False, True),
+    (8, 128, 8, 128, 128, 3, 2, False, False),   # Downsample2D: stride 2 -> 64x4
+    (8, 64, 4, 256, 768, 1, 1, False, False),    # qkv projection
+    (8, 128, 8, 128, 128, 1, 1, True, False),    # out projection + residual at level 1
+]
+
+
+@pytest.mark.parametrize("terms", [3, 2, 1])
+@pytest.mark.parametrize("case", FUSED_CONV_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_fused_conv_matches_standalone_conv(case, terms):
+    """[raw-cast prep, conv] as one fused run against the same two ops as separate launches: identical fp16 operands on
+    both sides, so the outputs agree to fp32 summation order and the GroupNorm moments to 1e-6, for every operand
+    precision, with bias + time embedding + residual in the epilogue."""
+    import rangeldm_b200 as R
+    from rangeldm_b200 import engine, models
+    B, W, H, Cin, Cout, ks, stride, use_res, use_temb = case
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    conv = models.LoRACompatibleConv(Cin, Cout, ks, stride=stride, padding=ks // 2).to(dev)
+    conv.circular = True
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (Cin * ks * ks) ** 0.5)
+        conv.bias.copy_(torch.randn(Cout, generator=g))
+    x = torch.randn(B, W, H, Cin, generator=g).to(dev)
+    Wo, Ho = W // stride, H // stride
+    res = torch.randn(B, Wo, Ho, Cout, generator=g).to(dev)
+    temb = torch.randn(B, Cout + 16, generator=g).to(dev)
+    outs = []
+    for fuse in (True, False):
+        pg = engine.Program(dev, fuse=fuse)
+        bd = engine.Builder(pg, B, cache={}, terms_of=lambda w, block=None: terms)
+        xa = engine.Act(pg.hold(x.clone()), B, W, H, Cin)
+        ra = engine.Act(pg.hold(res.clone()), B, Wo, Ho, Cout) if use_res else None
+        a = bd.prep(xa, None, None, terms=terms)
+        out = bd.conv(a, W, H, conv, temb=(temb, Cout + 16) if use_temb else None, residual=ra, stats=True, terms=terms)
+        bd.finish()
+        pg.finalize()
+        assert sum(1 for o in pg.exec_ops if o.kind == R._lib.OP_FUSED) == (1 if fuse else 0)
+        for _ in range(2):          # second run: memset + barrier generation carry over
+            pg.run()
+        torch.cuda.synchronize()
+        outs.append((out.t.clone(), out.stats.clone() if out.stats is not None else None, pg))
+    (fa, fs, _), (ua, us, _) = outs
+    assert relerr(fa, ua, f"fused_conv_vs_standalone_terms{terms}") < 2e-6
+    if fs is not None:
+        assert torch.allclose(fs, us, rtol=1e-6, atol=1e-3)
 
 
 def test_fused_create_rejects_unsupported_ops():

@@ -124,10 +124,17 @@ def test_dry_run_plans_and_fused_program_launch_counts(monkeypatch):
     assert kinds.count(_lib.OP_CONV_TC) == 82 and kinds.count(_lib.OP_ATTENTION) == 16
     assert kinds.count(_lib.OP_CONV_IN) == 1 and kinds.count(_lib.OP_NORM_CONV_OUT) == 1 and kinds[0] == _lib.OP_MEMSET
     assert kinds.count(_lib.OP_GN_STATS) == 0          # every GroupNorm reads moments fused into a producing epilogue
-    # 135 small ops of levels 1-3 run as 5 fused persistent launches between the five N = 1024 attention kernels
+    assert [op.kind for op in plan.prog.exec_ops] == kinds and plan.prog.n_launch == len(kinds) + 2   # temb = 3 launches
+    # opt-in experiment (RLDM_FUSE_LEVELS=1): 135 small ops of levels 1-3 as 5 fused persistent launches between the
+    # five N = 1024 attention kernels
+    from rangeldm_b200 import engine
+    monkeypatch.setattr(engine, "FUSE_LEVELS", True)
+    plan.prog.finalize()
     ex = [op.kind for op in plan.prog.exec_ops]
     assert ex.count(_lib.OP_FUSED) == 5 and len(ex) <= 40 and sum(op.n for op in plan.prog.exec_ops if op.kind == _lib.OP_FUSED) == 135
-    assert plan.prog.n_launch == len(ex) + 2           # (+2: the time embedding is three launches)
+    assert plan.prog.n_launch == len(ex) + 2
+    monkeypatch.setattr(engine, "FUSE_LEVELS", False)
+    plan.prog.finalize()
     sch = R.DPMSolverMultistepScheduler(timestep_spacing="leading")
     sch.set_timesteps(20)
     v = R.AutoencoderKL(in_channels=2, out_channels=2, down_block_types=["DownEncoderBlock2D"] * 3,

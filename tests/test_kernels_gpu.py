@@ -319,10 +319,15 @@ def test_attention_core(L, shape, kernel, monkeypatch):
     q, k, v = qkv.split(C, dim=-1)
     sp = lambda t: t.view(B, N, C // 8, 8).transpose(1, 2)
     y = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(B, N, C)
+    # single-plane output (the consumer runs below split-fp16 x3): the tcgen05 kernel then carries P as one fp16 plane
+    outp1 = torch.zeros_like(outp)
+    L.call("rldm_attention", L.ptr(qd), L.ptr(outp1), None, B, N, C, Hh)
+    out1 = unpadw(outp1).reshape(B, N, C)
     monkeypatch.undo()
     L.lib().rldm_reload_env()
     assert relerr(out.float().cpu(), y) < 1e-3
     assert relerr((out.float() + out_lo.float()).cpu(), y) < 1e-5
+    assert relerr(out1.float().cpu(), y) < 1e-3
 
 
 @pytest.mark.parametrize("rows", [3, 20, 37])
