@@ -32,9 +32,16 @@ CONV_KIND = _lib.OP_CONV_TC
 #   2 "fp16x2": activations single fp16, weights hi+lo: Xh*Wh + Xh*Wl.  No low-order activation plane exists: the
 #               producer pass writes, and the conv reads, half the operand bytes; 2/3 of the tensor work.
 #   1 "fp16":   plain fp16 operands (1 MMA per K step).
-# Errors of the 20-step UNet loop compound, the VAE decoder runs once: the defaults below are the measured Pareto
-# choice (parity table); RLDM_PRECISION / _TOP / _DEC override the UNet lower levels, the UNet
-# full-resolution level and the VAE.
+# Two classes of convolutions (measured: profiles/precision_blocks_r2.json):
+#   * STREAM convolutions carry the whole residual stream through their operand: the resamplers (Downsample2D /
+#     Upsample2D convs) and a ResnetBlock2D's conv2 when its 1x1 conv_shortcut is folded into it.  An fp16-rounded
+#     operand there puts 2^-11 relative noise on the signal itself: each such block alone costs 2.6-3.3e-4 of parity in
+#     the VAE decoder.  They stay at fp16x3.
+#   * BRANCH convolutions (conv1, conv2 of identity-shortcut blocks, attention projections) produce an increment that is
+#     ADDED to the fp32 stream: rounding their operands perturbs only the increment.  Plain fp16 on all of them moves
+#     the decoder's parity from 4.8e-6 to <1e-5 and the 20-step UNet latent to ~4e-5, and removes 2/3 of their tensor
+#     work and half of their operand bytes.
+# RLDM_PRECISION (branch) / RLDM_PRECISION_STREAM override the defaults.
 _TERMS = {"fp16x3": 3, "fp16x2": 2, "fp16": 1}
 
 
@@ -45,34 +52,8 @@ def _terms_env(name, default):
     return _TERMS[v]
 
 
-def _terms_list_env(name, default):
-    """one setting, or a comma list per resolution level from the LATENT resolution upwards (the last entry repeats)"""
-    v = os.environ.get(name, default)
-    out = []
-    for item in v.split(","):
-        if item.strip() not in _TERMS:
-            raise ValueError(f"{name} must be a comma list of {sorted(_TERMS)}, got {v!r}")
-        out.append(_TERMS[item.strip()])
-    return out
-
-
-PRECISION = _terms_env("RLDM_PRECISION", "fp16x3")                                    # UNet levels 1..n
-PRECISION_TOP = _terms_env("RLDM_PRECISION_TOP", os.environ.get("RLDM_PRECISION", "fp16x3"))   # UNet full resolution
-PRECISION_DEC = _terms_list_env("RLDM_PRECISION_DEC", os.environ.get("RLDM_PRECISION", "fp16x3"))   # VAE, per level
-
-
-# experiments: {block index: terms} overrides by running block number inside a plan (resnet / attention / down- /
-# upsampler, in build order), e.g. RLDM_PRECISION_BLOCKS="dec:12=3,11=3" (scripts/precision_sweep.py blocks)
-PRECISION_BLOCKS = {}
-for _item in filter(None, os.environ.get("RLDM_PRECISION_BLOCKS", "").replace("dec:", "").split(",")):
-    PRECISION_BLOCKS[int(_item.split("=")[0])] = int(_item.split("=")[1])
-
-
-def _vae_terms(w, w_latent, block=None):
-    if block in PRECISION_BLOCKS:
-        return PRECISION_BLOCKS[block]
-    lv = max(0, (max(w, 1) // max(w_latent, 1)).bit_length() - 1)
-    return PRECISION_DEC[min(lv, len(PRECISION_DEC) - 1)]
+PRECISION = _terms_env("RLDM_PRECISION", "fp16")                     # branch convolutions and projections
+PRECISION_STREAM = _terms_env("RLDM_PRECISION_STREAM", "fp16x3")     # stream-carrying convolutions
 # GroupNorm moments accumulated in the conv epilogue (RLDM_FUSE_STATS=0 forces the separate rldm_gn_stats pass)
 FUSE_STATS = os.environ.get("RLDM_FUSE_STATS", "1") != "0"
 # ResnetBlock2D.conv_shortcut folded into conv2's launch (RLDM_FUSE_SHORTCUT=0: separate 1x1 launch + fp32 residual)
@@ -248,10 +229,8 @@ class Builder:
 
     def __init__(self, prog, batch, max_gn=4096, groups=32, cache=None, terms_of=None):
         self.cache = cache if cache is not None else {}      # packed weights shared between plans of a model
-        # terms_of(W, block) -> 1 | 2 | 3: operand precision of a convolution whose INPUT grid is W columns wide
-        # (block = running number of the resnet / attention / resampling block being built)
-        self.terms_of = terms_of if terms_of is not None else (lambda W, block=None: PRECISION)
-        self.block = -1
+        # terms_of(stream: bool) -> 1 | 2 | 3: operand precision of a stream-carrying / branch convolution
+        self.terms_of = terms_of if terms_of is not None else (lambda stream: PRECISION_STREAM if stream else PRECISION)
         self.pg = prog
         self.B = batch
         self.groups = groups
@@ -265,9 +244,8 @@ class Builder:
         self.memset_op.n = self.gn_used * 8
 
     # ---- weights ---------------------------------------------------------------------------
-    def terms(self, W):
-        self.block += 1
-        t = self.terms_of(W, self.block)
+    def terms(self, stream=False):
+        t = self.terms_of(stream)
         if CONV_KIND == _lib.OP_CONV_REF and t == 2:         # the CUDA-core restatement knows 1 and 3 only
             t = 3
         return t
@@ -405,33 +383,36 @@ class Builder:
         """ResnetBlock2D on the virtual concat (x0 | x1) (App. A.1; `model.py:342-362`)."""
         pg = self.pg
         circ = lambda conv: bool(getattr(conv, "circular", False))
-        t = self.terms(x0.W)
+        fold = rb.conv_shortcut is not None and CONV_KIND == _lib.OP_CONV_TC and FUSE_SHORTCUT
+        t1 = self.terms()                                   # conv1: a branch convolution
+        ts = self.terms(stream=True)                        # the 1x1 shortcut carries the stream ...
+        t2 = ts if fold else t1                             # ... and conv2 with it when the shortcut rides in its K loop
         xr = None
         if rb.conv_shortcut is not None:
-            a1, xr = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1), also_raw=True, terms=t, raw_terms=t)
+            a1, xr = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1), also_raw=True, terms=t1, raw_terms=ts)
         else:
-            a1 = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1), terms=t)
+            a1 = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1), terms=t1)
         temb = None
         if rb.time_emb_proj is not None and self.temb is not None:
             tt, T = self.temb
             off = self.temb_rows[id(rb)]
             temb = (tt.view(-1)[off:], T)
-        h = self.conv(a1, x0.W, x0.H, rb.conv1, temb=temb, stats=True, terms=t)
+        h = self.conv(a1, x0.W, x0.H, rb.conv1, temb=temb, stats=True, terms=t1)
         self.free_half(a1)
-        a2 = self.prep(h, None, rb.norm2, silu=True, circular=circ(rb.conv2), terms=t)
+        a2 = self.prep(h, None, rb.norm2, silu=True, circular=circ(rb.conv2), terms=t2)
         pg.free(h.t)
-        if rb.conv_shortcut is not None and CONV_KIND == _lib.OP_CONV_TC and FUSE_SHORTCUT:
+        if fold:
             # the 1x1 conv_shortcut rides in conv2's K loop (extra K steps over the raw operand)
-            out = self.conv(a2, x0.W, x0.H, rb.conv2, stats=True, shortcut=(xr, rb.conv_shortcut), terms=t)
+            out = self.conv(a2, x0.W, x0.H, rb.conv2, stats=True, shortcut=(xr, rb.conv_shortcut), terms=t2)
             self.free_half(xr)
         elif rb.conv_shortcut is not None:
-            sc = self.conv(xr, x0.W, x0.H, rb.conv_shortcut, terms=t)
+            sc = self.conv(xr, x0.W, x0.H, rb.conv_shortcut, terms=ts)
             self.free_half(xr)
-            out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=sc, stats=True, terms=t)
+            out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=sc, stats=True, terms=t2)
             pg.free(sc.t)
         else:
             assert x1 is None
-            out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=x0, stats=True, terms=t)
+            out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=x0, stats=True, terms=t2)
         self.free_half(a2)
         pg.taps.append((rb, out))
         if free_inputs:
@@ -447,7 +428,7 @@ class Builder:
             raise NotImplementedError(f"attention head_dim {at.dim_head}: the sm_100a attention kernel implements the "
                                       "reference's attention_head_dim=8")
         C = x.C
-        t = self.terms(x.W)
+        t = self.terms()
         a = self.prep(x, None, at.group_norm, silu=False, terms=t)
         qkv = self.conv(a, x.W, x.H, packed=self.pack_linear([at.to_q, at.to_k, at.to_v], t), cin=C, cout=3 * C, ks=1,
                         pad_lo=0, terms=t)
@@ -466,7 +447,7 @@ class Builder:
     def downsample(self, ds, x, free_input=True):
         """Patched Downsample2D (`ldm/utils.py:107-116`): raw cast + stride-2 conv; padding=0 is the
         VAE-encoder asymmetric pad (pad_lo = 0)."""
-        t = self.terms(x.W)
+        t = self.terms(stream=True)
         xr = self.prep(x, None, None, circular=bool(getattr(ds.conv, "circular", False)), terms=t)
         out = self.conv(xr, x.W, x.H, ds.conv, stats=True, terms=t)
         self.free_half(xr)
@@ -477,7 +458,7 @@ class Builder:
 
     def upsample(self, us, x):
         """Upsample2D (`model.py:120-125`): nearest 2x folded into the cast, then 3x3 conv."""
-        t = self.terms(x.W * 2)
+        t = self.terms(stream=True)
         xr = self.prep(x, None, None, up=2, circular=bool(getattr(us.conv, "circular", False)), terms=t)
         out = self.conv(xr, x.W * 2, x.H * 2, us.conv, stats=True, terms=t)
         self.free_half(xr)
@@ -545,8 +526,7 @@ class UNetPlan:
         if W % (1 << (L - 1)) or H % (1 << (L - 1)):
             raise ValueError(f"sample size {(W, H)} must be divisible by {1 << (L - 1)}")
         pg = self.prog = Program(dev)
-        bd = Builder(pg, batch, groups=cfg.norm_num_groups, cache=model._packed,
-                     terms_of=lambda w, block=None: PRECISION_TOP if w >= W else PRECISION)
+        bd = Builder(pg, batch, groups=cfg.norm_num_groups, cache=model._packed)
         cin = cfg.in_channels
         self.x_in = pg.hold(torch.zeros(batch, cin - cond_channels, W, H, device=dev))
         self.cond = pg.hold(torch.zeros(batch, cond_channels, W, H, device=dev)) if cond_channels else None
@@ -632,7 +612,7 @@ class VaeDecoderPlan:
         dec = vae.decoder
         self.B = batch
         pg = self.prog = Program(dev)
-        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed, terms_of=lambda w, block=None: _vae_terms(w, W, block))
+        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed)
         zc = vae.config.latent_channels
         n_up = sum(1 for b in dec.up_blocks if b.upsamplers is not None)
         self.z_in = pg.hold(torch.zeros(batch, zc, W, H, device=dev))
@@ -669,8 +649,7 @@ class VaeEncoderPlan:
         self.B = batch
         pg = self.prog = Program(dev)
         n_down = sum(1 for b in enc.down_blocks if b.downsamplers is not None)
-        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed,
-                     terms_of=lambda w, block=None: _vae_terms(w, W >> n_down))
+        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed)
         ic = vae.config.in_channels
         self.x_in = pg.hold(torch.zeros(batch, ic, W, H, device=dev))
         self.out = pg.hold(torch.zeros(batch, enc.conv_out.out_channels, W >> n_down, H >> n_down, device=dev))

@@ -25,7 +25,15 @@ def _forward_both(u, x, t, monkeypatch):
     return outs, nodes
 
 
-def test_fused_levels_tiny_unet_matches_unfused_and_oracle(monkeypatch):
+@pytest.fixture
+def x3(monkeypatch):
+    from rangeldm_b200 import engine
+    monkeypatch.setattr(engine, "PRECISION", 3)
+    monkeypatch.setattr(engine, "PRECISION_STREAM", 3)
+    yield
+
+
+def test_fused_levels_tiny_unet_matches_unfused_and_oracle(monkeypatch, x3):
     from oracle import nets
     from oracle.make_golden import TINY_UNET, seeded
     ou = seeded(nets.OracleUNet2DModel, 4321, **TINY_UNET)
@@ -44,7 +52,7 @@ def test_fused_levels_tiny_unet_matches_unfused_and_oracle(monkeypatch):
 
 
 @pytest.mark.parametrize("batch", [8, 3, 1])
-def test_fused_levels_c3_unet_matches_unfused_and_oracle(batch, monkeypatch):
+def test_fused_levels_c3_unet_matches_unfused_and_oracle(batch, monkeypatch, x3):
     """BENCH shape (batch 8), a ragged batch (partial 128-pixel tiles at the 32x2 level) and a single image."""
     from oracle import nets
     from oracle.make_golden import seeded
@@ -77,7 +85,7 @@ def test_fused_levels_reduced_precision_and_graph_replay(monkeypatch):
     x = x.cuda()
     for terms in (2, 1):
         monkeypatch.setattr(engine, "PRECISION", terms)
-        monkeypatch.setattr(engine, "PRECISION_TOP", terms)
+        monkeypatch.setattr(engine, "PRECISION_STREAM", terms)
         (a, b), nodes = _forward_both(u, x, 300, monkeypatch)
         assert nodes[0][1] >= 1
         assert relerr(a, b, f"fused_vs_unfused_terms{terms}") < 2e-3
@@ -131,7 +139,7 @@ def test_fused_conv_matches_standalone_conv(case, terms):
     outs = []
     for fuse in (True, False):
         pg = engine.Program(dev, fuse=fuse)
-        bd = engine.Builder(pg, B, cache={}, terms_of=lambda w, block=None: terms)
+        bd = engine.Builder(pg, B, cache={}, terms_of=lambda stream: terms)
         xa = engine.Act(pg.hold(x.clone()), B, W, H, Cin)
         ra = engine.Act(pg.hold(res.clone()), B, Wo, Ho, Cout) if use_res else None
         a = bd.prep(xa, None, None, terms=terms)

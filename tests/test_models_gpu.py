@@ -9,7 +9,22 @@ import torch
 from conftest import relerr
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-3          # the north-star tolerance; the default split-fp16 engine lands ~100x inside it
+TOL = 1e-3          # the north-star tolerance (BASELINE.json); the default precision policy lands 5-20x inside it
+# Two runs of the SAME arithmetic in a different order (graph replay with atomics in another order, another batch
+# tiling, per-step vs fused program) differ by ~1e-7 in fp32 -- and the branch convolutions round their activations to
+# fp16, so such a difference occasionally flips one rounding (2^-11 of that element): run-to-run agreement of whole
+# trajectories is ~1e-5..1e-4, not bit-level.
+RUN_TO_RUN = 5e-4
+
+
+@pytest.fixture
+def x3(monkeypatch):
+    """Every convolution at split-fp16 x3 (RLDM_PRECISION=RLDM_PRECISION_STREAM=fp16x3): for structural checks that
+    need ~1e-6 agreement."""
+    from rangeldm_b200 import engine
+    monkeypatch.setattr(engine, "PRECISION", 3)
+    monkeypatch.setattr(engine, "PRECISION_STREAM", 3)
+    yield
 
 
 def make_unet(cfg, oracle_net, dev="cuda"):
@@ -58,10 +73,11 @@ def test_unet_forward_tiny(tiny):
         assert relerr(out, ref, f"unet_tiny_t{t}") < TOL
 
 
-def test_unet_forward_cuda_core_conv_path_agrees(tiny):
+def test_unet_forward_cuda_core_conv_path_agrees(tiny, x3):
     """Same program with the CUDA-core conv restatement: isolates tensor-core issues from precision."""
     from rangeldm_b200 import _lib, engine
     x = torch.randn(2, 5, 32, 8, generator=torch.Generator().manual_seed(1))
+    tiny["u"].invalidate_plans()
     a = tiny["u"](x.cuda(), 500).sample
     engine.CONV_KIND = _lib.OP_CONV_REF
     try:
@@ -101,7 +117,7 @@ def test_ldm_pipeline_golden_from_reference_pipeline(tiny, golden):
         # replaying the captured graph with the same seed: only the double-precision GroupNorm-moment atomics
         # are order dependent (split-K is a deterministic cluster reduction)
         img2 = pipe(batch_size=2, generator=torch.Generator().manual_seed(3), num_inference_steps=5)
-        assert relerr(img2, img, "graph_replay_stability") < 1e-5
+        assert relerr(img2, img, "graph_replay_stability") < RUN_TO_RUN
 
 
 def test_pixel_pipeline_golden_from_reference_pipeline(tiny, golden):
@@ -120,7 +136,7 @@ def test_step_by_step_module_api_matches_fused(tiny):
     a = pipe(batch_size=1, generator=torch.Generator().manual_seed(5), num_inference_steps=4)
     imgs = pipe(batch_size=1, generator=torch.Generator().manual_seed(5), num_inference_steps=4, final_only=False)
     assert len(imgs) == 5
-    assert relerr(imgs[-1], a, "stepwise_vs_fused") < 1e-4
+    assert relerr(imgs[-1], a, "stepwise_vs_fused") < RUN_TO_RUN
 
 
 def test_upscale_pipeline_matches_oracle(tiny):
@@ -443,7 +459,7 @@ def test_multi_stream_sampler_matches_single(tiny):
     pe = R.pipelines.make_pos_encoding(4, 32, 8, lat.device)
     a = R.FusedSampler(tiny["u"], sch, tiny["v"], 4, 1, streams=1).run(lat, pe)
     b = R.FusedSampler(tiny["u"], sch, tiny["v"], 4, 1, streams=2).run(lat, pe)
-    assert relerr(b, a, "multi_stream_vs_single") < 1e-5
+    assert relerr(b, a, "multi_stream_vs_single") < RUN_TO_RUN
 
 
 def test_batch_sharding_is_index_stable(tiny):
@@ -455,7 +471,7 @@ def test_batch_sharding_is_index_stable(tiny):
     gens = [torch.Generator().manual_seed(100), torch.Generator().manual_seed(101)]
     both = pipe(batch_size=2, generator=gens, num_inference_steps=3)
     one = pipe(batch_size=1, generator=[torch.Generator().manual_seed(101)], num_inference_steps=3)
-    assert relerr(both[1:], one, "batch_index_stability") < 1e-4
+    assert relerr(both[1:], one, "batch_index_stability") < RUN_TO_RUN
 
 
 def test_missing_library_fails_loudly(monkeypatch):
