@@ -37,11 +37,15 @@ CONV_KIND = _lib.OP_CONV_TC
 #     Upsample2D convs) and a ResnetBlock2D's conv2 when its 1x1 conv_shortcut is folded into it.  An fp16-rounded
 #     operand there puts 2^-11 relative noise on the signal itself: each such block alone costs 2.6-3.3e-4 of parity in
 #     the VAE decoder.  They stay at fp16x3.
+#     They stay at fp16x3 in the VAE.  In the UNet the sampler damps them (every step's eps error enters the latent
+#     with a small coefficient): all-fp16 costs 1.3e-4 on the 20-step latent, so the UNet's stream convolutions run in
+#     plain fp16 as well.
 #   * BRANCH convolutions (conv1, conv2 of identity-shortcut blocks, attention projections) produce an increment that is
 #     ADDED to the fp32 stream: rounding their operands perturbs only the increment.  Plain fp16 on all of them moves
-#     the decoder's parity from 4.8e-6 to <1e-5 and the 20-step UNet latent to ~4e-5, and removes 2/3 of their tensor
-#     work and half of their operand bytes.
-# RLDM_PRECISION (branch) / RLDM_PRECISION_STREAM override the defaults.
+#     the decoder's parity from 5.5e-6 to 9.6e-6, and removes 2/3 of their tensor work and half of their operand bytes.
+# Measured Pareto (profiles/precision_pareto_r2.json; C3, 20 steps, 4 images, tolerance 1e-3): all fp16x3 5.2e-6 /
+# 41.97 ms per batch of 8; this default 1.4e-4 / ~34.2 ms; everything fp16 6.8e-4 / 33.7 ms.
+# RLDM_PRECISION (branch), RLDM_PRECISION_STREAM (UNet stream), RLDM_PRECISION_STREAM_VAE override the defaults.
 _TERMS = {"fp16x3": 3, "fp16x2": 2, "fp16": 1}
 
 
@@ -52,8 +56,9 @@ def _terms_env(name, default):
     return _TERMS[v]
 
 
-PRECISION = _terms_env("RLDM_PRECISION", "fp16")                     # branch convolutions and projections
-PRECISION_STREAM = _terms_env("RLDM_PRECISION_STREAM", "fp16x3")     # stream-carrying convolutions
+PRECISION = _terms_env("RLDM_PRECISION", "fp16")                              # branch convolutions and projections
+PRECISION_STREAM = _terms_env("RLDM_PRECISION_STREAM", "fp16")                # stream-carrying convolutions of the UNet
+PRECISION_STREAM_VAE = _terms_env("RLDM_PRECISION_STREAM_VAE", "fp16x3")      # ... of the VAE decoder / encoder
 # GroupNorm moments accumulated in the conv epilogue (RLDM_FUSE_STATS=0 forces the separate rldm_gn_stats pass)
 FUSE_STATS = os.environ.get("RLDM_FUSE_STATS", "1") != "0"
 # ResnetBlock2D.conv_shortcut folded into conv2's launch (RLDM_FUSE_SHORTCUT=0: separate 1x1 launch + fp32 residual)
@@ -612,7 +617,8 @@ class VaeDecoderPlan:
         dec = vae.decoder
         self.B = batch
         pg = self.prog = Program(dev)
-        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed)
+        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed,
+                     terms_of=lambda stream: PRECISION_STREAM_VAE if stream else PRECISION)
         zc = vae.config.latent_channels
         n_up = sum(1 for b in dec.up_blocks if b.upsamplers is not None)
         self.z_in = pg.hold(torch.zeros(batch, zc, W, H, device=dev))
@@ -649,7 +655,8 @@ class VaeEncoderPlan:
         self.B = batch
         pg = self.prog = Program(dev)
         n_down = sum(1 for b in enc.down_blocks if b.downsamplers is not None)
-        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed)
+        bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed,
+                     terms_of=lambda stream: PRECISION_STREAM_VAE if stream else PRECISION)
         ic = vae.config.in_channels
         self.x_in = pg.hold(torch.zeros(batch, ic, W, H, device=dev))
         self.out = pg.hold(torch.zeros(batch, enc.conv_out.out_channels, W >> n_down, H >> n_down, device=dev))

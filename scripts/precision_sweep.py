@@ -38,12 +38,13 @@ if __name__ == "__main__":
     ref_img, traj = pipeline.ldm_sample(ou, ov, schedulers.OracleDPMSolverMultistepScheduler(timestep_spacing="leading"),
                                         noise, 20, return_latents=True)
     ref_lat = traj[-1]
-    settings = [(3, 3), (1, 3), (2, 3), (1, 2), (2, 2), (1, 1)]
+    settings = [(3, 3), (1, 3), (2, 3), (1, 2), (2, 2), (1, 1), (1, (1, 3)), (1, (2, 3))]      # (branch, stream | (UNet stream, VAE stream))
     if quick:
         settings = [(3, 3), (1, 3), (1, 1)]
     out = []
     for branch, stream in settings:
-        engine.PRECISION, engine.PRECISION_STREAM = branch, stream
+        su, sv = stream if isinstance(stream, tuple) else (stream, stream)
+        engine.PRECISION, engine.PRECISION_STREAM, engine.PRECISION_STREAM_VAE = branch, su, sv
         u.invalidate_plans(); v.invalidate_plans()
         sch = R.DPMSolverMultistepScheduler(timestep_spacing="leading")
         sch.set_timesteps(20)
@@ -51,7 +52,7 @@ if __name__ == "__main__":
         lat = R.FusedSampler(u, sch, None, NB, 1).run(noise.cuda(), pe)
         img = R.FusedSampler(u, sch, v, NB, 1).run(noise.cuda(), pe)
         dec_only = v.decode((ref_lat / ov.scaling_factor).cuda()).sample      # decoder alone on the ORACLE latent
-        row = {"branch": NAME[branch], "stream": NAME[stream], "latent_relerr": rel(lat, ref_lat),
+        row = {"branch": NAME[branch], "stream_unet": NAME[su], "stream_vae": NAME[sv], "latent_relerr": rel(lat, ref_lat),
                "image_relerr": rel(img, ref_img), "decoder_only_relerr": rel(dec_only, ref_img)}
         p = u.plan(8, 256, 16, 1)
         p.x_in.normal_(); p.t_buf.fill_(500.0)

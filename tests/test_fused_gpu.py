@@ -30,6 +30,7 @@ def x3(monkeypatch):
     from rangeldm_b200 import engine
     monkeypatch.setattr(engine, "PRECISION", 3)
     monkeypatch.setattr(engine, "PRECISION_STREAM", 3)
+    monkeypatch.setattr(engine, "PRECISION_STREAM_VAE", 3)
     yield
 
 
@@ -118,12 +119,13 @@ FUSED_CONV_CASES = [
 
 @pytest.mark.parametrize("terms", [3, 2, 1])
 @pytest.mark.parametrize("case", FUSED_CONV_CASES, ids=lambda c: "x".join(map(str, c)))
-def test_fused_conv_matches_standalone_conv(case, terms):
+def test_fused_conv_matches_standalone_conv(case, terms, monkeypatch):
     """[raw-cast prep, conv] as one fused run against the same two ops as separate launches: identical fp16 operands on
     both sides, so the outputs agree to fp32 summation order and the GroupNorm moments to 1e-6, for every operand
     precision, with bias + time embedding + residual in the epilogue."""
     import rangeldm_b200 as R
     from rangeldm_b200 import engine, models
+    monkeypatch.setattr(engine, "FUSE_LEVELS", True)           # (an opt-in experiment: see engine.FUSE_LEVELS)
     B, W, H, Cin, Cout, ks, stride, use_res, use_temb = case
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
