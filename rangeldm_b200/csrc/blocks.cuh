@@ -38,29 +38,30 @@ struct PrepArgs {
 };
 
 // prep: y = [silu]([gn](concat(x0,x1))) cast to fp16, optionally nearest-2x upsampled.
-// virtual grid (ceil(outpix/pix_per_block), B), 256 threads.  Thread = 8 channels of one OUTPUT pixel
-// (two float4 loads, one 16 B store).  shf: 2*C floats of shared memory (scale[C], shift[C]).
+// prep_range: `nthreads` threads (ids `tid`, synchronised by named barrier `bar_id`; 0 = __syncthreads of a CTA of
+// exactly that many threads) produce the padded output pixels [p_begin, p_end) of image b, channels [ch_lo, ch_hi).
+// Thread = 8 channels of one OUTPUT pixel (two float4 loads, one 16 B store).  shf: 2*(ch_hi-ch_lo) floats of shared
+// memory (scale, shift).
 template <bool COH>
-__device__ __forceinline__ void prep_block(const PrepArgs& a, int vbx, int vby, float* shf) {
+__device__ __forceinline__ void prep_range(const PrepArgs& a, int b, int p_begin, int p_end, int ch_lo, int ch_hi, float* shf,
+                                           int tid, int nthreads, int bar_id) {
   const int c0 = a.c0, c1 = a.c1, W = a.W, H = a.H, up = a.up, G = a.G;
   const int C = c0 + c1;
-  const int b = vby;
+  const int CR = ch_hi - ch_lo;
   float* sc = shf;
-  float* sf = shf + C;
+  float* sf = shf + CR;
   const bool norm = a.sums != nullptr || a.pairs0 != nullptr;
   // Output is W-PADDED: (B, Wo+2, Ho, C); padded column wp holds image column (wp-1) mod Wo, i.e. the
   // circular halo of `ldm/utils.py:47` is materialised here for free (zeros when !circular), so every
   // conv tap is a plain TMA box.
   const int Wo = W * up, Ho = H * up;
-  const int oct_per_pix = C >> 3;
+  const int oct_per_pix = CR >> 3;
   const int out_pix = (Wo + 2) * Ho;
-  const int p_begin = vbx * a.pix_per_block;
-  const int p_end = min(p_begin + a.pix_per_block, out_pix);
   const int total = (p_end - p_begin) * oct_per_pix;
   // (pixel, channel octet) of this thread's item advance incrementally: no integer division in the loop; Ho is a
   // power of two in every reference geometry (shift), otherwise one division per item
-  int pl = threadIdx.x / oct_per_pix, oc = threadIdx.x - pl * oct_per_pix;
-  const int step_p = blockDim.x / oct_per_pix, step_o = blockDim.x - step_p * oct_per_pix;
+  int pl = tid / oct_per_pix, oc = tid - pl * oct_per_pix;
+  const int step_p = nthreads / oct_per_pix, step_o = nthreads - step_p * oct_per_pix;
   const int sh_h = (Ho & (Ho - 1)) == 0 ? 31 - __clz(Ho) : -1;
   // Two items per step, software-pipelined one step ahead: the loads of step k+1 are in flight while step k is
   // consumed, and the loads of the FIRST step are issued before the GroupNorm prologue below (its dependent moment
@@ -74,10 +75,10 @@ __device__ __forceinline__ void prep_block(const PrepArgs& a, int vbx, int vby, 
   auto issue = [&](int i, Item (&it)[2]) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      it[u].live = i + u * static_cast<int>(blockDim.x) < total;
-      if (oc >= oct_per_pix) { oc -= oct_per_pix; ++pl; }
+      it[u].live = i + u * nthreads < total;
+      while (oc >= oct_per_pix) { oc -= oct_per_pix; ++pl; }
       const int po = p_begin + pl;
-      const int c = oc << 3;
+      const int c = ch_lo + (oc << 3);
       pl += step_p; oc += step_o;                         // advance to this thread's next item
       const int wp = sh_h >= 0 ? po >> sh_h : po / Ho;
       const int ho = po - wp * Ho;
@@ -86,7 +87,7 @@ __device__ __forceinline__ void prep_block(const PrepArgs& a, int vbx, int vby, 
       if (wo < 0) wo += Wo;
       if (wo >= Wo) wo -= Wo;
       it[u].o = (static_cast<size_t>(b) * out_pix + po) * C + c;
-      it[u].c = c;
+      it[u].c = c - ch_lo;
       it[u].zero = halo && !a.circular;
       it[u].v0 = it[u].v1 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (it[u].live && !it[u].zero) {
@@ -99,13 +100,14 @@ __device__ __forceinline__ void prep_block(const PrepArgs& a, int vbx, int vby, 
     }
   };
   Item cur[2];
-  issue(threadIdx.x, cur);
+  issue(tid, cur);
   if (norm) {
     // group moments: either the (sum, sum^2) per (image, group) of rldm_gn_stats, or the per channel-PAIR moments
     // that the producing convolutions accumulated in their epilogues (x0's pairs, then x1's for a skip concat)
     const int cpg = C / G;
     const double inv_n = 1.0 / (static_cast<double>(W) * H * cpg);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int cr = tid; cr < CR; cr += nthreads) {
+      const int c = ch_lo + cr;
       const int g = c / cpg;
       double s = 0.0, ss = 0.0;
       if (a.sums) {
@@ -124,16 +126,17 @@ __device__ __forceinline__ void prep_block(const PrepArgs& a, int vbx, int vby, 
       if (var < 0) var = 0;
       const float rstd = rsqrtf(static_cast<float>(var) + a.eps);
       const float sa = rstd * __ldg(a.gamma + c);
-      sc[c] = sa;
-      sf[c] = __ldg(a.beta + c) - static_cast<float>(mean) * sa;
+      sc[cr] = sa;
+      sf[cr] = __ldg(a.beta + c) - static_cast<float>(mean) * sa;
     }
-    __syncthreads();
+    if (bar_id == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
   }
   __half* out = a.out; __half* out_lo = a.out_lo; __half* raw = a.raw; __half* raw_lo = a.raw_lo;
-  for (int i = threadIdx.x; i < total; i += 2 * blockDim.x) {
+  for (int i = tid; i < total; i += 2 * nthreads) {
     Item nxt[2];
     nxt[0].live = nxt[1].live = false;
-    if (i + 2 * static_cast<int>(blockDim.x) < total) issue(i + 2 * blockDim.x, nxt);
+    if (i + 2 * nthreads < total) issue(i + 2 * nthreads, nxt);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (!cur[u].live) continue;
@@ -163,6 +166,14 @@ __device__ __forceinline__ void prep_block(const PrepArgs& a, int vbx, int vby, 
     cur[0] = nxt[0];
     cur[1] = nxt[1];
   }
+}
+
+// virtual grid (ceil(outpix/pix_per_block), B) of 256-thread blocks over the whole tensor (rldm_prep, fused levels)
+template <bool COH>
+__device__ __forceinline__ void prep_block(const PrepArgs& a, int vbx, int vby, float* shf) {
+  const int out_pix = (a.W * a.up + 2) * a.H * a.up;
+  const int p_begin = vbx * a.pix_per_block;
+  prep_range<COH>(a, vby, p_begin, min(p_begin + a.pix_per_block, out_pix), 0, a.c0 + a.c1, shf, threadIdx.x, blockDim.x, 0);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -32,20 +32,14 @@ CONV_KIND = _lib.OP_CONV_TC
 #   2 "fp16x2": activations single fp16, weights hi+lo: Xh*Wh + Xh*Wl.  No low-order activation plane exists: the
 #               producer pass writes, and the conv reads, half the operand bytes; 2/3 of the tensor work.
 #   1 "fp16":   plain fp16 operands (1 MMA per K step).
-# Two classes of convolutions (measured: profiles/precision_blocks_r2.json):
-#   * STREAM convolutions carry the whole residual stream through their operand: the resamplers (Downsample2D /
-#     Upsample2D convs) and a ResnetBlock2D's conv2 when its 1x1 conv_shortcut is folded into it.  An fp16-rounded
-#     operand there puts 2^-11 relative noise on the signal itself: each such block alone costs 2.6-3.3e-4 of parity in
-#     the VAE decoder.  They stay at fp16x3.
-#     They stay at fp16x3 in the VAE.  In the UNet the sampler damps them (every step's eps error enters the latent
-#     with a small coefficient): all-fp16 costs 1.3e-4 on the 20-step latent, so the UNet's stream convolutions run in
-#     plain fp16 as well.
-#   * BRANCH convolutions (conv1, conv2 of identity-shortcut blocks, attention projections) produce an increment that is
-#     ADDED to the fp32 stream: rounding their operands perturbs only the increment.  Plain fp16 on all of them moves
-#     the decoder's parity from 5.5e-6 to 9.6e-6, and removes 2/3 of their tensor work and half of their operand bytes.
-# Measured Pareto (profiles/precision_pareto_r2.json; C3, 20 steps, 4 images, tolerance 1e-3): all fp16x3 5.2e-6 /
-# 41.97 ms per batch of 8; this default 1.4e-4 / ~34.2 ms; everything fp16 6.8e-4 / 33.7 ms.
-# RLDM_PRECISION (branch), RLDM_PRECISION_STREAM (UNet stream), RLDM_PRECISION_STREAM_VAE override the defaults.
+# fp16 operands carry 11 bits: through the ~25 convolutions of the VAE decoder, or one UNet forward, that is a
+# max-norm error of 0.6-1.2e-3 against the fp32 reference -- AT the 1e-3 tolerance -- while a 20-step trajectory of the
+# UNet lands at 1.2e-4 (the sampler damps each step's eps error).  The defaults below are the measured choice
+# (profiles/precision_pareto_r2.json): every single forward stays below 5e-4, the trajectory
+# below 1e-4.  The latency-bound lower levels of the UNet gain little from fewer MMAs; its full-resolution level and
+# the VAE are where the tensor work is.
+#   RLDM_PRECISION      UNet levels 1..n          RLDM_PRECISION_TOP   UNet full-resolution level
+#   RLDM_PRECISION_VAE  VAE decoder / encoder
 _TERMS = {"fp16x3": 3, "fp16x2": 2, "fp16": 1}
 
 
@@ -56,9 +50,9 @@ def _terms_env(name, default):
     return _TERMS[v]
 
 
-PRECISION = _terms_env("RLDM_PRECISION", "fp16")                              # branch convolutions and projections
-PRECISION_STREAM = _terms_env("RLDM_PRECISION_STREAM", "fp16")                # stream-carrying convolutions of the UNet
-PRECISION_STREAM_VAE = _terms_env("RLDM_PRECISION_STREAM_VAE", "fp16x3")      # ... of the VAE decoder / encoder
+PRECISION = _terms_env("RLDM_PRECISION", "fp16x2")
+PRECISION_TOP = _terms_env("RLDM_PRECISION_TOP", "fp16x2")
+PRECISION_VAE = _terms_env("RLDM_PRECISION_VAE", "fp16x3")
 # GroupNorm moments accumulated in the conv epilogue (RLDM_FUSE_STATS=0 forces the separate rldm_gn_stats pass)
 FUSE_STATS = os.environ.get("RLDM_FUSE_STATS", "1") != "0"
 # ResnetBlock2D.conv_shortcut folded into conv2's launch (RLDM_FUSE_SHORTCUT=0: separate 1x1 launch + fp32 residual)
@@ -234,8 +228,8 @@ class Builder:
 
     def __init__(self, prog, batch, max_gn=4096, groups=32, cache=None, terms_of=None):
         self.cache = cache if cache is not None else {}      # packed weights shared between plans of a model
-        # terms_of(stream: bool) -> 1 | 2 | 3: operand precision of a stream-carrying / branch convolution
-        self.terms_of = terms_of if terms_of is not None else (lambda stream: PRECISION_STREAM if stream else PRECISION)
+        # terms_of(W) -> 1 | 2 | 3: operand precision of a convolution whose operand grid is W columns wide
+        self.terms_of = terms_of if terms_of is not None else (lambda W: PRECISION)
         self.pg = prog
         self.B = batch
         self.groups = groups
@@ -249,8 +243,8 @@ class Builder:
         self.memset_op.n = self.gn_used * 8
 
     # ---- weights ---------------------------------------------------------------------------
-    def terms(self, stream=False):
-        t = self.terms_of(stream)
+    def terms(self, W):
+        t = self.terms_of(W)
         if CONV_KIND == _lib.OP_CONV_REF and t == 2:         # the CUDA-core restatement knows 1 and 3 only
             t = 3
         return t
@@ -389,9 +383,7 @@ class Builder:
         pg = self.pg
         circ = lambda conv: bool(getattr(conv, "circular", False))
         fold = rb.conv_shortcut is not None and CONV_KIND == _lib.OP_CONV_TC and FUSE_SHORTCUT
-        t1 = self.terms()                                   # conv1: a branch convolution
-        ts = self.terms(stream=True)                        # the 1x1 shortcut carries the stream ...
-        t2 = ts if fold else t1                             # ... and conv2 with it when the shortcut rides in its K loop
+        t1 = t2 = ts = self.terms(x0.W)
         xr = None
         if rb.conv_shortcut is not None:
             a1, xr = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1), also_raw=True, terms=t1, raw_terms=ts)
@@ -433,7 +425,7 @@ class Builder:
             raise NotImplementedError(f"attention head_dim {at.dim_head}: the sm_100a attention kernel implements the "
                                       "reference's attention_head_dim=8")
         C = x.C
-        t = self.terms()
+        t = self.terms(x.W)
         a = self.prep(x, None, at.group_norm, silu=False, terms=t)
         qkv = self.conv(a, x.W, x.H, packed=self.pack_linear([at.to_q, at.to_k, at.to_v], t), cin=C, cout=3 * C, ks=1,
                         pad_lo=0, terms=t)
@@ -452,7 +444,7 @@ class Builder:
     def downsample(self, ds, x, free_input=True):
         """Patched Downsample2D (`ldm/utils.py:107-116`): raw cast + stride-2 conv; padding=0 is the
         VAE-encoder asymmetric pad (pad_lo = 0)."""
-        t = self.terms(stream=True)
+        t = self.terms(x.W)
         xr = self.prep(x, None, None, circular=bool(getattr(ds.conv, "circular", False)), terms=t)
         out = self.conv(xr, x.W, x.H, ds.conv, stats=True, terms=t)
         self.free_half(xr)
@@ -463,7 +455,7 @@ class Builder:
 
     def upsample(self, us, x):
         """Upsample2D (`model.py:120-125`): nearest 2x folded into the cast, then 3x3 conv."""
-        t = self.terms(stream=True)
+        t = self.terms(x.W * 2)
         xr = self.prep(x, None, None, up=2, circular=bool(getattr(us.conv, "circular", False)), terms=t)
         out = self.conv(xr, x.W * 2, x.H * 2, us.conv, stats=True, terms=t)
         self.free_half(xr)
@@ -531,7 +523,8 @@ class UNetPlan:
         if W % (1 << (L - 1)) or H % (1 << (L - 1)):
             raise ValueError(f"sample size {(W, H)} must be divisible by {1 << (L - 1)}")
         pg = self.prog = Program(dev)
-        bd = Builder(pg, batch, groups=cfg.norm_num_groups, cache=model._packed)
+        bd = Builder(pg, batch, groups=cfg.norm_num_groups, cache=model._packed,
+                     terms_of=lambda w: PRECISION_TOP if w >= W else PRECISION)
         cin = cfg.in_channels
         self.x_in = pg.hold(torch.zeros(batch, cin - cond_channels, W, H, device=dev))
         self.cond = pg.hold(torch.zeros(batch, cond_channels, W, H, device=dev)) if cond_channels else None
@@ -618,7 +611,7 @@ class VaeDecoderPlan:
         self.B = batch
         pg = self.prog = Program(dev)
         bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed,
-                     terms_of=lambda stream: PRECISION_STREAM_VAE if stream else PRECISION)
+                     terms_of=lambda w: PRECISION_VAE)
         zc = vae.config.latent_channels
         n_up = sum(1 for b in dec.up_blocks if b.upsamplers is not None)
         self.z_in = pg.hold(torch.zeros(batch, zc, W, H, device=dev))
@@ -656,7 +649,7 @@ class VaeEncoderPlan:
         pg = self.prog = Program(dev)
         n_down = sum(1 for b in enc.down_blocks if b.downsamplers is not None)
         bd = Builder(pg, batch, groups=vae.config.norm_num_groups, cache=vae._packed,
-                     terms_of=lambda stream: PRECISION_STREAM_VAE if stream else PRECISION)
+                     terms_of=lambda w: PRECISION_VAE)
         ic = vae.config.in_channels
         self.x_in = pg.hold(torch.zeros(batch, ic, W, H, device=dev))
         self.out = pg.hold(torch.zeros(batch, enc.conv_out.out_channels, W >> n_down, H >> n_down, device=dev))

@@ -29,8 +29,8 @@ def _forward_both(u, x, t, monkeypatch):
 def x3(monkeypatch):
     from rangeldm_b200 import engine
     monkeypatch.setattr(engine, "PRECISION", 3)
-    monkeypatch.setattr(engine, "PRECISION_STREAM", 3)
-    monkeypatch.setattr(engine, "PRECISION_STREAM_VAE", 3)
+    monkeypatch.setattr(engine, "PRECISION_TOP", 3)
+    monkeypatch.setattr(engine, "PRECISION_VAE", 3)
     yield
 
 
@@ -86,7 +86,7 @@ def test_fused_levels_reduced_precision_and_graph_replay(monkeypatch):
     x = x.cuda()
     for terms in (2, 1):
         monkeypatch.setattr(engine, "PRECISION", terms)
-        monkeypatch.setattr(engine, "PRECISION_STREAM", terms)
+        monkeypatch.setattr(engine, "PRECISION_TOP", terms)
         (a, b), nodes = _forward_both(u, x, 300, monkeypatch)
         assert nodes[0][1] >= 1
         assert relerr(a, b, f"fused_vs_unfused_terms{terms}") < 2e-3
@@ -141,7 +141,7 @@ def test_fused_conv_matches_standalone_conv(case, terms, monkeypatch):
     outs = []
     for fuse in (True, False):
         pg = engine.Program(dev, fuse=fuse)
-        bd = engine.Builder(pg, B, cache={}, terms_of=lambda stream: terms)
+        bd = engine.Builder(pg, B, cache={}, terms_of=lambda w: terms)
         xa = engine.Act(pg.hold(x.clone()), B, W, H, Cin)
         ra = engine.Act(pg.hold(res.clone()), B, Wo, Ho, Cout) if use_res else None
         a = bd.prep(xa, None, None, terms=terms)

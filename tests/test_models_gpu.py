@@ -19,12 +19,12 @@ RUN_TO_RUN = 5e-4
 
 @pytest.fixture
 def x3(monkeypatch):
-    """Every convolution at split-fp16 x3 (RLDM_PRECISION=RLDM_PRECISION_STREAM=fp16x3): for structural checks that
+    """Every convolution at split-fp16 x3 (RLDM_PRECISION=RLDM_PRECISION_TOP=RLDM_PRECISION_VAE=fp16x3): for structural checks that
     need ~1e-6 agreement."""
     from rangeldm_b200 import engine
     monkeypatch.setattr(engine, "PRECISION", 3)
-    monkeypatch.setattr(engine, "PRECISION_STREAM", 3)
-    monkeypatch.setattr(engine, "PRECISION_STREAM_VAE", 3)
+    monkeypatch.setattr(engine, "PRECISION_TOP", 3)
+    monkeypatch.setattr(engine, "PRECISION_VAE", 3)
     yield
 
 
