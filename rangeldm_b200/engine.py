@@ -32,14 +32,19 @@ CONV_KIND = _lib.OP_CONV_TC
 #   2 "fp16x2": activations single fp16, weights hi+lo: Xh*Wh + Xh*Wl.  No low-order activation plane exists: the
 #               producer pass writes, and the conv reads, half the operand bytes; 2/3 of the tensor work.
 #   1 "fp16":   plain fp16 operands (1 MMA per K step).
-# fp16 operands carry 11 bits: through the ~25 convolutions of the VAE decoder, or one UNet forward, that is a
-# max-norm error of 0.6-1.2e-3 against the fp32 reference -- AT the 1e-3 tolerance -- while a 20-step trajectory of the
-# UNet lands at 1.2e-4 (the sampler damps each step's eps error).  The defaults below are the measured choice
-# (profiles/precision_pareto_r2.json): every single forward stays below 5e-4, the trajectory
-# below 1e-4.  The latency-bound lower levels of the UNet gain little from fewer MMAs; its full-resolution level and
-# the VAE are where the tensor work is.
-#   RLDM_PRECISION      UNet levels 1..n          RLDM_PRECISION_TOP   UNet full-resolution level
-#   RLDM_PRECISION_VAE  VAE decoder / encoder
+# fp16 operands carry 11 bits.  Measured against the fp32 oracle (profiles/precision_pareto2_r2.json, C3 shapes,
+# max|a-b|/max|b|, tolerance 1e-3):
+#   * ONE UNet forward: all fp16 5.3e-4, full-resolution level at fp16x3 (rest fp16) 2.3e-4, all fp16x3 3e-6 -- the
+#     full-resolution level (K = 1152, last layers before conv_out) sets the error;
+#   * a 20-step DPM-Solver++ trajectory damps each step's eps error: all fp16 1.25e-4 on the final latent;
+#   * the VAE decoder (~25 convolutions, nothing damps it): fp16x2 1.0e-3 and fp16 1.5e-3 on an N(0,1) latent, fp16x3 2e-5.
+# Hence two UNet profiles: a lone `unet(x, t)` call keeps its full-resolution level at fp16x3 (every single forward
+# < 5e-4), the fused sampler's trajectory programs run all fp16 (trajectories < 2e-4, 1574 vs 1756 us per forward), and
+# the VAE stays at fp16x3.  The latency-bound lower UNet levels gain little from fewer MMAs but nothing from more.
+#   RLDM_PRECISION              UNet levels 1..n (both profiles)            default fp16
+#   RLDM_PRECISION_TOP          UNet full-resolution level, lone forwards   default fp16x3
+#   RLDM_PRECISION_TOP_SAMPLER  UNet full-resolution level, trajectories    default fp16
+#   RLDM_PRECISION_VAE          VAE decoder / encoder                       default fp16x3
 _TERMS = {"fp16x3": 3, "fp16x2": 2, "fp16": 1}
 
 
@@ -50,8 +55,9 @@ def _terms_env(name, default):
     return _TERMS[v]
 
 
-PRECISION = _terms_env("RLDM_PRECISION", "fp16x2")
-PRECISION_TOP = _terms_env("RLDM_PRECISION_TOP", "fp16x2")
+PRECISION = _terms_env("RLDM_PRECISION", "fp16")
+PRECISION_TOP = _terms_env("RLDM_PRECISION_TOP", "fp16x3")
+PRECISION_TOP_SAMPLER = _terms_env("RLDM_PRECISION_TOP_SAMPLER", "fp16")
 PRECISION_VAE = _terms_env("RLDM_PRECISION_VAE", "fp16x3")
 # GroupNorm moments accumulated in the conv epilogue (RLDM_FUSE_STATS=0 forces the separate rldm_gn_stats pass)
 FUSE_STATS = os.environ.get("RLDM_FUSE_STATS", "1") != "0"
@@ -514,7 +520,8 @@ class UNetPlan:
               so samplers never materialise torch.cat([latents, cond], 1)
     `t_buf` : (B,) fp32 timesteps;  `out`: (B, out_channels, W, H) fp32 ref layout."""
 
-    def __init__(self, model, batch, W, H, cond_channels=0):
+    def __init__(self, model, batch, W, H, cond_channels=0, sampler=False):
+        """sampler=True: the plan is one step of a fused trajectory (precision profile of the sampler, see PRECISION)."""
         dev = model.device
         _require_cuda_device(dev, "UNet2DModel")
         cfg = model.config
@@ -524,7 +531,7 @@ class UNetPlan:
             raise ValueError(f"sample size {(W, H)} must be divisible by {1 << (L - 1)}")
         pg = self.prog = Program(dev)
         bd = Builder(pg, batch, groups=cfg.norm_num_groups, cache=model._packed,
-                     terms_of=lambda w: PRECISION_TOP if w >= W else PRECISION)
+                     terms_of=lambda w: (PRECISION_TOP_SAMPLER if sampler else PRECISION_TOP) if w >= W else PRECISION)
         cin = cfg.in_channels
         self.x_in = pg.hold(torch.zeros(batch, cin - cond_channels, W, H, device=dev))
         self.cond = pg.hold(torch.zeros(batch, cond_channels, W, H, device=dev)) if cond_channels else None

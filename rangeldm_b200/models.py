@@ -245,15 +245,16 @@ class UNet2DModel(_PlannedModel):
         self.conv_out = LoRACompatibleConv(boc[0], out_channels, 3, padding=1)
 
     # ------------------------------------------------------------------------------------------
-    def plan(self, batch, W, H, cond_channels=0, replica=0):
+    def plan(self, batch, W, H, cond_channels=0, replica=0, sampler=False):
         """Compiled kernel program for inputs (batch, in_channels, W, H) (see engine.UNetPlan).  `replica`
         selects an independent set of activation buffers (weights are shared) so several programs of the same
-        shape can run concurrently on different streams."""
+        shape can run concurrently on different streams.  `sampler`: the plan is one step of a fused trajectory
+        (its own operand-precision profile, engine.PRECISION)."""
         from .engine import UNetPlan
-        key = (batch, W, H, cond_channels, replica)
+        key = (batch, W, H, cond_channels, replica, bool(sampler))
         p = self._plans.get(key)
         if p is None:
-            p = UNetPlan(self, batch, W, H, cond_channels)
+            p = UNetPlan(self, batch, W, H, cond_channels, sampler=sampler)
             self._plans[key] = p
         return p
 

@@ -143,7 +143,7 @@ class _Trajectory:
         cfg = unet.config
         W, H = cfg.sample_size if not isinstance(cfg.sample_size, int) else (cfg.sample_size, cfg.sample_size)
         self.B, self.steps = batch, len(scheduler.timesteps)
-        self.plan = unet.plan(batch, W, H, cond_channels, replica=replica)
+        self.plan = unet.plan(batch, W, H, cond_channels, replica=replica, sampler=True)
         self.latents, self.cond = self.plan.x_in, self.plan.cond
         pg = self.prog = Program(dev, fuse=fuse)
         pg.keep += [self.plan, scheduler]

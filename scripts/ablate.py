@@ -52,7 +52,7 @@ if __name__ == "__main__":
     dev = torch.device("cuda:0")
     pipe = bench.build_pipeline(dev)
     res = {}
-    for name, plan in (("unet", pipe.unet.plan(B, 256, 16, 1)), ("decoder", pipe.vae.decoder_plan(B, 256, 16))):
+    for name, plan in (("unet", pipe.unet.plan(B, 256, 16, 1, sampler=True)), ("decoder", pipe.vae.decoder_plan(B, 256, 16))):
         if name == "unet":
             plan.x_in.normal_(); plan.t_buf.fill_(500.0)
         else:

@@ -12,7 +12,7 @@ if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     dev = torch.device("cuda:0")
     pipe = bench.build_pipeline(dev)
-    plan = pipe.unet.plan(B, 256, 16, 1)
+    plan = pipe.unet.plan(B, 256, 16, 1, sampler=True)
     plan.x_in.normal_(); plan.t_buf.fill_(500.0)
     lib = _lib.lib()
     lib.rldm_fused_debug.restype = ctypes.c_int

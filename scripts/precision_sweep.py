@@ -46,7 +46,7 @@ if __name__ == "__main__":
     t_unet, t_dec, e_unet, e_dec = {}, {}, {}, {}
     for low in (3, 2, 1):
         for top in (3, 2, 1):
-            engine.PRECISION, engine.PRECISION_TOP = low, top
+            engine.PRECISION, engine.PRECISION_TOP, engine.PRECISION_TOP_SAMPLER = low, top, top
             u.invalidate_plans()
             f = u(xf.cuda(), torch.tensor(500)).sample
             sch = R.DPMSolverMultistepScheduler(timestep_spacing="leading")

@@ -11,7 +11,7 @@ which = sys.argv[1] if len(sys.argv) > 1 else "both"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 dev = torch.device("cuda:0")
 pipe = bench.build_pipeline(dev)
-uplan = pipe.unet.plan(B, 256, 16, 1)
+uplan = pipe.unet.plan(B, 256, 16, 1, sampler=True)
 dplan = pipe.vae.decoder_plan(B, 256, 16)
 uplan.x_in.normal_(); uplan.t_buf.fill_(500.0); dplan.z_in.normal_()
 for _ in range(2):

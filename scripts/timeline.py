@@ -59,7 +59,7 @@ if __name__ == "__main__":
         uplan.x_in.normal_(); uplan.t_buf.fill_(500.0)
         plans = (("unet_c2", uplan),)
     else:
-        uplan = pipe.unet.plan(B, 256, 16, 1)
+        uplan = pipe.unet.plan(B, 256, 16, 1, sampler=True)
         dplan = pipe.vae.decoder_plan(B, 256, 16)
         uplan.x_in.normal_(); uplan.t_buf.fill_(500.0); dplan.z_in.normal_()
         plans = (("unet", uplan), ("decoder", dplan))

@@ -24,6 +24,7 @@ def x3(monkeypatch):
     from rangeldm_b200 import engine
     monkeypatch.setattr(engine, "PRECISION", 3)
     monkeypatch.setattr(engine, "PRECISION_TOP", 3)
+    monkeypatch.setattr(engine, "PRECISION_TOP_SAMPLER", 3)
     monkeypatch.setattr(engine, "PRECISION_VAE", 3)
     yield
 
