@@ -117,6 +117,31 @@ int rldm_conv_tc_ex(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt
                     int stride, int pad_lo, int circular, int split_k, double* stats, const uint16_t* sc_x,
                     const uint16_t* sc_x_lo, const uint16_t* sc_wgt, int sc_cin, int terms, void* stream);
 
+/* rldm_conv_tc_ex that PRODUCES ITS OWN OPERAND: instead of a rldm_prep launch in front of the convolution, every CTA of
+ * the small-layer kernel turns the fp32 source into the part of the fp16 operand it is about to read (its tile's input
+ * window, halo columns included, x the channel chunks of its K slice), writes it to `x` (+ `x_lo`), which are then
+ * caller-provided SCRATCH buffers of the operand's shape (B, W+2, H, Cin), and loads it back by TMA.  Same arithmetic
+ * as rldm_prep followed by rldm_conv_tc_ex (bit-identical operands).
+ *   src    : source of the convolution's operand: concat(x0 (B,W/up,H/up,c0), x1 (.., c1)) fp32 cl, optional GroupNorm
+ *            (channel-pair moments pairs0/pairs1 as accumulated by the producing epilogues, gamma, beta, eps, G groups),
+ *            optional SiLU, nearest upsampling up in {1,2}, circular / zero halo
+ *   sc_src : source of the folded 1x1 shortcut's operand (raw cast: no norm), written to sc_x (+ sc_x_lo); or NULL
+ * Only layers that run on the small-layer kernel qualify (rldm_conv_tc_fusable() == 1: fewer 128 x 128 tiles than SMs,
+ * Cin and sc_cin <= 512); others return an error. */
+typedef struct rldm_conv_src {
+  const float* x0; const float* x1;
+  const double* pairs0; const double* pairs1;
+  const float* gamma; const float* beta;
+  float eps;
+  int c0, c1, G, silu, up, circular;
+} rldm_conv_src;
+int rldm_conv_tc_fused(const rldm_conv_src* src, const rldm_conv_src* sc_src, const uint16_t* x, const uint16_t* x_lo,
+                       const uint16_t* wgt, const float* bias, const float* temb, int temb_stride, const float* residual,
+                       float* out, int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo, int circular,
+                       int split_k, double* stats, const uint16_t* sc_x, const uint16_t* sc_x_lo, const uint16_t* sc_wgt,
+                       int sc_cin, int terms, void* stream);
+int rldm_conv_tc_fusable(int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo, int sc_cin, int has_residual);
+
 /* CUDA-core restatement of rldm_conv_tc with the identical contract (split_k ignored); used by the
  * GPU tests to isolate tensor-core descriptor bugs from precision, never by the product path. */
 int rldm_conv_ref(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias, const float* temb,
@@ -194,9 +219,9 @@ enum {
 };
 typedef struct rldm_op {
   int32_t kind;
-  int32_t i[15];      /* integer arguments in the order of the matching entry point */
+  int32_t i[23];      /* integer arguments in the order of the matching entry point */
   float f[2];         /* float arguments (eps) */
-  void* p[12];        /* pointer arguments in the order of the matching entry point */
+  void* p[20];        /* pointer arguments in the order of the matching entry point */
   int64_t n;          /* element / byte count where the entry point takes one */
 } rldm_op;
 int rldm_run(const rldm_op* ops, int n_ops, void* stream);

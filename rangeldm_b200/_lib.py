@@ -18,8 +18,16 @@ OP_GN_STATS, OP_PREP, OP_CONV_TC, OP_CONV_IN, OP_CONV_OUT, OP_ATTENTION, OP_TEMB
 
 
 class RldmOp(ctypes.Structure):
-    _fields_ = [("kind", ctypes.c_int32), ("i", ctypes.c_int32 * 15), ("f", ctypes.c_float * 2),
-                ("p", ctypes.c_void_p * 12), ("n", ctypes.c_int64)]
+    _fields_ = [("kind", ctypes.c_int32), ("i", ctypes.c_int32 * 23), ("f", ctypes.c_float * 2),
+                ("p", ctypes.c_void_p * 20), ("n", ctypes.c_int64)]
+
+
+class ConvSrc(ctypes.Structure):
+    """rldm_conv_src (include/rldm.h)"""
+    _fields_ = [("x0", ctypes.c_void_p), ("x1", ctypes.c_void_p), ("pairs0", ctypes.c_void_p), ("pairs1", ctypes.c_void_p),
+                ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p), ("eps", ctypes.c_float), ("c0", ctypes.c_int),
+                ("c1", ctypes.c_int), ("G", ctypes.c_int), ("silu", ctypes.c_int), ("up", ctypes.c_int),
+                ("circular", ctypes.c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/rldm.h declares
@@ -36,6 +44,9 @@ SIGNATURES = {
                               + [c_int] * 10 + [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "rldm_conv_tc_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
                         + [c_int] * 10 + [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "rldm_conv_tc_fused": (c_int, [c_void_p, c_void_p] + [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+                           + [c_int] * 10 + [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "rldm_conv_tc_fusable": (c_int, [c_int] * 10),
     "rldm_conv_ref": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
                       + [c_int] * 9 + [c_void_p]),
     "rldm_conv_in": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 5

@@ -29,7 +29,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "blocks.cuh"
 
 namespace rldm {
 
@@ -70,6 +70,18 @@ struct ConvParams {
 struct ConvMaps {
   CUtensorMap a, alo, b, a2, a2lo, b2;
 };
+
+// Operand production inside the small-layer kernel (replaces a rldm_prep launch in front of it): the CTA turns the fp32
+// source(s) into exactly the part of the fp16 W-padded operand it will read -- the input window of its 128-pixel tile
+// (halo columns included) x the 64-channel chunks of its own K slice -- writes it to the operand buffer and loads it
+// back by TMA like any other operand.  Neighbouring CTAs write the same values to the halo columns they share; nothing
+// crosses CTAs, so no grid-wide dependency is created.  `main`: the convolution's operand (GroupNorm-apply + SiLU +
+// concat + nearest-2x + circular halo, as rldm_prep); `sc`: the raw operand of a folded 1x1 conv_shortcut.
+struct ConvFused {
+  PrepArgs main, sc;
+  int main_on, sc_on;
+};
+constexpr int kFusedTabFloats = 1024;           // scale/shift of up to 512 channels
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   uint32_t r;
@@ -120,7 +132,7 @@ __device__ __forceinline__ void issue_kstep(uint32_t d_tmem, uint32_t a_addr, ui
 // deterministic), instead of one dependent load at a time.
 template <int BLOCK_N, int STAGES, int TERMS, int NSPLIT>
 __global__ void __launch_bounds__(192, 1)
-conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
+conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __grid_constant__ ConvFused fz) {
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   constexpr int XP = x_parts(TERMS), WP = w_parts(TERMS);
   constexpr int kStageBytes = XP * kABytes + WP * kBBytes;    // [X_hi][X_lo][W_hi][W_lo]
@@ -145,6 +157,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
   float* red_s = reinterpret_cast<float*>(tmem_ptr + 4);       // [4][BLOCK_N/2]
   float* red_q = red_s + 4 * (BLOCK_N / 2);
   int* red_b = reinterpret_cast<int*>(red_q + 4 * (BLOCK_N / 2));
+  float* fused_tab = reinterpret_cast<float*>(red_b + 4);      // [kFusedTabFloats]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -202,6 +215,41 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
   }
   pdl_wait();        // everything above overlapped the previous kernel; below we touch its outputs
   if (dbg && threadIdx.x == 0) p.dbg[1] = clock64();
+
+  if (fz.main_on | fz.sc_on) {
+    // ---- in-kernel operand production (see ConvFused): the four epilogue warps, idle until the K loop ends ----
+    if (warp >= 2) {
+      const int tid = threadIdx.x - 64;
+      const int taps = p.ks * p.ks;
+      const int q0 = m0 / p.Ho, b0 = q0 / p.Wo, wo0 = q0 - b0 * p.Wo;
+      const int nb = p.pix_per_img >= kBlockM ? 1 : kBlockM / p.pix_per_img;
+      const int ncols = p.pix_per_img >= kBlockM ? kBlockM / p.Ho : p.Wo;
+      const int n_img = p.M_total / p.pix_per_img;
+      const int Hop = p.Ho * p.stride;                      // operand rows per column
+      const int b_end = min(b0 + nb, n_img);
+      const int main_end = min(it1, p.main_iters);
+      if (fz.main_on && it0 < main_end) {
+        const int ch_lo = (it0 / taps) * kBlockK, ch_hi = ((main_end - 1) / taps + 1) * kBlockK;
+        const int first = p.stride * wo0 - p.pad_lo + 1;    // padded column of tap ti = 0
+        const int col_lo = max(first, 0), col_hi = min(first + (p.ks - 1) + ncols * p.stride, p.W_in + 2);
+        for (int b = b0; b < b_end; ++b) {
+          prep_range<false>(fz.main, b, col_lo * Hop, col_hi * Hop, ch_lo, ch_hi, fused_tab, tid, 128, 3);
+          asm volatile("bar.sync 3, 128;" ::: "memory");    // scale / shift table reusable
+        }
+      }
+      const int sc_begin = max(it0, p.main_iters);
+      if (fz.sc_on && sc_begin < it1) {
+        const int ch_lo = (sc_begin - p.main_iters) * kBlockK, ch_hi = (it1 - p.main_iters) * kBlockK;
+        for (int b = b0; b < b_end; ++b) {
+          prep_range<false>(fz.sc, b, (wo0 + 1) * p.Ho, (wo0 + 1 + ncols) * p.Ho, ch_lo, ch_hi, fused_tab, tid, 128, 3);
+          asm volatile("bar.sync 3, 128;" ::: "memory");
+        }
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores -> TMA (async proxy) reads below
+    }
+    if (warp != 1) asm volatile("bar.sync 2, 160;" ::: "memory");   // producer warp + the four writer warps
+    if (warp == 0) asm volatile("fence.proxy.async;" ::: "memory");
+  }
 
   // epilogue coordinates (meaningful for warps >= 2)
   const int ew = (warp - 2) & 3;
@@ -1025,7 +1073,7 @@ constexpr int conv_stage_bytes(int bn, int terms) { return x_parts(terms) * kABy
 constexpr int conv_stages(int bn, int terms) { return (bn == 128 && terms == 3) ? 3 : 4; }
 constexpr int conv_smem(int bn, int terms) {
   // pipeline stages (+ alignment slack) + barriers/TMEM pointer + the per-warp GroupNorm-moment scratch
-  return conv_stages(bn, terms) * conv_stage_bytes(bn, terms) + 1024 + 256 + 2 * 4 * (bn / 2) * 4 + 64;
+  return conv_stages(bn, terms) * conv_stage_bytes(bn, terms) + 1024 + 256 + 2 * 4 * (bn / 2) * 4 + 64 + kFusedTabFloats * 4;
 }
 constexpr int pers_stage_bytes(int bn, int terms, int mt) { return mt * x_parts(terms) * kABytes + w_parts(terms) * bn * kBlockK * 2; }
 constexpr int pers_fixed(int bn) { return kBlockM * 36 * 4 + 256 + 2 * 4 * (bn / 2) * 4 + 64 + 1024; }
@@ -1034,7 +1082,7 @@ constexpr int pers_stages(int bn, int terms, int mt) {
 }
 
 template <int BLOCK_N, int TERMS, int NSPLIT>
-static int launch_conv_n(const ConvMaps& tm, const ConvParams& p, cudaStream_t st) {
+static int launch_conv_n(const ConvMaps& tm, const ConvParams& p, const ConvFused& fz, cudaStream_t st) {
   constexpr int STAGES = conv_stages(BLOCK_N, TERMS);
   constexpr int smem = conv_smem(BLOCK_N, TERMS);
   static bool attr_set = false;
@@ -1065,17 +1113,17 @@ static int launch_conv_n(const ConvMaps& tm, const ConvParams& p, cudaStream_t s
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  RLDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, STAGES, TERMS, NSPLIT>, tm, p));
+  RLDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, STAGES, TERMS, NSPLIT>, tm, p, fz));
   return 0;
 }
 
 template <int BLOCK_N, int TERMS>
-static int launch_conv(const ConvMaps& tm, const ConvParams& p, int split, cudaStream_t st) {
+static int launch_conv(const ConvMaps& tm, const ConvParams& p, const ConvFused& fz, int split, cudaStream_t st) {
   switch (split) {
-    case 1: return launch_conv_n<BLOCK_N, TERMS, 1>(tm, p, st);
-    case 2: return launch_conv_n<BLOCK_N, TERMS, 2>(tm, p, st);
-    case 4: return launch_conv_n<BLOCK_N, TERMS, 4>(tm, p, st);
-    default: return launch_conv_n<BLOCK_N, TERMS, 8>(tm, p, st);
+    case 1: return launch_conv_n<BLOCK_N, TERMS, 1>(tm, p, fz, st);
+    case 2: return launch_conv_n<BLOCK_N, TERMS, 2>(tm, p, fz, st);
+    case 4: return launch_conv_n<BLOCK_N, TERMS, 4>(tm, p, fz, st);
+    default: return launch_conv_n<BLOCK_N, TERMS, 8>(tm, p, fz, st);
   }
 }
 
@@ -1146,7 +1194,10 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
                         const float* temb, int temb_stride, const float* residual, float* out,
                         int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
                         int circular, int split_k, double* stats, const uint16_t* sc_x, const uint16_t* sc_x_lo,
-                        const uint16_t* sc_wgt, int sc_cin, int terms, void* stream) {
+                        const uint16_t* sc_wgt, int sc_cin, int terms, const rldm_conv_src* src, const rldm_conv_src* sc_src,
+                        bool query_only, void* stream) {
+  // query_only: no launch; returns 0 when this layer would run on the small-layer kernel (the one that can produce its
+  // own operand from `src`), 1 otherwise
   if (terms == 0) terms = x_lo ? 3 : 1;          // legacy entry points: the operand planes say it
   RLDM_CHECK(terms >= 1 && terms <= 3, "conv_tc: terms must be 1, 2 or 3 (got %d)", terms);
   RLDM_CHECK(terms != 3 || x_lo, "conv_tc: split-fp16 x3 needs the low-order activation plane");
@@ -1164,8 +1215,8 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
   RLDM_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0 &&
              (reinterpret_cast<uintptr_t>(wgt) & 15) == 0 &&
              (reinterpret_cast<uintptr_t>(out) & 15) == 0, "conv_tc: pointers must be 16 B aligned");
-  EncodeTiledFn encode = get_encode();
-  RLDM_CHECK(encode != nullptr, "conv_tc: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  EncodeTiledFn encode = query_only ? nullptr : get_encode();
+  RLDM_CHECK(query_only || encode != nullptr, "conv_tc: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   const EnvSwitches& sw = env();
   const int n_sms = sw.n_sms;
   auto allowed = [&](int mode) { return mode == 1 || (mode == 2 && !residual); };      // 1: on, 2: "nores", 0: off
@@ -1208,6 +1259,8 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
                          split_k <= 1 && tiles_h > n_sms && sw.conv_persistent && BN == 128 && nws >= 3 &&
                          allowed(sw.conv_wt) && allowed(sw.conv_wt_halo);
     if (halo_wt) {
+      if (query_only) return 1;
+      RLDM_CHECK(!src && !sc_src, "conv_tc: in-kernel operand production is a feature of the small-layer kernel only");
       ConvMaps tmh;
       const int cols = 2 * (kBlockM / Ho);
       for (int part = 0; part < xp; ++part) {
@@ -1298,6 +1351,8 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
   while (split > p.total_iters) split /= 2;
   // more tiles than SMs and no K split: persistent CTAs with a double-buffered TMEM accumulator
   if (split == 1 && tiles > n_sms && sw.conv_persistent) {
+    if (query_only) return 1;
+    RLDM_CHECK(!src && !sc_src, "conv_tc: in-kernel operand production is a feature of the small-layer kernel only");
     // Cout tiles of 128 and whole 256-pixel units inside one image: roles swapped (weights = M side, N = 256 pixels)
     if (BN == 128 && p.M_total % 256 == 0 && pix % 256 == 0 && allowed(sw.conv_wt)) {
       if (int rc = build_maps()) return rc;
@@ -1319,9 +1374,36 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
     if (BN == 128) { RLDM_BY_TERMS(terms, return (launch_conv_persistent<128, T_, 1>(tm, p, ctas, st))); }
     RLDM_BY_TERMS(terms, return (launch_conv_persistent<64, T_, 1>(tm, p, ctas, st)));
   }
+  if (query_only) return (Cin <= 512 && sc_cin <= 512) ? 0 : 1;
+  ConvFused fz;
+  memset(&fz, 0, sizeof(fz));
+  auto fill = [&](PrepArgs& a, const rldm_conv_src* s, const uint16_t* o_hi, const uint16_t* o_lo, int C, int Wop, int Hop) -> int {
+    RLDM_CHECK(s->x0 != nullptr && s->c0 % 8 == 0 && s->c1 % 8 == 0 && s->c0 + s->c1 == C && (s->x1 != nullptr || s->c1 == 0),
+               "conv_tc: source channels %d + %d do not make the operand's %d", s->c0, s->c1, C);
+    RLDM_CHECK(s->up == 1 || s->up == 2, "conv_tc: source up must be 1 or 2");
+    RLDM_CHECK(Wop % s->up == 0 && Hop % s->up == 0, "conv_tc: operand grid not divisible by the upsampling factor");
+    RLDM_CHECK(!s->pairs0 || (s->gamma && s->beta && s->G > 0 && C % s->G == 0 && (C / s->G) % 2 == 0 && (s->c1 == 0 || s->pairs1)),
+               "conv_tc: GroupNorm of the source needs gamma/beta/G, an even group size and moments for both concat halves");
+    RLDM_CHECK(C <= kFusedTabFloats / 2, "conv_tc: in-kernel operand production supports up to %d channels", kFusedTabFloats / 2);
+    a.x0 = s->x0; a.x1 = s->x1; a.sums = nullptr; a.pairs0 = s->pairs0; a.pairs1 = s->pairs1; a.gamma = s->gamma; a.beta = s->beta;
+    a.out = reinterpret_cast<__half*>(const_cast<uint16_t*>(o_hi)); a.out_lo = reinterpret_cast<__half*>(const_cast<uint16_t*>(o_lo));
+    a.raw = nullptr; a.raw_lo = nullptr;
+    a.eps = s->eps; a.c0 = s->c0; a.c1 = s->c1; a.G = s->G; a.silu = s->silu; a.up = s->up; a.circular = s->circular;
+    a.W = Wop / s->up; a.H = Hop / s->up; a.pix_per_block = 0;
+    return 0;
+  };
+  if (src) {
+    if (int rc = fill(fz.main, src, x, x_lo, Cin, W, H)) return rc;
+    fz.main_on = 1;
+  }
+  if (sc_src) {
+    RLDM_CHECK(sc_x != nullptr, "conv_tc: a shortcut source needs the shortcut operand buffers and weights");
+    if (int rc = fill(fz.sc, sc_src, sc_x, sc_x_lo, sc_cin, W, H)) return rc;
+    fz.sc_on = 1;
+  }
   if (int rc = build_maps()) return rc;
-  if (BN == 128) { RLDM_BY_TERMS(terms, return (launch_conv<128, T_>(tm, p, split, st))); }
-  RLDM_BY_TERMS(terms, return (launch_conv<64, T_>(tm, p, split, st)));
+  if (BN == 128) { RLDM_BY_TERMS(terms, return (launch_conv<128, T_>(tm, p, fz, split, st))); }
+  RLDM_BY_TERMS(terms, return (launch_conv<64, T_>(tm, p, fz, split, st)));
 }
 
 extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias,
@@ -1329,7 +1411,7 @@ extern "C" int rldm_conv_tc(const uint16_t* x, const uint16_t* x_lo, const uint1
                             int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
                             int circular, int split_k, double* stats, void* stream) {
   return conv_tc_impl(x, x_lo, wgt, bias, temb, temb_stride, residual, out, B, W, H, Cin, Cout, ks, stride, pad_lo,
-                      circular, split_k, stats, nullptr, nullptr, nullptr, 0, 0, stream);
+                      circular, split_k, stats, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, false, stream);
 }
 
 extern "C" int rldm_conv_tc_shortcut(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias,
@@ -1338,7 +1420,7 @@ extern "C" int rldm_conv_tc_shortcut(const uint16_t* x, const uint16_t* x_lo, co
                                      int circular, int split_k, double* stats, const uint16_t* sc_x,
                                      const uint16_t* sc_x_lo, const uint16_t* sc_wgt, int sc_cin, void* stream) {
   return conv_tc_impl(x, x_lo, wgt, bias, temb, temb_stride, residual, out, B, W, H, Cin, Cout, ks, stride, pad_lo,
-                      circular, split_k, stats, sc_x, sc_x_lo, sc_wgt, sc_cin, 0, stream);
+                      circular, split_k, stats, sc_x, sc_x_lo, sc_wgt, sc_cin, 0, nullptr, nullptr, false, stream);
 }
 
 extern "C" int rldm_conv_tc_ex(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias,
@@ -1347,5 +1429,25 @@ extern "C" int rldm_conv_tc_ex(const uint16_t* x, const uint16_t* x_lo, const ui
                                int circular, int split_k, double* stats, const uint16_t* sc_x,
                                const uint16_t* sc_x_lo, const uint16_t* sc_wgt, int sc_cin, int terms, void* stream) {
   return conv_tc_impl(x, x_lo, wgt, bias, temb, temb_stride, residual, out, B, W, H, Cin, Cout, ks, stride, pad_lo,
-                      circular, split_k, stats, sc_x, sc_x_lo, sc_wgt, sc_cin, terms, stream);
+                      circular, split_k, stats, sc_x, sc_x_lo, sc_wgt, sc_cin, terms, nullptr, nullptr, false, stream);
+}
+
+extern "C" int rldm_conv_tc_fused(const rldm_conv_src* src, const rldm_conv_src* sc_src, const uint16_t* x, const uint16_t* x_lo,
+                                  const uint16_t* wgt, const float* bias, const float* temb, int temb_stride,
+                                  const float* residual, float* out, int B, int W, int H, int Cin, int Cout, int ks, int stride,
+                                  int pad_lo, int circular, int split_k, double* stats, const uint16_t* sc_x,
+                                  const uint16_t* sc_x_lo, const uint16_t* sc_wgt, int sc_cin, int terms, void* stream) {
+  return conv_tc_impl(x, x_lo, wgt, bias, temb, temb_stride, residual, out, B, W, H, Cin, Cout, ks, stride, pad_lo,
+                      circular, split_k, stats, sc_x, sc_x_lo, sc_wgt, sc_cin, terms, src, sc_src, false, stream);
+}
+
+extern "C" int rldm_conv_tc_fusable(int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo, int sc_cin,
+                                    int has_residual) {
+  // dummy 16 B-aligned, non-NULL pointers: the query path dereferences nothing
+  static const uint16_t* kDummy = reinterpret_cast<const uint16_t*>(static_cast<uintptr_t>(256));
+  const int rc = conv_tc_impl(kDummy, nullptr, kDummy, nullptr, nullptr, 0, has_residual ? reinterpret_cast<const float*>(kDummy) : nullptr,
+                              reinterpret_cast<float*>(const_cast<uint16_t*>(kDummy)), B, W, H, Cin, Cout, ks, stride, pad_lo, 1, 0,
+                              nullptr, sc_cin ? kDummy : nullptr, nullptr, sc_cin ? kDummy : nullptr, sc_cin, 1, nullptr, nullptr, true,
+                              nullptr);
+  return rc == 0 ? 1 : 0;
 }

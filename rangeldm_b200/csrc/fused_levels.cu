@@ -422,7 +422,7 @@ struct FConvGeom {
 static bool fused_conv_geom(const rldm_op& o, FConvGeom& g) {
   g.B = o.i[1]; g.W = o.i[2]; g.H = o.i[3]; g.Cin = o.i[4]; g.Cout = o.i[5]; g.ks = o.i[6]; g.stride = o.i[7];
   g.pad_lo = o.i[8]; g.sc_cin = o.i[11]; g.terms = o.i[12];
-  if (o.i[10] != 0) return false;                                   // explicit split_k: stand-alone kernel
+  if (o.i[10] != 0 || o.p[11] || o.p[17]) return false;             // explicit split_k / own operand production: stand-alone kernel
   if (g.terms < 1 || g.terms > 3) return false;
   if (g.terms == 3 && !o.p[6]) return false;
   if ((g.ks != 1 && g.ks != 3) || (g.stride != 1 && g.stride != 2)) return false;

@@ -1384,6 +1384,20 @@ static int run_ops(const rldm_op* ops, int n_ops, unsigned long long* stamps, vo
                        stream);
         break;
       case RLDM_OP_CONV_TC:
+        if (o.p[11] || o.p[17]) {       // the convolution produces its own operand (no rldm_prep in front of it)
+          rldm_conv_src ms, ss;
+          ms.x0 = (const float*)o.p[11]; ms.x1 = (const float*)o.p[12]; ms.pairs0 = (const double*)o.p[13];
+          ms.pairs1 = (const double*)o.p[14]; ms.gamma = (const float*)o.p[15]; ms.beta = (const float*)o.p[16];
+          ms.eps = o.f[0]; ms.c0 = o.i[13]; ms.c1 = o.i[14]; ms.G = o.i[15]; ms.silu = o.i[16]; ms.up = o.i[17]; ms.circular = o.i[9];
+          ss.x0 = (const float*)o.p[17]; ss.x1 = (const float*)o.p[18]; ss.pairs0 = ss.pairs1 = nullptr; ss.gamma = ss.beta = nullptr;
+          ss.eps = 0.f; ss.c0 = o.i[18]; ss.c1 = o.i[19]; ss.G = 0; ss.silu = 0; ss.up = 1; ss.circular = o.i[9];
+          rc = rldm_conv_tc_fused(o.p[11] ? &ms : nullptr, o.p[17] ? &ss : nullptr, (const uint16_t*)o.p[0], (const uint16_t*)o.p[6],
+                                  (const uint16_t*)o.p[1], (const float*)o.p[2], (const float*)o.p[3], o.i[0], (const float*)o.p[4],
+                                  (float*)o.p[5], o.i[1], o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], o.i[7], o.i[8], o.i[9], o.i[10],
+                                  (double*)o.p[7], (const uint16_t*)o.p[8], (const uint16_t*)o.p[9], (const uint16_t*)o.p[10],
+                                  o.i[11], o.i[12], stream);
+          break;
+        }
         rc = rldm_conv_tc_ex((const uint16_t*)o.p[0], (const uint16_t*)o.p[6], (const uint16_t*)o.p[1],
                              (const float*)o.p[2], (const float*)o.p[3], o.i[0], (const float*)o.p[4],
                              (float*)o.p[5], o.i[1], o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], o.i[7], o.i[8], o.i[9],

@@ -64,6 +64,10 @@ FUSE_STATS = os.environ.get("RLDM_FUSE_STATS", "1") != "0"
 # ResnetBlock2D.conv_shortcut folded into conv2's launch (RLDM_FUSE_SHORTCUT=0: separate 1x1 launch + fp32 residual)
 FUSE_SHORTCUT = os.environ.get("RLDM_FUSE_SHORTCUT", "1") != "0"
 FUSE_CONV_OUT = os.environ.get("RLDM_FUSE_CONV_OUT", "1") != "0"
+# The convolutions of the small layers (fewer 128 x 128 tiles than SMs: UNet levels 1..n) produce their own fp16 operand
+# from the fp32 stream inside the kernel (rldm_conv_tc_fused) instead of reading the output of a rldm_prep launch:
+# one graph node per convolution instead of two.  RLDM_FUSE_PREP=0 keeps the separate launches.
+FUSE_PREP = os.environ.get("RLDM_FUSE_PREP", "1") != "0"
 # RLDM_FUSE_LEVELS=1 (experiment, default off): runs of small consecutive ops (UNet levels 1..n) compiled into ONE
 # persistent launch each (csrc/fused_levels.cu).  Correct (tests/test_fused_gpu.py) but measured SLOWER on B200: a
 # grid-wide barrier costs 2.0-2.3 us against ~3 us for a PDL kernel boundary, and every convolution needs two of them
@@ -216,6 +220,19 @@ class Program:
         _lib.check(_lib.lib().rldm_run(self.arr, len(self.exec_ops), _lib.stream_ptr()))
 
 
+class Operand:
+    """fp16 tensor-core operand pair (hi, lo) in the W-padded layout (B, W+2, H, C).  While `src` is set the operand
+    has not been produced yet: the consuming convolution produces it itself (small-layer kernel) or `Builder` emits
+    the rldm_prep launch when it turns out that it cannot."""
+    __slots__ = ("hi", "lo", "src")
+
+    def __init__(self, hi, lo, src=None):
+        self.hi, self.lo, self.src = hi, lo, src
+
+    def __getitem__(self, k):
+        return (self.hi, self.lo)[k]
+
+
 class Act:
     """Channels-last fp32 activation (B, W, H, C).  `stats` = arena slice [B][C/2][2] when the producing conv already
     accumulated the channel-pair moments of this tensor in its epilogue."""
@@ -293,7 +310,7 @@ class Builder:
 
     def alloc_half(self, shape, terms):
         """(hi, lo) fp16 operand pair; lo only exists for a split-fp16 x3 consumer."""
-        return (self.pg.alloc(shape, torch.float16), self.pg.alloc(shape, torch.float16) if terms == 3 else None)
+        return Operand(self.pg.alloc(shape, torch.float16), self.pg.alloc(shape, torch.float16) if terms == 3 else None)
 
     def free_half(self, pair):
         self.pg.free(pair[0])
@@ -315,10 +332,34 @@ class Builder:
                     p=(x0.t, x1.t if x1 is not None else None, sums))
         return sums
 
-    def prep(self, x0, x1=None, norm=None, silu=False, up=1, circular=True, also_raw=False, terms=3, raw_terms=3):
+    def prep(self, x0, x1=None, norm=None, silu=False, up=1, circular=True, also_raw=False, terms=3, raw_terms=3,
+             defer=False):
         """-> fp16 operand pair in the W-padded layout (B, W*up + 2, H*up, C0+C1); also_raw=True returns a
         second pair holding the un-normalised input (1x1 shortcut operand) written by the same launch.  `terms` /
-        `raw_terms`: precision of the consuming convolutions (the lo plane is written for 3 only)."""
+        `raw_terms`: precision of the consuming convolutions (the lo plane is written for 3 only).
+        defer=True: no launch is emitted yet -- the operands carry their recipe (`Operand.src`) and the consuming
+        `conv()` decides (in-kernel production, or `_materialize`)."""
+        c1 = x1.C if x1 is not None else 0
+        C = x0.C + c1
+        shape = (self.B, x0.W * up + 2, x0.H * up, C)
+        out = self.alloc_half(shape, terms)
+        raw = self.alloc_half(shape, raw_terms) if also_raw else None
+        spec = dict(x0=x0, x1=x1, norm=norm, silu=silu, up=up, circular=circular)
+        fused_moments = norm is None or (x0.stats is not None and (x1 is None or x1.stats is not None)
+                                         and (C // norm.num_groups) % 2 == 0 and x0.C % 2 == 0)
+        out.src = spec
+        if raw is not None:
+            raw.src = dict(x0=x0, x1=x1, norm=None, silu=False, up=up, circular=circular)
+        if not (defer and FUSE_PREP and CONV_KIND == _lib.OP_CONV_TC and fused_moments):
+            self._materialize(out, raw)
+        return (out, raw) if also_raw else out
+
+    def _materialize(self, out, raw=None):
+        """Emit the rldm_prep launch that produces `out` (and, from the same read, the raw operand `raw` OF THE SAME
+        SOURCE tensors)."""
+        assert raw is None or raw.src is None or (raw.src["x0"] is out.src["x0"] and raw.src["x1"] is out.src["x1"])
+        sp = out.src
+        x0, x1, norm, up = sp["x0"], sp["x1"], sp["norm"], sp["up"]
         c1 = x1.C if x1 is not None else 0
         C = x0.C + c1
         sums = pairs0 = pairs1 = gamma = beta = None
@@ -332,12 +373,18 @@ class Builder:
             else:
                 sums = self.gn_stats(x0, x1, G)
             gamma, beta, eps = self.f32(norm.weight), self.f32(norm.bias), norm.eps
-        out = self.alloc_half((self.B, x0.W * up + 2, x0.H * up, C), terms)
-        raw = self.alloc_half((self.B, x0.W * up + 2, x0.H * up, C), raw_terms) if also_raw else (None, None)
-        self.pg.add(_lib.OP_PREP, i=(x0.C, c1, G, int(silu), up, self.B, x0.W, x0.H, int(circular)), f=(eps,),
-                    p=(x0.t, x1.t if x1 is not None else None, sums, gamma, beta, out[0], out[1], raw[0], raw[1],
-                       pairs0, pairs1))
-        return (out, raw) if also_raw else out
+        with_raw = raw is not None and raw.src is not None
+        self.pg.add(_lib.OP_PREP, i=(x0.C, c1, G, int(sp["silu"]), up, self.B, x0.W, x0.H, int(sp["circular"])), f=(eps,),
+                    p=(x0.t, x1.t if x1 is not None else None, sums, gamma, beta, out.hi, out.lo,
+                       raw.hi if with_raw else None, raw.lo if with_raw else None, pairs0, pairs1))
+        out.src = None
+        if with_raw:
+            raw.src = None
+
+    def _fusable(self, W, H, cin, cout, ks, stride, pad_lo, sc_cin, has_residual):
+        """True when this convolution runs on the small-layer kernel, which can produce its own operand."""
+        return bool(FUSE_PREP and CONV_KIND == _lib.OP_CONV_TC and
+                    _lib.lib().rldm_conv_tc_fusable(self.B, W, H, cin, cout, ks, stride, pad_lo, sc_cin, int(has_residual)))
 
     def conv(self, xh, W, H, conv=None, packed=None, cin=None, cout=None, ks=3, stride=1, pad_lo=1, circular=True,
              temb=None, residual=None, stats=False, shortcut=None, terms=3):
@@ -353,6 +400,21 @@ class Builder:
                 raise NotImplementedError("conv with groups/dilation/padding_mode is outside the reference path")
         else:
             wt, bias = packed
+        # operands that have not been produced yet: in-kernel production on the small-layer kernel, else a prep launch
+        sc_opnd = shortcut[0] if shortcut is not None else None
+        sc_cin_q = shortcut[1].in_channels if shortcut is not None else 0
+        main_src = sc_src = None
+        if xh.src is not None or (sc_opnd is not None and sc_opnd.src is not None):
+            if self._fusable(W, H, cin, cout, ks, stride, pad_lo, sc_cin_q, residual is not None):
+                main_src, sc_src = xh.src, (sc_opnd.src if sc_opnd is not None else None)
+                xh.src = None
+                if sc_opnd is not None:
+                    sc_opnd.src = None
+            else:
+                if xh.src is not None:
+                    self._materialize(xh)
+                if sc_opnd is not None and sc_opnd.src is not None:
+                    self._materialize(sc_opnd)
         Wo, Ho = W // stride, H // stride
         out = self.pg.alloc((self.B, Wo, Ho, cout))
         temb_t, temb_stride = (None, 0)
@@ -379,8 +441,23 @@ class Builder:
         else:
             assert shortcut is None
         assert (xh[1] is not None) == (terms == 3), "operand planes do not match the layer's precision"
-        self.pg.add(kind, i=ints, p=(xh[0], wt, bias, temb_t, residual.t if residual is not None else None, out,
-                                     xh[1], st) + sc_ptrs, launches=1)
+        src_ptrs, feps = (), ()
+        if main_src is not None or sc_src is not None:
+            def act_t(a):
+                return a.t if a is not None else None
+            m = main_src or dict(x0=None, x1=None, norm=None, silu=False, up=1)
+            norm = m["norm"]
+            mx0, mx1 = m["x0"], m["x1"]
+            sx0, sx1 = (sc_src["x0"], sc_src["x1"]) if sc_src is not None else (None, None)
+            src_ptrs = (act_t(mx0), act_t(mx1), mx0.stats if norm is not None else None,
+                        mx1.stats if (norm is not None and mx1 is not None) else None,
+                        self.f32(norm.weight) if norm is not None else None, self.f32(norm.bias) if norm is not None else None,
+                        act_t(sx0), act_t(sx1))
+            ints += [mx0.C if mx0 is not None else 0, mx1.C if mx1 is not None else 0, norm.num_groups if norm is not None else 0,
+                     int(m["silu"]), m["up"], sx0.C if sx0 is not None else 0, sx1.C if sx1 is not None else 0]
+            feps = (norm.eps if norm is not None else 0.0,)
+        self.pg.add(kind, i=ints, f=feps, p=(xh[0], wt, bias, temb_t, residual.t if residual is not None else None, out,
+                                             xh[1], st) + sc_ptrs + src_ptrs, launches=1)
         return Act(out, self.B, Wo, Ho, cout, st)
 
     # ---- blocks ----------------------------------------------------------------------------
@@ -392,9 +469,13 @@ class Builder:
         t1 = t2 = ts = self.terms(x0.W)
         xr = None
         if rb.conv_shortcut is not None:
-            a1, xr = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1), also_raw=True, terms=t1, raw_terms=ts)
+            a1, xr = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1), also_raw=True, terms=t1, raw_terms=ts,
+                               defer=True)
         else:
-            a1 = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1), terms=t1)
+            a1 = self.prep(x0, x1, rb.norm1, silu=True, circular=circ(rb.conv1), terms=t1, defer=True)
+        c1m = rb.conv1
+        if a1.src is not None and not self._fusable(x0.W, x0.H, c1m.in_channels, c1m.out_channels, 3, 1, 1, 0, False):
+            self._materialize(a1, xr)       # one launch for the operand and the shortcut's raw operand, as before
         temb = None
         if rb.time_emb_proj is not None and self.temb is not None:
             tt, T = self.temb
@@ -402,13 +483,14 @@ class Builder:
             temb = (tt.view(-1)[off:], T)
         h = self.conv(a1, x0.W, x0.H, rb.conv1, temb=temb, stats=True, terms=t1)
         self.free_half(a1)
-        a2 = self.prep(h, None, rb.norm2, silu=True, circular=circ(rb.conv2), terms=t2)
-        pg.free(h.t)
+        a2 = self.prep(h, None, rb.norm2, silu=True, circular=circ(rb.conv2), terms=t2, defer=True)
         if fold:
             # the 1x1 conv_shortcut rides in conv2's K loop (extra K steps over the raw operand)
             out = self.conv(a2, x0.W, x0.H, rb.conv2, stats=True, shortcut=(xr, rb.conv_shortcut), terms=t2)
             self.free_half(xr)
         elif rb.conv_shortcut is not None:
+            if xr.src is not None:
+                self._materialize(xr)
             sc = self.conv(xr, x0.W, x0.H, rb.conv_shortcut, terms=ts)
             self.free_half(xr)
             out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=sc, stats=True, terms=t2)
@@ -417,6 +499,7 @@ class Builder:
             assert x1 is None
             out = self.conv(a2, x0.W, x0.H, rb.conv2, residual=x0, stats=True, terms=t2)
         self.free_half(a2)
+        pg.free(h.t)                # (after conv2: it may read h itself when it produces its own operand)
         pg.taps.append((rb, out))
         if free_inputs:
             pg.free(x0.t)
@@ -432,7 +515,7 @@ class Builder:
                                       "reference's attention_head_dim=8")
         C = x.C
         t = self.terms(x.W)
-        a = self.prep(x, None, at.group_norm, silu=False, terms=t)
+        a = self.prep(x, None, at.group_norm, silu=False, terms=t, defer=True)
         qkv = self.conv(a, x.W, x.H, packed=self.pack_linear([at.to_q, at.to_k, at.to_v], t), cin=C, cout=3 * C, ks=1,
                         pad_lo=0, terms=t)
         self.free_half(a)
@@ -451,7 +534,7 @@ class Builder:
         """Patched Downsample2D (`ldm/utils.py:107-116`): raw cast + stride-2 conv; padding=0 is the
         VAE-encoder asymmetric pad (pad_lo = 0)."""
         t = self.terms(x.W)
-        xr = self.prep(x, None, None, circular=bool(getattr(ds.conv, "circular", False)), terms=t)
+        xr = self.prep(x, None, None, circular=bool(getattr(ds.conv, "circular", False)), terms=t, defer=True)
         out = self.conv(xr, x.W, x.H, ds.conv, stats=True, terms=t)
         self.free_half(xr)
         self.pg.taps.append((ds, out))
@@ -462,7 +545,7 @@ class Builder:
     def upsample(self, us, x):
         """Upsample2D (`model.py:120-125`): nearest 2x folded into the cast, then 3x3 conv."""
         t = self.terms(x.W * 2)
-        xr = self.prep(x, None, None, up=2, circular=bool(getattr(us.conv, "circular", False)), terms=t)
+        xr = self.prep(x, None, None, up=2, circular=bool(getattr(us.conv, "circular", False)), terms=t, defer=True)
         out = self.conv(xr, x.W * 2, x.H * 2, us.conv, stats=True, terms=t)
         self.free_half(xr)
         self.pg.taps.append((us, out))

@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 def _forward_both(u, x, t, monkeypatch):
     from rangeldm_b200 import _lib, engine
     outs, nodes = [], []
+    monkeypatch.setattr(engine, "FUSE_PREP", False)     # (the experiment fuses whole prep + conv runs instead)
     for fuse in (True, False):
         monkeypatch.setattr(engine, "FUSE_LEVELS", fuse)
         u.invalidate_plans()
@@ -93,6 +94,7 @@ def test_fused_levels_reduced_precision_and_graph_replay(monkeypatch):
         assert relerr(a, b, f"fused_vs_unfused_terms{terms}") < 2e-3
         assert relerr(a, ref, f"fused_terms{terms}_vs_oracle") < 1e-3 and relerr(b, ref) < 1e-3
         monkeypatch.setattr(engine, "FUSE_LEVELS", True)
+        monkeypatch.setattr(engine, "FUSE_PREP", False)
         u.invalidate_plans()
         plan = u.plan(2, 32, 8)
         plan.x_in.copy_(x); plan.t_buf.fill_(300.0)
@@ -127,6 +129,7 @@ def test_fused_conv_matches_standalone_conv(case, terms, monkeypatch):
     import rangeldm_b200 as R
     from rangeldm_b200 import engine, models
     monkeypatch.setattr(engine, "FUSE_LEVELS", True)           # (an opt-in experiment: see engine.FUSE_LEVELS)
+    monkeypatch.setattr(engine, "FUSE_PREP", False)
     B, W, H, Cin, Cout, ks, stride, use_res, use_temb = case
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
@@ -170,3 +173,116 @@ def test_fused_create_rejects_unsupported_ops():
     arr = (RldmOp * 1)(op)
     assert _lib.lib().rldm_fused_create(arr, 1, None, 0, ctypes.byref(h)) != 0 and not h.value
     assert b"cannot run inside a fused segment" in _lib.lib().rldm_last_error()
+
+
+# ---- convolutions that produce their own operand (rldm_conv_tc_fused) -------------------------------------------------
+OWN_OPERAND_CASES = [
+    # B, W, H, C0, C1, Cout, ks, stride, up, norm, silu
+    (8, 32, 2, 256, 0, 256, 3, 1, 1, True, True),       # level 3 ResnetBlock2D conv: GroupNorm + SiLU, two images per tile
+    (8, 32, 2, 256, 256, 256, 3, 1, 1, True, True),     # up-block conv1 over a skip concat (512 channels, K split 8 ways)
+    (3, 64, 4, 256, 128, 256, 3, 1, 1, True, True),     # 384-channel concat: one GroupNorm group straddles the two sources
+    (8, 64, 4, 256, 0, 256, 3, 2, 1, False, False),     # Downsample2D: raw cast, stride 2
+    (8, 32, 2, 256, 0, 256, 3, 1, 2, False, False),     # Upsample2D: nearest 2x folded into the operand production
+    (2, 64, 4, 256, 0, 768, 1, 1, 1, True, False),      # attention: GroupNorm without SiLU, qkv projection
+    (5, 128, 8, 128, 0, 128, 3, 1, 1, True, True),      # level 1, ragged batch: 40 tiles, K split 2
+]
+
+
+def _pair_moments(x):
+    """[B][C/2][2] doubles: (sum, sum of squares) per channel pair over the pixels of (B, W, H, C)."""
+    B, W, H, C = x.shape
+    xd = x.double().reshape(B, W * H, C // 2, 2)
+    return torch.stack([xd.sum((1, 3)), (xd * xd).sum((1, 3))], dim=-1).contiguous()
+
+
+@pytest.mark.parametrize("terms", [3, 1])
+@pytest.mark.parametrize("case", OWN_OPERAND_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_own_operand_matches_prep_then_conv(case, terms, monkeypatch):
+    """A small-layer convolution that turns the fp32 stream into its own fp16 operand inside the kernel against the same
+    convolution behind a rldm_prep launch: the operands are bit-identical, the kernel and its summation order are the
+    same, so the outputs are BIT-IDENTICAL (the GroupNorm moments agree to the order of the double atomics)."""
+    import rangeldm_b200 as R
+    from rangeldm_b200 import engine, models
+    B, W, H, C0, C1, Cout, ks, stride, up, use_norm, silu = case
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    Cin = C0 + C1
+    conv = models.LoRACompatibleConv(Cin, Cout, ks, stride=stride, padding=ks // 2).to(dev)
+    conv.circular = True
+    norm = torch.nn.GroupNorm(32, Cin, eps=1e-5).to(dev) if use_norm else None
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (Cin * ks * ks) ** 0.5)
+        conv.bias.copy_(torch.randn(Cout, generator=g))
+        if norm is not None:
+            norm.weight.copy_(1 + 0.3 * torch.randn(Cin, generator=g)); norm.bias.copy_(0.3 * torch.randn(Cin, generator=g))
+    x0 = (torch.randn(B, W, H, C0, generator=g) * 1.7 + 0.3).to(dev)
+    x1 = torch.randn(B, W, H, C1, generator=g).to(dev) if C1 else None
+    outs = []
+    for own in (True, False):
+        monkeypatch.setattr(engine, "FUSE_PREP", own)
+        pg = engine.Program(dev)
+        bd = engine.Builder(pg, B, cache={}, terms_of=lambda w: terms)
+        a0 = engine.Act(pg.hold(x0.clone()), B, W, H, C0, stats=pg.hold(_pair_moments(x0)))
+        a1 = engine.Act(pg.hold(x1.clone()), B, W, H, C1, stats=pg.hold(_pair_moments(x1))) if C1 else None
+        opnd = bd.prep(a0, a1, norm, silu=silu, up=up, terms=terms, defer=True)
+        out = bd.conv(opnd, W * up, H * up, conv, stats=True, terms=terms)
+        bd.finish()
+        pg.finalize()
+        kinds = [o.kind for o in pg.ops]
+        assert kinds.count(R._lib.OP_PREP) == (0 if own else 1), kinds
+        for _ in range(2):
+            pg.run()
+        torch.cuda.synchronize()
+        outs.append((out.t.clone(), out.stats.clone(), pg))
+    (fa, fs, _), (ua, us, _) = outs
+    assert torch.equal(fa, ua), relerr(fa, ua)
+    assert torch.allclose(fs, us, rtol=1e-9, atol=1e-6)
+    # and against the fp32 PyTorch reference of the same ops
+    xin = x0 if x1 is None else torch.cat([x0, x1], dim=-1)
+    xr = xin.permute(0, 3, 1, 2).cpu()
+    with torch.no_grad():
+        y = xr
+        if norm is not None:
+            y = torch.nn.functional.group_norm(y, 32, norm.weight.cpu(), norm.bias.cpu(), 1e-5)
+        if silu:
+            y = torch.nn.functional.silu(y)
+        if up == 2:
+            y = torch.nn.functional.interpolate(y, scale_factor=2.0, mode="nearest")
+        from oracle.nets import circ_conv2d
+        ref = circ_conv2d(y, conv.weight.cpu(), conv.bias.cpu(), stride, ks // 2)
+    assert relerr(fa.permute(0, 3, 1, 2).cpu(), ref, f"conv_own_operand_terms{terms}") < (1e-5 if terms == 3 else 2e-3)
+
+
+def test_resnet_with_folded_shortcut_own_operands(monkeypatch, x3):
+    """A whole ResnetBlock2D over a skip concat with its 1x1 conv_shortcut folded into conv2: conv1 produces its operand
+    from (h | skip) with GroupNorm + SiLU, conv2 produces BOTH its operand (from conv1's output) and the raw shortcut
+    operand (from (h | skip)) -- against the same block behind rldm_prep launches."""
+    from rangeldm_b200 import engine, models
+    from rangeldm_b200 import _lib
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(77)
+    B, W, H = 8, 64, 4
+    rb = models.ResnetBlock2D(384, 256, 512).to(dev)
+    for prm in rb.parameters():
+        with torch.no_grad():
+            prm.copy_(torch.randn(prm.shape, generator=g) * (0.05 if prm.ndim > 1 else 0.3) + (1.0 if prm.ndim == 1 and prm.numel() in (384, 256) else 0.0))
+    for m in rb.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            m.circular = True
+    x0 = torch.randn(B, W, H, 256, generator=g).to(dev)
+    x1 = torch.randn(B, W, H, 128, generator=g).to(dev)
+    temb = torch.randn(B, 256, generator=g).to(dev)
+    outs = []
+    for own in (True, False):
+        monkeypatch.setattr(engine, "FUSE_PREP", own)
+        pg = engine.Program(dev)
+        bd = engine.Builder(pg, B, cache={})
+        bd.temb, bd.temb_rows = (pg.hold(temb.clone()), 256), {id(rb): 0}
+        a0 = engine.Act(pg.hold(x0.clone()), B, W, H, 256, stats=pg.hold(_pair_moments(x0)))
+        a1 = engine.Act(pg.hold(x1.clone()), B, W, H, 128, stats=pg.hold(_pair_moments(x1)))
+        out = bd.resnet(rb, a0, a1, free_inputs=False)
+        bd.finish(); pg.finalize()
+        assert [o.kind for o in pg.ops].count(_lib.OP_PREP) == (0 if own else 2)
+        pg.run(); torch.cuda.synchronize()
+        outs.append(out.t.clone())
+    assert relerr(outs[0], outs[1], "resnet_own_operands_vs_prep") < 2e-6
