@@ -91,14 +91,40 @@ __device__ __forceinline__ float at_max32(const uint32_t (&r)[32]) {
 // PLO = false (the consuming projection runs below split-fp16 x3 precision): P is kept as ONE fp16 plane -- no
 // residual arithmetic, half the TMEM stores and half the P V MMAs; a probability rounded to 11 bits is averaged over
 // hundreds of keys.
-template <bool PLO>
+// 2^x for a PAIR of arguments x <= 0 on the FMA pipe (no MUFU): Cody-Waite split x = j + f with the magic-number round
+// (j = nearest integer, |f| <= 1/2), a degree-4 minimax polynomial of 2^f (relative error 2.7e-6, two hundred times
+// below the fp16 rounding of P that follows) and j added into the exponent field.  4 packed fp32 + 2 integer issue
+// slots per pair against 2 MUFU.EX2 -- the softmax warps of this kernel are bound by the 16-lane XU pipe, so a share
+// of every chunk's exponentials (kAtPolyOf8 pairs out of 8) is moved over (the FlashAttention-4 trick).
+// Arguments below -125 are clamped: 2^-125 vanishes in fp16 like the true value would.
+__device__ __forceinline__ float2 at_ex2_poly2(float2 x) {
+  const float kMagic = 12582912.f;                             // 1.5 * 2^23: (x + kMagic) holds round(x) in its low bits
+  x.x = fmaxf(x.x, -125.f); x.y = fmaxf(x.y, -125.f);
+  const float2 t = __fadd2_rn(x, make_float2(kMagic, kMagic));
+  const float2 f = __fadd2_rn(x, __fadd2_rn(make_float2(kMagic, kMagic), make_float2(-t.x, -t.y)));   // x - round(x)
+  float2 p = __ffma2_rn(make_float2(0.009570101276040077f, 0.009570101276040077f), f,
+                        make_float2(0.05591785907745361f, 0.05591785907745361f));
+  p = __ffma2_rn(p, f, make_float2(0.240247443318367f, 0.240247443318367f));
+  p = __ffma2_rn(p, f, make_float2(0.6931217908859253f, 0.6931217908859253f));
+  p = __ffma2_rn(p, f, make_float2(0.9999992847442627f, 0.9999992847442627f));
+  // low 9 bits of the magic pattern 0x4B400000 are zero: (t_bits << 23) is exactly j << 23
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return p;
+}
+// POLY pairs of every 8 take the polynomial (0 = all MUFU), spread evenly over the chunk so that MUFU and FMA work
+// interleave in the instruction stream
+__host__ __device__ constexpr bool at_use_poly(int e, int poly) { return ((e % 8 + 1) * poly) / 8 != ((e % 8) * poly) / 8; }
+
+template <bool PLO, int POLY>
 __device__ __forceinline__ void at_exp_store32_packed(const uint32_t (&r)[32], float m, uint32_t t_chunk) {
   uint32_t h[16], lo[16];
   const float2 nm = make_float2(-m, -m), neg1 = make_float2(-1.f, -1.f);
 #pragma unroll
   for (int e = 0; e < 16; ++e) {
     const float2 d = __fadd2_rn(make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), nm);
-    const float2 p = make_float2(at_ex2(d.x), at_ex2(d.y));
+    // split-fp16 P (PLO) needs all ~22 bits of the exponential: MUFU only there
+    const float2 p = (!PLO && at_use_poly(e, POLY)) ? at_ex2_poly2(d) : make_float2(at_ex2(d.x), at_ex2(d.y));
     const __half2 hh = __floats2half2_rn(p.x, p.y);
     h[e] = at_pack(hh);
     if (PLO) {
@@ -173,7 +199,7 @@ struct AttnPipeSmem {
   uint32_t pad;
 };
 
-template <bool PLO>
+template <bool PLO, int POLY>
 __global__ void __launch_bounds__(kApThreads, 2)
 attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restrict__ out, __half* __restrict__ out_lo, int N,
                                 int C, int H, int B) {
@@ -462,10 +488,10 @@ attention_umma_pipelined_kernel(const float* __restrict__ qkv, __half* __restric
       tmem_ld_32x32(t_s + 32, r);
       tmem_ld_wait();
       m = fmaxf(m, at_max32(r));
-      at_exp_store32_packed<PLO>(r, m, t_s + 32);               // P = 2^(S - m) in place: [hi 16 | lo 16] per 32-key chunk
+      at_exp_store32_packed<PLO, POLY>(r, m, t_s + 32);               // P = 2^(S - m) in place: [hi 16 | lo 16] per 32-key chunk
       tmem_ld_32x32(t_s, r);
       tmem_ld_wait();
-      at_exp_store32_packed<PLO>(r, m, t_s);
+      at_exp_store32_packed<PLO, POLY>(r, m, t_s);
       tmem_st_wait();
       // the group's previous tile has long finished its P V; its slot is overwritten by P V of this tile, which is
       // issued only after the arrival below
@@ -511,23 +537,24 @@ int rldm_attention_umma(const float* qkv, uint16_t* out, uint16_t* out_lo, int B
   }
   const size_t smem_p = 1024 + 2 * kAtQBytes + kApRing * (kApKBytes + kApVBytes) + kApXFloats * kAtTile * 4 +
                         sizeof(AttnPipeSmem);
-  static bool attr_p = false;
-  if (!attr_p) {
-    RLDM_CUDA(cudaFuncSetAttribute(attention_umma_pipelined_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(smem_p)));
-    RLDM_CUDA(cudaFuncSetAttribute(attention_umma_pipelined_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(smem_p)));
-    attr_p = true;
-  }
   const int items_p = B * (C / 8) * T;
   const int ctas_p = items_p < 2 * n_sms_p ? items_p : 2 * n_sms_p;      // two persistent CTAs per SM
-  // out_lo == NULL: the consumer takes single-fp16 activations, so P is carried as one fp16 plane as well
-  if (out_lo)
-    RLDM_CUDA(launch_pdl(attention_umma_pipelined_kernel<true>, dim3(ctas_p), dim3(kApThreads), smem_p, as_stream(stream), qkv,
-                         reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H, B));
-  else
-    RLDM_CUDA(launch_pdl(attention_umma_pipelined_kernel<false>, dim3(ctas_p), dim3(kApThreads), smem_p, as_stream(stream), qkv,
-                         reinterpret_cast<__half*>(out), nullptr, N, C, H, B));
+  // out_lo == NULL: the consumer takes single-fp16 activations, so P is carried as one fp16 plane as well, and
+  // env().attn_poly of every 8 exponential pairs run as a polynomial on the FMA pipe (RLDM_ATTN_POLY=0..4, default 2)
+  using Kern = void (*)(const float*, __half*, __half*, int, int, int, int);
+  static const Kern kerns[6] = {attention_umma_pipelined_kernel<true, 0>,  attention_umma_pipelined_kernel<false, 0>,
+                                attention_umma_pipelined_kernel<false, 1>, attention_umma_pipelined_kernel<false, 2>,
+                                attention_umma_pipelined_kernel<false, 3>, attention_umma_pipelined_kernel<false, 4>};
+  static bool attr_p = false;
+  if (!attr_p) {
+    for (Kern k : kerns)
+      RLDM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_p)));
+    attr_p = true;
+  }
+  const int poly = env().attn_poly;
+  const Kern kern = out_lo ? kerns[0] : kerns[1 + (poly < 0 || poly > 4 ? 2 : poly)];
+  RLDM_CUDA(launch_pdl(kern, dim3(ctas_p), dim3(kApThreads), smem_p, as_stream(stream), qkv,
+                       reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H, B));
   RLDM_LAUNCH_CHECK();
   return 0;
 }

@@ -42,7 +42,10 @@ struct PrepArgs {
 // exactly that many threads) produce the padded output pixels [p_begin, p_end) of image b, channels [ch_lo, ch_hi).
 // Thread = 8 channels of one OUTPUT pixel (two float4 loads, one 16 B store).  shf: 2*(ch_hi-ch_lo) floats of shared
 // memory (scale, shift).
-template <bool COH>
+// U items per thread and step; PIPE: the next step's loads are issued before the current step is consumed (the stand-alone
+// kernel: 2 items, pipelined, 1024 threads per SM); the in-kernel producer of the small-layer convolution has only one
+// CTA of 192 threads per SM and therefore issues 8 items (16 x 16 B loads) per thread at once.
+template <bool COH, int U = 2, bool PIPE = true>
 __device__ __forceinline__ void prep_range(const PrepArgs& a, int b, int p_begin, int p_end, int ch_lo, int ch_hi, float* shf,
                                            int tid, int nthreads, int bar_id) {
   const int c0 = a.c0, c1 = a.c1, W = a.W, H = a.H, up = a.up, G = a.G;
@@ -72,9 +75,9 @@ __device__ __forceinline__ void prep_range(const PrepArgs& a, int b, int p_begin
     bool live, zero;
     float4 v0, v1;
   };
-  auto issue = [&](int i, Item (&it)[2]) {
+  auto issue = [&](int i, Item (&it)[U]) {
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       it[u].live = i + u * nthreads < total;
       while (oc >= oct_per_pix) { oc -= oct_per_pix; ++pl; }
       const int po = p_begin + pl;
@@ -99,7 +102,7 @@ __device__ __forceinline__ void prep_range(const PrepArgs& a, int b, int p_begin
       }
     }
   };
-  Item cur[2];
+  Item cur[U];
   issue(tid, cur);
   if (norm) {
     // group moments: either the (sum, sum^2) per (image, group) of rldm_gn_stats, or the per channel-PAIR moments
@@ -133,12 +136,15 @@ __device__ __forceinline__ void prep_range(const PrepArgs& a, int b, int p_begin
     else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
   }
   __half* out = a.out; __half* out_lo = a.out_lo; __half* raw = a.raw; __half* raw_lo = a.raw_lo;
-  for (int i = tid; i < total; i += 2 * nthreads) {
-    Item nxt[2];
-    nxt[0].live = nxt[1].live = false;
-    if (i + 2 * nthreads < total) issue(i + 2 * nthreads, nxt);
+  for (int i = tid; i < total; i += U * nthreads) {
+    Item nxt[PIPE ? U : 1];
+    if (PIPE) {
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) nxt[u].live = false;
+      if (i + U * nthreads < total) issue(i + U * nthreads, reinterpret_cast<Item(&)[U]>(nxt));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
       if (!cur[u].live) continue;
       const size_t o = cur[u].o;
       if (cur[u].zero) {
@@ -163,8 +169,12 @@ __device__ __forceinline__ void prep_range(const PrepArgs& a, int b, int p_begin
       }
       store_split8(v, out, out_lo, o);
     }
-    cur[0] = nxt[0];
-    cur[1] = nxt[1];
+    if (PIPE) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+    } else if (i + U * nthreads < total) {
+      issue(i + U * nthreads, cur);
+    }
   }
 }
 

@@ -50,6 +50,7 @@ struct EnvSwitches {
   bool conv_mt1;            // RLDM_CONV_MT1:     pixel-M persistent kernel with one tile per unit
   bool conv_mt2_res;        // RLDM_CONV_MT2_RES: two tiles per unit also for 128-wide layers with a residual
   bool wt_pdl;              // RLDM_WT_PDL != 0:  PDL on single-wave role-swapped launches (default on)
+  int attn_poly;            // RLDM_ATTN_POLY: exponential pairs of every 8 on the FMA pipe (tcgen05 attention, fp16 P), 0..4
   bool attn_mmasync;        // RLDM_ATTN_MMASYNC: mma.sync attention kernel for every shape it covers
   bool attn_cudacore;       // RLDM_ATTN_CUDACORE: CUDA-core attention kernel for every shape
   bool nco_pp1;             // RLDM_NCO_PP1:      norm_conv_out with one pixel per thread

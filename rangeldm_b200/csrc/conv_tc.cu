@@ -157,7 +157,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
   float* red_s = reinterpret_cast<float*>(tmem_ptr + 4);       // [4][BLOCK_N/2]
   float* red_q = red_s + 4 * (BLOCK_N / 2);
   int* red_b = reinterpret_cast<int*>(red_q + 4 * (BLOCK_N / 2));
-  float* fused_tab = reinterpret_cast<float*>(red_b + 4);      // [kFusedTabFloats]
+  float* fused_tab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(red_b + 4) + 15) & ~static_cast<uintptr_t>(15));   // [kFusedTabFloats], float4 reads
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -217,9 +217,10 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
   if (dbg && threadIdx.x == 0) p.dbg[1] = clock64();
 
   if (fz.main_on | fz.sc_on) {
-    // ---- in-kernel operand production (see ConvFused): the four epilogue warps, idle until the K loop ends ----
-    if (warp >= 2) {
-      const int tid = threadIdx.x - 64;
+    // ---- in-kernel operand production (see ConvFused): all 192 threads -- nobody has anything else to do until the
+    // operand exists (the first weight tiles are already in flight) ----
+    {
+      const int tid = threadIdx.x;
       const int taps = p.ks * p.ks;
       const int q0 = m0 / p.Ho, b0 = q0 / p.Wo, wo0 = q0 - b0 * p.Wo;
       const int nb = p.pix_per_img >= kBlockM ? 1 : kBlockM / p.pix_per_img;
@@ -233,22 +234,21 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
         const int first = p.stride * wo0 - p.pad_lo + 1;    // padded column of tap ti = 0
         const int col_lo = max(first, 0), col_hi = min(first + (p.ks - 1) + ncols * p.stride, p.W_in + 2);
         for (int b = b0; b < b_end; ++b) {
-          prep_range<false>(fz.main, b, col_lo * Hop, col_hi * Hop, ch_lo, ch_hi, fused_tab, tid, 128, 3);
-          asm volatile("bar.sync 3, 128;" ::: "memory");    // scale / shift table reusable
+          prep_range<false, 8, false>(fz.main, b, col_lo * Hop, col_hi * Hop, ch_lo, ch_hi, fused_tab, tid, 192, 0);
+          __syncthreads();                                  // scale / shift table reusable
         }
       }
       const int sc_begin = max(it0, p.main_iters);
       if (fz.sc_on && sc_begin < it1) {
         const int ch_lo = (sc_begin - p.main_iters) * kBlockK, ch_hi = (it1 - p.main_iters) * kBlockK;
-        for (int b = b0; b < b_end; ++b) {
-          prep_range<false>(fz.sc, b, (wo0 + 1) * p.Ho, (wo0 + 1 + ncols) * p.Ho, ch_lo, ch_hi, fused_tab, tid, 128, 3);
-          asm volatile("bar.sync 3, 128;" ::: "memory");
-        }
+        for (int b = b0; b < b_end; ++b)
+          prep_range<false, 8, false>(fz.sc, b, (wo0 + 1) * p.Ho, (wo0 + 1 + ncols) * p.Ho, ch_lo, ch_hi, fused_tab, tid, 192, 0);
       }
       asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores -> TMA (async proxy) reads below
     }
-    if (warp != 1) asm volatile("bar.sync 2, 160;" ::: "memory");   // producer warp + the four writer warps
+    __syncthreads();
     if (warp == 0) asm volatile("fence.proxy.async;" ::: "memory");
+    if (dbg && threadIdx.x == 0) p.dbg[9] = clock64();
   }
 
   // epilogue coordinates (meaningful for warps >= 2)
@@ -1073,7 +1073,7 @@ constexpr int conv_stage_bytes(int bn, int terms) { return x_parts(terms) * kABy
 constexpr int conv_stages(int bn, int terms) { return (bn == 128 && terms == 3) ? 3 : 4; }
 constexpr int conv_smem(int bn, int terms) {
   // pipeline stages (+ alignment slack) + barriers/TMEM pointer + the per-warp GroupNorm-moment scratch
-  return conv_stages(bn, terms) * conv_stage_bytes(bn, terms) + 1024 + 256 + 2 * 4 * (bn / 2) * 4 + 64 + kFusedTabFloats * 4;
+  return conv_stages(bn, terms) * conv_stage_bytes(bn, terms) + 1024 + 256 + 2 * 4 * (bn / 2) * 4 + 64 + kFusedTabFloats * 4 + 16;
 }
 constexpr int pers_stage_bytes(int bn, int terms, int mt) { return mt * x_parts(terms) * kABytes + w_parts(terms) * bn * kBlockK * 2; }
 constexpr int pers_fixed(int bn) { return kBlockM * 36 * 4 + 256 + 2 * 4 * (bn / 2) * 4 + 64 + 1024; }

@@ -64,10 +64,14 @@ FUSE_STATS = os.environ.get("RLDM_FUSE_STATS", "1") != "0"
 # ResnetBlock2D.conv_shortcut folded into conv2's launch (RLDM_FUSE_SHORTCUT=0: separate 1x1 launch + fp32 residual)
 FUSE_SHORTCUT = os.environ.get("RLDM_FUSE_SHORTCUT", "1") != "0"
 FUSE_CONV_OUT = os.environ.get("RLDM_FUSE_CONV_OUT", "1") != "0"
-# The convolutions of the small layers (fewer 128 x 128 tiles than SMs: UNet levels 1..n) produce their own fp16 operand
-# from the fp32 stream inside the kernel (rldm_conv_tc_fused) instead of reading the output of a rldm_prep launch:
-# one graph node per convolution instead of two.  RLDM_FUSE_PREP=0 keeps the separate launches.
-FUSE_PREP = os.environ.get("RLDM_FUSE_PREP", "1") != "0"
+# RLDM_FUSE_PREP=1 (experiment, default off): the convolutions of the small layers (fewer 128 x 128 tiles than SMs: UNet
+# levels 1..n) produce their own fp16 operand from the fp32 stream inside the kernel (rldm_conv_tc_fused) instead of
+# reading the output of a rldm_prep launch: 118 graph nodes per UNet forward instead of 168.  Bit-identical
+# (tests/test_fused_gpu.py) but measured SLOWER on B200 (C3, batch 8: 174 vs 216 images/s): the one 192-thread CTA per
+# SM needs 10-22 k cycles for its slice (every output-channel tile of the same pixels repeats it, and six warps cannot
+# hide the load -> SiLU -> store chain), against ~5 us for the whole rldm_prep launch including its kernel boundary
+# (scripts/own_operand_probe.py).
+FUSE_PREP = os.environ.get("RLDM_FUSE_PREP", "0") == "1"
 # RLDM_FUSE_LEVELS=1 (experiment, default off): runs of small consecutive ops (UNet levels 1..n) compiled into ONE
 # persistent launch each (csrc/fused_levels.cu).  Correct (tests/test_fused_gpu.py) but measured SLOWER on B200: a
 # grid-wide barrier costs 2.0-2.3 us against ~3 us for a PDL kernel boundary, and every convolution needs two of them

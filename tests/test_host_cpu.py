@@ -125,15 +125,22 @@ def test_dry_run_plans_and_fused_program_launch_counts(monkeypatch):
     assert kinds.count(_lib.OP_CONV_IN) == 1 and kinds.count(_lib.OP_NORM_CONV_OUT) == 1 and kinds[0] == _lib.OP_MEMSET
     assert kinds.count(_lib.OP_GN_STATS) == 0          # every GroupNorm reads moments fused into a producing epilogue
     assert [op.kind for op in plan.prog.exec_ops] == kinds and plan.prog.n_launch == len(kinds) + 2   # temb = 3 launches
-    # the 50 convolutions of levels 1-3 that run on the small-layer kernel produce their own operand: only the
-    # full-resolution level and the three 192-tile qkv projections keep a rldm_prep launch -- 118 graph nodes, not 168
-    assert kinds.count(_lib.OP_PREP) == 16 and len(kinds) == 118
-    assert sum(1 for op in plan.prog.ops if op.kind == _lib.OP_CONV_TC and (op.p[11] or op.p[17])) == 50
-    # opt-in experiment (RLDM_FUSE_LEVELS=1 with RLDM_FUSE_PREP=0): 135 small ops of levels 1-3 as 5 fused persistent
-    # launches between the five N = 1024 attention kernels
+    # one rldm_prep launch per GroupNorm / resampler operand: 168 graph nodes
+    assert kinds.count(_lib.OP_PREP) == 66 and len(kinds) == 168
+    assert not any(op.p[11] or op.p[17] for op in plan.prog.ops if op.kind == _lib.OP_CONV_TC)
     from rangeldm_b200 import engine
-    monkeypatch.setattr(engine, "FUSE_LEVELS", True)
+    # opt-in experiment RLDM_FUSE_PREP=1: the 50 convolutions of levels 1-3 that run on the small-layer kernel produce
+    # their own operand; only the full-resolution level and the three 192-tile qkv projections keep a rldm_prep launch
+    monkeypatch.setattr(engine, "FUSE_PREP", True)
+    u.invalidate_plans()
+    plan1 = u.plan(8, 256, 16, 1)
+    kinds1 = [op.kind for op in plan1.prog.ops]
+    assert kinds1.count(_lib.OP_PREP) == 16 and len(kinds1) == 118
+    assert sum(1 for op in plan1.prog.ops if op.kind == _lib.OP_CONV_TC and (op.p[11] or op.p[17])) == 50
     monkeypatch.setattr(engine, "FUSE_PREP", False)
+    # opt-in experiment RLDM_FUSE_LEVELS=1: 135 small ops of levels 1-3 as 5 fused persistent launches between the five
+    # N = 1024 attention kernels
+    monkeypatch.setattr(engine, "FUSE_LEVELS", True)
     u.invalidate_plans()
     plan2 = u.plan(8, 256, 16, 1)
     assert len(plan2.prog.ops) == 168
@@ -141,7 +148,6 @@ def test_dry_run_plans_and_fused_program_launch_counts(monkeypatch):
     assert ex.count(_lib.OP_FUSED) == 5 and len(ex) <= 40 and sum(op.n for op in plan2.prog.exec_ops if op.kind == _lib.OP_FUSED) == 135
     assert plan2.prog.n_launch == len(ex) + 2
     monkeypatch.setattr(engine, "FUSE_LEVELS", False)
-    monkeypatch.setattr(engine, "FUSE_PREP", True)
     u.invalidate_plans()
     plan = u.plan(8, 256, 16, 1)
     sch = R.DPMSolverMultistepScheduler(timestep_spacing="leading")
