@@ -42,8 +42,10 @@ STEPS = 20
 PER_GPU_BATCH = 8
 GFLOP_PER_IMAGE = 20 * 34.07 + 157.46
 METRIC = "range-images/sec (64x1024, 20-step DPM-Solver)"
-DTYPE = ("split-fp16 x3 (activations and weights as hi+lo fp16 pairs; Ah*Wh + Al*Wh + Ah*Wl on tcgen05 kind::f16 into "
-         "fp32 TMEM: ~22-bit operands, 3 MMAs per algorithmic MAC), fp32 elsewhere")
+DTYPE = ("fp16 operands, fp32 accumulate on tcgen05 kind::f16; UNet inside the trajectory graph: plain fp16 (1 MMA per "
+         "algorithmic MAC); VAE decoder: split-fp16 x3 (activations and weights as hi+lo fp16 pairs, Ah*Wh + Al*Wh + "
+         "Ah*Wl, ~22-bit operands, 3 MMAs per MAC); fp32 residual stream / softmax / scheduler, GroupNorm moments in "
+         "fp64 (rangeldm_b200/engine.py PRECISION*)")
 WORKLOAD = ("C3 RangeLDM KITTI-360: latent 4x256x16 UNet[128,128,256,256] x 20-step DPM-Solver++(2M, leading) "
             "+ AutoencoderKL 4x decode -> 2x1024x64")
 
@@ -58,12 +60,14 @@ def peaks():
 
 def conv_traffic():
     """DRAM bytes (read + write) per conv_tc launch from the committed ncu capture of the same workload
-    (profiles/conv_tc_traffic_r1.json, written by scripts/conv_traffic.py); None when the file is absent."""
-    p = os.path.join(ROOT, "profiles", "conv_tc_traffic_r1.json")
-    try:
-        return round(json.load(open(p))["traffic_bytes_per_launch"])
-    except Exception:
-        return None
+    (profiles/conv_tc_traffic_r2.json, written by scripts/conv_traffic.py; the round-1 file as a fallback); None when
+    neither exists."""
+    for name in ("conv_tc_traffic_r2.json", "conv_tc_traffic_r1.json"):
+        try:
+            return round(json.load(open(os.path.join(ROOT, "profiles", name)))["traffic_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -133,6 +137,19 @@ def conv_flops(op):
     return 2.0 * B * (W // stride) * (H // stride) * Cout * (Cin * ks * ks + sc_cin)
 
 
+def conv_bytes(op):
+    """Algorithmic HBM bytes of one conv_tc launch: every operand plane, weight plane, residual and output element moves
+    once (fp16 operand planes as the layer's precision says, fp32 output / residual)."""
+    i = op.i
+    B, W, H, Cin, Cout, ks, stride, sc_cin, terms = i[1], i[2], i[3], i[4], i[5], i[6], i[7], i[11], i[12]
+    xp, wp = (2 if terms == 3 else 1), (2 if terms >= 2 else 1)
+    out_elems = B * (W // stride) * (H // stride) * Cout
+    b = xp * B * (W + 2) * H * (Cin + sc_cin) * 2 + wp * (ks * ks * Cin + sc_cin) * Cout * 2 + out_elems * 4
+    if op.p[4]:
+        b += out_elems * 4
+    return float(b)
+
+
 def timed_profile(prog, reps=5):
     """Per-op durations (us) of a librldm program: `rldm_run_timed` puts a one-thread %globaltimer stamp kernel after
     every op; the stamped program is captured in a CUDA graph and replayed, so the numbers are device-side, cache-warm
@@ -167,22 +184,25 @@ OP_NAMES = {1: "gn_stats", 2: "prep", 3: "conv_tc", 4: "conv_in", 5: "conv_out",
 
 
 def per_op_profile(sampler):
-    """One UNet forward + the decoder, every op timed on the device inside a CUDA graph (`timed_profile`).
-    Returns per-kind milliseconds, launch counts and the conv kernel's algorithmic FLOPs."""
+    """One UNet forward + the decoder, every op timed on the device inside a CUDA graph (`timed_profile`), weighted as
+    one step runs them (STEPS UNet forwards, one decode).  Returns per-kind milliseconds and launch counts per step, and
+    the conv kernels' algorithmic FLOPs, issued FLOPs and algorithmic HBM bytes per step."""
     from rangeldm_b200 import _lib
     # (profiles the first sub-batch program: with RLDM_STREAMS=2 that is half of the per-GPU batch)
-    progs = [sampler.plan.prog] + ([sampler.dec.prog] if sampler.dec is not None else [])
-    ms, cnt, flops, fused_flops = {}, {}, 0.0, 0.0
-    for prog in progs:
+    progs = [(sampler.plan.prog, STEPS)] + ([(sampler.dec.prog, 1)] if sampler.dec is not None else [])
+    ms, cnt, flops, fused_flops, hw_flops, nbytes = {}, {}, 0.0, 0.0, 0.0, 0.0
+    for prog, weight in progs:
         for op, (i, j), us in zip(prog.exec_ops, prog.exec_src, timed_profile(prog)):
             k = OP_NAMES.get(op.kind, str(op.kind))
-            ms[k] = ms.get(k, 0.0) + us / 1e3
-            cnt[k] = cnt.get(k, 0) + 1
+            ms[k] = ms.get(k, 0.0) + weight * us / 1e3
+            cnt[k] = cnt.get(k, 0) + weight
             if op.kind == _lib.OP_CONV_TC:
-                flops += conv_flops(op)
+                flops += weight * conv_flops(op)
+                hw_flops += weight * conv_flops(op) * op.i[12]       # MMAs actually issued: 1, 2 or 3 per algorithmic MAC
+                nbytes += weight * conv_bytes(op)
             if op.kind == _lib.OP_FUSED:          # convolutions inside a fused run of small layers
-                fused_flops += sum(conv_flops(o) for o in prog.ops[i:j] if o.kind == _lib.OP_CONV_TC)
-    return ms, cnt, flops, fused_flops
+                fused_flops += weight * sum(conv_flops(o) for o in prog.ops[i:j] if o.kind == _lib.OP_CONV_TC)
+    return ms, cnt, flops, fused_flops, hw_flops, nbytes
 
 
 def run_native(args):
@@ -269,7 +289,7 @@ def run_native(args):
     out = None
     if rank == 0:
         burst, sustained, hbm, src = peaks()
-        ms, cnt, flops, fused_flops = per_op_profile(sampler)
+        ms, cnt, flops, fused_flops, hw_flops, conv_nbytes = per_op_profile(sampler)
         conv_ms = ms.get("conv_tc", 0.0)
         all_ms = sum(ms.values())
         achieved = flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
@@ -288,13 +308,15 @@ def run_native(args):
                     "h2d_bytes_per_step": int(noise.numel() * 4), "d2h_bytes_per_step": int(host_img.numel() * 4)},
             "gpu_launches": int(launches_per_step * args.steps),
             "achieved_tflops_whole_job": round(value / world * GFLOP_PER_IMAGE / 1e3, 2),
-            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM circular conv)",
+            "roofline": {"bound": "tensor", "kernel": "conv_tc kernels (tcgen05 implicit-GEMM circular conv: small-layer, persistent and role-swapped variants)",
                          "achieved": round(achieved, 2), "peak": burst, "unit": "TFLOP/s",
                          "frac": round(achieved / burst, 4), "peak_source": f"{src} bf16 burst (kernel timed alone: device-side stamps around every launch, in-graph)",
                          "frac_of_sustained": round(achieved / sustained, 4), "traffic": conv_traffic(),
+                         "algorithmic_bytes": round(conv_nbytes / max(cnt.get("conv_tc", 1), 1)),
+                         "issued_tflops": round(hw_flops / (conv_ms / 1e3) / 1e12, 2) if conv_ms > 0 else 0.0,
                          "launches": cnt.get("conv_tc", 0), "avg_launch_us": round(1e3 * conv_ms / max(cnt.get("conv_tc", 1), 1), 2),
                          "share_of_step": round(conv_ms / all_ms, 4) if all_ms else None,
-                         "per_kind_ms_one_unet_plus_decoder": {k: round(v, 4) for k, v in sorted(ms.items())}},
+                         "per_kind_ms_per_step": {k: round(v, 4) for k, v in sorted(ms.items())}},
             "clocks": clk,
         }
         if not args.no_library_baseline and world == 1:
