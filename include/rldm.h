@@ -142,6 +142,29 @@ int rldm_conv_tc_fused(const rldm_conv_src* src, const rldm_conv_src* sc_src, co
                        int sc_cin, int terms, void* stream);
 int rldm_conv_tc_fusable(int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo, int sc_cin, int has_residual);
 
+/* rldm_conv_tc_ex that also EMITS THE NEXT GroupNorm's OPERAND: where the consumer of this convolution's output is
+ * F.group_norm (+ F.silu) in front of another convolution (ResnetBlock2D norm2 -> conv2, the GroupNorm of the next
+ * ResnetBlock2D / Attention; diffusers), the epilogue normalises its own output and writes the
+ * fp16 W-padded operand (B, W/stride + 2, H/stride, Cout) that a rldm_prep launch would have produced -- the
+ * (image, group) moments are completed inside a thread-block cluster that covers whole images (DSMEM), so no second
+ * launch has to wait for the whole grid.  `out` may be NULL when nothing else reads the fp32 result; `stats` still
+ * accumulates the channel-pair moments when given.  One fp16 plane only (consumers running below split-fp16 x3).
+ * Only layers for which rldm_conv_tc_emittable() == 1 qualify: small-layer kernel, 64..1024 output pixels per image,
+ * group size a power of two >= 4 that divides the output-channel tile. */
+typedef struct rldm_conv_emit {
+  uint16_t* out;                 /* (B, Wo+2, Ho, Cout) fp16 */
+  const float* gamma; const float* beta;
+  float eps;
+  int G, silu, circular;         /* groups of the consumer's GroupNorm; SiLU after it; halo columns wrap (1) or zero (0) */
+} rldm_conv_emit;
+int rldm_conv_tc_emit(const rldm_conv_emit* emit, const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt,
+                      const float* bias, const float* temb, int temb_stride, const float* residual, float* out,
+                      int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo, int circular,
+                      int split_k, double* stats, const uint16_t* sc_x, const uint16_t* sc_x_lo,
+                      const uint16_t* sc_wgt, int sc_cin, int terms, void* stream);
+int rldm_conv_tc_emittable(int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo, int sc_cin,
+                           int has_residual, int G);
+
 /* CUDA-core restatement of rldm_conv_tc with the identical contract (split_k ignored); used by the
  * GPU tests to isolate tensor-core descriptor bugs from precision, never by the product path. */
 int rldm_conv_ref(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias, const float* temb,
@@ -221,7 +244,7 @@ typedef struct rldm_op {
   int32_t kind;
   int32_t i[23];      /* integer arguments in the order of the matching entry point */
   float f[2];         /* float arguments (eps) */
-  void* p[20];        /* pointer arguments in the order of the matching entry point */
+  void* p[24];        /* pointer arguments in the order of the matching entry point */
   int64_t n;          /* element / byte count where the entry point takes one */
 } rldm_op;
 int rldm_run(const rldm_op* ops, int n_ops, void* stream);

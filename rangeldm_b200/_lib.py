@@ -19,7 +19,13 @@ OP_GN_STATS, OP_PREP, OP_CONV_TC, OP_CONV_IN, OP_CONV_OUT, OP_ATTENTION, OP_TEMB
 
 class RldmOp(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("i", ctypes.c_int32 * 23), ("f", ctypes.c_float * 2),
-                ("p", ctypes.c_void_p * 20), ("n", ctypes.c_int64)]
+                ("p", ctypes.c_void_p * 24), ("n", ctypes.c_int64)]
+
+
+class ConvEmit(ctypes.Structure):
+    """rldm_conv_emit (include/rldm.h)"""
+    _fields_ = [("out", ctypes.c_void_p), ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p), ("eps", ctypes.c_float),
+                ("G", ctypes.c_int), ("silu", ctypes.c_int), ("circular", ctypes.c_int)]
 
 
 class ConvSrc(ctypes.Structure):
@@ -47,6 +53,9 @@ SIGNATURES = {
     "rldm_conv_tc_fused": (c_int, [c_void_p, c_void_p] + [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
                            + [c_int] * 10 + [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "rldm_conv_tc_fusable": (c_int, [c_int] * 10),
+    "rldm_conv_tc_emit": (c_int, [c_void_p] + [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+                          + [c_int] * 10 + [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "rldm_conv_tc_emittable": (c_int, [c_int] * 11),
     "rldm_conv_ref": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
                       + [c_int] * 9 + [c_void_p]),
     "rldm_conv_in": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 5

@@ -62,6 +62,16 @@ struct ConvParams {
   int nb_stages;    // depth of the weight ring
   int units;        // (Cin/64) * 3 : one unit = (channel chunk, kernel column tj) = 3 taps
   long long* dbg;   // optional: clock64 timestamps written by CTA 0 (profiling aid, normally NULL)
+  // small-layer kernel only: the epilogue also EMITS the next GroupNorm's operand (see conv_tc_kernel)
+  __half* emit_out;           // fp16 W-padded operand (B, Wo+2, Ho, Cout) of the consumer, or NULL
+  const float* emit_gamma;    // [Cout] affine of the consumer's GroupNorm
+  const float* emit_beta;
+  float emit_eps;
+  float emit_inv_n;           // 1 / (pixels per image x channels per group)
+  int emit_cpg;               // channels per group of that GroupNorm (multiple of 4, divides BLOCK_N)
+  int emit_silu;
+  int emit_circular;          // halo columns of the emitted operand: wrap (1) or zeros (0)
+  int clm;                    // M tiles per image that share a cluster (1 unless emitting for images of > 128 pixels)
 };
 
 // Tensor maps of one launch.  a/alo/b: activation (hi, lo) and weights of the convolution.  a2/a2lo/b2: operand and
@@ -82,6 +92,16 @@ struct ConvFused {
   int main_on, sc_on;
 };
 constexpr int kFusedTabFloats = 1024;           // scale/shift of up to 512 channels
+// in-kernel operand production: items per thread and step / software pipelining of prep_range (the body runs ONCE per
+// launch on one warp per scheduler: a long unrolled body is bound by instruction fetch, `stall_no_inst` in ncu)
+#ifndef RLDM_OWN_U
+#define RLDM_OWN_U 2
+#endif
+#ifndef RLDM_OWN_PIPE
+#define RLDM_OWN_PIPE true
+#endif
+constexpr int kOwnU = RLDM_OWN_U;
+constexpr bool kOwnPipe = RLDM_OWN_PIPE;
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   uint32_t r;
@@ -130,6 +150,15 @@ __device__ __forceinline__ void issue_kstep(uint32_t d_tmem, uint32_t a_addr, ui
 // residual hides under the mainloop.  The split-K reduction pulls the partial tiles of the peer CTAs through
 // distributed shared memory in batches of 16 independent 16 B loads per lane (fixed summation order:
 // deterministic), instead of one dependent load at a time.
+//
+// EMIT (p.emit_out != NULL): the consumer of this convolution's output is a GroupNorm (+ SiLU) in front of another
+// convolution, i.e. a rldm_prep launch that could only start once every CTA of this grid has added its moments.  Here
+// the cluster is shaped so that it covers WHOLE IMAGES for its output-channel tile -- (p.clm M tiles) x (NSPLIT K
+// slices), <= 8 CTAs -- so the (image, group) moments are complete inside the cluster: every epilogue warp publishes
+// the moments of its finished rows in shared memory, one cluster barrier later each thread sums the <= 32 partials
+// of its own (image, group) through DSMEM, normalises the values it still holds in registers and writes the fp16
+// W-padded operand (halo columns included) the next convolution reads.  One prep launch and one kernel boundary less
+// per GroupNorm; the fp32 output (p.out) is still written when the residual stream needs it.
 template <int BLOCK_N, int STAGES, int TERMS, int NSPLIT>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __grid_constant__ ConvFused fz) {
@@ -139,6 +168,8 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
   constexpr int kBOff = XP * kABytes;
   constexpr int kStagePitch = BLOCK_N + 4;                     // floats per row of the epilogue staging tile
   static_assert(kBlockM * kStagePitch * 4 <= STAGES * kStageBytes, "staging tile must fit in the pipeline stages");
+  static_assert(NSPLIT == 1 || (kBlockM + kBlockM / NSPLIT) * kStagePitch * 4 <= STAGES * kStageBytes,
+                "the kept rows of an emitting launch must fit behind the staging tile");
   // epilogue geometry: a warp instruction covers kRowsPerIter rows of BLOCK_N floats (float4 per lane)
   constexpr int kLanesPerRow = BLOCK_N / 4;               // 32 (BN=128) or 16 (BN=64)
   constexpr int kRowsPerIter = 32 / kLanesPerRow;         // 1 or 2
@@ -234,7 +265,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
         const int first = p.stride * wo0 - p.pad_lo + 1;    // padded column of tap ti = 0
         const int col_lo = max(first, 0), col_hi = min(first + (p.ks - 1) + ncols * p.stride, p.W_in + 2);
         for (int b = b0; b < b_end; ++b) {
-          prep_range<false, 8, false>(fz.main, b, col_lo * Hop, col_hi * Hop, ch_lo, ch_hi, fused_tab, tid, 192, 0);
+          prep_range<false, kOwnU, kOwnPipe>(fz.main, b, col_lo * Hop, col_hi * Hop, ch_lo, ch_hi, fused_tab, tid, 192, 0);
           __syncthreads();                                  // scale / shift table reusable
         }
       }
@@ -242,7 +273,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
       if (fz.sc_on && sc_begin < it1) {
         const int ch_lo = (sc_begin - p.main_iters) * kBlockK, ch_hi = (it1 - p.main_iters) * kBlockK;
         for (int b = b0; b < b_end; ++b)
-          prep_range<false, 8, false>(fz.sc, b, (wo0 + 1) * p.Ho, (wo0 + 1 + ncols) * p.Ho, ch_lo, ch_hi, fused_tab, tid, 192, 0);
+          prep_range<false, kOwnU, kOwnPipe>(fz.sc, b, (wo0 + 1) * p.Ho, (wo0 + 1 + ncols) * p.Ho, ch_lo, ch_hi, fused_tab, tid, 192, 0);
       }
       asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores -> TMA (async proxy) reads below
     }
@@ -260,6 +291,9 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
   // all rows of one warp lie in one image (pix_per_img is a power of two >= 64, or whole images per tile row group)
   const int bimg = min(m_first, p.M_total - 1) / p.pix_per_img;
   float4 res[kPerLane];
+  float4 emit_g = make_float4(0.f, 0.f, 0.f, 0.f), emit_b = emit_g;      // consumer GroupNorm affine of this thread's 4 columns
+  float es = 0.f, eq = 0.f;                                              // this thread's share of its group's moments
+  const int cl_x = p.clm > 1 ? static_cast<int>(blockIdx.x) % p.clm : 0;   // position among the image's M tiles in the cluster
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp: lanes share the column loads) =============
@@ -317,6 +351,10 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
       const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.temb + static_cast<size_t>(bimg) * p.temb_stride + n0 + col));
       bias4.x += t4.x; bias4.y += t4.y; bias4.z += t4.z; bias4.w += t4.w;
     }
+    if (p.emit_out) {
+      emit_g = __ldg(reinterpret_cast<const float4*>(p.emit_gamma + n0 + col));
+      emit_b = __ldg(reinterpret_cast<const float4*>(p.emit_beta + n0 + col));
+    }
 #pragma unroll
     for (int u = 0; u < kPerLane; ++u) {
       const int m = m_first + u * kRowsPerIter + rsub;
@@ -360,24 +398,36 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
     float s01 = 0.f, q01 = 0.f, s23 = 0.f, q23 = 0.f;     // moments of channel pairs (0,1) and (2,3)
     const uint32_t stage_u32 = smem_u32(smem);
     if (NSPLIT == 1) {
+      // four rows per step: the shared-memory loads first, then the arithmetic, then the stores (one warp per scheduler
+      // runs this: a row at a time is a chain of dependent latencies)
+      constexpr int kRB = kPerLane < 4 ? kPerLane : 4;
+      const bool keep = p.emit_out != nullptr;
 #pragma unroll
-      for (int u = 0; u < kPerLane; ++u) {
-        const int r = r_begin + u * kRowsPerIter + rsub;
-        const int m = m0 + r;
-        const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem) + r * kStagePitch + col);
-        float4 v = res[u];
-        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-        if (m < p.M_total) {
-          *reinterpret_cast<float4*>(p.out + static_cast<size_t>(m) * p.Cout + n0 + col) = v;
-          s01 += v.x + v.y; q01 += v.x * v.x + v.y * v.y;
-          s23 += v.z + v.w; q23 += v.z * v.z + v.w * v.w;
+      for (int u0 = 0; u0 < kPerLane; u0 += kRB) {
+        float4 t[kRB];
+#pragma unroll
+        for (int j = 0; j < kRB; ++j)
+          t[j] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem) + (r_begin + (u0 + j) * kRowsPerIter + rsub) * kStagePitch + col);
+#pragma unroll
+        for (int j = 0; j < kRB; ++j) {
+          const int r = r_begin + (u0 + j) * kRowsPerIter + rsub;
+          const int m = m0 + r;
+          float4 v = res[u0 + j];
+          v.x += t[j].x; v.y += t[j].y; v.z += t[j].z; v.w += t[j].w;
+          if (keep)                                          // kept for the emit pass (in place: nobody else reads this tile)
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(smem) + r * kStagePitch + col) = v;
+          const bool live = m < p.M_total;
+          if (live && p.out) *reinterpret_cast<float4*>(p.out + static_cast<size_t>(m) * p.Cout + n0 + col) = v;
+          const float lm = live ? 1.f : 0.f;
+          s01 += lm * (v.x + v.y); q01 += lm * (v.x * v.x + v.y * v.y);
+          s23 += lm * (v.z + v.w); q23 += lm * (v.z * v.z + v.w * v.w);
         }
       }
     } else {
       constexpr int kUB = (16 / NSPLIT) < kPerLane ? (16 / NSPLIT) : kPerLane;   // rows per batch of <= 16 loads
       uint32_t rbase[NSPLIT];
 #pragma unroll
-      for (int sidx = 0; sidx < NSPLIT; ++sidx) rbase[sidx] = mapa_u32(stage_u32, sidx);
+      for (int sidx = 0; sidx < NSPLIT; ++sidx) rbase[sidx] = mapa_u32(stage_u32, cl_x + p.clm * sidx);   // rank = x + clm * z
 #pragma unroll
       for (int u0 = 0; u0 < kPerLane; u0 += kUB) {
         float4 part[kUB][NSPLIT];
@@ -396,8 +446,10 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
           for (int sidx = 0; sidx < NSPLIT; ++sidx) {
             v.x += part[ub][sidx].x; v.y += part[ub][sidx].y; v.z += part[ub][sidx].z; v.w += part[ub][sidx].w;
           }
+          if (p.emit_out)                                    // kept for the emit pass, behind the staging tile the peers still read
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(smem) + (kBlockM + r_begin - blockIdx.z * kRowsCta + (u0 + ub) * kRowsPerIter + rsub) * kStagePitch + col) = v;
           if (m < p.M_total) {
-            *reinterpret_cast<float4*>(p.out + static_cast<size_t>(m) * p.Cout + n0 + col) = v;
+            if (p.out) *reinterpret_cast<float4*>(p.out + static_cast<size_t>(m) * p.Cout + n0 + col) = v;
             s01 += v.x + v.y; q01 += v.x * v.x + v.y * v.y;
             s23 += v.z + v.w; q23 += v.z * v.z + v.w * v.w;
           }
@@ -405,6 +457,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
       }
     }
     if (dbg && threadIdx.x == 64) p.dbg[8] = clock64();
+    es = s01 + s23; eq = q01 + q23;
     if (p.stats) {
       // Moments of the finished output per (image, channel PAIR): lanes -> the 4 epilogue warps (shared memory) ->
       // ONE double atomic per (pair, moment) and image for the whole CTA.  Pairs are the finest granularity any
@@ -444,7 +497,104 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
     }
     if (dbg && threadIdx.x == 64) p.dbg[5] = clock64();
   }
-  if (NSPLIT > 1) cluster_sync_all();     // nobody exits while a peer may still read its staging tile
+  const bool clustered = NSPLIT > 1 || p.clm > 1;
+  if (p.emit_out) {
+    // ---- EMIT: (image, group) moments complete inside the cluster -> normalise own rows -> fp16 operand ----
+    // published per epilogue warp: [4][32] (sum, sum of squares) of the warp's rows per group of the tile
+    float2* pub = reinterpret_cast<float2*>(fused_tab);
+    const int lpg = p.emit_cpg >> 2;                        // lanes (column quads) per group
+    const int gl = col / p.emit_cpg;                        // group of this thread's columns inside the tile
+    if (warp >= 2) {
+      for (int o = 1; o < lpg; o <<= 1) {
+        es += __shfl_xor_sync(0xffffffffu, es, o); eq += __shfl_xor_sync(0xffffffffu, eq, o);
+      }
+      if (kRowsPerIter == 2) { es += __shfl_xor_sync(0xffffffffu, es, 16); eq += __shfl_xor_sync(0xffffffffu, eq, 16); }
+      if (rsub == 0 && ((lane % kLanesPerRow) % lpg) == 0) pub[ew * 32 + gl] = make_float2(es, eq);
+    }
+    if (clustered) cluster_sync_all();
+    else if (warp >= 2) asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (dbg && threadIdx.x == 64) p.dbg[10] = clock64();
+    if (warp >= 2) {
+      const int csize = clustered ? NSPLIT * p.clm : 1;
+      const uint32_t pub_u32 = smem_u32(fused_tab);
+      // Which image the rows of warp w of cluster rank rk = (x, z) belong to follows from the geometry (tile blockIdx.x
+      // - cl_x + x, rows [z * kRowsCta + w * kRowsWarp, ...)): only the partials of this thread's image are loaded, four
+      // ranks (16 independent DSMEM loads) per round trip.
+      const int tile0 = static_cast<int>(blockIdx.x) - cl_x;
+      const int img_lo = bimg * p.pix_per_img, img_hi = min(img_lo + p.pix_per_img, p.M_total);   // rows of this thread's image
+      const int clm_sh = 31 - __clz(p.clm);
+      float S = 0.f, Q = 0.f;           // <= 32 partials of <= 1024 values each: fp32 is ample next to the fp16 operand
+      for (int rk0 = 0; rk0 < csize; rk0 += 4) {
+        float2 pq[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rk = rk0 + j;
+          const int x = rk & (p.clm - 1), z = rk >> clm_sh;       // clm is a power of two (host check)
+          const uint32_t base = clustered ? mapa_u32(pub_u32, rk < csize ? rk : 0) : pub_u32;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int mf = (tile0 + x) * kBlockM + z * kRowsCta + w * kRowsWarp;
+            pq[j][w] = make_float2(0.f, 0.f);
+            if (rk < csize && mf >= img_lo && mf < img_hi)
+              asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];"
+                           : "=f"(pq[j][w].x), "=f"(pq[j][w].y) : "r"(base + static_cast<uint32_t>(w * 32 + gl) * 8u) : "memory");
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          S += (pq[j][0].x + pq[j][1].x) + (pq[j][2].x + pq[j][3].x);
+          Q += (pq[j][0].y + pq[j][1].y) + (pq[j][2].y + pq[j][3].y);
+        }
+      }
+      const float mu = S * p.emit_inv_n;
+      const float var = fmaxf(fmaf(-mu, mu, Q * p.emit_inv_n), 0.f);
+      const float rstd = rsqrtf(var + p.emit_eps);
+      const float4 sc = make_float4(rstd * emit_g.x, rstd * emit_g.y, rstd * emit_g.z, rstd * emit_g.w);
+      const float4 sf = make_float4(emit_b.x - mu * sc.x, emit_b.y - mu * sc.y, emit_b.z - mu * sc.z, emit_b.w - mu * sc.w);
+      if (dbg && threadIdx.x == 64) p.dbg[11] = clock64();
+      // W-padded operand (B, Wo+2, Ho, Cout): pixel pin = w*Ho + h of the image sits at padded pixel pin + Ho; padded
+      // column 0 holds image column Wo-1 and padded column Wo+1 image column 0 (zeros when the consumer does not wrap)
+      __half* obase = p.emit_out + static_cast<size_t>(bimg) * (p.Wo + 2) * p.Ho * p.Cout + n0 + col;
+      const int pin0 = m_first - bimg * p.pix_per_img + rsub;
+      const int rows_left = p.M_total - m_first - rsub;          // rows u with u * kRowsPerIter < rows_left exist
+      const int last_col0 = p.pix_per_img - p.Ho;                 // first pixel of image column Wo-1
+      // rows of this warp in the kept tile: NSPLIT == 1 in place (tile row r), else local row behind the staging tile
+      const float* kept = reinterpret_cast<const float*>(smem) +
+                          (NSPLIT == 1 ? r_begin : kBlockM + r_begin - static_cast<int>(blockIdx.z) * kRowsCta) * kStagePitch +
+                          rsub * kStagePitch + col;
+      // four rows per step: loads, then the arithmetic of all sixteen values, then the stores -- one warp per scheduler
+      // runs this, a row at a time would be a chain of dependent MUFU latencies
+      constexpr int kEB = kPerLane < 4 ? kPerLane : 4;
+#pragma unroll 1
+      for (int u0 = 0; u0 < kPerLane; u0 += kEB) {
+        float4 y[kEB];
+#pragma unroll
+        for (int j = 0; j < kEB; ++j) y[j] = *reinterpret_cast<const float4*>(kept + (u0 + j) * kRowsPerIter * kStagePitch);
+#pragma unroll
+        for (int j = 0; j < kEB; ++j) {
+          y[j].x = fmaf(y[j].x, sc.x, sf.x); y[j].y = fmaf(y[j].y, sc.y, sf.y);
+          y[j].z = fmaf(y[j].z, sc.z, sf.z); y[j].w = fmaf(y[j].w, sc.w, sf.w);
+        }
+        if (p.emit_silu) {
+#pragma unroll
+          for (int j = 0; j < kEB; ++j) { y[j].x = silu_f(y[j].x); y[j].y = silu_f(y[j].y); y[j].z = silu_f(y[j].z); y[j].w = silu_f(y[j].w); }
+        }
+#pragma unroll
+        for (int j = 0; j < kEB; ++j) {
+          const int pin = pin0 + (u0 + j) * kRowsPerIter;
+          const __half2 h01 = __floats2half2_rn(y[j].x, y[j].y), h23 = __floats2half2_rn(y[j].z, y[j].w);
+          uint2 pk = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+          const bool live = (u0 + j) * kRowsPerIter < rows_left;
+          if (live) *reinterpret_cast<uint2*>(obase + static_cast<size_t>(pin + p.Ho) * p.Cout) = pk;
+          if (!p.emit_circular) pk = make_uint2(0u, 0u);
+          if (live && pin < p.Ho) *reinterpret_cast<uint2*>(obase + static_cast<size_t>(p.pix_per_img + p.Ho + pin) * p.Cout) = pk;
+          if (live && pin >= last_col0) *reinterpret_cast<uint2*>(obase + static_cast<size_t>(pin - last_col0) * p.Cout) = pk;
+        }
+      }
+      if (dbg && threadIdx.x == 64) p.dbg[12] = clock64();
+    }
+  }
+  if (clustered) cluster_sync_all();      // nobody exits while a peer may still read its staging tile / published moments
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<BLOCK_N>(tmem_base);
@@ -1104,9 +1254,9 @@ static int launch_conv_n(const ConvMaps& tm, const ConvParams& p, const ConvFuse
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (NSPLIT > 1) {   // the K splits of one tile form a thread-block cluster (DSMEM reduction in the epilogue)
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 1;
+  if (NSPLIT > 1 || p.clm > 1) {   // the K splits of one tile (DSMEM reduction in the epilogue) x the M tiles of one image
+    attr[na].id = cudaLaunchAttributeClusterDimension;    // (emitting launches: moments complete inside the cluster)
+    attr[na].val.clusterDim.x = p.clm;
     attr[na].val.clusterDim.y = 1;
     attr[na].val.clusterDim.z = NSPLIT;
     ++na;
@@ -1195,9 +1345,9 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
                         int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
                         int circular, int split_k, double* stats, const uint16_t* sc_x, const uint16_t* sc_x_lo,
                         const uint16_t* sc_wgt, int sc_cin, int terms, const rldm_conv_src* src, const rldm_conv_src* sc_src,
-                        bool query_only, void* stream) {
+                        bool query_only, void* stream, const rldm_conv_emit* emit = nullptr) {
   // query_only: no launch; returns 0 when this layer would run on the small-layer kernel (the one that can produce its
-  // own operand from `src`), 1 otherwise
+  // own operand from `src` and emit the next GroupNorm's operand), 1 otherwise
   if (terms == 0) terms = x_lo ? 3 : 1;          // legacy entry points: the operand planes say it
   RLDM_CHECK(terms >= 1 && terms <= 3, "conv_tc: terms must be 1, 2 or 3 (got %d)", terms);
   RLDM_CHECK(terms != 3 || x_lo, "conv_tc: split-fp16 x3 needs the low-order activation plane");
@@ -1246,6 +1396,22 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
   p.stats = stats;
   p.stats_G = Cout / 2;       // channel pairs per image
   RLDM_CHECK(pix >= 64 || !stats, "conv_tc: fused statistics need >= 64 pixels per image");
+  p.emit_out = nullptr; p.emit_gamma = nullptr; p.emit_beta = nullptr; p.emit_eps = 0.f;
+  p.emit_cpg = 4; p.emit_silu = 0; p.emit_circular = 1; p.clm = 1; p.emit_inv_n = 0.f;
+  if (emit) {
+    // the cluster (clm M tiles of one image x the K slices) must hold whole images: <= 8 CTAs
+    const int cpg = emit->G > 0 ? Cout / emit->G : 0;
+    RLDM_CHECK(emit->out && emit->gamma && emit->beta && emit->G > 0 && Cout % emit->G == 0 && cpg % 4 == 0 && cpg <= 64 &&
+               BN % cpg == 0 && (cpg & (cpg - 1)) == 0,
+               "conv_tc: emit needs out/gamma/beta and a power-of-two group size that is a multiple of 4 and divides the %d-wide tile (Cout=%d G=%d)",
+               BN, Cout, emit->G);
+    RLDM_CHECK(pix >= 64 && pix <= 8 * kBlockM && (pix & (pix - 1)) == 0,
+               "conv_tc: emit needs a power of two of 64..1024 output pixels per image (got %d)", pix);
+    p.emit_out = reinterpret_cast<__half*>(emit->out); p.emit_gamma = emit->gamma; p.emit_beta = emit->beta;
+    p.emit_eps = emit->eps; p.emit_cpg = cpg; p.emit_silu = emit->silu; p.emit_circular = emit->circular;
+    p.clm = pix > kBlockM ? pix / kBlockM : 1;
+    p.emit_inv_n = static_cast<float>(1.0 / (static_cast<double>(pix) * cpg));
+  }
 
   // ---- role-swapped kernel with pixel windows: 3x3, stride 1, symmetric pad, more 128x128 tiles than SMs, whole
   //      256-pixel units, room for two pixel windows plus >= 3 weight entries ----
@@ -1260,7 +1426,7 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
                          allowed(sw.conv_wt) && allowed(sw.conv_wt_halo);
     if (halo_wt) {
       if (query_only) return 1;
-      RLDM_CHECK(!src && !sc_src, "conv_tc: in-kernel operand production is a feature of the small-layer kernel only");
+      RLDM_CHECK(!src && !sc_src && !emit, "conv_tc: in-kernel operand production / emission is a feature of the small-layer kernel only");
       ConvMaps tmh;
       const int cols = 2 * (kBlockM / Ho);
       for (int part = 0; part < xp; ++part) {
@@ -1349,10 +1515,11 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
   }
   RLDM_CHECK(split == 1 || split == 2 || split == 4 || split == 8, "conv_tc: split_k must be 1, 2, 4 or 8 (got %d)", split);
   while (split > p.total_iters) split /= 2;
+  while (p.clm * split > 8) split /= 2;          // emitting launch: (M tiles of the image) x (K slices) <= 8 CTAs per cluster
   // more tiles than SMs and no K split: persistent CTAs with a double-buffered TMEM accumulator
   if (split == 1 && tiles > n_sms && sw.conv_persistent) {
     if (query_only) return 1;
-    RLDM_CHECK(!src && !sc_src, "conv_tc: in-kernel operand production is a feature of the small-layer kernel only");
+    RLDM_CHECK(!src && !sc_src && !emit, "conv_tc: in-kernel operand production / emission is a feature of the small-layer kernel only");
     // Cout tiles of 128 and whole 256-pixel units inside one image: roles swapped (weights = M side, N = 256 pixels)
     if (BN == 128 && p.M_total % 256 == 0 && pix % 256 == 0 && allowed(sw.conv_wt)) {
       if (int rc = build_maps()) return rc;
@@ -1439,6 +1606,24 @@ extern "C" int rldm_conv_tc_fused(const rldm_conv_src* src, const rldm_conv_src*
                                   const uint16_t* sc_x_lo, const uint16_t* sc_wgt, int sc_cin, int terms, void* stream) {
   return conv_tc_impl(x, x_lo, wgt, bias, temb, temb_stride, residual, out, B, W, H, Cin, Cout, ks, stride, pad_lo,
                       circular, split_k, stats, sc_x, sc_x_lo, sc_wgt, sc_cin, terms, src, sc_src, false, stream);
+}
+
+extern "C" int rldm_conv_tc_emit(const rldm_conv_emit* emit, const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt,
+                                 const float* bias, const float* temb, int temb_stride, const float* residual, float* out,
+                                 int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo, int circular,
+                                 int split_k, double* stats, const uint16_t* sc_x, const uint16_t* sc_x_lo,
+                                 const uint16_t* sc_wgt, int sc_cin, int terms, void* stream) {
+  return conv_tc_impl(x, x_lo, wgt, bias, temb, temb_stride, residual, out, B, W, H, Cin, Cout, ks, stride, pad_lo,
+                      circular, split_k, stats, sc_x, sc_x_lo, sc_wgt, sc_cin, terms, nullptr, nullptr, false, stream, emit);
+}
+
+extern "C" int rldm_conv_tc_emittable(int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo, int sc_cin,
+                                      int has_residual, int G) {
+  if (G <= 0 || Cout % G != 0) return 0;
+  const int cpg = Cout / G, BN = (Cout % 128 == 0) ? 128 : 64;
+  const int pix = (W / stride) * (H / stride);
+  if (cpg % 4 != 0 || cpg > 64 || (cpg & (cpg - 1)) != 0 || BN % cpg != 0 || pix < 64 || pix > 8 * 128 || (pix & (pix - 1)) != 0) return 0;
+  return rldm_conv_tc_fusable(B, W, H, Cin, Cout, ks, stride, pad_lo, sc_cin, has_residual);
 }
 
 extern "C" int rldm_conv_tc_fusable(int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo, int sc_cin,

@@ -462,6 +462,7 @@ extern "C" int rldm_fused_supported(const rldm_op* op) {
       return ((op->i[0] + op->i[1]) <= 2048 && elems <= (4ll << 20)) ? 1 : 0;
     }
     case RLDM_OP_CONV_TC: {
+      if (op->p[19]) return 0;        // emitting convolutions (rldm_conv_tc_emit) keep their own launch
       FConvGeom g;
       return fused_conv_geom(*op, g) ? 1 : 0;
     }

@@ -1400,6 +1400,17 @@ static int run_ops(const rldm_op* ops, int n_ops, unsigned long long* stamps, vo
                                   o.i[11], o.i[12], stream);
           break;
         }
+        if (o.p[19]) {                  // the epilogue also emits the next GroupNorm's operand (p[19..21], i[20..22], f[1])
+          rldm_conv_emit em;
+          em.out = (uint16_t*)o.p[19]; em.gamma = (const float*)o.p[20]; em.beta = (const float*)o.p[21];
+          em.eps = o.f[1]; em.G = o.i[20]; em.silu = o.i[21]; em.circular = o.i[22];
+          rc = rldm_conv_tc_emit(&em, (const uint16_t*)o.p[0], (const uint16_t*)o.p[6], (const uint16_t*)o.p[1],
+                                 (const float*)o.p[2], (const float*)o.p[3], o.i[0], (const float*)o.p[4],
+                                 (float*)o.p[5], o.i[1], o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], o.i[7], o.i[8], o.i[9],
+                                 o.i[10], (double*)o.p[7], (const uint16_t*)o.p[8], (const uint16_t*)o.p[9],
+                                 (const uint16_t*)o.p[10], o.i[11], o.i[12], stream);
+          break;
+        }
         rc = rldm_conv_tc_ex((const uint16_t*)o.p[0], (const uint16_t*)o.p[6], (const uint16_t*)o.p[1],
                              (const float*)o.p[2], (const float*)o.p[3], o.i[0], (const float*)o.p[4],
                              (float*)o.p[5], o.i[1], o.i[2], o.i[3], o.i[4], o.i[5], o.i[6], o.i[7], o.i[8], o.i[9],

@@ -72,6 +72,16 @@ FUSE_CONV_OUT = os.environ.get("RLDM_FUSE_CONV_OUT", "1") != "0"
 # hide the load -> SiLU -> store chain), against ~5 us for the whole rldm_prep launch including its kernel boundary
 # (scripts/own_operand_probe.py).
 FUSE_PREP = os.environ.get("RLDM_FUSE_PREP", "0") == "1"
+# RLDM_EMIT_PREP=1 (experiment, default off): the small-layer convolutions EMIT the next GroupNorm's operand
+# (rldm_conv_tc_emit): where a convolution's output is consumed through GroupNorm (+ SiLU) by another convolution on the
+# same grid (norm2 -> conv2 of a ResnetBlock2D, the GroupNorm of the next block), its epilogue completes the
+# (image, group) moments inside a thread-block cluster that covers whole images, normalises its own rows and writes the
+# fp16 operand: 40 of the 66 prep launches of a C3 UNet forward disappear (128 graph nodes).  Parity-green (the model
+# tests pass with it on) but measured SLOWER on B200 (176 vs 216 images/s at first, break-even on level 3 after tuning,
+# scripts/emit_probe.py): the four epilogue warps of a CTA run the gather + normalise + SiLU + store of a 128 x 128 tile
+# at ~4 cycles per instruction (one warp per scheduler), 9.5 k cycles for the 32 rows a thread owns when K is not split,
+# and clusters of 8 CTAs that must cover an image (levels 1-2) are scheduled later than the 2-4 CTA clusters they replace.
+EMIT_PREP = os.environ.get("RLDM_EMIT_PREP", "0") == "1"
 # RLDM_FUSE_LEVELS=1 (experiment, default off): runs of small consecutive ops (UNet levels 1..n) compiled into ONE
 # persistent launch each (csrc/fused_levels.cu).  Correct (tests/test_fused_gpu.py) but measured SLOWER on B200: a
 # grid-wide barrier costs 2.0-2.3 us against ~3 us for a PDL kernel boundary, and every convolution needs two of them
@@ -109,15 +119,24 @@ class Program:
         return sum(self.exec_launches if self.exec_launches is not None else self.launches)
 
     # ---- buffers ---------------------------------------------------------------------------
-    def alloc(self, shape, dtype=torch.float32):
+    def alloc(self, shape, dtype=torch.float32, before_op=None):
+        """before_op=k: the buffer will be WRITTEN by op k, which has already been emitted (an epilogue that produces
+        the operand of a later op): only buffers that were free before op k was appended may be reused."""
         n = 1
         for s in shape:
             n *= int(s)
         nbytes = n * torch.empty((), dtype=dtype).element_size()
         lst = self._free.get(nbytes)
+        raw = None
         if lst:
-            raw = lst.pop()
-        else:
+            if before_op is None:
+                raw = lst.pop()[0]
+            else:
+                for k in range(len(lst) - 1, -1, -1):
+                    if lst[k][1] <= before_op:
+                        raw = lst.pop(k)[0]
+                        break
+        if raw is None:
             raw = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self.keep.append(raw)
         return raw.view(dtype).view(*shape)
@@ -126,7 +145,7 @@ class Program:
         if t is None or self.no_reuse:
             return
         raw = t.view(-1).view(torch.uint8)
-        self._free.setdefault(raw.numel(), []).append(raw)
+        self._free.setdefault(raw.numel(), []).append((raw, len(self.ops)))     # free from op index len(ops) on
 
     def hold(self, t):
         self.keep.append(t)
@@ -240,10 +259,11 @@ class Operand:
 class Act:
     """Channels-last fp32 activation (B, W, H, C).  `stats` = arena slice [B][C/2][2] when the producing conv already
     accumulated the channel-pair moments of this tensor in its epilogue."""
-    __slots__ = ("t", "B", "W", "H", "C", "stats")
+    __slots__ = ("t", "B", "W", "H", "C", "stats", "producer")
 
-    def __init__(self, t, B, W, H, C, stats=None):
+    def __init__(self, t, B, W, H, C, stats=None, producer=None):
         self.t, self.B, self.W, self.H, self.C, self.stats = t, B, W, H, C, stats
+        self.producer = producer      # the rldm_conv_tc record that writes this tensor (it may emit a consumer's operand)
 
 
 def _is_identity_attn(m):
@@ -346,6 +366,15 @@ class Builder:
         c1 = x1.C if x1 is not None else 0
         C = x0.C + c1
         shape = (self.B, x0.W * up + 2, x0.H * up, C)
+        if not also_raw and self._emit(x0, x1, norm, silu, up, circular, terms):
+            pr = x0.producer
+            out = Operand(self.pg.alloc(shape, torch.float16, before_op=pr["index"]), None)
+            op = pr["op"]
+            op.p[19], op.p[20], op.p[21] = out.hi.data_ptr(), self.f32(norm.weight).data_ptr(), self.f32(norm.bias).data_ptr()
+            op.i[20], op.i[21], op.i[22] = norm.num_groups, int(silu), int(circular)
+            op.f[1] = norm.eps
+            pr["emitted"] = True
+            return out
         out = self.alloc_half(shape, terms)
         raw = self.alloc_half(shape, raw_terms) if also_raw else None
         spec = dict(x0=x0, x1=x1, norm=norm, silu=silu, up=up, circular=circular)
@@ -384,6 +413,15 @@ class Builder:
         out.src = None
         if with_raw:
             raw.src = None
+
+    def _emit(self, x0, x1, norm, silu, up, circular, terms):
+        """True when the convolution that wrote x0 can produce this operand in its epilogue (rldm_conv_tc_emit)."""
+        pr = getattr(x0, "producer", None)
+        if not (EMIT_PREP and not FUSE_LEVELS and CONV_KIND == _lib.OP_CONV_TC and pr is not None and not pr.get("emitted")
+                and x1 is None and up == 1 and norm is not None and terms < 3):
+            return False
+        g = pr["geom"]
+        return bool(_lib.lib().rldm_conv_tc_emittable(*g, norm.num_groups))
 
     def _fusable(self, W, H, cin, cout, ks, stride, pad_lo, sc_cin, has_residual):
         """True when this convolution runs on the small-layer kernel, which can produce its own operand."""
@@ -460,9 +498,13 @@ class Builder:
             ints += [mx0.C if mx0 is not None else 0, mx1.C if mx1 is not None else 0, norm.num_groups if norm is not None else 0,
                      int(m["silu"]), m["up"], sx0.C if sx0 is not None else 0, sx1.C if sx1 is not None else 0]
             feps = (norm.eps if norm is not None else 0.0,)
-        self.pg.add(kind, i=ints, f=feps, p=(xh[0], wt, bias, temb_t, residual.t if residual is not None else None, out,
-                                             xh[1], st) + sc_ptrs + src_ptrs, launches=1)
-        return Act(out, self.B, Wo, Ho, cout, st)
+        op = self.pg.add(kind, i=ints, f=feps, p=(xh[0], wt, bias, temb_t, residual.t if residual is not None else None, out,
+                                                  xh[1], st) + sc_ptrs + src_ptrs, launches=1)
+        producer = None
+        if kind == _lib.OP_CONV_TC and main_src is None and sc_src is None:
+            producer = dict(op=op, index=len(self.pg.ops) - 1,
+                            geom=(self.B, W, H, cin, cout, ks, stride, pad_lo, sc_cin, int(residual is not None)))
+        return Act(out, self.B, Wo, Ho, cout, st, producer)
 
     # ---- blocks ----------------------------------------------------------------------------
     def resnet(self, rb, x0, x1=None, free_inputs=True):
@@ -488,6 +530,10 @@ class Builder:
         h = self.conv(a1, x0.W, x0.H, rb.conv1, temb=temb, stats=True, terms=t1)
         self.free_half(a1)
         a2 = self.prep(h, None, rb.norm2, silu=True, circular=circ(rb.conv2), terms=t2, defer=True)
+        if h.producer is not None and h.producer.get("emitted"):
+            # conv1 wrote conv2's operand itself and nothing else reads h: no fp32 store, no channel-pair moments
+            h.producer["op"].p[5] = None
+            h.producer["op"].p[7] = None
         if fold:
             # the 1x1 conv_shortcut rides in conv2's K loop (extra K steps over the raw operand)
             out = self.conv(a2, x0.W, x0.H, rb.conv2, stats=True, shortcut=(xr, rb.conv_shortcut), terms=t2)

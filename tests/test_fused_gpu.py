@@ -286,3 +286,90 @@ def test_resnet_with_folded_shortcut_own_operands(monkeypatch, x3):
         pg.run(); torch.cuda.synchronize()
         outs.append(out.t.clone())
     assert relerr(outs[0], outs[1], "resnet_own_operands_vs_prep") < 2e-6
+
+
+# ---- convolutions that emit the next GroupNorm's operand (rldm_conv_tc_emit) -------------------------------------------
+EMIT_CASES = [
+    # B, W, H, Cin, Cout, ks, stride, residual, silu
+    (8, 32, 2, 256, 256, 3, 1, False, True),       # level 3 conv1: two images per tile, K split 8 ways inside the cluster
+    (3, 32, 2, 256, 256, 1, 1, True, False),       # attention out-projection, ragged batch: half-empty last tile, no K split
+    (8, 64, 4, 256, 256, 3, 1, True, True),        # level 2: an image is two M tiles -> cluster (2, 1, 4)
+    (2, 64, 4, 256, 256, 1, 1, True, True),
+    (8, 128, 8, 128, 128, 3, 1, False, True),      # level 1: eight M tiles per image -> cluster (8, 1, 1)
+    (5, 128, 8, 128, 128, 1, 1, True, False),
+    (8, 128, 8, 128, 128, 3, 2, False, True),      # Downsample2D: stride 2, output on the 64 x 4 grid
+    (4, 32, 2, 512, 256, 3, 1, False, True),       # 72 K steps
+]
+
+
+@pytest.mark.parametrize("case", EMIT_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_emit_matches_conv_then_prep(case, monkeypatch):
+    """conv -> GroupNorm (+ SiLU) -> fp16 operand: produced by the convolution's own epilogue (cluster-complete moments)
+    against the same convolution followed by a rldm_prep launch.  The fp32 output and its channel-pair moments are the
+    same kernel's (equal up to the K-split geometry); the operand differs by the summation order of the moments only:
+    at most one fp16 ulp on a handful of values."""
+    import rangeldm_b200 as R
+    from rangeldm_b200 import engine, models
+    B, W, H, Cin, Cout, ks, stride, use_res, silu = case
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(abs(hash(case)) % (2 ** 31))
+    conv = models.LoRACompatibleConv(Cin, Cout, ks, stride=stride, padding=ks // 2).to(dev)
+    conv.circular = True
+    norm = torch.nn.GroupNorm(32, Cout, eps=1e-5).to(dev)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (Cin * ks * ks) ** 0.5)
+        conv.bias.copy_(torch.randn(Cout, generator=g))
+        norm.weight.copy_(1 + 0.3 * torch.randn(Cout, generator=g)); norm.bias.copy_(0.3 * torch.randn(Cout, generator=g))
+    x0 = (torch.randn(B, W, H, Cin, generator=g) * 1.3 + 0.2).to(dev)
+    res = torch.randn(B, W // stride, H // stride, Cout, generator=g).to(dev) if use_res else None
+    outs = []
+    for emit in (True, False):
+        monkeypatch.setattr(engine, "EMIT_PREP", emit)
+        pg = engine.Program(dev)
+        pg.no_reuse = True
+        bd = engine.Builder(pg, B, cache={}, terms_of=lambda w: 1)
+        a0 = engine.Act(pg.hold(x0.clone()), B, W, H, Cin)
+        ra = engine.Act(pg.hold(res.clone()), B, W // stride, H // stride, Cout) if use_res else None
+        opnd = bd.prep(a0, None, None, terms=1)
+        h = bd.conv(opnd, W, H, conv, residual=ra, stats=True, terms=1)
+        o2 = bd.prep(h, None, norm, silu=silu, terms=1)
+        bd.finish(); pg.finalize()
+        kinds = [o.kind for o in pg.ops]
+        assert kinds.count(R._lib.OP_PREP) == (1 if emit else 2), kinds
+        for _ in range(2):
+            pg.run()
+        torch.cuda.synchronize()
+        outs.append((h.t.clone(), h.stats.clone(), o2.hi.clone()))
+    (fa, fs, fo), (ua, us, uo) = outs
+    assert relerr(fa, ua, "conv_emit_fp32_out") < 2e-6
+    assert torch.allclose(fs, us, rtol=1e-6, atol=1e-3)
+    d = (fo.float() - uo.float()).abs()
+    tol = 2e-3 * uo.float().abs().clamp_min(1.0)            # two fp16 ulps
+    assert bool((d <= tol).all()), float((d / tol).max())
+    assert float((d > 0).float().mean()) < 0.02             # and almost every value is bit-identical
+    # halo columns of the W-padded operand: wrap of the image's first / last column
+    assert torch.equal(fo[:, 0], fo[:, -2]) and torch.equal(fo[:, -1], fo[:, 1])
+
+
+def test_unet_with_emitting_convolutions_matches_oracle(monkeypatch):
+    """C3 UNet forward, batch 3, with RLDM_EMIT_PREP on: 40 prep launches fewer, same parity gate as the default path."""
+    import rangeldm_b200 as R
+    from rangeldm_b200 import engine
+    from oracle import nets
+    from oracle.make_golden import seeded
+    monkeypatch.setattr(engine, "EMIT_PREP", True)
+    dev = torch.device("cuda")
+    ou = seeded(nets.OracleUNet2DModel, 11, **nets.UNET_C3)
+    u = R.UNet2DModel(**nets.UNET_C3)
+    R.replace_down(u); R.replace_conv(u)
+    u.load_state_dict(ou.state_dict())
+    u = u.to(dev)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 5, 256, 16, generator=g)
+    t = torch.tensor([900, 417, 12])
+    with torch.no_grad():
+        ref = ou(x, t)
+    y = u(x.to(dev), t.to(dev)).sample
+    plan = u.plan(3, 256, 16, 1)
+    assert sum(1 for op in plan.prog.ops if op.kind == R._lib.OP_CONV_TC and op.p[19]) == 40
+    assert relerr(y.cpu(), ref, "unet_c3_emit_prep") < 5e-4

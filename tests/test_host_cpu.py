@@ -138,6 +138,17 @@ def test_dry_run_plans_and_fused_program_launch_counts(monkeypatch):
     assert kinds1.count(_lib.OP_PREP) == 16 and len(kinds1) == 118
     assert sum(1 for op in plan1.prog.ops if op.kind == _lib.OP_CONV_TC and (op.p[11] or op.p[17])) == 50
     monkeypatch.setattr(engine, "FUSE_PREP", False)
+    # opt-in experiment RLDM_EMIT_PREP=1: 40 convolutions of levels 1-3 write the next GroupNorm's operand themselves (17
+    # of them, the conv1 of the ResnetBlock2Ds, no longer write an fp32 output at all)
+    monkeypatch.setattr(engine, "EMIT_PREP", True)
+    u.invalidate_plans()
+    plan3 = u.plan(8, 256, 16, 1)
+    kinds3 = [op.kind for op in plan3.prog.ops]
+    convs3 = [op for op in plan3.prog.ops if op.kind == _lib.OP_CONV_TC]
+    assert len(kinds3) == 128 and kinds3.count(_lib.OP_PREP) == 26
+    assert sum(1 for op in convs3 if op.p[19]) == 40 and sum(1 for op in convs3 if not op.p[5]) == 17
+    assert all(op.p[19] and op.p[20] and op.p[21] and op.i[20] == 32 for op in convs3 if not op.p[5])
+    monkeypatch.setattr(engine, "EMIT_PREP", False)
     # opt-in experiment RLDM_FUSE_LEVELS=1: 135 small ops of levels 1-3 as 5 fused persistent launches between the five
     # N = 1024 attention kernels
     monkeypatch.setattr(engine, "FUSE_LEVELS", True)
