@@ -92,6 +92,10 @@ struct ConvFused {
   int main_on, sc_on;
 };
 constexpr int kFusedTabFloats = 1024;           // scale/shift of up to 512 channels
+// small-layer kernel: TMA producer warp, MMA warp, kConvEpiWarps epilogue warps (two per TMEM lane quadrant: the epilogue
+// of these launches is latency-bound code that one warp per scheduler runs at ~4 cycles per instruction)
+constexpr int kConvEpiWarps = 8;
+constexpr int kConvThreads = 64 + 32 * kConvEpiWarps;
 // in-kernel operand production: items per thread and step / software pipelining of prep_range (the body runs ONCE per
 // launch on one warp per scheduler: a long unrolled body is bound by instruction fetch, `stall_no_inst` in ncu)
 #ifndef RLDM_OWN_U
@@ -160,7 +164,7 @@ __device__ __forceinline__ void issue_kstep(uint32_t d_tmem, uint32_t a_addr, ui
 // W-padded operand (halo columns included) the next convolution reads.  One prep launch and one kernel boundary less
 // per GroupNorm; the fp32 output (p.out) is still written when the residual stream needs it.
 template <int BLOCK_N, int STAGES, int TERMS, int NSPLIT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __grid_constant__ ConvFused fz) {
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   constexpr int XP = x_parts(TERMS), WP = w_parts(TERMS);
@@ -174,7 +178,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
   constexpr int kLanesPerRow = BLOCK_N / 4;               // 32 (BN=128) or 16 (BN=64)
   constexpr int kRowsPerIter = 32 / kLanesPerRow;         // 1 or 2
   constexpr int kRowsCta = kBlockM / NSPLIT;              // rows this CTA finalises
-  constexpr int kRowsWarp = kRowsCta / 4;                 // contiguous rows per epilogue warp
+  constexpr int kRowsWarp = kRowsCta / kConvEpiWarps;     // contiguous rows per epilogue warp
   constexpr int kPerLane = kRowsWarp / kRowsPerIter;      // float4 per lane: 32, 16, 8, 4 (BN=128); half for BN=64
   static_assert(kPerLane >= 1, "tile too small for this split");
   extern __shared__ uint8_t smem_raw[];
@@ -185,10 +189,10 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* red_s = reinterpret_cast<float*>(tmem_ptr + 4);       // [4][BLOCK_N/2]
-  float* red_q = red_s + 4 * (BLOCK_N / 2);
-  int* red_b = reinterpret_cast<int*>(red_q + 4 * (BLOCK_N / 2));
-  float* fused_tab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(red_b + 4) + 15) & ~static_cast<uintptr_t>(15));   // [kFusedTabFloats], float4 reads
+  float* red_s = reinterpret_cast<float*>(tmem_ptr + 4);       // [kConvEpiWarps][BLOCK_N/2]
+  float* red_q = red_s + kConvEpiWarps * (BLOCK_N / 2);
+  int* red_b = reinterpret_cast<int*>(red_q + kConvEpiWarps * (BLOCK_N / 2));
+  float* fused_tab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(red_b + kConvEpiWarps) + 15) & ~static_cast<uintptr_t>(15));   // [kFusedTabFloats], float4 reads
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -248,7 +252,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
   if (dbg && threadIdx.x == 0) p.dbg[1] = clock64();
 
   if (fz.main_on | fz.sc_on) {
-    // ---- in-kernel operand production (see ConvFused): all 192 threads -- nobody has anything else to do until the
+    // ---- in-kernel operand production (see ConvFused): all threads -- nobody has anything else to do until the
     // operand exists (the first weight tiles are already in flight) ----
     {
       const int tid = threadIdx.x;
@@ -265,7 +269,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
         const int first = p.stride * wo0 - p.pad_lo + 1;    // padded column of tap ti = 0
         const int col_lo = max(first, 0), col_hi = min(first + (p.ks - 1) + ncols * p.stride, p.W_in + 2);
         for (int b = b0; b < b_end; ++b) {
-          prep_range<false, kOwnU, kOwnPipe>(fz.main, b, col_lo * Hop, col_hi * Hop, ch_lo, ch_hi, fused_tab, tid, 192, 0);
+          prep_range<false, kOwnU, kOwnPipe>(fz.main, b, col_lo * Hop, col_hi * Hop, ch_lo, ch_hi, fused_tab, tid, kConvThreads, 0);
           __syncthreads();                                  // scale / shift table reusable
         }
       }
@@ -273,7 +277,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
       if (fz.sc_on && sc_begin < it1) {
         const int ch_lo = (sc_begin - p.main_iters) * kBlockK, ch_hi = (it1 - p.main_iters) * kBlockK;
         for (int b = b0; b < b_end; ++b)
-          prep_range<false, kOwnU, kOwnPipe>(fz.sc, b, (wo0 + 1) * p.Ho, (wo0 + 1 + ncols) * p.Ho, ch_lo, ch_hi, fused_tab, tid, 192, 0);
+          prep_range<false, kOwnU, kOwnPipe>(fz.sc, b, (wo0 + 1) * p.Ho, (wo0 + 1 + ncols) * p.Ho, ch_lo, ch_hi, fused_tab, tid, kConvThreads, 0);
       }
       asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores -> TMA (async proxy) reads below
     }
@@ -283,7 +287,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
   }
 
   // epilogue coordinates (meaningful for warps >= 2)
-  const int ew = (warp - 2) & 3;
+  const int ew = (warp - 2) & (kConvEpiWarps - 1);
   const int r_begin = blockIdx.z * kRowsCta + ew * kRowsWarp;     // first tile row this warp finalises
   const int col = (lane % kLanesPerRow) * 4;
   const int rsub = lane / kLanesPerRow;
@@ -371,8 +375,12 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
     // fp32 accumulator tile [128][BLOCK_N] is staged over them (row pitch +4 floats: conflict-free float4).
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     float* stage_row = reinterpret_cast<float*>(smem) + (q * 32 + lane) * kStagePitch;
+    // kConvEpiWarps / 4 warps share a lane quadrant; each takes its share of the 32-column chunks
+    constexpr int kChunksPerWarp = (BLOCK_N / 32) / (kConvEpiWarps / 4);
+    static_assert(kChunksPerWarp >= 1, "more epilogue warps than 32-column chunks per quadrant");
+    const int nc0 = ((warp - 2) >> 2) * kChunksPerWarp;
 #pragma unroll 1
-    for (int nc = 0; nc < BLOCK_N / 32; ++nc) {
+    for (int nc = nc0; nc < nc0 + kChunksPerWarp; ++nc) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + nc * 32, r);
       tmem_ld_wait();
@@ -391,7 +399,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
   if (NSPLIT > 1) {
     cluster_sync_all();
   } else if (warp >= 2) {
-    asm volatile("bar.sync 1, 128;" ::: "memory");        // only the epilogue warps touch the staging tile
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvEpiWarps) : "memory");        // only the epilogue warps touch the staging tile
   }
   if (warp >= 2) {
     if (dbg && threadIdx.x == 64) p.dbg[7] = clock64();
@@ -472,13 +480,13 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
         red_s[ew * nslots + col / 2 + 1] = s23; red_q[ew * nslots + col / 2 + 1] = q23;
       }
       if (lane == 0) red_b[ew] = m_first < p.M_total ? bimg : -1;
-      asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps only
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvEpiWarps) : "memory");      // the epilogue warps only
       const int t = ew * 32 + lane;
       if (t < nslots) {
         const int g = n0 / 2 + t;
         double ds = 0.0, dq = 0.0;
         int cur = red_b[0];
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < kConvEpiWarps; ++e) {
           const int be = red_b[e];
           if (be != cur) {
             if (cur >= 0) {
@@ -500,7 +508,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
   const bool clustered = NSPLIT > 1 || p.clm > 1;
   if (p.emit_out) {
     // ---- EMIT: (image, group) moments complete inside the cluster -> normalise own rows -> fp16 operand ----
-    // published per epilogue warp: [4][32] (sum, sum of squares) of the warp's rows per group of the tile
+    // published per epilogue warp: [kConvEpiWarps][32] (sum, sum of squares) of the warp's rows per group of the tile
     float2* pub = reinterpret_cast<float2*>(fused_tab);
     const int lpg = p.emit_cpg >> 2;                        // lanes (column quads) per group
     const int gl = col / p.emit_cpg;                        // group of this thread's columns inside the tile
@@ -512,27 +520,27 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
       if (rsub == 0 && ((lane % kLanesPerRow) % lpg) == 0) pub[ew * 32 + gl] = make_float2(es, eq);
     }
     if (clustered) cluster_sync_all();
-    else if (warp >= 2) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else if (warp >= 2) asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvEpiWarps) : "memory");
     if (dbg && threadIdx.x == 64) p.dbg[10] = clock64();
     if (warp >= 2) {
       const int csize = clustered ? NSPLIT * p.clm : 1;
       const uint32_t pub_u32 = smem_u32(fused_tab);
       // Which image the rows of warp w of cluster rank rk = (x, z) belong to follows from the geometry (tile blockIdx.x
-      // - cl_x + x, rows [z * kRowsCta + w * kRowsWarp, ...)): only the partials of this thread's image are loaded, four
+      // - cl_x + x, rows [z * kRowsCta + w * kRowsWarp, ...)): only the partials of this thread's image are loaded, two
       // ranks (16 independent DSMEM loads) per round trip.
       const int tile0 = static_cast<int>(blockIdx.x) - cl_x;
       const int img_lo = bimg * p.pix_per_img, img_hi = min(img_lo + p.pix_per_img, p.M_total);   // rows of this thread's image
       const int clm_sh = 31 - __clz(p.clm);
       float S = 0.f, Q = 0.f;           // <= 32 partials of <= 1024 values each: fp32 is ample next to the fp16 operand
-      for (int rk0 = 0; rk0 < csize; rk0 += 4) {
-        float2 pq[4][4];
+      for (int rk0 = 0; rk0 < csize; rk0 += 2) {
+        float2 pq[2][kConvEpiWarps];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
           const int rk = rk0 + j;
           const int x = rk & (p.clm - 1), z = rk >> clm_sh;       // clm is a power of two (host check)
           const uint32_t base = clustered ? mapa_u32(pub_u32, rk < csize ? rk : 0) : pub_u32;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
+          for (int w = 0; w < kConvEpiWarps; ++w) {
             const int mf = (tile0 + x) * kBlockM + z * kRowsCta + w * kRowsWarp;
             pq[j][w] = make_float2(0.f, 0.f);
             if (rk < csize && mf >= img_lo && mf < img_hi)
@@ -541,10 +549,9 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
           }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          S += (pq[j][0].x + pq[j][1].x) + (pq[j][2].x + pq[j][3].x);
-          Q += (pq[j][0].y + pq[j][1].y) + (pq[j][2].y + pq[j][3].y);
-        }
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int w = 0; w < kConvEpiWarps; w += 2) { S += pq[j][w].x + pq[j][w + 1].x; Q += pq[j][w].y + pq[j][w + 1].y; }
       }
       const float mu = S * p.emit_inv_n;
       const float var = fmaxf(fmaf(-mu, mu, Q * p.emit_inv_n), 0.f);
@@ -1223,7 +1230,7 @@ constexpr int conv_stage_bytes(int bn, int terms) { return x_parts(terms) * kABy
 constexpr int conv_stages(int bn, int terms) { return (bn == 128 && terms == 3) ? 3 : 4; }
 constexpr int conv_smem(int bn, int terms) {
   // pipeline stages (+ alignment slack) + barriers/TMEM pointer + the per-warp GroupNorm-moment scratch
-  return conv_stages(bn, terms) * conv_stage_bytes(bn, terms) + 1024 + 256 + 2 * 4 * (bn / 2) * 4 + 64 + kFusedTabFloats * 4 + 16;
+  return conv_stages(bn, terms) * conv_stage_bytes(bn, terms) + 1024 + 256 + 2 * kConvEpiWarps * (bn / 2) * 4 + 64 + kFusedTabFloats * 4 + 16;
 }
 constexpr int pers_stage_bytes(int bn, int terms, int mt) { return mt * x_parts(terms) * kABytes + w_parts(terms) * bn * kBlockK * 2; }
 constexpr int pers_fixed(int bn) { return kBlockM * 36 * 4 + 256 + 2 * 4 * (bn / 2) * 4 + 64 + 1024; }
@@ -1244,7 +1251,7 @@ static int launch_conv_n(const ConvMaps& tm, const ConvParams& p, const ConvFuse
   dim3 grid((p.M_total + kBlockM - 1) / kBlockM, p.Cout / BLOCK_N, NSPLIT);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(kConvThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
