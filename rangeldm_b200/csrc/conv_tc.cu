@@ -92,10 +92,13 @@ struct ConvFused {
   int main_on, sc_on;
 };
 constexpr int kFusedTabFloats = 1024;           // scale/shift of up to 512 channels
-// small-layer kernel: TMA producer warp, MMA warp, kConvEpiWarps epilogue warps (two per TMEM lane quadrant: the epilogue
-// of these launches is latency-bound code that one warp per scheduler runs at ~4 cycles per instruction)
-constexpr int kConvEpiWarps = 8;
-constexpr int kConvThreads = 64 + 32 * kConvEpiWarps;
+// small-layer kernel: TMA producer warp, MMA warp and eight epilogue warps (two per TMEM lane quadrant).  The epilogue
+// of these launches is latency-bound code that one warp per scheduler runs at ~4 cycles per instruction: with two warps
+// per scheduler the 1x1 projections lose ~1 us and the stride-2 convolutions 2-3 us per launch (UNet forward 1647 ->
+// 1583 us).  Four warps for the 4- and 8-way K splits (16-32 rows per CTA) measured the same within noise.
+__host__ __device__ constexpr int conv_epi_warps(int nsplit) { return 8; }
+__host__ __device__ constexpr int conv_threads(int nsplit) { return 64 + 32 * conv_epi_warps(nsplit); }
+constexpr int kConvEpiWarpsMax = 8;
 // in-kernel operand production: items per thread and step / software pipelining of prep_range (the body runs ONCE per
 // launch on one warp per scheduler: a long unrolled body is bound by instruction fetch, `stall_no_inst` in ncu)
 #ifndef RLDM_OWN_U
@@ -164,8 +167,9 @@ __device__ __forceinline__ void issue_kstep(uint32_t d_tmem, uint32_t a_addr, ui
 // W-padded operand (halo columns included) the next convolution reads.  One prep launch and one kernel boundary less
 // per GroupNorm; the fp32 output (p.out) is still written when the residual stream needs it.
 template <int BLOCK_N, int STAGES, int TERMS, int NSPLIT>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(conv_threads(NSPLIT), 1)
 conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __grid_constant__ ConvFused fz) {
+  constexpr int kEpiWarps = conv_epi_warps(NSPLIT), kThreads = conv_threads(NSPLIT);
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   constexpr int XP = x_parts(TERMS), WP = w_parts(TERMS);
   constexpr int kStageBytes = XP * kABytes + WP * kBBytes;    // [X_hi][X_lo][W_hi][W_lo]
@@ -178,7 +182,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
   constexpr int kLanesPerRow = BLOCK_N / 4;               // 32 (BN=128) or 16 (BN=64)
   constexpr int kRowsPerIter = 32 / kLanesPerRow;         // 1 or 2
   constexpr int kRowsCta = kBlockM / NSPLIT;              // rows this CTA finalises
-  constexpr int kRowsWarp = kRowsCta / kConvEpiWarps;     // contiguous rows per epilogue warp
+  constexpr int kRowsWarp = kRowsCta / kEpiWarps;     // contiguous rows per epilogue warp
   constexpr int kPerLane = kRowsWarp / kRowsPerIter;      // float4 per lane: 32, 16, 8, 4 (BN=128); half for BN=64
   static_assert(kPerLane >= 1, "tile too small for this split");
   extern __shared__ uint8_t smem_raw[];
@@ -189,10 +193,10 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* red_s = reinterpret_cast<float*>(tmem_ptr + 4);       // [kConvEpiWarps][BLOCK_N/2]
-  float* red_q = red_s + kConvEpiWarps * (BLOCK_N / 2);
-  int* red_b = reinterpret_cast<int*>(red_q + kConvEpiWarps * (BLOCK_N / 2));
-  float* fused_tab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(red_b + kConvEpiWarps) + 15) & ~static_cast<uintptr_t>(15));   // [kFusedTabFloats], float4 reads
+  float* red_s = reinterpret_cast<float*>(tmem_ptr + 4);       // [kEpiWarps][BLOCK_N/2]
+  float* red_q = red_s + kEpiWarps * (BLOCK_N / 2);
+  int* red_b = reinterpret_cast<int*>(red_q + kEpiWarps * (BLOCK_N / 2));
+  float* fused_tab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(red_b + kEpiWarps) + 15) & ~static_cast<uintptr_t>(15));   // [kFusedTabFloats], float4 reads
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -269,7 +273,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
         const int first = p.stride * wo0 - p.pad_lo + 1;    // padded column of tap ti = 0
         const int col_lo = max(first, 0), col_hi = min(first + (p.ks - 1) + ncols * p.stride, p.W_in + 2);
         for (int b = b0; b < b_end; ++b) {
-          prep_range<false, kOwnU, kOwnPipe>(fz.main, b, col_lo * Hop, col_hi * Hop, ch_lo, ch_hi, fused_tab, tid, kConvThreads, 0);
+          prep_range<false, kOwnU, kOwnPipe>(fz.main, b, col_lo * Hop, col_hi * Hop, ch_lo, ch_hi, fused_tab, tid, kThreads, 0);
           __syncthreads();                                  // scale / shift table reusable
         }
       }
@@ -277,7 +281,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
       if (fz.sc_on && sc_begin < it1) {
         const int ch_lo = (sc_begin - p.main_iters) * kBlockK, ch_hi = (it1 - p.main_iters) * kBlockK;
         for (int b = b0; b < b_end; ++b)
-          prep_range<false, kOwnU, kOwnPipe>(fz.sc, b, (wo0 + 1) * p.Ho, (wo0 + 1 + ncols) * p.Ho, ch_lo, ch_hi, fused_tab, tid, kConvThreads, 0);
+          prep_range<false, kOwnU, kOwnPipe>(fz.sc, b, (wo0 + 1) * p.Ho, (wo0 + 1 + ncols) * p.Ho, ch_lo, ch_hi, fused_tab, tid, kThreads, 0);
       }
       asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores -> TMA (async proxy) reads below
     }
@@ -287,7 +291,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
   }
 
   // epilogue coordinates (meaningful for warps >= 2)
-  const int ew = (warp - 2) & (kConvEpiWarps - 1);
+  const int ew = (warp - 2) & (kEpiWarps - 1);
   const int r_begin = blockIdx.z * kRowsCta + ew * kRowsWarp;     // first tile row this warp finalises
   const int col = (lane % kLanesPerRow) * 4;
   const int rsub = lane / kLanesPerRow;
@@ -375,8 +379,8 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
     // fp32 accumulator tile [128][BLOCK_N] is staged over them (row pitch +4 floats: conflict-free float4).
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     float* stage_row = reinterpret_cast<float*>(smem) + (q * 32 + lane) * kStagePitch;
-    // kConvEpiWarps / 4 warps share a lane quadrant; each takes its share of the 32-column chunks
-    constexpr int kChunksPerWarp = (BLOCK_N / 32) / (kConvEpiWarps / 4);
+    // kEpiWarps / 4 warps share a lane quadrant; each takes its share of the 32-column chunks
+    constexpr int kChunksPerWarp = (BLOCK_N / 32) / (kEpiWarps / 4);
     static_assert(kChunksPerWarp >= 1, "more epilogue warps than 32-column chunks per quadrant");
     const int nc0 = ((warp - 2) >> 2) * kChunksPerWarp;
 #pragma unroll 1
@@ -399,7 +403,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
   if (NSPLIT > 1) {
     cluster_sync_all();
   } else if (warp >= 2) {
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvEpiWarps) : "memory");        // only the epilogue warps touch the staging tile
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");        // only the epilogue warps touch the staging tile
   }
   if (warp >= 2) {
     if (dbg && threadIdx.x == 64) p.dbg[7] = clock64();
@@ -480,13 +484,13 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
         red_s[ew * nslots + col / 2 + 1] = s23; red_q[ew * nslots + col / 2 + 1] = q23;
       }
       if (lane == 0) red_b[ew] = m_first < p.M_total ? bimg : -1;
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvEpiWarps) : "memory");      // the epilogue warps only
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");      // the epilogue warps only
       const int t = ew * 32 + lane;
       if (t < nslots) {
         const int g = n0 / 2 + t;
         double ds = 0.0, dq = 0.0;
         int cur = red_b[0];
-        for (int e = 0; e < kConvEpiWarps; ++e) {
+        for (int e = 0; e < kEpiWarps; ++e) {
           const int be = red_b[e];
           if (be != cur) {
             if (cur >= 0) {
@@ -508,7 +512,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
   const bool clustered = NSPLIT > 1 || p.clm > 1;
   if (p.emit_out) {
     // ---- EMIT: (image, group) moments complete inside the cluster -> normalise own rows -> fp16 operand ----
-    // published per epilogue warp: [kConvEpiWarps][32] (sum, sum of squares) of the warp's rows per group of the tile
+    // published per epilogue warp: [kEpiWarps][32] (sum, sum of squares) of the warp's rows per group of the tile
     float2* pub = reinterpret_cast<float2*>(fused_tab);
     const int lpg = p.emit_cpg >> 2;                        // lanes (column quads) per group
     const int gl = col / p.emit_cpg;                        // group of this thread's columns inside the tile
@@ -520,7 +524,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
       if (rsub == 0 && ((lane % kLanesPerRow) % lpg) == 0) pub[ew * 32 + gl] = make_float2(es, eq);
     }
     if (clustered) cluster_sync_all();
-    else if (warp >= 2) asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvEpiWarps) : "memory");
+    else if (warp >= 2) asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
     if (dbg && threadIdx.x == 64) p.dbg[10] = clock64();
     if (warp >= 2) {
       const int csize = clustered ? NSPLIT * p.clm : 1;
@@ -533,14 +537,14 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
       const int clm_sh = 31 - __clz(p.clm);
       float S = 0.f, Q = 0.f;           // <= 32 partials of <= 1024 values each: fp32 is ample next to the fp16 operand
       for (int rk0 = 0; rk0 < csize; rk0 += 2) {
-        float2 pq[2][kConvEpiWarps];
+        float2 pq[2][kEpiWarps];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int rk = rk0 + j;
           const int x = rk & (p.clm - 1), z = rk >> clm_sh;       // clm is a power of two (host check)
           const uint32_t base = clustered ? mapa_u32(pub_u32, rk < csize ? rk : 0) : pub_u32;
 #pragma unroll
-          for (int w = 0; w < kConvEpiWarps; ++w) {
+          for (int w = 0; w < kEpiWarps; ++w) {
             const int mf = (tile0 + x) * kBlockM + z * kRowsCta + w * kRowsWarp;
             pq[j][w] = make_float2(0.f, 0.f);
             if (rk < csize && mf >= img_lo && mf < img_hi)
@@ -551,7 +555,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
-          for (int w = 0; w < kConvEpiWarps; w += 2) { S += pq[j][w].x + pq[j][w + 1].x; Q += pq[j][w].y + pq[j][w + 1].y; }
+          for (int w = 0; w < kEpiWarps; w += 2) { S += pq[j][w].x + pq[j][w + 1].x; Q += pq[j][w].y + pq[j][w + 1].y; }
       }
       const float mu = S * p.emit_inv_n;
       const float var = fmaxf(fmaf(-mu, mu, Q * p.emit_inv_n), 0.f);
@@ -1230,7 +1234,7 @@ constexpr int conv_stage_bytes(int bn, int terms) { return x_parts(terms) * kABy
 constexpr int conv_stages(int bn, int terms) { return (bn == 128 && terms == 3) ? 3 : 4; }
 constexpr int conv_smem(int bn, int terms) {
   // pipeline stages (+ alignment slack) + barriers/TMEM pointer + the per-warp GroupNorm-moment scratch
-  return conv_stages(bn, terms) * conv_stage_bytes(bn, terms) + 1024 + 256 + 2 * kConvEpiWarps * (bn / 2) * 4 + 64 + kFusedTabFloats * 4 + 16;
+  return conv_stages(bn, terms) * conv_stage_bytes(bn, terms) + 1024 + 256 + 2 * kConvEpiWarpsMax * (bn / 2) * 4 + 64 + kFusedTabFloats * 4 + 16;
 }
 constexpr int pers_stage_bytes(int bn, int terms, int mt) { return mt * x_parts(terms) * kABytes + w_parts(terms) * bn * kBlockK * 2; }
 constexpr int pers_fixed(int bn) { return kBlockM * 36 * 4 + 256 + 2 * 4 * (bn / 2) * 4 + 64 + 1024; }
@@ -1251,7 +1255,7 @@ static int launch_conv_n(const ConvMaps& tm, const ConvParams& p, const ConvFuse
   dim3 grid((p.M_total + kBlockM - 1) / kBlockM, p.Cout / BLOCK_N, NSPLIT);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(kConvThreads);
+  cfg.blockDim = dim3(conv_threads(NSPLIT));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
