@@ -191,6 +191,7 @@ def per_op_profile(sampler):
     # (profiles the first sub-batch program: with RLDM_STREAMS=2 that is half of the per-GPU batch)
     progs = [(sampler.plan.prog, STEPS)] + ([(sampler.dec.prog, 1)] if sampler.dec is not None else [])
     ms, cnt, flops, fused_flops, hw_flops, nbytes = {}, {}, 0.0, 0.0, 0.0, 0.0
+    set_bytes, set_n = 0.0, 0          # the launches of ONE UNet forward + one decode: the set the ncu traffic figure averages
     for prog, weight in progs:
         for op, (i, j), us in zip(prog.exec_ops, prog.exec_src, timed_profile(prog)):
             k = OP_NAMES.get(op.kind, str(op.kind))
@@ -200,9 +201,10 @@ def per_op_profile(sampler):
                 flops += weight * conv_flops(op)
                 hw_flops += weight * conv_flops(op) * op.i[12]       # MMAs actually issued: 1, 2 or 3 per algorithmic MAC
                 nbytes += weight * conv_bytes(op)
+                set_bytes += conv_bytes(op); set_n += 1
             if op.kind == _lib.OP_FUSED:          # convolutions inside a fused run of small layers
                 fused_flops += weight * sum(conv_flops(o) for o in prog.ops[i:j] if o.kind == _lib.OP_CONV_TC)
-    return ms, cnt, flops, fused_flops, hw_flops, nbytes
+    return ms, cnt, flops, fused_flops, hw_flops, nbytes, set_bytes / max(set_n, 1)
 
 
 def run_native(args):
@@ -289,7 +291,7 @@ def run_native(args):
     out = None
     if rank == 0:
         burst, sustained, hbm, src = peaks()
-        ms, cnt, flops, fused_flops, hw_flops, conv_nbytes = per_op_profile(sampler)
+        ms, cnt, flops, fused_flops, hw_flops, conv_nbytes, set_bytes = per_op_profile(sampler)
         conv_ms = ms.get("conv_tc", 0.0)
         all_ms = sum(ms.values())
         achieved = flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
@@ -313,6 +315,9 @@ def run_native(args):
                          "frac": round(achieved / burst, 4), "peak_source": f"{src} bf16 burst (kernel timed alone: device-side stamps around every launch, in-graph)",
                          "frac_of_sustained": round(achieved / sustained, 4), "traffic": conv_traffic(),
                          "algorithmic_bytes": round(conv_nbytes / max(cnt.get("conv_tc", 1), 1)),
+                         "traffic_set": {"what": "mean over the conv launches of ONE UNet forward + ONE decode (the set of the ncu capture, cold L2)",
+                                         "traffic": conv_traffic(), "algorithmic_bytes": round(set_bytes),
+                                         "ratio": round(conv_traffic() / set_bytes, 3) if conv_traffic() and set_bytes else None},
                          "issued_tflops": round(hw_flops / (conv_ms / 1e3) / 1e12, 2) if conv_ms > 0 else 0.0,
                          "launches": cnt.get("conv_tc", 0), "avg_launch_us": round(1e3 * conv_ms / max(cnt.get("conv_tc", 1), 1), 2),
                          "share_of_step": round(conv_ms / all_ms, 4) if all_ms else None,
