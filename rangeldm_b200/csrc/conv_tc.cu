@@ -96,9 +96,14 @@ constexpr int kFusedTabFloats = 1024;           // scale/shift of up to 512 chan
 // of these launches is latency-bound code that one warp per scheduler runs at ~4 cycles per instruction: with two warps
 // per scheduler the 1x1 projections lose ~1 us and the stride-2 convolutions 2-3 us per launch (UNet forward 1647 ->
 // 1583 us).  Four warps for the 4- and 8-way K splits (16-32 rows per CTA) measured the same within noise.
-__host__ __device__ constexpr int conv_epi_warps(int nsplit) { return 8; }
-__host__ __device__ constexpr int conv_threads(int nsplit) { return 64 + 32 * conv_epi_warps(nsplit); }
-constexpr int kConvEpiWarpsMax = 8;
+// Sixteen warps (four per quadrant) for the un-split and two-way split launches measured no better (224.1 vs 224.4
+// images/s): compile with -DRLDM_CONV_EPI16_MAXSPLIT=2 to re-check.
+#ifndef RLDM_CONV_EPI16_MAXSPLIT
+#define RLDM_CONV_EPI16_MAXSPLIT 0
+#endif
+__host__ __device__ constexpr int conv_epi_warps(int nsplit, int bn = 128) { return (bn == 128 && nsplit <= RLDM_CONV_EPI16_MAXSPLIT) ? 16 : 8; }
+__host__ __device__ constexpr int conv_threads(int nsplit, int bn = 128) { return 64 + 32 * conv_epi_warps(nsplit, bn); }
+constexpr int kConvEpiWarpsMax = 16;
 // in-kernel operand production: items per thread and step / software pipelining of prep_range (the body runs ONCE per
 // launch on one warp per scheduler: a long unrolled body is bound by instruction fetch, `stall_no_inst` in ncu)
 #ifndef RLDM_OWN_U
@@ -167,9 +172,9 @@ __device__ __forceinline__ void issue_kstep(uint32_t d_tmem, uint32_t a_addr, ui
 // W-padded operand (halo columns included) the next convolution reads.  One prep launch and one kernel boundary less
 // per GroupNorm; the fp32 output (p.out) is still written when the residual stream needs it.
 template <int BLOCK_N, int STAGES, int TERMS, int NSPLIT>
-__global__ void __launch_bounds__(conv_threads(NSPLIT), 1)
+__global__ void __launch_bounds__(conv_threads(NSPLIT, BLOCK_N), 1)
 conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __grid_constant__ ConvFused fz) {
-  constexpr int kEpiWarps = conv_epi_warps(NSPLIT), kThreads = conv_threads(NSPLIT);
+  constexpr int kEpiWarps = conv_epi_warps(NSPLIT, BLOCK_N), kThreads = conv_threads(NSPLIT, BLOCK_N);
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   constexpr int XP = x_parts(TERMS), WP = w_parts(TERMS);
   constexpr int kStageBytes = XP * kABytes + WP * kBBytes;    // [X_hi][X_lo][W_hi][W_lo]
@@ -1255,7 +1260,7 @@ static int launch_conv_n(const ConvMaps& tm, const ConvParams& p, const ConvFuse
   dim3 grid((p.M_total + kBlockM - 1) / kBlockM, p.Cout / BLOCK_N, NSPLIT);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(conv_threads(NSPLIT));
+  cfg.blockDim = dim3(conv_threads(NSPLIT, BLOCK_N));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -1382,7 +1387,9 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
   const int n_sms = sw.n_sms;
   auto allowed = [&](int mode) { return mode == 1 || (mode == 2 && !residual); };      // 1: on, 2: "nores", 0: off
 
-  const int BN = (Cout % 128 == 0) ? 128 : 64;
+  int BN = (Cout % 128 == 0) ? 128 : 64;
+  // experiment (RLDM_SMALL_BN64=<max tiles>): 64-wide tiles for layers with at most that many 128 x 128 tiles
+  if (BN == 128 && sw.small_bn64 > 0 && ((B * (W / stride) * (H / stride) + kBlockM - 1) / kBlockM) * (Cout / 128) <= sw.small_bn64) BN = 64;
   // M tile = 128 output pixels = ncols whole columns x nb images
   const int pix = Wo * Ho;
   RLDM_CHECK(pix % 128 == 0 || 128 % pix == 0, "conv_tc: Wo*Ho=%d must divide or be a multiple of 128", pix);
