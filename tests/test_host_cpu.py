@@ -350,3 +350,22 @@ def test_documented_switches_exist_in_the_sources():
                 sources += open(os.path.join(d, f)).read()
     missing = sorted(s for s in documented if s not in sources)
     assert not missing, f"documented but not read anywhere: {missing}"
+
+
+def test_program_alloc_respects_the_op_that_writes_the_buffer(monkeypatch):
+    """An operand EMITTED by an already recorded op (rldm_conv_tc_emit) must not land in a buffer that op still reads:
+    `alloc(before_op=k)` only reuses buffers that were free before op k was appended."""
+    monkeypatch.setenv("RLDM_DRYRUN", "1")
+    from rangeldm_b200 import engine, _lib
+    pg = engine.Program(torch.device("cpu"))
+    a = pg.alloc((4, 8), torch.float16)                 # e.g. the operand conv k reads
+    early = pg.alloc((4, 8), torch.float16)
+    pg.free(early)                                      # free before op 0 exists
+    pg.add(_lib.OP_MEMSET, p=(a,), n=0)                 # op 0 reads / writes `a`
+    pg.free(a)                                          # ... and `a` is released right after it
+    b = pg.alloc((4, 8), torch.float16, before_op=0)    # written BY op 0: may take `early`, never `a`
+    assert b.data_ptr() == early.data_ptr() and b.data_ptr() != a.data_ptr()
+    c = pg.alloc((4, 8), torch.float16, before_op=0)    # nothing else qualifies: a fresh buffer
+    assert c.data_ptr() not in (a.data_ptr(), early.data_ptr())
+    d = pg.alloc((4, 8), torch.float16)                 # an ordinary allocation may reuse `a`
+    assert d.data_ptr() == a.data_ptr()
