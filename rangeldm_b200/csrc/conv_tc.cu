@@ -1388,8 +1388,11 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
   auto allowed = [&](int mode) { return mode == 1 || (mode == 2 && !residual); };      // 1: on, 2: "nores", 0: off
 
   int BN = (Cout % 128 == 0) ? 128 : 64;
-  // experiment (RLDM_SMALL_BN64=<max tiles>): 64-wide tiles for layers with at most that many 128 x 128 tiles
-  if (BN == 128 && sw.small_bn64 > 0 && ((B * (W / stride) * (H / stride) + kBlockM - 1) / kBlockM) * (Cout / 128) <= sw.small_bn64) BN = 64;
+  // 1x1 projections with at most RLDM_SMALL_BN64 (default 128) 128 x 128 tiles run 64-wide tiles: they have 2-4 K steps
+  // and no K split, so a CTA's time is its epilogue, and twice as many CTAs halve it (224.7 -> 226.4 images/s).  For the
+  // 3x3 layers (RLDM_SMALL_BN64_ALL=1) the extra CTAs per cluster reduction cost more than they save (214 images/s).
+  if (BN == 128 && sw.small_bn64 > 0 && (ks == 1 || sw.small_bn64_all) &&
+      ((B * (W / stride) * (H / stride) + kBlockM - 1) / kBlockM) * (Cout / 128) <= sw.small_bn64) BN = 64;
   // M tile = 128 output pixels = ncols whole columns x nb images
   const int pix = Wo * Ho;
   RLDM_CHECK(pix % 128 == 0 || 128 % pix == 0, "conv_tc: Wo*Ho=%d must divide or be a multiple of 128", pix);

@@ -34,7 +34,8 @@ static void load_env() {
   g_env.attn_mmasync = getenv("RLDM_ATTN_MMASYNC") != nullptr;
   g_env.attn_cudacore = getenv("RLDM_ATTN_CUDACORE") != nullptr;
   e = getenv("RLDM_SMALL_BN64");
-  g_env.small_bn64 = e ? atoi(e) : 0;
+  g_env.small_bn64 = e ? atoi(e) : 128;
+  g_env.small_bn64_all = getenv("RLDM_SMALL_BN64_ALL") != nullptr;
   e = getenv("RLDM_ATTN_POLY");
   g_env.attn_poly = e ? atoi(e) : 2;
   g_env.nco_pp1 = getenv("RLDM_NCO_PP1") != nullptr;
