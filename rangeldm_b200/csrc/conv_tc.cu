@@ -1391,8 +1391,11 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
   // 1x1 projections with at most RLDM_SMALL_BN64 (default 128) 128 x 128 tiles run 64-wide tiles: they have 2-4 K steps
   // and no K split, so a CTA's time is its epilogue, and twice as many CTAs halve it (224.7 -> 226.4 images/s).  For the
   // 3x3 layers (RLDM_SMALL_BN64_ALL=1) the extra CTAs per cluster reduction cost more than they save (214 images/s).
-  if (BN == 128 && sw.small_bn64 > 0 && (ks == 1 || sw.small_bn64_all) &&
-      ((B * (W / stride) * (H / stride) + kBlockM - 1) / kBlockM) * (Cout / 128) <= sw.small_bn64) BN = 64;
+  // (only while the 64-wide tiles still fit one wave of the small-layer kernel)
+  if (BN == 128 && sw.small_bn64 > 0 && (ks == 1 || sw.small_bn64_all)) {
+    const int tiles128 = ((B * (W / stride) * (H / stride) + kBlockM - 1) / kBlockM) * (Cout / 128);
+    if (tiles128 <= sw.small_bn64 && 2 * tiles128 <= n_sms) BN = 64;
+  }
   // M tile = 128 output pixels = ncols whole columns x nb images
   const int pix = Wo * Ho;
   RLDM_CHECK(pix % 128 == 0 || 128 % pix == 0, "conv_tc: Wo*Ho=%d must divide or be a multiple of 128", pix);
