@@ -137,6 +137,19 @@ def conv_flops(op):
     return 2.0 * B * (W // stride) * (H // stride) * Cout * (Cin * ks * ks + sc_cin)
 
 
+def up2_flops(op):
+    """rldm_conv_tc_up2 (nearest-2x upsampling folded into the convolution): the multiply-adds it EXECUTES -- four phases of
+    a 2x2 convolution over the low-resolution grid, 16/36 of the 3x3 convolution on the upsampled tensor it replaces."""
+    B, W, H, Cin, Cout = op.i[0], op.i[1], op.i[2], op.i[3], op.i[4]
+    return 2.0 * B * W * H * 16 * Cin * Cout
+
+
+def up2_bytes(op):
+    B, W, H, Cin, Cout, terms = op.i[0], op.i[1], op.i[2], op.i[3], op.i[4], op.i[6]
+    xp, wp = (2 if terms == 3 else 1), (2 if terms >= 2 else 1)
+    return float(xp * B * (W + 2) * H * Cin * 2 + wp * 16 * Cin * Cout * 2 + B * 4 * W * H * Cout * 4)
+
+
 def conv_bytes(op):
     """Algorithmic HBM bytes of one conv_tc launch: every operand plane, weight plane, residual and output element moves
     once (fp16 operand planes as the layer's precision says, fp32 output / residual)."""
@@ -180,7 +193,7 @@ def timed_profile(prog, reps=5):
 
 
 OP_NAMES = {1: "gn_stats", 2: "prep", 3: "conv_tc", 4: "conv_in", 5: "conv_out", 6: "attention", 7: "temb",
-            8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale", 12: "norm_conv_out", 13: "fused_levels"}
+            8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale", 12: "norm_conv_out", 13: "fused_levels", 14: "conv_tc"}
 
 
 def per_op_profile(sampler):
@@ -202,6 +215,12 @@ def per_op_profile(sampler):
                 hw_flops += weight * conv_flops(op) * op.i[12]       # MMAs actually issued: 1, 2 or 3 per algorithmic MAC
                 nbytes += weight * conv_bytes(op)
                 set_bytes += conv_bytes(op); set_n += 1
+            if op.kind == _lib.OP_CONV_UP2:       # four role-swapped conv launches: counted with the conv kernels
+                flops += weight * up2_flops(op)
+                hw_flops += weight * up2_flops(op) * op.i[6]
+                nbytes += weight * up2_bytes(op)
+                set_bytes += up2_bytes(op); set_n += 4
+                cnt[k] += 3 * weight            # four launches behind one op
             if op.kind == _lib.OP_FUSED:          # convolutions inside a fused run of small layers
                 fused_flops += weight * sum(conv_flops(o) for o in prog.ops[i:j] if o.kind == _lib.OP_CONV_TC)
     return ms, cnt, flops, fused_flops, hw_flops, nbytes, set_bytes / max(set_n, 1)

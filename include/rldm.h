@@ -165,6 +165,21 @@ int rldm_conv_tc_emit(const rldm_conv_emit* emit, const uint16_t* x, const uint1
 int rldm_conv_tc_emittable(int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo, int sc_cin,
                            int has_residual, int G);
 
+/* Upsample2D (`vae/sgm/modules/diffusionmodules/model.py:120-125`; diffusers Upsample2D): F.interpolate(nearest, 2x)
+ * followed by the 3x3 convolution, with the upsampling FOLDED into the convolution: every output pixel (2w+a, 2h+b)
+ * sees a 2x2 neighbourhood of the low-resolution input, so the layer is four 2x2 "phase" convolutions over the
+ * low-resolution operand (4/9 of the multiply-adds, a quarter of the operand bytes), each writing one pixel phase.
+ *   x, x_lo : (B, W+2, H, Cin) fp16 operand of the LOW-resolution tensor (rldm_prep with up = 1)
+ *   wgt     : [4 phases: 2a+b][planes][4 taps: 2*ti+tj][Cout][Cin] fp16; phase (a, b), tap (ti, tj) holds the sum of the
+ *             3x3 taps (kw, kh) that read the same input pixel: a=0: ti=0 <- kw 0, ti=1 <- kw 1+2; a=1: ti=0 <- kw 0+1,
+ *             ti=1 <- kw 2 (same for b, tj, kh)
+ *   out     : (B, 2W, 2H, Cout) fp32;  stats: optional channel-pair moments of the output (all four launches add to it)
+ * Only layers for which rldm_conv_tc_up2_ok() == 1 (role-swapped kernel: Cout % 128 == 0, whole 256-pixel units, more
+ * tiles than SMs). */
+int rldm_conv_tc_up2(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias, float* out,
+                     int B, int W, int H, int Cin, int Cout, int circular, double* stats, int terms, void* stream);
+int rldm_conv_tc_up2_ok(int B, int W, int H, int Cin, int Cout);
+
 /* CUDA-core restatement of rldm_conv_tc with the identical contract (split_k ignored); used by the
  * GPU tests to isolate tensor-core descriptor bugs from precision, never by the product path. */
 int rldm_conv_ref(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias, const float* temb,
@@ -238,7 +253,8 @@ enum {
   RLDM_OP_GN_STATS = 1, RLDM_OP_PREP = 2, RLDM_OP_CONV_TC = 3, RLDM_OP_CONV_IN = 4,
   RLDM_OP_CONV_OUT = 5, RLDM_OP_ATTENTION = 6, RLDM_OP_TEMB = 7, RLDM_OP_SCHED_STEP = 8,
   RLDM_OP_MEMSET = 9, RLDM_OP_CONV_REF = 10, RLDM_OP_AXPY = 11, RLDM_OP_NORM_CONV_OUT = 12,
-  RLDM_OP_FUSED = 13     /* p[0] = rldm_fused handle: a compiled run of small ops (below) */
+  RLDM_OP_FUSED = 13,    /* p[0] = rldm_fused handle: a compiled run of small ops (below) */
+  RLDM_OP_CONV_UP2 = 14  /* rldm_conv_tc_up2: p = x, x_lo, wgt, bias, out, stats; i = B, W, H, Cin, Cout, circular, terms */
 };
 typedef struct rldm_op {
   int32_t kind;

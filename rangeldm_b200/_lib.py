@@ -14,7 +14,7 @@ c_int, c_float, c_void_p, c_i64 = ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
 
 # kind codes of rldm_op (include/rldm.h)
 OP_GN_STATS, OP_PREP, OP_CONV_TC, OP_CONV_IN, OP_CONV_OUT, OP_ATTENTION, OP_TEMB, OP_SCHED_STEP, \
-    OP_MEMSET, OP_CONV_REF, OP_AXPY, OP_NORM_CONV_OUT, OP_FUSED = range(1, 14)
+    OP_MEMSET, OP_CONV_REF, OP_AXPY, OP_NORM_CONV_OUT, OP_FUSED, OP_CONV_UP2 = range(1, 15)
 
 
 class RldmOp(ctypes.Structure):
@@ -53,6 +53,8 @@ SIGNATURES = {
     "rldm_conv_tc_fused": (c_int, [c_void_p, c_void_p] + [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
                            + [c_int] * 10 + [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "rldm_conv_tc_fusable": (c_int, [c_int] * 10),
+    "rldm_conv_tc_up2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p, c_int, c_void_p]),
+    "rldm_conv_tc_up2_ok": (c_int, [c_int] * 5),
     "rldm_conv_tc_emit": (c_int, [c_void_p] + [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
                           + [c_int] * 10 + [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "rldm_conv_tc_emittable": (c_int, [c_int] * 11),

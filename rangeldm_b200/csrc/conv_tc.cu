@@ -53,6 +53,9 @@ struct ConvParams {
   int pix_per_img;  // Wo*Ho
   int Cout;
   int ks, stride, pad_lo, circular;
+  int pad_h;        // low-side pad along H (beams); == pad_lo except for the phase convolutions of a folded nearest-2x upsampling
+  int out_up;       // 1, or 2: the output pixel (w, h) is written to (2w + out_a, 2h + out_b) of a (B, 2Wo, 2Ho, Cout) tensor
+  int out_a, out_b; // (role-swapped kernel only)
   int total_iters;  // main_iters + shortcut chunks
   int main_iters;   // (Cin/64) * ks*ks: K steps of the convolution proper; the rest are the fused 1x1 shortcut's
   double* stats;    // optional GroupNorm moments of the output: [B][stats_G][2]
@@ -332,7 +335,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
       // ONE box per operand part: the activation tensor is W-padded (halo columns hold the circular wrap,
       // written by rldm_prep), H zero padding is TMA out-of-bounds fill, stride 2 is the map's element stride.
       // Shortcut K steps read the centre tap of the second tensor (1x1, stride 1, same grid as the output).
-      const int h_in = main ? tj - p.pad_lo : 0;
+      const int h_in = main ? tj - p.pad_h : 0;
       const int w_in = main ? p.stride * wo0 + ti - p.pad_lo + 1 : wo0 + 1;
       if (lane == (XP == 1 ? 0 : 1)) tma_load_4d(a_dst, main ? &tm.a : &tm.a2, &full_bar[s], chunk * kBlockK, h_in, w_in, b0);
       if (XP > 1 && lane == 2)
@@ -712,7 +715,7 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvMaps tm, const ConvParams 
         const int kc = chunk * kBlockK;                            // first channel of this stage
         const uint32_t a_dst = smem_u32(smem + s * kStageBytes);
         // shortcut K steps: centre tap of the second tensor (1x1, stride 1, same grid as the output)
-        const int h_in = main ? tj - p.pad_lo : 0;
+        const int h_in = main ? tj - p.pad_h : 0;
         const int w_off = main ? ti - p.pad_lo + 1 : 1;
         const int w_mul = main ? p.stride : 1;
         if (lane == 0) {
@@ -1087,7 +1090,7 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
         const int kc = chunk * kBlockK;
         const uint32_t dst = smem_u32(smem + s * kStageBytes);
         // shortcut K steps: centre tap of the second tensor (1x1, stride 1, same grid as the output)
-        const int h_in = main ? tj - p.pad_lo : 0;
+        const int h_in = main ? tj - p.pad_h : 0;
         const int w_off = main ? ti - p.pad_lo + 1 : 1;
         const int w_mul = main ? p.stride : 1;
         if (lane == 0) {
@@ -1163,6 +1166,11 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
       if (p.temb) add += __ldg(p.temb + static_cast<size_t>(bimg) * p.temb_stride + c);
       float* outp = p.out + static_cast<size_t>(m0) * p.Cout + c;
       const float* resp = p.residual ? p.residual + static_cast<size_t>(m0) * p.Cout + c : nullptr;
+      // folded nearest-2x upsampling (one of the four output phases): pixel pin = w*Ho + h of the image -> pixel
+      // (2w + a)*2Ho + 2h + b of an image four times as large (Ho is a power of two)
+      const int up_sh = 31 - __clz(p.Ho);
+      const int pin0 = m0 - bimg * p.pix_per_img;
+      float* outp_up = p.out + static_cast<size_t>(bimg) * 4 * p.pix_per_img * p.Cout + c;
       float rs[32];
       auto fetch_res = [&](int ch) {                            // 32 coalesced 128 B rows
 #pragma unroll
@@ -1190,9 +1198,19 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + add + (resp ? rs[j] : 0.f);
         if (resp && ch + 1 < ch0 + kChunksPerWarp) fetch_res(ch + 1);   // next chunk's residual rows fly under these stores
+        if (p.out_up == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) outp[static_cast<size_t>(ch * 32 + j) * p.Cout] = v[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int pin = pin0 + ch * 32 + j;
+            const int w = pin >> up_sh, h = pin & (p.Ho - 1);
+            outp_up[static_cast<size_t>(((2 * w + p.out_a) << (up_sh + 1)) + 2 * h + p.out_b) * p.Cout] = v[j];
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          outp[static_cast<size_t>(ch * 32 + j) * p.Cout] = v[j];
           s1 += v[j];
           s2 = fmaf(v[j], v[j], s2);
         }
@@ -1356,19 +1374,24 @@ using namespace rldm;
 // complete, [5] epilogue done.
 extern "C" void rldm_debug_conv_timestamps(long long* dev_buf) { g_conv_dbg = dev_buf; }
 
+// one output phase of a nearest-2x upsampling folded into the convolution (rldm_conv_tc_up2): a 2x2 convolution over the
+// LOW-resolution operand with pads (pad_lo along W, pad_h along H) in {0, 1}, written to the pixels (2w + a, 2h + b)
+struct ConvPhase { int pad_h, a, b; };
+
 static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias,
                         const float* temb, int temb_stride, const float* residual, float* out,
                         int B, int W, int H, int Cin, int Cout, int ks, int stride, int pad_lo,
                         int circular, int split_k, double* stats, const uint16_t* sc_x, const uint16_t* sc_x_lo,
                         const uint16_t* sc_wgt, int sc_cin, int terms, const rldm_conv_src* src, const rldm_conv_src* sc_src,
-                        bool query_only, void* stream, const rldm_conv_emit* emit = nullptr) {
+                        bool query_only, void* stream, const rldm_conv_emit* emit = nullptr, const ConvPhase* phase = nullptr) {
   // query_only: no launch; returns 0 when this layer would run on the small-layer kernel (the one that can produce its
   // own operand from `src` and emit the next GroupNorm's operand), 1 otherwise
   if (terms == 0) terms = x_lo ? 3 : 1;          // legacy entry points: the operand planes say it
   RLDM_CHECK(terms >= 1 && terms <= 3, "conv_tc: terms must be 1, 2 or 3 (got %d)", terms);
   RLDM_CHECK(terms != 3 || x_lo, "conv_tc: split-fp16 x3 needs the low-order activation plane");
   if (terms != 3) { x_lo = nullptr; sc_x_lo = nullptr; }
-  RLDM_CHECK(ks == 1 || ks == 3, "conv_tc: ks must be 1 or 3 (got %d)", ks);
+  RLDM_CHECK(ks == 1 || ks == 3 || (ks == 2 && phase), "conv_tc: ks must be 1 or 3 (got %d)", ks);
+  RLDM_CHECK(!phase || (stride == 1 && !residual && !sc_x && !src && !sc_src && !emit), "conv_tc: a phase convolution is a plain stride-1 layer");
   RLDM_CHECK(!sc_x || (sc_wgt && sc_cin > 0 && sc_cin % 64 == 0 && stride == 1 && (terms != 3 || sc_x_lo)),
              "conv_tc: fused shortcut needs weights, Cin2 %% 64 == 0 (got %d), stride 1 and the same operand precision",
              sc_cin);
@@ -1413,6 +1436,7 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
   p.pix_per_img = pix;
   p.Cout = Cout;
   p.ks = ks; p.stride = stride; p.pad_lo = pad_lo; p.circular = circular;
+  p.pad_h = phase ? phase->pad_h : pad_lo; p.out_up = phase ? 2 : 1; p.out_a = phase ? phase->a : 0; p.out_b = phase ? phase->b : 0;
   p.main_iters = (Cin / kBlockK) * ks * ks;
   p.total_iters = p.main_iters + (sc_x ? sc_cin / kBlockK : 0);
   p.units = 0; p.a_part_bytes = 0; p.nb_stages = 0;
@@ -1550,6 +1574,7 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
       const int units_wt = (p.M_total / 256) * (Cout / 128);
       RLDM_BY_TERMS(terms, return launch_conv_wt<T_>(tm, p, units_wt < n_sms ? units_wt : n_sms, st));
     }
+    RLDM_CHECK(!phase, "conv_tc: phase convolutions run on the role-swapped kernel only (rldm_conv_tc_up2_ok)");
     // two M tiles per unit share the weight tiles when the tile count allows it (measured: -5..-20 % on layers without
     // a residual operand and on 64-channel layers; 128-wide layers WITH a residual are paced by the drain of two
     // tiles, not the K loop: they keep one tile per unit)
@@ -1566,6 +1591,7 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
     RLDM_BY_TERMS(terms, return (launch_conv_persistent<64, T_, 1>(tm, p, ctas, st)));
   }
   if (query_only) return (Cin <= 512 && sc_cin <= 512) ? 0 : 1;
+  RLDM_CHECK(!phase, "conv_tc: phase convolutions run on the role-swapped kernel only (rldm_conv_tc_up2_ok)");
   ConvFused fz;
   memset(&fz, 0, sizeof(fz));
   auto fill = [&](PrepArgs& a, const rldm_conv_src* s, const uint16_t* o_hi, const uint16_t* o_lo, int C, int Wop, int Hop) -> int {
@@ -1630,6 +1656,31 @@ extern "C" int rldm_conv_tc_fused(const rldm_conv_src* src, const rldm_conv_src*
                                   const uint16_t* sc_x_lo, const uint16_t* sc_wgt, int sc_cin, int terms, void* stream) {
   return conv_tc_impl(x, x_lo, wgt, bias, temb, temb_stride, residual, out, B, W, H, Cin, Cout, ks, stride, pad_lo,
                       circular, split_k, stats, sc_x, sc_x_lo, sc_wgt, sc_cin, terms, src, sc_src, false, stream);
+}
+
+extern "C" int rldm_conv_tc_up2_ok(int B, int W, int H, int Cin, int Cout) {
+  const EnvSwitches& sw = env();
+  const int pix = W * H;
+  if (Cin % 64 != 0 || Cout % 128 != 0 || pix % 256 != 0 || (H & (H - 1)) != 0 || H > 128) return 0;
+  if (!(sw.conv_wt == 1 || sw.conv_wt == 2) || !sw.conv_persistent) return 0;
+  return (B * pix / kBlockM) * (Cout / 128) > sw.n_sms ? 1 : 0;
+}
+
+extern "C" int rldm_conv_tc_up2(const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt, const float* bias, float* out,
+                                int B, int W, int H, int Cin, int Cout, int circular, double* stats, int terms, void* stream) {
+  RLDM_CHECK(rldm_conv_tc_up2_ok(B, W, H, Cin, Cout), "conv_tc_up2: layer B=%d %dx%d %d->%d does not run on the role-swapped kernel",
+             B, W, H, Cin, Cout);
+  if (terms == 0) terms = x_lo ? 3 : 1;
+  const size_t phase_elems = static_cast<size_t>(terms >= 2 ? 2 : 1) * 4 * Cout * Cin;
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      const ConvPhase ph{1 - b, a, b};
+      if (int rc = conv_tc_impl(x, x_lo, wgt + (2 * a + b) * phase_elems, bias, nullptr, 0, nullptr, out, B, W, H, Cin, Cout, 2, 1,
+                                1 - a, circular, 1, stats, nullptr, nullptr, nullptr, 0, terms, nullptr, nullptr, false, stream,
+                                nullptr, &ph))
+        return rc;
+    }
+  return 0;
 }
 
 extern "C" int rldm_conv_tc_emit(const rldm_conv_emit* emit, const uint16_t* x, const uint16_t* x_lo, const uint16_t* wgt,

@@ -1420,6 +1420,10 @@ static int run_ops(const rldm_op* ops, int n_ops, unsigned long long* stamps, vo
                              o.i[10], (double*)o.p[7], (const uint16_t*)o.p[8], (const uint16_t*)o.p[9],
                              (const uint16_t*)o.p[10], o.i[11], o.i[12], stream);
         break;
+      case RLDM_OP_CONV_UP2:
+        rc = rldm_conv_tc_up2((const uint16_t*)o.p[0], (const uint16_t*)o.p[1], (const uint16_t*)o.p[2], (const float*)o.p[3],
+                              (float*)o.p[4], o.i[0], o.i[1], o.i[2], o.i[3], o.i[4], o.i[5], (double*)o.p[5], o.i[6], stream);
+        break;
       case RLDM_OP_CONV_REF:
         rc = rldm_conv_ref((const uint16_t*)o.p[0], (const uint16_t*)o.p[6], (const uint16_t*)o.p[1], (const float*)o.p[2],
                            (const float*)o.p[3], o.i[0], (const float*)o.p[4], (float*)o.p[5], o.i[1],

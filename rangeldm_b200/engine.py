@@ -82,6 +82,10 @@ FUSE_PREP = os.environ.get("RLDM_FUSE_PREP", "0") == "1"
 # at ~4 cycles per instruction (one warp per scheduler), 9.5 k cycles for the 32 rows a thread owns when K is not split,
 # and clusters of 8 CTAs that must cover an image (levels 1-2) are scheduled later than the 2-4 CTA clusters they replace.
 EMIT_PREP = os.environ.get("RLDM_EMIT_PREP", "0") == "1"
+# Upsample2D of the layers the role-swapped kernel takes (the VAE decoder's): the nearest-2x upsampling is folded into
+# the convolution as four 2x2 phase convolutions over the low-resolution operand (RLDM_FOLD_UPSAMPLE=0: upsample in the
+# prep pass, then the 3x3 convolution on four times the pixels).
+FOLD_UPSAMPLE = os.environ.get("RLDM_FOLD_UPSAMPLE", "1") != "0"
 # RLDM_FUSE_LEVELS=1 (experiment, default off): runs of small consecutive ops (UNet levels 1..n) compiled into ONE
 # persistent launch each (csrc/fused_levels.cu).  Correct (tests/test_fused_gpu.py) but measured SLOWER on B200: a
 # grid-wide barrier costs 2.0-2.3 us against ~3 us for a PDL kernel boundary, and every convolution needs two of them
@@ -592,9 +596,54 @@ class Builder:
             self.pg.free(x.t)
         return out
 
+    def pack_conv_up2(self, conv, terms):
+        """3x3 weights of a convolution that follows a nearest-2x upsampling, combined per OUTPUT PHASE (a, b) into the 2x2
+        convolution the low-resolution input sees (rldm_conv_tc_up2): [4 phases][planes][4 taps][Cout][Cin] fp16."""
+        def make():
+            w = conv.weight.detach().to(self.pg.device, torch.float32)       # (Cout, Cin, kW, kH)
+            # along one axis: phase 0 reads (i-1, i) with weights (k0, k1 + k2); phase 1 reads (i, i+1) with (k0 + k1, k2)
+            comb = [((0,), (1, 2)), ((0, 1), (2,))]
+            phases = []
+            for a in range(2):
+                for b in range(2):
+                    taps = []
+                    for ti in range(2):
+                        for tj in range(2):
+                            acc = 0
+                            for kw in comb[a][ti]:
+                                for kh in comb[b][tj]:
+                                    acc = acc + w[:, :, kw, kh]
+                            taps.append(acc)
+                    wt = torch.stack(taps, 0)                                   # [4 taps][Cout][Cin]
+                    hi = wt.to(torch.float16)
+                    phases.append(hi if terms < 2 else torch.cat([hi, (wt - hi.float()).to(torch.float16)], 0))
+            return self.pg.hold(torch.stack(phases, 0).contiguous())
+        wt = self._cached(("conv_up2", id(conv.weight), min(terms, 2)), make)
+        b = self.f32(conv.bias) if conv.bias is not None else None
+        return wt, b
+
     def upsample(self, us, x):
-        """Upsample2D (`model.py:120-125`): nearest 2x folded into the cast, then 3x3 conv."""
+        """Upsample2D (`model.py:120-125`): nearest 2x folded into the cast, then 3x3 conv -- or, for the layers the
+        role-swapped kernel takes (the decoder's), folded into the convolution itself: four 2x2 phase convolutions over
+        the low-resolution operand (rldm_conv_tc_up2; 4/9 of the multiply-adds, a quarter of the operand bytes)."""
         t = self.terms(x.W * 2)
+        conv = us.conv
+        if (FOLD_UPSAMPLE and CONV_KIND == _lib.OP_CONV_TC and conv.kernel_size == (3, 3) and conv.stride == (1, 1)
+                and conv.padding == (1, 1) and conv.padding_mode == "zeros" and conv.groups == 1
+                and _lib.lib().rldm_conv_tc_up2_ok(self.B, x.W, x.H, conv.in_channels, conv.out_channels)):
+            circ = bool(getattr(conv, "circular", False))
+            xr = self.prep(x, None, None, up=1, circular=circ, terms=t)
+            wt, bias = self.pack_conv_up2(conv, t)
+            cout = conv.out_channels
+            out = self.pg.alloc((self.B, x.W * 2, x.H * 2, cout))
+            st = self.stats_slot(cout // 2) if FUSE_STATS else None
+            self.pg.add(_lib.OP_CONV_UP2, i=(self.B, x.W, x.H, conv.in_channels, cout, int(circ), t),
+                        p=(xr[0], xr[1], wt, bias, out, st), launches=4)
+            self.free_half(xr)
+            act = Act(out, self.B, x.W * 2, x.H * 2, cout, st)
+            self.pg.taps.append((us, act))
+            self.pg.free(x.t)
+            return act
         xr = self.prep(x, None, None, up=2, circular=bool(getattr(us.conv, "circular", False)), terms=t, defer=True)
         out = self.conv(xr, x.W * 2, x.H * 2, us.conv, stats=True, terms=t)
         self.free_half(xr)

@@ -9,7 +9,8 @@ import bench
 from rangeldm_b200 import _lib
 
 NAMES = {1: "gn_stats", 2: "prep", 3: "conv_tc", 4: "conv_in", 5: "conv_out", 6: "attention", 7: "temb",
-         8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale", 12: "norm_conv_out", 13: "fused_levels"}
+         8: "sched_step", 9: "memset", 10: "conv_ref", 11: "scale", 12: "norm_conv_out", 13: "fused_levels",
+         14: "conv_up2"}
 
 
 def describe(op):
@@ -20,6 +21,8 @@ def describe(op):
         return f"prep {i[6]}x{i[7]} C{i[0]}+{i[1]} up{i[4]}" + (" +raw" if op.p[7] else "")
     if op.kind == 6:
         return f"attention N{i[1]} C{i[2]}"
+    if op.kind == 14:
+        return f"conv_up2 B{i[0]} {i[1]}x{i[2]} -> {2 * i[1]}x{2 * i[2]} {i[3]}->{i[4]} (4 phase launches)"
     if op.kind == 13:
         return f"fused run of {op.n} ops"
     return NAMES.get(op.kind, str(op.kind))

@@ -373,3 +373,46 @@ def test_unet_with_emitting_convolutions_matches_oracle(monkeypatch):
     plan = u.plan(3, 256, 16, 1)
     assert sum(1 for op in plan.prog.ops if op.kind == R._lib.OP_CONV_TC and op.p[19]) == 40
     assert relerr(y.cpu(), ref, "unet_c3_emit_prep") < 5e-4
+
+
+# ---- nearest-2x upsampling folded into the convolution (rldm_conv_tc_up2) ----------------------------------------------
+@pytest.mark.parametrize("terms", [3, 1])
+@pytest.mark.parametrize("shape", [(8, 256, 16, 256, 256), (3, 512, 32, 128, 128)], ids=lambda s: "x".join(map(str, s)))
+def test_upsample_folded_into_the_convolution(shape, terms, monkeypatch):
+    """Upsample2D of the decoder: four 2x2 phase convolutions over the low-resolution operand against nearest-2x in the
+    prep pass + the 3x3 convolution, and against the fp32 PyTorch reference (circular along W, zero pad along H)."""
+    import rangeldm_b200 as R
+    from rangeldm_b200 import engine, models
+    B, W, H, Cin, Cout = shape
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(31 + W)
+    us = models.Upsample2D(Cin, use_conv=True, out_channels=Cout).to(dev)
+    us.conv.circular = True
+    with torch.no_grad():
+        us.conv.weight.copy_(torch.randn(us.conv.weight.shape, generator=g) / (9 * Cin) ** 0.5)
+        us.conv.bias.copy_(torch.randn(Cout, generator=g))
+    x0 = torch.randn(B, W, H, Cin, generator=g).to(dev)
+    outs = []
+    for fold in (True, False):
+        monkeypatch.setattr(engine, "FOLD_UPSAMPLE", fold)
+        pg = engine.Program(dev)
+        bd = engine.Builder(pg, B, cache={}, terms_of=lambda w: terms)
+        a0 = engine.Act(pg.hold(x0.clone()), B, W, H, Cin)
+        out = bd.upsample(us, a0)
+        bd.finish(); pg.finalize()
+        kinds = [o.kind for o in pg.ops]
+        assert kinds.count(R._lib.OP_CONV_UP2) == (1 if fold else 0) and kinds.count(R._lib.OP_CONV_TC) == (0 if fold else 1)
+        for _ in range(2):
+            pg.run()
+        torch.cuda.synchronize()
+        outs.append((out.t.clone(), out.stats.clone()))
+    (fa, fs), (ua, us_) = outs
+    assert fa.shape == (B, 2 * W, 2 * H, Cout)
+    tol = 1e-5 if terms == 3 else 2e-3       # (the combined phase weights are rounded once more than the 3x3 taps)
+    assert relerr(fa, ua, f"upsample_folded_vs_prep_terms{terms}") < tol
+    assert torch.allclose(fs, us_, rtol=1e-5 if terms == 3 else 1e-2, atol=1e-1)
+    from oracle.nets import circ_conv2d
+    xr = torch.nn.functional.interpolate(x0.permute(0, 3, 1, 2).cpu(), scale_factor=2.0, mode="nearest")
+    with torch.no_grad():
+        ref = circ_conv2d(xr, us.conv.weight.cpu(), us.conv.bias.cpu(), 1, 1)
+    assert relerr(fa.permute(0, 3, 1, 2).cpu(), ref, f"upsample_folded_vs_torch_terms{terms}") < (1e-5 if terms == 3 else 2e-3)
