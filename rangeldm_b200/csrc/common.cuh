@@ -50,6 +50,7 @@ struct EnvSwitches {
   bool conv_mt1;            // RLDM_CONV_MT1:     pixel-M persistent kernel with one tile per unit
   bool conv_mt2_res;        // RLDM_CONV_MT2_RES: two tiles per unit also for 128-wide layers with a residual
   bool wt_pdl;              // RLDM_WT_PDL != 0:  PDL on single-wave role-swapped launches (default on)
+  bool wt_pdl_all;          // RLDM_WT_PDL = 2: ... on every role-swapped / persistent convolution launch (experiment)
   int small_bn64;           // RLDM_SMALL_BN64: 64-wide tiles for 1x1 conv layers with at most this many 128x128 tiles (default 128)
   bool small_bn64_all;      // RLDM_SMALL_BN64_ALL: ... for the 3x3 layers as well (experiment)
   int attn_poly;            // RLDM_ATTN_POLY: exponential pairs of every 8 on the FMA pipe (tcgen05 attention, fp16 P), 0..4

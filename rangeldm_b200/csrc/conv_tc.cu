@@ -1323,7 +1323,8 @@ static int launch_conv_persistent(const ConvMaps& tm, const ConvParams& p, int n
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  RLDM_CUDA(launch_pdl(conv_tc_persistent_kernel<BLOCK_N, STAGES, TERMS, MT>, dim3(n_ctas), dim3(192), smem, st, tm, p));
+  if (env().wt_pdl_all) RLDM_CUDA(launch_pdl_small(conv_tc_persistent_kernel<BLOCK_N, STAGES, TERMS, MT>, dim3(n_ctas), dim3(192), smem, st, tm, p));
+  else RLDM_CUDA(launch_pdl(conv_tc_persistent_kernel<BLOCK_N, STAGES, TERMS, MT>, dim3(n_ctas), dim3(192), smem, st, tm, p));
   return 0;
 }
 
@@ -1336,7 +1337,8 @@ static int launch_conv_wt(const ConvMaps& tm, const ConvParams& p, int n_ctas, c
     RLDM_CUDA(cudaFuncSetAttribute(conv_tc_wt_kernel<TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  RLDM_CUDA(launch_pdl(conv_tc_wt_kernel<TERMS>, dim3(n_ctas), dim3(kWtThreads), smem, st, tm, p));
+  if (env().wt_pdl_all) RLDM_CUDA(launch_pdl_small(conv_tc_wt_kernel<TERMS>, dim3(n_ctas), dim3(kWtThreads), smem, st, tm, p));
+  else RLDM_CUDA(launch_pdl(conv_tc_wt_kernel<TERMS>, dim3(n_ctas), dim3(kWtThreads), smem, st, tm, p));
   return 0;
 }
 
@@ -1351,7 +1353,7 @@ static int launch_conv_wt_halo(const ConvMaps& tm, const ConvParams& p, int n_ct
   // single-wave launches (one unit per CTA: the top-level UNet layers) may start under the tail of the producing
   // pass: setup, TMEM allocation and descriptor prefetch overlap it (RLDM_WT_PDL=0 switches it off).
   const int units = (p.M_total / 256) * (p.Cout / 128);
-  if (env().wt_pdl && units <= n_ctas)
+  if (env().wt_pdl && (units <= n_ctas || env().wt_pdl_all))
     RLDM_CUDA(launch_pdl_small(conv_tc_wt_kernel<TERMS, true>, dim3(n_ctas), dim3(kWtThreads), smem, st, tm, p));
   else
     RLDM_CUDA(launch_pdl(conv_tc_wt_kernel<TERMS, true>, dim3(n_ctas), dim3(kWtThreads), smem, st, tm, p));

@@ -23,7 +23,9 @@ static void load_env() {
   const char* e = getenv("RLDM_PDL");
   g_env.pdl = e ? atoi(e) : 2;
   e = getenv("RLDM_PREP_PDL_MAX");
-  g_env.prep_pdl_max = e ? static_cast<size_t>(atoll(e)) : static_cast<size_t>(20000000);   // UNet forward 1988 -> 1965 us vs 2^21
+  // every prep pass carries the attribute (round 2, plain-fp16 UNet: 228.4 -> 229.7 images/s against the round-1 cut-off of
+  // 2e7 elements, which kept it off the decoder's full-resolution passes)
+  g_env.prep_pdl_max = e ? static_cast<size_t>(atoll(e)) : static_cast<size_t>(-1);
   g_env.conv_wt = tri("RLDM_CONV_WT");
   g_env.conv_wt_halo = tri("RLDM_CONV_WT_HALO");
   g_env.conv_persistent = getenv("RLDM_NO_PERSISTENT") == nullptr;
@@ -31,6 +33,7 @@ static void load_env() {
   g_env.conv_mt2_res = getenv("RLDM_CONV_MT2_RES") != nullptr;
   e = getenv("RLDM_WT_PDL");
   g_env.wt_pdl = e ? atoi(e) != 0 : true;
+  g_env.wt_pdl_all = e ? atoi(e) == 2 : false;
   g_env.attn_mmasync = getenv("RLDM_ATTN_MMASYNC") != nullptr;
   g_env.attn_cudacore = getenv("RLDM_ATTN_CUDACORE") != nullptr;
   e = getenv("RLDM_SMALL_BN64");
