@@ -553,7 +553,7 @@ int rldm_attention_umma(const float* qkv, uint16_t* out, uint16_t* out_lo, int B
   }
   const int poly = env().attn_poly;
   const Kern kern = out_lo ? kerns[0] : kerns[1 + (poly < 0 || poly > 4 ? 2 : poly)];
-  RLDM_CUDA(launch_pdl(kern, dim3(ctas_p), dim3(kApThreads), smem_p, as_stream(stream), qkv,
+  RLDM_CUDA(launch_pdl_cls(1, kern, dim3(ctas_p), dim3(kApThreads), smem_p, as_stream(stream), qkv,
                        reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H, B));
   RLDM_LAUNCH_CHECK();
   return 0;

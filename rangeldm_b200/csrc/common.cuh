@@ -50,6 +50,7 @@ struct EnvSwitches {
   bool conv_mt1;            // RLDM_CONV_MT1:     pixel-M persistent kernel with one tile per unit
   bool conv_mt2_res;        // RLDM_CONV_MT2_RES: two tiles per unit also for 128-wide layers with a residual
   bool wt_pdl;              // RLDM_WT_PDL != 0:  PDL on single-wave role-swapped launches (default on)
+  int pdl_extra;            // RLDM_PDL_EXTRA: bit mask of launch classes that also carry the PDL attribute in mode 2
   bool wt_pdl_all;          // RLDM_WT_PDL = 2: ... on every role-swapped / persistent convolution launch (experiment)
   int small_bn64;           // RLDM_SMALL_BN64: 64-wide tiles for 1x1 conv layers with at most this many 128x128 tiles (default 128)
   bool small_bn64_all;      // RLDM_SMALL_BN64_ALL: ... for the 3x3 layers as well (experiment)
@@ -77,6 +78,24 @@ static inline cudaError_t launch_pdl_small(void (*kernel)(KArgs...), dim3 grid, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled_small() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// launches of class `cls` (bit of RLDM_PDL_EXTRA: 1 tcgen05 attention, 2 short attention, 4 conv_in / conv_out, 8 scheduler
+// step / scale / fill / time embedding) carry the attribute in mode 2 when their bit is set
+bool pdl_enabled_class(int cls);
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_cls(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                         cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled_class(cls) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 template <typename... KArgs, typename... Args>

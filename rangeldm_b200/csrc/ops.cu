@@ -34,6 +34,8 @@ static void load_env() {
   e = getenv("RLDM_WT_PDL");
   g_env.wt_pdl = e ? atoi(e) != 0 : true;
   g_env.wt_pdl_all = e ? atoi(e) == 2 : false;
+  e = getenv("RLDM_PDL_EXTRA");
+  g_env.pdl_extra = e ? atoi(e) : 0;
   g_env.attn_mmasync = getenv("RLDM_ATTN_MMASYNC") != nullptr;
   g_env.attn_cudacore = getenv("RLDM_ATTN_CUDACORE") != nullptr;
   e = getenv("RLDM_SMALL_BN64");
@@ -59,6 +61,7 @@ const EnvSwitches& env() {
 // resources for the whole primary.  Mode 2 therefore marks only the latency-bound launches; 1 marks all.
 bool pdl_enabled() { return env().pdl == 1; }
 bool pdl_enabled_small() { return env().pdl == 1 || env().pdl == 2; }
+bool pdl_enabled_class(int cls) { return env().pdl == 1 || (env().pdl == 2 && (env().pdl_extra & cls) != 0); }
 
 // ------------------------------------------------------------------------------------------------
 // GroupNorm statistics.  grid (chunks, B), block 256.  Thread = one float4 of channels, striding
@@ -798,7 +801,7 @@ int zero_fill(void* p, size_t bytes, cudaStream_t st) {
   unsigned grid = static_cast<unsigned>((n16 + 255) / 256);
   if (grid > 1184) grid = 1184;
   if (grid == 0) return 0;
-  RLDM_CUDA(launch_pdl(zero_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<uint4*>(p), n16));
+  RLDM_CUDA(launch_pdl_cls(8, zero_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<uint4*>(p), n16));
   return 0;
 }
 
@@ -922,7 +925,7 @@ static int conv_in_impl(const float* x0, int c0, const float* x1, int c1, const 
   if (blocks > n_chunks) blocks = n_chunks;
   const int cpb = (n_chunks + blocks - 1) / blocks;
   blocks = (n_chunks + cpb - 1) / cpb;
-  RLDM_CUDA(launch_pdl(conv_in_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), smem, as_stream(stream), x0, c0, x1, c1,
+  RLDM_CUDA(launch_pdl_cls(4, conv_in_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), smem, as_stream(stream), x0, c0, x1, c1,
                        wgt, bias, out, B, W, H, Cout, circular, stats, cpb));
   RLDM_LAUNCH_CHECK();
   return 0;
@@ -953,8 +956,8 @@ extern "C" int rldm_conv_out(const uint16_t* x, const uint16_t* x_lo, const floa
   const size_t groups = (total_pix * (wide ? 8 : 1) + 255) / 256;
   const unsigned grid = static_cast<unsigned>(groups < 1184 ? groups : 1184);
 #define RLDM_CO(N)                                                                                              \
-  if (wide) RLDM_CUDA(launch_pdl(conv_out_kernel<N, 8>, dim3(grid), dim3(256), smem, st, xh, xl, wgt, bias, out, B, W, H, Cin, circular)); \
-  else RLDM_CUDA(launch_pdl(conv_out_kernel<N, 1>, dim3(grid), dim3(256), smem, st, xh, xl, wgt, bias, out, B, W, H, Cin, circular));
+  if (wide) RLDM_CUDA(launch_pdl_cls(4, conv_out_kernel<N, 8>, dim3(grid), dim3(256), smem, st, xh, xl, wgt, bias, out, B, W, H, Cin, circular)); \
+  else RLDM_CUDA(launch_pdl_cls(4, conv_out_kernel<N, 1>, dim3(grid), dim3(256), smem, st, xh, xl, wgt, bias, out, B, W, H, Cin, circular));
   switch (Cout) {
     case 2: RLDM_CO(2) break;
     case 4: RLDM_CO(4) break;
@@ -995,7 +998,7 @@ extern "C" int rldm_norm_conv_out(const float* x, const double* sums, const doub
       RLDM_CUDA(cudaFuncSetAttribute(norm_conv_out_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
       smem_set = 220 * 1024;                                                                                          \
     }                                                                                                                 \
-    RLDM_CUDA(launch_pdl(norm_conv_out_kernel<N>, grid, dim3(256), smem, st, x, sums, pairs, gamma, beta, eps, G, silu, wgt, \
+    RLDM_CUDA(launch_pdl_cls(4, norm_conv_out_kernel<N>, grid, dim3(256), smem, st, x, sums, pairs, gamma, beta, eps, G, silu, wgt, \
                          bias, out, W, H, Cin, circular, TW, LPP, PP));                                               \
   }
   switch (Cout) {
@@ -1019,7 +1022,7 @@ extern "C" int rldm_attention(const float* qkv, uint16_t* out, uint16_t* out_lo,
     if (rc >= 0) return rc;
   }
   if (N % 64 == 0 && !env().attn_cudacore) {   // tensor-path kernel; the CUDA-core kernel covers ragged N
-    RLDM_CUDA(launch_pdl(attention_tc_kernel, dim3(N / 64, C / 8, B), dim3(128), 0, as_stream(stream), qkv, reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H));
+    RLDM_CUDA(launch_pdl_cls(2, attention_tc_kernel, dim3(N / 64, C / 8, B), dim3(128), 0, as_stream(stream), qkv, reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), N, C, H));
     RLDM_LAUNCH_CHECK();
     return 0;
   }
@@ -1038,7 +1041,7 @@ static int temb_linear(const float* in, const float* t, const float* w, const fl
     RLDM_CUDA(cudaFuncSetAttribute(temb_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     smem_set = 64 * 1024;
   }
-  RLDM_CUDA(launch_pdl(temb_linear_kernel, dim3((N + 7) / 8), dim3(256), smem, st, in, t, w, b, out, R, K, N, silu_out));
+  RLDM_CUDA(launch_pdl_cls(8, temb_linear_kernel, dim3((N + 7) / 8), dim3(256), smem, st, in, t, w, b, out, R, K, N, silu_out));
   return 0;
 }
 
@@ -1062,13 +1065,13 @@ extern "C" int rldm_sched_step(const float* k, const float* x, const float* eps,
                                const float* x0_prev, const float* noise, float* x_out,
                                float* x0_out, int64_t n, void* stream) {
   const int64_t nthreads = (n + 3) / 4;
-  RLDM_CUDA(launch_pdl(sched_step_kernel, dim3(static_cast<unsigned>((nthreads + 255) / 256)), dim3(256), 0, as_stream(stream), k, x, eps, x0_prev, noise, x_out, x0_out, n));
+  RLDM_CUDA(launch_pdl_cls(8, sched_step_kernel, dim3(static_cast<unsigned>((nthreads + 255) / 256)), dim3(256), 0, as_stream(stream), k, x, eps, x0_prev, noise, x_out, x0_out, n));
   RLDM_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int rldm_scale(const float* x, float a, float* y, int64_t n, void* stream) {
-  RLDM_CUDA(launch_pdl(scale_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, as_stream(stream), x, a, y, n));
+  RLDM_CUDA(launch_pdl_cls(8, scale_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, as_stream(stream), x, a, y, n));
   RLDM_LAUNCH_CHECK();
   return 0;
 }
