@@ -121,7 +121,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 // x * sigmoid(x) with MUFU.EX2 + MUFU.RCP (~2 ulp): the IEEE division `x / (1 + e^-x)` costs ~20 instructions per
 // element (FCHK + refinement + slow-path branch) and made the GroupNorm-apply passes issue-bound.
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// The .ftz forms drop the denormal guards nvcc wraps around ex2.approx / the division (two FSETP + FMUL pairs per value).
+__device__ __forceinline__ float silu_f(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // Experiment switches (compile time): where a kernel fires launch_dependents.
