@@ -366,10 +366,20 @@ class _RangePipeline(DiffusionPipeline):
                 f" size of {batch_size}. Make sure the batch size matches the length of the generators.")
 
     def _set_steps(self, n, eta=0.0):
-        if isinstance(self.scheduler, DDIMScheduler):
-            self.scheduler.set_timesteps(n, eta=eta)
+        """`scheduler.set_timesteps(n)` as the reference loop does on every call (`ldm/pipelines.py:97,230,343,484`).  For
+        the native schedulers a repeated call with the same arguments only resets the multistep state: the tables (and
+        their device copy) are the ones of the previous call.  Any direct `set_timesteps` by the user re-installs them."""
+        sch = self.scheduler
+        key = (int(n), float(eta) if isinstance(sch, DDIMScheduler) else 0.0)
+        if _is_native_scheduler(sch) and getattr(sch, "_steps_key", None) == key:
+            sch._state = {}
+            return
+        if isinstance(sch, DDIMScheduler):
+            sch.set_timesteps(n, eta=eta)
         else:
-            self.scheduler.set_timesteps(n)
+            sch.set_timesteps(n)
+        if _is_native_scheduler(sch):
+            sch._steps_key = key
 
 
 class DDPMPipelineRange(_RangePipeline):

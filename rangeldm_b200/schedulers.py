@@ -79,6 +79,7 @@ class _SchedulerBase(ConfigMixin):
         self._coef_host = torch.tensor(np.asarray(coefs, dtype=np.float64), dtype=torch.float32)
         self._coef_dev = None
         self._state = {}
+        self._steps_key = None          # set by the pipelines after THEIR set_timesteps call (see _RangePipeline._set_steps)
 
     def coef_table(self, device):
         """(steps, 8) fp32 coefficient table on `device` (7 used, padded to 8 for 32 B rows)."""

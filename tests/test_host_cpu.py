@@ -369,3 +369,30 @@ def test_program_alloc_respects_the_op_that_writes_the_buffer(monkeypatch):
     assert c.data_ptr() not in (a.data_ptr(), early.data_ptr())
     d = pg.alloc((4, 8), torch.float16)                 # an ordinary allocation may reuse `a`
     assert d.data_ptr() == a.data_ptr()
+
+
+def test_pipeline_set_steps_reuses_tables_only_for_identical_arguments():
+    """`_RangePipeline._set_steps`: the second call with the same step count keeps the installed tables (and resets the
+    multistep state); another step count, another eta, or a direct `scheduler.set_timesteps` re-installs them."""
+    import rangeldm_b200 as R
+    from rangeldm_b200.pipelines import _RangePipeline
+    p = _RangePipeline.__new__(_RangePipeline)
+    sch = R.DPMSolverMultistepScheduler(timestep_spacing="leading")
+    p.scheduler = sch
+    p._set_steps(20)
+    t20 = sch.timesteps
+    sch._state["x0_prev"] = object()
+    p._set_steps(20)
+    assert sch.timesteps is t20 and sch._state == {}
+    p._set_steps(10)
+    assert sch.timesteps is not t20 and len(sch.timesteps) == 10
+    sch.set_timesteps(20)                       # direct call by the user: the pipeline must not trust its key afterwards
+    t20b = sch.timesteps
+    p._set_steps(10)
+    assert len(sch.timesteps) == 10 and sch.timesteps is not t20b
+    d = R.DDIMScheduler(clip_sample=False)
+    p.scheduler = d
+    p._set_steps(10, eta=0.0)
+    c0 = d._coef_host
+    p._set_steps(10, eta=0.5)
+    assert d._coef_host is not c0 and float(d._coef_host[:, 6].abs().max()) > 0
