@@ -520,51 +520,64 @@ conv_tc_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p, const __
   const bool clustered = NSPLIT > 1 || p.clm > 1;
   if (p.emit_out) {
     // ---- EMIT: (image, group) moments complete inside the cluster -> normalise own rows -> fp16 operand ----
-    // published per epilogue warp: [kEpiWarps][32] (sum, sum of squares) of the warp's rows per group of the tile
-    float2* pub = reinterpret_cast<float2*>(fused_tab);
+    // per epilogue warp: [kEpiWarps][32] (sum, sum of squares) of the warp's rows per group of the tile; then folded
+    // inside the CTA into [2 image slots][32] (a CTA's rows touch at most two images: slot = image - image of its first
+    // row), which is what the other CTAs of the cluster read: ONE DSMEM round trip of <= 8 loads per thread
+    float2* pub = reinterpret_cast<float2*>(fused_tab);                   // [kEpiWarps][32]
+    float2* pub2 = pub + kEpiWarps * 32;                                  // [2][32]
+    static_assert((kEpiWarps + 2) * 32 * 2 <= kFusedTabFloats, "moment exchange tables exceed the scratch area");
     const int lpg = p.emit_cpg >> 2;                        // lanes (column quads) per group
     const int gl = col / p.emit_cpg;                        // group of this thread's columns inside the tile
+    const int cta_first = m0 + static_cast<int>(blockIdx.z) * kRowsCta;   // first row this CTA finalises
+    const int pix_sh = 31 - __clz(p.pix_per_img);                         // pixels per image: a power of two (host check)
     if (warp >= 2) {
       for (int o = 1; o < lpg; o <<= 1) {
         es += __shfl_xor_sync(0xffffffffu, es, o); eq += __shfl_xor_sync(0xffffffffu, eq, o);
       }
       if (kRowsPerIter == 2) { es += __shfl_xor_sync(0xffffffffu, es, 16); eq += __shfl_xor_sync(0xffffffffu, eq, 16); }
       if (rsub == 0 && ((lane % kLanesPerRow) % lpg) == 0) pub[ew * 32 + gl] = make_float2(es, eq);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      const int t = ew * 32 + lane;
+      if (t < 64) {                                          // (slot, group): fold the warps of that image
+        const int slot = t >> 5, g = t & 31;
+        const int img = (cta_first >> pix_sh) + slot;
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < kEpiWarps; ++w) {
+          const int mf = cta_first + w * kRowsWarp;          // all rows of a warp lie in one image
+          if (mf < p.M_total && (mf >> pix_sh) == img) { const float2 v = pub[w * 32 + g]; acc.x += v.x; acc.y += v.y; }
+        }
+        pub2[slot * 32 + g] = acc;
+      }
     }
     if (clustered) cluster_sync_all();
     else if (warp >= 2) asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
     if (dbg && threadIdx.x == 64) p.dbg[10] = clock64();
     if (warp >= 2) {
       const int csize = clustered ? NSPLIT * p.clm : 1;
-      const uint32_t pub_u32 = smem_u32(fused_tab);
-      // Which image the rows of warp w of cluster rank rk = (x, z) belong to follows from the geometry (tile blockIdx.x
-      // - cl_x + x, rows [z * kRowsCta + w * kRowsWarp, ...)): only the partials of this thread's image are loaded, two
-      // ranks (16 independent DSMEM loads) per round trip.
+      const uint32_t pub2_u32 = smem_u32(pub2);
+      // the image slot of this thread's image in cluster rank rk = (x, z) follows from the geometry: the first row that
+      // CTA finalises is (tile blockIdx.x - cl_x + x) * 128 + z * kRowsCta
       const int tile0 = static_cast<int>(blockIdx.x) - cl_x;
-      const int img_lo = bimg * p.pix_per_img, img_hi = min(img_lo + p.pix_per_img, p.M_total);   // rows of this thread's image
       const int clm_sh = 31 - __clz(p.clm);
-      float S = 0.f, Q = 0.f;           // <= 32 partials of <= 1024 values each: fp32 is ample next to the fp16 operand
-      for (int rk0 = 0; rk0 < csize; rk0 += 2) {
-        float2 pq[2][kEpiWarps];
+      float2 pq[8];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int rk = rk0 + j;
+      for (int rk = 0; rk < 8; ++rk) {
+        pq[rk] = make_float2(0.f, 0.f);
+        if (rk < csize) {
           const int x = rk & (p.clm - 1), z = rk >> clm_sh;       // clm is a power of two (host check)
-          const uint32_t base = clustered ? mapa_u32(pub_u32, rk < csize ? rk : 0) : pub_u32;
-#pragma unroll
-          for (int w = 0; w < kEpiWarps; ++w) {
-            const int mf = (tile0 + x) * kBlockM + z * kRowsCta + w * kRowsWarp;
-            pq[j][w] = make_float2(0.f, 0.f);
-            if (rk < csize && mf >= img_lo && mf < img_hi)
-              asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];"
-                           : "=f"(pq[j][w].x), "=f"(pq[j][w].y) : "r"(base + static_cast<uint32_t>(w * 32 + gl) * 8u) : "memory");
+          const int first = (tile0 + x) * kBlockM + z * kRowsCta;
+          const int slot = bimg - (first >> pix_sh);
+          if (first < p.M_total && slot >= 0 && slot < 2) {
+            const uint32_t base = clustered ? mapa_u32(pub2_u32, rk) : pub2_u32;
+            asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];"
+                         : "=f"(pq[rk].x), "=f"(pq[rk].y) : "r"(base + static_cast<uint32_t>(slot * 32 + gl) * 8u) : "memory");
           }
         }
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int w = 0; w < kEpiWarps; w += 2) { S += pq[j][w].x + pq[j][w + 1].x; Q += pq[j][w].y + pq[j][w + 1].y; }
       }
+      // (fp32 is ample next to the fp16 operand: <= 16 partials of <= 1024 values each)
+      const float S = ((pq[0].x + pq[1].x) + (pq[2].x + pq[3].x)) + ((pq[4].x + pq[5].x) + (pq[6].x + pq[7].x));
+      const float Q = ((pq[0].y + pq[1].y) + (pq[2].y + pq[3].y)) + ((pq[4].y + pq[5].y) + (pq[6].y + pq[7].y));
       const float mu = S * p.emit_inv_n;
       const float var = fmaxf(fmaf(-mu, mu, Q * p.emit_inv_n), 0.f);
       const float rstd = rsqrtf(var + p.emit_eps);
@@ -1700,6 +1713,10 @@ extern "C" int rldm_conv_tc_emittable(int B, int W, int H, int Cin, int Cout, in
   const int cpg = Cout / G, BN = (Cout % 128 == 0) ? 128 : 64;
   const int pix = (W / stride) * (H / stride);
   if (cpg % 4 != 0 || cpg > 64 || (cpg & (cpg - 1)) != 0 || BN % cpg != 0 || pix < 64 || pix > 8 * 128 || (pix & (pix - 1)) != 0) return 0;
+  // RLDM_EMIT_MAXCLM (default 1: images of at most 128 pixels, i.e. clusters along K only -- level 3 of the C3 UNet;
+  // measured 230.3 -> 232.7 images/s; 2 -> 218.7: clusters that also span M tiles are placed too late): largest number
+  // of M tiles per image (= CTAs along M of the cluster) that still emits
+  if ((pix > 128 ? pix / 128 : 1) > env().emit_maxclm) return 0;
   return rldm_conv_tc_fusable(B, W, H, Cin, Cout, ks, stride, pad_lo, sc_cin, has_residual);
 }
 

@@ -34,6 +34,8 @@ static void load_env() {
   e = getenv("RLDM_WT_PDL");
   g_env.wt_pdl = e ? atoi(e) != 0 : true;
   g_env.wt_pdl_all = e ? atoi(e) == 2 : false;
+  e = getenv("RLDM_EMIT_MAXCLM");
+  g_env.emit_maxclm = e ? atoi(e) : 1;
   e = getenv("RLDM_PDL_EXTRA");
   g_env.pdl_extra = e ? atoi(e) : 0;
   g_env.attn_mmasync = getenv("RLDM_ATTN_MMASYNC") != nullptr;

@@ -72,16 +72,15 @@ FUSE_CONV_OUT = os.environ.get("RLDM_FUSE_CONV_OUT", "1") != "0"
 # hide the load -> SiLU -> store chain), against ~5 us for the whole rldm_prep launch including its kernel boundary
 # (scripts/own_operand_probe.py).
 FUSE_PREP = os.environ.get("RLDM_FUSE_PREP", "0") == "1"
-# RLDM_EMIT_PREP=1 (experiment, default off): the small-layer convolutions EMIT the next GroupNorm's operand
-# (rldm_conv_tc_emit): where a convolution's output is consumed through GroupNorm (+ SiLU) by another convolution on the
-# same grid (norm2 -> conv2 of a ResnetBlock2D, the GroupNorm of the next block), its epilogue completes the
-# (image, group) moments inside a thread-block cluster that covers whole images, normalises its own rows and writes the
-# fp16 operand: 40 of the 66 prep launches of a C3 UNet forward disappear (128 graph nodes).  Parity-green (the model
-# tests pass with it on) but measured SLOWER on B200 (176 vs 216 images/s at first, break-even on level 3 after tuning,
-# scripts/emit_probe.py): the four epilogue warps of a CTA run the gather + normalise + SiLU + store of a 128 x 128 tile
-# at ~4 cycles per instruction (one warp per scheduler), 9.5 k cycles for the 32 rows a thread owns when K is not split,
-# and clusters of 8 CTAs that must cover an image (levels 1-2) are scheduled later than the 2-4 CTA clusters they replace.
-EMIT_PREP = os.environ.get("RLDM_EMIT_PREP", "0") == "1"
+# The small-layer convolutions EMIT the next GroupNorm's operand (rldm_conv_tc_emit): where a convolution's output is
+# consumed through GroupNorm (+ SiLU) by another convolution on the same grid (norm2 -> conv2 of a ResnetBlock2D, the
+# GroupNorm of the next block), its epilogue completes the (image, group) moments inside a thread-block cluster that
+# covers whole images, normalises its own rows and writes the fp16 operand -- no rldm_prep launch, no kernel boundary.
+# librldm only accepts layers whose images fit RLDM_EMIT_MAXCLM tiles of 128 pixels (default 1: level 3 of the C3 UNet,
+# 17 of the 66 prep launches of a forward: 230.3 -> 232.7 images/s).  With clusters that also span the M tiles of larger
+# images (RLDM_EMIT_MAXCLM=2 / 8: 28 / 40 launches fewer) the 8-CTA clusters are placed later than the 2-4-CTA clusters
+# they replace and the whole step loses (218.7 / 209 images/s, scripts/emit_probe.py).  RLDM_EMIT_PREP=0: never.
+EMIT_PREP = os.environ.get("RLDM_EMIT_PREP", "1") != "0"
 # Upsample2D of the layers the role-swapped kernel takes (the VAE decoder's): the nearest-2x upsampling is folded into
 # the convolution as four 2x2 phase convolutions over the low-resolution operand (RLDM_FOLD_UPSAMPLE=0: upsample in the
 # prep pass, then the 3x3 convolution on four times the pixels).

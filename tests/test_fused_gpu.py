@@ -302,8 +302,19 @@ EMIT_CASES = [
 ]
 
 
+@pytest.fixture
+def emit_any_cluster(monkeypatch):
+    """RLDM_EMIT_MAXCLM=8: emitting convolutions also for images of 2..8 M tiles (the default keeps them to one tile)."""
+    import rangeldm_b200 as R
+    monkeypatch.setenv("RLDM_EMIT_MAXCLM", "8")
+    R._lib.lib().rldm_reload_env()
+    yield
+    monkeypatch.delenv("RLDM_EMIT_MAXCLM")
+    R._lib.lib().rldm_reload_env()
+
+
 @pytest.mark.parametrize("case", EMIT_CASES, ids=lambda c: "x".join(map(str, c)))
-def test_conv_emit_matches_conv_then_prep(case, monkeypatch):
+def test_conv_emit_matches_conv_then_prep(case, monkeypatch, emit_any_cluster):
     """conv -> GroupNorm (+ SiLU) -> fp16 operand: produced by the convolution's own epilogue (cluster-complete moments)
     against the same convolution followed by a rldm_prep launch.  The fp32 output and its channel-pair moments are the
     same kernel's (equal up to the K-split geometry); the operand differs by the summation order of the moments only:
@@ -351,8 +362,9 @@ def test_conv_emit_matches_conv_then_prep(case, monkeypatch):
     assert torch.equal(fo[:, 0], fo[:, -2]) and torch.equal(fo[:, -1], fo[:, 1])
 
 
-def test_unet_with_emitting_convolutions_matches_oracle(monkeypatch):
-    """C3 UNet forward, batch 3, with RLDM_EMIT_PREP on: 40 prep launches fewer, same parity gate as the default path."""
+def test_unet_with_emitting_convolutions_matches_oracle(monkeypatch, emit_any_cluster):
+    """C3 UNet forward, batch 3, with emitting convolutions on EVERY level (RLDM_EMIT_MAXCLM=8; the default emits on level
+    3 only): 40 prep launches fewer, same parity gate as the default path."""
     import rangeldm_b200 as R
     from rangeldm_b200 import engine
     from oracle import nets

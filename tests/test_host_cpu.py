@@ -125,10 +125,21 @@ def test_dry_run_plans_and_fused_program_launch_counts(monkeypatch):
     assert kinds.count(_lib.OP_CONV_IN) == 1 and kinds.count(_lib.OP_NORM_CONV_OUT) == 1 and kinds[0] == _lib.OP_MEMSET
     assert kinds.count(_lib.OP_GN_STATS) == 0          # every GroupNorm reads moments fused into a producing epilogue
     assert [op.kind for op in plan.prog.exec_ops] == kinds and plan.prog.n_launch == len(kinds) + 2   # temb = 3 launches
-    # one rldm_prep launch per GroupNorm / resampler operand: 168 graph nodes
-    assert kinds.count(_lib.OP_PREP) == 66 and len(kinds) == 168
-    assert not any(op.p[11] or op.p[17] for op in plan.prog.ops if op.kind == _lib.OP_CONV_TC)
+    # 17 convolutions of level 3 (images of 64 pixels: whole images inside one K-split cluster) write the next GroupNorm's
+    # operand themselves, 7 of them (the conv1 of the ResnetBlock2Ds) without an fp32 output: 151 graph nodes
+    convs = [op for op in plan.prog.ops if op.kind == _lib.OP_CONV_TC]
+    assert kinds.count(_lib.OP_PREP) == 49 and len(kinds) == 151
+    assert sum(1 for op in convs if op.p[19]) == 17 and sum(1 for op in convs if not op.p[5]) == 7
+    assert all(op.p[19] and op.p[20] and op.p[21] and op.i[20] == 32 for op in convs if not op.p[5])
+    assert not any(op.p[11] or op.p[17] for op in convs)
     from rangeldm_b200 import engine
+    # RLDM_EMIT_PREP=0: one rldm_prep launch per GroupNorm / resampler operand, 168 graph nodes
+    monkeypatch.setattr(engine, "EMIT_PREP", False)
+    u.invalidate_plans()
+    plan0 = u.plan(8, 256, 16, 1)
+    kinds0 = [op.kind for op in plan0.prog.ops]
+    assert kinds0.count(_lib.OP_PREP) == 66 and len(kinds0) == 168
+    assert not any(op.p[19] for op in plan0.prog.ops if op.kind == _lib.OP_CONV_TC)
     # opt-in experiment RLDM_FUSE_PREP=1: the 50 convolutions of levels 1-3 that run on the small-layer kernel produce
     # their own operand; only the full-resolution level and the three 192-tile qkv projections keep a rldm_prep launch
     monkeypatch.setattr(engine, "FUSE_PREP", True)
@@ -138,8 +149,10 @@ def test_dry_run_plans_and_fused_program_launch_counts(monkeypatch):
     assert kinds1.count(_lib.OP_PREP) == 16 and len(kinds1) == 118
     assert sum(1 for op in plan1.prog.ops if op.kind == _lib.OP_CONV_TC and (op.p[11] or op.p[17])) == 50
     monkeypatch.setattr(engine, "FUSE_PREP", False)
-    # opt-in experiment RLDM_EMIT_PREP=1: 40 convolutions of levels 1-3 write the next GroupNorm's operand themselves (17
-    # of them, the conv1 of the ResnetBlock2Ds, no longer write an fp32 output at all)
+    # experiment RLDM_EMIT_MAXCLM=8: the clusters may also span the M tiles of larger images -- 40 convolutions of levels
+    # 1-3 emit (17 of them, the conv1 of the ResnetBlock2Ds, no longer write an fp32 output at all)
+    monkeypatch.setenv("RLDM_EMIT_MAXCLM", "8")
+    _lib.lib().rldm_reload_env()
     monkeypatch.setattr(engine, "EMIT_PREP", True)
     u.invalidate_plans()
     plan3 = u.plan(8, 256, 16, 1)
@@ -147,7 +160,8 @@ def test_dry_run_plans_and_fused_program_launch_counts(monkeypatch):
     convs3 = [op for op in plan3.prog.ops if op.kind == _lib.OP_CONV_TC]
     assert len(kinds3) == 128 and kinds3.count(_lib.OP_PREP) == 26
     assert sum(1 for op in convs3 if op.p[19]) == 40 and sum(1 for op in convs3 if not op.p[5]) == 17
-    assert all(op.p[19] and op.p[20] and op.p[21] and op.i[20] == 32 for op in convs3 if not op.p[5])
+    monkeypatch.delenv("RLDM_EMIT_MAXCLM")
+    _lib.lib().rldm_reload_env()
     monkeypatch.setattr(engine, "EMIT_PREP", False)
     # opt-in experiment RLDM_FUSE_LEVELS=1: 135 small ops of levels 1-3 as 5 fused persistent launches between the five
     # N = 1024 attention kernels
