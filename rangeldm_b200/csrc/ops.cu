@@ -206,6 +206,12 @@ conv_in_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x
   const int K = 9 * Cin;
   float* w_s = sh_ci;                    // [K][Cout]
   float* in_s = sh_ci + K * Cout;        // [kCinPix][K]
+  __shared__ int koff[9 * 16];           // k -> (kernel row i, kernel column j, input channel c), K <= 144
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const int tap = k / Cin, c = k - tap * Cin;
+    const int i = tap / 3, j = tap - i * 3;
+    koff[k] = (i << 16) | (j << 8) | c;
+  }
   pdl_trigger();
   for (int i = threadIdx.x * 4; i < K * Cout; i += blockDim.x * 4)    // weights do not depend on prior kernels
     *reinterpret_cast<float4*>(w_s + i) = __ldg(reinterpret_cast<const float4*>(wgt + i));
@@ -247,17 +253,19 @@ conv_in_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x
       }
     }
     __syncthreads();                     // previous chunk's in_s fully consumed
-    // this thread's pixel is fixed (blockDim.x is a multiple of kCinPix): its coordinates are resolved once per chunk,
-    // then the K loop runs in batches of independent loads (the staging is bound by load latency otherwise)
+    // this thread's pixel is fixed (blockDim.x is a multiple of kCinPix): its coordinates are resolved once per chunk
+    // (32-bit arithmetic; the (tap, channel) decomposition of k comes from a table built once per block -- the integer
+    // divisions of the first version were a third of the kernel's instructions), then the K loop runs in batches of
+    // independent loads (the staging is bound by load latency otherwise)
     {
       const int p = threadIdx.x % kCinPix;
-      const size_t pp = p_begin + p;
-      const bool live = pp < total_pix;
-      const int h = live ? static_cast<int>(pp % H) : 0;
-      const int w = live ? static_cast<int>((pp / H) % W) : 0;
-      const size_t b = live ? pp / pix_per_img : 0;
-      const float* xb0 = x0 + b * c0 * W * H;
-      const float* xb1 = x1 ? x1 + b * c1 * W * H : nullptr;
+      const int pp = static_cast<int>(p_begin) + p;
+      const bool live = pp < static_cast<int>(total_pix);
+      const int b = live ? pp / static_cast<int>(pix_per_img) : 0;
+      const int pin = live ? pp - b * static_cast<int>(pix_per_img) : 0;
+      const int w = pin / H, h = pin - w * H;
+      const float* xb0 = x0 + static_cast<size_t>(b) * c0 * W * H;
+      const float* xb1 = x1 ? x1 + static_cast<size_t>(b) * c1 * W * H : nullptr;
       constexpr int kBatch = 6;
       const int k_step = blockDim.x / kCinPix;
       for (int k0 = threadIdx.x / kCinPix; k0 < K; k0 += k_step * kBatch) {
@@ -267,10 +275,10 @@ conv_in_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x
           const int k = k0 + u * k_step;
           a[u] = 0.f;
           if (live && k < K) {
-            const int tap = k / Cin, c = k - tap * Cin;
-            const int i = tap / 3, j = tap - i * 3;
-            int wi = w + i - 1;
-            const int hj = h + j - 1;
+            const int e = koff[k];                             // (i, j, c) = (e >> 16, (e >> 8) & 255, e & 255)
+            const int c = e & 255;
+            int wi = w + (e >> 16) - 1;
+            const int hj = h + ((e >> 8) & 255) - 1;
             bool ok = hj >= 0 && hj < H;
             if (circular) {
               if (wi < 0) wi += W;
@@ -279,8 +287,7 @@ conv_in_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x
               ok = ok && wi >= 0 && wi < W;
             }
             if (ok)
-              a[u] = (c < c0) ? __ldg(xb0 + (static_cast<size_t>(c) * W + wi) * H + hj)
-                              : __ldg(xb1 + (static_cast<size_t>(c - c0) * W + wi) * H + hj);
+              a[u] = (c < c0) ? __ldg(xb0 + (c * W + wi) * H + hj) : __ldg(xb1 + ((c - c0) * W + wi) * H + hj);
           }
         }
 #pragma unroll
@@ -912,6 +919,8 @@ static int conv_in_impl(const float* x0, int c0, const float* x1, int c1, const 
   RLDM_CHECK(Cout % 4 == 0 && Cout <= 1024 && 256 % (Cout / 4) == 0, "conv_in: unsupported Cout=%d", Cout);
   RLDM_CHECK(!stats || (W * H) % kCinPix == 0, "conv_in: fused moments need W*H %% %d == 0 (got %d)", kCinPix, W * H);
   const size_t total_pix = static_cast<size_t>(B) * W * H;
+  RLDM_CHECK(c0 + c1 >= 1 && c0 + c1 <= 16, "conv_in: 1..16 input channels (got %d + %d)", c0, c1);
+  RLDM_CHECK(total_pix < (1ull << 31) && static_cast<size_t>(c0 + c1) * W * H < (1ull << 31), "conv_in: tensor too large for 32-bit pixel indices");
   const int K = 9 * (c0 + c1);
   const size_t smem = (static_cast<size_t>(K) * Cout + static_cast<size_t>(kCinPix) * K) * sizeof(float);
   RLDM_CHECK(smem <= 200 * 1024, "conv_in: 9*Cin*Cout too large for shared memory (Cin=%d Cout=%d)", c0 + c1, Cout);
