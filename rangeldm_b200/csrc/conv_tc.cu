@@ -944,7 +944,7 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int x_stage = HALO ? XP * p.a_part_bytes : 0;           // HALO: one pixel-window stage, [hi][lo]
-  const int NW = HALO ? p.nb_stages : 0;
+  const int NW = HALO ? p.nb_stages : 1;                          // (1: the HALO branches are dead code otherwise)
   uint8_t* w_ring = smem + 2 * x_stage;                          // HALO: NW entries of kWPart
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(HALO ? w_ring + NW * kWPart : smem + STAGES * kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
