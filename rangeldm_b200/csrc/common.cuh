@@ -50,6 +50,7 @@ struct EnvSwitches {
   bool conv_mt1;            // RLDM_CONV_MT1:     pixel-M persistent kernel with one tile per unit
   bool conv_mt2_res;        // RLDM_CONV_MT2_RES: two tiles per unit also for 128-wide layers with a residual
   bool wt_pdl;              // RLDM_WT_PDL != 0:  PDL on single-wave role-swapped launches (default on)
+  int emit_maxcl;           // RLDM_EMIT_MAXCL: largest cluster (CTAs) of an emitting launch that spans several M tiles
   int emit_maxclm;          // RLDM_EMIT_MAXCLM: emitting convolutions only for images of at most this many 128-pixel tiles
   int pdl_extra;            // RLDM_PDL_EXTRA: bit mask of launch classes that also carry the PDL attribute in mode 2
   bool wt_pdl_all;          // RLDM_WT_PDL = 2: ... on every role-swapped / persistent convolution launch (experiment)

@@ -1578,7 +1578,9 @@ static int conv_tc_impl(const uint16_t* x, const uint16_t* x_lo, const uint16_t*
   }
   RLDM_CHECK(split == 1 || split == 2 || split == 4 || split == 8, "conv_tc: split_k must be 1, 2, 4 or 8 (got %d)", split);
   while (split > p.total_iters) split /= 2;
-  while (p.clm * split > 8) split /= 2;          // emitting launch: (M tiles of the image) x (K slices) <= 8 CTAs per cluster
+  // emitting launch: (M tiles of the image) x (K slices) <= 8 CTAs per cluster (RLDM_EMIT_MAXCL: a smaller limit for
+  // clusters that span M tiles -- sixteen 8-CTA clusters do not all fit the GPCs at once)
+  while (p.clm * split > (p.clm > 1 ? sw.emit_maxcl : 8) && split > 1) split /= 2;
   // more tiles than SMs and no K split: persistent CTAs with a double-buffered TMEM accumulator
   if (split == 1 && tiles > n_sms && sw.conv_persistent) {
     if (query_only) return 1;

@@ -34,6 +34,8 @@ static void load_env() {
   e = getenv("RLDM_WT_PDL");
   g_env.wt_pdl = e ? atoi(e) != 0 : true;
   g_env.wt_pdl_all = e ? atoi(e) == 2 : false;
+  e = getenv("RLDM_EMIT_MAXCL");
+  g_env.emit_maxcl = e ? atoi(e) : 8;
   e = getenv("RLDM_EMIT_MAXCLM");
   g_env.emit_maxclm = e ? atoi(e) : 1;
   e = getenv("RLDM_PDL_EXTRA");
