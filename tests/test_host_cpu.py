@@ -410,3 +410,37 @@ def test_pipeline_set_steps_reuses_tables_only_for_identical_arguments():
     c0 = d._coef_host
     p._set_steps(10, eta=0.5)
     assert d._coef_host is not c0 and float(d._coef_host[:, 6].abs().max()) > 0
+
+
+def test_folded_upsample_phase_weights_reproduce_the_upsampled_convolution(monkeypatch):
+    """`Builder.pack_conv_up2` (host side of rldm_conv_tc_up2): the four 2x2 phase convolutions over the low-resolution
+    input, with the pads librldm gives them (W: 1 - a, H: 1 - b; circular along W, zeros along H), reproduce
+    conv3x3(nearest-2x(x)) -- checked here with PyTorch on the CPU, in fp64 on the packed fp16 hi + lo planes."""
+    monkeypatch.setenv("RLDM_DRYRUN", "1")
+    import torch.nn.functional as F
+    from rangeldm_b200 import engine, models
+    from oracle.nets import circ_conv2d
+    g = torch.Generator().manual_seed(5)
+    Cin, Cout, W, H = 8, 16, 6, 4
+    conv = models.LoRACompatibleConv(Cin, Cout, 3, padding=1)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g))
+        conv.bias.copy_(torch.randn(Cout, generator=g))
+    pg = engine.Program(torch.device("cpu"))
+    bd = engine.Builder(pg, 1, cache={})
+    wt, bias = bd.pack_conv_up2(conv, 3)                     # [4 phases][2 planes * 4 taps][Cout][Cin] fp16
+    assert wt.shape == (4, 8, Cout, Cin) and wt.dtype == torch.float16
+    x = torch.randn(2, Cin, W, H, generator=g, dtype=torch.float64)
+    with torch.no_grad():
+        ref = circ_conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), conv.weight.double(), conv.bias.double(), 1, 1)
+    out = torch.zeros_like(ref)
+    for a in range(2):
+        for b in range(2):
+            w4 = (wt[2 * a + b, :4].double() + wt[2 * a + b, 4:].double())          # hi + lo planes, taps 2*ti + tj
+            k = w4.reshape(2, 2, Cout, Cin).permute(2, 3, 0, 1)                     # (Cout, Cin, ti, tj)
+            pw, ph = 1 - a, 1 - b                                                   # low-side pads of this phase
+            xp = torch.cat([x[:, :, -1:], x, x[:, :, :1]], dim=2)                   # circular halo along W
+            xp = xp[:, :, 1 - pw: 1 - pw + W + 1]                                   # columns w - pw .. w - pw + 1
+            xp = F.pad(xp, (ph, 1 - ph))                                            # zeros along H
+            out[:, :, a::2, b::2] = F.conv2d(xp, k) + conv.bias.detach().double()[None, :, None, None]
+    assert float((out - ref).abs().max() / ref.abs().max()) < 2e-6             # fp16 hi + lo weights: ~22 bits
