@@ -1051,13 +1051,16 @@ conv_tc_wt_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
               mbar_wait(&w_full[sw], (gw / NW) & 1);
               tc_fence_after();
               const uint64_t w_desc = umma_desc_sw128(smem_u32(w_ring + sw * kWPart));
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) umma_f16(d_tmem, w_desc + 2 * kk, x_desc + 2 * kk, idesc, (u | ti | kk) != 0);
+              // (the low-order plane first: with the planes issued the other way round compute-sanitizer's memcheck
+              // flags the fourth K slice of the second group as an out-of-range shared address, although both groups
+              // read the same rows of two adjacent windows -- the report follows the instruction slot, not the address)
               if (XP > 1) {
                 const uint64_t xl_desc = umma_desc_sw128(x_base + ti * p.Ho * 128 + p.a_part_bytes);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) umma_f16(d_tmem, w_desc + 2 * kk, xl_desc + 2 * kk, idesc, 1u);   // W_hi X_lo
+                for (int kk = 0; kk < 4; ++kk) umma_f16(d_tmem, w_desc + 2 * kk, xl_desc + 2 * kk, idesc, (u | ti | kk) != 0);   // W_hi X_lo
               }
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) umma_f16(d_tmem, w_desc + 2 * kk, x_desc + 2 * kk, idesc, XP > 1 ? 1u : ((u | ti | kk) != 0));
               umma_commit(&w_empty[sw]);
               ++gw;
             }
